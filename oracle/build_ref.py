@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE -- build the *real* reference for a mechanism into oracle/_ref/.
+
+Recipe:
+  1. run the unmodified reference generator where it lies,
+         PYTHONPATH=/root/reference python -m pyjac --lang c --input MECH -b oracle/_ref/<name>/src
+     (pyjac/__main__.py:7-26 -> create_jacobian, create_jacobian.py:3407)
+  2. compile the emitted C with the reference's own flags
+         gcc -std=c99 -O3 -mtune=native            (pyjac/libgen/libgen.py:43)
+     plus -fPIC -fopenmp, together with oracle/ref_batch.c (an OpenMP loop over states,
+     as pyjac/performance_tester/tester.c.in:23-31), into
+         oracle/_ref/<name>/libc_pyjac.so
+Nothing is copied out of /root/reference; generated sources and binaries stay under
+oracle/_ref/ (git-ignored, but they travel to the GPU box with the repo snapshot).
+
+Usage:  python oracle/build_ref.py NAME MECH.inp [--last-spec SP] [--opt -O3] [--jobs 8]
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = '/root/reference'
+OUT_ROOT = os.path.join(HERE, '_ref')
+
+
+def ref_dir(name: str) -> str:
+    return os.path.join(OUT_ROOT, name)
+
+
+def lib_path(name: str) -> str:
+    return os.path.join(ref_dir(name), 'libc_pyjac.so')
+
+
+def have_reference() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, 'pyjac'))
+
+
+def build(name: str, mech: str, last_spec=None, opt: str = '-O3', jobs: int = 8,
+          force: bool = False, quiet: bool = True) -> str:
+    out = ref_dir(name)
+    src = os.path.join(out, 'src')
+    lib = lib_path(name)
+    stamp = os.path.join(out, 'mech.inp')
+    mech_txt = open(mech).read()
+    if (not force and os.path.exists(lib) and os.path.exists(stamp)
+            and open(stamp).read() == mech_txt):
+        return lib
+    if not have_reference():
+        raise RuntimeError('reference sources not present at %s' % REF_ROOT)
+    os.makedirs(src, exist_ok=True)
+    for f in glob.glob(os.path.join(src, '**', '*.[cho]'), recursive=True):
+        os.remove(f)
+
+    env = dict(os.environ, PYTHONPATH=REF_ROOT)
+    cmd = [sys.executable, '-W', 'ignore', '-m', 'pyjac', '--lang', 'c',
+           '--input', os.path.abspath(mech), '-b', src]
+    if last_spec:
+        cmd += ['-ls', last_spec]
+    res = subprocess.run(cmd, env=env, cwd=out, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('reference codegen failed:\n' + res.stdout + res.stderr)
+
+    cfiles = [f for f in glob.glob(os.path.join(src, '**', '*.c'), recursive=True)]
+    cfiles.append(os.path.join(HERE, 'ref_batch.c'))
+    inc = ['-I', src, '-I', os.path.join(src, 'jacobs'), '-I', os.path.join(src, 'rates')]
+    flags = ['-std=c99', opt, '-mtune=native', '-fPIC', '-fopenmp', '-D_DEFAULT_SOURCE']
+
+    def cc(f):
+        o = os.path.join(out, 'obj_' + os.path.relpath(f, '/').replace('/', '_')[:-2] + '.o')
+        r = subprocess.run(['gcc'] + flags + inc + ['-c', f, '-o', o],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('gcc failed on %s:\n%s' % (f, r.stderr))
+        return o
+
+    with ThreadPoolExecutor(jobs) as ex:
+        objs = list(ex.map(cc, cfiles))
+    r = subprocess.run(['gcc', '-shared', '-fopenmp', '-o', lib] + objs + ['-lm'],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n' + r.stderr)
+    for o in objs:
+        os.remove(o)
+    with open(stamp, 'w') as fh:
+        fh.write(mech_txt)
+    if not quiet:
+        print('built', lib)
+    return lib
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('name')
+    ap.add_argument('mech')
+    ap.add_argument('--last-spec', default=None)
+    ap.add_argument('--opt', default='-O3')
+    ap.add_argument('--jobs', type=int, default=os.cpu_count() or 4)
+    ap.add_argument('--force', action='store_true')
+    a = ap.parse_args()
+    print(build(a.name, a.mech, a.last_spec, a.opt, a.jobs, a.force, quiet=False))

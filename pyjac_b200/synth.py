@@ -179,9 +179,11 @@ def generate(shape_name: str = 'gri30', seed: int = 0) -> str:
 
     # ---- thermo
     thermo_txt = 'THERMO ALL\n   300.000  1000.000  5000.000\n'
+    h_form: Dict[str, float] = {}
     for n, c in pool:
         tmid = float(rng.choice(shape.tmid_choices))
         lo, hi = _thermo(c, rng, tmid)
+        h_form[n] = lo[5]
         thermo_txt += _fmt_thermo(n, c, lo, hi, tmid)
     thermo_txt += 'END\n'
 
@@ -205,24 +207,35 @@ def generate(shape_name: str = 'gri30', seed: int = 0) -> str:
         a, b, c = recomb[rng.integers(len(recomb))]
         return [a, b], [c]
 
-    def arrh(order, kind='elem'):
+    def endo(r, p):
+        # endothermicity [cal/mol] of r -> p; an activation energy below it is unphysical
+        # and makes kf/Kc astronomically large
+        dh = sum(h_form[x] for x in p) - sum(h_form[x] for x in r)
+        return max(dh, 0.0) * 1.987
+
+    def arrh(order, kind='elem', e_min=0.0):
+        # log10(A) is tied to b so that k(1000 K) stays below collision-limit magnitudes
         if kind == 'third':
-            A = 10 ** rng.uniform(15.0, 18.5)
             b = round(rng.uniform(-2.0, 0.0), 2)
+            A = 10 ** (rng.uniform(13.5, 15.5) - 3.0 * b)
             E = 0.0 if rng.random() < 0.7 else round(rng.uniform(0, 20000), 1)
         elif kind == 'low':
             b = round(rng.uniform(-7.5, -1.0), 2)
-            A = 10 ** rng.uniform(20.0 - 4.0 * b / 3.0 - 4, 22.0 - 4.0 * b / 3.0)
+            A = 10 ** (rng.uniform(15.0, 19.0) - 3.0 * b)
             E = round(rng.uniform(-1000, 8000), 1)
+            if e_min > 0:
+                E = round(E + e_min, 1)
         elif kind == 'inf':
-            A = 10 ** rng.uniform(11.0, 14.5)
             b = round(rng.uniform(-1.0, 1.5), 3)
+            A = 10 ** (rng.uniform(11.0, 14.0) - 3.0 * b)
             E = 0.0 if rng.random() < 0.4 else round(rng.uniform(0, 12000), 1)
         else:
-            A = 10 ** (rng.uniform(9.0, 14.0) + 3.0 * (order - 2))
             u = rng.random()
             b = 0.0 if u < 0.35 else round(rng.uniform(-1.5, 2.8), 3)
+            A = 10 ** (rng.uniform(10.5, 14.0) - 3.0 * b + 3.0 * (order - 2))
             E = 0.0 if rng.random() < 0.3 else round(rng.uniform(-2000, 45000), 1)
+        if kind != 'low' and E < e_min:
+            E = round(e_min * (1.0 + 0.1 * rng.random()), 1)
         return '%.3E %8.3f %10.2f' % (A, b, E)
 
     def eff_line():
@@ -266,14 +279,14 @@ def generate(shape_name: str = 'gri30', seed: int = 0) -> str:
         if n_irrev_left > 0 and rng.random() < 1.5 * shape.n_irrev / shape.nr:
             rev = False
             n_irrev_left -= 1
-        emit(r, p, rev, arrh(len(r)))
+        emit(r, p, rev, arrh(len(r), 'elem', endo(r, p)))
         count += 1
 
     # duplicate pairs
     for _ in range(shape.n_dup_pairs):
         r, p = pick_exchange()
         for _k in range(2):
-            emit(r, p, True, arrh(2), (' DUPLICATE',))
+            emit(r, p, True, arrh(2, 'elem', endo(r, p)), (' DUPLICATE',))
 
     # third-body
     for k in range(shape.n_third):
@@ -282,7 +295,7 @@ def generate(shape_name: str = 'gri30', seed: int = 0) -> str:
             r, p = p, r
         aux = (eff_line(),) if k != 1 else ()      # one +M reaction without listed efficiencies
         lines.append('%-48s %s' % (_side(_merge(r)) + '+M<=>' + _side(_merge(p)) + '+M',
-                                   arrh(len(r), 'third')))
+                                   arrh(len(r), 'third', endo(r, p))))
         lines.extend(aux)
 
     # fall-off (Troe with/without T2, Lindemann)
@@ -290,7 +303,7 @@ def generate(shape_name: str = 'gri30', seed: int = 0) -> str:
         r, p = pick_recomb()
         if rng.random() < 0.15:
             r, p = p, r
-        aux = ['     LOW  / %s /' % arrh(len(r), 'low')]
+        aux = ['     LOW  / %s /' % arrh(len(r), 'low', endo(r, p))]
         if k < shape.n_troe:
             a = round(rng.uniform(0.2, 0.95), 4)
             T3 = round(10 ** rng.uniform(1.7, 3.5), 2)
@@ -303,7 +316,7 @@ def generate(shape_name: str = 'gri30', seed: int = 0) -> str:
         if k % 7 != 3:
             aux.append(eff_line())
         lines.append('%-48s %s' % (_side(_merge(r)) + '(+M)<=>' + _side(_merge(p)) + '(+M)',
-                                   arrh(len(r), 'inf')))
+                                   arrh(len(r), 'inf', endo(r, p))))
         lines.extend(aux)
 
     # interleave deterministically so reaction types are spread through the list

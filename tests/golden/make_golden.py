@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors from the REAL reference (run in the build
+container only -- needs /root/reference).
+
+For each mechanism it runs the reference's own generator + gcc (oracle/build_ref.py),
+evaluates the emitted C on fixed states and stores inputs and outputs:
+
+    tests/golden/h2o2_pasr.npz     H2/O2 10-species mechanism, all 1020 bundled PaSR states
+                                   (data/h2_pasr_output.npy, renormalised as
+                                   functional_tester/test.py:1254-1258)
+    tests/golden/torture_pasr.npz  branch-coverage mechanism, every 4th of those states
+    tests/golden/gri30_syn.npz     GRI-3.0-shaped synthetic mechanism, 48 synthetic states
+
+Arrays are in pyJac's internal (moved-last) species order, row-major per state:
+P[n], y[n,NSP] = [T, Y_0..Y_{NSP-2}], conc, fwd, rev, pres_mod, spec_rates, dydt, jac[n,NSP*NSP]
+(column-major inside a state).
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import build_ref                                   # noqa: E402
+from oracle.oracle import RefLib                               # noqa: E402
+from pyjac_b200 import synth                                   # noqa: E402
+from pyjac_b200.mechanism import Mechanism                     # noqa: E402
+from pyjac_b200.states import pasr_states, synthetic_states    # noqa: E402
+
+
+def dump(name, mech_file, P, y, out_name):
+    build_ref.build(name, mech_file)
+    ref = RefLib(name)
+    conc, fwd, rev, pm, sr = ref.rates(P, y)
+    out = dict(P=P, y=y, conc=conc, fwd=fwd, rev=rev, pres_mod=pm, spec_rates=sr,
+               dydt=ref.dydt(P, y, 1), jac=ref.eval_jacob(P, y, 1))
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(name, y.shape, 'jac nnz frac %.3f' % (out['jac'] != 0).mean())
+
+
+if __name__ == '__main__':
+    pasr = os.path.join(HERE, 'h2_pasr_output.npy')
+    if not os.path.exists(pasr):
+        shutil.copy('/root/reference/data/h2_pasr_output.npy', pasr)
+
+    mech = Mechanism.from_chemkin(os.path.join(HERE, 'h2o2_n2.inp'))
+    P, y = pasr_states(pasr, mech)
+    dump('h2o2', os.path.join(HERE, 'h2o2_n2.inp'), P, y, 'h2o2_pasr.npz')
+
+    mech = Mechanism.from_chemkin(os.path.join(HERE, 'torture.inp'))
+    P, y = pasr_states(pasr, mech)
+    dump('torture', os.path.join(HERE, 'torture.inp'), P[::4], y[::4], 'torture_pasr.npz')
+
+    gri = os.path.join(HERE, 'gri30_syn.inp')
+    synth.write('gri30', gri, seed=0)
+    mech = Mechanism.from_chemkin(gri)
+    P, y = synthetic_states(mech.NSP, 48, seed=0)
+    dump('gri30', gri, P, y, 'gri30_syn.npz')

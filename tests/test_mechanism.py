@@ -1,0 +1,73 @@
+"""Host-side mechanism front-end: parser, last-species permutation, synthetic generator."""
+import os
+
+import numpy as np
+import pytest
+
+from pyjac_b200 import synth
+from pyjac_b200.mechanism import Mechanism, species_mappings
+
+
+def test_h2o2_sizes(golden_dir):
+    m = Mechanism.from_chemkin(os.path.join(golden_dir, 'h2o2_n2.inp'))
+    # NSP 10, FWD 28, REV 28, PRES_MOD 6, last species N2 (original index 9)
+    assert (m.NSP, m.FWD_RATES, m.REV_RATES, m.PRES_MOD_RATES) == (10, 28, 28, 6)
+    assert m.specs[-1].name == 'N2' and m.last_spec_original == 9
+    hdr = m.mechanism_header()
+    assert '#define NSP 10' in hdr and '//last_spec 9' in hdr and '#define NN 11' in hdr
+
+
+def test_units_and_aux(golden_dir):
+    m = Mechanism.from_chemkin(os.path.join(golden_dir, 'h2o2_n2.inp'))
+    r0 = m.reacs[0]          # 2O+M<=>O2+M  1.2e17 -1 0 ; third body: A / 1000^order
+    assert r0.thd_body and not r0.pdep and r0.A == 1.2e17 / 1000. ** 2
+    r2 = m.reacs[2]          # O+H2<=>H+OH 3.87e4 2.7 6260 cal/mol -> K
+    assert r2.E == 6260.0 * (4.184 / 8.3144621) and r2.A == 3.87e4 / 1000. ** 1.
+    r20 = m.reacs[20]        # 2OH(+M)<=>H2O2(+M) Troe
+    assert r20.pdep and r20.troe and r20.pdep_sp is None and len(r20.troe_par) == 4
+    assert r20.low[0] == 2.3e18 / 1000. ** 2
+
+
+def test_last_species_moves(golden_dir):
+    m = Mechanism.from_chemkin(os.path.join(golden_dir, 'h2o2_n2.inp'), last_spec='AR')
+    assert m.specs[-1].name == 'AR' and m.specs[-2].name == 'N2'
+    fwd, back = species_mappings(5, 2)
+    assert fwd == [0, 1, 3, 4, 2] and back == [0, 1, 4, 2, 3]
+
+
+def test_explicit_rev_is_split(golden_dir):
+    m = Mechanism.from_chemkin(os.path.join(golden_dir, 'torture.inp'))
+    names = [sp.name for sp in m.specs]
+    pairs = [(i, rx) for i, rx in enumerate(m.reacs)
+             if not rx.rev and sorted(names[k] for k in rx.reac) == ['H2O', 'O']]
+    assert len(pairs) == 1                      # the generated backward half of H+HO2<=>O+H2O
+    assert pairs[0][1].b == 0.1
+    # REV / 0 0 0 / makes the reaction irreversible without adding a partner
+    h2o2 = [rx for rx in m.reacs if sorted(names[k] for k in rx.reac) == ['H2', 'O2']]
+    assert len(h2o2) == 1 and not h2o2[0].rev
+
+
+def test_synth_reproduces_committed_gri30(golden_dir):
+    txt = synth.generate('gri30', seed=0)
+    assert txt == open(os.path.join(golden_dir, 'gri30_syn.inp')).read()
+
+
+@pytest.mark.parametrize('shape', ['mini', 'gri30', 'usc2'])
+def test_synth_shapes(tmp_path, shape):
+    p = synth.write(shape, str(tmp_path / (shape + '.inp')))
+    m = Mechanism.from_chemkin(p)
+    s = synth.SHAPES[shape]
+    assert (m.NSP, m.FWD_RATES) == (s.nsp, s.nr)
+    assert m.PRES_MOD_RATES == s.n_third + s.n_troe + s.n_lind
+    assert m.specs[-1].name == 'N2'
+
+
+def test_plog_rejected(tmp_path, golden_dir):
+    src = open(os.path.join(golden_dir, 'h2o2_n2.inp')).read()
+    src = src.replace('O+H2<=>H+OH                              3.870E+04    2.700    6260.00\n',
+                      'O+H2<=>H+OH                              3.870E+04    2.700    6260.00\n'
+                      ' PLOG / 1.0 3.87E+04 2.7 6260.0 /\n')
+    p = tmp_path / 'plog.inp'
+    p.write_text(src)
+    with pytest.raises(NotImplementedError):
+        Mechanism.from_chemkin(str(p))

@@ -1,0 +1,61 @@
+"""Pin the CPU restatement oracle (oracle/pyjac_oracle.c) to the REAL reference.
+
+The golden .npz files under tests/golden/ hold outputs of the reference's own generated C
+(made by tests/golden/make_golden.py in the build container).  The restatement follows the
+emitted code's evaluation order, so agreement is expected to be bit-exact; the assertion
+allows a few ulp so that a different libm build cannot turn it red.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle, RefLib
+from pyjac_b200.mechanism import Mechanism
+
+CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz', 'h2o2'),
+         ('torture.inp', 'torture_pasr.npz', 'torture'),
+         ('gri30_syn.inp', 'gri30_syn.npz', 'gri30')]
+KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
+
+
+def _close(a, b, what):
+    assert a.shape == b.shape, what
+    assert np.isfinite(a).all(), what
+    scale = np.abs(b).max(axis=-1, keepdims=True) + 1e-300
+    err = (np.abs(a - b) / scale).max()
+    assert err <= 4e-15, '%s: |d|/rowmax = %.3e' % (what, err)
+    return float((a == b).mean())
+
+
+@pytest.mark.parametrize('mech_file,npz,name', CASES)
+def test_oracle_matches_reference_golden(golden_dir, mech_file, npz, name):
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
+    g = np.load(os.path.join(golden_dir, npz))
+    ora = Oracle(mech)
+    assert (ora.NSP, ora.NR, ora.NREV, ora.NPD) == (
+        g['y'].shape[1], g['fwd'].shape[1], g['rev'].shape[1], g['pres_mod'].shape[1])
+    P, y = g['P'], g['y']
+    exact = {}
+    for key, arr in zip(KEYS, ora.rates(P, y)):
+        exact[key] = _close(arr, g[key], name + ':' + key)
+    exact['dydt'] = _close(ora.dydt(P, y), g['dydt'], name + ':dydt')
+    jac = ora.eval_jacob(P, y)
+    assert (g['jac'] != 0).mean() > 0.5
+    exact['jac'] = _close(jac, g['jac'], name + ':jac')
+    # every output was bit-identical when the goldens were made
+    assert min(exact.values()) > 0.999, exact
+
+
+@pytest.mark.parametrize('mech_file,npz,name', CASES)
+def test_oracle_matches_live_reference_build(golden_dir, mech_file, npz, name):
+    """When oracle/_ref/<name> was built here (reference present), run it live."""
+    if not RefLib.available(name):
+        pytest.skip('oracle/_ref/%s not built' % name)
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
+    g = np.load(os.path.join(golden_dir, npz))
+    P, y = g['P'][:64], g['y'][:64]
+    ref = RefLib(name)
+    ora = Oracle(mech)
+    assert np.array_equal(ref.eval_jacob(P, y, 1), ora.eval_jacob(P, y, 1))
+    assert np.array_equal(ref.dydt(P, y, 1), ora.dydt(P, y, 1))
