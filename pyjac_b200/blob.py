@@ -3,7 +3,7 @@
 Layout (little endian):
     char   magic[8]  = "PJB200T1"
     int64  n_entries
-    entry[n_entries]: char name[24]; int32 dtype (0 = float64, 1 = int32); int32 pad;
+    entry[n_entries]: char name[24]; int32 dtype (0 = float64, 1 = int32, 2 = uint16); int32 pad;
                       int64 count; int64 offset   (offset from blob start, 16-byte aligned)
     payload
 Read on the C side by ``pjt_find`` (pyjac_b200/csrc/pjtable.h) and by the oracle.
@@ -31,6 +31,8 @@ def pack(tables: Dict[str, np.ndarray]) -> bytes:
             code = 0
         elif a.dtype == np.int32:
             code = 1
+        elif a.dtype == np.uint16:
+            code = 2
         else:
             raise TypeError('table %s has unsupported dtype %s' % (nm, a.dtype))
         if len(nm) > 23:
@@ -52,6 +54,6 @@ def unpack(blob: bytes) -> Dict[str, np.ndarray]:
     out = {}
     for k in range(n):
         nm, code, _, count, off = _ENTRY.unpack_from(blob, 16 + k * _ENTRY.size)
-        dt = np.float64 if code == 0 else np.int32
+        dt = (np.float64, np.int32, np.uint16)[code]
         out[nm.rstrip(b'\0').decode()] = np.frombuffer(blob, dt, count, off).copy()
     return out

@@ -1,0 +1,358 @@
+"""Mechanism -> device tables for the data-driven sm_100a kernels.
+
+This replaces the reference's *source generators* (pyjac/core/rate_subs.py and
+pyjac/core/create_jacobian.py): instead of unrolling the mechanism into C/CUDA text, the
+same information is exported once as flat arrays (packed with :mod:`pyjac_b200.blob`) that
+one fixed kernel family (pyjac_b200/csrc/pyjac_b200.cu) interprets.
+
+The kernel does not follow the generated code's statement order; it uses the algebraic
+structure of the emitted Jacobian (SURVEY.md section 7 / 8a'):
+
+    jac[k+1, j+1] = W_k/W_j * ( A_k + B_k * W_j/W_N + S_kj )
+    A_k = sum_i nu_ki X1_i + wdot_k mw_avg/rho         B_k = sum_i nu_ki X2_i - wdot_k mw_avg/rho
+    S_kj = sum over reactions i, sum over "raw" per-reaction derivative values r:
+           coef * raw[r]      (only for j among reactants/products/listed colliders of i)
+
+so every Jacobian element is produced once, from a dense rank-2 part and a sparse gather.
+Where the generator prints a constant with a lossy format string and the difference can
+exceed ~1e-16 relative, the same quantisation is applied here (citations: rs =
+pyjac/core/rate_subs.py, cj = pyjac/core/create_jacobian.py).
+
+Table reference (all reaction-indexed arrays are in *kernel order*, see ``rx_orig``):
+
+  dims      int32[16]  NSP NR NREV NPD NRAW NNZ NCON NCOEF FIRST_PM NPM NRED MAXRED
+  cst       f64[4]     RU ({:.8e}), ln(PA/RU)
+  sp_*      per species (internal, moved-last order): w, iw (=1/W {:.16e}), ruw (=RU/W),
+            tmid, mwf (=W_j/W_N), seen;  sp_nasa[k][branch][16] polynomial coefficients
+  rx_*      orig (original reaction index), flags, rev_idx, pm_idx (positions in the
+            reference's rev_rates / pres_mod arrays), raw_base, slots[6] (3 reactant + 3
+            product species, NSP = empty slot), arr[4] = lnA, b, Ta, sum(nu)*ln(PA/RU)
+  pm_*      per pressure-modified reaction (kernel index - FIRST_PM): collider list
+            (eff_off/eff_sp/eff_am1 = alpha-1), sp (specific collider or -1), par[32]
+  red_*     per species CSR of (reaction, nu) for the species-side reductions
+  ent_*     sparse Jacobian entries (k, j) sorted by work, CSR into con (packed
+            src | coef_index<<16), coef f64[NCOEF]
+  jmap      uint16[(NSP-1)*NSP]: (j, k) -> entry slot (NNZ = always-zero slot)
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List
+
+import numpy as np
+
+from .chem import PA, RU
+from .mechanism import Mechanism
+
+# flag bits shared with csrc/pyjac_b200.cu
+F_REV, F_THD, F_PDEP, F_LOW, F_TROE, F_SRI = 1, 2, 4, 8, 16, 32
+F_PMT, F_PMT_INJ, F_TROE_T2, F_SRI5, F_SRI5_DT, F_NO_T = 64, 128, 256, 512, 1024, 2048
+F_EFFN1 = 4096         # third-body (non fall-off) reaction with a collider list: n' += 1
+F_WANT_PMT = 1 << 16   # the kernel stores pres_mod_temp as a raw value
+NRE_SHIFT, NPR_SHIFT = 20, 24    # occupied reactant / product slots
+
+MAXS = 3               # concentration slots per side of a reaction
+UNROLL = 40            # CParams.Jacob_Unroll (cj:2651): scope of the stale pres_mod_temp quirk
+NPAR = 32
+
+
+class UnsupportedMechanism(NotImplementedError):
+    pass
+
+
+def q(fmt: str, x: float) -> float:
+    """x after a round trip through one of the generator's format strings."""
+    return float(fmt.format(x))
+
+
+def _slots(sp: List[int], nu: list, empty: int, what: str) -> List[int]:
+    out: List[int] = []
+    for s, n in zip(sp, nu):
+        if not float(n).is_integer() or n < 0:
+            raise UnsupportedMechanism('non-integer stoichiometric coefficient in ' + what)
+        out += [s] * int(n)
+    if len(out) > MAXS:
+        raise UnsupportedMechanism('%s has more than %d molecules on one side' % (what, MAXS))
+    return out + [empty] * (MAXS - len(out))
+
+
+def _nasa_row(a) -> List[float]:
+    """Coefficient forms the generator prints (rs:540-561, 1834-1857, 2049-2066; cj:829-858)."""
+    return [a[0], a[1], a[2], a[3], a[4],
+            a[5], a[1] / 2.0, a[2] / 3.0, a[3] / 4.0, a[4] / 5.0,
+            a[6] - a[0], a[0] - 1.0, a[2] / 6.0, a[3] / 12.0, a[4] / 20.0, 0.0]
+
+
+def build(mech: Mechanism) -> Dict[str, np.ndarray]:
+    specs, reacs = mech.specs, mech.reacs
+    nsp, nr = len(specs), len(reacs)
+    last = nsp - 1
+    if nsp < 2:
+        raise UnsupportedMechanism('need at least two species')
+    if nsp >= 0xFFFF:
+        raise UnsupportedMechanism('too many species')
+    rev_reacs, pdep_reacs = mech.rev_reacs, mech.pdep_reacs
+    f64 = lambda x: np.asarray(x, dtype=np.float64)
+    i32 = lambda x: np.asarray(x, dtype=np.int32)
+    T: Dict[str, np.ndarray] = {}
+
+    for i, rx in enumerate(reacs):
+        if rx.plog or rx.cheb:
+            raise UnsupportedMechanism('PLOG / Chebyshev reactions (reaction %d)' % i)
+        if not rx.A > 0:
+            raise UnsupportedMechanism('non-positive pre-exponential (reaction %d)' % i)
+        if rx.pdep and not (rx.low or rx.high):
+            raise UnsupportedMechanism('fall-off reaction %d without LOW or HIGH' % i)
+
+    # ---------------- species
+    mwN = specs[last].mw
+    T['sp_w'] = f64([sp.mw for sp in specs])
+    T['sp_iw'] = f64([q('{:.16e}', 1.0 / sp.mw) for sp in specs])            # rs:1678,1698
+    T['sp_ruw'] = f64([q('{:.16e}', RU / sp.mw) for sp in specs])            # rs:1834,2049
+    T['sp_tmid'] = f64([sp.Trange[1] for sp in specs])
+    T['sp_mwf'] = f64([q('{:.16e}', sp.mw / mwN) for sp in specs])           # cj:467
+    T['sp_nasa'] = f64([[_nasa_row(sp.lo), _nasa_row(sp.hi)] for sp in specs]).ravel()
+    seen = [False] * nsp
+    for rx in reacs:
+        for k in set(rx.reac + rx.prod):
+            if rx.net_nu(k) != 0:
+                seen[k] = True
+    T['sp_seen'] = i32(seen)                                                   # rs:1425-1527
+
+    # ---------------- kernel order: plain, third-body, fall-off; reversible first
+    def sort_key(i):
+        rx = reacs[i]
+        cls = 2 if rx.pdep else (1 if rx.thd_body else 0)
+        sub = (1 if rx.troe else (2 if rx.sri else 0)) if rx.pdep else 0
+        return (cls, sub, 0 if rx.rev else 1, i)
+    order = sorted(range(nr), key=sort_key)
+    pos_of = {orig: p for p, orig in enumerate(order)}
+    npm = len(pdep_reacs)
+    first_pm = nr - npm
+
+    # the stale pres_mod_temp of cj:154,226 (a specific collider that is species 0 is tested
+    # by truthiness): the value left behind by the closest earlier reaction that assigned it
+    def has_pmt(rx):
+        return bool((rx.pdep or rx.thd_body) and (rx.thd_body_eff or rx.pdep_sp))
+    stale_src = {}
+    for i, rx in enumerate(reacs):
+        if rx.pdep and rx.pdep_sp == 0 and not has_pmt(rx):
+            lo = (i // UNROLL) * UNROLL if nr > UNROLL else 0
+            src = [s for s in range(lo, i) if has_pmt(reacs[s])]
+            stale_src[i] = src[-1] if src else None
+
+    flags, rev_idx, pm_idx, raw_base = [], [], [], []
+    slots = np.full((nr, 2 * MAXS), nsp, dtype=np.int32)
+    arr = np.zeros((nr, 4))
+    pm_par = np.zeros((max(npm, 1), NPAR))
+    pm_sp = np.full(max(npm, 1), -1, dtype=np.int32)
+    eff_off, eff_sp, eff_am1 = [0], [], []
+    ln_pa_ru = math.log(PA / RU)
+
+    # raw slot bookkeeping: for kernel reaction p the kernel stores, in this order,
+    #   one value per occupied reactant slot whose species is not the last one,
+    #   one value per occupied product slot (reversible only) likewise,
+    #   then pres_mod_temp if ``want_pmt``.
+    want_pmt = [False] * nr
+    for i, rx in enumerate(reacs):
+        if has_pmt(rx):
+            listed = any(s != last and a != 1.0 for s, a in rx.thd_body_eff)
+            if listed or (rx.pdep_sp is not None and rx.pdep_sp != last):
+                want_pmt[i] = True
+    for i, src in stale_src.items():
+        if src is not None:
+            want_pmt[src] = True
+
+    raw_of_slot: List[List[int]] = [None] * nr      # per original reaction: raw index per slot / -1
+    raw_of_pmt = [-1] * nr
+    nraw = 0
+    for p, i in enumerate(order):
+        rx = reacs[i]
+        what = 'reaction %d' % i
+        rs = _slots(rx.reac, rx.reac_nu, nsp, what)
+        ps = _slots(rx.prod, rx.prod_nu, nsp, what)
+        slots[p, :MAXS] = rs
+        slots[p, MAXS:] = ps
+        fl = 0
+        if rx.rev:
+            fl |= F_REV
+        if rx.thd_body:
+            fl |= F_THD
+        if rx.pdep:
+            fl |= F_PDEP
+            if rx.low:
+                fl |= F_LOW
+        if rx.troe:
+            fl |= F_TROE
+        if rx.sri:
+            fl |= F_SRI
+        if has_pmt(rx):
+            fl |= F_PMT
+        if rx.pdep and (rx.pdep_sp or rx.thd_body_eff):
+            fl |= F_PMT_INJ
+        if rx.thd_body_eff and not rx.pdep:
+            fl |= F_EFFN1                                                      # cj:201-206
+        b_on, E_on = abs(rx.b) > 1.0e-90, abs(rx.E) > 1.0e-90
+        if not rx.rev and not b_on and not E_on and sum(rx.reac_nu) == 1.0:
+            fl |= F_NO_T                                                       # cj:1507-1523
+        rev_idx.append(rev_reacs.index(i) if rx.rev else -1)
+        pm_idx.append(pdep_reacs.index(i) if (rx.thd_body or rx.pdep) else -1)
+        if want_pmt[i]:
+            fl |= F_WANT_PMT
+        fl |= sum(1 for s in rs if s != nsp) << NRE_SHIFT
+        fl |= sum(1 for s in ps if s != nsp) << NPR_SHIFT
+
+        # Arrhenius (rs:27-146, A > 0: always the exponential form for parsed floats)
+        sum_nu = sum(rx.prod_nu) - sum(rx.reac_nu)
+        arr[p] = [q('{:.16e}', math.log(rx.A)), rx.b, q('{:.16e}', rx.E),
+                  float(sum_nu) * ln_pa_ru if rx.rev else 0.0]
+
+        raw_base.append(nraw)
+        ros = []
+        for s in rs:
+            if s != nsp and s != last:
+                ros.append(nraw)
+                nraw += 1
+            else:
+                ros.append(-1)
+        for s in ps:
+            if rx.rev and s != nsp and s != last:
+                ros.append(nraw)
+                nraw += 1
+            else:
+                ros.append(-1)
+        raw_of_slot[i] = ros
+        if want_pmt[i]:
+            raw_of_pmt[i] = nraw
+            nraw += 1
+
+        if rx.thd_body or rx.pdep:
+            m = p - first_pm
+            assert m >= 0
+            par = pm_par[m]
+            for s, a in rx.thd_body_eff:
+                if a != 1.0:
+                    eff_sp.append(s)
+                    eff_am1.append(a - 1.0)                                    # rs:1128-1130
+            eff_off.append(len(eff_sp))
+            pm_sp[m] = rx.pdep_sp if rx.pdep_sp is not None else -1
+            eff_case = bool(((rx.pdep and rx.pdep_sp is None) or rx.thd_body) and rx.thd_body_eff)
+            if eff_case:
+                par[4] = next((a for s, a in rx.thd_body_eff if s == last), 1.0)
+                par[5] = 1.0
+            elif rx.pdep_sp == last and has_pmt(rx):
+                par[4] = 1.0
+            if rx.pdep:
+                k0 = rx.low if rx.low else [rx.A, rx.b, rx.E]
+                kinf = [rx.A, rx.b, rx.E] if rx.low else rx.high
+                beta, Ea = k0[1] - kinf[1], k0[2] - kinf[2]                   # cj:641-655
+                par[0] = q('{:.16e}', math.log(k0[0] / kinf[0]))
+                par[1] = q('{:.16e}', beta)
+                par[2] = q('{:.16e}', Ea)
+                par[3] = q('{:.4e}', beta)                                    # cj:1167
+            if rx.troe:
+                a, T3, T1 = rx.troe_par[:3]
+                T2 = rx.troe_par[3] if len(rx.troe_par) == 4 else 0.0
+                if len(rx.troe_par) == 4 and T2 != 0.0:
+                    fl |= F_TROE_T2
+                par[6:14] = [q('{:.16e}', 1.0 - a), q('{:.16e}', -T3), q('{:.16e}', a),
+                             q('{:.16e}', -T1), q('{:.16e}', -T2),
+                             q('{:.16e}', -(1.0 - a) / T3), q('{:.16e}', a / T1),
+                             q('{:.16e}', T2)]                                 # cj:1083-1090,1262-1282
+            elif rx.sri:
+                s_ = rx.sri_par
+                five = len(s_) == 5
+                if five and s_[3] != 1.0 and s_[4] != 0.0:
+                    fl |= F_SRI5
+                if five and s_[4] != 0.0:
+                    fl |= F_SRI5_DT
+                d, e = (s_[3], s_[4]) if five else (1.0, 0.0)
+                par[14:19] = [q('{:.6}', s_[0]), q('{:.6}', s_[1]), q('{:.6}', s_[2]),
+                              q('{:.8e}', d), q('{:.6}', e)]                   # rs:1239-1255
+                par[19:22] = [q('{:.4}', s_[0]), q('{:.4}', -s_[1]), q('{:.4}', -s_[2])]  # cj:173-180
+                par[22:28] = [q('{:.16}', s_[0] * s_[1]), q('{:.16}', -s_[1]),
+                              q('{:.16e}', 1.0 / s_[2]), q('{:.16}', -s_[2]),
+                              q('{:.16}', s_[0]), q('{:.16}', e)]              # cj:1215-1235
+        flags.append(fl)
+    if not npm:
+        eff_off = [0, 0]
+
+    T['rx_orig'] = i32(order)
+    T['rx_flags'] = i32(flags)
+    T['rx_rev_idx'] = i32(rev_idx)
+    T['rx_pm_idx'] = i32(pm_idx)
+    T['rx_raw_base'] = i32(raw_base)
+    T['rx_slots'] = slots.ravel()
+    T['rx_arr'] = arr.ravel()
+    T['pm_par'] = pm_par.ravel()
+    T['pm_sp'] = pm_sp
+    T['pm_eff_off'] = i32(eff_off)
+    T['pm_eff_sp'] = i32(eff_sp if eff_sp else [0])
+    T['pm_eff_am1'] = f64(eff_am1 if eff_am1 else [0.0])
+
+    # ---------------- species-side reductions: wdot, T column, A, B share one CSR
+    red = [[] for _ in range(nsp)]
+    for p, i in enumerate(order):
+        rx = reacs[i]
+        for k in sorted(set(rx.reac + rx.prod)):
+            nu = rx.net_nu(k)
+            if nu != 0:
+                red[k].append((p, float(nu)))
+    red_off = [0]
+    for k in range(nsp):
+        red_off.append(red_off[-1] + len(red[k]))
+    T['red_off'] = i32(red_off)
+    T['red_rx'] = i32([p for lst in red for p, _ in lst] or [0])
+    T['red_nu'] = f64([nu for lst in red for _, nu in lst] or [0.0])
+
+    # ---------------- sparse part: entry (k, j) <- sum coef * raw[src]
+    contrib: Dict[tuple, list] = {}
+
+    def add(k, j, src, coef):
+        if coef != 0.0 and src >= 0:
+            contrib.setdefault((k, j), []).append((src, float(coef)))
+
+    for i, rx in enumerate(reacs):
+        part = [(k, rx.net_nu(k)) for k in sorted(set(rx.reac + rx.prod)) if rx.net_nu(k) != 0]
+        p = pos_of[i]
+        sl = slots[p]
+        eff_case = bool(((rx.pdep and rx.pdep_sp is None) or rx.thd_body) and rx.thd_body_eff)
+        for k, nu in part:
+            for a in range(2 * MAXS):
+                if raw_of_slot[i][a] >= 0:
+                    add(k, int(sl[a]), raw_of_slot[i][a], nu)                  # cj:410-448
+            if has_pmt(rx):
+                if eff_case:
+                    for s, al in rx.thd_body_eff:
+                        if s != last:
+                            add(k, s, raw_of_pmt[i], nu * (al - 1.0))          # cj:379-400
+                elif rx.pdep_sp is not None and rx.pdep_sp != last:
+                    add(k, rx.pdep_sp, raw_of_pmt[i], nu)                      # cj:401-404
+            elif i in stale_src and stale_src[i] is not None:
+                add(k, 0, raw_of_pmt[stale_src[i]], nu)
+    ents = sorted(contrib, key=lambda kj: (-len(contrib[kj]), kj[1], kj[0]))
+    nnz = len(ents)
+    if nnz >= 0xFFFF or nraw >= 0xFFFF:
+        raise UnsupportedMechanism('mechanism too large for 16-bit sparse indices')
+    coef_ix: Dict[float, int] = {}
+    con, ent_off = [], [0]
+    for kj in ents:
+        for src, c in contrib[kj]:
+            ci = coef_ix.setdefault(c, len(coef_ix))
+            con.append(src | (ci << 16))
+        ent_off.append(len(con))
+    if len(coef_ix) >= 0x7FFF:
+        raise UnsupportedMechanism('too many distinct sparse coefficients')
+    T['ent_kj'] = i32([k | (j << 16) for k, j in ents] or [0])
+    T['ent_off'] = i32(ent_off)
+    T['con'] = i32(con or [0])
+    T['coef'] = f64(list(coef_ix) or [0.0])
+    jmap = np.full((nsp - 1, nsp), nnz, dtype=np.uint16)
+    for e, (k, j) in enumerate(ents):
+        jmap[j, k] = e
+    T['jmap'] = jmap.ravel()
+
+    T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
+    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, nnz, len(con), len(coef_ix),
+                     first_pm, npm, red_off[-1], max(len(l) for l in red), 0, 0, 0, 0])
+    return T
