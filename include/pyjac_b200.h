@@ -1,0 +1,131 @@
+/* pyjac_b200 -- C ABI of the B200-native batched kinetics evaluator.
+ *
+ * One shared library (pyjac_b200/_build/libpyjac_b200.so) replaces the library that the
+ * reference *generates and compiles per mechanism* (libc_pyjac / libcu_pyjac,
+ * pyjac/libgen/libgen.py:170-186).  The mechanism arrives at run time as a table blob
+ * (pyjac_b200/tables.py + pyjac_b200/blob.py) instead of being unrolled into source.
+ *
+ * Three surfaces, each citing the reference interface it stands in for:
+ *
+ *  1. device-pointer batch API (new; the reference has no equivalent -- its GPU entry
+ *     point pyjac/pywrap/pyjacob.cu:134-188 always round-trips through host memory),
+ *  2. host-pointer batch API = pyjac/pywrap/pyjacob.cuh:6-10 (init / run / cleanup bound by
+ *     pyjac/pywrap/pyjacob_cuda_wrapper.pyx:5-34),
+ *  3. scalar API with the emitted library's own names and signatures
+ *     (headers emitted at pyjac/core/create_jacobian.py:2226-2248,
+ *     pyjac/core/rate_subs.py:292-323,1581-1608,2130-2150; bound by
+ *     pyjac/pywrap/pyjacob_wrapper.pyx:4-16 and linked by
+ *     pyjac/performance_tester/tester.c.in:2,28).
+ *
+ * Conventions: plain pointers and sizes only.  Species / reaction order is pyJac's internal
+ * order (last species moved to the end, utils.py:55-91).  A state is y = [T, Y_0..Y_{NSP-2}]
+ * plus a pressure; a Jacobian is NSP x NSP column-major, jac[i + NSP*j] = d f_i / d y_j
+ * (docs/faqs.rst:82-87).  Unlike the reference (all entry points void, exit() on error) the
+ * pyjac_* functions return 0 on success or a negative PYJAC_E* code and keep a message
+ * retrievable with pyjac_last_error(); the reference-named scalar functions keep the
+ * reference's behaviour (message on stderr, exit(1)).  There is NO CPU fallback: without a
+ * CUDA device every compute entry point fails with PYJAC_ENODEVICE.
+ */
+#ifndef PYJAC_B200_H
+#define PYJAC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pyjac_mech pyjac_mech;
+
+enum {
+    PYJAC_OK = 0,
+    PYJAC_EINVAL = -1,      /* bad argument / malformed table blob */
+    PYJAC_ENODEVICE = -2,   /* no usable CUDA device */
+    PYJAC_ECUDA = -3,       /* CUDA runtime error (see pyjac_last_error) */
+    PYJAC_ENOMEM = -4,      /* device or host allocation failed */
+    PYJAC_ETOOBIG = -5      /* mechanism does not fit the kernel's on-chip working set */
+};
+
+/* Jacobian output layouts */
+enum {
+    PYJAC_JAC_STATE_MAJOR = 0,  /* jac[s*NSP*NSP + i + NSP*j]: one contiguous column-major
+                                   Jacobian per state -- what eval_jacob() writes for one state */
+    PYJAC_JAC_STATE_FASTEST = 1 /* jac[(i + NSP*j)*ld + s]: the reference GPU layout
+                                   (mech_auxiliary.py:418-420 INDEX(); docs/faqs.rst:163-172) */
+};
+
+const char* pyjac_last_error(void);
+int pyjac_device_count(void);
+
+/* ---- mechanism handle ------------------------------------------------------------- */
+/* Parses a PJB200T1 table blob, uploads the tables to `device` (-1 = current device). */
+int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out);
+void pyjac_mech_destroy(pyjac_mech* m);
+/* dims[0..3] = NSP, FWD_RATES, REV_RATES, PRES_MOD_RATES (the mechanism.h macros,
+ * mech_auxiliary.py:109-176) */
+int pyjac_mech_dims(const pyjac_mech* m, int dims[4]);
+/* Launch tuning: states per thread block (1, 2 or 4), threads per block, blocks per SM
+ * (0 = keep automatic choice).  Results do not depend on these. */
+int pyjac_mech_tune(pyjac_mech* m, int states_per_block, int threads, int blocks_per_sm);
+/* number of kernels launched through this handle since creation */
+long long pyjac_mech_launches(const pyjac_mech* m);
+
+/* ---- 1. device-pointer batch API -------------------------------------------------- */
+/* All pointers are device pointers on the handle's device; `stream` is a cudaStream_t
+ * (NULL = default stream); calls are asynchronous.
+ * State input: element v (0 = T, 1.. = Y_{v-1}) of state s is d_y[s*y_ss + v*y_sv]:
+ *   state-fastest ("SoA", the reference GPU layout):  y_ss = 1,   y_sv = ld
+ *   one row per state (what the scalar API takes):    y_ss = NSP, y_sv = 1            */
+int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
+                         long long y_ss, long long y_sv, double* d_jac, int jac_layout,
+                         long long jac_ld, void* stream);
+/* dy element v of state s -> d_dy[s*o_ss + v*o_sv] */
+int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
+                   long long y_ss, long long y_sv, double* d_dy, long long o_ss,
+                   long long o_sv, void* stream);
+/* conc[NSP], fwd[FWD_RATES], rev[REV_RATES], pres_mod[PRES_MOD_RATES], spec_rates[NSP] and
+ * dy[NSP] per state; any output pointer may be NULL.  Element v of state s of every output
+ * goes to out[s*o_ss_mult*width + v] when o_state_fastest == 0 (rows), or out[v*o_ld + s]
+ * when o_state_fastest != 0. */
+int pyjac_rates_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
+                    long long y_ss, long long y_sv, double* d_conc, double* d_fwd,
+                    double* d_rev, double* d_pres_mod, double* d_spec_rates, double* d_dy,
+                    int o_state_fastest, long long o_ld, void* stream);
+
+/* ---- 2. host-pointer batch API (pyjac/pywrap/pyjacob.cuh:6-10) --------------------- */
+/* Selects the mechanism used by surfaces 2 and 3 (the reference bakes it in at build time). */
+int pyjac_set_mechanism(pyjac_mech* m);
+/* init(num): returns `padded` >= num (the reference pads to its 64-thread block and may
+ * cap at 80 % of free memory, pyjacob.cu:97-121; here padded == num rounded up to 8 and
+ * large batches are streamed in chunks instead of being capped).  Deviation: does NOT call
+ * cudaDeviceReset() (pyjacob.cu:88), which would destroy the caller's CUDA context. */
+int pyjac_cu_init(int num);
+/* run(): host arrays, flattened Fortran order (variable-major / state-fastest), pitch `num`
+ * (functional_tester/test.py:656-660,732-733): mass_frac is NSP x num ([T; Y_0..Y_{NSP-2}]),
+ * conc NSP x num, fwd FWD_RATES x num, rev REV_RATES x num, pres_mod PRES_MOD_RATES x num,
+ * spec_rates NSP x num, dy NSP x num, jac NSP*NSP x num. */
+void pyjac_cu_run(int num, int padded, const double* pres, const double* mass_frac,
+                  double* conc, double* fwd_rxn_rates, double* rev_rxn_rates,
+                  double* pres_mod, double* spec_rates, double* dy, double* jac);
+void pyjac_cu_cleanup(void);
+/* Host batch of row-major states (n x NSP) -> row-major Jacobians (n x NSP*NSP), streamed
+ * through pinned staging buffers; the path bench.py's e2e figure times. */
+int pyjac_eval_jacob_host(pyjac_mech* m, int n, const double* pres, const double* y,
+                          double* jac);
+int pyjac_dydt_host(pyjac_mech* m, int n, const double* pres, const double* y, double* dy);
+
+/* ---- 3. scalar API, reference names ------------------------------------------------ */
+void eval_jacob(const double t, const double pres, const double* y, double* jac);
+void dydt(const double t, const double pres, const double* y, double* dy);
+void eval_conc(const double T, const double pres, const double* mass_frac, double* y_N,
+               double* mw_avg, double* rho, double* conc);
+void eval_rxn_rates(const double T, const double pres, const double* C, double* fwd_rxn_rates,
+                    double* rev_rxn_rates);
+void get_rxn_pres_mod(const double T, const double pres, const double* C, double* pres_mod);
+void eval_spec_rates(const double* fwd_rates, const double* rev_rates, const double* pres_mod,
+                     double* sp_rates, double* dy_N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

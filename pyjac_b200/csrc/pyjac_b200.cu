@@ -1,0 +1,587 @@
+// C ABI of the B200-native evaluator (include/pyjac_b200.h): mechanism handle, launch
+// logic, the host-pointer batch API that stands in for pyjac/pywrap/pyjacob.cu:84-188 and
+// the reference-named scalar entry points.  There is no CPU compute path in this file.
+#include "pyjac_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "pjtable.h"
+
+using pj::IO;
+using pj::Layout;
+using pj::Tables;
+
+struct pyjac_mech {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    Tables tb{};
+    std::vector<void*> dev_allocs;
+    // launch configuration (per mode: 0 jac, 1 dydt, 2 rates)
+    int G[3] = {0, 0, 0};
+    int threads[3] = {0, 0, 0};
+    int blocks_per_sm[3] = {0, 0, 0};
+    int user_G = 0, user_threads = 0, user_bpsm = 0;
+    long long launches = 0;
+    // staging for the host-pointer API
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    double* h_pin[2] = {nullptr, nullptr};
+    double* d_in[2] = {nullptr, nullptr};
+    double* d_out[2] = {nullptr, nullptr};
+    size_t pin_bytes = 0, din_bytes = 0, dout_bytes = 0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+pyjac_mech* g_current = nullptr;    // mechanism behind surfaces 2 and 3
+int g_cu_num = 0;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? PYJAC_ENOMEM : PYJAC_ECUDA,     \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+Layout make_layout(const Tables& tb, int G, bool jac)
+{
+    Layout L{};
+    L.nsp1 = (tb.nsp + 1 + 1) & ~1;
+    int off = 0;
+    L.off_vec = off;  off += G * pj::NVEC * L.nsp1;
+    L.off_scal = off; off += G * pj::NSCAL;
+    L.off_r4 = off;   off += G * 4 * tb.nr;
+    L.off_raw = off;  if (jac) off += G * (tb.nraw + 1);
+    off = (off + 1) & ~1;
+    L.off_sval = off; if (jac) off += G * (tb.nnz + 1);
+    L.total = (off + 1) & ~1;
+    return L;
+}
+
+template <int MODE>
+const void* kernel_for(int G)
+{
+    switch (G) {
+    case 1: return (const void*)pj::k_eval<1, MODE>;
+    case 2: return (const void*)pj::k_eval<2, MODE>;
+    default: return (const void*)pj::k_eval<4, MODE>;
+    }
+}
+
+const void* kernel_ptr(int mode_ix, int G)
+{
+    switch (mode_ix) {
+    case 0: return kernel_for<pj::M_JAC>(G);
+    case 1: return kernel_for<pj::M_DYDT>(G);
+    default: return kernel_for<pj::M_RATES>(G);
+    }
+}
+
+// choose G / threads / blocks per SM for one mode and opt the kernel in to its smem size
+int configure(pyjac_mech* m, int mode_ix)
+{
+    const bool jac = mode_ix == 0;
+    const int cands[3] = {4, 2, 1};
+    int G = 0;
+    if (m->user_G) {
+        G = m->user_G;
+        if ((size_t)make_layout(m->tb, G, jac).total * 8 > (size_t)m->smem_optin) G = 0;
+    }
+    if (!G) {
+        // default: the largest group that still lets two blocks share an SM, else the
+        // largest that fits at all
+        for (int c : cands)
+            if ((size_t)make_layout(m->tb, c, jac).total * 8 * 2 + 2048 <= (size_t)m->smem_optin) { G = c; break; }
+        if (!G)
+            for (int c : cands)
+                if ((size_t)make_layout(m->tb, c, jac).total * 8 <= (size_t)m->smem_optin) { G = c; break; }
+    }
+    if (!G)
+        return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
+    const size_t bytes = (size_t)make_layout(m->tb, G, jac).total * 8;
+    int threads = m->user_threads ? m->user_threads : 384;
+    threads = std::max(64, std::min(512, (threads + 31) / 32 * 32));
+    int bpsm = (int)((size_t)m->smem_optin / (bytes + 1024));
+    bpsm = std::max(1, std::min(bpsm, 2048 / threads));
+    if (m->user_bpsm) bpsm = std::max(1, std::min(bpsm, m->user_bpsm));
+    m->G[mode_ix] = G;
+    m->threads[mode_ix] = threads;
+    m->blocks_per_sm[mode_ix] = bpsm;
+    CU(cudaFuncSetAttribute(kernel_ptr(mode_ix, G), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PYJAC_OK;
+}
+
+int launch(pyjac_mech* m, int mode_ix, const IO& io, cudaStream_t st)
+{
+    if (io.n <= 0) return PYJAC_OK;
+    CU(cudaSetDevice(m->device));
+    if (!m->G[mode_ix]) {
+        int rc = configure(m, mode_ix);
+        if (rc) return rc;
+    }
+    const int G = m->G[mode_ix];
+    Layout L = make_layout(m->tb, G, mode_ix == 0);
+    const long long groups = ((long long)io.n + G - 1) / G;
+    const int grid = (int)std::min<long long>(groups, (long long)m->sm_count * m->blocks_per_sm[mode_ix]);
+    void* args[3] = {(void*)&m->tb, (void*)&io, (void*)&L};
+    CU(cudaLaunchKernel(kernel_ptr(mode_ix, G), dim3(grid), dim3(m->threads[mode_ix]), args,
+                        (size_t)L.total * 8, st));
+    ++m->launches;
+    return PYJAC_OK;
+}
+
+template <typename T>
+int upload(pyjac_mech* m, const void* blob, const char* name, const T** out, int dtype)
+{
+    const pjt::Entry* e = pjt::find(blob, name);
+    if (!e || e->dtype != dtype) return fail(PYJAC_EINVAL, std::string("table blob lacks ") + name);
+    const size_t bytes = std::max<size_t>((size_t)e->count * sizeof(T), 16);
+    void* d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    m->dev_allocs.push_back(d);
+    CU(cudaMemset(d, 0, bytes));
+    CU(cudaMemcpy(d, (const char*)blob + e->offset, (size_t)e->count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)d;
+    return PYJAC_OK;
+}
+
+void release_staging(pyjac_mech* m)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (m->h_pin[i]) cudaFreeHost(m->h_pin[i]);
+        if (m->d_in[i]) cudaFree(m->d_in[i]);
+        if (m->d_out[i]) cudaFree(m->d_out[i]);
+        m->h_pin[i] = m->d_in[i] = m->d_out[i] = nullptr;
+    }
+    m->pin_bytes = m->din_bytes = m->dout_bytes = 0;
+}
+
+int ensure_staging(pyjac_mech* m, size_t pin, size_t din, size_t dout)
+{
+    CU(cudaSetDevice(m->device));
+    for (int i = 0; i < 2; ++i)
+        if (!m->stream[i]) CU(cudaStreamCreateWithFlags(&m->stream[i], cudaStreamNonBlocking));
+    if (pin > m->pin_bytes || din > m->din_bytes || dout > m->dout_bytes) {
+        for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(m->stream[i]));
+        pin = std::max(pin, m->pin_bytes); din = std::max(din, m->din_bytes); dout = std::max(dout, m->dout_bytes);
+        release_staging(m);
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaMallocHost((void**)&m->h_pin[i], pin));
+            CU(cudaMalloc((void**)&m->d_in[i], din));
+            CU(cudaMalloc((void**)&m->d_out[i], dout));
+        }
+        m->pin_bytes = pin; m->din_bytes = din; m->dout_bytes = dout;
+    }
+    return PYJAC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pyjac_last_error(void) { return g_err.c_str(); }
+
+int pyjac_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out)
+{
+    if (!out) return fail(PYJAC_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!pjt::valid(blob, len)) return fail(PYJAC_EINVAL, "not a PJB200T1 table blob");
+    if (pyjac_device_count() <= 0) return fail(PYJAC_ENODEVICE, "no CUDA device available (no CPU fallback exists)");
+    if (device < 0) CU(cudaGetDevice(&device));
+    CU(cudaSetDevice(device));
+    const pjt::Entry* de = pjt::find(blob, "dims");
+    const pjt::Entry* ce = pjt::find(blob, "cst");
+    if (!de || de->dtype != 1 || de->count < 12 || !ce || ce->dtype != 0 || ce->count < 2)
+        return fail(PYJAC_EINVAL, "table blob lacks dims / cst");
+    const int* d = (const int*)((const char*)blob + de->offset);
+    const double* c = (const double*)((const char*)blob + ce->offset);
+    pyjac_mech* m = new pyjac_mech();
+    m->device = device;
+    Tables& t = m->tb;
+    t.nsp = d[0]; t.nr = d[1]; t.nrev = d[2]; t.npd = d[3]; t.nraw = d[4]; t.nnz = d[5];
+    t.ncon = d[6]; t.ncoef = d[7]; t.first_pm = d[8]; t.npm = d[9]; t.nred = d[10]; t.maxred = d[11];
+    t.ru = c[0]; t.ln_pa_ru = c[1];
+    int rc = PYJAC_OK;
+#define UP(field, name, type, code) if (!rc) rc = upload<type>(m, blob, name, &t.field, code)
+    UP(sp_w, "sp_w", double, 0); UP(sp_iw, "sp_iw", double, 0); UP(sp_ruw, "sp_ruw", double, 0);
+    UP(sp_tmid, "sp_tmid", double, 0); UP(sp_mwf, "sp_mwf", double, 0); UP(sp_nasa, "sp_nasa", double, 0);
+    UP(sp_seen, "sp_seen", int, 1);
+    UP(rx_orig, "rx_orig", int, 1); UP(rx_flags, "rx_flags", int, 1); UP(rx_rev_idx, "rx_rev_idx", int, 1);
+    UP(rx_pm_idx, "rx_pm_idx", int, 1); UP(rx_raw_base, "rx_raw_base", int, 1); UP(rx_slots, "rx_slots", int, 1);
+    UP(rx_arr, "rx_arr", double, 0); UP(pm_par, "pm_par", double, 0); UP(pm_sp, "pm_sp", int, 1);
+    UP(pm_eff_off, "pm_eff_off", int, 1); UP(pm_eff_sp, "pm_eff_sp", int, 1); UP(pm_eff_am1, "pm_eff_am1", double, 0);
+    UP(red_off, "red_off", int, 1); UP(red_rx, "red_rx", int, 1); UP(red_nu, "red_nu", double, 0);
+    UP(ent_kj, "ent_kj", int, 1); UP(ent_off, "ent_off", int, 1); UP(con, "con", int, 1);
+    UP(coef, "coef", double, 0); UP(jmap, "jmap", unsigned short, 2);
+#undef UP
+    if (!rc) {
+        cudaDeviceProp prop;
+        cudaError_t e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) rc = fail(PYJAC_ECUDA, cudaGetErrorString(e));
+        else { m->sm_count = prop.multiProcessorCount; m->smem_optin = (int)prop.sharedMemPerBlockOptin; }
+    }
+    if (rc) { pyjac_mech_destroy(m); return rc; }
+    *out = m;
+    return PYJAC_OK;
+}
+
+void pyjac_mech_destroy(pyjac_mech* m)
+{
+    if (!m) return;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_current == m) g_current = nullptr;
+    }
+    cudaSetDevice(m->device);
+    release_staging(m);
+    for (int i = 0; i < 2; ++i) if (m->stream[i]) cudaStreamDestroy(m->stream[i]);
+    for (void* p : m->dev_allocs) cudaFree(p);
+    delete m;
+}
+
+int pyjac_mech_dims(const pyjac_mech* m, int dims[4])
+{
+    if (!m || !dims) return fail(PYJAC_EINVAL, "NULL argument");
+    dims[0] = m->tb.nsp; dims[1] = m->tb.nr; dims[2] = m->tb.nrev; dims[3] = m->tb.npd;
+    return PYJAC_OK;
+}
+
+int pyjac_mech_tune(pyjac_mech* m, int states_per_block, int threads, int blocks_per_sm)
+{
+    if (!m) return fail(PYJAC_EINVAL, "NULL mechanism");
+    if (states_per_block != 0 && states_per_block != 1 && states_per_block != 2 && states_per_block != 4)
+        return fail(PYJAC_EINVAL, "states_per_block must be 0, 1, 2 or 4");
+    m->user_G = states_per_block; m->user_threads = threads; m->user_bpsm = blocks_per_sm;
+    m->G[0] = m->G[1] = m->G[2] = 0;    // re-derive at next launch
+    return PYJAC_OK;
+}
+
+long long pyjac_mech_launches(const pyjac_mech* m) { return m ? m->launches : 0; }
+
+int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
+                         long long y_ss, long long y_sv, double* d_jac, int jac_layout,
+                         long long jac_ld, void* stream)
+{
+    if (!m || n < 0 || (n && (!d_pres || !d_y || !d_jac))) return fail(PYJAC_EINVAL, "bad argument");
+    if (jac_layout == PYJAC_JAC_STATE_FASTEST && jac_ld < n) return fail(PYJAC_EINVAL, "jac_ld < n");
+    IO io{};
+    io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
+    io.jac = d_jac; io.jac_layout = jac_layout; io.jac_ld = jac_ld;
+    return launch(m, 0, io, (cudaStream_t)stream);
+}
+
+int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
+                   long long y_ss, long long y_sv, double* d_dy, long long o_ss,
+                   long long o_sv, void* stream)
+{
+    if (!m || n < 0 || (n && (!d_pres || !d_y || !d_dy))) return fail(PYJAC_EINVAL, "bad argument");
+    IO io{};
+    io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
+    io.dy = d_dy; io.dy_ss = o_ss; io.dy_sv = o_sv;
+    return launch(m, 1, io, (cudaStream_t)stream);
+}
+
+int pyjac_rates_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
+                    long long y_ss, long long y_sv, double* d_conc, double* d_fwd,
+                    double* d_rev, double* d_pres_mod, double* d_spec_rates, double* d_dy,
+                    int o_state_fastest, long long o_ld, void* stream)
+{
+    if (!m || n < 0 || (n && (!d_pres || !d_y))) return fail(PYJAC_EINVAL, "bad argument");
+    if (o_state_fastest && o_ld < n) return fail(PYJAC_EINVAL, "o_ld < n");
+    IO io{};
+    io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
+    io.conc = d_conc; io.fwd = d_fwd; io.rev = d_rev; io.pm = d_pres_mod; io.sr = d_spec_rates;
+    io.dy = d_dy; io.o_sf = o_state_fastest; io.o_ld = o_ld;
+    return launch(m, 2, io, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- host-pointer batch API
+
+// Streams row-major host states through two pinned/device staging slots:
+// H2D(y, P) -> kernel -> D2H(result), chunk c+1 overlapping the D2H of chunk c.
+static int host_stream(pyjac_mech* m, int n, const double* pres, const double* y, double* out, bool jac)
+{
+    if (!m || n < 0 || (n && (!pres || !y || !out))) return fail(PYJAC_EINVAL, "bad argument");
+    if (!n) return PYJAC_OK;
+    const int nsp = m->tb.nsp;
+    const size_t in_w = (size_t)nsp + 1;                       // y row + pressure
+    const size_t out_w = jac ? (size_t)nsp * nsp : (size_t)nsp;
+    const size_t budget = (size_t)256 << 20;                   // bytes of output per chunk
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, budget / (out_w * 8)));
+    int rc = ensure_staging(m, (size_t)chunk * in_w * 8, (size_t)chunk * in_w * 8, (size_t)chunk * out_w * 8);
+    if (rc) return rc;
+    int slot = 0;
+    for (int s0 = 0; s0 < n; s0 += chunk, slot ^= 1) {
+        const int cn = std::min(chunk, n - s0);
+        cudaStream_t st = m->stream[slot];
+        CU(cudaStreamSynchronize(st));                         // slot's previous D2H finished
+        double* hp = m->h_pin[slot];
+        std::memcpy(hp, y + (size_t)s0 * nsp, (size_t)cn * nsp * 8);
+        std::memcpy(hp + (size_t)cn * nsp, pres + s0, (size_t)cn * 8);
+        CU(cudaMemcpyAsync(m->d_in[slot], hp, (size_t)cn * in_w * 8, cudaMemcpyHostToDevice, st));
+        const double* dy_ = m->d_in[slot];
+        const double* dp_ = dy_ + (size_t)cn * nsp;
+        if (jac) rc = pyjac_eval_jacob_dev(m, cn, dp_, dy_, nsp, 1, m->d_out[slot], PYJAC_JAC_STATE_MAJOR, 0, st);
+        else rc = pyjac_dydt_dev(m, cn, dp_, dy_, nsp, 1, m->d_out[slot], nsp, 1, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(out + (size_t)s0 * out_w, m->d_out[slot], (size_t)cn * out_w * 8,
+                           cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(m->stream[i]));
+    return PYJAC_OK;
+}
+
+int pyjac_eval_jacob_host(pyjac_mech* m, int n, const double* pres, const double* y, double* jac)
+{
+    return host_stream(m, n, pres, y, jac, true);
+}
+
+int pyjac_dydt_host(pyjac_mech* m, int n, const double* pres, const double* y, double* dy)
+{
+    return host_stream(m, n, pres, y, dy, false);
+}
+
+int pyjac_set_mechanism(pyjac_mech* m)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_current = m;
+    return PYJAC_OK;
+}
+
+static pyjac_mech* current_or_die(const char* who)
+{
+    pyjac_mech* m;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        m = g_current;
+    }
+    if (!m) {
+        std::fprintf(stderr, "%s: no mechanism selected (pyjac_set_mechanism)\n", who);
+        std::exit(1);
+    }
+    return m;
+}
+
+static void die_on(int rc, const char* who)
+{
+    if (rc) {
+        // the reference's entry points cannot report errors: cudaErrorCheck prints and exits
+        // (mech_auxiliary.py:424-436)
+        std::fprintf(stderr, "%s: %s\n", who, pyjac_last_error());
+        std::exit(1);
+    }
+}
+
+int pyjac_cu_init(int num)
+{
+    pyjac_mech* m;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        m = g_current;
+    }
+    if (!m) return fail(PYJAC_EINVAL, "no mechanism selected (pyjac_set_mechanism)");
+    if (num <= 0) return fail(PYJAC_EINVAL, "num must be positive");
+    g_cu_num = num;
+    return (num + 7) / 8 * 8;
+}
+
+// device chunk of state-fastest arrays with leading dimension ld
+static int cu_run_impl(pyjac_mech* m, int num, const double* pres, const double* mass_frac,
+                       double* conc, double* fwd, double* rev, double* pmod, double* sr,
+                       double* dy, double* jac)
+{
+    const Tables& t = m->tb;
+    const int nsp = t.nsp;
+    const size_t widths[7] = {(size_t)nsp, (size_t)t.nr, (size_t)t.nrev, (size_t)t.npd, (size_t)nsp,
+                              (size_t)nsp, (size_t)nsp * nsp};
+    double* outs[7] = {conc, fwd, rev, pmod, sr, dy, jac};
+    size_t wsum = 0;
+    for (int i = 0; i < 7; ++i) if (outs[i]) wsum += widths[i];
+    const size_t budget = (size_t)512 << 20;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)num, budget / ((wsum + nsp + 1) * 8)));
+    const int ld = (chunk + 7) / 8 * 8;
+    int rc = ensure_staging(m, 16, (size_t)ld * (nsp + 1) * 8, (size_t)ld * std::max<size_t>(wsum, 1) * 8);
+    if (rc) return rc;
+    cudaStream_t st = m->stream[0];
+    for (int s0 = 0; s0 < num; s0 += chunk) {
+        const int cn = std::min(chunk, num - s0);
+        double* d_y = m->d_in[0];
+        double* d_p = d_y + (size_t)ld * nsp;
+        CU(cudaMemcpy2DAsync(d_y, (size_t)ld * 8, mass_frac + s0, (size_t)num * 8, (size_t)cn * 8, nsp,
+                             cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_p, pres + s0, (size_t)cn * 8, cudaMemcpyHostToDevice, st));
+        double* d_o[7];
+        size_t off = 0;
+        for (int i = 0; i < 7; ++i) {
+            d_o[i] = outs[i] ? m->d_out[0] + off : nullptr;
+            if (outs[i]) off += widths[i] * ld;
+        }
+        if (d_o[0] || d_o[1] || d_o[2] || d_o[3] || d_o[4] || d_o[5]) {
+            rc = pyjac_rates_dev(m, cn, d_p, d_y, 1, ld, d_o[0], d_o[1], d_o[2], d_o[3], d_o[4], d_o[5], 1, ld, st);
+            if (rc) return rc;
+        }
+        if (d_o[6]) {
+            rc = pyjac_eval_jacob_dev(m, cn, d_p, d_y, 1, ld, d_o[6], PYJAC_JAC_STATE_FASTEST, ld, st);
+            if (rc) return rc;
+        }
+        for (int i = 0; i < 7; ++i)
+            if (outs[i] && widths[i])
+                CU(cudaMemcpy2DAsync(outs[i] + s0, (size_t)num * 8, d_o[i], (size_t)ld * 8, (size_t)cn * 8,
+                                     widths[i], cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return PYJAC_OK;
+}
+
+void pyjac_cu_run(int num, int padded, const double* pres, const double* mass_frac,
+                  double* conc, double* fwd_rxn_rates, double* rev_rxn_rates,
+                  double* pres_mod, double* spec_rates, double* dy, double* jac)
+{
+    (void)padded;
+    pyjac_mech* m = current_or_die("run");
+    die_on(cu_run_impl(m, num, pres, mass_frac, conc, fwd_rxn_rates, rev_rxn_rates, pres_mod,
+                       spec_rates, dy, jac), "run");
+}
+
+void pyjac_cu_cleanup(void)
+{
+    pyjac_mech* m;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        m = g_current;
+    }
+    if (m) { cudaSetDevice(m->device); release_staging(m); }
+    g_cu_num = 0;
+}
+
+// ---------------------------------------------------------------- scalar API (batch of 1)
+
+void eval_jacob(const double t, const double pres, const double* y, double* jac)
+{
+    (void)t;
+    pyjac_mech* m = current_or_die("eval_jacob");
+    die_on(pyjac_eval_jacob_host(m, 1, &pres, y, jac), "eval_jacob");
+}
+
+void dydt(const double t, const double pres, const double* y, double* dy)
+{
+    (void)t;
+    pyjac_mech* m = current_or_die("dydt");
+    die_on(pyjac_dydt_host(m, 1, &pres, y, dy), "dydt");
+}
+
+// one state through the M_RATES kernel; in_conc selects [T, C...] input
+static int scalar_rates(pyjac_mech* m, double T, double pres, const double* in, int n_in, bool in_conc,
+                        double* conc, double* fwd, double* rev, double* pmod, double* extra3)
+{
+    const Tables& t = m->tb;
+    const int nsp = t.nsp;
+    const size_t in_d = (size_t)nsp + 2, n_out = (size_t)nsp + t.nr + t.nrev + t.npd, out_d = n_out + 4;
+    int rc = ensure_staging(m, std::max(in_d, out_d) * 8, in_d * 8, out_d * 8);
+    if (rc) return rc;
+    cudaStream_t st = m->stream[0];
+    double* hp = m->h_pin[0];
+    hp[0] = T;
+    std::memcpy(hp + 1, in, (size_t)n_in * 8);
+    hp[nsp + 1] = pres;
+    CU(cudaMemcpyAsync(m->d_in[0], hp, in_d * 8, cudaMemcpyHostToDevice, st));
+    double* d = m->d_out[0];
+    IO io{};
+    io.n = 1; io.pres = m->d_in[0] + nsp + 1; io.y = m->d_in[0]; io.y_ss = 0; io.y_sv = 1;
+    io.in_conc = in_conc ? 1 : 0;
+    io.conc = d; io.fwd = d + nsp; io.rev = d + nsp + t.nr; io.pm = d + nsp + t.nr + t.nrev;
+    io.scal3 = d + n_out;
+    rc = launch(m, 2, io, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hp, d, out_d * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (conc) std::memcpy(conc, hp, (size_t)nsp * 8);
+    if (fwd) std::memcpy(fwd, hp + nsp, (size_t)t.nr * 8);
+    if (rev) std::memcpy(rev, hp + nsp + t.nr, (size_t)t.nrev * 8);
+    if (pmod) std::memcpy(pmod, hp + nsp + t.nr + t.nrev, (size_t)t.npd * 8);
+    if (extra3) std::memcpy(extra3, hp + n_out, 3 * 8);
+    return PYJAC_OK;
+}
+
+void eval_conc(const double T, const double pres, const double* mass_frac, double* y_N,
+               double* mw_avg, double* rho, double* conc)
+{
+    pyjac_mech* m = current_or_die("eval_conc");
+    const int nsp = m->tb.nsp;
+    double s3[3];
+    die_on(scalar_rates(m, T, pres, mass_frac, nsp - 1, false, conc, nullptr, nullptr, nullptr, s3),
+           "eval_conc");
+    if (y_N) *y_N = s3[0];
+    if (mw_avg) *mw_avg = s3[1];
+    if (rho) *rho = s3[2];
+}
+
+void eval_rxn_rates(const double T, const double pres, const double* C, double* fwd_rxn_rates,
+                    double* rev_rxn_rates)
+{
+    pyjac_mech* m = current_or_die("eval_rxn_rates");
+    die_on(scalar_rates(m, T, pres, C, m->tb.nsp, true, nullptr, fwd_rxn_rates, rev_rxn_rates, nullptr, nullptr),
+           "eval_rxn_rates");
+}
+
+void get_rxn_pres_mod(const double T, const double pres, const double* C, double* pres_mod)
+{
+    pyjac_mech* m = current_or_die("get_rxn_pres_mod");
+    die_on(scalar_rates(m, T, pres, C, m->tb.nsp, true, nullptr, nullptr, nullptr, pres_mod, nullptr),
+           "get_rxn_pres_mod");
+}
+
+void eval_spec_rates(const double* fwd_rates, const double* rev_rates, const double* pres_mod,
+                     double* sp_rates, double* dy_N)
+{
+    pyjac_mech* m = current_or_die("eval_spec_rates");
+    const Tables& t = m->tb;
+    const size_t in_d = (size_t)t.nr + t.nrev + t.npd + 1, out_d = (size_t)t.nsp;
+    auto run = [&]() -> int {
+        int rc = ensure_staging(m, std::max(in_d, out_d) * 8, in_d * 8, out_d * 8);
+        if (rc) return rc;
+        cudaStream_t st = m->stream[0];
+        double* hp = m->h_pin[0];
+        std::memcpy(hp, fwd_rates, (size_t)t.nr * 8);
+        if (t.nrev) std::memcpy(hp + t.nr, rev_rates, (size_t)t.nrev * 8);
+        if (t.npd) std::memcpy(hp + t.nr + t.nrev, pres_mod, (size_t)t.npd * 8);
+        CU(cudaMemcpyAsync(m->d_in[0], hp, in_d * 8, cudaMemcpyHostToDevice, st));
+        pj::k_spec_rates<<<(t.nsp + 63) / 64, 64, 0, st>>>(t, m->d_in[0], m->d_in[0] + t.nr,
+                                                          m->d_in[0] + t.nr + t.nrev, m->d_out[0]);
+        CU(cudaGetLastError());
+        ++m->launches;
+        CU(cudaMemcpyAsync(hp, m->d_out[0], out_d * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::memcpy(sp_rates, hp, (size_t)(t.nsp - 1) * 8);
+        *dy_N = hp[t.nsp - 1];
+        return PYJAC_OK;
+    };
+    die_on(run(), "eval_spec_rates");
+}
+
+}  // extern "C"

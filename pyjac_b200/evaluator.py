@@ -1,0 +1,158 @@
+"""Host-side handle on one mechanism loaded into the CUDA library.
+
+``Evaluator`` owns a ``pyjac_mech`` (include/pyjac_b200.h) and exposes the batched
+device-pointer calls on torch CUDA tensors (torch is used for device memory and streams
+only) and the streamed host-pointer calls on numpy arrays.  Layout vocabulary:
+
+* ``'rows'``          one row per state: ``y[n, NSP] = [T, Y_0..Y_{NSP-2}]`` -- what the
+                      reference's scalar API takes (docs/faqs.rst:82-87)
+* ``'state_fastest'`` variable-major ``y[NSP, ld]`` -- the reference GPU layout
+                      (mech_auxiliary.py:418-420; docs/faqs.rst:163-172)
+
+Jacobians: ``'rows'`` gives ``jac[n, NSP*NSP]``, each row one column-major NSP x NSP matrix
+(``jac[s, i + NSP*j]``); ``'state_fastest'`` gives ``jac[NSP*NSP, ld]``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import blob as _blob
+from . import lib as _lib
+from . import tables as _tables
+from .mechanism import Mechanism
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class Evaluator:
+    def __init__(self, mech: Mechanism, device: Optional[int] = None):
+        import torch
+        self._torch = torch
+        self.mech = mech
+        self.lib = _lib.load()
+        if self.lib.pyjac_device_count() <= 0:
+            raise _lib.PyjacError('no CUDA device: pyjac_b200 has no CPU fallback')
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.tables = _tables.build(mech)
+        data = _blob.pack(self.tables)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.pyjac_mech_create(data, len(data), self.device, ctypes.byref(h)))
+        self._h = h
+        dims = (ctypes.c_int * 4)()
+        _lib.check(self.lib.pyjac_mech_dims(self._h, dims))
+        self.NSP, self.NR, self.NREV, self.NPD = (int(v) for v in dims)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.pyjac_mech_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def tune(self, states_per_block: int = 0, threads: int = 0, blocks_per_sm: int = 0):
+        _lib.check(self.lib.pyjac_mech_tune(self._h, states_per_block, threads, blocks_per_sm))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.pyjac_mech_launches(self._h))
+
+    def make_current(self):
+        """Select this mechanism for the reference-named entry points (pyjacob / cu_pyjacob)."""
+        _lib.check(self.lib.pyjac_set_mechanism(self._h))
+
+    def _stream(self, stream):
+        s = self._torch.cuda.current_stream(self.device) if stream is None else stream
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def _strides(self, y, layout: str):
+        if layout == 'rows':
+            assert y.dim() == 2 and y.shape[1] == self.NSP and y.is_contiguous()
+            return y.shape[0], self.NSP, 1
+        if layout == 'state_fastest':
+            assert y.dim() == 2 and y.shape[0] == self.NSP and y.is_contiguous()
+            return y.shape[1], 1, y.shape[1]
+        raise ValueError(layout)
+
+    def _check_dev(self, *ts):
+        for t in ts:
+            if t is not None:
+                assert t.is_cuda and t.dtype == self._torch.float64 and t.device.index == self.device
+
+    # ------------------------------------------------------------------ device batch API
+    def eval_jacob(self, P, y, out=None, y_layout: str = 'rows', jac_layout: str = 'rows',
+                   stream=None):
+        torch = self._torch
+        self._check_dev(P, y, out)
+        n, ss, sv = self._strides(y, y_layout)
+        nn = self.NSP * self.NSP
+        if jac_layout == 'rows':
+            if out is None:
+                out = torch.empty((n, nn), dtype=torch.float64, device=y.device)
+            assert out.shape == (n, nn) and out.is_contiguous()
+            lay, ld = _lib.JAC_STATE_MAJOR, 0
+        else:
+            if out is None:
+                out = torch.empty((nn, n), dtype=torch.float64, device=y.device)
+            assert out.shape[0] == nn and out.shape[1] >= n and out.is_contiguous()
+            lay, ld = _lib.JAC_STATE_FASTEST, out.shape[1]
+        _lib.check(self.lib.pyjac_eval_jacob_dev(self._h, n, _ptr(P), _ptr(y), ss, sv, _ptr(out),
+                                                 lay, ld, self._stream(stream)))
+        return out
+
+    def dydt(self, P, y, out=None, y_layout: str = 'rows', stream=None):
+        torch = self._torch
+        self._check_dev(P, y, out)
+        n, ss, sv = self._strides(y, y_layout)
+        if out is None:
+            out = torch.empty_like(y)
+        assert out.shape == y.shape and out.is_contiguous()
+        _lib.check(self.lib.pyjac_dydt_dev(self._h, n, _ptr(P), _ptr(y), ss, sv, _ptr(out), ss, sv,
+                                           self._stream(stream)))
+        return out
+
+    def rates(self, P, y, y_layout: str = 'rows', want_dy: bool = False, stream=None):
+        """conc, fwd, rev, pres_mod, spec_rates[, dy] in the layout of ``y``."""
+        torch = self._torch
+        self._check_dev(P, y)
+        n, ss, sv = self._strides(y, y_layout)
+        widths = [self.NSP, self.NR, self.NREV, self.NPD, self.NSP] + ([self.NSP] if want_dy else [])
+        sf = y_layout == 'state_fastest'
+        outs = [torch.zeros((w, n) if sf else (n, w), dtype=torch.float64, device=y.device)
+                for w in widths]
+        ptrs = [_ptr(o) if o.numel() else 0 for o in outs] + ([] if want_dy else [0])
+        _lib.check(self.lib.pyjac_rates_dev(self._h, n, _ptr(P), _ptr(y), ss, sv, *ptrs,
+                                            1 if sf else 0, n, self._stream(stream)))
+        return tuple(outs)
+
+    # ------------------------------------------------------------------ host batch API
+    def eval_jacob_host(self, P, y, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """numpy rows in, numpy rows out, streamed through pinned staging buffers."""
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        P = np.ascontiguousarray(np.broadcast_to(np.asarray(P, dtype=np.float64), (y.shape[0],)))
+        assert y.ndim == 2 and y.shape[1] == self.NSP
+        if out is None:
+            out = np.empty((y.shape[0], self.NSP * self.NSP))
+        assert out.flags.c_contiguous and out.shape == (y.shape[0], self.NSP * self.NSP)
+        _lib.check(self.lib.pyjac_eval_jacob_host(self._h, y.shape[0], P.ctypes.data, y.ctypes.data,
+                                                  out.ctypes.data))
+        return out
+
+    def dydt_host(self, P, y, out: Optional[np.ndarray] = None) -> np.ndarray:
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        P = np.ascontiguousarray(np.broadcast_to(np.asarray(P, dtype=np.float64), (y.shape[0],)))
+        assert y.ndim == 2 and y.shape[1] == self.NSP
+        if out is None:
+            out = np.empty_like(y)
+        _lib.check(self.lib.pyjac_dydt_host(self._h, y.shape[0], P.ctypes.data, y.ctypes.data,
+                                            out.ctypes.data))
+        return out

@@ -1,0 +1,79 @@
+"""ctypes binding of include/pyjac_b200.h -- the only doorway from Python to the kernels.
+
+Stands where the reference's Cython glue does (pyjac/pywrap/pyjacob_wrapper.pyx,
+pyjac/pywrap/pyjacob_cuda_wrapper.pyx): typed buffers in, raw pointers out.  Loading fails
+loudly if the in-tree CUDA library cannot be found or built; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_size_t, c_void_p
+
+from . import libgen
+
+_dp = POINTER(c_double)
+
+PYJAC_OK = 0
+JAC_STATE_MAJOR = 0
+JAC_STATE_FASTEST = 1
+
+# every symbol include/pyjac_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    'pyjac_last_error': (c_char_p, []),
+    'pyjac_device_count': (c_int, []),
+    'pyjac_mech_create': (c_int, [c_void_p, c_size_t, c_int, POINTER(c_void_p)]),
+    'pyjac_mech_destroy': (None, [c_void_p]),
+    'pyjac_mech_dims': (c_int, [c_void_p, POINTER(c_int)]),
+    'pyjac_mech_tune': (c_int, [c_void_p, c_int, c_int, c_int]),
+    'pyjac_mech_launches': (c_longlong, [c_void_p]),
+    'pyjac_eval_jacob_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
+                                     c_void_p, c_int, c_longlong, c_void_p]),
+    'pyjac_dydt_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
+                               c_void_p, c_longlong, c_longlong, c_void_p]),
+    'pyjac_rates_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_longlong, c_void_p]),
+    'pyjac_set_mechanism': (c_int, [c_void_p]),
+    'pyjac_cu_init': (c_int, [c_int]),
+    'pyjac_cu_run': (None, [c_int, c_int] + [c_void_p] * 9),
+    'pyjac_cu_cleanup': (None, []),
+    'pyjac_eval_jacob_host': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'pyjac_dydt_host': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'eval_jacob': (None, [c_double, c_double, c_void_p, c_void_p]),
+    'dydt': (None, [c_double, c_double, c_void_p, c_void_p]),
+    'eval_conc': (None, [c_double, c_double, c_void_p, _dp, _dp, _dp, c_void_p]),
+    'eval_rxn_rates': (None, [c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    'get_rxn_pres_mod': (None, [c_double, c_double, c_void_p, c_void_p]),
+    'eval_spec_rates': (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+_LIB = None
+
+
+class PyjacError(RuntimeError):
+    pass
+
+
+def load(path: str = None) -> ctypes.CDLL:
+    """The C-ABI library, built in-tree on first use (nvcc, sm_100a)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    lib_path = path or libgen.build_library()
+    try:
+        lib = ctypes.CDLL(lib_path)
+    except OSError as exc:
+        raise PyjacError('cannot load the pyjac_b200 CUDA library %s: %s' % (lib_path, exc))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != PYJAC_OK:
+        msg = load().pyjac_last_error()
+        raise PyjacError('pyjac_b200 error %d: %s' % (rc, msg.decode() if msg else '?'))

@@ -1,0 +1,101 @@
+"""Parity gates.  fp64, tolerance 1e-10 as BASELINE.json's north_star states.
+
+Near-equilibrium states make *net* rates pure cancellation noise (the reference recompiled
+with -fassociative-math differs from itself by x860 elementwise in dydt), so the gates scale
+the error by the quantity that sets the rounding level:
+
+  jac         |d| <= RTOL * max_i |ref[i, j]|              per column j, per state
+  spec_rates  |d| <= RTOL * sum_i |nu_ki| (|qf_i| + |qr_i|) |pm_i|        (gross rate)
+  dydt[k+1]   same, times W_k / rho;   dydt[0] scaled by sum_k |h_k W_k| gross_k / (rho cp_avg)
+  fwd, rev, pres_mod   elementwise rtol RTOL
+  conc        |d| W_k / rho <= 1e-13                        (error in mass-fraction units)
+"""
+import numpy as np
+
+RTOL = 1.0e-10
+
+
+def _thermo(mech, T):
+    n = len(mech.specs)
+    cp = np.empty((T.size, n))
+    h = np.empty((T.size, n))
+    from pyjac_b200.chem import RU
+    for k, sp in enumerate(mech.specs):
+        lo = T <= sp.Trange[1]
+        a = np.where(lo[:, None], np.asarray(sp.lo)[None, :], np.asarray(sp.hi)[None, :]).T
+        cp[:, k] = RU / sp.mw * (a[0] + T * (a[1] + T * (a[2] + T * (a[3] + a[4] * T))))
+        h[:, k] = RU / sp.mw * (a[5] + T * (a[0] + T * (a[1] / 2 + T * (a[2] / 3 + T * (a[3] / 4 + a[4] / 5 * T)))))
+    return cp, h
+
+
+def gross_rates(mech, fwd, rev, pres_mod):
+    """sum_i |nu_ki| (|qf| + |qr|) |pm| per species, from reference-ordered rate arrays."""
+    n = fwd.shape[0]
+    g = np.zeros((n, mech.NSP))
+    rev_reacs, pdep_reacs = mech.rev_reacs, mech.pdep_reacs
+    for i, rx in enumerate(mech.reacs):
+        tot = np.abs(fwd[:, i])
+        if rx.rev:
+            tot = tot + np.abs(rev[:, rev_reacs.index(i)])
+        if rx.thd_body or rx.pdep:
+            tot = tot * np.abs(pres_mod[:, pdep_reacs.index(i)])
+        for k in set(rx.reac + rx.prod):
+            nu = rx.net_nu(k)
+            if nu:
+                g[:, k] += abs(nu) * tot
+    return g
+
+
+def check_jac(new, ref, nsp, what='jac'):
+    a = new.reshape(-1, nsp, nsp)        # [state, col, row]
+    b = ref.reshape(-1, nsp, nsp)
+    assert np.isfinite(a).all(), what + ': non-finite values'
+    colmax = np.abs(b).max(axis=2, keepdims=True)
+    err = np.abs(a - b) / (colmax + 1e-300)
+    worst = float(err.max())
+    assert worst <= RTOL, '%s: |d|/colmax = %.3e at %s' % (what, worst, np.unravel_index(err.argmax(), err.shape))
+    rel = np.abs(a - b) / (np.abs(b) + 1e-300)
+    return worst, float((rel[b != 0] <= RTOL).mean())
+
+
+def check_rates(mech, P, y, new, ref, what=''):
+    """new / ref: dicts with conc, fwd, rev, pres_mod, spec_rates and optionally dydt."""
+    w = np.array([sp.mw for sp in mech.specs])
+    rho = (ref['conc'] * w[None, :]).sum(axis=1)
+    out = {}
+    e = np.abs(new['conc'] - ref['conc']) * w[None, :] / rho[:, None]
+    out['conc'] = float(e.max())
+    assert out['conc'] <= 1e-13, what + ' conc %.3e' % out['conc']
+    for key in ('fwd', 'rev', 'pres_mod'):
+        if ref[key].size == 0:
+            continue
+        e = np.abs(new[key] - ref[key]) / (np.abs(ref[key]) + 1e-300)
+        out[key] = float(e.max())
+        assert out[key] <= RTOL, what + ' %s rel %.3e' % (key, out[key])
+    g = gross_rates(mech, ref['fwd'], ref['rev'], ref['pres_mod'])
+    e = np.abs(new['spec_rates'] - ref['spec_rates']) / (g + 1e-300)
+    e[g == 0] = np.abs(new['spec_rates'] - ref['spec_rates'])[g == 0]
+    out['spec_rates'] = float(e.max())
+    assert out['spec_rates'] <= RTOL, what + ' spec_rates %.3e' % out['spec_rates']
+    if 'dydt' in new and 'dydt' in ref:
+        out['dydt'] = check_dydt(mech, y, new['dydt'], ref, what)
+    return out
+
+
+def check_dydt(mech, y, new_dy, ref, what=''):
+    w = np.array([sp.mw for sp in mech.specs])
+    rho = (ref['conc'] * w[None, :]).sum(axis=1)
+    g = gross_rates(mech, ref['fwd'], ref['rev'], ref['pres_mod'])
+    T = y[:, 0]
+    cp, h = _thermo(mech, T)
+    Y = np.concatenate([y[:, 1:], 1.0 - y[:, 1:].sum(axis=1, keepdims=True)], axis=1)
+    cp_avg = (Y * cp).sum(axis=1)
+    scale = np.empty_like(ref['dydt'])
+    scale[:, 1:] = g[:, :-1] * w[None, :-1] / rho[:, None]
+    scale[:, 0] = (np.abs(h * w[None, :]) * g).sum(axis=1) / (rho * cp_avg)
+    d = np.abs(new_dy - ref['dydt'])
+    e = d / (scale + 1e-300)
+    e[scale == 0] = d[scale == 0]
+    worst = float(e.max())
+    assert worst <= RTOL, what + ' dydt %.3e' % worst
+    return worst
