@@ -24,12 +24,14 @@ struct pyjac_mech {
     int device = 0;
     int sm_count = 0;
     int smem_optin = 0;
+    int smem_per_sm = 0;
     Tables tb{};
     std::vector<void*> dev_allocs;
     // launch configuration (per mode: 0 jac, 1 dydt, 2 rates)
     int G[3] = {0, 0, 0};
     int threads[3] = {0, 0, 0};
     int blocks_per_sm[3] = {0, 0, 0};
+    int minb[3] = {1, 1, 1};
     int user_G = 0, user_threads = 0, user_bpsm = 0;
     long long launches = 0;
     // staging for the host-pointer API
@@ -64,34 +66,40 @@ int fail(int code, const std::string& msg)
 Layout make_layout(const Tables& tb, int G, bool jac)
 {
     Layout L{};
-    L.nsp1 = (tb.nsp + 1 + 1) & ~1;
+    auto even = [](int v) { return (v + 1) & ~1; };
+    L.nsp1 = even(tb.nsp + 1);
     int off = 0;
-    L.off_vec = off;  off += G * pj::NVEC * L.nsp1;
-    L.off_scal = off; off += G * pj::NSCAL;
-    L.off_r4 = off;   off += G * 4 * tb.nr;
-    L.off_raw = off;  if (jac) off += G * (tb.nraw + 1);
-    off = (off + 1) & ~1;
-    L.off_sval = off; if (jac) off += G * (tb.nnz + 1);
-    L.total = (off + 1) & ~1;
+    L.off_spv = off;  L.st_spv = 4 * L.nsp1;            off += G * L.st_spv;
+    L.off_vec = off;  L.st_vec = pj::NVEC * L.nsp1;     off += G * L.st_vec;
+    L.off_cp = off;   L.st_cp = L.nsp1;                 off += 2 * G * L.st_cp;
+    L.off_y = off;    L.st_y = L.nsp1;                  off += G * L.st_y;
+    L.off_scal = off;                                   off += 2 * G * pj::NSCAL;
+    L.off_r4 = off;   L.st_r4 = 4 * tb.nr;              off += G * L.st_r4;
+    L.off_part = off; L.st_part = 4 * tb.nchunk;        off += G * L.st_part;
+    L.off_rh = off;   L.st_rh = even(tb.nr);            if (jac) off += G * L.st_rh;
+    L.off_raw = off;  L.st_raw = even(tb.nraw + 1);     if (jac) off += G * L.st_raw;
+    L.off_sval = off; L.st_sval = even(tb.zero_slot + 1); if (jac) off += G * L.st_sval;
+    L.total = off;
     return L;
 }
 
-template <int MODE>
+template <int MODE, int MINB>
 const void* kernel_for(int G)
 {
     switch (G) {
-    case 1: return (const void*)pj::k_eval<1, MODE>;
-    case 2: return (const void*)pj::k_eval<2, MODE>;
-    default: return (const void*)pj::k_eval<4, MODE>;
+    case 1: return (const void*)pj::k_eval<1, MODE, MINB>;
+    case 2: return (const void*)pj::k_eval<2, MODE, MINB>;
+    default: return (const void*)pj::k_eval<4, MODE, MINB>;
     }
 }
 
-const void* kernel_ptr(int mode_ix, int G)
+// minb = 2 selects the 80-register build (<= 384 threads) so two blocks fit on an SM
+const void* kernel_ptr(int mode_ix, int G, int minb)
 {
     switch (mode_ix) {
-    case 0: return kernel_for<pj::M_JAC>(G);
-    case 1: return kernel_for<pj::M_DYDT>(G);
-    default: return kernel_for<pj::M_RATES>(G);
+    case 0: return minb == 2 ? kernel_for<pj::M_JAC, 2>(G) : kernel_for<pj::M_JAC, 1>(G);
+    case 1: return kernel_for<pj::M_DYDT, 1>(G);
+    default: return kernel_for<pj::M_RATES, 1>(G);
     }
 }
 
@@ -109,7 +117,7 @@ int configure(pyjac_mech* m, int mode_ix)
         // default: the largest group that still lets two blocks share an SM, else the
         // largest that fits at all
         for (int c : cands)
-            if ((size_t)make_layout(m->tb, c, jac).total * 8 * 2 + 2048 <= (size_t)m->smem_optin) { G = c; break; }
+            if (((size_t)make_layout(m->tb, c, jac).total * 8 + 1024) * 2 <= (size_t)m->smem_per_sm) { G = c; break; }
         if (!G)
             for (int c : cands)
                 if ((size_t)make_layout(m->tb, c, jac).total * 8 <= (size_t)m->smem_optin) { G = c; break; }
@@ -118,14 +126,22 @@ int configure(pyjac_mech* m, int mode_ix)
         return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
     const size_t bytes = (size_t)make_layout(m->tb, G, jac).total * 8;
     int threads = m->user_threads ? m->user_threads : 384;
-    threads = std::max(64, std::min(512, (threads + 31) / 32 * 32));
-    int bpsm = (int)((size_t)m->smem_optin / (bytes + 1024));
+    threads = std::max(32 * (G + 1), std::min(512, (threads + 31) / 32 * 32));
+    int bpsm = (int)((size_t)m->smem_per_sm / (bytes + 1024));
     bpsm = std::max(1, std::min(bpsm, 2048 / threads));
     if (m->user_bpsm) bpsm = std::max(1, std::min(bpsm, m->user_bpsm));
+    // register file: 64 K registers per SM; the 128-register build allows 512 threads per SM
+    int minb = 1;
+    if (mode_ix == 0 && bpsm >= 2 && threads <= 384) minb = 2;
+    if (minb == 1) bpsm = std::max(1, std::min(bpsm, 512 / threads));
+    else bpsm = std::min(bpsm, 768 / threads);
     m->G[mode_ix] = G;
     m->threads[mode_ix] = threads;
     m->blocks_per_sm[mode_ix] = bpsm;
-    CU(cudaFuncSetAttribute(kernel_ptr(mode_ix, G), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    m->minb[mode_ix] = minb;
+    const void* fn = kernel_ptr(mode_ix, G, minb);
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return PYJAC_OK;
 }
 
@@ -142,7 +158,7 @@ int launch(pyjac_mech* m, int mode_ix, const IO& io, cudaStream_t st)
     const long long groups = ((long long)io.n + G - 1) / G;
     const int grid = (int)std::min<long long>(groups, (long long)m->sm_count * m->blocks_per_sm[mode_ix]);
     void* args[3] = {(void*)&m->tb, (void*)&io, (void*)&L};
-    CU(cudaLaunchKernel(kernel_ptr(mode_ix, G), dim3(grid), dim3(m->threads[mode_ix]), args,
+    CU(cudaLaunchKernel(kernel_ptr(mode_ix, G, m->minb[mode_ix]), dim3(grid), dim3(m->threads[mode_ix]), args,
                         (size_t)L.total * 8, st));
     ++m->launches;
     return PYJAC_OK;
@@ -153,12 +169,13 @@ int upload(pyjac_mech* m, const void* blob, const char* name, const T** out, int
 {
     const pjt::Entry* e = pjt::find(blob, name);
     if (!e || e->dtype != dtype) return fail(PYJAC_EINVAL, std::string("table blob lacks ") + name);
-    const size_t bytes = std::max<size_t>((size_t)e->count * sizeof(T), 16);
+    const size_t payload = (size_t)e->count * pjt::elem_size(e->dtype);
+    const size_t bytes = std::max<size_t>((payload + 15) / 16 * 16, 64);
     void* d = nullptr;
     CU(cudaMalloc(&d, bytes));
     m->dev_allocs.push_back(d);
     CU(cudaMemset(d, 0, bytes));
-    CU(cudaMemcpy(d, (const char*)blob + e->offset, (size_t)e->count * sizeof(T), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d, (const char*)blob + e->offset, payload, cudaMemcpyHostToDevice));
     *out = (const T*)d;
     return PYJAC_OK;
 }
@@ -216,34 +233,46 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     CU(cudaSetDevice(device));
     const pjt::Entry* de = pjt::find(blob, "dims");
     const pjt::Entry* ce = pjt::find(blob, "cst");
-    if (!de || de->dtype != 1 || de->count < 12 || !ce || ce->dtype != 0 || ce->count < 2)
+    if (!de || de->dtype != 1 || de->count < 16 || !ce || ce->dtype != 0 || ce->count < 2)
         return fail(PYJAC_EINVAL, "table blob lacks dims / cst");
     const int* d = (const int*)((const char*)blob + de->offset);
     const double* c = (const double*)((const char*)blob + ce->offset);
     pyjac_mech* m = new pyjac_mech();
     m->device = device;
     Tables& t = m->tb;
-    t.nsp = d[0]; t.nr = d[1]; t.nrev = d[2]; t.npd = d[3]; t.nraw = d[4]; t.nnz = d[5];
-    t.ncon = d[6]; t.ncoef = d[7]; t.first_pm = d[8]; t.npm = d[9]; t.nred = d[10]; t.maxred = d[11];
-    t.ru = c[0]; t.ln_pa_ru = c[1];
+    t.nsp = d[0]; t.nr = d[1]; t.nrev = d[2]; t.npd = d[3]; t.nraw = d[4]; t.nsub = d[5];
+    t.ncon = d[6]; t.ncoef = d[7]; t.first_pm = d[8]; t.npm = d[9]; t.nsub_j = d[12]; t.nsplit = d[13];
+    t.nchunk = d[14]; t.zero_slot = d[15];
+    t.ru = c[0];
     int rc = PYJAC_OK;
 #define UP(field, name, type, code) if (!rc) rc = upload<type>(m, blob, name, &t.field, code)
     UP(sp_w, "sp_w", double, 0); UP(sp_iw, "sp_iw", double, 0); UP(sp_ruw, "sp_ruw", double, 0);
     UP(sp_tmid, "sp_tmid", double, 0); UP(sp_mwf, "sp_mwf", double, 0); UP(sp_nasa, "sp_nasa", double, 0);
-    UP(sp_seen, "sp_seen", int, 1);
-    UP(rx_orig, "rx_orig", int, 1); UP(rx_flags, "rx_flags", int, 1); UP(rx_rev_idx, "rx_rev_idx", int, 1);
-    UP(rx_pm_idx, "rx_pm_idx", int, 1); UP(rx_raw_base, "rx_raw_base", int, 1); UP(rx_slots, "rx_slots", int, 1);
-    UP(rx_arr, "rx_arr", double, 0); UP(pm_par, "pm_par", double, 0); UP(pm_sp, "pm_sp", int, 1);
+    UP(rx_rec, "rx_rec", int4, 1);
+    UP(pm_par, "pm_par", double, 0); UP(pm_sp, "pm_sp", int, 1);
     UP(pm_eff_off, "pm_eff_off", int, 1); UP(pm_eff_sp, "pm_eff_sp", int, 1); UP(pm_eff_am1, "pm_eff_am1", double, 0);
+    UP(chk_rx, "chk_rx", int, 1); UP(chk_nu, "chk_nu", double, 0); UP(sp_chk_off, "sp_chk_off", int, 1);
+    UP(con, "con", unsigned, 1); UP(sub_w, "sub_w", double, 0);
+    UP(cmb_off, "cmb_off", int, 1); UP(cmb_idx, "cmb_idx", int, 1);
+    UP(jmap, "jmap", unsigned short, 2);
+    if (!rc) {
+        const pjt::Entry* s_ = pjt::find(blob, "cls_sub");
+        const pjt::Entry* c_ = pjt::find(blob, "cls_con");
+        if (!s_ || !c_ || s_->dtype != 1 || c_->dtype != 1 || s_->count != 9 || c_->count != 8)
+            rc = fail(PYJAC_EINVAL, "table blob lacks cls_sub / cls_con");
+        else {
+            std::memcpy(t.cls_sub, (const char*)blob + s_->offset, sizeof(t.cls_sub));
+            std::memcpy(t.cls_con, (const char*)blob + c_->offset, sizeof(t.cls_con));
+        }
+    }
     UP(red_off, "red_off", int, 1); UP(red_rx, "red_rx", int, 1); UP(red_nu, "red_nu", double, 0);
-    UP(ent_kj, "ent_kj", int, 1); UP(ent_off, "ent_off", int, 1); UP(con, "con", int, 1);
-    UP(coef, "coef", double, 0); UP(jmap, "jmap", unsigned short, 2);
 #undef UP
     if (!rc) {
         cudaDeviceProp prop;
         cudaError_t e = cudaGetDeviceProperties(&prop, device);
         if (e != cudaSuccess) rc = fail(PYJAC_ECUDA, cudaGetErrorString(e));
-        else { m->sm_count = prop.multiProcessorCount; m->smem_optin = (int)prop.sharedMemPerBlockOptin; }
+        else { m->sm_count = prop.multiProcessorCount; m->smem_optin = (int)prop.sharedMemPerBlockOptin;
+               m->smem_per_sm = (int)prop.sharedMemPerMultiprocessor; }
     }
     if (rc) { pyjac_mech_destroy(m); return rc; }
     *out = m;

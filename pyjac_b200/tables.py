@@ -20,7 +20,8 @@ pyjac/core/rate_subs.py, cj = pyjac/core/create_jacobian.py).
 
 Table reference (all reaction-indexed arrays are in *kernel order*, see ``rx_orig``):
 
-  dims      int32[16]  NSP NR NREV NPD NRAW NNZ NCON NCOEF FIRST_PM NPM NRED MAXRED
+  dims      int32[16]  NSP NR NREV NPD NRAW NSUB NCON NCOEF FIRST_PM NPM NRED MAXRED
+                       NSUB_J NSPLIT NCHUNK ZERO_SLOT
   cst       f64[4]     RU ({:.8e}), ln(PA/RU)
   sp_*      per species (internal, moved-last order): w, iw (=1/W {:.16e}), ruw (=RU/W),
             tmid, mwf (=W_j/W_N), seen;  sp_nasa[k][branch][16] polynomial coefficients
@@ -29,10 +30,18 @@ Table reference (all reaction-indexed arrays are in *kernel order*, see ``rx_ori
             product species, NSP = empty slot), arr[4] = lnA, b, Ta, sum(nu)*ln(PA/RU)
   pm_*      per pressure-modified reaction (kernel index - FIRST_PM): collider list
             (eff_off/eff_sp/eff_am1 = alpha-1), sp (specific collider or -1), par[32]
-  red_*     per species CSR of (reaction, nu) for the species-side reductions
-  ent_*     sparse Jacobian entries (k, j) sorted by work, CSR into con (packed
-            src | coef_index<<16), coef f64[NCOEF]
-  jmap      uint16[(NSP-1)*NSP]: (j, k) -> entry slot (NNZ = always-zero slot)
+  rx_rec    the same per-reaction data as one 64-byte record (what the kernel loads)
+  red_*     per species CSR of (reaction, nu) for the species-side reductions;
+            chk_rx / chk_nu: the same lists cut into chunks of RCH pairs, sp_chk_off[k]
+  con       sparse sub-entries (<= SUBL contributions each, padded to 8 / 4 / 2 / 1 with
+            null contributions): classes J8 J4 J2 J1 T8 T4 T2 T1 in that order, class c holds
+            sub-entries [cls_sub[c], cls_sub[c+1]) and its contributions start at cls_con[c].
+            J: Jacobian entry (k, j), word = src | bf16(nu)<<16, result times sub_w (= W_k);
+            T: energy-equation row, word = src | reaction<<16 (coefficient = that reaction's
+            enthalpy change), result times -1/cp_avg
+  cmb_*     entries cut into several sub-entries: slot NSUB+t = sum of sub slots cmb_idx[...]
+  jmap      uint16[(NSP-1)*NSP]: (j, output row r) -> slot (ZERO_SLOT = always zero);
+            r = 0 is the energy-equation row, r >= 1 species r-1
 """
 from __future__ import annotations
 
@@ -49,11 +58,14 @@ F_REV, F_THD, F_PDEP, F_LOW, F_TROE, F_SRI = 1, 2, 4, 8, 16, 32
 F_PMT, F_PMT_INJ, F_TROE_T2, F_SRI5, F_SRI5_DT, F_NO_T = 64, 128, 256, 512, 1024, 2048
 F_EFFN1 = 4096         # third-body (non fall-off) reaction with a collider list: n' += 1
 F_WANT_PMT = 1 << 16   # the kernel stores pres_mod_temp as a raw value
+F_EFF_SLOTS = 1 << 17  # ... and pres_mod_temp * (alpha_j - 1) for each listed collider j
 NRE_SHIFT, NPR_SHIFT = 20, 24    # occupied reactant / product slots
 
 MAXS = 3               # concentration slots per side of a reaction
 UNROLL = 40            # CParams.Jacob_Unroll (cj:2651): scope of the stale pres_mod_temp quirk
 NPAR = 32
+RCH = 8                # (reaction, nu) pairs per species-reduction chunk
+SUBL = 8               # contributions per sparse sub-entry
 
 
 class UnsupportedMechanism(NotImplementedError):
@@ -149,22 +161,26 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     eff_off, eff_sp, eff_am1 = [0], [], []
     ln_pa_ru = math.log(PA / RU)
 
+    def eff_case(rx):
+        return bool(((rx.pdep and rx.pdep_sp is None) or rx.thd_body) and rx.thd_body_eff)
+
     # raw slot bookkeeping: for kernel reaction p the kernel stores, in this order,
     #   one value per occupied reactant slot whose species is not the last one,
     #   one value per occupied product slot (reversible only) likewise,
-    #   then pres_mod_temp if ``want_pmt``.
+    #   (collider list reactions) pres_mod_temp * (alpha_j - 1) per listed j != last, alpha_j != 1,
+    #   pres_mod_temp itself if ``want_pmt`` (specific collider, or source of a stale read).
     want_pmt = [False] * nr
     for i, rx in enumerate(reacs):
-        if has_pmt(rx):
-            listed = any(s != last and a != 1.0 for s, a in rx.thd_body_eff)
-            if listed or (rx.pdep_sp is not None and rx.pdep_sp != last):
-                want_pmt[i] = True
+        if has_pmt(rx) and not eff_case(rx) and rx.pdep_sp is not None and rx.pdep_sp != last:
+            want_pmt[i] = True
     for i, src in stale_src.items():
         if src is not None:
             want_pmt[src] = True
 
     raw_of_slot: List[List[int]] = [None] * nr      # per original reaction: raw index per slot / -1
+    raw_of_eff: List[Dict[int, int]] = [dict() for _ in range(nr)]
     raw_of_pmt = [-1] * nr
+    raw_rxn: List[int] = []                         # kernel reaction index of every raw slot
     nraw = 0
     for p, i in enumerate(order):
         rx = reacs[i]
@@ -199,6 +215,8 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
         pm_idx.append(pdep_reacs.index(i) if (rx.thd_body or rx.pdep) else -1)
         if want_pmt[i]:
             fl |= F_WANT_PMT
+        if eff_case(rx):
+            fl |= F_EFF_SLOTS
         fl |= sum(1 for s in rs if s != nsp) << NRE_SHIFT
         fl |= sum(1 for s in ps if s != nsp) << NPR_SHIFT
 
@@ -222,9 +240,15 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
             else:
                 ros.append(-1)
         raw_of_slot[i] = ros
+        if eff_case(rx):
+            for s, a in rx.thd_body_eff:
+                if a != 1.0 and s != last:
+                    raw_of_eff[i][s] = nraw
+                    nraw += 1
         if want_pmt[i]:
             raw_of_pmt[i] = nraw
             nraw += 1
+        raw_rxn += [p] * (nraw - raw_base[-1])
 
         if rx.thd_body or rx.pdep:
             m = p - first_pm
@@ -236,8 +260,7 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
                     eff_am1.append(a - 1.0)                                    # rs:1128-1130
             eff_off.append(len(eff_sp))
             pm_sp[m] = rx.pdep_sp if rx.pdep_sp is not None else -1
-            eff_case = bool(((rx.pdep and rx.pdep_sp is None) or rx.thd_body) and rx.thd_body_eff)
-            if eff_case:
+            if eff_case(rx):
                 par[4] = next((a for s, a in rx.thd_body_eff if s == last), 1.0)
                 par[5] = 1.0
             elif rx.pdep_sp == last and has_pmt(rx):
@@ -276,7 +299,21 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
         flags.append(fl)
     if not npm:
         eff_off = [0, 0]
+    if nraw >= 0xFFFF or nr >= 0xFFFF:
+        raise UnsupportedMechanism('mechanism too large for 16-bit sparse indices')
 
+    # one 64-byte record per reaction: 4 doubles (lnA, b, Ta, sum(nu) ln(PA/RU)) then 8 ints
+    # (flags, raw_base, slots packed two per int, rev_idx, pm_idx, original index)
+    rec = np.zeros((nr, 16), dtype=np.int32)
+    rec[:, :8] = arr.view(np.int32).reshape(nr, 8)
+    rec[:, 8] = flags
+    rec[:, 9] = raw_base
+    for a in range(3):
+        rec[:, 10 + a] = slots[:, 2 * a] | (slots[:, 2 * a + 1] << 16)
+    rec[:, 13] = rev_idx
+    rec[:, 14] = pm_idx
+    rec[:, 15] = order
+    T['rx_rec'] = rec.ravel()
     T['rx_orig'] = i32(order)
     T['rx_flags'] = i32(flags)
     T['rx_rev_idx'] = i32(rev_idx)
@@ -290,7 +327,8 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     T['pm_eff_sp'] = i32(eff_sp if eff_sp else [0])
     T['pm_eff_am1'] = f64(eff_am1 if eff_am1 else [0.0])
 
-    # ---------------- species-side reductions: wdot, T column, A, B share one CSR
+    # ---------------- species-side reductions: wdot, T column, A, B share one list per
+    # species, cut into chunks of RCH (reaction, nu) pairs (padded with nu = 0)
     red = [[] for _ in range(nsp)]
     for p, i in enumerate(order):
         rx = reacs[i]
@@ -304,6 +342,19 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     T['red_off'] = i32(red_off)
     T['red_rx'] = i32([p for lst in red for p, _ in lst] or [0])
     T['red_nu'] = f64([nu for lst in red for _, nu in lst] or [0.0])
+    chk_rx, chk_nu, sp_chk_off = [], [], [0]
+    for k in range(nsp):
+        lst = red[k]
+        for c0 in range(0, len(lst), RCH):
+            part = lst[c0:c0 + RCH]
+            part = part + [(0, 0.0)] * (RCH - len(part))
+            chk_rx += [p for p, _ in part]
+            chk_nu += [nu for _, nu in part]
+        sp_chk_off.append(len(chk_rx) // RCH)
+    nchunk = sp_chk_off[-1]
+    T['chk_rx'] = i32(chk_rx or [0] * RCH)
+    T['chk_nu'] = f64(chk_nu or [0.0] * RCH)
+    T['sp_chk_off'] = i32(sp_chk_off)
 
     # ---------------- sparse part: entry (k, j) <- sum coef * raw[src]
     contrib: Dict[tuple, list] = {}
@@ -316,43 +367,124 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
         part = [(k, rx.net_nu(k)) for k in sorted(set(rx.reac + rx.prod)) if rx.net_nu(k) != 0]
         p = pos_of[i]
         sl = slots[p]
-        eff_case = bool(((rx.pdep and rx.pdep_sp is None) or rx.thd_body) and rx.thd_body_eff)
         for k, nu in part:
             for a in range(2 * MAXS):
                 if raw_of_slot[i][a] >= 0:
                     add(k, int(sl[a]), raw_of_slot[i][a], nu)                  # cj:410-448
             if has_pmt(rx):
-                if eff_case:
-                    for s, al in rx.thd_body_eff:
-                        if s != last:
-                            add(k, s, raw_of_pmt[i], nu * (al - 1.0))          # cj:379-400
+                if eff_case(rx):
+                    for s, src in raw_of_eff[i].items():
+                        add(k, s, src, nu)                                     # cj:379-400
                 elif rx.pdep_sp is not None and rx.pdep_sp != last:
                     add(k, rx.pdep_sp, raw_of_pmt[i], nu)                      # cj:401-404
             elif i in stale_src and stale_src[i] is not None:
                 add(k, 0, raw_of_pmt[stale_src[i]], nu)
-    ents = sorted(contrib, key=lambda kj: (-len(contrib[kj]), kj[1], kj[0]))
-    nnz = len(ents)
-    if nnz >= 0xFFFF or nraw >= 0xFFFF:
-        raise UnsupportedMechanism('mechanism too large for 16-bit sparse indices')
-    coef_ix: Dict[float, int] = {}
-    con, ent_off = [], [0]
-    for kj in ents:
-        for src, c in contrib[kj]:
-            ci = coef_ix.setdefault(c, len(coef_ix))
-            con.append(src | (ci << 16))
-        ent_off.append(len(con))
-    if len(coef_ix) >= 0x7FFF:
-        raise UnsupportedMechanism('too many distinct sparse coefficients')
-    T['ent_kj'] = i32([k | (j << 16) for k, j in ents] or [0])
-    T['ent_off'] = i32(ent_off)
-    T['con'] = i32(con or [0])
-    T['coef'] = f64(list(coef_ix) or [0.0])
-    jmap = np.full((nsp - 1, nsp), nnz, dtype=np.uint16)
-    for e, (k, j) in enumerate(ents):
-        jmap[j, k] = e
+    # energy-equation row: sum_k h_k W_k S_kj = sum over raw values of column j of
+    # dH_i * raw  (dH_i = sum_k nu_ki h_k W_k, evaluated per state by the kernel), so its
+    # contributions carry the *reaction* whose dH multiplies the raw value
+    tcontrib: Dict[int, list] = {}
+    for i, rx in enumerate(reacs):
+        p = pos_of[i]
+        sl = slots[p]
+        if not any(rx.net_nu(k) != 0 for k in set(rx.reac + rx.prod)):
+            continue
+        for a in range(2 * MAXS):
+            if raw_of_slot[i][a] >= 0:
+                tcontrib.setdefault(int(sl[a]), []).append((raw_of_slot[i][a], p))
+        if has_pmt(rx):
+            if eff_case(rx):
+                for s, src in raw_of_eff[i].items():
+                    tcontrib.setdefault(s, []).append((src, p))
+            elif rx.pdep_sp is not None and rx.pdep_sp != last:
+                tcontrib.setdefault(rx.pdep_sp, []).append((raw_of_pmt[i], p))
+        elif i in stale_src and stale_src[i] is not None:
+            tcontrib.setdefault(0, []).append((raw_of_pmt[stale_src[i]], p))
+
+    # sub-entries: at most SUBL contributions each; an entry cut into several sub-entries is
+    # summed by a short combine list afterwards.  Each sub-entry is padded to a power-of-two
+    # length (its class: 8, 4, 2 or 1 contributions) with null contributions that read the
+    # always-zero raw slot ``nraw``, so that the kernel runs fixed-length unrolled loops.
+    # kind 0: Jacobian entry, contribution = src | bf16(nu) << 16, result scaled by W_k;
+    # kind 1: energy row, contribution = src | reaction << 16 (coefficient = that reaction's
+    # enthalpy change), result scaled by -1/cp_avg.
+    def bf16_bits(c: float) -> int:
+        bits = int(np.float32(c).view(np.uint32))
+        if bits & 0xFFFF:
+            raise UnsupportedMechanism('stoichiometric coefficient %r not representable' % c)
+        return bits >> 16
+
+    def cls_len(n: int) -> int:
+        return 1 if n <= 1 else (2 if n <= 2 else (4 if n <= 4 else 8))
+
+    subs = []          # (kind, class length, owner, [packed contributions])
+    for kj, lst in contrib.items():
+        if kj[0] == last:
+            continue   # the last species has no Jacobian row; its enthalpy enters through dH
+        packed = [src | (bf16_bits(c) << 16) for src, c in lst]
+        for c0 in range(0, len(packed), SUBL):
+            piece = packed[c0:c0 + SUBL]
+            subs.append((0, cls_len(len(piece)), ('J',) + kj, piece))
+    for j, lst in tcontrib.items():
+        packed = [src | (p << 16) for src, p in lst]
+        for c0 in range(0, len(packed), SUBL):
+            piece = packed[c0:c0 + SUBL]
+            subs.append((1, cls_len(len(piece)), ('T', j), piece))
+    subs.sort(key=lambda s: (s[0], -s[1], s[2]))
+    nsub = len(subs)
+    nsub_j = sum(1 for s in subs if s[0] == 0)
+    by_owner: Dict[tuple, list] = {}
+    for ix, (_, _, owner, _) in enumerate(subs):
+        by_owner.setdefault(owner, []).append(ix)
+    split = [o for o, lst in by_owner.items() if len(lst) > 1]
+    nsplit = len(split)
+    zero_slot = nsub + nsplit
+    if zero_slot >= 0xFFFF:
+        raise UnsupportedMechanism('too many sparse Jacobian entries for 16-bit slots')
+    final_slot = {}
+    cmb_off, cmb_idx = [0], []
+    for t, o in enumerate(split):
+        final_slot[o] = nsub + t
+        cmb_idx += by_owner[o]
+        cmb_off.append(len(cmb_idx))
+    for o, lst in by_owner.items():
+        if len(lst) == 1:
+            final_slot[o] = lst[0]
+    con = []
+    cls_sub = [0] * 9      # sub index where each of the 8 (kind, length) classes starts
+    cls_con = [0] * 8      # offset of that class's first contribution in ``con``
+    sub_w = []
+    order_cls = [(0, 8), (0, 4), (0, 2), (0, 1), (1, 8), (1, 4), (1, 2), (1, 1)]
+    ix = 0
+    for c, (kind, ln) in enumerate(order_cls):
+        while len(con) % ln:
+            con.append(nraw)       # keep each class aligned to its own vector width
+        cls_sub[c] = ix
+        cls_con[c] = len(con)
+        while ix < nsub and (subs[ix][0], subs[ix][1]) == (kind, ln):
+            piece = subs[ix][3]
+            con += piece + [nraw] * (ln - len(piece))
+            sub_w.append(specs[subs[ix][2][1]].mw if kind == 0 else 0.0)
+            ix += 1
+    assert ix == nsub
+    cls_sub[8] = nsub
+    T['cls_sub'] = i32(cls_sub)
+    T['cls_con'] = i32(cls_con)
+    T['con'] = np.asarray(con + [nraw] * 8, dtype=np.uint32).view(np.int32)
+    T['sub_w'] = f64(sub_w or [0.0])
+    T['cmb_off'] = i32(cmb_off)
+    T['cmb_idx'] = i32(cmb_idx or [0])
+    # jmap[j][r]: output row r of column j+1 -> slot.  r = 0 is the energy-equation row,
+    # r >= 1 is species r-1.
+    jmap = np.full((nsp - 1, nsp), zero_slot, dtype=np.uint16)
+    for o, slot in final_slot.items():
+        if o[0] == 'J':
+            jmap[o[2], o[1] + 1] = slot
+        else:
+            jmap[o[1], 0] = slot
     T['jmap'] = jmap.ravel()
 
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
-    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, nnz, len(con), len(coef_ix),
-                     first_pm, npm, red_off[-1], max(len(l) for l in red), 0, 0, 0, 0])
+    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, nsub, len(con), 0,
+                     first_pm, npm, red_off[-1], max(len(l) for l in red),
+                     nsub_j, nsplit, nchunk, zero_slot])
     return T

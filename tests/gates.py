@@ -4,7 +4,10 @@ Near-equilibrium states make *net* rates pure cancellation noise (the reference 
 with -fassociative-math differs from itself by x860 elementwise in dydt), so the gates scale
 the error by the quantity that sets the rounding level:
 
-  jac         |d| <= RTOL * max_i |ref[i, j]|              per column j, per state
+  jac         |d| <= RTOL * max_i |ref[i, j]|              per column j, per state; the
+              energy-equation row jac[0, j] = -sum_k h_k jac[k, j] / cp_avg + ... inherits the
+              species rows' rounding multiplied by h_k / cp_avg (~1e4 K), so its scale is
+              max(colmax, sum_k |h_k ref[k, j]| / cp_avg) when the states are supplied
   spec_rates  |d| <= RTOL * sum_i |nu_ki| (|qf_i| + |qr_i|) |pm_i|        (gross rate)
   dydt[k+1]   same, times W_k / rho;   dydt[0] scaled by sum_k |h_k W_k| gross_k / (rho cp_avg)
   fwd, rev, pres_mod   elementwise rtol RTOL
@@ -46,12 +49,19 @@ def gross_rates(mech, fwd, rev, pres_mod):
     return g
 
 
-def check_jac(new, ref, nsp, what='jac'):
+def check_jac(new, ref, nsp, what='jac', mech=None, y=None):
     a = new.reshape(-1, nsp, nsp)        # [state, col, row]
     b = ref.reshape(-1, nsp, nsp)
     assert np.isfinite(a).all(), what + ': non-finite values'
     colmax = np.abs(b).max(axis=2, keepdims=True)
-    err = np.abs(a - b) / (colmax + 1e-300)
+    scale = np.broadcast_to(colmax, b.shape).copy()
+    if mech is not None:
+        cp, h = _thermo(mech, y[:, 0])
+        Y = np.concatenate([y[:, 1:], 1.0 - y[:, 1:].sum(axis=1, keepdims=True)], axis=1)
+        cp_avg = (Y * cp).sum(axis=1)
+        row0 = (np.abs(h[:, None, :nsp - 1]) * np.abs(b[:, :, 1:])).sum(axis=2) / cp_avg[:, None]
+        scale[:, :, 0] = np.maximum(scale[:, :, 0], row0)
+    err = np.abs(a - b) / (scale + 1e-300)
     worst = float(err.max())
     assert worst <= RTOL, '%s: |d|/colmax = %.3e at %s' % (what, worst, np.unravel_index(err.argmax(), err.shape))
     rel = np.abs(a - b) / (np.abs(b) + 1e-300)

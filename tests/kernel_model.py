@@ -16,7 +16,7 @@ LN10 = np.log(10.0)
 def evaluate(Tb, P, y):
     """Returns dict(conc, fwd, rev, pres_mod, spec_rates, dydt, jac); layouts as the oracle."""
     d = Tb['dims']
-    nsp, nr, nrev, npd, nraw, nnz = (int(v) for v in d[:6])
+    nsp, nr, nrev, npd, nraw = (int(v) for v in d[:5])
     first_pm = int(d[8])
     RU8, ln_pa_ru = Tb['cst'][:2]
     n = y.shape[0]
@@ -53,6 +53,9 @@ def evaluate(Tb, P, y):
     par_all = Tb['pm_par'].reshape(-1, tb.NPAR)
     raw = np.zeros((n, nraw + 1))
     R4 = np.zeros((nr, 4, n))
+    RH = np.zeros((nr, n))
+    hw = np.zeros((n, nsp + 1))
+    hw[:, :nsp] = h * w[None, :]
     fwd = np.zeros((n, nr)); rev = np.zeros((n, max(nrev, 1))); pres_mod = np.zeros((n, max(npd, 1)))
     lg10 = lambda x: np.log10(np.maximum(x, 1.0e-300))
     for p in range(nr):
@@ -193,44 +196,71 @@ def evaluate(Tb, P, y):
                 else:
                     raw[:, rb] = dv
                     rb += 1
+        if fl & tb.F_EFF_SLOTS:
+            for e in range(Tb['pm_eff_off'][mi], Tb['pm_eff_off'][mi + 1]):
+                if Tb['pm_eff_sp'][e] != last:
+                    raw[:, rb] = pmt * Tb['pm_eff_am1'][e]
+                    rb += 1
         if fl & tb.F_WANT_PMT:
             raw[:, rb] = pmt
         R4[p, 0], R4[p, 1], R4[p, 2], R4[p, 3] = net * PM, tT, X1, X2
+        RH[p] = (hw[:, s[3]] + hw[:, s[4]] + hw[:, s[5]]) - (hw[:, s[0]] + hw[:, s[1]] + hw[:, s[2]])
 
-    # --- species reductions
+    # --- species reductions (chunked two-level, as the kernel does)
+    nchunk = int(d[14])
+    part = np.zeros((nchunk, 4, n))
+    crx, cnu = Tb['chk_rx'].reshape(-1, tb.RCH), Tb['chk_nu'].reshape(-1, tb.RCH)
+    for c in range(nchunk):
+        for e in range(tb.RCH):
+            part[c] += cnu[c, e] * R4[crx[c, e]]
     wdot = np.zeros((n, nsp)); tcol = np.zeros((n, nsp)); Ak = np.zeros((n, nsp)); Bk = np.zeros((n, nsp))
     for k in range(nsp):
-        for e in range(Tb['red_off'][k], Tb['red_off'][k + 1]):
-            p_, nu = Tb['red_rx'][e], Tb['red_nu'][e]
-            wdot[:, k] += nu * R4[p_, 0]; tcol[:, k] += nu * R4[p_, 1]
-            Ak[:, k] += nu * R4[p_, 2]; Bk[:, k] += nu * R4[p_, 3]
+        for c in range(Tb['sp_chk_off'][k], Tb['sp_chk_off'][k + 1]):
+            wdot[:, k] += part[c, 0]; tcol[:, k] += part[c, 1]; Ak[:, k] += part[c, 2]; Bk[:, k] += part[c, 3]
     comp = wdot * (mw_avg * rho_inv)[:, None]
-    Ak += comp
-    Bk -= comp
+    Ak = w[None, :] * (Ak + comp)
+    Bk = w[None, :] * (Bk - comp)
+    tc = w[None, :] * tcol
 
-    # --- sparse gather
-    sval = np.zeros((n, nnz + 1))
-    for e in range(nnz):
-        for cidx in range(Tb['ent_off'][e], Tb['ent_off'][e + 1]):
-            cc = int(Tb['con'][cidx])
-            sval[:, e] += Tb['coef'][cc >> 16] * raw[:, cc & 0xFFFF]
+    # --- sparse gather: class-padded sub-entries, then the combine lists
+    nsub, nsub_j, nsplit, zero_slot = int(d[5]), int(d[12]), int(d[13]), int(d[15])
+    sval = np.zeros((n, zero_slot + 1))
+    con = Tb['con'].view(np.uint32)
+    raw[:, nraw] = 0.0
+    wt = 1.0 / cp_avg
+    lens = [8, 4, 2, 1, 8, 4, 2, 1]
+    for c in range(8):
+        for e in range(Tb['cls_sub'][c], Tb['cls_sub'][c + 1]):
+            o = Tb['cls_con'][c] + (e - Tb['cls_sub'][c]) * lens[c]
+            for cc in con[o:o + lens[c]]:
+                cc = int(cc)
+                if c < 4:
+                    cf = float(np.uint32(cc & 0xFFFF0000).view(np.float32))
+                    sval[:, e] += cf * raw[:, cc & 0xFFFF]
+                else:
+                    sval[:, e] += RH[cc >> 16] * raw[:, cc & 0xFFFF]
+            sval[:, e] *= Tb['sub_w'][e] if c < 4 else -wt
+    for t in range(nsplit):
+        for cidx in range(Tb['cmb_off'][t], Tb['cmb_off'][t + 1]):
+            sval[:, nsub + t] += sval[:, Tb['cmb_idx'][cidx]]
 
-    # --- assembly
+    # --- assembly: output row r of column j+1 is iw_j (rowA[r] + rowB[r] mwf_j + sval[jmap[j][r]])
     jmap = Tb['jmap'].reshape(nsp - 1, nsp)
     jac = np.zeros((n, nsp, nsp))          # [state, col, row]
-    hw = h * w[None, :]
-    H1 = (hw * wdot).sum(axis=1)
-    wt = 1.0 / cp_avg
-    jt = 1.0 / (rho * cp_avg * cp_avg)
+    H1 = (hw[:, :nsp] * wdot).sum(axis=1)
+    HA = (h * Ak).sum(axis=1)
+    HB = (h * Bk).sum(axis=1)
+    HT = (h * tc).sum(axis=1)
+    SCP = (cp * w[None, :] * wdot).sum(axis=1)
+    XT = H1 / (rho * cp_avg * cp_avg)
+    rowA = np.concatenate([(-wt * HA)[:, None], Ak[:, :last]], axis=1)
+    rowB = np.concatenate([(-wt * HB)[:, None], Bk[:, :last]], axis=1)
     for j in range(nsp - 1):
-        v = w[None, :] * iw[j] * (Ak + Bk * mwf[j] + sval[:, jmap[j]])
-        v[:, Tb['sp_seen'] == 0] = 0.0
-        jac[:, j + 1, 1:] = v[:, :last]
-        jac[:, j + 1, 0] = -wt * (h * v).sum(axis=1) + jt * (cp[:, j] - cp[:, last]) * H1
-    tc = w[None, :] * tcol
+        v = iw[j] * (rowA + rowB * mwf[j] + sval[:, jmap[j]])
+        v[:, 0] += XT * (cp[:, j] - cp[:, last])
+        jac[:, j + 1, :] = v
     jac[:, 0, 1:] = tc[:, :last]
-    s0 = (wdot * w[None, :] * (-wdcp[:, None] * h / cp_avg[:, None] + cp)).sum(axis=1) \
-        + ((tc * h).sum(axis=1)) * rho
+    s0 = -wdcp / cp_avg * H1 + SCP + HT * rho
     jac[:, 0, 0] = -s0 / (rho * cp_avg)
 
     dydt = np.empty((n, nsp))

@@ -52,7 +52,7 @@ def test_device_api_vs_reference_golden(torch, golden_dir, mech_file, npz, layou
     new = dict(zip(KEYS + ['dydt'], host))
     gates.check_rates(mech, g['P'], g['y'], new, g, mech_file)
     gates.check_dydt(mech, g['y'], dy2, g, mech_file + ' dydt kernel')
-    worst, frac = gates.check_jac(np.ascontiguousarray(jac), g['jac'], mech.NSP, mech_file)
+    worst, frac = gates.check_jac(np.ascontiguousarray(jac), g['jac'], mech.NSP, mech_file, mech, g['y'])
     assert frac > 0.97
     ev.close()
 
@@ -83,7 +83,7 @@ def test_against_oracle_on_synthetic_states(torch, golden_dir):
     P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
     new = dict(zip(KEYS + ['dydt'], [o.cpu().numpy() for o in ev.rates(P, y, want_dy=True)]))
     gates.check_rates(mech, P_h, y_h, new, ref, 'gri30 synthetic')
-    worst, frac = gates.check_jac(ev.eval_jacob(P, y).cpu().numpy(), ref_jac, mech.NSP)
+    worst, frac = gates.check_jac(ev.eval_jacob(P, y).cpu().numpy(), ref_jac, mech.NSP, 'gri30 synthetic', mech, y_h)
     assert frac > 0.999, frac
     ev.close()
 
@@ -101,7 +101,7 @@ def test_host_batch_api(torch, golden_dir):
     mech, ev = _evaluator(golden_dir, 'h2o2_n2.inp')
     g = np.load(os.path.join(golden_dir, 'h2o2_pasr.npz'))
     jac = ev.eval_jacob_host(g['P'], g['y'])
-    gates.check_jac(jac, g['jac'], mech.NSP)
+    gates.check_jac(jac, g['jac'], mech.NSP, 'host api', mech, g['y'])
     dy = ev.dydt_host(g['P'], g['y'])
     gates.check_dydt(mech, g['y'], dy, g)
     # device and host entry points run the same kernel

@@ -23,7 +23,7 @@ def test_model_matches_reference_golden(golden_dir, mech_file, npz, sl):
     g = {k: v[sl] for k, v in np.load(os.path.join(golden_dir, npz)).items()}
     out = kernel_model.evaluate(T, g['P'], g['y'])
     gates.check_rates(mech, g['P'], g['y'], out, g, mech_file)
-    worst, frac = gates.check_jac(out['jac'], g['jac'], mech.NSP, mech_file)
+    worst, frac = gates.check_jac(out['jac'], g['jac'], mech.NSP, mech_file, mech, g['y'])
     assert frac > 0.97
 
 
@@ -37,15 +37,26 @@ def test_tables_reject_unsupported(golden_dir):
 def test_table_structure(golden_dir):
     mech = Mechanism.from_chemkin(os.path.join(golden_dir, 'gri30_syn.inp'))
     T = tables.build(mech)
-    nsp, nr, nrev, npd, nraw, nnz, ncon = (int(v) for v in T['dims'][:7])
+    nsp, nr, nrev, npd, nraw = (int(v) for v in T['dims'][:5])
     assert (nsp, nr, nrev, npd) == (mech.NSP, mech.FWD_RATES, mech.REV_RATES, mech.PRES_MOD_RATES)
     assert sorted(T['rx_orig']) == list(range(nr))
     # pressure-modified reactions are the tail of the kernel order
     fl = T['rx_flags']
     pm = (fl & (tables.F_THD | tables.F_PDEP)) != 0
     assert not pm[:int(T['dims'][8])].any() and pm[int(T['dims'][8]):].all()
-    # sparse entries sorted by decreasing work, every contribution points at a raw slot
-    cnt = np.diff(T['ent_off'])
-    assert (cnt[:-1] >= cnt[1:]).all() and T['ent_off'][-1] == ncon
-    assert ((T['con'] & 0xFFFF) < nraw).all() and ((T['con'] >> 16) < int(T['dims'][7])).all()
-    assert T['jmap'].max() == nnz and (np.sort(T['jmap'][T['jmap'] < nnz]) == np.arange(nnz)).all()
+    # sparse sub-entries: eight (kind, padded length) classes, every contribution in range
+    nsub, ncon, nsub_j, nsplit, zero = (int(T['dims'][i]) for i in (5, 6, 12, 13, 15))
+    cs, cc = T['cls_sub'], T['cls_con']
+    lens = [8, 4, 2, 1, 8, 4, 2, 1]
+    assert cs[0] == 0 and cs[4] == nsub_j and cs[8] == nsub and (np.diff(cs) >= 0).all()
+    for c in range(8):
+        assert cc[c] % lens[c] == 0
+        assert cc[c] + (cs[c + 1] - cs[c]) * lens[c] <= (cc[c + 1] if c < 7 else ncon)
+    con = T['con'].view(np.uint32)
+    assert ((con & 0xFFFF) <= nraw).all()
+    assert ((con[cc[4]:ncon] >> 16) < nr).all()
+    assert zero == nsub + nsplit and T['jmap'].max() == zero
+    assert (T['cmb_idx'] < nsub).all() and len(T['cmb_off']) == nsplit + 1
+    # every species-reduction chunk belongs to one species and is padded with nu = 0
+    assert len(T['chk_rx']) == int(T['dims'][14]) * tables.RCH
+    assert T['sp_chk_off'][-1] == int(T['dims'][14])
