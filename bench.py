@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched eval_jacob, states/s (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One *step* = one pass of eval_jacob over one batch of synthetic states of the GRI-Mech-3.0-
+shaped mechanism (53 species / 325 reactions; the real GRI file is not available offline, see
+DESIGN.md).  With N > 1 (launched by torchrun, one rank per GPU) every rank evaluates its own
+batch of the same size -- the state batch is partitioned, there is no data-path collective --
+and `value` is the states all ranks processed divided by the max-over-ranks device time.
+
+value        device-resident: states and Jacobians stay in HBM, CUDA events around K launches
+e2e          the same metric through the host-pointer C-ABI call (pyjac_eval_jacob_host) with
+             pinned HOST buffers: H2D of the states and D2H of every Jacobian inside the timing
+roofline     HBM bound; algorithmic bytes = 8*NSP^2 + 8*(NSP+1) per state
+cpu_baseline the reference's own generated C (oracle/_ref, OpenMP over states, all host
+             threads) on a bounded sample of the same states; rank 0, N = 1 only
+
+--impl reference times that generated C alone (the reference has no working sm_100 GPU path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MECH_FILE = os.path.join(ROOT, 'tests', 'golden', 'gri30_syn.inp')
+REF_NAME = 'gri30'
+WORKLOAD = 'GRI-3.0-shaped synthetic mechanism (53 sp / 325 rxn), eval_jacob, fp64'
+METRIC = 'eval_jacob states/s'
+UNIT = 'states/s'
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(nsp: int):
+    """dram bytes per state from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            return json.load(fh).get('gri30_dram_bytes_per_state')
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1 and len(r) >= 7] or \
+               [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return None
+        sm = []
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+            except ValueError:
+                pass
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({nm for r in rows for nm, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        try:
+            smax = float(rows[0][1])
+        except ValueError:
+            smax = None
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': smax,
+                'reasons': reasons, 'samples': len(rows)}
+
+
+def load_states(nsp: int, n: int, seed: int):
+    from pyjac_b200.states import synthetic_states
+    return synthetic_states(nsp, n, seed=seed)
+
+
+def cpu_reference(mech):
+    """The CPU checker used as the reported baseline: the reference's generated C when
+    oracle/_ref holds it, else the oracle port."""
+    from oracle.oracle import Oracle, RefLib
+    if RefLib.available(REF_NAME):
+        return RefLib(REF_NAME), 'reference'
+    return Oracle(mech), 'port'
+
+
+def time_cpu(ref, kind, P, y, threads, target_s):
+    """states/s of the CPU implementation on a bounded sample sized for ~target_s seconds."""
+    def run(n):
+        t = time.perf_counter()
+        if kind == 'reference':
+            ref.eval_jacob(P[:n], y[:n], nthreads=threads, keep=False)
+        else:
+            ref.eval_jacob(P[:n], y[:n], nthreads=threads)
+        return time.perf_counter() - t
+    probe = min(len(P), 512 * threads)
+    run(probe)                                  # warm caches / OpenMP pool
+    rate = probe / run(probe)
+    n = int(max(probe, min(len(P), rate * target_s)))
+    dt = run(n)
+    return n / dt, n, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from pyjac_b200.mechanism import Mechanism
+    mech = Mechanism.from_chemkin(MECH_FILE)
+    threads = host_threads()
+    ref, kind = cpu_reference(mech)
+    P, y = load_states(mech.NSP, 1 << 18, seed=0)
+    # bounded sample per step: ~2 s of CPU work
+    probe = min(len(P), 512 * threads)
+    ref.eval_jacob(P[:probe], y[:probe], nthreads=threads, **({'keep': False} if kind == 'reference' else {}))
+    t = time.perf_counter()
+    ref.eval_jacob(P[:probe], y[:probe], nthreads=threads, **({'keep': False} if kind == 'reference' else {}))
+    rate = probe / (time.perf_counter() - t)
+    n = int(max(probe, min(len(P), rate * 2.0)))
+    kw = {'keep': False} if kind == 'reference' else {}
+    for _ in range(args.warmup):
+        ref.eval_jacob(P[:n], y[:n], nthreads=threads, **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.eval_jacob(P[:n], y[:n], nthreads=threads, **kw)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = '%d states/step of the seed-0 synthetic batch, %d OpenMP threads' % (n, threads)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'states_per_step': n, 'path':
+                   "reference's generated C (pyjac --lang c, gcc -std=c99 -O3 -mtune=native -fopenmp) on host cores"
+                   if kind == 'reference' else 'oracle port (oracle/pyjac_oracle.c) on host cores'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pyjac_b200.evaluator import Evaluator
+    from pyjac_b200.mechanism import Mechanism
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- pyjac_b200 has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    mech = Mechanism.from_chemkin(MECH_FILE)
+    nsp = mech.NSP
+    n = args.states
+    bytes_per_state = 8 * nsp * nsp + 8 * (nsp + 1)
+    ev = Evaluator(mech, local_rank)
+    # every rank gets its own shard of the (n * world)-state batch: seed = rank
+    P_h, y_h = load_states(nsp, n, seed=rank)
+    P = torch.tensor(P_h, device=dev)
+    y = torch.tensor(y_h, device=dev)
+    jac = torch.empty((n, nsp * nsp), dtype=torch.float64, device=dev)
+
+    # ---- device-resident timing -------------------------------------------------------
+    for _ in range(args.warmup):
+        ev.eval_jacob(P, y, jac)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = ev.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        ev.eval_jacob(P, y, jac)
+    e1.record()
+    barrier()
+    w1 = time.time()
+    launches = ev.launches - l0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(w0, w1) if sampler else None
+    ms_per_step = ms / args.steps
+    value = n * world * args.steps / (ms * 1e-3)
+    kernel_ms = e0.elapsed_time(e1) / max(launches, 1)         # this rank's average launch
+    achieved = bytes_per_state * n / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    traffic = ncu_traffic(nsp)
+
+    # ---- end to end through the host-pointer C-ABI call -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        n_e = n
+        need = n_e * nsp * nsp * 8
+        avail = psutil.virtual_memory().available // max(1, min(world, torch.cuda.device_count()))
+        while n_e > 4096 and need * 1.5 > avail:
+            n_e //= 2
+            need = n_e * nsp * nsp * 8
+        yp = torch.empty((n_e, nsp), dtype=torch.float64, pin_memory=True)
+        Pp = torch.empty((n_e,), dtype=torch.float64, pin_memory=True)
+        jp = torch.empty((n_e, nsp * nsp), dtype=torch.float64, pin_memory=True)
+        yp.numpy()[:] = y_h[:n_e]
+        Pp.numpy()[:] = P_h[:n_e]
+        y_np, P_np, j_np = yp.numpy(), Pp.numpy(), jp.numpy()
+        e_steps = max(1, min(args.steps, args.e2e_steps))
+        ev.eval_jacob_host(P_np, y_np, j_np)                       # warm-up (staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            ev.eval_jacob_host(P_np, y_np, j_np)                   # synchronous: returns after D2H
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        # spot-check that the host path delivered the same Jacobians as the device path
+        if n_e == n:
+            k = min(n, 64)
+            assert np.array_equal(j_np[:k], jac[:k].cpu().numpy()), 'host / device API mismatch'
+        e2e = {'value': n_e * world * e_steps / dt, 'unit': UNIT,
+               'h2d_bytes_per_step': n_e * (nsp + 1) * 8, 'd2h_bytes_per_step': n_e * nsp * nsp * 8,
+               'states_per_step': n_e, 'steps': e_steps,
+               'api': 'pyjac_eval_jacob_host (pinned host rows in, pinned host Jacobians out)'}
+        del yp, Pp, jp
+
+    # ---- CPU baseline (rank 0, single GPU runs only) ----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = host_threads()
+        ref, kind = cpu_reference(mech)
+        v, ns, dt = time_cpu(ref, kind, P_h, y_h, threads, args.cpu_seconds)
+        cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': kind,
+               'sample': 'first %d states of the same batch, %.1f s, %d OpenMP threads' % (ns, dt, threads)}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'states_per_gpu': n, 'global_states': n * world,
+                       'jacobian_bytes_per_gpu': n * nsp * nsp * 8,
+                       'l2': 'inputs (%.0f MB) and outputs (%.1f GB) per step exceed the 126 MB L2'
+                             % (n * (nsp + 1) * 8 / 1e6, n * nsp * nsp * 8 / 1e9),
+                       'layout': 'row per state in, one column-major NSPxNSP Jacobian per state out',
+                       'parallelism': 'state batch sharded over %d GPU(s), no collective' % world},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': None if traffic is None else traffic * n,
+                         'peak_source': peak_src, 'bytes_per_state': bytes_per_state,
+                         'kernel': 'pj::k_eval<G, M_JAC, MINB>', 'kernel_ms': kernel_ms},
+            'e2e': e2e, 'cpu_baseline': cpu, 'gpu_launches': launches, 'clocks': clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--states', type=int, default=1 << 20, help='states per GPU per step')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--cpu-seconds', type=float, default=10.0)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world == 1 and args.gpus > 1 and args.impl == 'ours':
+        # not launched by torchrun: re-exec under it so that one rank drives each GPU
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+               '--nproc-per-node', str(args.gpus), '--master-addr', '127.0.0.1',
+               '--master-port', str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -65,9 +65,16 @@ def test_launch_shapes_give_identical_results(torch, golden_dir, G, threads):
     P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
     ref = ev.eval_jacob(P, y).cpu().numpy()
     ev.tune(G, threads, 0)
+    # Different launch shapes are different template instances: the compiler may contract
+    # multiply-adds differently, so across shapes the results agree to rounding, not bitwise.
+    full = ev.eval_jacob(P, y).cpu().numpy()
+    a, b = full.reshape(-1, mech.NSP, mech.NSP), ref.reshape(-1, mech.NSP, mech.NSP)
+    err = np.abs(a - b) / (np.abs(b).max(axis=2, keepdims=True) + 1e-300)
+    assert err.max() <= 1e-11, (G, threads, err.max())
+    # Within one launch shape the result of a state does not depend on the batch around it.
     for n in (203, 1, 2, 3, 5, 64):
         out = ev.eval_jacob(P[:n].contiguous(), y[:n].contiguous()).cpu().numpy()
-        assert np.array_equal(out, ref[:n]), (G, threads, n)
+        assert np.array_equal(out, full[:n]), (G, threads, n)
     ev.close()
 
 
