@@ -6,25 +6,29 @@
 // eval_rxn_rates (:254-876), get_rxn_pres_mod (:879-1294), eval_spec_rates (:1297-1542),
 // eval_h / eval_cp (:1806-2086), dydt (:2171-2335) and eval_jacob
 // (create_jacobian.py:2189-3298).  The arithmetic is regrouped (see tables.py) so that
-// each Jacobian element is produced and stored exactly once.  A persistent thread block
-// walks over groups of G states; per group, separated by block barriers:
+// each Jacobian element is produced and stored exactly once.
 //
-//   A   one warp per state: mass fractions -> concentrations and NASA-7 thermo; per species
-//       {C_k, B_k (Gibbs term of Kc), dB_k/dT, h_k W_k} as one 32-byte record in shared
-//       memory (runs for the *next* group while phase E stores the current one)
-//   B   one thread per reaction (x G states; one thread per (reaction, state) for the
-//       pressure-dependent ones): kf, kr = exp(ln kf - sum nu B - ...), rates of progress,
-//       third-body / fall-off factors and derivatives -> 4 scalars per reaction (R4), the
-//       reaction enthalpy dH, and the non-zero d(rate)/dC values ("raw")
-//   C1  species reductions, first level: chunks of 8 (reaction, nu) pairs -> partial sums
-//   D   sparse gather: one thread per sub-entry (1, 2, 4 or 8 contributions, unrolled) of a
-//       structurally non-zero Jacobian element (scaled by W_k), and of the energy row's
-//       sparse part (dH-weighted, scaled by -1/cp_avg)
-//   C2  one warp per state: per species sum of its chunk partials -> wdot_k and the row
-//       vectors rowT / rowA / rowB (row 0 = energy equation, from five dot products: the only
-//       warp-shuffle reductions left); other warps sum the entries cut into sub-entries
-//   E   one warp per Jacobian column, lanes = rows:
-//       out[r] = (rowA[r] + rowB[r] W_j/W_N + S[jmap[j][r]]) / W_j, coalesced stores to HBM
+// A persistent thread block walks over groups of G states (G = 1 or 2).  Every per-state
+// quantity in shared memory is interleaved over the G states of the group (slot-major,
+// state-minor), so that one 16-byte shared-memory access serves both states of a group and
+// the index decoding of the mechanism tables is done once per group.  Per group, separated by
+// three block barriers:
+//
+//   A   one warp per state: mass fractions -> concentrations and NASA-7 thermo per species
+//       (C_k, B_k = Gibbs term of Kc, dB_k/dT, h_k W_k).  Runs for the *next* group while
+//       phase E stores the current one.
+//   B   one thread per reaction, both states of the group in registers: kf, kr, rates of
+//       progress, third-body / fall-off factors and their derivatives -> four scalars per
+//       reaction (net rate, T-column term, X1, X2), the reaction enthalpy dH and the non-zero
+//       d(rate)/dC values ("raw")
+//   C   four lanes per species: sum over its reactions of nu * (the four scalars) -> wdot_k
+//       and the dense rank-2 part of the Jacobian (a_k, b_k, T column)
+//   D   sparse gather into a dense NSP x NSP tile in shared memory: one thread per
+//       structurally non-zero element (1, 2, 4 or 8 contributions, unrolled), four lanes for
+//       long lists and for the dH-weighted energy-equation row
+//   E   one warp per Jacobian column, lanes = rows: tile + rank-2 part -> HBM, coalesced;
+//       warp g < G instead finishes the energy-equation row of state g (five dot products) and
+//       then runs phase A of the next group
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,29 +39,31 @@ enum : int {
     F_REV = 1, F_THD = 2, F_PDEP = 4, F_LOW = 8, F_TROE = 16, F_SRI = 32, F_PMT = 64,
     F_PMT_INJ = 128, F_TROE_T2 = 256, F_SRI5 = 512, F_SRI5_DT = 1024, F_NO_T = 2048,
     F_EFFN1 = 4096, F_WANT_PMT = 1 << 16, F_EFF_SLOTS = 1 << 17, NRE_SHIFT = 20, NPR_SHIFT = 24,
-    NPAR = 32, RCH = 8
+    NPAR = 32, NONE16 = 0xFFFF
 };
 
 enum : int { M_JAC = 1, M_DYDT = 2, M_RATES = 4 };
 
 struct Tables {
-    int nsp, nr, nrev, npd, nraw, nsub, ncon, ncoef, first_pm, npm, nsub_j, nsplit, nchunk, zero_slot;
+    int nsp, nr, nrev, npd, nraw, first_pm, npm;
+    int nfix, nq, nq_j;              // sparse entries: fixed-length classes, quad entries
+    int d_cls[5], d_ccon[4];
     double ru;
     const double *sp_w, *sp_iw, *sp_ruw, *sp_tmid, *sp_mwf, *sp_nasa;
     const int4* rx_rec;
+    const uint4* rx_dst;             // 8 x u16 per reaction
     const double* pm_par;
     const int *pm_sp, *pm_eff_off, *pm_eff_sp;
     const double* pm_eff_am1;
-    const int* chk_rx;
-    const double* chk_nu;
-    const int* sp_chk_off;
-    int cls_sub[9], cls_con[8];   // sparse sub-entry classes J8 J4 J2 J1 T8 T4 T2 T1
-    const unsigned* con;
-    const double* sub_w;
-    const int *cmb_off, *cmb_idx;
-    const unsigned short* jmap;
+    const int* red_off;
+    const unsigned* red_pk;
+    const unsigned short* d_dst;
+    const unsigned* d_con;
+    const unsigned short* q_dst;
+    const int* q_off;
+    const unsigned* q_con;
     // eval_spec_rates entry point only
-    const int *red_off, *red_rx;
+    const int* red_rx;
     const double* red_nu;
 };
 
@@ -78,25 +84,22 @@ struct IO {
     long long o_ld;
 };
 
-// shared-memory carve-up (offsets and per-state strides in doubles), filled on the host
+// shared-memory carve-up: offsets in doubles, every array interleaved over the G states
 struct Layout {
-    int nsp1;                 // padded species count (>= nsp + 1, even)
-    int off_spv, st_spv;      // double4 {conc, B, dB, hW} per species
-    int off_vec, st_vec;      // wdot, tcol, Ap, Bp
-    int off_cp, st_cp;        // [buf][g][nsp1]
-    int off_y, st_y;
-    int off_scal;             // [buf][g][NSCAL]
-    int off_r4, st_r4;        // double4 per reaction
-    int off_rh, st_rh;
-    int off_raw, st_raw;
-    int off_part, st_part;    // double4 per chunk
-    int off_sval, st_sval;
+    int nsp1;                 // padded species count (>= nsp + 1)
+    int off_C, off_B, off_dB, off_hW;     // [nsp1][G], slot nsp = empty reaction slot
+    int off_wdot, off_sT, off_a, off_b;   // [nsp1][G] per species
+    int off_cp;               // [2][nsp1][G]
+    int off_y;                // [nsp1][G]
+    int off_scal;             // [2][NSCAL][G]
+    int off_net, off_tT, off_X1, off_X2, off_rh;   // [nr][G]
+    int off_raw;              // [nraw + 2][G]: nraw = zero slot
+    int off_tile;             // [nsp*nsp][G]
     int total;
 };
 
-enum : int { V_WDOT = 0, V_ROWT, V_ROWA, V_ROWB, NVEC };   // ROW*: indexed by output row r
 enum : int { S_T = 0, S_LOGT, S_IT, S_RHO, S_RHOINV, S_MW, S_M, S_CPAVG, S_WDCP, S_P,
-             S_H1, S_XT, S_NWT, NSCAL = 16 };
+             S_H1, S_NWT, S_NMWR, NSCAL = 16 };
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -107,6 +110,56 @@ __device__ __forceinline__ double warp_sum(double v)
 
 __device__ __forceinline__ double log10_clamped(double x) { return log10(fmax(x, 1.0e-300)); }
 
+// exp for |x| <= 708 without the range handling of the library version: Cody-Waite reduction
+// to |r| <= ln2/2, degree-12 Taylor polynomial (truncation 1.7e-16 relative), exponent added
+// to the high word.  Anything else (overflow, underflow, NaN) takes the library path.
+__device__ __forceinline__ double exp_fast(double x)
+{
+    if (!(fabs(x) <= 708.0)) return exp(x);
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 2.08767569878680989792e-09;               // 1/12!
+    p = fma(p, r, 2.50521083854417187751e-08);
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// G interleaved doubles at p (16-byte vector access for G = 2)
+template <int G>
+__device__ __forceinline__ void ldv(const double* p, double (&o)[G])
+{
+    if (G == 2) {
+        const double2 t = *reinterpret_cast<const double2*>(p);
+        o[0] = t.x;
+        o[G - 1] = t.y;
+    } else {
+        o[0] = *p;
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void stv(double* p, const double (&v)[G])
+{
+    if (G == 2) *reinterpret_cast<double2*>(p) = make_double2(v[0], v[G - 1]);
+    else *p = v[0];
+}
+
+// the double whose top 16 bits are the upper half of w (small integers: low 48 bits zero)
+__device__ __forceinline__ double coef_of(unsigned w) { return __hiloint2double((int)(w & 0xFFFF0000u), 0); }
+
 // out element v of state s for the M_RATES outputs
 __device__ __forceinline__ void put(double* base, const IO& io, int width, long long s, int v, double x)
 {
@@ -116,7 +169,7 @@ __device__ __forceinline__ void put(double* base, const IO& io, int width, long 
 
 struct RxP {
     double lnA, b, Ta, lnKc;
-    int fl, rbase, s0, s1, s2, s3, s4, s5, rev_idx, pm_idx, orig;
+    int fl, s0, s1, s2, s3, s4, s5, rev_idx, pm_idx, orig;
 };
 
 __device__ __forceinline__ RxP load_rx(const int4* rec, int p)
@@ -128,7 +181,7 @@ __device__ __forceinline__ RxP load_rx(const int4* rec, int p)
     r.b = __hiloint2double(a.w, a.z);
     r.Ta = __hiloint2double(b.y, b.x);
     r.lnKc = __hiloint2double(b.w, b.z);
-    r.fl = c.x; r.rbase = c.y;
+    r.fl = c.x;
     r.s0 = c.z & 0xFFFF; r.s1 = (unsigned)c.z >> 16;
     r.s2 = c.w & 0xFFFF; r.s3 = (unsigned)c.w >> 16;
     r.s4 = d.x & 0xFFFF; r.s5 = (unsigned)d.x >> 16;
@@ -136,161 +189,293 @@ __device__ __forceinline__ RxP load_rx(const int4* rec, int p)
     return r;
 }
 
-// Everything phase B does for one (reaction, state).  PM selects the third-body / fall-off
-// code; plain reactions compile without it.
-template <bool PM, bool JAC, bool RATES>
-__device__ __forceinline__ void reaction(const Tables& tb, const IO& io, const RxP& rx, int p,
-                                         const double4* __restrict__ sv, const double* __restrict__ sc,
-                                         double4* __restrict__ r4, double* __restrict__ rh,
-                                         double* __restrict__ raw, long long s_out)
+// Everything phase B does for one reaction and the G states of the group.  PM selects the
+// third-body / fall-off code.  THREE: some lane of the warp has a third molecule on a side.
+template <int G, bool PM, bool JAC, bool RATES>
+__device__ __forceinline__ void reaction(const Tables& tb, const IO& io, const Layout& L,
+                                         double* __restrict__ smem, int buf, int p, bool valid,
+                                         bool three, long long s0)
 {
     const int nsp = tb.nsp, last = tb.nsp - 1;
+    const RxP rx = load_rx(tb.rx_rec, p);
     const int fl = rx.fl;
-    const double T = sc[S_T], logT = sc[S_LOGT], iT = sc[S_IT];
-    const double4 v0 = sv[rx.s0], v1 = sv[rx.s1], v2 = sv[rx.s2];
-    const double4 v3 = sv[rx.s3], v4 = sv[rx.s4], v5 = sv[rx.s5];
-    const double lnkf = rx.lnA + rx.b * logT - rx.Ta * iT;
-    const double kf = exp(lnkf);
-    const double f = kf * v0.x * v1.x * v2.x;
     const bool isrev = fl & F_REV;
-    double kr = 0.0, r = 0.0;
-    if (isrev) {
-        const double sB = (v3.y + v4.y + v5.y) - (v0.y + v1.y + v2.y);
-        kr = exp(lnkf - sB - rx.lnKc);
-        r = kr * v3.x * v4.x * v5.x;
-    }
-    const double net = f - r;
+    const double* sc = smem + L.off_scal + buf * NSCAL * G;
+    const double* Cv = smem + L.off_C;
+    double T[G], logT[G], iT[G];
+    ldv<G>(sc + S_T * G, T);
+    ldv<G>(sc + S_LOGT * G, logT);
+    ldv<G>(sc + S_IT * G, iT);
 
-    double PM_ = 1.0, pmt = 0.0, Xd = 0.0, e1Fi = 0.0;
-    const int mi = p - tb.first_pm;
-    const double* par = tb.pm_par + (PM ? mi : 0) * NPAR;
+    // ---- pressure modification first: PM_, and for the Jacobian gg, Xd, e1Fi
+    double PM_[G], gg[G], Xd[G], e1Fi[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { PM_[g] = 1.0; gg[g] = 1.0; Xd[g] = 0.0; e1Fi[g] = 0.0; }
+    const int mi = PM ? p - tb.first_pm : 0;
+    const double* par = tb.pm_par + mi * NPAR;
     if (PM) {
-        double thd = sc[S_M];
+        double thd[G];
+        ldv<G>(sc + S_M * G, thd);
         const int e0 = tb.pm_eff_off[mi], e1_ = tb.pm_eff_off[mi + 1];
-        for (int e = e0; e < e1_; ++e) thd += tb.pm_eff_am1[e] * sv[tb.pm_eff_sp[e]].x;
+        for (int e = e0; e < e1_; ++e) {
+            double ce[G];
+            ldv<G>(Cv + tb.pm_eff_sp[e] * G, ce);
+            const double am1 = tb.pm_eff_am1[e];
+#pragma unroll
+            for (int g = 0; g < G; ++g) thd[g] += am1 * ce[g];
+        }
         if (fl & F_PDEP) {
             const int csp = tb.pm_sp[mi];
-            const double ct = csp >= 0 ? sv[csp].x : thd;
-            const double e1 = exp(par[0] + par[1] * logT - par[2] * iT);
-            const double Pr = ct * e1;
-            const double dpr4 = par[3] + par[2] * iT - 1.0;
-            const double dpr = par[1] + par[2] * iT - 1.0;
-            const double i1p = 1.0 / (1.0 + Pr);
+            double ct[G];
+            if (csp >= 0) ldv<G>(Cv + csp * G, ct);
+            else {
+#pragma unroll
+                for (int g = 0; g < G; ++g) ct[g] = thd[g];
+            }
             const bool low = fl & F_LOW;
-            double gg;
-            if (low) { Xd = dpr4 * iT * i1p; gg = i1p; }
-            else { Xd = -Pr * dpr4 * iT * i1p; gg = -Pr * i1p; }
-            double F = 1.0;
+            const double p0 = par[0], p1 = par[1], p2 = par[2], p3 = par[3];
+            double Pr[G], i1p[G], F[G], dpr[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const double e1 = exp_fast(p0 + p1 * logT[g] - p2 * iT[g]);
+                Pr[g] = ct[g] * e1;
+                const double dpr4 = p3 + p2 * iT[g] - 1.0;
+                dpr[g] = p1 + p2 * iT[g] - 1.0;
+                i1p[g] = 1.0 / (1.0 + Pr[g]);
+                if (low) { Xd[g] = dpr4 * iT[g] * i1p[g]; gg[g] = i1p[g]; }
+                else { Xd[g] = -Pr[g] * dpr4 * iT[g] * i1p[g]; gg[g] = -Pr[g] * i1p[g]; }
+                F[g] = 1.0;
+                e1Fi[g] = e1;
+            }
             if (fl & F_TROE) {
-                const double e3 = exp(T / par[7]), e1t = exp(T / par[9]);
-                double Fc = par[6] * e3 + par[8] * e1t;
-                double dF = par[11] * e3 - par[12] * e1t;
-                if (fl & F_TROE_T2) {
-                    const double e2 = exp(par[10] * iT);
-                    Fc += e2;
-                    dF += par[13] * iT * iT * e2;
-                }
-                const double lnFc = log(fmax(Fc, 1.0e-300));
                 const double iln10 = 0.43429448190325182765;
-                const double lF = lnFc * iln10, lP = log10_clamped(Pr);
-                const double A = lP - 0.67 * lF - 0.4;
-                const double Bq = 0.806 - 1.1762 * lF - 0.14 * lP;
-                const double q1 = 1.0 + A * A / (Bq * Bq);
-                const double lnF_AB = 2.0 * lnFc * A / (Bq * Bq * Bq * q1 * q1);
-                F = exp(lnFc / q1);
-                if (JAC) {
-                    Xd += (1.0 / (Fc * q1) - lnF_AB * (-0.67 * iln10 * Bq + 1.1762 * iln10 * A) / Fc) * dF
-                          - lnF_AB * (Bq * iln10 + 0.14 * iln10 * A) * dpr * iT;
-                    gg -= lnF_AB * (Bq * iln10 + A * 0.14 * iln10);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const double e3 = exp_fast(T[g] / par[7]), e1t = exp_fast(T[g] / par[9]);
+                    double Fc = par[6] * e3 + par[8] * e1t;
+                    double dF = par[11] * e3 - par[12] * e1t;
+                    if (fl & F_TROE_T2) {
+                        const double e2 = exp_fast(par[10] * iT[g]);
+                        Fc += e2;
+                        dF += par[13] * iT[g] * iT[g] * e2;
+                    }
+                    const double lnFc = log(fmax(Fc, 1.0e-300));
+                    const double lF = lnFc * iln10, lP = log10_clamped(Pr[g]);
+                    const double A = lP - 0.67 * lF - 0.4;
+                    const double Bq = 0.806 - 1.1762 * lF - 0.14 * lP;
+                    const double q1 = 1.0 + A * A / (Bq * Bq);
+                    const double lnF_AB = 2.0 * lnFc * A / (Bq * Bq * Bq * q1 * q1);
+                    F[g] = exp_fast(lnFc / q1);
+                    if (JAC) {
+                        Xd[g] += (1.0 / (Fc * q1) - lnF_AB * (-0.67 * iln10 * Bq + 1.1762 * iln10 * A) / Fc) * dF
+                                 - lnF_AB * (Bq * iln10 + 0.14 * iln10 * A) * dpr[g] * iT[g];
+                        gg[g] -= lnF_AB * (Bq * iln10 + A * 0.14 * iln10);
+                    }
                 }
             } else if (fl & F_SRI) {
-                const double lP = log10_clamped(Pr);
-                const double X = 1.0 / (1.0 + lP * lP);
-                F = pow(par[14] * exp(-par[15] * iT) + exp(-T / par[16]), X);
-                if (fl & F_SRI5) F *= par[17] * pow(T, par[18]);
-                if (JAC) {
-                    const double two_iln10 = 0.86858896380650365530;
-                    const double eb = exp(par[23] * iT), ec = exp(T / par[25]);
-                    const double den = par[26] * eb + ec;
-                    Xd += X * ((par[22] * iT * iT * eb - par[24] * ec) / den
-                               - X * two_iln10 * lP * dpr * log(den) * iT);
-                    if (fl & F_SRI5_DT) Xd += par[27] * iT;
-                    gg -= X * X * two_iln10 * lP * log(par[19] * exp(par[20] * iT) + exp(T / par[21]));
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const double lP = log10_clamped(Pr[g]);
+                    const double X = 1.0 / (1.0 + lP * lP);
+                    F[g] = pow(par[14] * exp(-par[15] * iT[g]) + exp(-T[g] / par[16]), X);
+                    if (fl & F_SRI5) F[g] *= par[17] * pow(T[g], par[18]);
+                    if (JAC) {
+                        const double two_iln10 = 0.86858896380650365530;
+                        const double eb = exp(par[23] * iT[g]), ec = exp(T[g] / par[25]);
+                        const double den = par[26] * eb + ec;
+                        Xd[g] += X * ((par[22] * iT[g] * iT[g] * eb - par[24] * ec) / den
+                                      - X * two_iln10 * lP * dpr[g] * log(den) * iT[g]);
+                        if (fl & F_SRI5_DT) Xd[g] += par[27] * iT[g];
+                        gg[g] -= X * X * two_iln10 * lP * log(par[19] * exp(par[20] * iT[g]) + exp(T[g] / par[21]));
+                    }
                 }
             }
-            const double Fi = F * i1p;
-            PM_ = low ? Fi * Pr : Fi;
-            e1Fi = e1 * Fi;
-            if (fl & F_PMT) pmt = gg * net;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const double Fi = F[g] * i1p[g];
+                PM_[g] = low ? Fi * Pr[g] : Fi;
+                e1Fi[g] *= Fi;
+            }
         } else {
-            PM_ = thd;
-            if (fl & F_PMT) pmt = net;
+#pragma unroll
+            for (int g = 0; g < G; ++g) PM_[g] = thd[g];
         }
     }
-    if (RATES && s_out >= 0) {
-        if (io.fwd) put(io.fwd, io, tb.nr, s_out, rx.orig, f);
-        if (io.rev && isrev) put(io.rev, io, tb.nrev, s_out, rx.rev_idx, r);
-        if (PM && io.pm) put(io.pm, io, tb.npd, s_out, rx.pm_idx, PM_);
+
+    // ---- rate constants and rates of progress
+    double c0[G], c1[G], c2[G], c3[G], c4[G], c5[G];
+    ldv<G>(Cv + rx.s0 * G, c0);
+    ldv<G>(Cv + rx.s1 * G, c1);
+    ldv<G>(Cv + rx.s3 * G, c3);
+    ldv<G>(Cv + rx.s4 * G, c4);
+    if (three) { ldv<G>(Cv + rx.s2 * G, c2); ldv<G>(Cv + rx.s5 * G, c5); }
+    else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) { c2[g] = 1.0; c5[g] = 1.0; }
+    }
+    double kf[G], kr[G], f[G], r[G], net[G];
+    {
+        const double* Bv = smem + L.off_B;
+        double b0[G], b1[G], b3[G], b4[G];
+        ldv<G>(Bv + rx.s0 * G, b0);
+        ldv<G>(Bv + rx.s1 * G, b1);
+        ldv<G>(Bv + rx.s3 * G, b3);
+        ldv<G>(Bv + rx.s4 * G, b4);
+        double sB[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) sB[g] = (b3[g] + b4[g]) - (b0[g] + b1[g]);
+        if (three) {
+            double b2[G], b5[G];
+            ldv<G>(Bv + rx.s2 * G, b2);
+            ldv<G>(Bv + rx.s5 * G, b5);
+#pragma unroll
+            for (int g = 0; g < G; ++g) sB[g] += b5[g] - b2[g];
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const double lnkf = rx.lnA + rx.b * logT[g] - rx.Ta * iT[g];
+            kf[g] = exp_fast(lnkf);
+            const double krv = exp_fast(lnkf - sB[g] - rx.lnKc);
+            kr[g] = isrev ? krv : 0.0;
+            f[g] = kf[g] * c0[g] * c1[g] * c2[g];
+            r[g] = kr[g] * c3[g] * c4[g] * c5[g];
+            net[g] = f[g] - r[g];
+        }
+    }
+    double pmt[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) pmt[g] = (PM && (fl & F_PMT)) ? gg[g] * net[g] : 0.0;
+
+    if (RATES && valid) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const long long s = s0 + g;
+            if (s >= io.n) continue;
+            if (io.fwd) put(io.fwd, io, tb.nr, s, rx.orig, f[g]);
+            if (io.rev && isrev) put(io.rev, io, tb.nrev, s, rx.rev_idx, r[g]);
+            if (PM && io.pm) put(io.pm, io, tb.npd, s, rx.pm_idx, PM_[g]);
+        }
     }
     if (!JAC) {
-        r4[p].x = net * PM_;
+        if (valid) {
+            double v[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) v[g] = net[g] * PM_[g];
+            stv<G>(smem + L.off_net + p * G, v);
+        }
         return;
     }
+
+    // ---- Jacobian scalars
     const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
-    const double rho_inv = sc[S_RHOINV];
-    const double dk = rx.b + rx.Ta * iT;
-    const double sdB = (v3.z + v4.z + v5.z) - (v0.z + v1.z + v2.z);
-    // irreversible: r = 0 makes this f * (dk + 1 - nre)          (cj:1461-1523)
-    const double elem = net * dk + f * (1.0 - nre) - r * ((1.0 - npr) - T * sdB);
-    double tT;
-    if (PM) {
-        if (fl & F_PDEP) tT = (PM_ * Xd * net + PM_ * iT * elem) * rho_inv;
-        else tT = (-PM_ * net * iT + PM_ * iT * elem) * rho_inv;
-    } else {
-        tT = iT * elem * rho_inv;
+    double rho_inv[G], nmwr[G];
+    ldv<G>(sc + S_RHOINV * G, rho_inv);
+    ldv<G>(sc + S_NMWR * G, nmwr);
+    double sdB[G], dH[G];
+    {
+        const double* Dv = smem + L.off_dB;
+        const double* Hv = smem + L.off_hW;
+        double a0[G], a1[G], a3[G], a4[G];
+        ldv<G>(Dv + rx.s0 * G, a0);
+        ldv<G>(Dv + rx.s1 * G, a1);
+        ldv<G>(Dv + rx.s3 * G, a3);
+        ldv<G>(Dv + rx.s4 * G, a4);
+#pragma unroll
+        for (int g = 0; g < G; ++g) sdB[g] = (a3[g] + a4[g]) - (a0[g] + a1[g]);
+        ldv<G>(Hv + rx.s0 * G, a0);
+        ldv<G>(Hv + rx.s1 * G, a1);
+        ldv<G>(Hv + rx.s3 * G, a3);
+        ldv<G>(Hv + rx.s4 * G, a4);
+#pragma unroll
+        for (int g = 0; g < G; ++g) dH[g] = (a3[g] + a4[g]) - (a0[g] + a1[g]);
+        if (three) {
+            ldv<G>(Dv + rx.s2 * G, a0);
+            ldv<G>(Dv + rx.s5 * G, a1);
+            ldv<G>(Hv + rx.s2 * G, a3);
+            ldv<G>(Hv + rx.s5 * G, a4);
+#pragma unroll
+            for (int g = 0; g < G; ++g) { sdB[g] += a1[g] - a0[g]; dH[g] += a4[g] - a3[g]; }
+        }
     }
-    if (fl & F_NO_T) tT = 0.0;
     const double extra = (PM && (fl & F_EFFN1)) ? 1.0 : 0.0;
-    double inner = (nre + extra) * f - (isrev ? (npr + extra) * r : 0.0);
-    if (PM && (fl & F_PMT_INJ)) inner += pmt;
-    const double jy = -sc[S_MW] * rho_inv * PM_ * inner;
-    if (PM && (fl & F_PMT_INJ)) pmt *= e1Fi;
-    double X1 = jy, X2 = -jy;
-    if (PM) { X1 += par[5] * pmt; X2 -= par[4] * pmt; }
-    double* rw = raw + rx.rbase;
-    const double pk = PM_ * kf;
-    const double d0 = pk * v1.x * v2.x, d1 = pk * v0.x * v2.x, d2 = pk * v0.x * v1.x;
-    if (rx.s0 != nsp) { if (rx.s0 == last) X2 -= d0; else *rw++ = d0; }
-    if (rx.s1 != nsp) { if (rx.s1 == last) X2 -= d1; else *rw++ = d1; }
-    if (rx.s2 != nsp) { if (rx.s2 == last) X2 -= d2; else *rw++ = d2; }
-    if (isrev) {
-        const double pr = -PM_ * kr;
-        const double d3 = pr * v4.x * v5.x, d4 = pr * v3.x * v5.x, d5 = pr * v3.x * v4.x;
-        if (rx.s3 != nsp) { if (rx.s3 == last) X2 -= d3; else *rw++ = d3; }
-        if (rx.s4 != nsp) { if (rx.s4 == last) X2 -= d4; else *rw++ = d4; }
-        if (rx.s5 != nsp) { if (rx.s5 == last) X2 -= d5; else *rw++ = d5; }
+    double tT[G], X1[G], X2[G], pk[G], pr[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const double dk = rx.b + rx.Ta * iT[g];
+        // irreversible: r = 0 makes this f * (dk + 1 - nre)          (cj:1461-1523)
+        const double elem = net[g] * dk + f[g] * (1.0 - nre) - r[g] * ((1.0 - npr) - T[g] * sdB[g]);
+        double t;
+        if (PM) {
+            if (fl & F_PDEP) t = (PM_[g] * Xd[g] * net[g] + PM_[g] * iT[g] * elem) * rho_inv[g];
+            else t = (-PM_[g] * net[g] * iT[g] + PM_[g] * iT[g] * elem) * rho_inv[g];
+        } else {
+            t = iT[g] * elem * rho_inv[g];
+        }
+        tT[g] = (fl & F_NO_T) ? 0.0 : t;
+        double inner = (nre + extra) * f[g] - (npr + extra) * r[g];
+        if (PM && (fl & F_PMT_INJ)) inner += pmt[g];
+        const double jy = nmwr[g] * PM_[g] * inner;
+        if (PM && (fl & F_PMT_INJ)) pmt[g] *= e1Fi[g];
+        X1[g] = jy;
+        X2[g] = -jy;
+        if (PM) { X1[g] += par[5] * pmt[g]; X2[g] -= par[4] * pmt[g]; }
+        pk[g] = PM_[g] * kf[g];
+        pr[g] = -PM_[g] * kr[g];
     }
-    if (PM) {
+
+    // ---- d(rate)/dC values: to their raw slots, or folded into X2 for the last species
+    const uint4 dq = __ldg(tb.rx_dst + p);
+    double* raw = smem + L.off_raw;
+    double d[G];
+#define PJ_EMIT(SLOT, DST, EXPR)                                               \
+    if ((SLOT) != nsp) {                                                       \
+        _Pragma("unroll") for (int g = 0; g < G; ++g) d[g] = (EXPR);           \
+        if ((SLOT) == last) {                                                  \
+            _Pragma("unroll") for (int g = 0; g < G; ++g) X2[g] -= d[g];       \
+        } else if (valid) {                                                    \
+            stv<G>(raw + (int)(DST) * G, d);                                   \
+        }                                                                      \
+    }
+    PJ_EMIT(rx.s0, dq.x & 0xFFFFu, pk[g] * c1[g] * c2[g])
+    PJ_EMIT(rx.s1, dq.x >> 16, pk[g] * c0[g] * c2[g])
+    if (three) { PJ_EMIT(rx.s2, dq.y & 0xFFFFu, pk[g] * c0[g] * c1[g]) }
+    if (isrev) {
+        PJ_EMIT(rx.s3, dq.y >> 16, pr[g] * c4[g] * c5[g])
+        PJ_EMIT(rx.s4, dq.z & 0xFFFFu, pr[g] * c3[g] * c5[g])
+        if (three) { PJ_EMIT(rx.s5, dq.z >> 16, pr[g] * c3[g] * c4[g]) }
+    }
+#undef PJ_EMIT
+    if (PM && valid) {
         if (fl & F_EFF_SLOTS) {
+            int rb = dq.w & 0xFFFFu;
             const int e0 = tb.pm_eff_off[mi], e1_ = tb.pm_eff_off[mi + 1];
             for (int e = e0; e < e1_; ++e)
-                if (tb.pm_eff_sp[e] != last) *rw++ = pmt * tb.pm_eff_am1[e];
+                if (tb.pm_eff_sp[e] != last) {
+                    const double am1 = tb.pm_eff_am1[e];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) d[g] = pmt[g] * am1;
+                    stv<G>(raw + rb * G, d);
+                    ++rb;
+                }
         }
-        if (fl & F_WANT_PMT) *rw = pmt;
+        if (fl & F_WANT_PMT) stv<G>(raw + (int)(dq.w >> 16) * G, pmt);
     }
-    r4[p] = make_double4(net * PM_, tT, X1, X2);
-    rh[p] = (v3.w + v4.w + v5.w) - (v0.w + v1.w + v2.w);
+    if (valid) {
+        double v[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) v[g] = net[g] * PM_[g];
+        stv<G>(smem + L.off_net + p * G, v);
+        stv<G>(smem + L.off_tT + p * G, tT);
+        stv<G>(smem + L.off_X1 + p * G, X1);
+        stv<G>(smem + L.off_X2 + p * G, X2);
+        stv<G>(smem + L.off_rh + p * G, dH);
+    }
 }
 
-
-// Phase D for one sub-entry of LEN contributions.  TROW: energy-equation row (coefficient =
-// reaction enthalpy change, scale = -1/cp_avg), else Jacobian entry (coefficient = nu as a
-// bf16 pattern in the upper half of the word, scale = W_k).
-template <int G, int LEN, bool TROW>
-__device__ __forceinline__ void gather(const unsigned* __restrict__ cw, const double* __restrict__ raw0,
-                                       int st_raw, const double* __restrict__ rh0, int st_rh,
-                                       const double* __restrict__ scale, int scale_st,
-                                       double* __restrict__ sval0, int st_sval, int e)
+// Phase D, fixed-length class: LEN contributions of one tile element for the G states.
+template <int G, int LEN>
+__device__ __forceinline__ void gather_fixed(const unsigned* __restrict__ cw, const double* __restrict__ raw,
+                                             double* __restrict__ dst)
 {
     unsigned w[LEN];
     if (LEN == 8) {
@@ -311,78 +496,13 @@ __device__ __forceinline__ void gather(const unsigned* __restrict__ cw, const do
     for (int g = 0; g < G; ++g) acc[g] = 0.0;
 #pragma unroll
     for (int i = 0; i < LEN; ++i) {
-        const int src = w[i] & 0xFFFFu;
-        if (TROW) {
-            const int rxn = w[i] >> 16;
+        double v[G];
+        ldv<G>(raw + (w[i] & 0xFFFFu) * G, v);
+        const double cf = coef_of(w[i]);
 #pragma unroll
-            for (int g = 0; g < G; ++g) acc[g] += rh0[g * st_rh + rxn] * raw0[g * st_raw + src];
-        } else {
-            const double cf = (double)__uint_as_float(w[i] & 0xFFFF0000u);
-#pragma unroll
-            for (int g = 0; g < G; ++g) acc[g] += cf * raw0[g * st_raw + src];
-        }
+        for (int g = 0; g < G; ++g) acc[g] = fma(cf, v[g], acc[g]);
     }
-#pragma unroll
-    for (int g = 0; g < G; ++g) sval0[g * st_sval + e] = acc[g] * scale[g * scale_st];
-}
-
-// Phase E for one state: this warp's share of the Jacobian columns, lanes = output rows.
-// NK = ceil(nsp / 32) rows per lane (0: generic loop).  SF: state-fastest output layout.
-template <int NK, bool SF>
-__device__ __forceinline__ void store_columns(const Tables& tb, int nsp, int lane, int w0, int wn,
-                                              const double* __restrict__ rowT, const double* __restrict__ rowA,
-                                              const double* __restrict__ rowB, const double* __restrict__ sv,
-                                              const double* __restrict__ cp, double XT,
-                                              double* __restrict__ base, long long es)
-{
-    const int last = nsp - 1;
-    if (NK > 0) {
-        double rA[NK > 0 ? NK : 1], rB[NK > 0 ? NK : 1];
-#pragma unroll
-        for (int i = 0; i < NK; ++i) {
-            const int r = lane + 32 * i;
-            rA[i] = r < nsp ? rowA[r] : 0.0;
-            rB[i] = r < nsp ? rowB[r] : 0.0;
-        }
-        if (w0 == 0) {
-#pragma unroll
-            for (int i = 0; i < NK; ++i) {
-                const int r = lane + 32 * i;
-                if (r < nsp) base[SF ? (long long)r * es : r] = rowT[r];
-            }
-        }
-        for (int col = w0 == 0 ? wn : w0; col < nsp; col += wn) {
-            const int j = col - 1;
-            const double iwj = __ldg(tb.sp_iw + j), mwfj = __ldg(tb.sp_mwf + j);
-            const double ex = XT * (cp[j] - cp[last]);
-            const unsigned short* jm = tb.jmap + j * nsp;
-            double* out = base + (SF ? (long long)col * nsp * es : (long long)(col * nsp));
-#pragma unroll
-            for (int i = 0; i < NK; ++i) {
-                const int r = lane + 32 * i;
-                if (r < nsp) {
-                    double v = iwj * (rA[i] + rB[i] * mwfj + sv[__ldg(jm + r)]);
-                    if (i == 0 && r == 0) v += ex;
-                    out[SF ? (long long)r * es : r] = v;
-                }
-            }
-        }
-    } else {
-        if (w0 == 0)
-            for (int r = lane; r < nsp; r += 32) base[SF ? (long long)r * es : r] = rowT[r];
-        for (int col = w0 == 0 ? wn : w0; col < nsp; col += wn) {
-            const int j = col - 1;
-            const double iwj = __ldg(tb.sp_iw + j), mwfj = __ldg(tb.sp_mwf + j);
-            const double ex = XT * (cp[j] - cp[last]);
-            const unsigned short* jm = tb.jmap + (size_t)j * nsp;
-            double* out = base + (SF ? (long long)col * nsp * es : (long long)col * nsp);
-            for (int r = lane; r < nsp; r += 32) {
-                double v = iwj * (rowA[r] + rowB[r] * mwfj + sv[__ldg(jm + r)]);
-                if (r == 0) v += ex;
-                out[SF ? (long long)r * es : r] = v;
-            }
-        }
-    }
+    stv<G>(dst, acc);
 }
 
 // MINB = 1: up to 512 threads and 128 registers per thread; MINB = 2: up to 384 threads and
@@ -394,28 +514,18 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ IO io,
 {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int nsp = tb.nsp, last = tb.nsp - 1, nsp1 = L.nsp1;
+    const int nsp = tb.nsp, last = tb.nsp - 1;
     constexpr bool JAC = (MODE & M_JAC) != 0;
     constexpr bool RATES = (MODE & M_RATES) != 0;
 
-#define SPV(g) ((double4*)(smem + L.off_spv + (g) * L.st_spv))
-#define VEC(g, v) (smem + L.off_vec + (g) * L.st_vec + (v) * nsp1)
-#define CPV(b, g) (smem + L.off_cp + ((b) * G + (g)) * L.st_cp)
-#define SCAL(b, g) (smem + L.off_scal + ((b) * G + (g)) * NSCAL)
-#define R4V(g) ((double4*)(smem + L.off_r4 + (g) * L.st_r4))
-#define RHV(g) (smem + L.off_rh + (g) * L.st_rh)
-#define RAWV(g) (smem + L.off_raw + (g) * L.st_raw)
-#define PARTV(g) ((double4*)(smem + L.off_part + (g) * L.st_part))
-#define SVALV(g) (smem + L.off_sval + (g) * L.st_sval)
-
-    // ---- phase A for the group starting at state s0, into buffer `buf` (one warp / state)
+    // ---- phase A for state g of the group starting at s0, into buffer `buf` (one warp)
     auto phase_a = [&](long long s0, int buf, int g) {
         const bool live = s0 + g < io.n;
         const long long s = live ? s0 + g : (long long)io.n - 1;
         const double* ys = io.y + s * io.y_ss;
         const double T = ys[0];
         const double P = io.pres[s];
-        double* Yv = smem + L.off_y + g * L.st_y;
+        double* Yv = smem + L.off_y;
         double sumY = 0.0, sumYW = 0.0;
         double mw_avg, rho;
         if (io.in_conc) {
@@ -430,11 +540,11 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ IO io,
             rho = warp_sum(sumYW);
             mw_avg = rho / sumY;
             for (int k = lane; k < nsp; k += 32)
-                Yv[k] = ys[(long long)(k + 1) * io.y_sv] * tb.sp_w[k] / rho;
+                Yv[k * G + g] = ys[(long long)(k + 1) * io.y_sv] * tb.sp_w[k] / rho;
         } else {
             for (int k = lane; k < last; k += 32) {
                 const double Yk = ys[(long long)(k + 1) * io.y_sv];
-                Yv[k] = Yk;
+                Yv[k * G + g] = Yk;
                 sumY += Yk;
                 sumYW += Yk * tb.sp_iw[k];
             }
@@ -444,15 +554,14 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ IO io,
             sumYW += yN * tb.sp_iw[last];
             mw_avg = 1.0 / sumYW;
             rho = P * mw_avg / (tb.ru * T);
-            if (lane == 0) Yv[last] = yN;
+            if (lane == 0) Yv[last * G + g] = yN;
         }
         __syncwarp();
         const double logT = log(T), iT = 1.0 / T;
         double cpavg = 0.0, wdcp = 0.0;
-        double4* spv = SPV(g);
-        double* cpv = CPV(buf, g);
+        double* cpv = smem + L.off_cp + buf * L.nsp1 * G;
         for (int k = lane; k < nsp; k += 32) {
-            const double Yk = Yv[k];
+            const double Yk = Yv[k * G + g];
             const double ck = io.in_conc ? ys[(long long)(k + 1) * io.y_sv] : rho * Yk * tb.sp_iw[k];
             if (RATES && io.conc && live) put(io.conc, io, nsp, s, k, ck);
             const double* c = tb.sp_nasa + (k * 2 + (T <= tb.sp_tmid[k] ? 0 : 1)) * 16;
@@ -460,7 +569,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ IO io,
             const double cp = ruw * (c[0] + T * (c[1] + T * (c[2] + T * (c[3] + c[4] * T))));
             const double hh = c[6] + T * (c[7] + T * (c[8] + c[9] * T));
             const double h = ruw * (c[5] + T * (c[0] + T * hh));
-            cpv[k] = cp;
+            cpv[k * G + g] = cp;
             cpavg += Yk * cp;
             double dB = 0.0;
             if (JAC) {
@@ -469,24 +578,36 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ IO io,
                 dB = (c[11] + c[5] * iT) * iT + hh;
             }
             const double Bk = c[10] + c[11] * logT + T * (c[6] + T * (c[12] + T * (c[13] + c[14] * T))) - c[5] * iT;
-            spv[k] = make_double4(ck, Bk, dB, h * tb.sp_w[k]);
+            smem[L.off_C + k * G + g] = ck;
+            smem[L.off_B + k * G + g] = Bk;
+            smem[L.off_dB + k * G + g] = dB;
+            smem[L.off_hW + k * G + g] = h * tb.sp_w[k];
         }
         cpavg = warp_sum(cpavg);
         if (JAC) wdcp = warp_sum(wdcp);
         if (lane == 0) {
-            spv[nsp] = make_double4(1.0, 0.0, 0.0, 0.0);       // empty reaction slot
-            double* sc = SCAL(buf, g);
-            sc[S_T] = T; sc[S_LOGT] = logT; sc[S_IT] = iT; sc[S_RHO] = rho;
-            sc[S_RHOINV] = 1.0 / rho; sc[S_MW] = mw_avg; sc[S_M] = P / (tb.ru * T);
-            sc[S_CPAVG] = cpavg; sc[S_WDCP] = wdcp; sc[S_P] = P; sc[S_NWT] = -1.0 / cpavg;
+            smem[L.off_C + nsp * G + g] = 1.0;          // empty reaction slot
+            smem[L.off_B + nsp * G + g] = 0.0;
+            smem[L.off_dB + nsp * G + g] = 0.0;
+            smem[L.off_hW + nsp * G + g] = 0.0;
+            double* sc = smem + L.off_scal + buf * NSCAL * G + g;
+            const double rho_inv = 1.0 / rho;
+            sc[S_T * G] = T; sc[S_LOGT * G] = logT; sc[S_IT * G] = iT; sc[S_RHO * G] = rho;
+            sc[S_RHOINV * G] = rho_inv; sc[S_MW * G] = mw_avg; sc[S_M * G] = P / (tb.ru * T);
+            sc[S_CPAVG * G] = cpavg; sc[S_WDCP * G] = wdcp; sc[S_P * G] = P; sc[S_NWT * G] = -1.0 / cpavg;
+            sc[S_NMWR * G] = -mw_avg * rho_inv;
             if (RATES && io.scal3 && live) {
                 double* o = io.scal3 + s * 3;
-                o[0] = Yv[last]; o[1] = mw_avg; o[2] = rho;
+                o[0] = Yv[last * G + g]; o[1] = mw_avg; o[2] = rho;
             }
         }
     };
 
-    if (JAC && tid < G) { SVALV(tid)[tb.zero_slot] = 0.0; RAWV(tid)[tb.nraw] = 0.0; }
+    if (JAC) {
+        // structurally zero tile elements are never written again
+        for (int e = tid; e < nsp * nsp * G; e += blockDim.x) smem[L.off_tile + e] = 0.0;
+        for (int e = tid; e < 2 * G; e += blockDim.x) smem[L.off_raw + tb.nraw * G + e] = 0.0;
+    }
 
     const long long ngroups = ((long long)io.n + G - 1) / G;
     int buf = 0;
@@ -494,211 +615,266 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ IO io,
         for (int g = warp; g < G; g += nwarps) phase_a((long long)blockIdx.x * G, 0, g);
     __syncthreads();
 
-    const bool split_roles = nwarps >= 2 * G + 2;      // enough warps to overlap A(next) with E
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, buf ^= 1) {
         const long long s0 = grp * G;
+        const double* sc = smem + L.off_scal + buf * NSCAL * G;
 
         // ------------------------------------------------------------ phase B
+        // pressure-modified reactions first (longest), then the plain ones; whole warps
         {
-            const int n_plain = tb.first_pm;
-            const int items = n_plain + tb.npm * G;
-            for (int it = tid; it < items; it += blockDim.x) {
-                if (it < n_plain) {
-                    const RxP rx = load_rx(tb.rx_rec, it);
-#pragma unroll 1
-                    for (int g = 0; g < G; ++g)
-                        reaction<false, JAC, RATES>(tb, io, rx, it, SPV(g), SCAL(buf, g), R4V(g), RHV(g),
-                                                    RAWV(g), s0 + g < io.n ? s0 + g : -1);
+            const int npm_pad = (tb.npm + 31) & ~31, n_plain = tb.first_pm;
+            const int items = npm_pad + ((n_plain + 31) & ~31);
+            for (int base = warp * 32; base < items; base += blockDim.x) {
+                const int it = base + lane;
+                if (base < npm_pad) {
+                    const bool valid = it < tb.npm;
+                    reaction<G, true, JAC, RATES>(tb, io, L, smem, buf, tb.first_pm + (valid ? it : 0), valid, true, s0);
                 } else {
-                    const int q = it - n_plain;
-                    const int p = n_plain + q / G, g = q % G;
-                    const RxP rx = load_rx(tb.rx_rec, p);
-                    reaction<true, JAC, RATES>(tb, io, rx, p, SPV(g), SCAL(buf, g), R4V(g), RHV(g),
-                                               RAWV(g), s0 + g < io.n ? s0 + g : -1);
+                    const int q = it - npm_pad;
+                    const bool valid = q < n_plain;
+                    const int p = valid ? q : 0;
+                    const int4 c = __ldg(tb.rx_rec + p * 4 + 2);
+                    const int4 dd = __ldg(tb.rx_rec + p * 4 + 3);
+                    const bool has3 = ((c.w & 0xFFFF) != nsp) || (((unsigned)dd.x >> 16) != (unsigned)nsp);
+                    const bool three = __any_sync(0xffffffffu, has3);
+                    reaction<G, false, JAC, RATES>(tb, io, L, smem, buf, p, valid, three, s0);
                 }
             }
         }
         __syncthreads();
 
-        // ------------------------------------------------------------ phase C1
-        for (int c = tid; c < tb.nchunk; c += blockDim.x) {
-            const int4* rxp = (const int4*)(tb.chk_rx + c * RCH);
-            const double2* nup = (const double2*)(tb.chk_nu + c * RCH);
-            const int4 pa = __ldg(rxp), pb = __ldg(rxp + 1);
-            const double2 na = __ldg(nup), nb = __ldg(nup + 1), nc = __ldg(nup + 2), nd = __ldg(nup + 3);
-            const int pi[RCH] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-            const double nu[RCH] = {na.x, na.y, nb.x, nb.y, nc.x, nc.y, nd.x, nd.y};
+        // ------------------------------------------------------------ phase C: four lanes per species
+        {
+            const int q = lane & 3;
+            for (int kb = (tid >> 2); kb < ((nsp + 7) & ~7); kb += blockDim.x >> 2) {
+                const int k = kb < nsp ? kb : nsp - 1;
+                const int e0 = __ldg(tb.red_off + k), e1 = __ldg(tb.red_off + k + 1);
+                const int len = kb < nsp ? e1 - e0 : 0;
+                int mx = len;
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const double4* R = R4V(g);
-                double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
+                for (int o = 4; o < 32; o <<= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                double aN[G], aT[G], a1[G], a2[G];
 #pragma unroll
-                for (int e = 0; e < RCH; ++e) {
-                    if (JAC) {
-                        const double4 v = R[pi[e]];
-                        a.x += nu[e] * v.x; a.y += nu[e] * v.y; a.z += nu[e] * v.z; a.w += nu[e] * v.w;
-                    } else {
-                        a.x += nu[e] * R[pi[e]].x;
+                for (int g = 0; g < G; ++g) { aN[g] = 0.0; aT[g] = 0.0; a1[g] = 0.0; a2[g] = 0.0; }
+                for (int i = q; i < mx; i += 4) {
+                    if (i < len) {
+                        const unsigned w = __ldg(tb.red_pk + e0 + i);
+                        const int p = w & 0xFFFFu;
+                        const double cf = coef_of(w);
+                        double v[G];
+                        ldv<G>(smem + L.off_net + p * G, v);
+#pragma unroll
+                        for (int g = 0; g < G; ++g) aN[g] = fma(cf, v[g], aN[g]);
+                        if (JAC) {
+                            ldv<G>(smem + L.off_tT + p * G, v);
+#pragma unroll
+                            for (int g = 0; g < G; ++g) aT[g] = fma(cf, v[g], aT[g]);
+                            ldv<G>(smem + L.off_X1 + p * G, v);
+#pragma unroll
+                            for (int g = 0; g < G; ++g) a1[g] = fma(cf, v[g], a1[g]);
+                            ldv<G>(smem + L.off_X2 + p * G, v);
+#pragma unroll
+                            for (int g = 0; g < G; ++g) a2[g] = fma(cf, v[g], a2[g]);
+                        }
                     }
                 }
-                PARTV(g)[c] = a;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    aN[g] += __shfl_xor_sync(0xffffffffu, aN[g], 1);
+                    aN[g] += __shfl_xor_sync(0xffffffffu, aN[g], 2);
+                    if (JAC) {
+                        aT[g] += __shfl_xor_sync(0xffffffffu, aT[g], 1);
+                        aT[g] += __shfl_xor_sync(0xffffffffu, aT[g], 2);
+                        a1[g] += __shfl_xor_sync(0xffffffffu, a1[g], 1);
+                        a1[g] += __shfl_xor_sync(0xffffffffu, a1[g], 2);
+                        a2[g] += __shfl_xor_sync(0xffffffffu, a2[g], 1);
+                        a2[g] += __shfl_xor_sync(0xffffffffu, a2[g], 2);
+                    }
+                }
+                if (q == 0 && kb < nsp) {
+                    stv<G>(smem + L.off_wdot + k * G, aN);
+                    if (JAC) {
+                        double mw[G], ri[G];
+                        ldv<G>(sc + S_MW * G, mw);
+                        ldv<G>(sc + S_RHOINV * G, ri);
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            const double comp = aN[g] * (mw[g] * ri[g]);
+                            a1[g] += comp;
+                            a2[g] -= comp;
+                        }
+                        stv<G>(smem + L.off_sT + k * G, aT);
+                        stv<G>(smem + L.off_a + k * G, a1);
+                        stv<G>(smem + L.off_b + k * G, a2);
+                    }
+                }
             }
         }
 
         // ------------------------------------------------------------ phase D
         if (JAC) {
-            const double* raw0 = RAWV(0);
-            const double* rh0 = RHV(0);
-            double* sval0 = SVALV(0);
-            const double* nwt0 = SCAL(buf, 0) + S_NWT;
-            for (int e = tid; e < tb.nsub; e += blockDim.x) {
-                int c = 0;
-#pragma unroll
-                for (int i = 1; i < 8; ++i) c += e >= tb.cls_sub[i];
-                const int rel = e - tb.cls_sub[c];
-                const unsigned* cw = tb.con + tb.cls_con[c];
-                switch (c) {
-                case 0: gather<G, 8, false>(cw + rel * 8, raw0, L.st_raw, rh0, L.st_rh, tb.sub_w + e, 0, sval0, L.st_sval, e); break;
-                case 1: gather<G, 4, false>(cw + rel * 4, raw0, L.st_raw, rh0, L.st_rh, tb.sub_w + e, 0, sval0, L.st_sval, e); break;
-                case 2: gather<G, 2, false>(cw + rel * 2, raw0, L.st_raw, rh0, L.st_rh, tb.sub_w + e, 0, sval0, L.st_sval, e); break;
-                case 3: gather<G, 1, false>(cw + rel, raw0, L.st_raw, rh0, L.st_rh, tb.sub_w + e, 0, sval0, L.st_sval, e); break;
-                case 4: gather<G, 8, true>(cw + rel * 8, raw0, L.st_raw, rh0, L.st_rh, nwt0, NSCAL, sval0, L.st_sval, e); break;
-                case 5: gather<G, 4, true>(cw + rel * 4, raw0, L.st_raw, rh0, L.st_rh, nwt0, NSCAL, sval0, L.st_sval, e); break;
-                case 6: gather<G, 2, true>(cw + rel * 2, raw0, L.st_raw, rh0, L.st_rh, nwt0, NSCAL, sval0, L.st_sval, e); break;
-                default: gather<G, 1, true>(cw + rel, raw0, L.st_raw, rh0, L.st_rh, nwt0, NSCAL, sval0, L.st_sval, e); break;
-                }
-            }
-        }
-        __syncthreads();
-
-        // ------------------------------------------------------------ phase C2 (+ combine)
-        if (warp < G) {
-            const int g = warp;
-            double* sc = SCAL(buf, g);
-            const double mw_rho = sc[S_MW] * sc[S_RHOINV];
-            const double4* part = PARTV(g);
-            const double4* spv = SPV(g);
-            const double* cpv = CPV(buf, g);
-            double H1 = 0.0, HA = 0.0, HB = 0.0, HT = 0.0, SCP = 0.0;
-            for (int k = lane; k < nsp; k += 32) {
-                const int c0 = tb.sp_chk_off[k], c1 = tb.sp_chk_off[k + 1];
-                double4 s = make_double4(0.0, 0.0, 0.0, 0.0);
-                for (int c = c0; c < c1; ++c) {
-                    const double4 v = part[c];
-                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-                }
-                const double wk = tb.sp_w[k], hW = spv[k].w;
-                VEC(g, V_WDOT)[k] = s.x;
-                H1 += hW * s.x;
-                if (JAC) {
-                    const double comp = s.x * mw_rho;
-                    const double a = s.z + comp, b = s.w - comp;
-                    if (k < last) {
-                        VEC(g, V_ROWT)[k + 1] = wk * s.y;
-                        VEC(g, V_ROWA)[k + 1] = wk * a;
-                        VEC(g, V_ROWB)[k + 1] = wk * b;
-                    }
-                    HT += hW * s.y; HA += hW * a; HB += hW * b; SCP += cpv[k] * wk * s.x;
-                }
-            }
-            H1 = warp_sum(H1);
-            if (JAC) { HA = warp_sum(HA); HB = warp_sum(HB); HT = warp_sum(HT); SCP = warp_sum(SCP); }
-            if (lane == 0) {
-                sc[S_H1] = H1;
-                if (JAC) {
-                    // energy-equation row (cj:3095-3254) and jac[0] (cj:1853-1905)
-                    const double rho = sc[S_RHO], cpavg = sc[S_CPAVG];
-                    const double nwt = sc[S_NWT];
-                    VEC(g, V_ROWA)[0] = nwt * HA;
-                    VEC(g, V_ROWB)[0] = nwt * HB;
-                    VEC(g, V_ROWT)[0] = -(-sc[S_WDCP] / cpavg * H1 + SCP + HT * rho) / (rho * cpavg);
-                    sc[S_XT] = H1 / (rho * cpavg * cpavg);
-                }
-            }
-        } else if (JAC) {
-            const int t0 = tid - 32 * G, tn = blockDim.x - 32 * G;
-            for (int t = t0; t < tb.nsplit; t += tn) {
-                const int c0 = tb.cmb_off[t], c1 = tb.cmb_off[t + 1];
+            const double* raw = smem + L.off_raw;
+            double* tile = smem + L.off_tile;
+            for (int e = tid; e < tb.d_cls[1]; e += blockDim.x)
+                gather_fixed<G, 8>(tb.d_con + tb.d_ccon[0] + e * 8, raw, tile + (int)__ldg(tb.d_dst + e) * G);
+            for (int e = tb.d_cls[1] + tid; e < tb.d_cls[2]; e += blockDim.x)
+                gather_fixed<G, 4>(tb.d_con + tb.d_ccon[1] + (e - tb.d_cls[1]) * 4, raw, tile + (int)__ldg(tb.d_dst + e) * G);
+            for (int e = tb.d_cls[2] + tid; e < tb.d_cls[3]; e += blockDim.x)
+                gather_fixed<G, 2>(tb.d_con + tb.d_ccon[2] + (e - tb.d_cls[2]) * 2, raw, tile + (int)__ldg(tb.d_dst + e) * G);
+            for (int e = tb.d_cls[3] + tid; e < tb.d_cls[4]; e += blockDim.x)
+                gather_fixed<G, 1>(tb.d_con + tb.d_ccon[3] + (e - tb.d_cls[3]), raw, tile + (int)__ldg(tb.d_dst + e) * G);
+            // quad entries: four lanes per element, lists padded to multiples of 16 words
+            const int q = lane & 3;
+            const double* rh = smem + L.off_rh;
+            for (int eb = (tid >> 2); eb < ((tb.nq + 7) & ~7); eb += blockDim.x >> 2) {
+                const bool on = eb < tb.nq;
+                const int e = on ? eb : 0;
+                const int o0 = __ldg(tb.q_off + e), o1 = on ? __ldg(tb.q_off + e + 1) : o0;
+                const bool trow = e >= tb.nq_j;
                 double acc[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) acc[g] = 0.0;
-                for (int c = c0; c < c1; ++c) {
-                    const int ix = tb.cmb_idx[c];
+                for (int o = o0 + q * 4; o < o1; o += 16) {
+                    const uint4 ww = __ldg((const uint4*)(tb.q_con + o));
+                    const unsigned w[4] = {ww.x, ww.y, ww.z, ww.w};
 #pragma unroll
-                    for (int g = 0; g < G; ++g) acc[g] += SVALV(g)[ix];
+                    for (int i = 0; i < 4; ++i) {
+                        double v[G], cf[G];
+                        ldv<G>(raw + (w[i] & 0xFFFFu) * G, v);
+                        if (trow) ldv<G>(rh + (w[i] >> 16) * G, cf);
+                        else {
+#pragma unroll
+                            for (int g = 0; g < G; ++g) cf[g] = coef_of(w[i]);
+                        }
+#pragma unroll
+                        for (int g = 0; g < G; ++g) acc[g] = fma(cf[g], v[g], acc[g]);
+                    }
                 }
 #pragma unroll
-                for (int g = 0; g < G; ++g) SVALV(g)[tb.nsub + t] = acc[g];
+                for (int g = 0; g < G; ++g) {
+                    acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], 1);
+                    acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], 2);
+                }
+                if (on && q == 0) stv<G>(tile + (int)__ldg(tb.q_dst + e) * G, acc);
             }
         }
         __syncthreads();
 
-        // ------------------------------------------------------------ rates / dydt outputs
-        if (RATES || (MODE & M_DYDT)) {
-            for (int g = warp; g < G; g += nwarps) {
-                const long long s = s0 + g;
-                if (s >= io.n) continue;
-                const double* sc = SCAL(buf, g);
-                const double* wd = VEC(g, V_WDOT);
+        // ------------------------------------------------------------ phase E  (|| row 0, A of next group)
+        const long long next = grp + gridDim.x;
+        if (warp < G) {
+            const int g = warp;
+            const long long s = s0 + g;
+            // five dot products over the species: H1 (dydt[0]) and the energy-equation row
+            double H1 = 0.0, HA = 0.0, HB = 0.0, HT = 0.0, SCP = 0.0;
+            const double* cpv = smem + L.off_cp + buf * L.nsp1 * G;
+            for (int k = lane; k < nsp; k += 32) {
+                const double hW = smem[L.off_hW + k * G + g], wd = smem[L.off_wdot + k * G + g];
+                H1 += hW * wd;
+                if (JAC) {
+                    HT += hW * smem[L.off_sT + k * G + g];
+                    HA += hW * smem[L.off_a + k * G + g];
+                    HB += hW * smem[L.off_b + k * G + g];
+                    SCP += cpv[k * G + g] * __ldg(tb.sp_w + k) * wd;
+                }
+            }
+            H1 = warp_sum(H1);
+            const double rho = sc[S_RHO * G + g], cpavg = sc[S_CPAVG * G + g], rho_inv = sc[S_RHOINV * G + g];
+            if (JAC) {
+                HA = warp_sum(HA); HB = warp_sum(HB); HT = warp_sum(HT); SCP = warp_sum(SCP);
+                if (s < io.n) {
+                    // energy-equation row (cj:3095-3254) and jac[0] (cj:1853-1905)
+                    const double nwt = sc[S_NWT * G + g];
+                    const double XT = H1 / (rho * cpavg * cpavg);
+                    const double A0 = nwt * HA, B0 = nwt * HB;
+                    const bool sf = io.jac_layout != 0;
+                    double* base = sf ? io.jac + s : io.jac + s * (long long)(nsp * nsp);
+                    const long long es = sf ? io.jac_ld : 1;
+                    const double* tile = smem + L.off_tile;
+                    const double cpl = cpv[last * G + g];
+                    for (int col = lane; col < nsp; col += 32) {
+                        double v;
+                        if (col == 0) {
+                            v = -(-sc[S_WDCP * G + g] / cpavg * H1 + SCP + HT * rho) / (rho * cpavg);
+                        } else {
+                            const int j = col - 1;
+                            const double iwj = __ldg(tb.sp_iw + j), mwfj = __ldg(tb.sp_mwf + j);
+                            v = iwj * (A0 + B0 * mwfj + nwt * tile[(col * nsp) * G + g])
+                                + XT * (cpv[j * G + g] - cpl);
+                        }
+                        base[(long long)(col * nsp) * es] = v;
+                    }
+                }
+            }
+            // rates / dydt outputs of this state
+            if ((RATES || (MODE & M_DYDT)) && s < io.n) {
                 for (int k = lane; k < nsp; k += 32) {
-                    if (RATES && io.sr) put(io.sr, io, nsp, s, k, wd[k]);
+                    const double wd = smem[L.off_wdot + k * G + g];
+                    if (RATES && io.sr) put(io.sr, io, nsp, s, k, wd);
                     if (io.dy && k < last) {
-                        const double v = wd[k] * tb.sp_w[k] * sc[S_RHOINV];
+                        const double v = wd * __ldg(tb.sp_w + k) * rho_inv;
                         if (RATES) put(io.dy, io, nsp, s, k + 1, v);
                         else io.dy[s * io.dy_ss + (long long)(k + 1) * io.dy_sv] = v;
                     }
                 }
                 if (lane == 0 && io.dy) {
-                    const double v = -1.0 / (sc[S_RHO] * sc[S_CPAVG]) * sc[S_H1];
+                    const double v = -1.0 / (rho * cpavg) * H1;
                     if (RATES) put(io.dy, io, nsp, s, 0, v);
                     else io.dy[s * io.dy_ss] = v;
                 }
             }
-        }
-
-        // ------------------------------------------------------------ phase E  (|| A of next group)
-        const long long next = grp + gridDim.x;
-        const bool a_here = split_roles && warp < G;
-        if (a_here) {
-            if (next < ngroups) phase_a(next * G, buf ^ 1, warp);
+            if (next < ngroups) phase_a(next * G, buf ^ 1, g);
         } else if (JAC) {
-            const int w0 = split_roles ? warp - G : warp, wn = split_roles ? nwarps - G : nwarps;
+            // columns: warp -> (row chunk, column subset); lanes = species rows k (output row k+1)
+            const int nchunks = (last + 31) >> 5;
+            const int ew = warp - G, enw = nwarps - G;
             const bool sf = io.jac_layout != 0;
-            for (int g = 0; g < G; ++g) {
-                const long long s = s0 + g;
-                if (s >= io.n) break;
-                const double* sc = SCAL(buf, g);
-                const double* cp = CPV(buf, g);
-                const double *rT = VEC(g, V_ROWT), *rA = VEC(g, V_ROWA), *rB = VEC(g, V_ROWB);
-                const double* sv = SVALV(g);
-                const double XT = sc[S_XT];
-                if (sf) {
-                    store_columns<0, true>(tb, nsp, lane, w0, wn, rT, rA, rB, sv, cp, XT, io.jac + s, io.jac_ld);
-                } else {
-                    double* base = io.jac + s * (long long)(nsp * nsp);
-                    if (nsp <= 32) store_columns<1, false>(tb, nsp, lane, w0, wn, rT, rA, rB, sv, cp, XT, base, 1);
-                    else if (nsp <= 64) store_columns<2, false>(tb, nsp, lane, w0, wn, rT, rA, rB, sv, cp, XT, base, 1);
-                    else if (nsp <= 128) store_columns<4, false>(tb, nsp, lane, w0, wn, rT, rA, rB, sv, cp, XT, base, 1);
-                    else store_columns<0, false>(tb, nsp, lane, w0, wn, rT, rA, rB, sv, cp, XT, base, 1);
+            const double* tile = smem + L.off_tile;
+            auto columns = [&](int ch, int c0, int cstep) {
+                const int k = ch * 32 + lane;
+                const bool on = k < last;
+                const int kk = on ? k : 0;
+                const double wk = __ldg(tb.sp_w + kk);
+                double WA[G], WB[G], WT[G];
+                ldv<G>(smem + L.off_a + kk * G, WA);
+                ldv<G>(smem + L.off_b + kk * G, WB);
+                ldv<G>(smem + L.off_sT + kk * G, WT);
+#pragma unroll
+                for (int g = 0; g < G; ++g) { WA[g] *= wk; WB[g] *= wk; WT[g] *= wk; }
+                for (int col = c0; col < nsp; col += cstep) {
+                    double v[G];
+                    if (col == 0) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) v[g] = WT[g];
+                    } else {
+                        const int j = col - 1;
+                        const double iwj = __ldg(tb.sp_iw + j), mwfj = __ldg(tb.sp_mwf + j);
+                        double S[G];
+                        ldv<G>(tile + (col * nsp + kk + 1) * G, S);
+#pragma unroll
+                        for (int g = 0; g < G; ++g) v[g] = iwj * (WA[g] + WB[g] * mwfj + wk * S[g]);
+                    }
+                    if (on) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            const long long s = s0 + g;
+                            if (s < io.n) {
+                                if (sf) io.jac[(long long)(col * nsp + k + 1) * io.jac_ld + s] = v[g];
+                                else io.jac[s * (long long)(nsp * nsp) + col * nsp + k + 1] = v[g];
+                            }
+                        }
+                    }
                 }
+            };
+            if (enw >= nchunks) {
+                const int ch = ew % nchunks;
+                columns(ch, ew / nchunks, (enw - ch + nchunks - 1) / nchunks);
+            } else {
+                for (int ch = ew; ch < nchunks; ch += enw) columns(ch, 0, 1);
             }
-        }
-        if (!split_roles) {
-            __syncthreads();
-            if (next < ngroups)
-                for (int g = warp; g < G; g += nwarps) phase_a(next * G, buf ^ 1, g);
         }
         __syncthreads();
     }
-#undef SPV
-#undef VEC
-#undef CPV
-#undef SCAL
-#undef R4V
-#undef RHV
-#undef RAWV
-#undef PARTV
-#undef SVALV
 }
 
 // ---- small kernels behind the reference-named scalar entry points ---------------------

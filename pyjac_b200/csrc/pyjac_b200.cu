@@ -66,19 +66,20 @@ int fail(int code, const std::string& msg)
 Layout make_layout(const Tables& tb, int G, bool jac)
 {
     Layout L{};
-    auto even = [](int v) { return (v + 1) & ~1; };
-    L.nsp1 = even(tb.nsp + 1);
+    L.nsp1 = tb.nsp + 1;
     int off = 0;
-    L.off_spv = off;  L.st_spv = 4 * L.nsp1;            off += G * L.st_spv;
-    L.off_vec = off;  L.st_vec = pj::NVEC * L.nsp1;     off += G * L.st_vec;
-    L.off_cp = off;   L.st_cp = L.nsp1;                 off += 2 * G * L.st_cp;
-    L.off_y = off;    L.st_y = L.nsp1;                  off += G * L.st_y;
-    L.off_scal = off;                                   off += 2 * G * pj::NSCAL;
-    L.off_r4 = off;   L.st_r4 = 4 * tb.nr;              off += G * L.st_r4;
-    L.off_part = off; L.st_part = 4 * tb.nchunk;        off += G * L.st_part;
-    L.off_rh = off;   L.st_rh = even(tb.nr);            if (jac) off += G * L.st_rh;
-    L.off_raw = off;  L.st_raw = even(tb.nraw + 1);     if (jac) off += G * L.st_raw;
-    L.off_sval = off; L.st_sval = even(tb.zero_slot + 1); if (jac) off += G * L.st_sval;
+    auto take = [&](int n) { int o = off; off += ((n * G + 1) & ~1); return o; };
+    L.off_C = take(L.nsp1); L.off_B = take(L.nsp1); L.off_dB = take(L.nsp1); L.off_hW = take(L.nsp1);
+    L.off_wdot = take(L.nsp1); L.off_sT = take(L.nsp1); L.off_a = take(L.nsp1); L.off_b = take(L.nsp1);
+    L.off_cp = take(2 * L.nsp1);
+    L.off_y = take(L.nsp1);
+    L.off_scal = take(2 * pj::NSCAL);
+    L.off_net = take(tb.nr);
+    if (jac) {
+        L.off_tT = take(tb.nr); L.off_X1 = take(tb.nr); L.off_X2 = take(tb.nr); L.off_rh = take(tb.nr);
+        L.off_raw = take(tb.nraw + 2);
+        L.off_tile = take(tb.nsp * tb.nsp);
+    }
     L.total = off;
     return L;
 }
@@ -88,8 +89,7 @@ const void* kernel_for(int G)
 {
     switch (G) {
     case 1: return (const void*)pj::k_eval<1, MODE, MINB>;
-    case 2: return (const void*)pj::k_eval<2, MODE, MINB>;
-    default: return (const void*)pj::k_eval<4, MODE, MINB>;
+    default: return (const void*)pj::k_eval<2, MODE, MINB>;
     }
 }
 
@@ -107,7 +107,7 @@ const void* kernel_ptr(int mode_ix, int G, int minb)
 int configure(pyjac_mech* m, int mode_ix)
 {
     const bool jac = mode_ix == 0;
-    const int cands[3] = {4, 2, 1};
+    const int cands[2] = {2, 1};
     int G = 0;
     if (m->user_G) {
         G = m->user_G;
@@ -126,7 +126,7 @@ int configure(pyjac_mech* m, int mode_ix)
         return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
     const size_t bytes = (size_t)make_layout(m->tb, G, jac).total * 8;
     int threads = m->user_threads ? m->user_threads : 384;
-    threads = std::max(32 * (G + 1), std::min(512, (threads + 31) / 32 * 32));
+    threads = std::max(32 * (G + 2), std::min(512, (threads + 31) / 32 * 32));
     int bpsm = (int)((size_t)m->smem_per_sm / (bytes + 1024));
     bpsm = std::max(1, std::min(bpsm, 2048 / threads));
     if (m->user_bpsm) bpsm = std::max(1, std::min(bpsm, m->user_bpsm));
@@ -240,32 +240,34 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     pyjac_mech* m = new pyjac_mech();
     m->device = device;
     Tables& t = m->tb;
-    t.nsp = d[0]; t.nr = d[1]; t.nrev = d[2]; t.npd = d[3]; t.nraw = d[4]; t.nsub = d[5];
-    t.ncon = d[6]; t.ncoef = d[7]; t.first_pm = d[8]; t.npm = d[9]; t.nsub_j = d[12]; t.nsplit = d[13];
-    t.nchunk = d[14]; t.zero_slot = d[15];
+    const pjt::Entry* d3e = pjt::find(blob, "dims3");
+    if (!d3e || d3e->dtype != 1 || d3e->count < 8) { delete m; return fail(PYJAC_EINVAL, "table blob lacks dims3"); }
+    const int* d3 = (const int*)((const char*)blob + d3e->offset);
+    t.nsp = d[0]; t.nr = d[1]; t.nrev = d[2]; t.npd = d[3]; t.nraw = d[4];
+    t.first_pm = d[8]; t.npm = d[9];
+    t.nfix = d3[0]; t.nq = d3[1]; t.nq_j = d3[2];
     t.ru = c[0];
     int rc = PYJAC_OK;
 #define UP(field, name, type, code) if (!rc) rc = upload<type>(m, blob, name, &t.field, code)
     UP(sp_w, "sp_w", double, 0); UP(sp_iw, "sp_iw", double, 0); UP(sp_ruw, "sp_ruw", double, 0);
     UP(sp_tmid, "sp_tmid", double, 0); UP(sp_mwf, "sp_mwf", double, 0); UP(sp_nasa, "sp_nasa", double, 0);
-    UP(rx_rec, "rx_rec", int4, 1);
+    UP(rx_rec, "rx_rec", int4, 1); UP(rx_dst, "rx_dst", uint4, 2);
     UP(pm_par, "pm_par", double, 0); UP(pm_sp, "pm_sp", int, 1);
     UP(pm_eff_off, "pm_eff_off", int, 1); UP(pm_eff_sp, "pm_eff_sp", int, 1); UP(pm_eff_am1, "pm_eff_am1", double, 0);
-    UP(chk_rx, "chk_rx", int, 1); UP(chk_nu, "chk_nu", double, 0); UP(sp_chk_off, "sp_chk_off", int, 1);
-    UP(con, "con", unsigned, 1); UP(sub_w, "sub_w", double, 0);
-    UP(cmb_off, "cmb_off", int, 1); UP(cmb_idx, "cmb_idx", int, 1);
-    UP(jmap, "jmap", unsigned short, 2);
+    UP(red_off, "red_off", int, 1); UP(red_pk, "red_pk", unsigned, 1);
+    UP(d_dst, "d_dst", unsigned short, 2); UP(d_con, "d_con", unsigned, 1);
+    UP(q_dst, "q_dst", unsigned short, 2); UP(q_off, "q_off", int, 1); UP(q_con, "q_con", unsigned, 1);
     if (!rc) {
-        const pjt::Entry* s_ = pjt::find(blob, "cls_sub");
-        const pjt::Entry* c_ = pjt::find(blob, "cls_con");
-        if (!s_ || !c_ || s_->dtype != 1 || c_->dtype != 1 || s_->count != 9 || c_->count != 8)
-            rc = fail(PYJAC_EINVAL, "table blob lacks cls_sub / cls_con");
+        const pjt::Entry* s_ = pjt::find(blob, "d_cls");
+        const pjt::Entry* c_ = pjt::find(blob, "d_ccon");
+        if (!s_ || !c_ || s_->dtype != 1 || c_->dtype != 1 || s_->count != 5 || c_->count != 4)
+            rc = fail(PYJAC_EINVAL, "table blob lacks d_cls / d_ccon");
         else {
-            std::memcpy(t.cls_sub, (const char*)blob + s_->offset, sizeof(t.cls_sub));
-            std::memcpy(t.cls_con, (const char*)blob + c_->offset, sizeof(t.cls_con));
+            std::memcpy(t.d_cls, (const char*)blob + s_->offset, sizeof(t.d_cls));
+            std::memcpy(t.d_ccon, (const char*)blob + c_->offset, sizeof(t.d_ccon));
         }
     }
-    UP(red_off, "red_off", int, 1); UP(red_rx, "red_rx", int, 1); UP(red_nu, "red_nu", double, 0);
+    UP(red_rx, "red_rx", int, 1); UP(red_nu, "red_nu", double, 0);
 #undef UP
     if (!rc) {
         cudaDeviceProp prop;
@@ -303,8 +305,8 @@ int pyjac_mech_dims(const pyjac_mech* m, int dims[4])
 int pyjac_mech_tune(pyjac_mech* m, int states_per_block, int threads, int blocks_per_sm)
 {
     if (!m) return fail(PYJAC_EINVAL, "NULL mechanism");
-    if (states_per_block != 0 && states_per_block != 1 && states_per_block != 2 && states_per_block != 4)
-        return fail(PYJAC_EINVAL, "states_per_block must be 0, 1, 2 or 4");
+    if (states_per_block != 0 && states_per_block != 1 && states_per_block != 2)
+        return fail(PYJAC_EINVAL, "states_per_block must be 0, 1 or 2");
     m->user_G = states_per_block; m->user_threads = threads; m->user_bpsm = blocks_per_sm;
     m->G[0] = m->G[1] = m->G[2] = 0;    // re-derive at next launch
     return PYJAC_OK;

@@ -483,6 +483,78 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
             jmap[o[1], 0] = slot
     T['jmap'] = jmap.ravel()
 
+    # ---------------- v3 kernel tables -------------------------------------------------
+    # rx_dst[p][0..5]: raw slot written by concentration slot a (0xFFFF: none);
+    # [6]: first collider-list raw slot, [7]: raw slot of pres_mod_temp (0xFFFF: none)
+    NONE = 0xFFFF
+    rx_dst = np.full((nr, 8), NONE, dtype=np.uint16)
+    for p, i in enumerate(order):
+        for a in range(2 * MAXS):
+            if raw_of_slot[i][a] >= 0:
+                rx_dst[p, a] = raw_of_slot[i][a]
+        if raw_of_eff[i]:
+            rx_dst[p, 6] = min(raw_of_eff[i].values())
+        if raw_of_pmt[i] >= 0:
+            rx_dst[p, 7] = raw_of_pmt[i]
+    T['rx_dst'] = rx_dst.ravel()
+
+    def hi16(c: float) -> int:
+        """Top 16 bits of the double c; the kernel rebuilds c as (hi16 << 48)."""
+        bits = int(np.float64(c).view(np.uint64))
+        if bits & ((1 << 48) - 1):
+            raise UnsupportedMechanism('stoichiometric coefficient %r not representable' % c)
+        return bits >> 48
+
+    # species reductions, one packed word per (reaction, nu): reaction | hi16(nu) << 16
+    T['red_pk'] = np.asarray([p | (hi16(nu) << 16) for lst in red for p, nu in lst] or [0],
+                             dtype=np.uint32).view(np.int32)
+
+    # sparse part, one entry per structurally non-zero Jacobian element.  dst = r + NSP*(j+1)
+    # with r the output row (0: energy equation, k+1: species k).  Entries with <= 8
+    # contributions go to the fixed-length classes (8, 4, 2, 1; one thread each, padded with
+    # null contributions); longer ones and every energy-row entry are summed by four lanes
+    # ("quad" entries, list padded to a multiple of 16 words, lane q takes words 4q..4q+3 of
+    # each 16).  J word: raw slot | hi16(nu) << 16; T word: raw slot | reaction << 16.
+    null_j = nraw                      # zero raw slot, coefficient +0.0
+    fixed = {8: [], 4: [], 2: [], 1: []}
+    quad_j, quad_t = [], []
+    for (k, j), lst in sorted(contrib.items()):
+        if k == last:
+            continue
+        words = [src | (hi16(c) << 16) for src, c in lst]
+        dst = (k + 1) + nsp * (j + 1)
+        if len(words) <= 8:
+            ln = cls_len(len(words))
+            fixed[ln].append((dst, words + [null_j] * (ln - len(words))))
+        else:
+            quad_j.append((dst, words))
+    for j, lst in sorted(tcontrib.items()):
+        quad_t.append((nsp * (j + 1), [src | (p << 16) for src, p in lst]))
+    d_dst, d_con, d_cls, d_ccon = [], [], [0], []
+    for ln in (8, 4, 2, 1):
+        while len(d_con) % 4:
+            d_con.append(null_j)
+        d_ccon.append(len(d_con))
+        for dst, words in fixed[ln]:
+            d_dst.append(dst)
+            d_con += words
+        d_cls.append(len(d_dst))
+    quad_j.sort(key=lambda e: -len(e[1]))
+    quad_t.sort(key=lambda e: -len(e[1]))
+    q_dst, q_off, q_con = [], [0], []
+    for dst, words in quad_j + quad_t:
+        q_dst.append(dst)
+        q_con += words + [null_j] * ((-len(words)) % 16)
+        q_off.append(len(q_con))
+    T['d_dst'] = np.asarray(d_dst or [0], dtype=np.uint16)
+    T['d_con'] = np.asarray(d_con + [null_j] * 8, dtype=np.uint32).view(np.int32)
+    T['d_cls'] = i32(d_cls)
+    T['d_ccon'] = i32(d_ccon)
+    T['q_dst'] = np.asarray(q_dst or [0], dtype=np.uint16)
+    T['q_off'] = i32(q_off)
+    T['q_con'] = np.asarray(q_con + [null_j] * 16, dtype=np.uint32).view(np.int32)
+    T['dims3'] = i32([len(d_dst), len(q_dst), len(quad_j), len(d_con), len(q_con), 0, 0, 0])
+
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
     T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, nsub, len(con), 0,
                      first_pm, npm, red_off[-1], max(len(l) for l in red),

@@ -52,6 +52,7 @@ def evaluate(Tb, P, y):
     flags, slots, arr = Tb['rx_flags'], Tb['rx_slots'].reshape(nr, 6), Tb['rx_arr'].reshape(nr, 4)
     par_all = Tb['pm_par'].reshape(-1, tb.NPAR)
     raw = np.zeros((n, nraw + 1))
+    rx_dst = Tb['rx_dst'].reshape(nr, 8)
     R4 = np.zeros((nr, 4, n))
     RH = np.zeros((nr, n))
     hw = np.zeros((n, nsp + 1))
@@ -176,7 +177,7 @@ def evaluate(Tb, P, y):
         adef = par[5] if has_pm else 0.0
         X1 = jy + adef * pmt
         X2 = -jy - aN * pmt
-        rb = int(Tb['rx_raw_base'][p])
+        dst = rx_dst[p]
         for a in range(3):
             if s[a] == nsp:
                 continue
@@ -184,8 +185,8 @@ def evaluate(Tb, P, y):
             if s[a] == last:
                 X2 = X2 - dv
             else:
-                raw[:, rb] = dv
-                rb += 1
+                assert dst[a] != 0xFFFF
+                raw[:, dst[a]] = dv
         if isrev:
             for a in range(3):
                 if s[3 + a] == nsp:
@@ -194,72 +195,78 @@ def evaluate(Tb, P, y):
                 if s[3 + a] == last:
                     X2 = X2 - dv
                 else:
-                    raw[:, rb] = dv
-                    rb += 1
+                    assert dst[3 + a] != 0xFFFF
+                    raw[:, dst[3 + a]] = dv
         if fl & tb.F_EFF_SLOTS:
+            rb = int(dst[6])
             for e in range(Tb['pm_eff_off'][mi], Tb['pm_eff_off'][mi + 1]):
                 if Tb['pm_eff_sp'][e] != last:
                     raw[:, rb] = pmt * Tb['pm_eff_am1'][e]
                     rb += 1
         if fl & tb.F_WANT_PMT:
-            raw[:, rb] = pmt
+            raw[:, dst[7]] = pmt
         R4[p, 0], R4[p, 1], R4[p, 2], R4[p, 3] = net * PM, tT, X1, X2
         RH[p] = (hw[:, s[3]] + hw[:, s[4]] + hw[:, s[5]]) - (hw[:, s[0]] + hw[:, s[1]] + hw[:, s[2]])
 
-    # --- species reductions (chunked two-level, as the kernel does)
-    nchunk = int(d[14])
-    part = np.zeros((nchunk, 4, n))
-    crx, cnu = Tb['chk_rx'].reshape(-1, tb.RCH), Tb['chk_nu'].reshape(-1, tb.RCH)
-    for c in range(nchunk):
-        for e in range(tb.RCH):
-            part[c] += cnu[c, e] * R4[crx[c, e]]
+    # --- species reductions: packed (reaction | hi16(nu) << 16) lists per species
+    def coef(word):
+        return float(np.uint64((int(word) >> 16) << 48).view(np.float64))
+    red_pk = Tb['red_pk'].view(np.uint32)
     wdot = np.zeros((n, nsp)); tcol = np.zeros((n, nsp)); Ak = np.zeros((n, nsp)); Bk = np.zeros((n, nsp))
     for k in range(nsp):
-        for c in range(Tb['sp_chk_off'][k], Tb['sp_chk_off'][k + 1]):
-            wdot[:, k] += part[c, 0]; tcol[:, k] += part[c, 1]; Ak[:, k] += part[c, 2]; Bk[:, k] += part[c, 3]
+        for e in range(Tb['red_off'][k], Tb['red_off'][k + 1]):
+            wd = red_pk[e]
+            cf, rxn = coef(wd), int(wd) & 0xFFFF
+            wdot[:, k] += cf * R4[rxn, 0]; tcol[:, k] += cf * R4[rxn, 1]
+            Ak[:, k] += cf * R4[rxn, 2]; Bk[:, k] += cf * R4[rxn, 3]
     comp = wdot * (mw_avg * rho_inv)[:, None]
-    Ak = w[None, :] * (Ak + comp)
-    Bk = w[None, :] * (Bk - comp)
-    tc = w[None, :] * tcol
+    Ak = Ak + comp                       # unscaled a_k, b_k, as the kernel keeps them
+    Bk = Bk - comp
 
-    # --- sparse gather: class-padded sub-entries, then the combine lists
-    nsub, nsub_j, nsplit, zero_slot = int(d[5]), int(d[12]), int(d[13]), int(d[15])
-    sval = np.zeros((n, zero_slot + 1))
-    con = Tb['con'].view(np.uint32)
+    # --- sparse gather into the dense tile: fixed-length classes, then quad entries
+    nfix, nq, nq_j = (int(v) for v in Tb['dims3'][:3])
+    tile = np.zeros((n, nsp * nsp))
     raw[:, nraw] = 0.0
-    wt = 1.0 / cp_avg
-    lens = [8, 4, 2, 1, 8, 4, 2, 1]
-    for c in range(8):
-        for e in range(Tb['cls_sub'][c], Tb['cls_sub'][c + 1]):
-            o = Tb['cls_con'][c] + (e - Tb['cls_sub'][c]) * lens[c]
-            for cc in con[o:o + lens[c]]:
-                cc = int(cc)
-                if c < 4:
-                    cf = float(np.uint32(cc & 0xFFFF0000).view(np.float32))
-                    sval[:, e] += cf * raw[:, cc & 0xFFFF]
-                else:
-                    sval[:, e] += RH[cc >> 16] * raw[:, cc & 0xFFFF]
-            sval[:, e] *= Tb['sub_w'][e] if c < 4 else -wt
-    for t in range(nsplit):
-        for cidx in range(Tb['cmb_off'][t], Tb['cmb_off'][t + 1]):
-            sval[:, nsub + t] += sval[:, Tb['cmb_idx'][cidx]]
+    d_con, q_con = Tb['d_con'].view(np.uint32), Tb['q_con'].view(np.uint32)
+    for c, ln in enumerate((8, 4, 2, 1)):
+        for e in range(Tb['d_cls'][c], Tb['d_cls'][c + 1]):
+            o = Tb['d_ccon'][c] + (e - Tb['d_cls'][c]) * ln
+            acc = np.zeros(n)
+            for wd in d_con[o:o + ln]:
+                acc += coef(wd) * raw[:, int(wd) & 0xFFFF]
+            assert not tile[:, Tb['d_dst'][e]].any()
+            tile[:, Tb['d_dst'][e]] = acc
+    for e in range(nq):
+        acc = np.zeros(n)
+        assert (Tb['q_off'][e + 1] - Tb['q_off'][e]) % 16 == 0
+        for wd in q_con[Tb['q_off'][e]:Tb['q_off'][e + 1]]:
+            if e < nq_j:
+                acc += coef(wd) * raw[:, int(wd) & 0xFFFF]
+            else:
+                acc += RH[int(wd) >> 16] * raw[:, int(wd) & 0xFFFF]
+        assert not tile[:, Tb['q_dst'][e]].any()
+        tile[:, Tb['q_dst'][e]] = acc
+    tile = tile.reshape(n, nsp, nsp)       # [state, col, row]
 
-    # --- assembly: output row r of column j+1 is iw_j (rowA[r] + rowB[r] mwf_j + sval[jmap[j][r]])
-    jmap = Tb['jmap'].reshape(nsp - 1, nsp)
+    # --- assembly: row k+1 of column j+1 is iw_j (W_k a_k + W_k b_k mwf_j + W_k tile);
+    # row 0 (energy equation) uses -1/cp_avg times the dH-weighted sums
     jac = np.zeros((n, nsp, nsp))          # [state, col, row]
-    H1 = (hw[:, :nsp] * wdot).sum(axis=1)
-    HA = (h * Ak).sum(axis=1)
-    HB = (h * Bk).sum(axis=1)
-    HT = (h * tc).sum(axis=1)
+    wt = 1.0 / cp_avg
+    hwk = hw[:, :nsp]
+    H1 = (hwk * wdot).sum(axis=1)
+    HA = (hwk * Ak).sum(axis=1)
+    HB = (hwk * Bk).sum(axis=1)
+    HT = (hwk * tcol).sum(axis=1)
     SCP = (cp * w[None, :] * wdot).sum(axis=1)
     XT = H1 / (rho * cp_avg * cp_avg)
-    rowA = np.concatenate([(-wt * HA)[:, None], Ak[:, :last]], axis=1)
-    rowB = np.concatenate([(-wt * HB)[:, None], Bk[:, :last]], axis=1)
+    WA, WB = w[None, :last] * Ak[:, :last], w[None, :last] * Bk[:, :last]
     for j in range(nsp - 1):
-        v = iw[j] * (rowA + rowB * mwf[j] + sval[:, jmap[j]])
-        v[:, 0] += XT * (cp[:, j] - cp[:, last])
+        v = np.empty((n, nsp))
+        v[:, 1:] = iw[j] * (WA + WB * mwf[j] + w[None, :last] * tile[:, j + 1, 1:])
+        v[:, 0] = iw[j] * (-wt * HA + -wt * HB * mwf[j] + -wt * tile[:, j + 1, 0]) \
+            + XT * (cp[:, j] - cp[:, last])
         jac[:, j + 1, :] = v
-    jac[:, 0, 1:] = tc[:, :last]
+    jac[:, 0, 1:] = w[None, :last] * tcol[:, :last]
     s0 = -wdcp / cp_avg * H1 + SCP + HT * rho
     jac[:, 0, 0] = -s0 / (rho * cp_avg)
 

@@ -19,7 +19,7 @@ def main():
     ap.add_argument('--mech', default=os.path.join(ROOT, 'tests', 'golden', 'gri30_syn.inp'))
     ap.add_argument('--shape', default=None, help='synthetic shape name instead of --mech')
     ap.add_argument('--n', type=int, default=262144)
-    ap.add_argument('--configs', default='1:256:0,2:256:0,2:384:0,4:384:0,4:512:0,2:512:0,1:128:0')
+    ap.add_argument('--configs', default='2:384:0,2:256:0,2:320:0,2:512:0,1:256:0,1:384:0,1:512:0')
     ap.add_argument('--layout', default='rows')
     ap.add_argument('--reps', type=int, default=5)
     a = ap.parse_args()
