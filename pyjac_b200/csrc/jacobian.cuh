@@ -1,0 +1,596 @@
+// eval_jacob for sm_100a: the analytical Jacobian of a batch of states, driven by mechanism
+// tables (pyjac_b200/tables.py) and a static work schedule (pyjac_b200/plan.py).
+//
+// Replaces the reference's generated, fully unrolled one-thread-per-state eval_jacob
+// (pyjac/core/create_jacobian.py:2189-3298) together with the rate routines it calls
+// (rate_subs.py:254-876, 879-1294, 1297-1542, 1626-1706, 1806-2086).
+//
+// A persistent thread block evaluates GS states at a time.  The 32 lanes of a warp are NSUB
+// = 64 / GS sub-groups of GS / 2 lanes; a lane carries two neighbouring states.  Shared
+// memory holds *rows* of GS doubles (one value per state), so one 16-byte access serves both
+// states of a lane, and the NSUB sub-groups of a warp work on NSUB different table items at
+// the same time; table indices are decoded once per item for all GS states.  A species owns
+// eight consecutive rows (C, B, dB/dT, hW, WA, WB, WT, cp), a reaction five (net, tT, X1, X2,
+// dH), so that one address computation serves all values of an item.  All shared-memory
+// traffic uses 32-bit shared-space addresses (ld/st.shared.v2.f64).
+//
+// Phases per group of GS states, separated by block barriers:
+//
+//   A0  warp 0: mass fractions -> Y_N, mean molecular weight, density, per-state scalars
+//   A1  per species: concentration, NASA-7 cp / h / Gibbs term B_k / dB_k/dT
+//   B   per reaction: kf, kr, rates of progress, third-body / fall-off factors and their
+//       derivatives -> (net rate, T-column term, X1, X2, reaction enthalpy) and the non-zero
+//       d(rate)/dC values ("raw" rows)
+//   C   per species: sum_i nu_ki (net, tT, X1, X2) -> the dense rank-2 part of the Jacobian
+//       (WA = W_k a_k, WB = W_k b_k, WT = W_k * T-column); per-warp partial dot products for
+//       the energy equation
+//   DE  per Jacobian element, in steps of NSUB elements of equal (padded) list length:
+//       dense part + sparse gather over raw rows in registers -> one store per element.
+//       Warp 0 first reduces the partial dot products; the energy-equation row (enthalpy-
+//       weighted gathers) runs after the species rows, behind a named barrier that only the
+//       warps owning such elements wait on.
+#pragma once
+#include "kernels.cuh"
+
+namespace pj5 {
+
+using namespace pj;
+
+struct Plan {
+    int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync;
+    const int4* rx;
+    const int *b_off, *b_npm, *b_item;
+    const int *c_off, *c_item;
+    const unsigned* c_con;
+    const int *e_off, *e_nst;
+    const uint2* e_str;
+    const int *t_off, *t_nst;
+    const uint2* t_str;
+    const double2* colfac;
+};
+
+enum : int { Q_T = 0, Q_LOGT, Q_IT, Q_RHO, Q_RHOINV, Q_NMWR, Q_MWR, Q_M,
+             Q_NWT, Q_A0, Q_B0, Q_XT, Q_CPL, NQ = 16 };
+enum : int { D_H1 = 0, D_HA, D_HB, D_HT, D_SCP, D_CPAVG, D_WDCP, NPART = 7 };
+enum : int { SP_C = 0, SP_B, SP_DB, SP_HW, SP_WA, SP_WB, SP_WT, SP_CP, SP_SLOTS, SP_Y = SP_WA };
+enum : int { RX_NET = 0, RX_TT, RX_X1, RX_X2, RX_DH, RX_SLOTS };
+enum : unsigned { NULL_E = 0x3FFFFFu };
+
+struct V {
+    double x, y;
+};
+template <int OFF = 0>
+__device__ __forceinline__ V lds(unsigned a)
+{
+    V v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF = 0>
+__device__ __forceinline__ void sts(unsigned a, V v)
+{
+    asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ V vfma(double a, V b, V c) { return V{fma(a, b.x, c.x), fma(a, b.y, c.y)}; }
+__device__ __forceinline__ V vfma(V a, V b, V c) { return V{fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)}; }
+__device__ __forceinline__ V vadd(V a, V b) { return V{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ V vsub(V a, V b) { return V{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ V vmul(double a, V b) { return V{a * b.x, a * b.y}; }
+__device__ __forceinline__ V vmul(V a, V b) { return V{a.x * b.x, a.y * b.y}; }
+__device__ __forceinline__ V vexp(V a) { return V{exp_fast(a.x), exp_fast(a.y)}; }
+
+// sum over the sub-groups of a warp (lanes with equal state pair); result in every lane
+template <int GS>
+__device__ __forceinline__ double sub_sum(double v)
+{
+#pragma unroll
+    for (int o = GS / 2; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int GS>
+__device__ __forceinline__ V sub_sum(V v) { return V{sub_sum<GS>(v.x), sub_sum<GS>(v.y)}; }
+
+// Everything phase B does for one reaction and the two states of the lane.
+template <int GS, bool PM>
+__device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsigned aSP, unsigned aRX,
+                                         unsigned aRAW, unsigned aSC, int p, bool valid, bool three,
+                                         const V T, const V logT, const V iT)
+{
+    constexpr int RB = GS * 8, SPB = SP_SLOTS * RB, RXB = RX_SLOTS * RB;
+    const int nsp = tb.nsp, last = tb.nsp - 1;
+    const int4* rp = pl.rx + p * 4;
+    const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+    const double lnA = __hiloint2double(q0.y, q0.x), bexp = __hiloint2double(q0.w, q0.z);
+    const double Ta = __hiloint2double(q1.y, q1.x), lnKc = __hiloint2double(q1.w, q1.z);
+    const int fl = q2.x;
+    const unsigned s0 = q2.y & 0xFFFFu, s1 = (unsigned)q2.y >> 16, s2 = q2.z & 0xFFFFu;
+    const unsigned s3 = (unsigned)q2.z >> 16, s4 = q2.w & 0xFFFFu, s5 = (unsigned)q2.w >> 16;
+    const unsigned a0 = aSP + s0 * SPB, a1 = aSP + s1 * SPB, a2 = aSP + s2 * SPB;
+    const unsigned a3 = aSP + s3 * SPB, a4 = aSP + s4 * SPB, a5 = aSP + s5 * SPB;
+    const bool isrev = fl & F_REV;
+
+    // ---- pressure modification first: PM_, and for the Jacobian gg, Xd, e1Fi
+    V PM_{1.0, 1.0}, gg{1.0, 1.0}, Xd{0.0, 0.0}, e1Fi{0.0, 0.0};
+    const int mi = PM ? p - tb.first_pm : 0;
+    const double* par = tb.pm_par + mi * NPAR;
+    if (PM) {
+        V thd = lds<Q_M * RB>(aSC);
+        const int e0 = __ldg(tb.pm_eff_off + mi), e1_ = __ldg(tb.pm_eff_off + mi + 1);
+        for (int e = e0; e < e1_; ++e)
+            thd = vfma(__ldg(tb.pm_eff_am1 + e), lds<SP_C * RB>(aSP + __ldg(tb.pm_eff_sp + e) * SPB), thd);
+        if (fl & F_PDEP) {
+            const int csp = __ldg(tb.pm_sp + mi);
+            const V ctv = csp >= 0 ? lds<SP_C * RB>(aSP + csp * SPB) : thd;
+            const bool low = fl & F_LOW;
+            const double p0 = par[0], p1 = par[1], p2 = par[2], p3 = par[3];
+            const double ct[2] = {ctv.x, ctv.y}, Tt[2] = {T.x, T.y}, lT[2] = {logT.x, logT.y}, rT[2] = {iT.x, iT.y};
+            double Pr[2], i1p[2], F[2], dpr[2], xd[2], g_[2], e1f[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const double e1 = exp_fast(p0 + p1 * lT[g] - p2 * rT[g]);
+                Pr[g] = ct[g] * e1;
+                const double dpr4 = p3 + p2 * rT[g] - 1.0;
+                dpr[g] = p1 + p2 * rT[g] - 1.0;
+                i1p[g] = 1.0 / (1.0 + Pr[g]);
+                if (low) { xd[g] = dpr4 * rT[g] * i1p[g]; g_[g] = i1p[g]; }
+                else { xd[g] = -Pr[g] * dpr4 * rT[g] * i1p[g]; g_[g] = -Pr[g] * i1p[g]; }
+                F[g] = 1.0;
+                e1f[g] = e1;
+            }
+            if (fl & F_TROE) {
+                const double iln10 = 0.43429448190325182765;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const double e3 = exp_fast(Tt[g] / par[7]), e1t = exp_fast(Tt[g] / par[9]);
+                    double Fc = par[6] * e3 + par[8] * e1t;
+                    double dF = par[11] * e3 - par[12] * e1t;
+                    if (fl & F_TROE_T2) {
+                        const double e2 = exp_fast(par[10] * rT[g]);
+                        Fc += e2;
+                        dF += par[13] * rT[g] * rT[g] * e2;
+                    }
+                    const double lnFc = log(fmax(Fc, 1.0e-300));
+                    const double lF = lnFc * iln10, lP = log10_clamped(Pr[g]);
+                    const double A = lP - 0.67 * lF - 0.4;
+                    const double Bq = 0.806 - 1.1762 * lF - 0.14 * lP;
+                    const double q1_ = 1.0 + A * A / (Bq * Bq);
+                    const double lnF_AB = 2.0 * lnFc * A / (Bq * Bq * Bq * q1_ * q1_);
+                    F[g] = exp_fast(lnFc / q1_);
+                    xd[g] += (1.0 / (Fc * q1_) - lnF_AB * (-0.67 * iln10 * Bq + 1.1762 * iln10 * A) / Fc) * dF
+                             - lnF_AB * (Bq * iln10 + 0.14 * iln10 * A) * dpr[g] * rT[g];
+                    g_[g] -= lnF_AB * (Bq * iln10 + A * 0.14 * iln10);
+                }
+            } else if (fl & F_SRI) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const double lP = log10_clamped(Pr[g]);
+                    const double X = 1.0 / (1.0 + lP * lP);
+                    F[g] = pow(par[14] * exp(-par[15] * rT[g]) + exp(-Tt[g] / par[16]), X);
+                    if (fl & F_SRI5) F[g] *= par[17] * pow(Tt[g], par[18]);
+                    const double two_iln10 = 0.86858896380650365530;
+                    const double eb = exp(par[23] * rT[g]), ec = exp(Tt[g] / par[25]);
+                    const double den = par[26] * eb + ec;
+                    xd[g] += X * ((par[22] * rT[g] * rT[g] * eb - par[24] * ec) / den
+                                  - X * two_iln10 * lP * dpr[g] * log(den) * rT[g]);
+                    if (fl & F_SRI5_DT) xd[g] += par[27] * rT[g];
+                    g_[g] -= X * X * two_iln10 * lP * log(par[19] * exp(par[20] * rT[g]) + exp(Tt[g] / par[21]));
+                }
+            }
+            double pm_[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const double Fi = F[g] * i1p[g];
+                pm_[g] = low ? Fi * Pr[g] : Fi;
+                e1f[g] *= Fi;
+            }
+            PM_ = V{pm_[0], pm_[1]}; gg = V{g_[0], g_[1]}; Xd = V{xd[0], xd[1]}; e1Fi = V{e1f[0], e1f[1]};
+        } else {
+            PM_ = thd;
+        }
+    }
+
+    // ---- rate constants and rates of progress
+    const V c0 = lds<SP_C * RB>(a0), c1 = lds<SP_C * RB>(a1), c3 = lds<SP_C * RB>(a3), c4 = lds<SP_C * RB>(a4);
+    V c2{1.0, 1.0}, c5{1.0, 1.0};
+    V sB = vsub(vadd(lds<SP_B * RB>(a3), lds<SP_B * RB>(a4)), vadd(lds<SP_B * RB>(a0), lds<SP_B * RB>(a1)));
+    V sdB = vsub(vadd(lds<SP_DB * RB>(a3), lds<SP_DB * RB>(a4)), vadd(lds<SP_DB * RB>(a0), lds<SP_DB * RB>(a1)));
+    V dH = vsub(vadd(lds<SP_HW * RB>(a3), lds<SP_HW * RB>(a4)), vadd(lds<SP_HW * RB>(a0), lds<SP_HW * RB>(a1)));
+    if (three) {
+        c2 = lds<SP_C * RB>(a2);
+        c5 = lds<SP_C * RB>(a5);
+        sB = vadd(sB, vsub(lds<SP_B * RB>(a5), lds<SP_B * RB>(a2)));
+        sdB = vadd(sdB, vsub(lds<SP_DB * RB>(a5), lds<SP_DB * RB>(a2)));
+        dH = vadd(dH, vsub(lds<SP_HW * RB>(a5), lds<SP_HW * RB>(a2)));
+    }
+    const V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
+    const V kf = vexp(lnkf);
+    V kr = vexp(V{lnkf.x - sB.x - lnKc, lnkf.y - sB.y - lnKc});
+    if (!isrev) kr = V{0.0, 0.0};
+    V f = vmul(kf, vmul(c0, c1)), r = vmul(kr, vmul(c3, c4));
+    if (three) { f = vmul(f, c2); r = vmul(r, c5); }
+    const V net = vsub(f, r);
+    V pmt{0.0, 0.0};
+    if (PM && (fl & F_PMT)) pmt = vmul(gg, net);
+
+    // ---- Jacobian scalars
+    const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
+    const V rho_inv = lds<Q_RHOINV * RB>(aSC), nmwr = lds<Q_NMWR * RB>(aSC);
+    const double extra = (PM && (fl & F_EFFN1)) ? 1.0 : 0.0;
+    const double n1 = nre + extra, n2 = npr + extra, omre = 1.0 - nre, ompr = 1.0 - npr;
+    V tT, X1, X2;
+    {
+        const double fv[2] = {f.x, f.y}, rv[2] = {r.x, r.y}, nv[2] = {net.x, net.y}, Tv[2] = {T.x, T.y};
+        const double iv[2] = {iT.x, iT.y}, sd[2] = {sdB.x, sdB.y}, pmv[2] = {PM_.x, PM_.y};
+        const double xdv[2] = {Xd.x, Xd.y}, ri[2] = {rho_inv.x, rho_inv.y}, nm[2] = {nmwr.x, nmwr.y};
+        const double ef[2] = {e1Fi.x, e1Fi.y};
+        double pt[2] = {pmt.x, pmt.y}, t_[2], x1[2], x2[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const double dk = bexp + Ta * iv[g];
+            // irreversible: r = 0 makes this f * (dk + 1 - nre)          (cj:1461-1523)
+            const double elem = nv[g] * dk + fv[g] * omre - rv[g] * (ompr - Tv[g] * sd[g]);
+            double t;
+            if (PM) {
+                if (fl & F_PDEP) t = (pmv[g] * xdv[g] * nv[g] + pmv[g] * iv[g] * elem) * ri[g];
+                else t = (-pmv[g] * nv[g] * iv[g] + pmv[g] * iv[g] * elem) * ri[g];
+            } else {
+                t = iv[g] * elem * ri[g];
+            }
+            t_[g] = (fl & F_NO_T) ? 0.0 : t;
+            double inner = n1 * fv[g] - n2 * rv[g];
+            if (PM && (fl & F_PMT_INJ)) inner += pt[g];
+            const double jy = nm[g] * pmv[g] * inner;
+            if (PM && (fl & F_PMT_INJ)) pt[g] *= ef[g];
+            x1[g] = jy;
+            x2[g] = -jy;
+            if (PM) { x1[g] += par[5] * pt[g]; x2[g] -= par[4] * pt[g]; }
+        }
+        tT = V{t_[0], t_[1]}; X1 = V{x1[0], x1[1]}; X2 = V{x2[0], x2[1]}; pmt = V{pt[0], pt[1]};
+    }
+    const V pk = PM ? vmul(PM_, kf) : kf;
+    const V prv = PM ? V{-PM_.x * kr.x, -PM_.y * kr.y} : V{-kr.x, -kr.y};
+
+    // ---- d(rate)/dC values: to their raw rows, or folded into X2 for the last species
+#define PJ_EMIT(SLOT, DST, EXPR)                                         \
+    if ((SLOT) != (unsigned)nsp) {                                       \
+        const V d_ = (EXPR);                                             \
+        if ((SLOT) == (unsigned)last) X2 = vsub(X2, d_);                 \
+        else if (valid) sts<0>(aRAW + (DST) * RB, d_);                   \
+    }
+    if (three) {
+        PJ_EMIT(s0, q3.x & 0xFFFFu, vmul(pk, vmul(c1, c2)))
+        PJ_EMIT(s1, (unsigned)q3.x >> 16, vmul(pk, vmul(c0, c2)))
+        PJ_EMIT(s2, q3.y & 0xFFFFu, vmul(pk, vmul(c0, c1)))
+        if (isrev) {
+            PJ_EMIT(s3, (unsigned)q3.y >> 16, vmul(prv, vmul(c4, c5)))
+            PJ_EMIT(s4, q3.z & 0xFFFFu, vmul(prv, vmul(c3, c5)))
+            PJ_EMIT(s5, (unsigned)q3.z >> 16, vmul(prv, vmul(c3, c4)))
+        }
+    } else {
+        PJ_EMIT(s0, q3.x & 0xFFFFu, vmul(pk, c1))
+        PJ_EMIT(s1, (unsigned)q3.x >> 16, vmul(pk, c0))
+        if (isrev) {
+            PJ_EMIT(s3, (unsigned)q3.y >> 16, vmul(prv, c4))
+            PJ_EMIT(s4, q3.z & 0xFFFFu, vmul(prv, c3))
+        }
+    }
+#undef PJ_EMIT
+    if (PM && valid) {
+        if (fl & F_EFF_SLOTS) {
+            unsigned rb = q3.w & 0xFFFFu;
+            const int e0 = __ldg(tb.pm_eff_off + mi), e1_ = __ldg(tb.pm_eff_off + mi + 1);
+            for (int e = e0; e < e1_; ++e)
+                if (__ldg(tb.pm_eff_sp + e) != last) {
+                    sts<0>(aRAW + rb * RB, vmul(__ldg(tb.pm_eff_am1 + e), pmt));
+                    ++rb;
+                }
+        }
+        if (fl & F_WANT_PMT) sts<0>(aRAW + ((unsigned)q3.w >> 16) * RB, pmt);
+    }
+    if (valid) {
+        const unsigned ar = aRX + p * RXB;
+        sts<RX_NET * RB>(ar, PM ? vmul(net, PM_) : net);
+        sts<RX_TT * RB>(ar, tT);
+        sts<RX_X1 * RB>(ar, X1);
+        sts<RX_X2 * RB>(ar, X2);
+        sts<RX_DH * RB>(ar, dH);
+    }
+}
+
+template <int GS>
+__global__ void __launch_bounds__(512, 1)
+k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const __grid_constant__ IO io)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NSUB = 64 / GS;          // table items a warp works on at the same time
+    constexpr int NPR = GS / 2;            // state pairs = lanes per sub-group
+    constexpr int RB = GS * 8, SPB = SP_SLOTS * RB, RXB = RX_SLOTS * RB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = pl.nw;
+    const int sub = lane / NPR, pr = lane % NPR;
+    const int nsp = tb.nsp, last = tb.nsp - 1;
+    // 32-bit shared addresses of this lane's state pair in each region
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + pr * 16;
+    const unsigned aSP = sb + pl.oSP * 8, aRX = sb + pl.oRX * 8, aRAW = sb + pl.oRAW * 8;
+    const unsigned aSC = sb + pl.oSC * 8, aPA = sb + pl.oPA * 8;
+    const V zero{0.0, 0.0};
+
+    // rows that never change: the empty reaction slot, the zero reaction, the zero raw row
+    if (warp == 0 && sub == 0) {
+        const unsigned a = aSP + nsp * SPB;
+        sts<SP_C * RB>(a, V{1.0, 1.0});
+        sts<SP_B * RB>(a, zero); sts<SP_DB * RB>(a, zero); sts<SP_HW * RB>(a, zero);
+        sts<SP_WA * RB>(a, zero); sts<SP_WB * RB>(a, zero); sts<SP_WT * RB>(a, zero); sts<SP_CP * RB>(a, zero);
+        const unsigned ar = aRX + tb.nr * RXB;
+        sts<RX_NET * RB>(ar, zero); sts<RX_TT * RB>(ar, zero); sts<RX_X1 * RB>(ar, zero);
+        sts<RX_X2 * RB>(ar, zero); sts<RX_DH * RB>(ar, zero);
+        sts<0>(aRAW + tb.nraw * RB, zero);
+    }
+
+    const bool sf = io.jac_layout != 0;
+    const bool vec_ok = sf && ((io.jac_ld & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.jac) & 15) == 0);
+    const long long nn = (long long)nsp * nsp;
+    const long long ngroups = ((long long)io.n + GS - 1) / GS;
+    // element e of the lane's first state: SoA jac[e * ld + s], AoS jac[s * nn + e]
+    const long long estride = sf ? io.jac_ld : 1;
+
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long s0 = grp * GS + 2 * pr;           // first state of this lane
+        const bool ok0 = s0 < io.n, ok1 = s0 + 1 < io.n;
+        double* const out0 = sf ? io.jac + s0 : io.jac + s0 * nn;
+        auto store = [&](unsigned e, V v) {
+            double* o = out0 + (long long)e * estride;
+            if (vec_ok && ok1) { *reinterpret_cast<double2*>(o) = make_double2(v.x, v.y); }
+            else if (sf) { if (ok0) o[0] = v.x; if (ok1) o[1] = v.y; }
+            else { if (ok0) o[0] = v.x; if (ok1) o[nn] = v.y; }
+        };
+
+        // ------------------------------------------------------------ phase A0 (warp 0)
+        if (warp == 0) {
+            const long long i0 = ok0 ? s0 : (long long)io.n - 1, i1 = ok1 ? s0 + 1 : (long long)io.n - 1;
+            const double* y0 = io.y + i0 * io.y_ss;
+            const double* y1 = io.y + i1 * io.y_ss;
+            V sumY = zero, sumYW = zero;
+            for (int k = sub; k < last; k += NSUB) {
+                const V Yk{y0[(long long)(k + 1) * io.y_sv], y1[(long long)(k + 1) * io.y_sv]};
+                sts<SP_Y * RB>(aSP + k * SPB, Yk);
+                sumY = vadd(sumY, Yk);
+                sumYW = vfma(__ldg(tb.sp_iw + k), Yk, sumYW);
+            }
+            sumY = sub_sum<GS>(sumY);
+            sumYW = sub_sum<GS>(sumYW);
+            if (sub == 0) {
+                const double T[2] = {y0[0], y1[0]};
+                const double P[2] = {io.pres[i0], io.pres[i1]};
+                const double yN[2] = {1.0 - sumY.x, 1.0 - sumY.y};
+                const double sw[2] = {sumYW.x, sumYW.y};
+                double o[8][2];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const double mw = 1.0 / (sw[g] + yN[g] * __ldg(tb.sp_iw + last));
+                    const double rho = P[g] * mw / (tb.ru * T[g]);
+                    const double rho_inv = 1.0 / rho;
+                    o[Q_T][g] = T[g]; o[Q_LOGT][g] = log(T[g]); o[Q_IT][g] = 1.0 / T[g];
+                    o[Q_RHO][g] = rho; o[Q_RHOINV][g] = rho_inv;
+                    o[Q_NMWR][g] = -mw * rho_inv; o[Q_MWR][g] = mw * rho_inv;
+                    o[Q_M][g] = P[g] / (tb.ru * T[g]);
+                }
+                sts<SP_Y * RB>(aSP + last * SPB, V{yN[0], yN[1]});
+                sts<Q_T * RB>(aSC, V{o[Q_T][0], o[Q_T][1]});
+                sts<Q_LOGT * RB>(aSC, V{o[Q_LOGT][0], o[Q_LOGT][1]});
+                sts<Q_IT * RB>(aSC, V{o[Q_IT][0], o[Q_IT][1]});
+                sts<Q_RHO * RB>(aSC, V{o[Q_RHO][0], o[Q_RHO][1]});
+                sts<Q_RHOINV * RB>(aSC, V{o[Q_RHOINV][0], o[Q_RHOINV][1]});
+                sts<Q_NMWR * RB>(aSC, V{o[Q_NMWR][0], o[Q_NMWR][1]});
+                sts<Q_MWR * RB>(aSC, V{o[Q_MWR][0], o[Q_MWR][1]});
+                sts<Q_M * RB>(aSC, V{o[Q_M][0], o[Q_M][1]});
+            }
+        }
+        __syncthreads();
+
+        const V T = lds<Q_T * RB>(aSC), logT = lds<Q_LOGT * RB>(aSC), iT = lds<Q_IT * RB>(aSC);
+
+        // ------------------------------------------------------------ phase A1: species thermo
+        {
+            const V rho = lds<Q_RHO * RB>(aSC);
+            const double Tv[2] = {T.x, T.y}, lT[2] = {logT.x, logT.y}, rT[2] = {iT.x, iT.y}, rh[2] = {rho.x, rho.y};
+            double cpavg[2] = {0.0, 0.0}, wdcp[2] = {0.0, 0.0};
+            for (int k = warp * NSUB + sub; k < nsp; k += nw * NSUB) {
+                const unsigned a = aSP + k * SPB;
+                const V Yv = lds<SP_Y * RB>(a);
+                const double Yk[2] = {Yv.x, Yv.y};
+                const double iw = __ldg(tb.sp_iw + k), ruw = __ldg(tb.sp_ruw + k), wk = __ldg(tb.sp_w + k);
+                const double tmid = __ldg(tb.sp_tmid + k);
+                double ck[2], cp[2], Bk[2], dB[2], hW[2];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const double* c = tb.sp_nasa + (k * 2 + (Tv[g] <= tmid ? 0 : 1)) * 16;
+                    const double t = Tv[g];
+                    ck[g] = rh[g] * Yk[g] * iw;
+                    cp[g] = ruw * (c[0] + t * (c[1] + t * (c[2] + t * (c[3] + c[4] * t))));
+                    const double hh = c[6] + t * (c[7] + t * (c[8] + c[9] * t));
+                    hW[g] = ruw * (c[5] + t * (c[0] + t * hh)) * wk;
+                    const double dcp = ruw * (c[1] + t * (2.0 * c[2] + t * (3.0 * c[3] + 4.0 * c[4] * t)));
+                    cpavg[g] += Yk[g] * cp[g];
+                    wdcp[g] += Yk[g] * dcp;
+                    dB[g] = (c[11] + c[5] * rT[g]) * rT[g] + hh;
+                    Bk[g] = c[10] + c[11] * lT[g] + t * (c[6] + t * (c[12] + t * (c[13] + c[14] * t))) - c[5] * rT[g];
+                }
+                sts<SP_C * RB>(a, V{ck[0], ck[1]});
+                sts<SP_B * RB>(a, V{Bk[0], Bk[1]});
+                sts<SP_DB * RB>(a, V{dB[0], dB[1]});
+                sts<SP_HW * RB>(a, V{hW[0], hW[1]});
+                sts<SP_CP * RB>(a, V{cp[0], cp[1]});
+            }
+            const V ca = sub_sum<GS>(V{cpavg[0], cpavg[1]}), wd = sub_sum<GS>(V{wdcp[0], wdcp[1]});
+            if (sub == 0) {
+                sts<D_CPAVG * RB>(aPA + warp * NPART * RB, ca);
+                sts<D_WDCP * RB>(aPA + warp * NPART * RB, wd);
+            }
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------ phase B: reactions
+        {
+            const int r0 = __ldg(pl.b_off + warp), r1 = __ldg(pl.b_off + warp + 1);
+            const int rpm = r0 + __ldg(pl.b_npm + warp);
+            for (int r = r0; r < r1; ++r) {
+                const int item = __ldg(pl.b_item + r * NSUB + sub);
+                const bool valid = item >= 0;
+                if (r < rpm) {
+                    reaction<GS, true>(tb, pl, aSP, aRX, aRAW, aSC, valid ? item : tb.first_pm, valid, true, T, logT, iT);
+                } else {
+                    const int p = valid ? item : 0;
+                    const int4 c = __ldg(pl.rx + p * 4 + 2);
+                    const bool has3 = ((c.z & 0xFFFF) != nsp) || (((unsigned)c.w >> 16) != (unsigned)nsp);
+                    const bool three = __any_sync(0xffffffffu, has3);
+                    reaction<GS, false>(tb, pl, aSP, aRX, aRAW, aSC, p, valid, three, T, logT, iT);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------ phase C: species sums
+        {
+            const int i0 = __ldg(pl.c_off + warp), i1 = __ldg(pl.c_off + warp + 1);
+            const V mwr = lds<Q_MWR * RB>(aSC);
+            V pH1 = zero, pHA = zero, pHB = zero, pHT = zero, pSCP = zero;
+            for (int it = i0; it < i1; ++it) {
+                const int k = __ldg(pl.c_item + it * 3), off = __ldg(pl.c_item + it * 3 + 1);
+                const int nit = __ldg(pl.c_item + it * 3 + 2);
+                V aN = zero, aT = zero, a1 = zero, a2 = zero;
+                const unsigned* cw = pl.c_con + off * NSUB + sub;
+#pragma unroll 2
+                for (int i = 0; i < nit; ++i) {
+                    const unsigned w = __ldg(cw + i * NSUB);
+                    const unsigned a = aRX + (w & 0xFFFFu) * RXB;
+                    const double cf = coef_of(w);
+                    aN = vfma(cf, lds<RX_NET * RB>(a), aN);
+                    aT = vfma(cf, lds<RX_TT * RB>(a), aT);
+                    a1 = vfma(cf, lds<RX_X1 * RB>(a), a1);
+                    a2 = vfma(cf, lds<RX_X2 * RB>(a), a2);
+                }
+                aN = sub_sum<GS>(aN); aT = sub_sum<GS>(aT); a1 = sub_sum<GS>(a1); a2 = sub_sum<GS>(a2);
+                if (sub == 0) {
+                    const unsigned a = aSP + k * SPB;
+                    const double wk = __ldg(tb.sp_w + k);
+                    const V comp = vmul(aN, mwr);
+                    a1 = vadd(a1, comp);
+                    a2 = vsub(a2, comp);
+                    const V hW = lds<SP_HW * RB>(a), cp = lds<SP_CP * RB>(a);
+                    pH1 = vfma(hW, aN, pH1);
+                    pHA = vfma(hW, a1, pHA);
+                    pHB = vfma(hW, a2, pHB);
+                    pHT = vfma(hW, aT, pHT);
+                    pSCP = vfma(vmul(wk, cp), aN, pSCP);
+                    sts<SP_WA * RB>(a, vmul(wk, a1));
+                    sts<SP_WB * RB>(a, vmul(wk, a2));
+                    sts<SP_WT * RB>(a, vmul(wk, aT));
+                }
+            }
+            if (sub == 0) {
+                const unsigned a = aPA + warp * NPART * RB;
+                sts<D_H1 * RB>(a, pH1); sts<D_HA * RB>(a, pHA); sts<D_HB * RB>(a, pHB);
+                sts<D_HT * RB>(a, pHT); sts<D_SCP * RB>(a, pSCP);
+            }
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------ phase DE
+        if (warp == 0) {
+            // energy-equation scalars from the per-warp partial sums; result of quantity q
+            // replaces warp 0's own partial
+            for (int q = sub; q < NPART; q += NSUB) {
+                V a = zero;
+                for (int w = 0; w < nw; ++w) a = vadd(a, lds<0>(aPA + (w * NPART + q) * RB));
+                sts<0>(aPA + q * RB, a);
+            }
+            __syncwarp();
+            if (sub == 0) {
+                const V H1 = lds<D_H1 * RB>(aPA), HA = lds<D_HA * RB>(aPA), HB = lds<D_HB * RB>(aPA);
+                const V HT = lds<D_HT * RB>(aPA), SCP = lds<D_SCP * RB>(aPA);
+                const V cpavg = lds<D_CPAVG * RB>(aPA), wdcp = lds<D_WDCP * RB>(aPA);
+                const V rho = lds<Q_RHO * RB>(aSC), cpl = lds<SP_CP * RB>(aSP + last * SPB);
+                const V nwt{-1.0 / cpavg.x, -1.0 / cpavg.y};
+                sts<Q_NWT * RB>(aSC, nwt);
+                sts<Q_A0 * RB>(aSC, vmul(nwt, HA));
+                sts<Q_B0 * RB>(aSC, vmul(nwt, HB));
+                sts<Q_XT * RB>(aSC, V{H1.x / (rho.x * cpavg.x * cpavg.x), H1.y / (rho.y * cpavg.y * cpavg.y)});
+                sts<Q_CPL * RB>(aSC, cpl);
+                // jac[0] (cj:1853-1905)
+                store(0u, V{-(-wdcp.x / cpavg.x * H1.x + SCP.x + HT.x * rho.x) / (rho.x * cpavg.x),
+                            -(-wdcp.y / cpavg.y * H1.y + SCP.y + HT.y * rho.y) / (rho.y * cpavg.y)});
+            }
+            if (pl.t_sync > 32) {
+                __threadfence_block();
+                asm volatile("bar.arrive 1, %0;" ::"r"(pl.t_sync) : "memory");
+            }
+        }
+        {
+            // species rows: dense rank-2 part + sparse gather
+            const uint2* up = pl.e_str + (long long)__ldg(pl.e_off + warp) * NSUB + sub;
+            const int nst = __ldg(pl.e_nst + warp);
+            for (int st = 0; st < nst; ++st) {
+                const uint2 r = __ldg(up);
+                up += NSUB;
+                const unsigned L2 = r.x >> 22, e = r.x & NULL_E;
+                V acc0 = zero, acc1 = zero;
+                double pw = 0.0;
+                if (L2) {
+                    const uint2 pu = __ldg(up);
+                    pw = __hiloint2double((int)pu.y, (int)pu.x);
+                    up += NSUB;
+#pragma unroll 2
+                    for (unsigned i = 0; i < L2; ++i) {
+                        const uint2 c = __ldg(up + i * NSUB);
+                        acc0 = vfma(coef_of(c.x), lds<0>(aRAW + (c.x & 0xFFFFu) * RB), acc0);
+                        acc1 = vfma(coef_of(c.y), lds<0>(aRAW + (c.y & 0xFFFFu) * RB), acc1);
+                    }
+                    up += L2 * NSUB;
+                }
+                if (e != NULL_E) {
+                    const unsigned a = aSP + (r.y & 0xFFFFu) * RB;
+                    const double2 cf = __ldg(pl.colfac + (r.y >> 16));
+                    V v = vfma(cf.y, lds<RB>(a), vmul(cf.x, lds<0>(a)));
+                    if (L2) v = vfma(pw, vadd(acc0, acc1), v);
+                    store(e, v);
+                }
+            }
+        }
+        {
+            // energy-equation row (cj:3095-3254): enthalpy-weighted gathers
+            const int nst = __ldg(pl.t_nst + warp);
+            if (nst) {
+                if (warp != 0) asm volatile("bar.sync 1, %0;" ::"r"(pl.t_sync) : "memory");
+                const uint2* up = pl.t_str + (long long)__ldg(pl.t_off + warp) * NSUB + sub;
+                const V nwt = lds<Q_NWT * RB>(aSC), A0 = lds<Q_A0 * RB>(aSC), B0 = lds<Q_B0 * RB>(aSC);
+                const V XT = lds<Q_XT * RB>(aSC), cpl = lds<Q_CPL * RB>(aSC);
+                for (int st = 0; st < nst; ++st) {
+                    const uint2 r = __ldg(up);
+                    up += NSUB;
+                    const unsigned L2 = r.x >> 22, e = r.x & NULL_E;
+                    V acc0 = zero, acc1 = zero;
+#pragma unroll 2
+                    for (unsigned i = 0; i < L2; ++i) {
+                        const uint2 c = __ldg(up + i * NSUB);
+                        acc0 = vfma(lds<RX_DH * RB>(aRX + (c.x >> 16) * RXB), lds<0>(aRAW + (c.x & 0xFFFFu) * RB), acc0);
+                        acc1 = vfma(lds<RX_DH * RB>(aRX + (c.y >> 16) * RXB), lds<0>(aRAW + (c.y & 0xFFFFu) * RB), acc1);
+                    }
+                    up += L2 * NSUB;
+                    if (e != NULL_E) {
+                        const double2 cf = __ldg(pl.colfac + r.y);
+                        const V cpj = lds<SP_CP * RB>(aSP + (r.y - 1) * SPB);
+                        const V E0 = vadd(acc0, acc1);
+                        V v = vmul(cf.x, vfma(nwt, E0, A0));
+                        v = vfma(cf.y, B0, v);
+                        v = vfma(XT, vsub(cpj, cpl), v);
+                        store(e, v);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pj5

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "jacobian.cuh"
 #include "pjtable.h"
 
 using pj::IO;
@@ -26,6 +27,8 @@ struct pyjac_mech {
     int smem_optin = 0;
     int smem_per_sm = 0;
     Tables tb{};
+    pj5::Plan plan{};
+    int jac_bpsm = 0;                // blocks per SM of the Jacobian kernel (0 = not configured)
     std::vector<void*> dev_allocs;
     // launch configuration (per mode: 0 jac, 1 dydt, 2 rates)
     int G[3] = {0, 0, 0};
@@ -164,6 +167,46 @@ int launch(pyjac_mech* m, int mode_ix, const IO& io, cudaStream_t st)
     return PYJAC_OK;
 }
 
+const void* jac_kernel(int gs)
+{
+    switch (gs) {
+    case 2: return (const void*)pj5::k_jacobian<2>;
+    case 4: return (const void*)pj5::k_jacobian<4>;
+    case 8: return (const void*)pj5::k_jacobian<8>;
+    case 16: return (const void*)pj5::k_jacobian<16>;
+    case 32: return (const void*)pj5::k_jacobian<32>;
+    default: return nullptr;
+    }
+}
+
+// eval_jacob: the plan in the table blob fixes states per block and block size
+int launch_jac(pyjac_mech* m, const IO& io, cudaStream_t st)
+{
+    if (io.n <= 0) return PYJAC_OK;
+    CU(cudaSetDevice(m->device));
+    const pj5::Plan& pl = m->plan;
+    const void* fn = jac_kernel(pl.gs);
+    if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable Jacobian plan");
+    const size_t bytes = (size_t)pl.total * 8;
+    if (!m->jac_bpsm) {
+        if (bytes > (size_t)m->smem_optin)
+            return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.nt, bytes));
+        if (occ < 1) return fail(PYJAC_ETOOBIG, "Jacobian kernel cannot be resident with this plan");
+        if (m->user_bpsm) occ = std::min(occ, m->user_bpsm);
+        m->jac_bpsm = occ;
+    }
+    const long long groups = ((long long)io.n + pl.gs - 1) / pl.gs;
+    const int grid = (int)std::min<long long>(groups, (long long)m->sm_count * m->jac_bpsm);
+    void* args[3] = {(void*)&m->tb, (void*)&m->plan, (void*)&io};
+    CU(cudaLaunchKernel(fn, dim3(grid), dim3(pl.nt), args, bytes, st));
+    ++m->launches;
+    return PYJAC_OK;
+}
+
 template <typename T>
 int upload(pyjac_mech* m, const void* blob, const char* name, const T** out, int dtype)
 {
@@ -248,15 +291,15 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     t.nfix = d3[0]; t.nq = d3[1]; t.nq_j = d3[2];
     t.ru = c[0];
     int rc = PYJAC_OK;
-#define UP(field, name, type, code) if (!rc) rc = upload<type>(m, blob, name, &t.field, code)
-    UP(sp_w, "sp_w", double, 0); UP(sp_iw, "sp_iw", double, 0); UP(sp_ruw, "sp_ruw", double, 0);
-    UP(sp_tmid, "sp_tmid", double, 0); UP(sp_mwf, "sp_mwf", double, 0); UP(sp_nasa, "sp_nasa", double, 0);
-    UP(rx_rec, "rx_rec", int4, 1); UP(rx_dst, "rx_dst", uint4, 2);
-    UP(pm_par, "pm_par", double, 0); UP(pm_sp, "pm_sp", int, 1);
-    UP(pm_eff_off, "pm_eff_off", int, 1); UP(pm_eff_sp, "pm_eff_sp", int, 1); UP(pm_eff_am1, "pm_eff_am1", double, 0);
-    UP(red_off, "red_off", int, 1); UP(red_pk, "red_pk", unsigned, 1);
-    UP(d_dst, "d_dst", unsigned short, 2); UP(d_con, "d_con", unsigned, 1);
-    UP(q_dst, "q_dst", unsigned short, 2); UP(q_off, "q_off", int, 1); UP(q_con, "q_con", unsigned, 1);
+#define UP(field, name, type, code) if (!rc) rc = upload<type>(m, blob, name, &m->field, code)
+    UP(tb.sp_w, "sp_w", double, 0); UP(tb.sp_iw, "sp_iw", double, 0); UP(tb.sp_ruw, "sp_ruw", double, 0);
+    UP(tb.sp_tmid, "sp_tmid", double, 0); UP(tb.sp_mwf, "sp_mwf", double, 0); UP(tb.sp_nasa, "sp_nasa", double, 0);
+    UP(tb.rx_rec, "rx_rec", int4, 1); UP(tb.rx_dst, "rx_dst", uint4, 2);
+    UP(tb.pm_par, "pm_par", double, 0); UP(tb.pm_sp, "pm_sp", int, 1);
+    UP(tb.pm_eff_off, "pm_eff_off", int, 1); UP(tb.pm_eff_sp, "pm_eff_sp", int, 1); UP(tb.pm_eff_am1, "pm_eff_am1", double, 0);
+    UP(tb.red_off, "red_off", int, 1); UP(tb.red_pk, "red_pk", unsigned, 1);
+    UP(tb.d_dst, "d_dst", unsigned short, 2); UP(tb.d_con, "d_con", unsigned, 1);
+    UP(tb.q_dst, "q_dst", unsigned short, 2); UP(tb.q_off, "q_off", int, 1); UP(tb.q_con, "q_con", unsigned, 1);
     if (!rc) {
         const pjt::Entry* s_ = pjt::find(blob, "d_cls");
         const pjt::Entry* c_ = pjt::find(blob, "d_ccon");
@@ -267,7 +310,25 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
             std::memcpy(t.d_ccon, (const char*)blob + c_->offset, sizeof(t.d_ccon));
         }
     }
-    UP(red_rx, "red_rx", int, 1); UP(red_nu, "red_nu", double, 0);
+    UP(tb.red_rx, "red_rx", int, 1); UP(tb.red_nu, "red_nu", double, 0);
+    if (!rc) {
+        const pjt::Entry* pe = pjt::find(blob, "p5_cfg");
+        if (!pe || pe->dtype != 1 || pe->count < 11) rc = fail(PYJAC_EINVAL, "table blob lacks p5_cfg");
+        else {
+            const int* c5 = (const int*)((const char*)blob + pe->offset);
+            pj5::Plan& pl = m->plan;
+            int* o = &pl.gs;
+            for (int i = 0; i < 11; ++i) o[i] = c5[i];
+            if (!jac_kernel(pl.gs) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64)
+                rc = fail(PYJAC_EINVAL, "bad Jacobian plan configuration");
+        }
+    }
+    UP(plan.rx, "p5_rx", int4, 1);
+    UP(plan.b_off, "p5_b_off", int, 1); UP(plan.b_npm, "p5_b_npm", int, 1); UP(plan.b_item, "p5_b_item", int, 1);
+    UP(plan.c_off, "p5_c_off", int, 1); UP(plan.c_item, "p5_c_item", int, 1); UP(plan.c_con, "p5_c_con", unsigned, 1);
+    UP(plan.e_off, "p5_e_off", int, 1); UP(plan.e_nst, "p5_e_nst", int, 1); UP(plan.e_str, "p5_e_str", uint2, 1);
+    UP(plan.t_off, "p5_t_off", int, 1); UP(plan.t_nst, "p5_t_nst", int, 1); UP(plan.t_str, "p5_t_str", uint2, 1);
+    UP(plan.colfac, "p5_colfac", double2, 0);
 #undef UP
     if (!rc) {
         cudaDeviceProp prop;
@@ -309,6 +370,7 @@ int pyjac_mech_tune(pyjac_mech* m, int states_per_block, int threads, int blocks
         return fail(PYJAC_EINVAL, "states_per_block must be 0, 1 or 2");
     m->user_G = states_per_block; m->user_threads = threads; m->user_bpsm = blocks_per_sm;
     m->G[0] = m->G[1] = m->G[2] = 0;    // re-derive at next launch
+    m->jac_bpsm = 0;
     return PYJAC_OK;
 }
 
@@ -323,7 +385,7 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
     IO io{};
     io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
     io.jac = d_jac; io.jac_layout = jac_layout; io.jac_ld = jac_ld;
-    return launch(m, 0, io, (cudaStream_t)stream);
+    return launch_jac(m, io, (cudaStream_t)stream);
 }
 
 int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,

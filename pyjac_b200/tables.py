@@ -50,6 +50,7 @@ from typing import Dict, List
 
 import numpy as np
 
+from . import plan
 from .chem import PA, RU
 from .mechanism import Mechanism
 
@@ -95,7 +96,8 @@ def _nasa_row(a) -> List[float]:
             a[6] - a[0], a[0] - 1.0, a[2] / 6.0, a[3] / 12.0, a[4] / 20.0, 0.0]
 
 
-def build(mech: Mechanism) -> Dict[str, np.ndarray]:
+def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarray]:
+    """gs / threads: states per block and block size of the Jacobian kernel's plan (0 = automatic)."""
     specs, reacs = mech.specs, mech.reacs
     nsp, nr = len(specs), len(reacs)
     last = nsp - 1
@@ -554,6 +556,32 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     T['q_off'] = i32(q_off)
     T['q_con'] = np.asarray(q_con + [null_j] * 16, dtype=np.uint32).view(np.int32)
     T['dims3'] = i32([len(d_dst), len(q_dst), len(quad_j), len(d_con), len(q_con), 0, 0, 0])
+
+    # ---------------- schedule of the Jacobian kernel (plan.py)
+    nt = threads or 512
+    if not gs:
+        gs = plan.choose_gs(nsp, nr, nraw, nt // 32)
+        if not gs:
+            raise UnsupportedMechanism('working set of one state pair exceeds shared memory')
+    kinds, n_eff = [], []
+    for p, i in enumerate(order):
+        rx = reacs[i]
+        kinds.append('sri' if rx.sri else 'troe' if rx.troe else 'lind' if rx.pdep else
+                     'thd' if rx.thd_body else 'plain')
+        n_eff.append(sum(1 for s, a in rx.thd_body_eff if a != 1.0) if (rx.thd_body or rx.pdep) else 0)
+    T.update(plan.build_plan(nsp, nr, nraw, first_pm, kinds, [bool(reacs[i].rev) for i in order],
+                             [bool(slots[p, 2] != nsp or slots[p, 5] != nsp) for p in range(nr)],
+                             n_eff, red, {kj: v for kj, v in contrib.items() if kj[0] != last},
+                             tcontrib, T['sp_w'], T['sp_iw'], T['sp_mwf'], gs, nt))
+    # the 64-byte reaction record of the Jacobian kernel: lnA, b, Ta, sum(nu) ln(PA/RU); flags;
+    # six species slots and eight raw destinations packed two per int
+    rec5 = np.zeros((nr, 16), dtype=np.int32)
+    rec5[:, :9] = rec[:, :9]
+    for a in range(3):
+        rec5[:, 9 + a] = slots[:, 2 * a] | (slots[:, 2 * a + 1] << 16)
+    for a in range(4):
+        rec5[:, 12 + a] = rx_dst[:, 2 * a].astype(np.int32) | (rx_dst[:, 2 * a + 1].astype(np.int32) << 16)
+    T['p5_rx'] = rec5.ravel()
 
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
     T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, nsub, len(con), 0,

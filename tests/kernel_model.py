@@ -208,49 +208,35 @@ def evaluate(Tb, P, y):
         R4[p, 0], R4[p, 1], R4[p, 2], R4[p, 3] = net * PM, tT, X1, X2
         RH[p] = (hw[:, s[3]] + hw[:, s[4]] + hw[:, s[5]]) - (hw[:, s[0]] + hw[:, s[1]] + hw[:, s[2]])
 
-    # --- species reductions: packed (reaction | hi16(nu) << 16) lists per species
+    # --- phase C of the plan: per species, lists of (reaction | hi16(nu) << 16) split over the
+    # NSUB sub-groups of a warp (padding words point at the all-zero reaction row nr)
     def coef(word):
         return float(np.uint64((int(word) >> 16) << 48).view(np.float64))
-    red_pk = Tb['red_pk'].view(np.uint32)
+    cfg = Tb['p5_cfg']
+    gs, nt, nw, nsub = (int(v) for v in cfg[:4])
+    assert nsub * gs == 64 and nt == nw * 32
+    R4z = np.concatenate([R4, np.zeros((1, 4, n))], axis=0)
     wdot = np.zeros((n, nsp)); tcol = np.zeros((n, nsp)); Ak = np.zeros((n, nsp)); Bk = np.zeros((n, nsp))
-    for k in range(nsp):
-        for e in range(Tb['red_off'][k], Tb['red_off'][k + 1]):
-            wd = red_pk[e]
-            cf, rxn = coef(wd), int(wd) & 0xFFFF
-            wdot[:, k] += cf * R4[rxn, 0]; tcol[:, k] += cf * R4[rxn, 1]
-            Ak[:, k] += cf * R4[rxn, 2]; Bk[:, k] += cf * R4[rxn, 3]
+    c_item, c_con = Tb['p5_c_item'].reshape(-1, 3), Tb['p5_c_con'].view(np.uint32)
+    seen_k = set()
+    for wp in range(nw):
+        for it in range(Tb['p5_c_off'][wp], Tb['p5_c_off'][wp + 1]):
+            k, off, nit = (int(v) for v in c_item[it])
+            assert k not in seen_k
+            seen_k.add(k)
+            for wd in c_con[off * nsub:(off + nit) * nsub]:
+                cf, rxn = coef(wd), int(wd) & 0xFFFF
+                wdot[:, k] += cf * R4z[rxn, 0]; tcol[:, k] += cf * R4z[rxn, 1]
+                Ak[:, k] += cf * R4z[rxn, 2]; Bk[:, k] += cf * R4z[rxn, 3]
+    assert seen_k == set(range(nsp))
     comp = wdot * (mw_avg * rho_inv)[:, None]
-    Ak = Ak + comp                       # unscaled a_k, b_k, as the kernel keeps them
+    Ak = Ak + comp
     Bk = Bk - comp
 
-    # --- sparse gather into the dense tile: fixed-length classes, then quad entries
-    nfix, nq, nq_j = (int(v) for v in Tb['dims3'][:3])
-    tile = np.zeros((n, nsp * nsp))
+    # --- phase DE of the plan: elements in steps of NSUB, one padded length L2 (pairs of
+    # contributions) per step; unit u of a warp's stream is e_str[(u * NSUB + sub) * 2 + {0, 1}]
     raw[:, nraw] = 0.0
-    d_con, q_con = Tb['d_con'].view(np.uint32), Tb['q_con'].view(np.uint32)
-    for c, ln in enumerate((8, 4, 2, 1)):
-        for e in range(Tb['d_cls'][c], Tb['d_cls'][c + 1]):
-            o = Tb['d_ccon'][c] + (e - Tb['d_cls'][c]) * ln
-            acc = np.zeros(n)
-            for wd in d_con[o:o + ln]:
-                acc += coef(wd) * raw[:, int(wd) & 0xFFFF]
-            assert not tile[:, Tb['d_dst'][e]].any()
-            tile[:, Tb['d_dst'][e]] = acc
-    for e in range(nq):
-        acc = np.zeros(n)
-        assert (Tb['q_off'][e + 1] - Tb['q_off'][e]) % 16 == 0
-        for wd in q_con[Tb['q_off'][e]:Tb['q_off'][e + 1]]:
-            if e < nq_j:
-                acc += coef(wd) * raw[:, int(wd) & 0xFFFF]
-            else:
-                acc += RH[int(wd) >> 16] * raw[:, int(wd) & 0xFFFF]
-        assert not tile[:, Tb['q_dst'][e]].any()
-        tile[:, Tb['q_dst'][e]] = acc
-    tile = tile.reshape(n, nsp, nsp)       # [state, col, row]
-
-    # --- assembly: row k+1 of column j+1 is iw_j (W_k a_k + W_k b_k mwf_j + W_k tile);
-    # row 0 (energy equation) uses -1/cp_avg times the dH-weighted sums
-    jac = np.zeros((n, nsp, nsp))          # [state, col, row]
+    RHz = np.concatenate([RH, np.zeros((1, n))], axis=0)
     wt = 1.0 / cp_avg
     hwk = hw[:, :nsp]
     H1 = (hwk * wdot).sum(axis=1)
@@ -259,16 +245,71 @@ def evaluate(Tb, P, y):
     HT = (hwk * tcol).sum(axis=1)
     SCP = (cp * w[None, :] * wdot).sum(axis=1)
     XT = H1 / (rho * cp_avg * cp_avg)
-    WA, WB = w[None, :last] * Ak[:, :last], w[None, :last] * Bk[:, :last]
-    for j in range(nsp - 1):
-        v = np.empty((n, nsp))
-        v[:, 1:] = iw[j] * (WA + WB * mwf[j] + w[None, :last] * tile[:, j + 1, 1:])
-        v[:, 0] = iw[j] * (-wt * HA + -wt * HB * mwf[j] + -wt * tile[:, j + 1, 0]) \
-            + XT * (cp[:, j] - cp[:, last])
-        jac[:, j + 1, :] = v
-    jac[:, 0, 1:] = w[None, :last] * tcol[:, :last]
+    slots8 = np.zeros((n, nsp, 8))                 # the species rows as the kernel keeps them
+    slots8[:, :, 4], slots8[:, :, 5], slots8[:, :, 6] = w[None, :] * Ak, w[None, :] * Bk, w[None, :] * tcol
+    slots8[:, :, 7] = cp
+    colfac = Tb['p5_colfac'].reshape(nsp, 2)
+    jac = np.full((n, nsp * nsp), np.nan)          # [state, col * nsp + row]; every element once
+    e_str = Tb['p5_e_str'].view(np.uint32)
+    NULL_E = 0x3FFFFF
+    for wp in range(nw):
+        u = int(Tb['p5_e_off'][wp])
+        for _ in range(int(Tb['p5_e_nst'][wp])):
+            rowu = [(int(e_str[(u * nsub + sub) * 2]), int(e_str[(u * nsub + sub) * 2 + 1])) for sub in range(nsub)]
+            L2 = rowu[0][0] >> 22
+            assert all(r[0] >> 22 == L2 for r in rowu)
+            u += 1
+            pwu = None
+            if L2:
+                pwu = [np.array([e_str[(u * nsub + sub) * 2], e_str[(u * nsub + sub) * 2 + 1]], dtype=np.uint32)
+                       .view(np.float64)[0] for sub in range(nsub)]
+                u += 1
+            for sub in range(nsub):
+                eidx, y = rowu[sub][0] & 0x3FFFFF, rowu[sub][1]
+                acc = np.zeros(n)
+                for i2 in range(L2):
+                    for h in range(2):
+                        cw = int(e_str[((u + i2) * nsub + sub) * 2 + h])
+                        acc += coef(cw) * raw[:, cw & 0xFFFF]
+                if eidx == NULL_E:
+                    assert not acc.any()
+                    continue
+                sl, col = y & 0xFFFF, y >> 16
+                a_, b_ = slots8[:, sl // 8, sl % 8], slots8[:, (sl + 1) // 8, (sl + 1) % 8]
+                v = colfac[col, 0] * a_ + colfac[col, 1] * b_
+                if L2:
+                    v = v + pwu[sub] * acc
+                assert np.isnan(jac[:, eidx]).all() and eidx == col * nsp + sl // 8 + 1
+                jac[:, eidx] = v
+            u += L2
+        assert u == Tb['p5_e_off'][wp + 1]
+    t_str = Tb['p5_t_str'].view(np.uint32)
+    for wp in range(nw):
+        u = int(Tb['p5_t_off'][wp])
+        for _ in range(int(Tb['p5_t_nst'][wp])):
+            rowu = [(int(t_str[(u * nsub + sub) * 2]), int(t_str[(u * nsub + sub) * 2 + 1])) for sub in range(nsub)]
+            L2 = rowu[0][0] >> 22
+            u += 1
+            for sub in range(nsub):
+                eidx, col = rowu[sub][0] & 0x3FFFFF, rowu[sub][1]
+                E0 = np.zeros(n)
+                for i2 in range(L2):
+                    for h in range(2):
+                        cw = int(t_str[((u + i2) * nsub + sub) * 2 + h])
+                        E0 += RHz[cw >> 16] * raw[:, cw & 0xFFFF]
+                if eidx == NULL_E:
+                    assert not E0.any()
+                    continue
+                assert eidx == col * nsp and np.isnan(jac[:, eidx]).all()
+                pj, qj = colfac[col]
+                jac[:, eidx] = pj * (-wt * HA) + qj * (-wt * HB) + pj * (-wt) * E0 \
+                    + XT * (cp[:, col - 1] - cp[:, last])
+            u += L2
+        assert u == Tb['p5_t_off'][wp + 1]
     s0 = -wdcp / cp_avg * H1 + SCP + HT * rho
-    jac[:, 0, 0] = -s0 / (rho * cp_avg)
+    jac[:, 0] = -s0 / (rho * cp_avg)
+    assert not np.isnan(jac).any()
+    jac = jac.reshape(n, nsp, nsp)
 
     dydt = np.empty((n, nsp))
     dydt[:, 0] = -1.0 / (rho * cp_avg) * H1

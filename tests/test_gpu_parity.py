@@ -57,25 +57,44 @@ def test_device_api_vs_reference_golden(torch, golden_dir, mech_file, npz, layou
     ev.close()
 
 
-@pytest.mark.parametrize('G,threads', [(1, 128), (2, 256), (1, 384), (2, 512), (2, 96)])
-def test_launch_shapes_give_identical_results(torch, golden_dir, G, threads):
-    """Results must not depend on states per block / block size; ragged batch sizes included."""
-    mech, ev = _evaluator(golden_dir, 'gri30_syn.inp')
+def _evaluator_with(golden_dir, mech_file, **kw):
+    from pyjac_b200.evaluator import Evaluator
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
+    return mech, Evaluator(mech, **kw)
+
+
+@pytest.mark.parametrize('gs,threads', [(8, 256), (4, 512), (4, 256), (2, 128), (2, 512), (8, 64)])
+@pytest.mark.parametrize('layout', ['rows', 'state_fastest'])
+def test_launch_shapes_give_identical_results(torch, golden_dir, gs, threads, layout):
+    """Results must not depend on states per block / block size (the plan); ragged batch
+    sizes and odd leading dimensions included."""
+    mech, ev0 = _evaluator(golden_dir, 'gri30_syn.inp')
     P_h, y_h = synthetic_states(mech.NSP, 203, seed=3)
     P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
-    ref = ev.eval_jacob(P, y).cpu().numpy()
-    ev.tune(G, threads, 0)
-    # Different launch shapes are different template instances: the compiler may contract
-    # multiply-adds differently, so across shapes the results agree to rounding, not bitwise.
-    full = ev.eval_jacob(P, y).cpu().numpy()
+
+    def run(ev, n, ld=None):
+        yy = y[:n].contiguous()
+        if layout == 'rows':
+            return ev.eval_jacob(P[:n].contiguous(), yy).cpu().numpy()
+        out = torch.full((mech.NSP ** 2, ld or n), float('nan'), dtype=torch.float64, device='cuda')
+        ev.eval_jacob(P[:n].contiguous(), yy.t().contiguous(), out, y_layout=layout, jac_layout=layout)
+        return out[:, :n].t().cpu().numpy()
+
+    ref = run(ev0, 203)
+    assert np.isfinite(ref).all()
+    mech, ev = _evaluator_with(golden_dir, 'gri30_syn.inp', gs=gs, threads=threads)
+    assert (ev.plan_gs, ev.plan_threads) == (gs, threads)
+    # Different plans sum in different orders: agreement to rounding, not bitwise.
+    full = run(ev, 203)
     a, b = full.reshape(-1, mech.NSP, mech.NSP), ref.reshape(-1, mech.NSP, mech.NSP)
     err = np.abs(a - b) / (np.abs(b).max(axis=2, keepdims=True) + 1e-300)
-    assert err.max() <= 1e-11, (G, threads, err.max())
-    # Within one launch shape the result of a state does not depend on the batch around it.
-    for n in (203, 1, 2, 3, 5, 64):
-        out = ev.eval_jacob(P[:n].contiguous(), y[:n].contiguous()).cpu().numpy()
-        assert np.array_equal(out, full[:n]), (G, threads, n)
+    assert err.max() <= 5e-11, (gs, threads, err.max())
+    # Within one plan the result of a state does not depend on the batch around it.
+    for n, ld in ((203, 205), (1, 1), (2, 2), (3, 4), (5, 7), (64, 64)):
+        out = run(ev, n, ld)
+        assert np.array_equal(out, full[:n]), (gs, threads, n)
     ev.close()
+    ev0.close()
 
 
 def test_against_oracle_on_synthetic_states(torch, golden_dir):

@@ -1,13 +1,15 @@
 #!/usr/bin/env python
-"""Aggregate an ncu source-page profile by source line ranges.
-usage: ncu_phases.py REPORT LIB KERNEL name:lo-hi[,lo-hi] ..."""
+"""Aggregate an ncu source-page profile by source line ranges of one file.
+usage: ncu_phases.py REPORT LIB KERNEL FILE name:lo-hi[,lo-hi] ...
+Instructions inlined from other files (or from FILE lines outside every range, e.g. small
+helpers) inherit the phase of the closest preceding instruction that has one."""
 import csv, re, subprocess, sys, tempfile, os
 from collections import defaultdict
 
 def main():
-    rep, so, kname = sys.argv[1:4]
+    rep, so, kname, src = sys.argv[1:5]
     ranges = []
-    for a in sys.argv[4:]:
+    for a in sys.argv[5:]:
         nm, rs = a.split(':')
         ranges.append((nm, [tuple(int(v) for v in r.split('-')) for r in rs.split(',')]))
     tmp = tempfile.mkdtemp()
@@ -27,8 +29,8 @@ def main():
             m2 = re.findall(r'File "([^"]+)", line (\d+)', ln)
             cur = (fn, l)
             for f2, l2 in m2:
-                if os.path.basename(f2) == 'kernels.cuh':
-                    cur = ('kernels.cuh', int(l2))
+                if os.path.basename(f2) == src:
+                    cur = (src, int(l2))
             continue
         m = re.match(r'\s*/\*([0-9a-f]+)\*/\s+(.*?);', ln)
         if m:
@@ -42,19 +44,21 @@ def main():
     base = int(body[0][0], 16)
     agg = defaultdict(lambda: [0.0, 0.0, 0.0, 0.0, 0.0])
     tot = [0.0, 0.0]
+    prev = 'other'
     for r in body:
         off = int(r[0], 16) - base
         key, sass = line_of.get(off, (None, ''))
         s = float(r[ix['# Samples']] or 0); ins = float(r[ix['Instructions Executed']] or 0)
         thr = float(r[ix['Thread Instructions Executed']] or 0)
-        name = 'other'
-        if key and key[0] == 'kernels.cuh':
+        name = None
+        if key and key[0] == src:
             for nm, rs in ranges:
                 if any(lo <= key[1] <= hi for lo, hi in rs):
                     name = nm
                     break
-        elif key:
-            name = 'lib:' + key[0]
+        if name is None:
+            name = prev
+        prev = name
         a = agg[name]
         a[0] += s; a[1] += ins; a[2] += thr
         op = sass.split()[0] if sass else ''

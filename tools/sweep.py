@@ -19,8 +19,9 @@ def main():
     ap.add_argument('--mech', default=os.path.join(ROOT, 'tests', 'golden', 'gri30_syn.inp'))
     ap.add_argument('--shape', default=None, help='synthetic shape name instead of --mech')
     ap.add_argument('--n', type=int, default=262144)
-    ap.add_argument('--configs', default='2:384:0,2:256:0,2:320:0,2:512:0,1:256:0,1:384:0,1:512:0')
-    ap.add_argument('--layout', default='rows')
+    ap.add_argument('--configs', default='8:512:0,8:256:0,4:512:0,4:256:0,4:384:0,8:384:0,2:256:0',
+                    help='gs:threads:blocks_per_sm of the Jacobian plan')
+    ap.add_argument('--layout', default='state_fastest')
     ap.add_argument('--reps', type=int, default=5)
     a = ap.parse_args()
     if a.shape:
@@ -28,7 +29,6 @@ def main():
         synth.write(a.shape, path)
         a.mech = path
     mech = Mechanism.from_chemkin(a.mech)
-    ev = Evaluator(mech, 0)
     P_h, y_h = synthetic_states(mech.NSP, a.n, seed=0)
     P = torch.tensor(P_h, device='cuda')
     y = torch.tensor(y_h, device='cuda')
@@ -41,11 +41,12 @@ def main():
     for cfg in a.configs.split(','):
         G, th, bp = (int(v) for v in cfg.split(':'))
         try:
-            ev.tune(G, th, bp)
+            ev = Evaluator(mech, 0, gs=G, threads=th)
+            ev.tune(0, 0, bp)
             ev.eval_jacob(P, y, out, y_layout=a.layout, jac_layout=a.layout)
             torch.cuda.synchronize()
         except Exception as exc:
-            print('G=%d threads=%d bpsm=%d: %s' % (G, th, bp, exc))
+            print('gs=%d threads=%d bpsm=%d: %s' % (G, th, bp, exc))
             continue
         best = 1e30
         for _ in range(a.reps):
@@ -55,10 +56,10 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        print('G=%d threads=%3d bpsm=%d: %8.3f ms  %.3e states/s  %7.1f GB/s' %
+        print('gs=%d threads=%3d bpsm=%d: %8.3f ms  %.3e states/s  %7.1f GB/s' %
               (G, th, bp, best, a.n / best * 1e3, a.n * bytes_per_state / best / 1e6))
     # dydt for reference
-    ev.tune(0, 0, 0)
+    ev = Evaluator(mech, 0)
     dy = torch.empty_like(y)
     ev.dydt(P, y, dy, y_layout=a.layout)
     torch.cuda.synchronize()
