@@ -40,21 +40,28 @@ struct Plan {
     int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync;
     const int4* rx;
     const int *b_off, *b_npm, *b_item;
-    const int *c_off, *c_item;
-    const unsigned* c_con;
-    const int *e_off, *e_nst;
-    const uint2* e_str;
-    const int *t_off, *t_nst;
+    const int* c_off;
+    const int4* c_item;
+    const uint2* c_str;
+    const int* d_off;
+    const uint2* d_str;
+    const int* s_off;
+    const uint4* s_str;
+    const int* o_off;
+    const uint2* o_str;
+    const int *t_off, *t_n;
     const uint2* t_str;
     const double2* colfac;
 };
 
-enum : int { Q_T = 0, Q_LOGT, Q_IT, Q_RHO, Q_RHOINV, Q_NMWR, Q_MWR, Q_M,
-             Q_NWT, Q_A0, Q_B0, Q_XT, Q_CPL, NQ = 16 };
+// per-state scalars: phase A0 writes Q_* (two buffers of 8 rows), phase DE derives S_*
+enum : int { Q_T = 0, Q_LOGT, Q_IT, Q_RHO, Q_RHOINV, Q_NMWR, Q_MWR, Q_M };
+enum : int { S_NWT = 0, S_A0, S_B0, S_XT, S_CPL, NQ = 24 };
 enum : int { D_H1 = 0, D_HA, D_HB, D_HT, D_SCP, D_CPAVG, D_WDCP, NPART = 7 };
-enum : int { SP_C = 0, SP_B, SP_DB, SP_HW, SP_WA, SP_WB, SP_WT, SP_CP, SP_SLOTS, SP_Y = SP_WA };
+enum : int { SP_C = 0, SP_B, SP_DB, SP_HW, SP_WA, SP_WB, SP_WT, SP_CP, SP_SLOTS, SP_Y = SP_C };
 enum : int { RX_NET = 0, RX_TT, RX_X1, RX_X2, RX_DH, RX_SLOTS };
 enum : unsigned { NULL_E = 0x3FFFFFu };
+enum : int { F_HAS_LAST = 1 << 13 };    // some occupied slot of the reaction holds the last species
 
 struct V {
     double x, y;
@@ -71,6 +78,45 @@ __device__ __forceinline__ void sts(unsigned a, V v)
 {
     asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v.x), "d"(v.y) : "memory");
 }
+// store only where p holds (no branch)
+template <int OFF = 0>
+__device__ __forceinline__ void sts_if(bool p, unsigned a, V v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t@q st.shared.v2.f64 [%0+%1], {%2, %3};\n\t}"
+                 ::"r"(a), "n"(OFF), "d"(v.x), "d"(v.y), "r"((int)p) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// exp of N values at once (so that the polynomial constants are materialised once): arguments
+// clamped to [-708, 708], Cody-Waite reduction to |r| <= ln2/2, degree-12 Taylor polynomial
+// (truncation 1.7e-16 relative), exponent added to the high word.
+template <int N>
+__device__ __forceinline__ void exp_n(const double (&x)[N], double (&e)[N])
+{
+    double r[N], p[N];
+    int k[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double xi = fmin(fmax(x[i], -708.0), 708.0);
+        const double t = fma(xi, 1.4426950408889634074, 6755399441055744.0);
+        k[i] = __double2loint(t);
+        const double kd = t - 6755399441055744.0;
+        r[i] = fma(kd, -1.90821492927058770002e-10, fma(kd, -6.93147180369123816490e-01, xi));
+        p[i] = 2.08767569878680989792e-09;               // 1/12!
+    }
+    const double c[12] = {2.50521083854417187751e-08, 2.75573192239858906526e-07, 2.75573192239858906526e-06,
+                          2.48015873015873015873e-05, 1.98412698412698412698e-04, 1.38888888888888888889e-03,
+                          8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01,
+                          0.5, 1.0, 1.0};
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) e[i] = __hiloint2double(__double2hiint(p[i]) + (k[i] << 20), __double2loint(p[i]));
+}
+
 __device__ __forceinline__ V vfma(double a, V b, V c) { return V{fma(a, b.x, c.x), fma(a, b.y, c.y)}; }
 __device__ __forceinline__ V vfma(V a, V b, V c) { return V{fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)}; }
 __device__ __forceinline__ V vadd(V a, V b) { return V{a.x + b.x, a.y + b.y}; }
@@ -78,6 +124,7 @@ __device__ __forceinline__ V vsub(V a, V b) { return V{a.x - b.x, a.y - b.y}; }
 __device__ __forceinline__ V vmul(double a, V b) { return V{a * b.x, a * b.y}; }
 __device__ __forceinline__ V vmul(V a, V b) { return V{a.x * b.x, a.y * b.y}; }
 __device__ __forceinline__ V vexp(V a) { return V{exp_fast(a.x), exp_fast(a.y)}; }
+__device__ __forceinline__ V zero_v() { return V{0.0, 0.0}; }
 
 // sum over the sub-groups of a warp (lanes with equal state pair); result in every lane
 template <int GS>
@@ -297,6 +344,89 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsig
     }
 }
 
+// Phase B for one reaction without pressure modification (the common case) and the two states
+// of the lane: no branches except `three` (warp-uniform) and the rare last-species fold.
+template <int GS>
+__device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl, unsigned aSP, unsigned aRX,
+                                               unsigned aRAW, unsigned aSC, int p, bool valid, bool three,
+                                               const V T, const V logT, const V iT)
+{
+    constexpr int RB = GS * 8, SPB = SP_SLOTS * RB, RXB = RX_SLOTS * RB;
+    const int4* rp = pl.rx + p * 4;
+    const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+    const double lnA = __hiloint2double(q0.y, q0.x), bexp = __hiloint2double(q0.w, q0.z);
+    const double Ta = __hiloint2double(q1.y, q1.x), lnKc = __hiloint2double(q1.w, q1.z);
+    const int fl = q2.x;
+    const unsigned s0 = q2.y & 0xFFFFu, s1 = (unsigned)q2.y >> 16, s3 = (unsigned)q2.z >> 16, s4 = q2.w & 0xFFFFu;
+    const unsigned a0 = aSP + s0 * SPB, a1 = aSP + s1 * SPB, a3 = aSP + s3 * SPB, a4 = aSP + s4 * SPB;
+    V c0 = lds<SP_C * RB>(a0), c1 = lds<SP_C * RB>(a1), c3 = lds<SP_C * RB>(a3), c4 = lds<SP_C * RB>(a4);
+    V sB = vsub(vadd(lds<SP_B * RB>(a3), lds<SP_B * RB>(a4)), vadd(lds<SP_B * RB>(a0), lds<SP_B * RB>(a1)));
+    V sdB = vsub(vadd(lds<SP_DB * RB>(a3), lds<SP_DB * RB>(a4)), vadd(lds<SP_DB * RB>(a0), lds<SP_DB * RB>(a1)));
+    V dH = vsub(vadd(lds<SP_HW * RB>(a3), lds<SP_HW * RB>(a4)), vadd(lds<SP_HW * RB>(a0), lds<SP_HW * RB>(a1)));
+    V c2{1.0, 1.0}, c5{1.0, 1.0};
+    const unsigned s2 = q2.z & 0xFFFFu, s5 = (unsigned)q2.w >> 16;
+    if (three) {
+        const unsigned a2 = aSP + s2 * SPB, a5 = aSP + s5 * SPB;
+        c2 = lds<SP_C * RB>(a2);
+        c5 = lds<SP_C * RB>(a5);
+        sB = vadd(sB, vsub(lds<SP_B * RB>(a5), lds<SP_B * RB>(a2)));
+        sdB = vadd(sdB, vsub(lds<SP_DB * RB>(a5), lds<SP_DB * RB>(a2)));
+        dH = vadd(dH, vsub(lds<SP_HW * RB>(a5), lds<SP_HW * RB>(a2)));
+    }
+    const V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
+    const double ex[4] = {lnkf.x, lnkf.y, lnkf.x - sB.x - lnKc, lnkf.y - sB.y - lnKc};
+    double ev[4];
+    exp_n<4>(ex, ev);
+    const bool isrev = fl & F_REV;
+    const V kf{ev[0], ev[1]};
+    const V kr{isrev ? ev[2] : 0.0, isrev ? ev[3] : 0.0};
+    // d(rate)/dC per occupied slot; f = d0 * c0, r = -d3 * c3
+    V o0 = c1, o1 = c0, o3 = c4, o4 = c3, o2 = vmul(c0, c1), o5 = vmul(c3, c4);
+    if (three) { o0 = vmul(c1, c2); o1 = vmul(c0, c2); o3 = vmul(c4, c5); o4 = vmul(c3, c5); }
+    const V d0 = vmul(kf, o0), d1 = vmul(kf, o1), d3 = vmul(kr, o3), d4 = vmul(kr, o4);
+    const V f = vmul(d0, c0), r = vmul(d3, c3);
+    const V net = vsub(f, r);
+    const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
+    const double omre = 1.0 - nre, ompr = 1.0 - npr;
+    const V rho_inv = lds<Q_RHOINV * RB>(aSC), nmwr = lds<Q_NMWR * RB>(aSC);
+    const V dk{fma(Ta, iT.x, bexp), fma(Ta, iT.y, bexp)};
+    // irreversible: r = 0 makes this f * (dk + 1 - nre)          (cj:1461-1523)
+    V elem = vfma(net, dk, vmul(omre, f));
+    elem = V{elem.x - r.x * (ompr - T.x * sdB.x), elem.y - r.y * (ompr - T.y * sdB.y)};
+    const double tmask = (fl & F_NO_T) ? 0.0 : 1.0;
+    const V tT = vmul(tmask, vmul(vmul(iT, rho_inv), elem));
+    const V X1 = vmul(nmwr, V{nre * f.x - npr * r.x, nre * f.y - npr * r.y});
+    V X2{-X1.x, -X1.y};
+    const V n3{-d3.x, -d3.y}, n4{-d4.x, -d4.y};
+    V d2 = zero_v(), n5 = zero_v();
+    if (three) { d2 = vmul(kf, o2); n5 = vmul(kr, o5); n5 = V{-n5.x, -n5.y}; }
+    if (fl & F_HAS_LAST) {
+        // a slot holding the last species has no column: its derivative joins the W_j / W_N term
+        const unsigned last = tb.nsp - 1;
+        if (s0 == last) X2 = vsub(X2, d0);
+        if (s1 == last) X2 = vsub(X2, d1);
+        if (s2 == last) X2 = vsub(X2, d2);
+        if (s3 == last) X2 = vsub(X2, n3);
+        if (s4 == last) X2 = vsub(X2, n4);
+        if (s5 == last) X2 = vsub(X2, n5);
+    }
+    // raw rows (slots without one point at the scratch row)
+    sts_if<0>(valid, aRAW + (q3.x & 0xFFFFu) * RB, d0);
+    sts_if<0>(valid, aRAW + ((unsigned)q3.x >> 16) * RB, d1);
+    sts_if<0>(valid, aRAW + ((unsigned)q3.y >> 16) * RB, n3);
+    sts_if<0>(valid, aRAW + (q3.z & 0xFFFFu) * RB, n4);
+    if (three) {
+        sts_if<0>(valid, aRAW + (q3.y & 0xFFFFu) * RB, d2);
+        sts_if<0>(valid, aRAW + ((unsigned)q3.z >> 16) * RB, n5);
+    }
+    const unsigned ar = aRX + p * RXB;
+    sts_if<RX_NET * RB>(valid, ar, net);
+    sts_if<RX_TT * RB>(valid, ar, tT);
+    sts_if<RX_X1 * RB>(valid, ar, X1);
+    sts_if<RX_X2 * RB>(valid, ar, X2);
+    sts_if<RX_DH * RB>(valid, ar, dH);
+}
+
 template <int GS>
 __global__ void __launch_bounds__(512, 1)
 k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const __grid_constant__ IO io)
@@ -305,6 +435,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
     constexpr int NSUB = 64 / GS;          // table items a warp works on at the same time
     constexpr int NPR = GS / 2;            // state pairs = lanes per sub-group
     constexpr int RB = GS * 8, SPB = SP_SLOTS * RB, RXB = RX_SLOTS * RB;
+    constexpr int SCB = 8 * RB;            // one buffer of the phase A0 scalars
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = pl.nw;
     const int sub = lane / NPR, pr = lane % NPR;
@@ -312,7 +443,8 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
     // 32-bit shared addresses of this lane's state pair in each region
     const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + pr * 16;
     const unsigned aSP = sb + pl.oSP * 8, aRX = sb + pl.oRX * 8, aRAW = sb + pl.oRAW * 8;
-    const unsigned aSC = sb + pl.oSC * 8, aPA = sb + pl.oPA * 8;
+    const unsigned aSC0 = sb + pl.oSC * 8, aPA = sb + pl.oPA * 8;
+    const unsigned aSD = aSC0 + 2 * SCB;   // scalars derived in phase DE
     const V zero{0.0, 0.0};
 
     // rows that never change: the empty reaction slot, the zero reaction, the zero raw row
@@ -325,68 +457,81 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
         sts<RX_NET * RB>(ar, zero); sts<RX_TT * RB>(ar, zero); sts<RX_X1 * RB>(ar, zero);
         sts<RX_X2 * RB>(ar, zero); sts<RX_DH * RB>(ar, zero);
         sts<0>(aRAW + tb.nraw * RB, zero);
+        sts<0>(aRAW + (tb.nraw + 1) * RB, zero);
     }
 
     const bool sf = io.jac_layout != 0;
     const bool vec_ok = sf && ((io.jac_ld & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.jac) & 15) == 0);
     const long long nn = (long long)nsp * nsp;
     const long long ngroups = ((long long)io.n + GS - 1) / GS;
-    // element e of the lane's first state: SoA jac[e * ld + s], AoS jac[s * nn + e]
-    const long long estride = sf ? io.jac_ld : 1;
+    // element e of state s: SoA jac[e * ld + s], AoS jac[s * nn + e]
+    const unsigned ld8 = sf ? (unsigned)(io.jac_ld * 8) : 8u;
+    const long long second = sf ? 8 : nn * 8;
 
-    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    // phase A0 of group g into scalar buffer b: mass fractions (to the C slot of the species
+    // rows, where A1 turns them into concentrations), Y_N, mean molecular weight, density
+    auto phase_a0 = [&](long long g, int b) {
+        const long long s0 = g * GS + 2 * pr;
+        const long long i0 = s0 < io.n ? s0 : (long long)io.n - 1, i1 = s0 + 1 < io.n ? s0 + 1 : (long long)io.n - 1;
+        const double* y0 = io.y + i0 * io.y_ss;
+        const double* y1 = io.y + i1 * io.y_ss;
+        V sumY = zero, sumYW = zero;
+        for (int k = sub; k < last; k += NSUB) {
+            const V Yk{y0[(long long)(k + 1) * io.y_sv], y1[(long long)(k + 1) * io.y_sv]};
+            sts<SP_Y * RB>(aSP + k * SPB, Yk);
+            sumY = vadd(sumY, Yk);
+            sumYW = vfma(__ldg(tb.sp_iw + k), Yk, sumYW);
+        }
+        sumY = sub_sum<GS>(sumY);
+        sumYW = sub_sum<GS>(sumYW);
+        if (sub == 0) {
+            const double T[2] = {y0[0], y1[0]};
+            const double P[2] = {io.pres[i0], io.pres[i1]};
+            const double yN[2] = {1.0 - sumY.x, 1.0 - sumY.y};
+            const double sw[2] = {sumYW.x, sumYW.y};
+            double o[8][2];
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+                const double mw = 1.0 / (sw[g2] + yN[g2] * __ldg(tb.sp_iw + last));
+                const double rho = P[g2] * mw / (tb.ru * T[g2]);
+                const double rho_inv = 1.0 / rho;
+                o[Q_T][g2] = T[g2]; o[Q_LOGT][g2] = log(T[g2]); o[Q_IT][g2] = 1.0 / T[g2];
+                o[Q_RHO][g2] = rho; o[Q_RHOINV][g2] = rho_inv;
+                o[Q_NMWR][g2] = -mw * rho_inv; o[Q_MWR][g2] = mw * rho_inv;
+                o[Q_M][g2] = P[g2] / (tb.ru * T[g2]);
+            }
+            const unsigned a = aSC0 + b * SCB;
+            sts<SP_Y * RB>(aSP + last * SPB, V{yN[0], yN[1]});
+            sts<Q_T * RB>(a, V{o[Q_T][0], o[Q_T][1]});
+            sts<Q_LOGT * RB>(a, V{o[Q_LOGT][0], o[Q_LOGT][1]});
+            sts<Q_IT * RB>(a, V{o[Q_IT][0], o[Q_IT][1]});
+            sts<Q_RHO * RB>(a, V{o[Q_RHO][0], o[Q_RHO][1]});
+            sts<Q_RHOINV * RB>(a, V{o[Q_RHOINV][0], o[Q_RHOINV][1]});
+            sts<Q_NMWR * RB>(a, V{o[Q_NMWR][0], o[Q_NMWR][1]});
+            sts<Q_MWR * RB>(a, V{o[Q_MWR][0], o[Q_MWR][1]});
+            sts<Q_M * RB>(a, V{o[Q_M][0], o[Q_M][1]});
+        }
+    };
+
+    if (warp == 0 && (long long)blockIdx.x < ngroups) phase_a0(blockIdx.x, 0);
+    __syncthreads();
+
+    int buf = 0;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, buf ^= 1) {
         const long long s0 = grp * GS + 2 * pr;           // first state of this lane
         const bool ok0 = s0 < io.n, ok1 = s0 + 1 < io.n;
-        double* const out0 = sf ? io.jac + s0 : io.jac + s0 * nn;
-        auto store = [&](unsigned e, V v) {
-            double* o = out0 + (long long)e * estride;
-            if (vec_ok && ok1) { *reinterpret_cast<double2*>(o) = make_double2(v.x, v.y); }
-            else if (sf) { if (ok0) o[0] = v.x; if (ok1) o[1] = v.y; }
-            else { if (ok0) o[0] = v.x; if (ok1) o[nn] = v.y; }
+        char* const out0 = reinterpret_cast<char*>(sf ? io.jac + s0 : io.jac + s0 * nn);
+        const unsigned aSC = aSC0 + buf * SCB;
+        auto store = [&](unsigned e, V v, bool on) {
+            char* o = out0 + (unsigned long long)e * ld8;
+            if (vec_ok) {
+                if (on && ok1) *reinterpret_cast<double2*>(o) = make_double2(v.x, v.y);
+                else if (on && ok0) *reinterpret_cast<double*>(o) = v.x;
+            } else {
+                if (on && ok0) *reinterpret_cast<double*>(o) = v.x;
+                if (on && ok1) *reinterpret_cast<double*>(o + second) = v.y;
+            }
         };
-
-        // ------------------------------------------------------------ phase A0 (warp 0)
-        if (warp == 0) {
-            const long long i0 = ok0 ? s0 : (long long)io.n - 1, i1 = ok1 ? s0 + 1 : (long long)io.n - 1;
-            const double* y0 = io.y + i0 * io.y_ss;
-            const double* y1 = io.y + i1 * io.y_ss;
-            V sumY = zero, sumYW = zero;
-            for (int k = sub; k < last; k += NSUB) {
-                const V Yk{y0[(long long)(k + 1) * io.y_sv], y1[(long long)(k + 1) * io.y_sv]};
-                sts<SP_Y * RB>(aSP + k * SPB, Yk);
-                sumY = vadd(sumY, Yk);
-                sumYW = vfma(__ldg(tb.sp_iw + k), Yk, sumYW);
-            }
-            sumY = sub_sum<GS>(sumY);
-            sumYW = sub_sum<GS>(sumYW);
-            if (sub == 0) {
-                const double T[2] = {y0[0], y1[0]};
-                const double P[2] = {io.pres[i0], io.pres[i1]};
-                const double yN[2] = {1.0 - sumY.x, 1.0 - sumY.y};
-                const double sw[2] = {sumYW.x, sumYW.y};
-                double o[8][2];
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const double mw = 1.0 / (sw[g] + yN[g] * __ldg(tb.sp_iw + last));
-                    const double rho = P[g] * mw / (tb.ru * T[g]);
-                    const double rho_inv = 1.0 / rho;
-                    o[Q_T][g] = T[g]; o[Q_LOGT][g] = log(T[g]); o[Q_IT][g] = 1.0 / T[g];
-                    o[Q_RHO][g] = rho; o[Q_RHOINV][g] = rho_inv;
-                    o[Q_NMWR][g] = -mw * rho_inv; o[Q_MWR][g] = mw * rho_inv;
-                    o[Q_M][g] = P[g] / (tb.ru * T[g]);
-                }
-                sts<SP_Y * RB>(aSP + last * SPB, V{yN[0], yN[1]});
-                sts<Q_T * RB>(aSC, V{o[Q_T][0], o[Q_T][1]});
-                sts<Q_LOGT * RB>(aSC, V{o[Q_LOGT][0], o[Q_LOGT][1]});
-                sts<Q_IT * RB>(aSC, V{o[Q_IT][0], o[Q_IT][1]});
-                sts<Q_RHO * RB>(aSC, V{o[Q_RHO][0], o[Q_RHO][1]});
-                sts<Q_RHOINV * RB>(aSC, V{o[Q_RHOINV][0], o[Q_RHOINV][1]});
-                sts<Q_NMWR * RB>(aSC, V{o[Q_NMWR][0], o[Q_NMWR][1]});
-                sts<Q_MWR * RB>(aSC, V{o[Q_MWR][0], o[Q_MWR][1]});
-                sts<Q_M * RB>(aSC, V{o[Q_M][0], o[Q_M][1]});
-            }
-        }
-        __syncthreads();
 
         const V T = lds<Q_T * RB>(aSC), logT = lds<Q_LOGT * RB>(aSC), iT = lds<Q_IT * RB>(aSC);
 
@@ -434,8 +579,10 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
         {
             const int r0 = __ldg(pl.b_off + warp), r1 = __ldg(pl.b_off + warp + 1);
             const int rpm = r0 + __ldg(pl.b_npm + warp);
+            int item = r0 < r1 ? __ldg(pl.b_item + r0 * NSUB + sub) : -1;
             for (int r = r0; r < r1; ++r) {
-                const int item = __ldg(pl.b_item + r * NSUB + sub);
+                const int nxt = __ldg(pl.b_item + (r + 1) * NSUB + sub);    // the table ends with a null round
+                if (nxt >= 0) prefetch_l1(pl.rx + nxt * 4);
                 const bool valid = item >= 0;
                 if (r < rpm) {
                     reaction<GS, true>(tb, pl, aSP, aRX, aRAW, aSC, valid ? item : tb.first_pm, valid, true, T, logT, iT);
@@ -444,8 +591,9 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                     const int4 c = __ldg(pl.rx + p * 4 + 2);
                     const bool has3 = ((c.z & 0xFFFF) != nsp) || (((unsigned)c.w >> 16) != (unsigned)nsp);
                     const bool three = __any_sync(0xffffffffu, has3);
-                    reaction<GS, false>(tb, pl, aSP, aRX, aRAW, aSC, p, valid, three, T, logT, iT);
+                    reaction_plain<GS>(tb, pl, aSP, aRX, aRAW, aSC, p, valid, three, T, logT, iT);
                 }
+                item = nxt;
             }
         }
         __syncthreads();
@@ -455,38 +603,47 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
             const int i0 = __ldg(pl.c_off + warp), i1 = __ldg(pl.c_off + warp + 1);
             const V mwr = lds<Q_MWR * RB>(aSC);
             V pH1 = zero, pHA = zero, pHB = zero, pHT = zero, pSCP = zero;
+            // item header {species row offset, first unit, #(+1) units, #(-1) units}; the header and
+            // the first two units of the next item are fetched while this one is summed
+            int4 h = __ldg(pl.c_item + i0);
+            const uint2* cp = pl.c_str + (long long)h.y * NSUB + sub;
+            uint2 u0 = __ldg(cp), u1 = __ldg(cp + NSUB);
             for (int it = i0; it < i1; ++it) {
-                const int k = __ldg(pl.c_item + it * 3), off = __ldg(pl.c_item + it * 3 + 1);
-                const int nit = __ldg(pl.c_item + it * 3 + 2);
+                const int n = h.z + h.w;
+                const int4 nh = __ldg(pl.c_item + it + 1);
+                const uint2* ncp = cp + n * NSUB;
+                const uint2 nu0 = __ldg(ncp), nu1 = __ldg(ncp + NSUB);
                 V aN = zero, aT = zero, a1 = zero, a2 = zero;
-                const unsigned* cw = pl.c_con + off * NSUB + sub;
-#pragma unroll 2
-                for (int i = 0; i < nit; ++i) {
-                    const unsigned w = __ldg(cw + i * NSUB);
-                    const unsigned a = aRX + (w & 0xFFFFu) * RXB;
-                    const double cf = coef_of(w);
-                    aN = vfma(cf, lds<RX_NET * RB>(a), aN);
-                    aT = vfma(cf, lds<RX_TT * RB>(a), aT);
-                    a1 = vfma(cf, lds<RX_X1 * RB>(a), a1);
-                    a2 = vfma(cf, lds<RX_X2 * RB>(a), a2);
-                }
+                auto unit = [&](uint2 c, int i) {
+                    const double sg = i < h.z ? 1.0 : -1.0;
+                    const unsigned x = aRX + c.x, y = aRX + c.y;
+                    aN = vfma(sg, vadd(lds<RX_NET * RB>(x), lds<RX_NET * RB>(y)), aN);
+                    aT = vfma(sg, vadd(lds<RX_TT * RB>(x), lds<RX_TT * RB>(y)), aT);
+                    a1 = vfma(sg, vadd(lds<RX_X1 * RB>(x), lds<RX_X1 * RB>(y)), a1);
+                    a2 = vfma(sg, vadd(lds<RX_X2 * RB>(x), lds<RX_X2 * RB>(y)), a2);
+                };
+                if (n > 0) unit(u0, 0);
+                if (n > 1) unit(u1, 1);
+#pragma unroll 1
+                for (int i = 2; i < n; ++i) unit(__ldg(cp + i * NSUB), i);
                 aN = sub_sum<GS>(aN); aT = sub_sum<GS>(aT); a1 = sub_sum<GS>(a1); a2 = sub_sum<GS>(a2);
                 if (sub == 0) {
-                    const unsigned a = aSP + k * SPB;
-                    const double wk = __ldg(tb.sp_w + k);
+                    const unsigned a = aSP + h.x;
+                    const double wk = __ldg(tb.sp_w + h.x / SPB);
                     const V comp = vmul(aN, mwr);
                     a1 = vadd(a1, comp);
                     a2 = vsub(a2, comp);
-                    const V hW = lds<SP_HW * RB>(a), cp = lds<SP_CP * RB>(a);
+                    const V hW = lds<SP_HW * RB>(a), cp_ = lds<SP_CP * RB>(a);
                     pH1 = vfma(hW, aN, pH1);
                     pHA = vfma(hW, a1, pHA);
                     pHB = vfma(hW, a2, pHB);
                     pHT = vfma(hW, aT, pHT);
-                    pSCP = vfma(vmul(wk, cp), aN, pSCP);
+                    pSCP = vfma(vmul(wk, cp_), aN, pSCP);
                     sts<SP_WA * RB>(a, vmul(wk, a1));
                     sts<SP_WB * RB>(a, vmul(wk, a2));
                     sts<SP_WT * RB>(a, vmul(wk, aT));
                 }
+                h = nh; cp = ncp; u0 = nu0; u1 = nu1;
             }
             if (sub == 0) {
                 const unsigned a = aPA + warp * NPART * RB;
@@ -498,7 +655,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
 
         // ------------------------------------------------------------ phase DE
         if (warp == 0) {
-            // energy-equation scalars from the per-warp partial sums; result of quantity q
+            // energy-equation scalars from the per-warp partial sums; the result of quantity q
             // replaces warp 0's own partial
             for (int q = sub; q < NPART; q += NSUB) {
                 V a = zero;
@@ -512,80 +669,122 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 const V cpavg = lds<D_CPAVG * RB>(aPA), wdcp = lds<D_WDCP * RB>(aPA);
                 const V rho = lds<Q_RHO * RB>(aSC), cpl = lds<SP_CP * RB>(aSP + last * SPB);
                 const V nwt{-1.0 / cpavg.x, -1.0 / cpavg.y};
-                sts<Q_NWT * RB>(aSC, nwt);
-                sts<Q_A0 * RB>(aSC, vmul(nwt, HA));
-                sts<Q_B0 * RB>(aSC, vmul(nwt, HB));
-                sts<Q_XT * RB>(aSC, V{H1.x / (rho.x * cpavg.x * cpavg.x), H1.y / (rho.y * cpavg.y * cpavg.y)});
-                sts<Q_CPL * RB>(aSC, cpl);
+                sts<S_NWT * RB>(aSD, nwt);
+                sts<S_A0 * RB>(aSD, vmul(nwt, HA));
+                sts<S_B0 * RB>(aSD, vmul(nwt, HB));
+                sts<S_XT * RB>(aSD, V{H1.x / (rho.x * cpavg.x * cpavg.x), H1.y / (rho.y * cpavg.y * cpavg.y)});
+                sts<S_CPL * RB>(aSD, cpl);
                 // jac[0] (cj:1853-1905)
                 store(0u, V{-(-wdcp.x / cpavg.x * H1.x + SCP.x + HT.x * rho.x) / (rho.x * cpavg.x),
-                            -(-wdcp.y / cpavg.y * H1.y + SCP.y + HT.y * rho.y) / (rho.y * cpavg.y)});
+                            -(-wdcp.y / cpavg.y * H1.y + SCP.y + HT.y * rho.y) / (rho.y * cpavg.y)}, true);
             }
             if (pl.t_sync > 32) {
                 __threadfence_block();
                 asm volatile("bar.arrive 1, %0;" ::"r"(pl.t_sync) : "memory");
             }
+            // the next group's phase A0 (its inputs come from HBM: latency hidden behind DE)
+            if (grp + gridDim.x < ngroups) phase_a0(grp + gridDim.x, buf ^ 1);
         }
         {
-            // species rows: dense rank-2 part + sparse gather
-            const uint2* up = pl.e_str + (long long)__ldg(pl.e_off + warp) * NSUB + sub;
-            const int nst = __ldg(pl.e_nst + warp);
-            for (int st = 0; st < nst; ++st) {
-                const uint2 r = __ldg(up);
-                up += NSUB;
-                const unsigned L2 = r.x >> 22, e = r.x & NULL_E;
-                V acc0 = zero, acc1 = zero;
-                double pw = 0.0;
-                if (L2) {
-                    const uint2 pu = __ldg(up);
-                    pw = __hiloint2double((int)pu.y, (int)pu.x);
-                    up += NSUB;
+            // class S: elements with a sparse part, two steps per iteration, next pair in flight
+            const int st0 = __ldg(pl.s_off + warp), st1 = __ldg(pl.s_off + warp + 1);
+            const uint4* sp = pl.s_str + (long long)st0 * 2 * NSUB + sub;
+            const uint2* ov = pl.o_str + (long long)__ldg(pl.o_off + warp) * NSUB + sub;
+            uint4 nA0 = __ldg(sp), nB0 = __ldg(sp + NSUB), nA1 = __ldg(sp + 2 * NSUB), nB1 = __ldg(sp + 3 * NSUB);
+            for (int st = st0; st < st1; st += 2) {
+                const uint4 A0 = nA0, B0 = nB0, A1 = nA1, B1 = nB1;
+                sp += 4 * NSUB;
+                nA0 = __ldg(sp); nB0 = __ldg(sp + NSUB); nA1 = __ldg(sp + 2 * NSUB); nB1 = __ldg(sp + 3 * NSUB);
+                const unsigned La = A0.x >> 22, Lb = A1.x >> 22;
+                const unsigned xa = aSP + (A0.y & 0xFFFFFu), xb = aSP + (A1.y & 0xFFFFFu);
+                const double2 cfa = __ldg(pl.colfac + (A0.y >> 20)), cfb = __ldg(pl.colfac + (A1.y >> 20));
+                V pa = vadd(lds<0>(aRAW + B0.x), lds<0>(aRAW + B0.z)), ma = vadd(lds<0>(aRAW + B0.y), lds<0>(aRAW + B0.w));
+                V pb = vadd(lds<0>(aRAW + B1.x), lds<0>(aRAW + B1.z)), mb = vadd(lds<0>(aRAW + B1.y), lds<0>(aRAW + B1.w));
+                V va = vfma(cfa.y, lds<RB>(xa), vmul(cfa.x, lds<0>(xa)));
+                V vb = vfma(cfb.y, lds<RB>(xb), vmul(cfb.x, lds<0>(xb)));
+                if (La > 2) {
 #pragma unroll 2
-                    for (unsigned i = 0; i < L2; ++i) {
-                        const uint2 c = __ldg(up + i * NSUB);
-                        acc0 = vfma(coef_of(c.x), lds<0>(aRAW + (c.x & 0xFFFFu) * RB), acc0);
-                        acc1 = vfma(coef_of(c.y), lds<0>(aRAW + (c.y & 0xFFFFu) * RB), acc1);
+                    for (unsigned i = 2; i < La; ++i) {
+                        const uint2 c = __ldg(ov);
+                        prefetch_l1(ov + 8 * NSUB);
+                        ov += NSUB;
+                        pa = vadd(pa, lds<0>(aRAW + c.x));
+                        ma = vadd(ma, lds<0>(aRAW + c.y));
                     }
-                    up += L2 * NSUB;
                 }
-                if (e != NULL_E) {
-                    const unsigned a = aSP + (r.y & 0xFFFFu) * RB;
-                    const double2 cf = __ldg(pl.colfac + (r.y >> 16));
-                    V v = vfma(cf.y, lds<RB>(a), vmul(cf.x, lds<0>(a)));
-                    if (L2) v = vfma(pw, vadd(acc0, acc1), v);
-                    store(e, v);
+                if (Lb > 2) {
+#pragma unroll 2
+                    for (unsigned i = 2; i < Lb; ++i) {
+                        const uint2 c = __ldg(ov);
+                        ov += NSUB;
+                        pb = vadd(pb, lds<0>(aRAW + c.x));
+                        mb = vadd(mb, lds<0>(aRAW + c.y));
+                    }
                 }
+                va = vfma(__hiloint2double((int)A0.w, (int)A0.z), vsub(pa, ma), va);
+                vb = vfma(__hiloint2double((int)A1.w, (int)A1.z), vsub(pb, mb), vb);
+                store(A0.x & NULL_E, va, (A0.x & NULL_E) != NULL_E);
+                store(A1.x & NULL_E, vb, (A1.x & NULL_E) != NULL_E);
             }
         }
         {
-            // energy-equation row (cj:3095-3254): enthalpy-weighted gathers
-            const int nst = __ldg(pl.t_nst + warp);
-            if (nst) {
-                if (warp != 0) asm volatile("bar.sync 1, %0;" ::"r"(pl.t_sync) : "memory");
+            // class D: dense-only elements, four steps per iteration, next four in flight
+            const int st0 = __ldg(pl.d_off + warp), st1 = __ldg(pl.d_off + warp + 1);
+            const uint2* dp = pl.d_str + (long long)st0 * NSUB + sub;
+            uint2 nx[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nx[j] = __ldg(dp + j * NSUB);
+            for (int st = st0; st < st1; st += 4) {
+                uint2 r[4];
+                dp += 4 * NSUB;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { r[j] = nx[j]; nx[j] = __ldg(dp + j * NSUB); }
+                V v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned x = aSP + (r[j].y & 0xFFFFFu);
+                    const double2 cf = __ldg(pl.colfac + (r[j].y >> 20));
+                    v[j] = vfma(cf.y, lds<RB>(x), vmul(cf.x, lds<0>(x)));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) store(r[j].x, v[j], r[j].x != NULL_E);
+            }
+        }
+        {
+            // class T, the energy-equation row (cj:3095-3254): per column an enthalpy-weighted
+            // gather split over the sub-groups of the warp
+            const int nit = __ldg(pl.t_n + warp);
+            if (nit) {
                 const uint2* up = pl.t_str + (long long)__ldg(pl.t_off + warp) * NSUB + sub;
-                const V nwt = lds<Q_NWT * RB>(aSC), A0 = lds<Q_A0 * RB>(aSC), B0 = lds<Q_B0 * RB>(aSC);
-                const V XT = lds<Q_XT * RB>(aSC), cpl = lds<Q_CPL * RB>(aSC);
-                for (int st = 0; st < nst; ++st) {
-                    const uint2 r = __ldg(up);
-                    up += NSUB;
-                    const unsigned L2 = r.x >> 22, e = r.x & NULL_E;
+                uint2 hd = __ldg(up), c0 = __ldg(up + NSUB), c1 = __ldg(up + 2 * NSUB);
+                if (warp != 0) asm volatile("bar.sync 1, %0;" ::"r"(pl.t_sync) : "memory");
+                const V nwt = lds<S_NWT * RB>(aSD), A0 = lds<S_A0 * RB>(aSD), B0 = lds<S_B0 * RB>(aSD);
+                const V XT = lds<S_XT * RB>(aSD), cpl = lds<S_CPL * RB>(aSD);
+                for (int it = 0; it < nit; ++it) {
+                    const unsigned n = hd.y & 0xFFFFu, col = hd.y >> 16, e = hd.x;
+                    const uint2* nup = up + (n + 1) * NSUB;
+                    const uint2 nhd = __ldg(nup), nc0 = __ldg(nup + NSUB), nc1 = __ldg(nup + 2 * NSUB);
                     V acc0 = zero, acc1 = zero;
-#pragma unroll 2
-                    for (unsigned i = 0; i < L2; ++i) {
-                        const uint2 c = __ldg(up + i * NSUB);
-                        acc0 = vfma(lds<RX_DH * RB>(aRX + (c.x >> 16) * RXB), lds<0>(aRAW + (c.x & 0xFFFFu) * RB), acc0);
-                        acc1 = vfma(lds<RX_DH * RB>(aRX + (c.y >> 16) * RXB), lds<0>(aRAW + (c.y & 0xFFFFu) * RB), acc1);
+                    if (n) {
+                        acc0 = vmul(lds<RX_DH * RB>(aRX + c0.y), lds<0>(aRAW + c0.x));
+                        acc1 = vmul(lds<RX_DH * RB>(aRX + c1.y), lds<0>(aRAW + c1.x));
+#pragma unroll 1
+                        for (unsigned i = 2; i < n; i += 2) {
+                            const uint2 c = __ldg(up + (i + 1) * NSUB), d = __ldg(up + (i + 2) * NSUB);
+                            acc0 = vfma(lds<RX_DH * RB>(aRX + c.y), lds<0>(aRAW + c.x), acc0);
+                            acc1 = vfma(lds<RX_DH * RB>(aRX + d.y), lds<0>(aRAW + d.x), acc1);
+                        }
                     }
-                    up += L2 * NSUB;
-                    if (e != NULL_E) {
-                        const double2 cf = __ldg(pl.colfac + r.y);
-                        const V cpj = lds<SP_CP * RB>(aSP + (r.y - 1) * SPB);
-                        const V E0 = vadd(acc0, acc1);
+                    const V E0 = sub_sum<GS>(vadd(acc0, acc1));
+                    if (sub == 0) {
+                        const double2 cf = __ldg(pl.colfac + col);
+                        const V cpj = lds<SP_CP * RB>(aSP + (col - 1) * SPB);
                         V v = vmul(cf.x, vfma(nwt, E0, A0));
                         v = vfma(cf.y, B0, v);
                         v = vfma(XT, vsub(cpj, cpl), v);
-                        store(e, v);
+                        store(e, v, true);
                     }
+                    up = nup; hd = nhd; c0 = nc0; c1 = nc1;
                 }
             }
         }

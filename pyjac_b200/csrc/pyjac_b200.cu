@@ -325,9 +325,11 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     }
     UP(plan.rx, "p5_rx", int4, 1);
     UP(plan.b_off, "p5_b_off", int, 1); UP(plan.b_npm, "p5_b_npm", int, 1); UP(plan.b_item, "p5_b_item", int, 1);
-    UP(plan.c_off, "p5_c_off", int, 1); UP(plan.c_item, "p5_c_item", int, 1); UP(plan.c_con, "p5_c_con", unsigned, 1);
-    UP(plan.e_off, "p5_e_off", int, 1); UP(plan.e_nst, "p5_e_nst", int, 1); UP(plan.e_str, "p5_e_str", uint2, 1);
-    UP(plan.t_off, "p5_t_off", int, 1); UP(plan.t_nst, "p5_t_nst", int, 1); UP(plan.t_str, "p5_t_str", uint2, 1);
+    UP(plan.c_off, "p5_c_off", int, 1); UP(plan.c_item, "p5_c_item", int4, 1); UP(plan.c_str, "p5_c_str", uint2, 1);
+    UP(plan.d_off, "p5_d_off", int, 1); UP(plan.d_str, "p5_d_str", uint2, 1);
+    UP(plan.s_off, "p5_s_off", int, 1); UP(plan.s_str, "p5_s_str", uint4, 1);
+    UP(plan.o_off, "p5_o_off", int, 1); UP(plan.o_str, "p5_o_str", uint2, 1);
+    UP(plan.t_off, "p5_t_off", int, 1); UP(plan.t_n, "p5_t_n", int, 1); UP(plan.t_str, "p5_t_str", uint2, 1);
     UP(plan.colfac, "p5_colfac", double2, 0);
 #undef UP
     if (!rc) {
@@ -381,7 +383,8 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
                          long long jac_ld, void* stream)
 {
     if (!m || n < 0 || (n && (!d_pres || !d_y || !d_jac))) return fail(PYJAC_EINVAL, "bad argument");
-    if (jac_layout == PYJAC_JAC_STATE_FASTEST && jac_ld < n) return fail(PYJAC_EINVAL, "jac_ld < n");
+    if (jac_layout == PYJAC_JAC_STATE_FASTEST && (jac_ld < n || jac_ld >= (1LL << 28)))
+        return fail(PYJAC_EINVAL, "jac_ld must be in [n, 2^28)");
     IO io{};
     io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
     io.jac = d_jac; io.jac_layout = jac_layout; io.jac_ld = jac_ld;

@@ -28,7 +28,7 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 SMEM_LIMIT = 232448          # bytes of dynamic shared memory one block may opt in to (sm_100)
-NSCAL = 16                   # per-state scalar rows kept in shared memory
+NSCAL = 24                   # per-state scalar rows: 2 x 8 from phase A0, 5 derived in DE
 NPART = 7                    # per-warp partial sums
 GS_CHOICES = (32, 16, 8, 4, 2)
 SP_SLOTS, RX_SLOTS = 8, 5    # C B dB hW WA(Y) WB WT cp  /  net tT X1 X2 dH
@@ -40,10 +40,10 @@ MAX_L2 = 1023
 COST_PLAIN, COST_IRREV, COST_THREE = 215.0, 150.0, 40.0
 COST_PM = {'thd': 300.0, 'lind': 450.0, 'troe': 900.0, 'sri': 1200.0}
 COST_EFF = 8.0
-COST_C_ITEM, COST_C_IT = 90.0, 18.0
-COST_J_STEP, COST_J_SPARSE, COST_J_IT = 22.0, 8.0, 16.0
-COST_T_STEP, COST_T_IT = 40.0, 18.0
-COST_DOTS = 150.0
+COST_C_ITEM, COST_C_IT = 90.0, 28.0
+COST_D_STEP, COST_S_STEP, COST_S_OVF = 20.0, 34.0, 12.0
+COST_T_ITEM, COST_T_IT = 60.0, 8.0
+COST_DOTS = 400.0            # warp 0: energy-equation scalars + the next group's phase A0
 
 
 def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:
@@ -59,7 +59,7 @@ def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:
 
     take('SP', (nsp + 1) * SP_SLOTS)     # species nsp: the empty reaction slot (C = 1, others 0)
     take('RX', (nr + 1) * RX_SLOTS)      # reaction nr: zeros (padding of the phase C lists)
-    take('RAW', nraw + 1)                # row nraw: zero (null contributions)
+    take('RAW', nraw + 2)                # row nraw: zero (null contributions); nraw + 1: scratch
     take('SC', NSCAL)
     take('PA', nw * NPART)
     L['total'] = off
@@ -141,105 +141,162 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
         b_off.append(len(b_item) // nsub)
     P['p5_b_off'] = i32(b_off)
     P['p5_b_npm'] = i32(b_npm)
-    P['p5_b_item'] = i32(b_item or [-1] * nsub)
+    P['p5_b_item'] = i32(b_item + [-1] * nsub)               # ends with a null round (look-ahead)
+
+    # byte offsets inside the shared-memory regions (a row is GS doubles)
+    RB = gs * 8
+    SPB, RXB = SP_SLOTS * RB, RX_SLOTS * RB
+    PF = 16                                    # null units after each stream (prefetch runs ahead)
+
+    def expand(lst):
+        """[(source, nu)] -> (sources with weight +1, sources with weight -1), nu an integer."""
+        plus, minus = [], []
+        for src, c in lst:
+            if not float(c).is_integer():
+                raise ValueError('non-integer coefficient %r' % c)
+            (plus if c > 0 else minus).extend([src] * int(abs(c)))
+        return plus, minus
 
     # ---------------------------------------------------------------- phase C
-    c_cost = [COST_C_ITEM + COST_C_IT * ((len(red[k]) + nsub - 1) // nsub) for k in range(nsp)]
+    # item: species k; its (reaction, nu) list split into +1 and -1 entries, each cut into units
+    # of 2 entries per sub-group; stream unit u of sub-group s is c_str[(u * NSUB + s) * 2 + {0,1}]
+    c_lists = [expand(red[k]) for k in range(nsp)]
+    c_np = [(len(pl_) + 2 * nsub - 1) // (2 * nsub) for pl_, _ in c_lists]
+    c_nm = [(len(mi_) + 2 * nsub - 1) // (2 * nsub) for _, mi_ in c_lists]
+    c_cost = [COST_C_ITEM + COST_C_IT * (c_np[k] + c_nm[k]) for k in range(nsp)]
     bins, _ = _lpt(c_cost, nw)
-    c_off, c_item, c_con = [0], [], []
+    c_off, c_item, c_str = [0], [], []
     for w in range(nw):
         for k in bins[w]:
-            words = [p | (hi16(nu) << 16) for p, nu in red[k]]
-            nit = (len(words) + nsub - 1) // nsub
-            words += [nr] * (nit * nsub - len(words))          # reaction row nr is all zero
-            c_item += [k, len(c_con) // nsub, nit]
-            c_con += words
-        c_off.append(len(c_item) // 3)
+            c_item += [k * SPB, len(c_str) // (2 * nsub), c_np[k], c_nm[k]]
+            for lst, n in ((c_lists[k][0], c_np[k]), (c_lists[k][1], c_nm[k])):
+                offs = [p * RXB for p in lst] + [nr * RXB] * (n * 2 * nsub - len(lst))
+                for u in range(n):
+                    for sb in range(nsub):
+                        c_str += [offs[(u * nsub + sb) * 2], offs[(u * nsub + sb) * 2 + 1]]
+        c_off.append(len(c_item) // 4)
     P['p5_c_off'] = i32(c_off)
-    P['p5_c_item'] = i32(c_item)
-    P['p5_c_con'] = u32(c_con + [nr] * nsub)
+    P['p5_c_item'] = i32(c_item + [0, len(c_str) // (2 * nsub), 0, 0])   # + null item (look-ahead)
+    P['p5_c_str'] = u32(c_str + [nr * RXB] * (2 * nsub * PF))
 
-    # ---------------------------------------------------------------- phase DE, species rows
-    # element (col, k): output row k + 1 of column col; col 0 is the temperature column
+    # ---------------------------------------------------------------- phase DE
+    # element (col, k): output row k + 1 of column col; col 0 is the temperature column.  NSUB
+    # elements form a step.  Three classes of work, each with its own stream:
+    #   D  dense-only elements: one uint2 {e, SP offset | col << 20} per element; a warp takes
+    #      them four steps at a time
+    #   S  elements with a sparse part of padded length L >= 1: two uint4 per element,
+    #      {e | L << 22, SP offset | col << 20, the double (1/W_j) W_k} and the first two units
+    #      {+1 raw row, -1 raw row, +1 raw row, -1 raw row} (byte offsets; padding = zero row);
+    #      units 3..L go to an overflow stream of uint2; a warp takes two steps at a time
+    #   T  the energy-equation row: one item per column, its enthalpy-weighted list split over
+    #      the NSUB sub-groups: header {e, n | col << 16}, then n units {raw row, reaction row}
+    def row_words(col, k):
+        slot = SLOT_WT if col == 0 else SLOT_WA
+        return [col * nsp + k + 1, (k * SPB + slot * RB) | (col << 20)]
+    null_row = [NULL_E, SLOT_WA * RB]
+    zr = nraw * RB
+
     elems = []
     for col in range(nsp):
         for k in range(last):
-            lst = contrib.get((k, col - 1), []) if col else []
-            elems.append((len(lst), col, k, lst))
-    elems.sort(key=lambda e: (-e[0], e[1], e[2]))
-    steps = []
-    for c0 in range(0, len(elems), nsub):
-        grp = elems[c0:c0 + nsub]
-        L2 = (grp[0][0] + 1) // 2
-        if L2 > MAX_L2:
+            plus, minus = expand(contrib.get((k, col - 1), []) if col else [])
+            elems.append((max(len(plus), len(minus)), col, k, plus, minus))
+    dense = sorted((e for e in elems if e[0] == 0), key=lambda e: (e[1], e[2]))
+    sparse = sorted((e for e in elems if e[0] > 0), key=lambda e: (-e[0], e[1], e[2]))
+
+    d_steps = []
+    for c0 in range(0, len(dense), nsub):
+        grp = dense[c0:c0 + nsub]
+        d_steps.append([row_words(e[1], e[2]) for e in grp] + [null_row] * (nsub - len(grp)))
+    d_quads = []
+    for c0 in range(0, len(d_steps), 4):
+        q4 = d_steps[c0:c0 + 4]
+        d_quads.append(q4 + [[null_row] * nsub] * (4 - len(q4)))
+
+    s_steps = []                               # (A words, B words, overflow units, L)
+    for c0 in range(0, len(sparse), nsub):
+        grp = sparse[c0:c0 + nsub]
+        L = grp[0][0]
+        if L > MAX_L2:
             raise ValueError('sparse Jacobian element with too many contributions')
-        units: List[List[int]] = []            # units[u][sub] = [x, y]
-        row, pw = [], []
-        for s in range(nsub):
-            if s < len(grp):
-                _, col, k, lst = grp[s]
-                slot = SLOT_WT if col == 0 else SLOT_WA
-                row.append([(col * nsp + k + 1) | (L2 << 22), (k * SP_SLOTS + slot) | (col << 16)])
-                pw.append(_f64_words(sp_iw[col - 1] * sp_w[k]) if col else [0, 0])
+        A, B, ovf = [], [], [[] for _ in range(max(L - 2, 0))]
+        for sb in range(nsub):
+            if sb < len(grp):
+                _, col, k, plus, minus = grp[sb]
+                rw = row_words(col, k)
+                A.append([rw[0] | (L << 22), rw[1]] + _f64_words(sp_iw[col - 1] * sp_w[k]))
             else:
-                row.append([NULL_E | (L2 << 22), SLOT_WA])
-                pw.append([0, 0])
-        units.append(row)
-        if L2:
-            units.append(pw)
-            for i2 in range(L2):
-                u = []
-                for s in range(nsub):
-                    lst = grp[s][3] if s < len(grp) else []
-                    w = [src | (hi16(c) << 16) for src, c in lst[2 * i2:2 * i2 + 2]]
-                    u.append(w + [nraw] * (2 - len(w)))        # null: zero raw row, coefficient +0
-                units.append(u)
-        steps.append((COST_J_STEP + (COST_J_SPARSE + COST_J_IT * L2 if L2 else 0.0), units))
+                plus, minus = [], []
+                A.append([NULL_E | (L << 22), null_row[1], 0, 0])
+            po = [x * RB for x in plus] + [zr] * (max(L, 2) - len(plus))
+            mo = [x * RB for x in minus] + [zr] * (max(L, 2) - len(minus))
+            B.append([po[0], mo[0], po[1], mo[1]])
+            for i in range(2, L):
+                ovf[i - 2].append([po[i], mo[i]])
+        s_steps.append((A, B, ovf, L))
+    null_s = ([[NULL_E, null_row[1], 0, 0]] * nsub, [[zr] * 4] * nsub, [], 0)
+    s_pairs = []
+    for c0 in range(0, len(s_steps), 2):
+        pr_ = s_steps[c0:c0 + 2]
+        s_pairs.append(pr_ + [null_s] * (2 - len(pr_)))
+
+    t_items = []
+    for j in range(last):
+        lst = tcontrib.get(j, [])
+        n = (len(lst) + nsub - 1) // nsub
+        n += n & 1                                             # units come in pairs
+        if n > 0xFFFF:
+            raise ValueError('energy-row element with too many contributions')
+        pad = lst + [(nraw, nr)] * (n * nsub - len(lst))
+        units = [[[(j + 1) * nsp, n | ((j + 1) << 16)]] * nsub]
+        for u in range(n):
+            units.append([[pad[u * nsub + sb][0] * RB, pad[u * nsub + sb][1] * RXB] for sb in range(nsub)])
+        t_items.append((n, units))
+
+    # one longest-first assignment over all three classes
+    costs = ([COST_T_ITEM + COST_T_IT * n for n, _ in t_items] +
+             [sum(COST_S_STEP + COST_S_OVF * max(st[3] - 2, 0) for st in pr_) for pr_ in s_pairs] +
+             [4 * COST_D_STEP] * len(d_quads))
     init = [0.0] * nw
     init[0] = COST_DOTS
-    bins, load = _lpt([st[0] for st in steps], nw, init)
-    e_off, e_nst, e_str = [0], [], []
+    allbins, _ = _lpt(costs, nw, init)
+    nT, nS = len(t_items), len(s_pairs)
+    d_off, d_str, s_off, s_str, o_off, o_str, t_off, t_n, t_str = [0], [], [0], [], [0], [], [0], [], []
     for w in range(nw):
-        e_nst.append(len(bins[w]))
-        for ix in bins[w]:
-            for u in steps[ix][1]:
-                for xy in u:
-                    e_str += xy
-        e_off.append(len(e_str) // (2 * nsub))
-    P['p5_e_off'] = i32(e_off)
-    P['p5_e_nst'] = i32(e_nst)
-    P['p5_e_str'] = u32(e_str + [0] * (2 * nsub))
-
-    # ---------------------------------------------------------------- phase DE, energy row
-    telems = sorted(((len(tcontrib.get(j, [])), j) for j in range(last)), key=lambda e: (-e[0], e[1]))
-    tsteps = []
-    for c0 in range(0, len(telems), nsub):
-        grp = telems[c0:c0 + nsub]
-        L2 = (grp[0][0] + 1) // 2
-        if L2 > MAX_L2:
-            raise ValueError('energy-row element with too many contributions')
-        units = [[[((j + 1) * nsp) | (L2 << 22), j + 1] for _, j in grp] +
-                 [[NULL_E | (L2 << 22), 1]] * (nsub - len(grp))]
-        for i2 in range(L2):
-            u = []
-            for s in range(nsub):
-                lst = tcontrib.get(grp[s][1], []) if s < len(grp) else []
-                w = [src | (p << 16) for src, p in lst[2 * i2:2 * i2 + 2]]
-                u.append(w + [nraw | (nr << 16)] * (2 - len(w)))
-            units.append(u)
-        tsteps.append((COST_T_STEP + COST_T_IT * L2, units))
-    bins, _ = _lpt([st[0] for st in tsteps], nw, load)
-    t_off, t_nst, t_str = [0], [], []
-    for w in range(nw):
-        t_nst.append(len(bins[w]))
-        for ix in bins[w]:
-            for u in tsteps[ix][1]:
-                for xy in u:
-                    t_str += xy
+        mine = sorted(allbins[w])
+        for ix in mine:
+            if ix < nT:
+                for u in t_items[ix][1]:
+                    for xy in u:
+                        t_str += xy
+            elif ix < nT + nS:
+                for A, B, ovf, _ in s_pairs[ix - nT]:
+                    for ws in A:
+                        s_str += ws
+                    for ws in B:
+                        s_str += ws
+                    for u in ovf:
+                        for xy in u:
+                            o_str += xy
+            else:
+                for st in d_quads[ix - nT - nS]:
+                    for xy in st:
+                        d_str += xy
+        t_n.append(sum(1 for ix in mine if ix < nT))
         t_off.append(len(t_str) // (2 * nsub))
+        s_off.append(len(s_str) // (8 * nsub))          # in steps
+        o_off.append(len(o_str) // (2 * nsub))
+        d_off.append(len(d_str) // (2 * nsub))          # in steps
+    P['p5_d_off'] = i32(d_off)
+    P['p5_d_str'] = u32(d_str + null_row * (nsub * PF))
+    P['p5_s_off'] = i32(s_off)
+    P['p5_s_str'] = u32(s_str + ([NULL_E, null_row[1], 0, 0] * nsub + [zr] * (4 * nsub)) * 4)
+    P['p5_o_off'] = i32(o_off)
+    P['p5_o_str'] = u32(o_str + [zr] * (2 * nsub * PF))
     P['p5_t_off'] = i32(t_off)
-    P['p5_t_nst'] = i32(t_nst)
-    P['p5_t_str'] = u32(t_str + [0] * (2 * nsub))
+    P['p5_t_n'] = i32(t_n)
+    P['p5_t_str'] = u32(t_str + [zr, nr * RXB] * (nsub * PF))
+    t_nst = t_n
 
     # per column: (1 / W_j, (1 / W_j) (W_j / W_N)); the temperature column takes W_k * T-term as is
     colfac = [1.0, 0.0]

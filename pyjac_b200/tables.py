@@ -58,6 +58,7 @@ from .mechanism import Mechanism
 F_REV, F_THD, F_PDEP, F_LOW, F_TROE, F_SRI = 1, 2, 4, 8, 16, 32
 F_PMT, F_PMT_INJ, F_TROE_T2, F_SRI5, F_SRI5_DT, F_NO_T = 64, 128, 256, 512, 1024, 2048
 F_EFFN1 = 4096         # third-body (non fall-off) reaction with a collider list: n' += 1
+F_HAS_LAST = 1 << 13   # (Jacobian kernel record only) an occupied slot holds the last species
 F_WANT_PMT = 1 << 16   # the kernel stores pres_mod_temp as a raw value
 F_EFF_SLOTS = 1 << 17  # ... and pres_mod_temp * (alpha_j - 1) for each listed collider j
 NRE_SHIFT, NPR_SHIFT = 20, 24    # occupied reactant / product slots
@@ -579,8 +580,12 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     rec5[:, :9] = rec[:, :9]
     for a in range(3):
         rec5[:, 9 + a] = slots[:, 2 * a] | (slots[:, 2 * a + 1] << 16)
+    dst5 = np.where(rx_dst == NONE, nraw + 1, rx_dst).astype(np.int32)     # none -> scratch raw row
     for a in range(4):
-        rec5[:, 12 + a] = rx_dst[:, 2 * a].astype(np.int32) | (rx_dst[:, 2 * a + 1].astype(np.int32) << 16)
+        rec5[:, 12 + a] = dst5[:, 2 * a] | (dst5[:, 2 * a + 1] << 16)
+    for p in range(nr):
+        if any(int(sl) == last for sl in slots[p]):
+            rec5[p, 8] |= F_HAS_LAST
     T['p5_rx'] = rec5.ravel()
 
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])

@@ -208,33 +208,38 @@ def evaluate(Tb, P, y):
         R4[p, 0], R4[p, 1], R4[p, 2], R4[p, 3] = net * PM, tT, X1, X2
         RH[p] = (hw[:, s[3]] + hw[:, s[4]] + hw[:, s[5]]) - (hw[:, s[0]] + hw[:, s[1]] + hw[:, s[2]])
 
-    # --- phase C of the plan: per species, lists of (reaction | hi16(nu) << 16) split over the
-    # NSUB sub-groups of a warp (padding words point at the all-zero reaction row nr)
-    def coef(word):
-        return float(np.uint64((int(word) >> 16) << 48).view(np.float64))
+    # --- phase C of the plan: per species, +1 and -1 lists of reaction-row byte offsets, two
+    # entries per unit and sub-group (padding entries point at the all-zero reaction row nr)
     cfg = Tb['p5_cfg']
     gs, nt, nw, nsub = (int(v) for v in cfg[:4])
     assert nsub * gs == 64 and nt == nw * 32
+    RB = gs * 8
+    SPB, RXB = 8 * RB, 5 * RB
     R4z = np.concatenate([R4, np.zeros((1, 4, n))], axis=0)
     wdot = np.zeros((n, nsp)); tcol = np.zeros((n, nsp)); Ak = np.zeros((n, nsp)); Bk = np.zeros((n, nsp))
-    c_item, c_con = Tb['p5_c_item'].reshape(-1, 3), Tb['p5_c_con'].view(np.uint32)
+    c_item, c_str = Tb['p5_c_item'].reshape(-1, 4), Tb['p5_c_str'].view(np.uint32)
     seen_k = set()
     for wp in range(nw):
         for it in range(Tb['p5_c_off'][wp], Tb['p5_c_off'][wp + 1]):
-            k, off, nit = (int(v) for v in c_item[it])
+            spoff, u, n_p, n_m = (int(v) for v in c_item[it])
+            assert spoff % SPB == 0
+            k = spoff // SPB
             assert k not in seen_k
             seen_k.add(k)
-            for wd in c_con[off * nsub:(off + nit) * nsub]:
-                cf, rxn = coef(wd), int(wd) & 0xFFFF
-                wdot[:, k] += cf * R4z[rxn, 0]; tcol[:, k] += cf * R4z[rxn, 1]
-                Ak[:, k] += cf * R4z[rxn, 2]; Bk[:, k] += cf * R4z[rxn, 3]
+            for sign, cnt in ((1.0, n_p), (-1.0, n_m)):
+                for off in c_str[u * nsub * 2:(u + cnt) * nsub * 2]:
+                    assert off % RXB == 0
+                    rxn = int(off) // RXB
+                    wdot[:, k] += sign * R4z[rxn, 0]; tcol[:, k] += sign * R4z[rxn, 1]
+                    Ak[:, k] += sign * R4z[rxn, 2]; Bk[:, k] += sign * R4z[rxn, 3]
+                u += cnt
     assert seen_k == set(range(nsp))
     comp = wdot * (mw_avg * rho_inv)[:, None]
     Ak = Ak + comp
     Bk = Bk - comp
 
-    # --- phase DE of the plan: elements in steps of NSUB, one padded length L2 (pairs of
-    # contributions) per step; unit u of a warp's stream is e_str[(u * NSUB + sub) * 2 + {0, 1}]
+    # --- phase DE of the plan: elements in steps of NSUB with one padded length L per step;
+    # unit u of a warp's stream is e_str[(u * NSUB + sub) * 2 + {0, 1}]
     raw[:, nraw] = 0.0
     RHz = np.concatenate([RH, np.zeros((1, n))], axis=0)
     wt = 1.0 / cp_avg
@@ -250,61 +255,74 @@ def evaluate(Tb, P, y):
     slots8[:, :, 7] = cp
     colfac = Tb['p5_colfac'].reshape(nsp, 2)
     jac = np.full((n, nsp * nsp), np.nan)          # [state, col * nsp + row]; every element once
-    e_str = Tb['p5_e_str'].view(np.uint32)
     NULL_E = 0x3FFFFF
-    for wp in range(nw):
-        u = int(Tb['p5_e_off'][wp])
-        for _ in range(int(Tb['p5_e_nst'][wp])):
-            rowu = [(int(e_str[(u * nsub + sub) * 2]), int(e_str[(u * nsub + sub) * 2 + 1])) for sub in range(nsub)]
-            L2 = rowu[0][0] >> 22
-            assert all(r[0] >> 22 == L2 for r in rowu)
-            u += 1
-            pwu = None
-            if L2:
-                pwu = [np.array([e_str[(u * nsub + sub) * 2], e_str[(u * nsub + sub) * 2 + 1]], dtype=np.uint32)
-                       .view(np.float64)[0] for sub in range(nsub)]
-                u += 1
-            for sub in range(nsub):
-                eidx, y = rowu[sub][0] & 0x3FFFFF, rowu[sub][1]
-                acc = np.zeros(n)
-                for i2 in range(L2):
-                    for h in range(2):
-                        cw = int(e_str[((u + i2) * nsub + sub) * 2 + h])
-                        acc += coef(cw) * raw[:, cw & 0xFFFF]
-                if eidx == NULL_E:
-                    assert not acc.any()
-                    continue
-                sl, col = y & 0xFFFF, y >> 16
-                a_, b_ = slots8[:, sl // 8, sl % 8], slots8[:, (sl + 1) // 8, (sl + 1) % 8]
-                v = colfac[col, 0] * a_ + colfac[col, 1] * b_
-                if L2:
-                    v = v + pwu[sub] * acc
-                assert np.isnan(jac[:, eidx]).all() and eidx == col * nsp + sl // 8 + 1
-                jac[:, eidx] = v
-            u += L2
-        assert u == Tb['p5_e_off'][wp + 1]
+
+    def rawrow(off):
+        assert off % RB == 0 and off // RB <= nraw
+        return raw[:, off // RB]
+
+    def put(eidx, y, extra):
+        """dense part of element eidx from the species-row offset / column word y, plus extra."""
+        off, col = y & 0xFFFFF, y >> 20
+        assert off % RB == 0
+        sl = off // RB
+        a_, b_ = slots8[:, sl // 8, sl % 8], slots8[:, (sl + 1) // 8, (sl + 1) % 8]
+        assert np.isnan(jac[:, eidx]).all() and eidx == col * nsp + sl // 8 + 1
+        jac[:, eidx] = colfac[col, 0] * a_ + colfac[col, 1] * b_ + extra
+
+    d_str = Tb['p5_d_str'].view(np.uint32)
+    s_str, o_str = Tb['p5_s_str'].view(np.uint32), Tb['p5_o_str'].view(np.uint32)
     t_str = Tb['p5_t_str'].view(np.uint32)
     for wp in range(nw):
-        u = int(Tb['p5_t_off'][wp])
-        for _ in range(int(Tb['p5_t_nst'][wp])):
-            rowu = [(int(t_str[(u * nsub + sub) * 2]), int(t_str[(u * nsub + sub) * 2 + 1])) for sub in range(nsub)]
-            L2 = rowu[0][0] >> 22
-            u += 1
+        # class D: dense-only elements, four steps at a time
+        lo, hi = int(Tb['p5_d_off'][wp]), int(Tb['p5_d_off'][wp + 1])
+        assert (hi - lo) % 4 == 0
+        for st in range(lo, hi):
             for sub in range(nsub):
-                eidx, col = rowu[sub][0] & 0x3FFFFF, rowu[sub][1]
-                E0 = np.zeros(n)
-                for i2 in range(L2):
-                    for h in range(2):
-                        cw = int(t_str[((u + i2) * nsub + sub) * 2 + h])
-                        E0 += RHz[cw >> 16] * raw[:, cw & 0xFFFF]
+                eidx, y = int(d_str[(st * nsub + sub) * 2]), int(d_str[(st * nsub + sub) * 2 + 1])
+                if eidx != NULL_E:
+                    put(eidx, y, 0.0)
+        # class S: two uint4 per element and step, overflow units beyond the first two
+        lo, hi = int(Tb['p5_s_off'][wp]), int(Tb['p5_s_off'][wp + 1])
+        assert (hi - lo) % 2 == 0
+        ou = int(Tb['p5_o_off'][wp])
+        for st in range(lo, hi):
+            A = [s_str[((st * 2) * nsub + sub) * 4:((st * 2) * nsub + sub) * 4 + 4] for sub in range(nsub)]
+            B = [s_str[((st * 2 + 1) * nsub + sub) * 4:((st * 2 + 1) * nsub + sub) * 4 + 4] for sub in range(nsub)]
+            L = int(A[0][0]) >> 22
+            assert all(int(a_[0]) >> 22 == L for a_ in A)
+            for sub in range(nsub):
+                eidx, y = int(A[sub][0]) & 0x3FFFFF, int(A[sub][1])
+                pw_ = A[sub][2:4].copy().view(np.float64)[0]
+                accp = rawrow(int(B[sub][0])) + rawrow(int(B[sub][2]))
+                accm = rawrow(int(B[sub][1])) + rawrow(int(B[sub][3]))
+                for i in range(max(L - 2, 0)):
+                    accp = accp + rawrow(int(o_str[((ou + i) * nsub + sub) * 2]))
+                    accm = accm + rawrow(int(o_str[((ou + i) * nsub + sub) * 2 + 1]))
                 if eidx == NULL_E:
-                    assert not E0.any()
+                    assert not accp.any() and not accm.any()
                     continue
-                assert eidx == col * nsp and np.isnan(jac[:, eidx]).all()
-                pj, qj = colfac[col]
-                jac[:, eidx] = pj * (-wt * HA) + qj * (-wt * HB) + pj * (-wt) * E0 \
-                    + XT * (cp[:, col - 1] - cp[:, last])
-            u += L2
+                put(eidx, y, pw_ * (accp - accm))
+            ou += max(L - 2, 0)
+        assert ou == Tb['p5_o_off'][wp + 1]
+        # class T: energy-equation row, one column per item, list split over the sub-groups
+        u = int(Tb['p5_t_off'][wp])
+        for _ in range(int(Tb['p5_t_n'][wp])):
+            eidx, w1 = int(t_str[u * nsub * 2]), int(t_str[u * nsub * 2 + 1])
+            nun, col = w1 & 0xFFFF, w1 >> 16
+            assert nun % 2 == 0
+            u += 1
+            E0 = np.zeros(n)
+            for i in range(nun):
+                for sub in range(nsub):
+                    ro, xo = int(t_str[((u + i) * nsub + sub) * 2]), int(t_str[((u + i) * nsub + sub) * 2 + 1])
+                    assert xo % RXB == 0
+                    E0 += RHz[xo // RXB] * rawrow(ro)
+            u += nun
+            assert eidx == col * nsp and np.isnan(jac[:, eidx]).all()
+            pj, qj = colfac[col]
+            jac[:, eidx] = pj * (-wt * HA) + qj * (-wt * HB) + pj * (-wt) * E0 \
+                + XT * (cp[:, col - 1] - cp[:, last])
         assert u == Tb['p5_t_off'][wp + 1]
     s0 = -wdcp / cp_avg * H1 + SCP + HT * rho
     jac[:, 0] = -s0 / (rho * cp_avg)

@@ -43,6 +43,8 @@ def main():
     body = [r for r in rows[start + 2:] if r and r[0] != 'Kernel Name']
     base = int(body[0][0], 16)
     agg = defaultdict(lambda: [0.0, 0.0, 0.0, 0.0, 0.0])
+    stalls = defaultdict(lambda: defaultdict(float))
+    scols = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
     tot = [0.0, 0.0]
     prev = 'other'
     for r in body:
@@ -60,6 +62,8 @@ def main():
             name = prev
         prev = name
         a = agg[name]
+        for h in scols:
+            stalls[name][h] += float(r[ix[h]] or 0)
         a[0] += s; a[1] += ins; a[2] += thr
         op = sass.split()[0] if sass else ''
         if op.startswith('@'):
@@ -74,6 +78,10 @@ def main():
         print('%-14s %8.1f %8.1f %8.1f %8.1f %8.1f' % (nm, 100 * a[0] / tot[0], 100 * a[1] / tot[1],
               a[2] / max(a[1], 1), 100 * a[3] / max(a[1], 1), 100 * a[4] / max(a[1], 1)))
     print('total warp inst %.3e' % tot[1])
+    for nm, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        st = sorted(stalls[nm].items(), key=lambda kv: -kv[1])[:5]
+        tt = sum(stalls[nm].values()) or 1
+        print('%-10s' % nm, '  '.join('%s %.0f%%' % (k[6:], 100 * v / tt) for k, v in st))
 
 if __name__ == '__main__':
     main()
