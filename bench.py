@@ -9,7 +9,9 @@ DESIGN.md).  With N > 1 (launched by torchrun, one rank per GPU) every rank eval
 batch of the same size -- the state batch is partitioned, there is no data-path collective --
 and `value` is the states all ranks processed divided by the max-over-ranks device time.
 
-value        device-resident: states and Jacobians stay in HBM, CUDA events around K launches
+value        device-resident: states and Jacobians stay in HBM in the reference's GPU layout
+             (state-fastest / struct-of-arrays: y[NSP][n], jac[NSP*NSP][n], mech_auxiliary.py:418-420),
+             CUDA events around K launches
 e2e          the same metric through the host-pointer C-ABI call (pyjac_eval_jacob_host) with
              pinned HOST buffers: H2D of the states and D2H of every Jacobian inside the timing
 roofline     HBM bound; algorithmic bytes = 8*NSP^2 + 8*(NSP+1) per state
@@ -224,12 +226,13 @@ def run_ours(args, rank, world, local_rank):
     # every rank gets its own shard of the (n * world)-state batch: seed = rank
     P_h, y_h = load_states(nsp, n, seed=rank)
     P = torch.tensor(P_h, device=dev)
-    y = torch.tensor(y_h, device=dev)
-    jac = torch.empty((n, nsp * nsp), dtype=torch.float64, device=dev)
+    y = torch.tensor(y_h, device=dev).t().contiguous()              # [NSP][n], state-fastest
+    jac = torch.empty((nsp * nsp, n), dtype=torch.float64, device=dev)
+    SF = dict(y_layout='state_fastest', jac_layout='state_fastest')
 
     # ---- device-resident timing -------------------------------------------------------
     for _ in range(args.warmup):
-        ev.eval_jacob(P, y, jac)
+        ev.eval_jacob(P, y, jac, **SF)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if sampler:
@@ -241,7 +244,7 @@ def run_ours(args, rank, world, local_rank):
     w0 = time.time()
     e0.record()
     for _ in range(args.steps):
-        ev.eval_jacob(P, y, jac)
+        ev.eval_jacob(P, y, jac, **SF)
     e1.record()
     barrier()
     w1 = time.time()
@@ -283,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
         # spot-check that the host path delivered the same Jacobians as the device path
         if n_e == n:
             k = min(n, 64)
-            assert np.array_equal(j_np[:k], jac[:k].cpu().numpy()), 'host / device API mismatch'
+            assert np.array_equal(j_np[:k], jac[:, :k].t().cpu().numpy()), 'host / device API mismatch'
         e2e = {'value': n_e * world * e_steps / dt, 'unit': UNIT,
                'h2d_bytes_per_step': n_e * (nsp + 1) * 8, 'd2h_bytes_per_step': n_e * nsp * nsp * 8,
                'states_per_step': n_e, 'steps': e_steps,
@@ -308,12 +311,15 @@ def run_ours(args, rank, world, local_rank):
                        'jacobian_bytes_per_gpu': n * nsp * nsp * 8,
                        'l2': 'inputs (%.0f MB) and outputs (%.1f GB) per step exceed the 126 MB L2'
                              % (n * (nsp + 1) * 8 / 1e6, n * nsp * nsp * 8 / 1e9),
-                       'layout': 'row per state in, one column-major NSPxNSP Jacobian per state out',
+                       'layout': 'state-fastest (struct-of-arrays) in and out: y[NSP][n], jac[NSP*NSP][n] -- the '
+                                 "reference's GPU layout; e2e: one row per state in, one column-major "
+                                 'NSPxNSP Jacobian per state out (the scalar API layout)',
+                       'plan': 'gs=%d states per block, %d threads' % (ev.plan_gs, ev.plan_threads),
                        'parallelism': 'state batch sharded over %d GPU(s), no collective' % world},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': None if traffic is None else traffic * n,
                          'peak_source': peak_src, 'bytes_per_state': bytes_per_state,
-                         'kernel': 'pj::k_eval<G, M_JAC, MINB>', 'kernel_ms': kernel_ms},
+                         'kernel': 'pj5::k_jacobian<GS>', 'kernel_ms': kernel_ms},
             'e2e': e2e, 'cpu_baseline': cpu, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)

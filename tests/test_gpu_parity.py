@@ -134,3 +134,82 @@ def test_host_batch_api(torch, golden_dir):
     dev = ev.eval_jacob(torch.tensor(g['P'], device='cuda'), torch.tensor(g['y'], device='cuda'))
     assert np.array_equal(dev.cpu().numpy(), jac)
     ev.close()
+
+
+def test_pyjacob_wrappers_vs_reference_golden(torch, golden_dir, tmp_path):
+    """The reference's Python surface (pyjacob / cu_pyjacob function names and calling
+    conventions, pyjacob_wrapper.pyx:18-55, pyjacob_cuda_wrapper.pyx:13-34) on the PaSR states,
+    through create_jacobian -> generate_library -> generate_wrapper."""
+    from pyjac_b200 import libgen
+    from pyjac_b200.create_jacobian import create_jacobian
+    from pyjac_b200.pywrap import generate_wrapper
+    out = str(tmp_path / 'out')
+    mech = create_jacobian('cuda', os.path.join(golden_dir, 'h2o2_n2.inp'), build_path=out)
+    libgen.generate_library('cuda', out)
+    mod = generate_wrapper('cuda', out)
+    g = dict(np.load(os.path.join(golden_dir, 'h2o2_pasr.npz')))
+    nsp, nr, nrev, npd = mech.NSP, mech.FWD_RATES, mech.REV_RATES, mech.PRES_MOD_RATES
+
+    # scalar API, a few states (each call is a batch of one on the GPU)
+    pick = [0, 17, 511, 1019]
+    new = {k: np.zeros((len(pick), w)) for k, w in
+           (('conc', nsp), ('fwd', nr), ('rev', nrev), ('pres_mod', npd), ('spec_rates', nsp), ('dydt', nsp))}
+    jac = np.zeros((len(pick), nsp * nsp))
+    for r, s in enumerate(pick):
+        y, P = np.ascontiguousarray(g['y'][s]), float(g['P'][s])
+        mf = np.zeros(nsp)
+        mf[:nsp - 1] = y[1:]
+        mod.py_eval_conc(y[0], P, mf, 0.0, 0.0, new['conc'][r])
+        assert abs(mf[-1] - (1.0 - y[1:].sum())) < 1e-15
+        mod.py_eval_rxn_rates(y[0], P, new['conc'][r], new['fwd'][r], new['rev'][r])
+        mod.py_get_rxn_pres_mod(y[0], P, new['conc'][r], new['pres_mod'][r])
+        mod.py_eval_spec_rates(new['fwd'][r], new['rev'][r], new['pres_mod'][r], new['spec_rates'][r])
+        mod.py_dydt(0.0, P, y, new['dydt'][r])
+        mod.py_eval_jacobian(0.0, P, y, jac[r])
+    sub = {k: v[pick] for k, v in g.items()}
+    gates.check_rates(mech, sub['P'], sub['y'], new, sub, 'pyjacob scalar API')
+    gates.check_jac(jac, sub['jac'], nsp, 'pyjacob scalar API', mech, sub['y'])
+
+    # batched host API: Fortran-order (state-fastest) flat arrays
+    num = g['y'].shape[0]
+    padded = mod.py_cuinit(num)
+    assert padded >= num
+    flat = lambda a: np.ascontiguousarray(a.T).ravel()
+    outs = {k: np.zeros(num * w) for k, w in
+            (('conc', nsp), ('fwd', nr), ('rev', nrev), ('pres_mod', npd), ('spec_rates', nsp), ('dydt', nsp),
+             ('jac', nsp * nsp))}
+    mod.py_cujac(num, padded, np.ascontiguousarray(g['P']), flat(g['y']), outs['conc'], outs['fwd'], outs['rev'],
+                 outs['pres_mod'], outs['spec_rates'], outs['dydt'], outs['jac'])
+    mod.py_cuclean()
+    back = {k: v.reshape(-1, num).T for k, v in outs.items()}
+    gates.check_rates(mech, g['P'], g['y'], back, g, 'cu_pyjacob')
+    worst, frac = gates.check_jac(np.ascontiguousarray(back['jac']), g['jac'], nsp, 'cu_pyjacob', mech, g['y'])
+    assert frac > 0.97
+    mod.close()
+
+
+def test_full_size_properties(torch, golden_dir):
+    """BASELINE size (2^20 states, GRI-shaped): properties that need no oracle.  The batch is a
+    small seeded set tiled many times, so every replica must equal the first one bitwise, and
+    the first one is checked against the oracle."""
+    from oracle.oracle import Oracle
+    mech, ev = _evaluator(golden_dir, 'gri30_syn.inp')
+    base, reps = 1024, 1024
+    P_h, y_h = synthetic_states(mech.NSP, base, seed=21)
+    P = torch.tensor(P_h, device='cuda').repeat(reps)
+    y = torch.tensor(y_h, device='cuda').t().contiguous().repeat(1, reps)      # [NSP][n]
+    n = base * reps
+    jac = torch.empty((mech.NSP ** 2, n), dtype=torch.float64, device='cuda')
+    ev.eval_jacob(P, y, jac, y_layout='state_fastest', jac_layout='state_fastest')
+    torch.cuda.synchronize()
+    first = jac[:, :base]
+    assert torch.isfinite(first).all()
+    for r in (1, 2, 513, reps - 1):
+        assert torch.equal(jac[:, r * base:(r + 1) * base], first), r
+    assert torch.equal(jac.view(mech.NSP ** 2, reps, base).amax(dim=1), first)
+    assert torch.equal(jac.view(mech.NSP ** 2, reps, base).amin(dim=1), first)
+    ref = Oracle(mech).eval_jacob(P_h, y_h)
+    worst, frac = gates.check_jac(np.ascontiguousarray(first.t().cpu().numpy()), ref, mech.NSP,
+                                  'full size, first replica', mech, y_h)
+    assert frac > 0.999
+    ev.close()

@@ -1,0 +1,73 @@
+"""create_jacobian / generate_library / generate_wrapper keep the reference's pipeline shape:
+the build directory holds a mechanism.h that the reference's own regex consumers can read
+(functional_tester/test.py:311-318,358; libgen/libgen.py:385) plus the table blob."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pyjac_b200 import blob, libgen
+from pyjac_b200.create_jacobian import create_jacobian, load_tables
+
+
+def test_create_jacobian_writes_header_and_tables(golden_dir, tmp_path):
+    out = str(tmp_path / 'out')
+    mech = create_jacobian('cuda', os.path.join(golden_dir, 'h2o2_n2.inp'), build_path=out)
+    lines = open(os.path.join(out, 'mechanism.h')).read().splitlines()
+    found = {}
+    for line in lines:
+        for key in ('NSP', 'NN', 'FWD_RATES', 'REV_RATES'):
+            m = re.search(r'^#define %s (\d+)$' % key, line)
+            if m:
+                found[key] = int(m.group(1))
+        m = re.search(r'\s*#define PRES_MOD_RATES (\d+)', line.strip())
+        if m:
+            found['PRES_MOD_RATES'] = int(m.group(1))
+        m = re.search(r'^//last_spec (\d+)$', line)
+        if m:
+            found['last_spec'] = int(m.group(1))
+    assert found == {'NSP': 10, 'NN': 11, 'FWD_RATES': 28, 'REV_RATES': 28, 'PRES_MOD_RATES': 6,
+                     'last_spec': mech.last_spec_original}
+    T = blob.unpack(load_tables(out))
+    assert int(T['dims'][0]) == 10 and 'p5_cfg' in T
+    # the library stage hands back the one fixed sm_100a library
+    assert libgen.generate_library('cuda', out) == libgen.build_library()
+
+
+def test_create_jacobian_rejects_what_it_cannot_do(golden_dir, tmp_path):
+    mech = os.path.join(golden_dir, 'h2o2_n2.inp')
+    with pytest.raises(ValueError):
+        create_jacobian('c', mech, build_path=str(tmp_path))          # no CPU back end
+    with pytest.raises(NotImplementedError):
+        create_jacobian('cuda', mech, build_path=str(tmp_path), auto_diff=True)
+    with pytest.raises(FileNotFoundError):
+        libgen.generate_library('cuda', str(tmp_path / 'nothing'))
+
+
+def test_plan_tables_are_consistent(golden_dir, tmp_path):
+    """Every species, reaction and Jacobian element is scheduled exactly once for several
+    (states per block, block size) choices."""
+    from pyjac_b200 import tables
+    from pyjac_b200.mechanism import Mechanism
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, 'gri30_syn.inp'))
+    for gs, nt in ((8, 512), (4, 256), (2, 128), (8, 64), (32, 512)):
+        if gs == 32:
+            mech_ = Mechanism.from_chemkin(os.path.join(golden_dir, 'h2o2_n2.inp'))
+        else:
+            mech_ = mech
+        T = tables.build(mech_, gs=gs, threads=nt)
+        nsp, nr = int(T['dims'][0]), int(T['dims'][1])
+        nw, nsub = nt // 32, 64 // gs
+        items = T['p5_b_item'][:int(T['p5_b_off'][nw]) * nsub]
+        assert sorted(items[items >= 0]) == list(range(nr))
+        c_item = T['p5_c_item'].reshape(-1, 4)[:int(T['p5_c_off'][nw])]
+        assert sorted(c_item[:, 0] // (gs * 8 * 8)) == list(range(nsp))
+        d = T['p5_d_str'].view(np.uint32).reshape(-1, 2)[:int(T['p5_d_off'][nw]) * nsub, 0]
+        s = T['p5_s_str'].view(np.uint32).reshape(-1, nsub, 4)[:int(T['p5_s_off'][nw]) * 2][0::2, :, 0].ravel() & 0x3FFFFF
+        t = T['p5_t_str'].view(np.uint32)
+        elems = sorted([int(e) for e in d if e != 0x3FFFFF] + [int(e) for e in s if e != 0x3FFFFF])
+        want = sorted(c * nsp + r for c in range(nsp) for r in range(1, nsp))
+        assert elems == want
+        assert int(T['p5_cfg'][9]) * 8 <= 232448
+        assert int(T['p5_t_n'].sum()) == nsp - 1 and len(t) > 0
