@@ -37,19 +37,21 @@ namespace pj5 {
 using namespace pj;
 
 struct Plan {
-    int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync;
+    int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync, coop, tcoop;
     const int4* rx;
     const int *b_off, *b_npm, *b_item;
     const int* c_off;
     const int4* c_item;
     const uint2* c_str;
     const int* d_off;
+    const int2* d_item;
     const uint2* d_str;
     const int* s_off;
     const uint4* s_str;
     const int* o_off;
     const uint2* o_str;
-    const int *t_off, *t_n;
+    const int* t_off;
+    const int2* t_item;
     const uint2* t_str;
     const double2* colfac;
 };
@@ -58,7 +60,12 @@ struct Plan {
 enum : int { Q_T = 0, Q_LOGT, Q_IT, Q_RHO, Q_RHOINV, Q_NMWR, Q_MWR, Q_M };
 enum : int { S_NWT = 0, S_A0, S_B0, S_XT, S_CPL, NQ = 24 };
 enum : int { D_H1 = 0, D_HA, D_HB, D_HT, D_SCP, D_CPAVG, D_WDCP, NPART = 7 };
-enum : int { SP_C = 0, SP_B, SP_DB, SP_HW, SP_WA, SP_WB, SP_WT, SP_CP, SP_SLOTS, SP_Y = SP_C };
+// A species owns SP_SLOTS rows.  Even slots (C, dB, WA, WT) are read at E + {0, 2, 4, 6} rows, odd
+// slots (B, hW, WB, cp) at O + {0, 2, 4, 6} rows, where E = region + k * SPB + (k & 1) * RB is the
+// species' even-slot base and O = E ^ RB: the slot pair of odd species is swapped, so that the
+// rows of different species, which all sit at the same offset of a 128-byte bank line otherwise,
+// spread over both halves of the banks.
+enum : int { SP_SLOTS = 8, E_C = 0, E_DB = 2, E_WA = 4, E_WT = 6, O_B = 0, O_HW = 2, O_WB = 4, O_CP = 6, E_Y = E_C };
 enum : int { RX_NET = 0, RX_TT, RX_X1, RX_X2, RX_DH, RX_SLOTS };
 enum : unsigned { NULL_E = 0x3FFFFFu };
 enum : int { F_HAS_LAST = 1 << 13 };    // some occupied slot of the reaction holds the last species
@@ -125,6 +132,8 @@ __device__ __forceinline__ V vmul(double a, V b) { return V{a * b.x, a * b.y}; }
 __device__ __forceinline__ V vmul(V a, V b) { return V{a.x * b.x, a.y * b.y}; }
 __device__ __forceinline__ V vexp(V a) { return V{exp_fast(a.x), exp_fast(a.y)}; }
 __device__ __forceinline__ V zero_v() { return V{0.0, 0.0}; }
+template <int GS>
+__device__ __forceinline__ unsigned sp_even(unsigned aSP, unsigned k) { return aSP + k * (SP_SLOTS * GS * 8) + (k & 1u) * (GS * 8); }
 
 // sum over the sub-groups of a warp (lanes with equal state pair); result in every lane
 template <int GS>
@@ -150,77 +159,123 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsig
     const double lnA = __hiloint2double(q0.y, q0.x), bexp = __hiloint2double(q0.w, q0.z);
     const double Ta = __hiloint2double(q1.y, q1.x), lnKc = __hiloint2double(q1.w, q1.z);
     const int fl = q2.x;
+    // species slots: (offset of the even-slot base) / 16; nsp_f / last_f: the same for the empty
+    // slot and the last species
     const unsigned s0 = q2.y & 0xFFFFu, s1 = (unsigned)q2.y >> 16, s2 = q2.z & 0xFFFFu;
     const unsigned s3 = (unsigned)q2.z >> 16, s4 = q2.w & 0xFFFFu, s5 = (unsigned)q2.w >> 16;
-    const unsigned a0 = aSP + s0 * SPB, a1 = aSP + s1 * SPB, a2 = aSP + s2 * SPB;
-    const unsigned a3 = aSP + s3 * SPB, a4 = aSP + s4 * SPB, a5 = aSP + s5 * SPB;
+    const unsigned a0 = aSP + s0 * 16, a1 = aSP + s1 * 16, a2 = aSP + s2 * 16;
+    const unsigned a3 = aSP + s3 * 16, a4 = aSP + s4 * 16, a5 = aSP + s5 * 16;
+    const unsigned nsp_f = (sp_even<GS>(0u, (unsigned)nsp)) / 16, last_f = (sp_even<GS>(0u, (unsigned)last)) / 16;
     const bool isrev = fl & F_REV;
 
-    // ---- pressure modification first: PM_, and for the Jacobian gg, Xd, e1Fi
+    // ---- species values and the arguments of kf, kr
+    const V c0 = lds<E_C * RB>(a0), c1 = lds<E_C * RB>(a1), c3 = lds<E_C * RB>(a3), c4 = lds<E_C * RB>(a4);
+    V c2{1.0, 1.0}, c5{1.0, 1.0};
+    V sB = vsub(vadd(lds<O_B * RB>(a3 ^ RB), lds<O_B * RB>(a4 ^ RB)), vadd(lds<O_B * RB>(a0 ^ RB), lds<O_B * RB>(a1 ^ RB)));
+    V sdB = vsub(vadd(lds<E_DB * RB>(a3), lds<E_DB * RB>(a4)), vadd(lds<E_DB * RB>(a0), lds<E_DB * RB>(a1)));
+    V dH = vsub(vadd(lds<O_HW * RB>(a3 ^ RB), lds<O_HW * RB>(a4 ^ RB)), vadd(lds<O_HW * RB>(a0 ^ RB), lds<O_HW * RB>(a1 ^ RB)));
+    if (three) {
+        c2 = lds<E_C * RB>(a2);
+        c5 = lds<E_C * RB>(a5);
+        sB = vadd(sB, vsub(lds<O_B * RB>(a5 ^ RB), lds<O_B * RB>(a2 ^ RB)));
+        sdB = vadd(sdB, vsub(lds<E_DB * RB>(a5), lds<E_DB * RB>(a2)));
+        dH = vadd(dH, vsub(lds<O_HW * RB>(a5 ^ RB), lds<O_HW * RB>(a2 ^ RB)));
+    }
+    const V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
+    const V lnkr{lnkf.x - sB.x - lnKc, lnkf.y - sB.y - lnKc};
+    V kf, kr;
+
+    // ---- pressure modification: PM_, and for the Jacobian gg, Xd, e1Fi.  All exponentials of a
+    // reaction are evaluated in two batches (exp_n) so that the lane's two states and the
+    // independent terms overlap.
     V PM_{1.0, 1.0}, gg{1.0, 1.0}, Xd{0.0, 0.0}, e1Fi{0.0, 0.0};
     const int mi = PM ? p - tb.first_pm : 0;
     const double* par = tb.pm_par + mi * NPAR;
+    bool rates_done = false;
     if (PM) {
         V thd = lds<Q_M * RB>(aSC);
         const int e0 = __ldg(tb.pm_eff_off + mi), e1_ = __ldg(tb.pm_eff_off + mi + 1);
         for (int e = e0; e < e1_; ++e)
-            thd = vfma(__ldg(tb.pm_eff_am1 + e), lds<SP_C * RB>(aSP + __ldg(tb.pm_eff_sp + e) * SPB), thd);
+            thd = vfma(__ldg(tb.pm_eff_am1 + e), lds<E_C * RB>(sp_even<GS>(aSP, (unsigned)__ldg(tb.pm_eff_sp + e))), thd);
         if (fl & F_PDEP) {
             const int csp = __ldg(tb.pm_sp + mi);
-            const V ctv = csp >= 0 ? lds<SP_C * RB>(aSP + csp * SPB) : thd;
+            const V ctv = csp >= 0 ? lds<E_C * RB>(sp_even<GS>(aSP, (unsigned)csp)) : thd;
             const bool low = fl & F_LOW;
             const double p0 = par[0], p1 = par[1], p2 = par[2], p3 = par[3];
             const double ct[2] = {ctv.x, ctv.y}, Tt[2] = {T.x, T.y}, lT[2] = {logT.x, logT.y}, rT[2] = {iT.x, iT.y};
             double Pr[2], i1p[2], F[2], dpr[2], xd[2], g_[2], e1f[2];
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const double e1 = exp_fast(p0 + p1 * lT[g] - p2 * rT[g]);
-                Pr[g] = ct[g] * e1;
-                const double dpr4 = p3 + p2 * rT[g] - 1.0;
-                dpr[g] = p1 + p2 * rT[g] - 1.0;
-                i1p[g] = 1.0 / (1.0 + Pr[g]);
-                if (low) { xd[g] = dpr4 * rT[g] * i1p[g]; g_[g] = i1p[g]; }
-                else { xd[g] = -Pr[g] * dpr4 * rT[g] * i1p[g]; g_[g] = -Pr[g] * i1p[g]; }
-                F[g] = 1.0;
-                e1f[g] = e1;
-            }
             if (fl & F_TROE) {
+                // batch 1: the Pr exponential and the three Troe exponentials (par[28], par[29] =
+                // 1 / par[7], 1 / par[9]); a missing T2 term is masked out
+                const double m2 = (fl & F_TROE_T2) ? 1.0 : 0.0;
+                const double x1[8] = {p0 + p1 * lT[0] - p2 * rT[0], p0 + p1 * lT[1] - p2 * rT[1],
+                                      Tt[0] * par[28], Tt[1] * par[28], Tt[0] * par[29], Tt[1] * par[29],
+                                      m2 * par[10] * rT[0], m2 * par[10] * rT[1]};
+                double y1[8];
+                exp_n<8>(x1, y1);
                 const double iln10 = 0.43429448190325182765;
+                double fa[2];
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    const double e3 = exp_fast(Tt[g] / par[7]), e1t = exp_fast(Tt[g] / par[9]);
-                    double Fc = par[6] * e3 + par[8] * e1t;
-                    double dF = par[11] * e3 - par[12] * e1t;
-                    if (fl & F_TROE_T2) {
-                        const double e2 = exp_fast(par[10] * rT[g]);
-                        Fc += e2;
-                        dF += par[13] * rT[g] * rT[g] * e2;
-                    }
+                    const double e1 = y1[g], e3 = y1[2 + g], e1t = y1[4 + g], e2 = m2 * y1[6 + g];
+                    Pr[g] = ct[g] * e1;
+                    const double dpr4 = p3 + p2 * rT[g] - 1.0;
+                    dpr[g] = p1 + p2 * rT[g] - 1.0;
+                    i1p[g] = __drcp_rn(1.0 + Pr[g]);
+                    if (low) { xd[g] = dpr4 * rT[g] * i1p[g]; g_[g] = i1p[g]; }
+                    else { xd[g] = -Pr[g] * dpr4 * rT[g] * i1p[g]; g_[g] = -Pr[g] * i1p[g]; }
+                    e1f[g] = e1;
+                    const double Fc = par[6] * e3 + par[8] * e1t + e2;
+                    const double dF = par[11] * e3 - par[12] * e1t + par[13] * rT[g] * rT[g] * e2;
                     const double lnFc = log(fmax(Fc, 1.0e-300));
-                    const double lF = lnFc * iln10, lP = log10_clamped(Pr[g]);
+                    const double lF = lnFc * iln10, lP = log(fmax(Pr[g], 1.0e-300)) * iln10;
                     const double A = lP - 0.67 * lF - 0.4;
                     const double Bq = 0.806 - 1.1762 * lF - 0.14 * lP;
-                    const double q1_ = 1.0 + A * A / (Bq * Bq);
-                    const double lnF_AB = 2.0 * lnFc * A / (Bq * Bq * Bq * q1_ * q1_);
-                    F[g] = exp_fast(lnFc / q1_);
-                    xd[g] += (1.0 / (Fc * q1_) - lnF_AB * (-0.67 * iln10 * Bq + 1.1762 * iln10 * A) / Fc) * dF
+                    const double rB = __drcp_rn(Bq), rFc = __drcp_rn(Fc);
+                    const double t = A * rB;
+                    const double rq = __drcp_rn(fma(t, t, 1.0));
+                    const double lnF_AB = 2.0 * lnFc * t * (rB * rq) * (rB * rq);
+                    fa[g] = lnFc * rq;
+                    xd[g] += (rFc * rq - lnF_AB * (-0.67 * iln10 * Bq + 1.1762 * iln10 * A) * rFc) * dF
                              - lnF_AB * (Bq * iln10 + 0.14 * iln10 * A) * dpr[g] * rT[g];
                     g_[g] -= lnF_AB * (Bq * iln10 + A * 0.14 * iln10);
                 }
-            } else if (fl & F_SRI) {
+                // batch 2: the broadening factor F and the two rate constants
+                const double x2[6] = {fa[0], fa[1], lnkf.x, lnkf.y, lnkr.x, lnkr.y};
+                double y2[6];
+                exp_n<6>(x2, y2);
+                F[0] = y2[0]; F[1] = y2[1];
+                kf = V{y2[2], y2[3]};
+                kr = V{y2[4], y2[5]};
+                rates_done = true;
+            } else {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    const double lP = log10_clamped(Pr[g]);
-                    const double X = 1.0 / (1.0 + lP * lP);
-                    F[g] = pow(par[14] * exp(-par[15] * rT[g]) + exp(-Tt[g] / par[16]), X);
-                    if (fl & F_SRI5) F[g] *= par[17] * pow(Tt[g], par[18]);
-                    const double two_iln10 = 0.86858896380650365530;
-                    const double eb = exp(par[23] * rT[g]), ec = exp(Tt[g] / par[25]);
-                    const double den = par[26] * eb + ec;
-                    xd[g] += X * ((par[22] * rT[g] * rT[g] * eb - par[24] * ec) / den
-                                  - X * two_iln10 * lP * dpr[g] * log(den) * rT[g]);
-                    if (fl & F_SRI5_DT) xd[g] += par[27] * rT[g];
-                    g_[g] -= X * X * two_iln10 * lP * log(par[19] * exp(par[20] * rT[g]) + exp(Tt[g] / par[21]));
+                    const double e1 = exp_fast(p0 + p1 * lT[g] - p2 * rT[g]);
+                    Pr[g] = ct[g] * e1;
+                    const double dpr4 = p3 + p2 * rT[g] - 1.0;
+                    dpr[g] = p1 + p2 * rT[g] - 1.0;
+                    i1p[g] = 1.0 / (1.0 + Pr[g]);
+                    if (low) { xd[g] = dpr4 * rT[g] * i1p[g]; g_[g] = i1p[g]; }
+                    else { xd[g] = -Pr[g] * dpr4 * rT[g] * i1p[g]; g_[g] = -Pr[g] * i1p[g]; }
+                    F[g] = 1.0;
+                    e1f[g] = e1;
+                }
+                if (fl & F_SRI) {
+#pragma unroll 1
+                    for (int g = 0; g < 2; ++g) {
+                        const double lP = log10_clamped(Pr[g]);
+                        const double X = 1.0 / (1.0 + lP * lP);
+                        F[g] = pow(par[14] * exp(-par[15] * rT[g]) + exp(-Tt[g] / par[16]), X);
+                        if (fl & F_SRI5) F[g] *= par[17] * pow(Tt[g], par[18]);
+                        const double two_iln10 = 0.86858896380650365530;
+                        const double eb = exp(par[23] * rT[g]), ec = exp(Tt[g] / par[25]);
+                        const double den = par[26] * eb + ec;
+                        xd[g] += X * ((par[22] * rT[g] * rT[g] * eb - par[24] * ec) / den
+                                      - X * two_iln10 * lP * dpr[g] * log(den) * rT[g]);
+                        if (fl & F_SRI5_DT) xd[g] += par[27] * rT[g];
+                        g_[g] -= X * X * two_iln10 * lP * log(par[19] * exp(par[20] * rT[g]) + exp(Tt[g] / par[21]));
+                    }
                 }
             }
             double pm_[2];
@@ -237,21 +292,13 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsig
     }
 
     // ---- rate constants and rates of progress
-    const V c0 = lds<SP_C * RB>(a0), c1 = lds<SP_C * RB>(a1), c3 = lds<SP_C * RB>(a3), c4 = lds<SP_C * RB>(a4);
-    V c2{1.0, 1.0}, c5{1.0, 1.0};
-    V sB = vsub(vadd(lds<SP_B * RB>(a3), lds<SP_B * RB>(a4)), vadd(lds<SP_B * RB>(a0), lds<SP_B * RB>(a1)));
-    V sdB = vsub(vadd(lds<SP_DB * RB>(a3), lds<SP_DB * RB>(a4)), vadd(lds<SP_DB * RB>(a0), lds<SP_DB * RB>(a1)));
-    V dH = vsub(vadd(lds<SP_HW * RB>(a3), lds<SP_HW * RB>(a4)), vadd(lds<SP_HW * RB>(a0), lds<SP_HW * RB>(a1)));
-    if (three) {
-        c2 = lds<SP_C * RB>(a2);
-        c5 = lds<SP_C * RB>(a5);
-        sB = vadd(sB, vsub(lds<SP_B * RB>(a5), lds<SP_B * RB>(a2)));
-        sdB = vadd(sdB, vsub(lds<SP_DB * RB>(a5), lds<SP_DB * RB>(a2)));
-        dH = vadd(dH, vsub(lds<SP_HW * RB>(a5), lds<SP_HW * RB>(a2)));
+    if (!rates_done) {
+        const double x2[4] = {lnkf.x, lnkf.y, lnkr.x, lnkr.y};
+        double y2[4];
+        exp_n<4>(x2, y2);
+        kf = V{y2[0], y2[1]};
+        kr = V{y2[2], y2[3]};
     }
-    const V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
-    const V kf = vexp(lnkf);
-    V kr = vexp(V{lnkf.x - sB.x - lnKc, lnkf.y - sB.y - lnKc});
     if (!isrev) kr = V{0.0, 0.0};
     V f = vmul(kf, vmul(c0, c1)), r = vmul(kr, vmul(c3, c4));
     if (three) { f = vmul(f, c2); r = vmul(r, c5); }
@@ -299,9 +346,9 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsig
 
     // ---- d(rate)/dC values: to their raw rows, or folded into X2 for the last species
 #define PJ_EMIT(SLOT, DST, EXPR)                                         \
-    if ((SLOT) != (unsigned)nsp) {                                       \
+    if ((SLOT) != nsp_f) {                                               \
         const V d_ = (EXPR);                                             \
-        if ((SLOT) == (unsigned)last) X2 = vsub(X2, d_);                 \
+        if ((SLOT) == last_f) X2 = vsub(X2, d_);                         \
         else if (valid) sts<0>(aRAW + (DST) * RB, d_);                   \
     }
     if (three) {
@@ -358,20 +405,20 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     const double Ta = __hiloint2double(q1.y, q1.x), lnKc = __hiloint2double(q1.w, q1.z);
     const int fl = q2.x;
     const unsigned s0 = q2.y & 0xFFFFu, s1 = (unsigned)q2.y >> 16, s3 = (unsigned)q2.z >> 16, s4 = q2.w & 0xFFFFu;
-    const unsigned a0 = aSP + s0 * SPB, a1 = aSP + s1 * SPB, a3 = aSP + s3 * SPB, a4 = aSP + s4 * SPB;
-    V c0 = lds<SP_C * RB>(a0), c1 = lds<SP_C * RB>(a1), c3 = lds<SP_C * RB>(a3), c4 = lds<SP_C * RB>(a4);
-    V sB = vsub(vadd(lds<SP_B * RB>(a3), lds<SP_B * RB>(a4)), vadd(lds<SP_B * RB>(a0), lds<SP_B * RB>(a1)));
-    V sdB = vsub(vadd(lds<SP_DB * RB>(a3), lds<SP_DB * RB>(a4)), vadd(lds<SP_DB * RB>(a0), lds<SP_DB * RB>(a1)));
-    V dH = vsub(vadd(lds<SP_HW * RB>(a3), lds<SP_HW * RB>(a4)), vadd(lds<SP_HW * RB>(a0), lds<SP_HW * RB>(a1)));
+    const unsigned a0 = aSP + s0 * 16, a1 = aSP + s1 * 16, a3 = aSP + s3 * 16, a4 = aSP + s4 * 16;
+    V c0 = lds<E_C * RB>(a0), c1 = lds<E_C * RB>(a1), c3 = lds<E_C * RB>(a3), c4 = lds<E_C * RB>(a4);
+    V sB = vsub(vadd(lds<O_B * RB>(a3 ^ RB), lds<O_B * RB>(a4 ^ RB)), vadd(lds<O_B * RB>(a0 ^ RB), lds<O_B * RB>(a1 ^ RB)));
+    V sdB = vsub(vadd(lds<E_DB * RB>(a3), lds<E_DB * RB>(a4)), vadd(lds<E_DB * RB>(a0), lds<E_DB * RB>(a1)));
+    V dH = vsub(vadd(lds<O_HW * RB>(a3 ^ RB), lds<O_HW * RB>(a4 ^ RB)), vadd(lds<O_HW * RB>(a0 ^ RB), lds<O_HW * RB>(a1 ^ RB)));
     V c2{1.0, 1.0}, c5{1.0, 1.0};
     const unsigned s2 = q2.z & 0xFFFFu, s5 = (unsigned)q2.w >> 16;
     if (three) {
-        const unsigned a2 = aSP + s2 * SPB, a5 = aSP + s5 * SPB;
-        c2 = lds<SP_C * RB>(a2);
-        c5 = lds<SP_C * RB>(a5);
-        sB = vadd(sB, vsub(lds<SP_B * RB>(a5), lds<SP_B * RB>(a2)));
-        sdB = vadd(sdB, vsub(lds<SP_DB * RB>(a5), lds<SP_DB * RB>(a2)));
-        dH = vadd(dH, vsub(lds<SP_HW * RB>(a5), lds<SP_HW * RB>(a2)));
+        const unsigned a2 = aSP + s2 * 16, a5 = aSP + s5 * 16;
+        c2 = lds<E_C * RB>(a2);
+        c5 = lds<E_C * RB>(a5);
+        sB = vadd(sB, vsub(lds<O_B * RB>(a5 ^ RB), lds<O_B * RB>(a2 ^ RB)));
+        sdB = vadd(sdB, vsub(lds<E_DB * RB>(a5), lds<E_DB * RB>(a2)));
+        dH = vadd(dH, vsub(lds<O_HW * RB>(a5 ^ RB), lds<O_HW * RB>(a2 ^ RB)));
     }
     const V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
     const double ex[4] = {lnkf.x, lnkf.y, lnkf.x - sB.x - lnKc, lnkf.y - sB.y - lnKc};
@@ -402,7 +449,7 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     if (three) { d2 = vmul(kf, o2); n5 = vmul(kr, o5); n5 = V{-n5.x, -n5.y}; }
     if (fl & F_HAS_LAST) {
         // a slot holding the last species has no column: its derivative joins the W_j / W_N term
-        const unsigned last = tb.nsp - 1;
+        const unsigned last = sp_even<GS>(0u, (unsigned)(tb.nsp - 1)) / 16;
         if (s0 == last) X2 = vsub(X2, d0);
         if (s1 == last) X2 = vsub(X2, d1);
         if (s2 == last) X2 = vsub(X2, d2);
@@ -427,8 +474,8 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     sts_if<RX_DH * RB>(valid, ar, dH);
 }
 
-template <int GS>
-__global__ void __launch_bounds__(512, 1)
+template <int GS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const __grid_constant__ IO io)
 {
     extern __shared__ __align__(16) double smem[];
@@ -442,6 +489,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
     const int nsp = tb.nsp, last = tb.nsp - 1;
     // 32-bit shared addresses of this lane's state pair in each region
     const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + pr * 16;
+    if (((unsigned)__cvta_generic_to_shared(smem) + pl.oSP * 8) & (2 * RB - 1)) __trap();   // E ^ RB needs this
     const unsigned aSP = sb + pl.oSP * 8, aRX = sb + pl.oRX * 8, aRAW = sb + pl.oRAW * 8;
     const unsigned aSC0 = sb + pl.oSC * 8, aPA = sb + pl.oPA * 8;
     const unsigned aSD = aSC0 + 2 * SCB;   // scalars derived in phase DE
@@ -449,10 +497,10 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
 
     // rows that never change: the empty reaction slot, the zero reaction, the zero raw row
     if (warp == 0 && sub == 0) {
-        const unsigned a = aSP + nsp * SPB;
-        sts<SP_C * RB>(a, V{1.0, 1.0});
-        sts<SP_B * RB>(a, zero); sts<SP_DB * RB>(a, zero); sts<SP_HW * RB>(a, zero);
-        sts<SP_WA * RB>(a, zero); sts<SP_WB * RB>(a, zero); sts<SP_WT * RB>(a, zero); sts<SP_CP * RB>(a, zero);
+        const unsigned a = sp_even<GS>(aSP, (unsigned)nsp), o = a ^ RB;
+        sts<E_C * RB>(a, V{1.0, 1.0});
+        sts<O_B * RB>(o, zero); sts<E_DB * RB>(a, zero); sts<O_HW * RB>(o, zero);
+        sts<E_WA * RB>(a, zero); sts<O_WB * RB>(o, zero); sts<E_WT * RB>(a, zero); sts<O_CP * RB>(o, zero);
         const unsigned ar = aRX + tb.nr * RXB;
         sts<RX_NET * RB>(ar, zero); sts<RX_TT * RB>(ar, zero); sts<RX_X1 * RB>(ar, zero);
         sts<RX_X2 * RB>(ar, zero); sts<RX_DH * RB>(ar, zero);
@@ -478,7 +526,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
         V sumY = zero, sumYW = zero;
         for (int k = sub; k < last; k += NSUB) {
             const V Yk{y0[(long long)(k + 1) * io.y_sv], y1[(long long)(k + 1) * io.y_sv]};
-            sts<SP_Y * RB>(aSP + k * SPB, Yk);
+            sts<E_Y * RB>(sp_even<GS>(aSP, (unsigned)k), Yk);
             sumY = vadd(sumY, Yk);
             sumYW = vfma(__ldg(tb.sp_iw + k), Yk, sumYW);
         }
@@ -501,7 +549,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 o[Q_M][g2] = P[g2] / (tb.ru * T[g2]);
             }
             const unsigned a = aSC0 + b * SCB;
-            sts<SP_Y * RB>(aSP + last * SPB, V{yN[0], yN[1]});
+            sts<E_Y * RB>(sp_even<GS>(aSP, (unsigned)last), V{yN[0], yN[1]});
             sts<Q_T * RB>(a, V{o[Q_T][0], o[Q_T][1]});
             sts<Q_LOGT * RB>(a, V{o[Q_LOGT][0], o[Q_LOGT][1]});
             sts<Q_IT * RB>(a, V{o[Q_IT][0], o[Q_IT][1]});
@@ -516,33 +564,36 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
     if (warp == 0 && (long long)blockIdx.x < ngroups) phase_a0(blockIdx.x, 0);
     __syncthreads();
 
+    long long clk[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define PJ_TICK(i) { const long long tn_ = clock64(); clk[i] += tn_ - tprev; tprev = tn_; }
     int buf = 0;
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, buf ^= 1) {
         const long long s0 = grp * GS + 2 * pr;           // first state of this lane
         const bool ok0 = s0 < io.n, ok1 = s0 + 1 < io.n;
         char* const out0 = reinterpret_cast<char*>(sf ? io.jac + s0 : io.jac + s0 * nn);
         const unsigned aSC = aSC0 + buf * SCB;
+        // fast: both states of the lane in range and 16-byte stores possible (all but tail groups)
+        const bool fast = vec_ok && ok1;
         auto store = [&](unsigned e, V v, bool on) {
             char* o = out0 + (unsigned long long)e * ld8;
-            if (vec_ok) {
-                if (on && ok1) *reinterpret_cast<double2*>(o) = make_double2(v.x, v.y);
-                else if (on && ok0) *reinterpret_cast<double*>(o) = v.x;
+            if (fast) {
+                asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q st.global.v2.f64 [%0], {%1, %2};\n\t}"
+                             ::"l"(o), "d"(v.x), "d"(v.y), "r"((int)on) : "memory");
             } else {
                 if (on && ok0) *reinterpret_cast<double*>(o) = v.x;
                 if (on && ok1) *reinterpret_cast<double*>(o + second) = v.y;
             }
         };
 
-        const V T = lds<Q_T * RB>(aSC), logT = lds<Q_LOGT * RB>(aSC), iT = lds<Q_IT * RB>(aSC);
-
         // ------------------------------------------------------------ phase A1: species thermo
-        {
+        if (!(io.dbg_skip & 1)) {
+            const V T = lds<Q_T * RB>(aSC), logT = lds<Q_LOGT * RB>(aSC), iT = lds<Q_IT * RB>(aSC);
             const V rho = lds<Q_RHO * RB>(aSC);
             const double Tv[2] = {T.x, T.y}, lT[2] = {logT.x, logT.y}, rT[2] = {iT.x, iT.y}, rh[2] = {rho.x, rho.y};
             double cpavg[2] = {0.0, 0.0}, wdcp[2] = {0.0, 0.0};
             for (int k = warp * NSUB + sub; k < nsp; k += nw * NSUB) {
-                const unsigned a = aSP + k * SPB;
-                const V Yv = lds<SP_Y * RB>(a);
+                const unsigned a = sp_even<GS>(aSP, (unsigned)k), o = a ^ RB;
+                const V Yv = lds<E_Y * RB>(a);
                 const double Yk[2] = {Yv.x, Yv.y};
                 const double iw = __ldg(tb.sp_iw + k), ruw = __ldg(tb.sp_ruw + k), wk = __ldg(tb.sp_w + k);
                 const double tmid = __ldg(tb.sp_tmid + k);
@@ -561,11 +612,11 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                     dB[g] = (c[11] + c[5] * rT[g]) * rT[g] + hh;
                     Bk[g] = c[10] + c[11] * lT[g] + t * (c[6] + t * (c[12] + t * (c[13] + c[14] * t))) - c[5] * rT[g];
                 }
-                sts<SP_C * RB>(a, V{ck[0], ck[1]});
-                sts<SP_B * RB>(a, V{Bk[0], Bk[1]});
-                sts<SP_DB * RB>(a, V{dB[0], dB[1]});
-                sts<SP_HW * RB>(a, V{hW[0], hW[1]});
-                sts<SP_CP * RB>(a, V{cp[0], cp[1]});
+                sts<E_C * RB>(a, V{ck[0], ck[1]});
+                sts<O_B * RB>(o, V{Bk[0], Bk[1]});
+                sts<E_DB * RB>(a, V{dB[0], dB[1]});
+                sts<O_HW * RB>(o, V{hW[0], hW[1]});
+                sts<O_CP * RB>(o, V{cp[0], cp[1]});
             }
             const V ca = sub_sum<GS>(V{cpavg[0], cpavg[1]}), wd = sub_sum<GS>(V{wdcp[0], wdcp[1]});
             if (sub == 0) {
@@ -574,9 +625,11 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
             }
         }
         __syncthreads();
+        PJ_TICK(0)
 
         // ------------------------------------------------------------ phase B: reactions
-        {
+        if (!(io.dbg_skip & 2)) {
+            const V T = lds<Q_T * RB>(aSC), logT = lds<Q_LOGT * RB>(aSC), iT = lds<Q_IT * RB>(aSC);
             const int r0 = __ldg(pl.b_off + warp), r1 = __ldg(pl.b_off + warp + 1);
             const int rpm = r0 + __ldg(pl.b_npm + warp);
             int item = r0 < r1 ? __ldg(pl.b_item + r0 * NSUB + sub) : -1;
@@ -589,62 +642,72 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 } else {
                     const int p = valid ? item : 0;
                     const int4 c = __ldg(pl.rx + p * 4 + 2);
-                    const bool has3 = ((c.z & 0xFFFF) != nsp) || (((unsigned)c.w >> 16) != (unsigned)nsp);
+                    const unsigned nsp_f = sp_even<GS>(0u, (unsigned)nsp) / 16;
+                    const bool has3 = ((c.z & 0xFFFFu) != nsp_f) || (((unsigned)c.w >> 16) != nsp_f);
                     const bool three = __any_sync(0xffffffffu, has3);
                     reaction_plain<GS>(tb, pl, aSP, aRX, aRAW, aSC, p, valid, three, T, logT, iT);
                 }
                 item = nxt;
             }
         }
+        PJ_TICK(1)
         __syncthreads();
+        PJ_TICK(2)
 
         // ------------------------------------------------------------ phase C: species sums
-        {
+        if (!(io.dbg_skip & 4)) {
             const int i0 = __ldg(pl.c_off + warp), i1 = __ldg(pl.c_off + warp + 1);
             const V mwr = lds<Q_MWR * RB>(aSC);
             V pH1 = zero, pHA = zero, pHB = zero, pHT = zero, pSCP = zero;
-            // item header {species row offset, first unit, #(+1) units, #(-1) units}; the header and
-            // the first two units of the next item are fetched while this one is summed
+            // round header {first unit, #(+1) units, #(-1) units}; unit 0 = {species row offset or
+            // NONE, 1 if this sub-group stores}; pl.coop sub-groups share one species
             int4 h = __ldg(pl.c_item + i0);
-            const uint2* cp = pl.c_str + (long long)h.y * NSUB + sub;
-            uint2 u0 = __ldg(cp), u1 = __ldg(cp + NSUB);
             for (int it = i0; it < i1; ++it) {
-                const int n = h.z + h.w;
-                const int4 nh = __ldg(pl.c_item + it + 1);
-                const uint2* ncp = cp + n * NSUB;
-                const uint2 nu0 = __ldg(ncp), nu1 = __ldg(ncp + NSUB);
+                const uint2* cp = pl.c_str + (long long)h.x * NSUB + sub;
+                const int np_ = h.y, n = h.y + h.z;
+                h = __ldg(pl.c_item + it + 1);
+                const uint2 hd = __ldg(cp);
                 V aN = zero, aT = zero, a1 = zero, a2 = zero;
-                auto unit = [&](uint2 c, int i) {
-                    const double sg = i < h.z ? 1.0 : -1.0;
+                auto unit = [&](uint2 c, double sg) {
                     const unsigned x = aRX + c.x, y = aRX + c.y;
                     aN = vfma(sg, vadd(lds<RX_NET * RB>(x), lds<RX_NET * RB>(y)), aN);
                     aT = vfma(sg, vadd(lds<RX_TT * RB>(x), lds<RX_TT * RB>(y)), aT);
                     a1 = vfma(sg, vadd(lds<RX_X1 * RB>(x), lds<RX_X1 * RB>(y)), a1);
                     a2 = vfma(sg, vadd(lds<RX_X2 * RB>(x), lds<RX_X2 * RB>(y)), a2);
                 };
-                if (n > 0) unit(u0, 0);
-                if (n > 1) unit(u1, 1);
-#pragma unroll 1
-                for (int i = 2; i < n; ++i) unit(__ldg(cp + i * NSUB), i);
-                aN = sub_sum<GS>(aN); aT = sub_sum<GS>(aT); a1 = sub_sum<GS>(a1); a2 = sub_sum<GS>(a2);
-                if (sub == 0) {
-                    const unsigned a = aSP + h.x;
-                    const double wk = __ldg(tb.sp_w + h.x / SPB);
+                int i = 0;
+                for (; i + 2 <= n; i += 2) {                   // two units in flight
+                    const uint2 c = __ldg(cp + (i + 1) * NSUB), d = __ldg(cp + (i + 2) * NSUB);
+                    unit(c, i < np_ ? 1.0 : -1.0);
+                    unit(d, i + 1 < np_ ? 1.0 : -1.0);
+                }
+                if (i < n) unit(__ldg(cp + (i + 1) * NSUB), i < np_ ? 1.0 : -1.0);
+                for (int o = NPR; o < NPR * pl.coop; o <<= 1) {
+                    aN = V{aN.x + __shfl_xor_sync(0xffffffffu, aN.x, o), aN.y + __shfl_xor_sync(0xffffffffu, aN.y, o)};
+                    aT = V{aT.x + __shfl_xor_sync(0xffffffffu, aT.x, o), aT.y + __shfl_xor_sync(0xffffffffu, aT.y, o)};
+                    a1 = V{a1.x + __shfl_xor_sync(0xffffffffu, a1.x, o), a1.y + __shfl_xor_sync(0xffffffffu, a1.y, o)};
+                    a2 = V{a2.x + __shfl_xor_sync(0xffffffffu, a2.x, o), a2.y + __shfl_xor_sync(0xffffffffu, a2.y, o)};
+                }
+                if (hd.y) {
+                    const unsigned a = aSP + hd.x, o = a ^ RB;      // hd.x: even-slot base of species k
+                    const double wk = __ldg(tb.sp_w + hd.x / SPB);
                     const V comp = vmul(aN, mwr);
                     a1 = vadd(a1, comp);
                     a2 = vsub(a2, comp);
-                    const V hW = lds<SP_HW * RB>(a), cp_ = lds<SP_CP * RB>(a);
+                    const V hW = lds<O_HW * RB>(o), cp_ = lds<O_CP * RB>(o);
                     pH1 = vfma(hW, aN, pH1);
                     pHA = vfma(hW, a1, pHA);
                     pHB = vfma(hW, a2, pHB);
                     pHT = vfma(hW, aT, pHT);
                     pSCP = vfma(vmul(wk, cp_), aN, pSCP);
-                    sts<SP_WA * RB>(a, vmul(wk, a1));
-                    sts<SP_WB * RB>(a, vmul(wk, a2));
-                    sts<SP_WT * RB>(a, vmul(wk, aT));
+                    sts<E_WA * RB>(a, vmul(wk, a1));
+                    sts<O_WB * RB>(o, vmul(wk, a2));
+                    sts<E_WT * RB>(a, vmul(wk, aT));
                 }
-                h = nh; cp = ncp; u0 = nu0; u1 = nu1;
             }
+            // the warp's share of the energy-equation dot products
+            pH1 = sub_sum<GS>(pH1); pHA = sub_sum<GS>(pHA); pHB = sub_sum<GS>(pHB);
+            pHT = sub_sum<GS>(pHT); pSCP = sub_sum<GS>(pSCP);
             if (sub == 0) {
                 const unsigned a = aPA + warp * NPART * RB;
                 sts<D_H1 * RB>(a, pH1); sts<D_HA * RB>(a, pHA); sts<D_HB * RB>(a, pHB);
@@ -652,9 +715,10 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
             }
         }
         __syncthreads();
+        PJ_TICK(3)
 
         // ------------------------------------------------------------ phase DE
-        if (warp == 0) {
+        if (warp == 0 && !(io.dbg_skip & 64)) {
             // energy-equation scalars from the per-warp partial sums; the result of quantity q
             // replaces warp 0's own partial
             for (int q = sub; q < NPART; q += NSUB) {
@@ -667,7 +731,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 const V H1 = lds<D_H1 * RB>(aPA), HA = lds<D_HA * RB>(aPA), HB = lds<D_HB * RB>(aPA);
                 const V HT = lds<D_HT * RB>(aPA), SCP = lds<D_SCP * RB>(aPA);
                 const V cpavg = lds<D_CPAVG * RB>(aPA), wdcp = lds<D_WDCP * RB>(aPA);
-                const V rho = lds<Q_RHO * RB>(aSC), cpl = lds<SP_CP * RB>(aSP + last * SPB);
+                const V rho = lds<Q_RHO * RB>(aSC), cpl = lds<O_CP * RB>(sp_even<GS>(aSP, (unsigned)last) ^ RB);
                 const V nwt{-1.0 / cpavg.x, -1.0 / cpavg.y};
                 sts<S_NWT * RB>(aSD, nwt);
                 sts<S_A0 * RB>(aSD, vmul(nwt, HA));
@@ -685,111 +749,120 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
             // the next group's phase A0 (its inputs come from HBM: latency hidden behind DE)
             if (grp + gridDim.x < ngroups) phase_a0(grp + gridDim.x, buf ^ 1);
         }
-        {
+        if (!(io.dbg_skip & 8)) {
             // class S: elements with a sparse part, two steps per iteration, next pair in flight
             const int st0 = __ldg(pl.s_off + warp), st1 = __ldg(pl.s_off + warp + 1);
             const uint4* sp = pl.s_str + (long long)st0 * 2 * NSUB + sub;
             const uint2* ov = pl.o_str + (long long)__ldg(pl.o_off + warp) * NSUB + sub;
-            uint4 nA0 = __ldg(sp), nB0 = __ldg(sp + NSUB), nA1 = __ldg(sp + 2 * NSUB), nB1 = __ldg(sp + 3 * NSUB);
-            for (int st = st0; st < st1; st += 2) {
-                const uint4 A0 = nA0, B0 = nB0, A1 = nA1, B1 = nB1;
-                sp += 4 * NSUB;
-                nA0 = __ldg(sp); nB0 = __ldg(sp + NSUB); nA1 = __ldg(sp + 2 * NSUB); nB1 = __ldg(sp + 3 * NSUB);
-                const unsigned La = A0.x >> 22, Lb = A1.x >> 22;
-                const unsigned xa = aSP + (A0.y & 0xFFFFFu), xb = aSP + (A1.y & 0xFFFFFu);
-                const double2 cfa = __ldg(pl.colfac + (A0.y >> 20)), cfb = __ldg(pl.colfac + (A1.y >> 20));
-                V pa = vadd(lds<0>(aRAW + B0.x), lds<0>(aRAW + B0.z)), ma = vadd(lds<0>(aRAW + B0.y), lds<0>(aRAW + B0.w));
-                V pb = vadd(lds<0>(aRAW + B1.x), lds<0>(aRAW + B1.z)), mb = vadd(lds<0>(aRAW + B1.y), lds<0>(aRAW + B1.w));
-                V va = vfma(cfa.y, lds<RB>(xa), vmul(cfa.x, lds<0>(xa)));
-                V vb = vfma(cfb.y, lds<RB>(xb), vmul(cfb.x, lds<0>(xb)));
-                if (La > 2) {
-#pragma unroll 2
-                    for (unsigned i = 2; i < La; ++i) {
-                        const uint2 c = __ldg(ov);
+            // one step: the bundle (A, B) is consumed while `nA`, `nB` of a later step are fetched
+            auto step = [&](const uint4& A, const uint4& B) {
+                const unsigned L = A.x >> 22, e = A.x & NULL_E;
+                const unsigned x = aSP + (A.y & 0xFFFFFu);
+                const double2 cf = __ldg(pl.colfac + (A.y >> 20));
+                V p = vadd(lds<0>(aRAW + B.x), lds<0>(aRAW + B.z)), m = vadd(lds<0>(aRAW + B.y), lds<0>(aRAW + B.w));
+                V v = vfma(cf.y, lds<0>(x ^ RB), vmul(cf.x, lds<0>(x)));     // W_k a_k at x, W_k b_k at x ^ RB
+                if (L > 2) {
+                    // units 3..L come from the overflow stream in batches of four (padded)
+#pragma unroll 1
+                    for (unsigned i = 2; i < L; i += 4) {
+                        const uint2 c0 = __ldg(ov), c1 = __ldg(ov + NSUB), c2 = __ldg(ov + 2 * NSUB), c3 = __ldg(ov + 3 * NSUB);
                         prefetch_l1(ov + 8 * NSUB);
-                        ov += NSUB;
-                        pa = vadd(pa, lds<0>(aRAW + c.x));
-                        ma = vadd(ma, lds<0>(aRAW + c.y));
+                        ov += 4 * NSUB;
+                        p = vadd(p, vadd(vadd(lds<0>(aRAW + c0.x), lds<0>(aRAW + c1.x)), vadd(lds<0>(aRAW + c2.x), lds<0>(aRAW + c3.x))));
+                        m = vadd(m, vadd(vadd(lds<0>(aRAW + c0.y), lds<0>(aRAW + c1.y)), vadd(lds<0>(aRAW + c2.y), lds<0>(aRAW + c3.y))));
                     }
                 }
-                if (Lb > 2) {
-#pragma unroll 2
-                    for (unsigned i = 2; i < Lb; ++i) {
-                        const uint2 c = __ldg(ov);
-                        ov += NSUB;
-                        pb = vadd(pb, lds<0>(aRAW + c.x));
-                        mb = vadd(mb, lds<0>(aRAW + c.y));
-                    }
-                }
-                va = vfma(__hiloint2double((int)A0.w, (int)A0.z), vsub(pa, ma), va);
-                vb = vfma(__hiloint2double((int)A1.w, (int)A1.z), vsub(pb, mb), vb);
-                store(A0.x & NULL_E, va, (A0.x & NULL_E) != NULL_E);
-                store(A1.x & NULL_E, vb, (A1.x & NULL_E) != NULL_E);
-            }
-        }
-        {
-            // class D: dense-only elements, four steps per iteration, next four in flight
-            const int st0 = __ldg(pl.d_off + warp), st1 = __ldg(pl.d_off + warp + 1);
-            const uint2* dp = pl.d_str + (long long)st0 * NSUB + sub;
-            uint2 nx[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) nx[j] = __ldg(dp + j * NSUB);
+                v = vfma(__hiloint2double((int)A.w, (int)A.z), vsub(p, m), v);
+                store(e, v, e != NULL_E);
+            };
+            // four bundles rotate through registers; every bundle is fetched two steps ahead
+            uint4 A0 = __ldg(sp), B0 = __ldg(sp + NSUB), A1 = __ldg(sp + 2 * NSUB), B1 = __ldg(sp + 3 * NSUB);
             for (int st = st0; st < st1; st += 4) {
-                uint2 r[4];
-                dp += 4 * NSUB;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { r[j] = nx[j]; nx[j] = __ldg(dp + j * NSUB); }
-                V v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const unsigned x = aSP + (r[j].y & 0xFFFFFu);
-                    const double2 cf = __ldg(pl.colfac + (r[j].y >> 20));
-                    v[j] = vfma(cf.y, lds<RB>(x), vmul(cf.x, lds<0>(x)));
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) store(r[j].x, v[j], r[j].x != NULL_E);
+                const uint4 A2 = __ldg(sp + 4 * NSUB), B2 = __ldg(sp + 5 * NSUB);
+                const uint4 A3 = __ldg(sp + 6 * NSUB), B3 = __ldg(sp + 7 * NSUB);
+                step(A0, B0);
+                step(A1, B1);
+                if (st + 2 >= st1) break;
+                sp += 8 * NSUB;
+                A0 = __ldg(sp); B0 = __ldg(sp + NSUB); A1 = __ldg(sp + 2 * NSUB); B1 = __ldg(sp + 3 * NSUB);
+                step(A2, B2);
+                step(A3, B3);
             }
         }
-        {
+        if (!(io.dbg_skip & 16)) {
+            // class D: dense-only elements by row.  A sub-group keeps W_k a_k, W_k b_k of its row
+            // in registers and walks the row's dense-only columns, four in flight.
+            const int i0 = __ldg(pl.d_off + warp), i1 = __ldg(pl.d_off + warp + 1);
+            for (int it = i0; it < i1; ++it) {
+                const int2 di = __ldg(pl.d_item + it);                 // first unit, #columns (multiple of 4)
+                const uint2* dp = pl.d_str + (long long)di.x * NSUB + sub;
+                const uint2 hd = __ldg(dp);                            // {even-slot base or NONE, element of column 0}
+                const bool on = hd.x != 0xFFFFFFFFu;
+                const unsigned x = aSP + (on ? hd.x : 0u);
+                const V wa = lds<E_WA * RB>(x), wb = lds<O_WB * RB>(x ^ RB);
+                store(hd.y, lds<E_WT * RB>(x), on);                    // temperature column: W_k * T-term
+                uint2 nx[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) nx[j] = __ldg(dp + (1 + j) * NSUB);
+                for (int c = 0; c < di.y; c += 4) {
+                    uint2 r[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { r[j] = nx[j]; nx[j] = __ldg(dp + (5 + c + j) * NSUB); }
+                    double2 cf[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cf[j] = __ldg(pl.colfac + r[j].y);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) store(r[j].x, vfma(cf[j].y, wb, vmul(cf[j].x, wa)), r[j].x != NULL_E);
+                }
+            }
+        }
+        if (!(io.dbg_skip & 32)) {
             // class T, the energy-equation row (cj:3095-3254): per column an enthalpy-weighted
-            // gather split over the sub-groups of the warp
-            const int nit = __ldg(pl.t_n + warp);
-            if (nit) {
-                const uint2* up = pl.t_str + (long long)__ldg(pl.t_off + warp) * NSUB + sub;
-                uint2 hd = __ldg(up), c0 = __ldg(up + NSUB), c1 = __ldg(up + 2 * NSUB);
+            // gather; pl.tcoop sub-groups share a column, units come four at a time
+            const int i0 = __ldg(pl.t_off + warp), i1 = __ldg(pl.t_off + warp + 1);
+            if (i0 < i1) {
+                int2 ti = __ldg(pl.t_item + i0);
                 if (warp != 0) asm volatile("bar.sync 1, %0;" ::"r"(pl.t_sync) : "memory");
                 const V nwt = lds<S_NWT * RB>(aSD), A0 = lds<S_A0 * RB>(aSD), B0 = lds<S_B0 * RB>(aSD);
                 const V XT = lds<S_XT * RB>(aSD), cpl = lds<S_CPL * RB>(aSD);
-                for (int it = 0; it < nit; ++it) {
-                    const unsigned n = hd.y & 0xFFFFu, col = hd.y >> 16, e = hd.x;
-                    const uint2* nup = up + (n + 1) * NSUB;
-                    const uint2 nhd = __ldg(nup), nc0 = __ldg(nup + NSUB), nc1 = __ldg(nup + 2 * NSUB);
+                for (int it = i0; it < i1; ++it) {
+                    const uint2* up = pl.t_str + (long long)ti.x * NSUB + sub;
+                    const int n = ti.y;
+                    ti = __ldg(pl.t_item + it + 1);
+                    const uint2 hd = __ldg(up);                        // {col | store << 16, offset of cp_j}
                     V acc0 = zero, acc1 = zero;
-                    if (n) {
-                        acc0 = vmul(lds<RX_DH * RB>(aRX + c0.y), lds<0>(aRAW + c0.x));
-                        acc1 = vmul(lds<RX_DH * RB>(aRX + c1.y), lds<0>(aRAW + c1.x));
-#pragma unroll 1
-                        for (unsigned i = 2; i < n; i += 2) {
-                            const uint2 c = __ldg(up + (i + 1) * NSUB), d = __ldg(up + (i + 2) * NSUB);
-                            acc0 = vfma(lds<RX_DH * RB>(aRX + c.y), lds<0>(aRAW + c.x), acc0);
-                            acc1 = vfma(lds<RX_DH * RB>(aRX + d.y), lds<0>(aRAW + d.x), acc1);
-                        }
+                    uint2 nx[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) nx[j] = __ldg(up + (1 + j) * NSUB);
+                    for (int c = 0; c < n; c += 4) {
+                        uint2 r[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { r[j] = nx[j]; nx[j] = __ldg(up + (5 + c + j) * NSUB); }
+                        acc0 = vfma(lds<RX_DH * RB>(aRX + r[0].y), lds<0>(aRAW + r[0].x), acc0);
+                        acc1 = vfma(lds<RX_DH * RB>(aRX + r[1].y), lds<0>(aRAW + r[1].x), acc1);
+                        acc0 = vfma(lds<RX_DH * RB>(aRX + r[2].y), lds<0>(aRAW + r[2].x), acc0);
+                        acc1 = vfma(lds<RX_DH * RB>(aRX + r[3].y), lds<0>(aRAW + r[3].x), acc1);
                     }
-                    const V E0 = sub_sum<GS>(vadd(acc0, acc1));
-                    if (sub == 0) {
-                        const double2 cf = __ldg(pl.colfac + col);
-                        const V cpj = lds<SP_CP * RB>(aSP + (col - 1) * SPB);
-                        V v = vmul(cf.x, vfma(nwt, E0, A0));
-                        v = vfma(cf.y, B0, v);
-                        v = vfma(XT, vsub(cpj, cpl), v);
-                        store(e, v, true);
-                    }
-                    up = nup; hd = nhd; c0 = nc0; c1 = nc1;
+                    V E0 = vadd(acc0, acc1);
+                    for (int o = NPR; o < NPR * pl.tcoop; o <<= 1)
+                        E0 = V{E0.x + __shfl_xor_sync(0xffffffffu, E0.x, o), E0.y + __shfl_xor_sync(0xffffffffu, E0.y, o)};
+                    const unsigned col = hd.x & 0xFFFFu;
+                    const double2 cf = __ldg(pl.colfac + col);
+                    const V cpj = lds<0>(aSP + hd.y);
+                    V v = vmul(cf.x, vfma(nwt, E0, A0));
+                    v = vfma(cf.y, B0, v);
+                    v = vfma(XT, vsub(cpj, cpl), v);
+                    store(col * (unsigned)nsp, v, (hd.x >> 16) != 0u);
                 }
             }
         }
+        PJ_TICK(4)
         __syncthreads();
+        PJ_TICK(5)
     }
+#undef PJ_TICK
+    if (io.dbg_clk && blockIdx.x == 0 && lane == 0)
+        for (int i = 0; i < 6; ++i) io.dbg_clk[warp * 8 + i] = clk[i];
 }
 
 }  // namespace pj5

@@ -82,6 +82,8 @@ struct IO {
     double* scal3;   // M_RATES: y_N, mw_avg, rho per state (3 doubles, rows), nullable
     int o_sf;
     long long o_ld;
+    int dbg_skip;    // development only (PYJAC_DEBUG_SKIP): phases of k_jacobian to skip when timing
+    long long* dbg_clk;   // development only: per-phase cycle counts of block 0 (8 slots) or NULL
 };
 
 // shared-memory carve-up: offsets in doubles, every array interleaved over the G states

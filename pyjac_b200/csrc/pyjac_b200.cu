@@ -167,16 +167,25 @@ int launch(pyjac_mech* m, int mode_ix, const IO& io, cudaStream_t st)
     return PYJAC_OK;
 }
 
-const void* jac_kernel(int gs)
+template <int MAXT>
+const void* jac_kernel_t(int gs)
 {
     switch (gs) {
-    case 2: return (const void*)pj5::k_jacobian<2>;
-    case 4: return (const void*)pj5::k_jacobian<4>;
-    case 8: return (const void*)pj5::k_jacobian<8>;
-    case 16: return (const void*)pj5::k_jacobian<16>;
-    case 32: return (const void*)pj5::k_jacobian<32>;
+    case 2: return (const void*)pj5::k_jacobian<2, MAXT>;
+    case 4: return (const void*)pj5::k_jacobian<4, MAXT>;
+    case 8: return (const void*)pj5::k_jacobian<8, MAXT>;
+    case 16: return (const void*)pj5::k_jacobian<16, MAXT>;
+    case 32: return (const void*)pj5::k_jacobian<32, MAXT>;
     default: return nullptr;
     }
+}
+
+// the build with the smallest thread bound (= most registers per thread) that admits nt
+const void* jac_kernel(int gs, int nt = 512)
+{
+    if (nt <= 512) return jac_kernel_t<512>(gs);
+    if (nt <= 768) return jac_kernel_t<768>(gs);
+    return jac_kernel_t<1024>(gs);
 }
 
 // eval_jacob: the plan in the table blob fixes states per block and block size
@@ -185,7 +194,7 @@ int launch_jac(pyjac_mech* m, const IO& io, cudaStream_t st)
     if (io.n <= 0) return PYJAC_OK;
     CU(cudaSetDevice(m->device));
     const pj5::Plan& pl = m->plan;
-    const void* fn = jac_kernel(pl.gs);
+    const void* fn = jac_kernel(pl.gs, pl.nt);
     if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable Jacobian plan");
     const size_t bytes = (size_t)pl.total * 8;
     if (!m->jac_bpsm) {
@@ -313,23 +322,23 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     UP(tb.red_rx, "red_rx", int, 1); UP(tb.red_nu, "red_nu", double, 0);
     if (!rc) {
         const pjt::Entry* pe = pjt::find(blob, "p5_cfg");
-        if (!pe || pe->dtype != 1 || pe->count < 11) rc = fail(PYJAC_EINVAL, "table blob lacks p5_cfg");
+        if (!pe || pe->dtype != 1 || pe->count < 13) rc = fail(PYJAC_EINVAL, "table blob lacks p5_cfg");
         else {
             const int* c5 = (const int*)((const char*)blob + pe->offset);
             pj5::Plan& pl = m->plan;
             int* o = &pl.gs;
-            for (int i = 0; i < 11; ++i) o[i] = c5[i];
-            if (!jac_kernel(pl.gs) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64)
+            for (int i = 0; i < 13; ++i) o[i] = c5[i];
+            if (!jac_kernel(pl.gs) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 1024 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
                 rc = fail(PYJAC_EINVAL, "bad Jacobian plan configuration");
         }
     }
     UP(plan.rx, "p5_rx", int4, 1);
     UP(plan.b_off, "p5_b_off", int, 1); UP(plan.b_npm, "p5_b_npm", int, 1); UP(plan.b_item, "p5_b_item", int, 1);
     UP(plan.c_off, "p5_c_off", int, 1); UP(plan.c_item, "p5_c_item", int4, 1); UP(plan.c_str, "p5_c_str", uint2, 1);
-    UP(plan.d_off, "p5_d_off", int, 1); UP(plan.d_str, "p5_d_str", uint2, 1);
+    UP(plan.d_off, "p5_d_off", int, 1); UP(plan.d_item, "p5_d_item", int2, 1); UP(plan.d_str, "p5_d_str", uint2, 1);
     UP(plan.s_off, "p5_s_off", int, 1); UP(plan.s_str, "p5_s_str", uint4, 1);
     UP(plan.o_off, "p5_o_off", int, 1); UP(plan.o_str, "p5_o_str", uint2, 1);
-    UP(plan.t_off, "p5_t_off", int, 1); UP(plan.t_n, "p5_t_n", int, 1); UP(plan.t_str, "p5_t_str", uint2, 1);
+    UP(plan.t_off, "p5_t_off", int, 1); UP(plan.t_item, "p5_t_item", int2, 1); UP(plan.t_str, "p5_t_str", uint2, 1);
     UP(plan.colfac, "p5_colfac", double2, 0);
 #undef UP
     if (!rc) {
@@ -388,6 +397,8 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
     IO io{};
     io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
     io.jac = d_jac; io.jac_layout = jac_layout; io.jac_ld = jac_ld;
+    if (const char* dbg = std::getenv("PYJAC_DEBUG_SKIP")) io.dbg_skip = std::atoi(dbg);   // timing experiments only
+    if (const char* dbg = std::getenv("PYJAC_DEBUG_CLK")) io.dbg_clk = (long long*)std::strtoull(dbg, nullptr, 0);
     return launch_jac(m, io, (cudaStream_t)stream);
 }
 

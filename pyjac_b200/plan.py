@@ -34,6 +34,7 @@ GS_CHOICES = (32, 16, 8, 4, 2)
 SP_SLOTS, RX_SLOTS = 8, 5    # C B dB hW WA(Y) WB WT cp  /  net tT X1 X2 dH
 SLOT_WA, SLOT_WT, SLOT_CP = 4, 6, 7
 NULL_E = 0x3FFFFF            # element index of a padding element
+NONE32 = 0xFFFFFFFF
 MAX_L2 = 1023
 
 # cost estimates (warp instructions) used only for load balancing
@@ -41,8 +42,9 @@ COST_PLAIN, COST_IRREV, COST_THREE = 215.0, 150.0, 40.0
 COST_PM = {'thd': 300.0, 'lind': 450.0, 'troe': 900.0, 'sri': 1200.0}
 COST_EFF = 8.0
 COST_C_ITEM, COST_C_IT = 90.0, 28.0
-COST_D_STEP, COST_S_STEP, COST_S_OVF = 20.0, 34.0, 12.0
-COST_T_ITEM, COST_T_IT = 60.0, 8.0
+COST_S_STEP, COST_S_OVF = 40.0, 25.0
+COST_D_ITEM, COST_D_COL = 50.0, 10.0
+COST_T_ITEM, COST_T_IT = 80.0, 8.0
 COST_DOTS = 400.0            # warp 0: energy-equation scalars + the next group's phase A0
 
 
@@ -104,7 +106,7 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
                ) -> Dict[str, np.ndarray]:
     """kinds[p] in {'plain','thd','lind','troe','sri'} per kernel-order reaction p;
     contrib[(k, j)] = [(raw row, nu)], tcontrib[j] = [(raw row, reaction)]."""
-    assert gs in GS_CHOICES and nt % 32 == 0 and 64 <= nt <= 512
+    assert gs in GS_CHOICES and nt % 32 == 0 and 64 <= nt <= 1024
     if nsp > 2000:
         raise ValueError('too many species for the 22-bit element index')
     nw = nt // 32
@@ -157,61 +159,92 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
             (plus if c > 0 else minus).extend([src] * int(abs(c)))
         return plus, minus
 
+    # byte offsets inside the shared-memory regions (a row is GS doubles)
+    RB = gs * 8
+    SPB, RXB = SP_SLOTS * RB, RX_SLOTS * RB
+    PF = 16                                    # null units after each stream (prefetch runs ahead)
+
+    def expand(lst):
+        """[(source, nu)] -> (sources with weight +1, sources with weight -1), nu an integer."""
+        plus, minus = [], []
+        for src, c in lst:
+            if not float(c).is_integer():
+                raise ValueError('non-integer coefficient %r' % c)
+            (plus if c > 0 else minus).extend([src] * int(abs(c)))
+        return plus, minus
+
     # ---------------------------------------------------------------- phase C
-    # item: species k; its (reaction, nu) list split into +1 and -1 entries, each cut into units
-    # of 2 entries per sub-group; stream unit u of sub-group s is c_str[(u * NSUB + s) * 2 + {0,1}]
+    # Per species k: sum over its reactions of nu_ki * (net, tT, X1, X2), nu split into +1 and -1
+    # entries (byte offsets of reaction rows).  D sub-groups share one species (D = the largest
+    # power of two that still lets every species be summed in one round of the block); a warp
+    # round handles NSUB / D species of similar list length.  Round r of a warp: header unit
+    # {species row offset or NONE32, 1 if this sub-group stores the result}, then nP units of
+    # two +1 entries and nM units of two -1 entries per sub-group, all padded with the zero row.
+    coop = nsub
+    while coop > 1 and nw * (nsub // coop) < nsp:
+        coop //= 2
+    per_round = nsub // coop
     c_lists = [expand(red[k]) for k in range(nsp)]
-    c_np = [(len(pl_) + 2 * nsub - 1) // (2 * nsub) for pl_, _ in c_lists]
-    c_nm = [(len(mi_) + 2 * nsub - 1) // (2 * nsub) for _, mi_ in c_lists]
-    c_cost = [COST_C_ITEM + COST_C_IT * (c_np[k] + c_nm[k]) for k in range(nsp)]
-    bins, _ = _lpt(c_cost, nw)
+
+    def n_units(n_entries):
+        return (-(-n_entries // coop) + 1) // 2
+
+    order_c = sorted(range(nsp), key=lambda k: (-(n_units(len(c_lists[k][0])) + n_units(len(c_lists[k][1]))), k))
+    chunks = [order_c[c0:c0 + per_round] for c0 in range(0, nsp, per_round)]
+    per_warp: List[List[List[int]]] = [[] for _ in range(nw)]
+    for ci, ch in enumerate(chunks):
+        per_warp[ci % nw].append(ch)
     c_off, c_item, c_str = [0], [], []
     for w in range(nw):
-        for k in bins[w]:
-            c_item += [k * SPB, len(c_str) // (2 * nsub), c_np[k], c_nm[k]]
-            for lst, n in ((c_lists[k][0], c_np[k]), (c_lists[k][1], c_nm[k])):
-                offs = [p * RXB for p in lst] + [nr * RXB] * (n * 2 * nsub - len(lst))
+        for ch in per_warp[w]:
+            n_p = max(n_units(len(c_lists[k][0])) for k in ch)
+            n_m = max(n_units(len(c_lists[k][1])) for k in ch)
+            c_item += [len(c_str) // (2 * nsub), n_p, n_m, 0]
+            # header unit, then the units; sub-group sb works for species ch[sb // coop], part sb % coop
+            subs_k = [ch[sb // coop] if sb // coop < len(ch) else None for sb in range(nsub)]
+            for sb in range(nsub):
+                k = subs_k[sb]
+                c_str += [NONE32 if k is None else k * SPB + (k & 1) * RB, 1 if (k is not None and sb % coop == 0) else 0]
+            for which, n in ((0, n_p), (1, n_m)):
+                per_sub = []
+                for sb in range(nsub):
+                    k = subs_k[sb]
+                    lst = [] if k is None else c_lists[k][which][sb % coop::coop]
+                    per_sub.append([q_ * RXB for q_ in lst] + [nr * RXB] * (2 * n - len(lst)))
                 for u in range(n):
                     for sb in range(nsub):
-                        c_str += [offs[(u * nsub + sb) * 2], offs[(u * nsub + sb) * 2 + 1]]
+                        c_str += per_sub[sb][2 * u:2 * u + 2]
         c_off.append(len(c_item) // 4)
     P['p5_c_off'] = i32(c_off)
-    P['p5_c_item'] = i32(c_item + [0, len(c_str) // (2 * nsub), 0, 0])   # + null item (look-ahead)
+    P['p5_c_item'] = i32(c_item + [len(c_str) // (2 * nsub), 0, 0, 0])      # + null round (look-ahead)
     P['p5_c_str'] = u32(c_str + [nr * RXB] * (2 * nsub * PF))
 
     # ---------------------------------------------------------------- phase DE
-    # element (col, k): output row k + 1 of column col; col 0 is the temperature column.  NSUB
-    # elements form a step.  Three classes of work, each with its own stream:
-    #   D  dense-only elements: one uint2 {e, SP offset | col << 20} per element; a warp takes
-    #      them four steps at a time
-    #   S  elements with a sparse part of padded length L >= 1: two uint4 per element,
-    #      {e | L << 22, SP offset | col << 20, the double (1/W_j) W_k} and the first two units
-    #      {+1 raw row, -1 raw row, +1 raw row, -1 raw row} (byte offsets; padding = zero row);
-    #      units 3..L go to an overflow stream of uint2; a warp takes two steps at a time
-    #   T  the energy-equation row: one item per column, its enthalpy-weighted list split over
-    #      the NSUB sub-groups: header {e, n | col << 16}, then n units {raw row, reaction row}
-    def row_words(col, k):
-        slot = SLOT_WT if col == 0 else SLOT_WA
-        return [col * nsp + k + 1, (k * SPB + slot * RB) | (col << 20)]
-    null_row = [NULL_E, SLOT_WA * RB]
+    # element (col, k): output row k + 1 of column col; col 0 is the temperature column.
+    # Three classes of work, each with its own stream of uint2 / uint4 units per sub-group:
+    #   S  elements with a sparse part (NSUB per step, sorted by padded list length L >= 1): two
+    #      uint4 per element, {e | L << 22, species-row offset of WA | col << 20, the double
+    #      (1/W_j) W_k} and the first two units {+1 raw row, -1 raw row, +1, -1} (byte offsets;
+    #      padding = zero row); units 3..L, padded to a multiple of four, go to an overflow
+    #      stream of uint2; a warp takes two steps at a time
+    #   D  dense-only elements by row: a sub-group keeps W_k a_k, W_k b_k of one species row in
+    #      registers and walks that row's dense-only columns: header {species-row offset or NONE,
+    #      element index of the row's temperature-column entry}, then n units {e, col}
+    #   T  the energy-equation row: pl.tcoop sub-groups share one column's enthalpy-weighted
+    #      list: header {col | store << 16, offset of cp_j}, then n units {raw row, reaction row}
+    def sp_even(k):
+        """Byte offset of species k's even-slot base; odd slots sit at (base ^ RB): the slot pair
+        is swapped for odd k so that rows of different species fall on different banks."""
+        return k * SPB + (k & 1) * RB
     zr = nraw * RB
+    null_sp = sp_even(0) + SLOT_WA * RB
 
     elems = []
-    for col in range(nsp):
+    for col in range(1, nsp):
         for k in range(last):
-            plus, minus = expand(contrib.get((k, col - 1), []) if col else [])
+            plus, minus = expand(contrib.get((k, col - 1), []))
             elems.append((max(len(plus), len(minus)), col, k, plus, minus))
-    dense = sorted((e for e in elems if e[0] == 0), key=lambda e: (e[1], e[2]))
     sparse = sorted((e for e in elems if e[0] > 0), key=lambda e: (-e[0], e[1], e[2]))
-
-    d_steps = []
-    for c0 in range(0, len(dense), nsub):
-        grp = dense[c0:c0 + nsub]
-        d_steps.append([row_words(e[1], e[2]) for e in grp] + [null_row] * (nsub - len(grp)))
-    d_quads = []
-    for c0 in range(0, len(d_steps), 4):
-        q4 = d_steps[c0:c0 + 4]
-        d_quads.append(q4 + [[null_row] * nsub] * (4 - len(q4)))
 
     s_steps = []                               # (A words, B words, overflow units, L)
     for c0 in range(0, len(sparse), nsub):
@@ -219,53 +252,83 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
         L = grp[0][0]
         if L > MAX_L2:
             raise ValueError('sparse Jacobian element with too many contributions')
-        A, B, ovf = [], [], [[] for _ in range(max(L - 2, 0))]
+        n_ovf = (max(L - 2, 0) + 3) // 4 * 4              # overflow units come in batches of four
+        A, B, ovf = [], [], [[] for _ in range(n_ovf)]
         for sb in range(nsub):
             if sb < len(grp):
                 _, col, k, plus, minus = grp[sb]
-                rw = row_words(col, k)
-                A.append([rw[0] | (L << 22), rw[1]] + _f64_words(sp_iw[col - 1] * sp_w[k]))
+                A.append([(col * nsp + k + 1) | (L << 22), (sp_even(k) + SLOT_WA * RB) | (col << 20)]
+                         + _f64_words(sp_iw[col - 1] * sp_w[k]))
             else:
                 plus, minus = [], []
-                A.append([NULL_E | (L << 22), null_row[1], 0, 0])
-            po = [x * RB for x in plus] + [zr] * (max(L, 2) - len(plus))
-            mo = [x * RB for x in minus] + [zr] * (max(L, 2) - len(minus))
+                A.append([NULL_E | (L << 22), null_sp, 0, 0])
+            po = [x * RB for x in plus] + [zr] * (n_ovf + 2 - len(plus))
+            mo = [x * RB for x in minus] + [zr] * (n_ovf + 2 - len(minus))
             B.append([po[0], mo[0], po[1], mo[1]])
-            for i in range(2, L):
+            for i in range(2, n_ovf + 2):
                 ovf[i - 2].append([po[i], mo[i]])
         s_steps.append((A, B, ovf, L))
-    null_s = ([[NULL_E, null_row[1], 0, 0]] * nsub, [[zr] * 4] * nsub, [], 0)
+    null_s = ([[NULL_E, null_sp, 0, 0]] * nsub, [[zr] * 4] * nsub, [], 0)
     s_pairs = []
     for c0 in range(0, len(s_steps), 2):
         pr_ = s_steps[c0:c0 + 2]
         s_pairs.append(pr_ + [null_s] * (2 - len(pr_)))
 
+    # D: rows sorted by their number of dense-only columns, NSUB rows per item
+    sparse_set = {(e[1], e[2]) for e in sparse}
+    d_rows = sorted(((k, [col for col in range(1, nsp) if (col, k) not in sparse_set]) for k in range(last)),
+                    key=lambda r: (-len(r[1]), r[0]))
+    d_items = []
+    for c0 in range(0, len(d_rows), nsub):
+        grp = d_rows[c0:c0 + nsub]
+        n = (len(grp[0][1]) + 3) // 4 * 4                  # columns come in batches of four
+        units = [[[sp_even(k), k + 1] for k, _ in grp] + [[NONE32, NULL_E]] * (nsub - len(grp))]
+        for u in range(n):
+            units.append([[cols[u] * nsp + k + 1, cols[u]] if u < len(cols) else [NULL_E, 0] for k, cols in grp]
+                         + [[NULL_E, 0]] * (nsub - len(grp)))
+        d_items.append((n, units))
+
+    # T: columns sorted by list length; tcoop sub-groups per column, one round per warp if possible
+    tcoop = nsub
+    while tcoop > 1 and nw * (nsub // tcoop) < last:
+        tcoop //= 2
+    t_per = nsub // tcoop
+    t_cols = sorted(range(last), key=lambda j: (-len(tcontrib.get(j, [])), j))
     t_items = []
-    for j in range(last):
-        lst = tcontrib.get(j, [])
-        n = (len(lst) + nsub - 1) // nsub
-        n += n & 1                                             # units come in pairs
+    for c0 in range(0, last, t_per):
+        grp = t_cols[c0:c0 + t_per]
+        n = max(-(-len(tcontrib.get(j, [])) // tcoop) for j in grp)
+        n = (n + 3) // 4 * 4                               # units come in batches of four
         if n > 0xFFFF:
             raise ValueError('energy-row element with too many contributions')
-        pad = lst + [(nraw, nr)] * (n * nsub - len(lst))
-        units = [[[(j + 1) * nsp, n | ((j + 1) << 16)]] * nsub]
-        for u in range(n):
-            units.append([[pad[u * nsub + sb][0] * RB, pad[u * nsub + sb][1] * RXB] for sb in range(nsub)])
+        hdr, per_sub = [], []
+        for sb in range(nsub):
+            j = grp[sb // tcoop] if sb // tcoop < len(grp) else None
+            if j is None:
+                hdr.append([0, null_sp])
+                per_sub.append([[zr, nr * RXB]] * n)
+            else:
+                lst = tcontrib.get(j, [])[sb % tcoop::tcoop]
+                hdr.append([(j + 1) | ((1 if sb % tcoop == 0 else 0) << 16), (sp_even(j) ^ RB) + (SLOT_CP - 1) * RB])
+                per_sub.append([[src * RB, rx_ * RXB] for src, rx_ in lst] + [[zr, nr * RXB]] * (n - len(lst)))
+        units = [hdr] + [[per_sub[sb][u] for sb in range(nsub)] for u in range(n)]
         t_items.append((n, units))
 
     # one longest-first assignment over all three classes
     costs = ([COST_T_ITEM + COST_T_IT * n for n, _ in t_items] +
-             [sum(COST_S_STEP + COST_S_OVF * max(st[3] - 2, 0) for st in pr_) for pr_ in s_pairs] +
-             [4 * COST_D_STEP] * len(d_quads))
+             [sum(COST_S_STEP + COST_S_OVF * len(st[2]) for st in pr_) for pr_ in s_pairs] +
+             [COST_D_ITEM + COST_D_COL * n for n, _ in d_items])
     init = [0.0] * nw
     init[0] = COST_DOTS
     allbins, _ = _lpt(costs, nw, init)
     nT, nS = len(t_items), len(s_pairs)
-    d_off, d_str, s_off, s_str, o_off, o_str, t_off, t_n, t_str = [0], [], [0], [], [0], [], [0], [], []
+    s_off, s_str, o_off, o_str = [0], [], [0], []
+    d_off, d_item, d_str, t_off, t_item, t_str = [0], [], [], [0], [], []
     for w in range(nw):
         mine = sorted(allbins[w])
         for ix in mine:
             if ix < nT:
+                t_item += [len(t_str) // (2 * nsub), t_items[ix][0]]
                 for u in t_items[ix][1]:
                     for xy in u:
                         t_str += xy
@@ -279,24 +342,25 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
                         for xy in u:
                             o_str += xy
             else:
-                for st in d_quads[ix - nT - nS]:
-                    for xy in st:
+                d_item += [len(d_str) // (2 * nsub), d_items[ix - nT - nS][0]]
+                for u in d_items[ix - nT - nS][1]:
+                    for xy in u:
                         d_str += xy
-        t_n.append(sum(1 for ix in mine if ix < nT))
-        t_off.append(len(t_str) // (2 * nsub))
+        t_off.append(len(t_item) // 2)
+        d_off.append(len(d_item) // 2)
         s_off.append(len(s_str) // (8 * nsub))          # in steps
         o_off.append(len(o_str) // (2 * nsub))
-        d_off.append(len(d_str) // (2 * nsub))          # in steps
     P['p5_d_off'] = i32(d_off)
-    P['p5_d_str'] = u32(d_str + null_row * (nsub * PF))
+    P['p5_d_item'] = i32(d_item + [len(d_str) // (2 * nsub), 0])
+    P['p5_d_str'] = u32(d_str + [NULL_E, 0] * (nsub * PF))
     P['p5_s_off'] = i32(s_off)
-    P['p5_s_str'] = u32(s_str + ([NULL_E, null_row[1], 0, 0] * nsub + [zr] * (4 * nsub)) * 4)
+    P['p5_s_str'] = u32(s_str + ([NULL_E, null_sp, 0, 0] * nsub + [zr] * (4 * nsub)) * 4)
     P['p5_o_off'] = i32(o_off)
     P['p5_o_str'] = u32(o_str + [zr] * (2 * nsub * PF))
     P['p5_t_off'] = i32(t_off)
-    P['p5_t_n'] = i32(t_n)
+    P['p5_t_item'] = i32(t_item + [len(t_str) // (2 * nsub), 0])
     P['p5_t_str'] = u32(t_str + [zr, nr * RXB] * (nsub * PF))
-    t_nst = t_n
+    t_nst = [t_off[w + 1] - t_off[w] for w in range(nw)]
 
     # per column: (1 / W_j, (1 / W_j) (W_j / W_N)); the temperature column takes W_k * T-term as is
     colfac = [1.0, 0.0]
@@ -309,6 +373,6 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
     # dot products) and every other warp that owns such steps (waits)
     waiters = sum(1 for w in range(1, nw) if t_nst[w])
     t_sync = 32 * (waiters + 1) if waiters else 0
-    P['p5_cfg'] = i32([gs, nt, nw, nsub, L['SP'], L['RX'], L['RAW'], L['SC'], L['PA'], L['total'], t_sync]
-                      + [0] * 5)
+    P['p5_cfg'] = i32([gs, nt, nw, nsub, L['SP'], L['RX'], L['RAW'], L['SC'], L['PA'], L['total'], t_sync, coop, tcoop]
+                      + [0] * 3)
     return P

@@ -285,6 +285,9 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
                              q('{:.16e}', -T1), q('{:.16e}', -T2),
                              q('{:.16e}', -(1.0 - a) / T3), q('{:.16e}', a / T1),
                              q('{:.16e}', T2)]                                 # cj:1083-1090,1262-1282
+                # reciprocals of par[7], par[9] for the Jacobian kernel (T / (-T3) as a product)
+                par[28] = 1.0 / par[7] if par[7] != 0.0 else 0.0
+                par[29] = 1.0 / par[9] if par[9] != 0.0 else 0.0
             elif rx.sri:
                 s_ = rx.sri_par
                 five = len(s_) == 5
@@ -578,8 +581,14 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     # six species slots and eight raw destinations packed two per int
     rec5 = np.zeros((nr, 16), dtype=np.int32)
     rec5[:, :9] = rec[:, :9]
+    # species slots as (byte offset of the species' even-slot base) / 16; the slot pair of odd
+    # species is swapped (plan.py, sp_even) so that rows of different species use different banks
+    gs_ = int(T['p5_cfg'][0])
+    spf = (slots * (plan.SP_SLOTS * gs_ * 8) + (slots & 1) * (gs_ * 8)) // 16
+    if spf.max() > 0xFFFF:
+        raise UnsupportedMechanism('too many species for 16-bit species-row offsets')
     for a in range(3):
-        rec5[:, 9 + a] = slots[:, 2 * a] | (slots[:, 2 * a + 1] << 16)
+        rec5[:, 9 + a] = spf[:, 2 * a] | (spf[:, 2 * a + 1] << 16)
     dst5 = np.where(rx_dst == NONE, nraw + 1, rx_dst).astype(np.int32)     # none -> scratch raw row
     for a in range(4):
         rec5[:, 12 + a] = dst5[:, 2 * a] | (dst5[:, 2 * a + 1] << 16)

@@ -217,22 +217,40 @@ def evaluate(Tb, P, y):
     SPB, RXB = 8 * RB, 5 * RB
     R4z = np.concatenate([R4, np.zeros((1, 4, n))], axis=0)
     wdot = np.zeros((n, nsp)); tcol = np.zeros((n, nsp)); Ak = np.zeros((n, nsp)); Bk = np.zeros((n, nsp))
+    def sp_slot0(off):
+        k_, chunk = off // SPB, (off % SPB) // RB
+        return k_, chunk ^ (k_ & 1)
     c_item, c_str = Tb['p5_c_item'].reshape(-1, 4), Tb['p5_c_str'].view(np.uint32)
+    coop = int(cfg[11])
+    assert coop >= 1 and nsub % coop == 0
     seen_k = set()
     for wp in range(nw):
         for it in range(Tb['p5_c_off'][wp], Tb['p5_c_off'][wp + 1]):
-            spoff, u, n_p, n_m = (int(v) for v in c_item[it])
-            assert spoff % SPB == 0
-            k = spoff // SPB
-            assert k not in seen_k
-            seen_k.add(k)
+            u, n_p, n_m = (int(v) for v in c_item[it][:3])
+            hdr = [(int(c_str[(u * nsub + sub) * 2]), int(c_str[(u * nsub + sub) * 2 + 1])) for sub in range(nsub)]
+            u += 1
+            part = np.zeros((nsub, 4, n))
             for sign, cnt in ((1.0, n_p), (-1.0, n_m)):
-                for off in c_str[u * nsub * 2:(u + cnt) * nsub * 2]:
-                    assert off % RXB == 0
-                    rxn = int(off) // RXB
-                    wdot[:, k] += sign * R4z[rxn, 0]; tcol[:, k] += sign * R4z[rxn, 1]
-                    Ak[:, k] += sign * R4z[rxn, 2]; Bk[:, k] += sign * R4z[rxn, 3]
+                for i in range(cnt):
+                    for sub in range(nsub):
+                        for h in range(2):
+                            off = int(c_str[((u + i) * nsub + sub) * 2 + h])
+                            assert off % RXB == 0
+                            part[sub] += sign * R4z[off // RXB]
                 u += cnt
+            for g0 in range(0, nsub, coop):
+                spoff, lead = hdr[g0]
+                assert all(hdr[g0 + d][0] == spoff for d in range(coop))
+                assert lead == (0 if spoff == 0xFFFFFFFF else 1) and all(hdr[g0 + d][1] == 0 for d in range(1, coop))
+                tot = part[g0:g0 + coop].sum(axis=0)
+                if spoff == 0xFFFFFFFF:
+                    assert not tot.any()
+                    continue
+                k, sl0 = sp_slot0(spoff)
+                assert sl0 == 0
+                assert k not in seen_k
+                seen_k.add(k)
+                wdot[:, k], tcol[:, k], Ak[:, k], Bk[:, k] = tot
     assert seen_k == set(range(nsp))
     comp = wdot * (mw_avg * rho_inv)[:, None]
     Ak = Ak + comp
@@ -261,27 +279,45 @@ def evaluate(Tb, P, y):
         assert off % RB == 0 and off // RB <= nraw
         return raw[:, off // RB]
 
+    def sp_slot(off):
+        """(species, logical slot) of a byte offset into the species rows; the slot pair of odd
+        species is swapped (plan.sp_even)."""
+        assert off % RB == 0
+        k, chunk = off // SPB, (off % SPB) // RB
+        return k, chunk ^ (k & 1)
+
     def put(eidx, y, extra):
         """dense part of element eidx from the species-row offset / column word y, plus extra."""
         off, col = y & 0xFFFFF, y >> 20
-        assert off % RB == 0
-        sl = off // RB
-        a_, b_ = slots8[:, sl // 8, sl % 8], slots8[:, (sl + 1) // 8, (sl + 1) % 8]
-        assert np.isnan(jac[:, eidx]).all() and eidx == col * nsp + sl // 8 + 1
-        jac[:, eidx] = colfac[col, 0] * a_ + colfac[col, 1] * b_ + extra
+        k, sl = sp_slot(off)
+        k2, sl2 = sp_slot(off ^ RB)
+        assert k2 == k and sl == 4 and sl2 == 5 and col >= 1
+        assert np.isnan(jac[:, eidx]).all() and eidx == col * nsp + k + 1
+        jac[:, eidx] = colfac[col, 0] * slots8[:, k, sl] + colfac[col, 1] * slots8[:, k, sl2] + extra
 
-    d_str = Tb['p5_d_str'].view(np.uint32)
+    d_str, d_item = Tb['p5_d_str'].view(np.uint32), Tb['p5_d_item'].reshape(-1, 2)
     s_str, o_str = Tb['p5_s_str'].view(np.uint32), Tb['p5_o_str'].view(np.uint32)
-    t_str = Tb['p5_t_str'].view(np.uint32)
+    t_str, t_item = Tb['p5_t_str'].view(np.uint32), Tb['p5_t_item'].reshape(-1, 2)
+    tcoop = int(cfg[12])
     for wp in range(nw):
-        # class D: dense-only elements, four steps at a time
-        lo, hi = int(Tb['p5_d_off'][wp]), int(Tb['p5_d_off'][wp + 1])
-        assert (hi - lo) % 4 == 0
-        for st in range(lo, hi):
+        # class D: dense-only elements by row
+        for it in range(int(Tb['p5_d_off'][wp]), int(Tb['p5_d_off'][wp + 1])):
+            u, ncol = int(d_item[it][0]), int(d_item[it][1])
+            assert ncol % 4 == 0
             for sub in range(nsub):
-                eidx, y = int(d_str[(st * nsub + sub) * 2]), int(d_str[(st * nsub + sub) * 2 + 1])
-                if eidx != NULL_E:
-                    put(eidx, y, 0.0)
+                base, e0 = int(d_str[(u * nsub + sub) * 2]), int(d_str[(u * nsub + sub) * 2 + 1])
+                if base == 0xFFFFFFFF:
+                    assert all(int(d_str[((u + 1 + i) * nsub + sub) * 2]) == NULL_E for i in range(ncol))
+                    continue
+                k, sl = sp_slot(base)
+                assert sl == 0 and e0 == k + 1 and np.isnan(jac[:, e0]).all()
+                jac[:, e0] = slots8[:, k, 6]                       # temperature column: W_k * T-term
+                for i in range(ncol):
+                    eidx, col = int(d_str[((u + 1 + i) * nsub + sub) * 2]), int(d_str[((u + 1 + i) * nsub + sub) * 2 + 1])
+                    if eidx == NULL_E:
+                        continue
+                    assert eidx == col * nsp + k + 1 and col >= 1 and np.isnan(jac[:, eidx]).all()
+                    jac[:, eidx] = colfac[col, 0] * slots8[:, k, 4] + colfac[col, 1] * slots8[:, k, 5]
         # class S: two uint4 per element and step, overflow units beyond the first two
         lo, hi = int(Tb['p5_s_off'][wp]), int(Tb['p5_s_off'][wp + 1])
         assert (hi - lo) % 2 == 0
@@ -291,39 +327,46 @@ def evaluate(Tb, P, y):
             B = [s_str[((st * 2 + 1) * nsub + sub) * 4:((st * 2 + 1) * nsub + sub) * 4 + 4] for sub in range(nsub)]
             L = int(A[0][0]) >> 22
             assert all(int(a_[0]) >> 22 == L for a_ in A)
+            n_ovf = (max(L - 2, 0) + 3) // 4 * 4
             for sub in range(nsub):
                 eidx, y = int(A[sub][0]) & 0x3FFFFF, int(A[sub][1])
                 pw_ = A[sub][2:4].copy().view(np.float64)[0]
                 accp = rawrow(int(B[sub][0])) + rawrow(int(B[sub][2]))
                 accm = rawrow(int(B[sub][1])) + rawrow(int(B[sub][3]))
-                for i in range(max(L - 2, 0)):
+                for i in range(n_ovf):
                     accp = accp + rawrow(int(o_str[((ou + i) * nsub + sub) * 2]))
                     accm = accm + rawrow(int(o_str[((ou + i) * nsub + sub) * 2 + 1]))
                 if eidx == NULL_E:
                     assert not accp.any() and not accm.any()
                     continue
                 put(eidx, y, pw_ * (accp - accm))
-            ou += max(L - 2, 0)
+            ou += n_ovf
         assert ou == Tb['p5_o_off'][wp + 1]
-        # class T: energy-equation row, one column per item, list split over the sub-groups
-        u = int(Tb['p5_t_off'][wp])
-        for _ in range(int(Tb['p5_t_n'][wp])):
-            eidx, w1 = int(t_str[u * nsub * 2]), int(t_str[u * nsub * 2 + 1])
-            nun, col = w1 & 0xFFFF, w1 >> 16
-            assert nun % 2 == 0
-            u += 1
-            E0 = np.zeros(n)
+        # class T: energy-equation row, tcoop sub-groups per column
+        for it in range(int(Tb['p5_t_off'][wp]), int(Tb['p5_t_off'][wp + 1])):
+            u, nun = int(t_item[it][0]), int(t_item[it][1])
+            assert nun % 4 == 0
+            part = np.zeros((nsub, n))
+            hdr = [(int(t_str[(u * nsub + sub) * 2]), int(t_str[(u * nsub + sub) * 2 + 1])) for sub in range(nsub)]
             for i in range(nun):
                 for sub in range(nsub):
-                    ro, xo = int(t_str[((u + i) * nsub + sub) * 2]), int(t_str[((u + i) * nsub + sub) * 2 + 1])
+                    ro, xo = int(t_str[((u + 1 + i) * nsub + sub) * 2]), int(t_str[((u + 1 + i) * nsub + sub) * 2 + 1])
                     assert xo % RXB == 0
-                    E0 += RHz[xo // RXB] * rawrow(ro)
-            u += nun
-            assert eidx == col * nsp and np.isnan(jac[:, eidx]).all()
-            pj, qj = colfac[col]
-            jac[:, eidx] = pj * (-wt * HA) + qj * (-wt * HB) + pj * (-wt) * E0 \
-                + XT * (cp[:, col - 1] - cp[:, last])
-        assert u == Tb['p5_t_off'][wp + 1]
+                    part[sub] += RHz[xo // RXB] * rawrow(ro)
+            for g0 in range(0, nsub, tcoop):
+                col, lead = hdr[g0][0] & 0xFFFF, hdr[g0][0] >> 16
+                E0 = part[g0:g0 + tcoop].sum(axis=0)
+                if col == 0:
+                    assert not E0.any() and lead == 0
+                    continue
+                assert lead == 1 and all(hdr[g0 + d][0] == col for d in range(1, tcoop))
+                kcp, slcp = sp_slot(hdr[g0][1])
+                assert kcp == col - 1 and slcp == 7
+                eidx = col * nsp
+                assert np.isnan(jac[:, eidx]).all()
+                pj, qj = colfac[col]
+                jac[:, eidx] = pj * (-wt * HA) + qj * (-wt * HB) + pj * (-wt) * E0 \
+                    + XT * (cp[:, col - 1] - cp[:, last])
     s0 = -wdcp / cp_avg * H1 + SCP + HT * rho
     jac[:, 0] = -s0 / (rho * cp_avg)
     assert not np.isnan(jac).any()

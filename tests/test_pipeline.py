@@ -62,12 +62,22 @@ def test_plan_tables_are_consistent(golden_dir, tmp_path):
         items = T['p5_b_item'][:int(T['p5_b_off'][nw]) * nsub]
         assert sorted(items[items >= 0]) == list(range(nr))
         c_item = T['p5_c_item'].reshape(-1, 4)[:int(T['p5_c_off'][nw])]
-        assert sorted(c_item[:, 0] // (gs * 8 * 8)) == list(range(nsp))
-        d = T['p5_d_str'].view(np.uint32).reshape(-1, 2)[:int(T['p5_d_off'][nw]) * nsub, 0]
+        c_str = T['p5_c_str'].view(np.uint32).reshape(-1, nsub, 2)
+        heads = [int(c_str[int(u), sb, 0]) for u in c_item[:, 0] for sb in range(nsub) if c_str[int(u), sb, 1]]
+        assert sorted(hd // (gs * 8 * 8) for hd in heads) == list(range(nsp))
+        d_str = T['p5_d_str'].view(np.uint32).reshape(-1, nsub, 2)
+        d_elems = []
+        for u, ncol in T['p5_d_item'].reshape(-1, 2)[:int(T['p5_d_off'][nw])]:
+            for sb in range(nsub):
+                if d_str[u, sb, 0] != 0xFFFFFFFF:
+                    d_elems.append(int(d_str[u, sb, 1]))
+                    d_elems += [int(e) for e in d_str[u + 1:u + 1 + ncol, sb, 0] if e != 0x3FFFFF]
         s = T['p5_s_str'].view(np.uint32).reshape(-1, nsub, 4)[:int(T['p5_s_off'][nw]) * 2][0::2, :, 0].ravel() & 0x3FFFFF
-        t = T['p5_t_str'].view(np.uint32)
-        elems = sorted([int(e) for e in d if e != 0x3FFFFF] + [int(e) for e in s if e != 0x3FFFFF])
+        elems = sorted(d_elems + [int(e) for e in s if e != 0x3FFFFF])
         want = sorted(c * nsp + r for c in range(nsp) for r in range(1, nsp))
         assert elems == want
+        t_str = T['p5_t_str'].view(np.uint32).reshape(-1, nsub, 2)
+        t_cols = [int(t_str[u, sb, 0]) & 0xFFFF for u, _ in T['p5_t_item'].reshape(-1, 2)[:int(T['p5_t_off'][nw])]
+                  for sb in range(nsub) if t_str[u, sb, 0] >> 16]
+        assert sorted(t_cols) == list(range(1, nsp))
         assert int(T['p5_cfg'][9]) * 8 <= 232448
-        assert int(T['p5_t_n'].sum()) == nsp - 1 and len(t) > 0

@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Per-warp, per-phase cycle counts of block 0 of k_jacobian (development tool).
+Slots: 0 A1+barrier, 1 B work, 2 B barrier wait, 3 C+barrier, 4 DE work, 5 DE barrier wait."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pyjac_b200.evaluator import Evaluator
+from pyjac_b200.mechanism import Mechanism
+from pyjac_b200.states import synthetic_states
+
+mech = Mechanism.from_chemkin(os.path.join(ROOT, 'tests', 'golden', 'gri30_syn.inp'))
+n = 131072
+P_h, y_h = synthetic_states(mech.NSP, n, seed=0)
+P = torch.tensor(P_h, device='cuda'); y = torch.tensor(y_h, device='cuda').t().contiguous()
+out = torch.empty((mech.NSP ** 2, n), dtype=torch.float64, device='cuda')
+clk = torch.zeros(32 * 8, dtype=torch.int64, device='cuda')
+ev = Evaluator(mech, 0)
+ev.eval_jacob(P, y, out, y_layout='state_fastest', jac_layout='state_fastest')
+os.environ['PYJAC_DEBUG_CLK'] = str(clk.data_ptr())
+ev.eval_jacob(P, y, out, y_layout='state_fastest', jac_layout='state_fastest')
+torch.cuda.synchronize()
+c = clk.cpu().numpy().reshape(32, 8)[:16, :6]
+groups = (n // 8 + 147) // 148
+print('groups per block', groups)
+print('warp   A1   Bwork  Bwait  C     DEwork DEwait   (cycles per group)')
+for w in range(16):
+    print('%3d ' % w + ' '.join('%6d' % (v / groups) for v in c[w]))
+print('sum over phases (warp 0): %d cycles/group' % (c[0].sum() / groups))
