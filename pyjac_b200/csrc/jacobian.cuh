@@ -37,7 +37,7 @@ namespace pj5 {
 using namespace pj;
 
 struct Plan {
-    int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync, coop, tcoop;
+    int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync, coop, tcoop, oCF;
     const int4* rx;
     const int *b_off, *b_npm, *b_item;
     const int* c_off;
@@ -493,7 +493,15 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
     const unsigned aSP = sb + pl.oSP * 8, aRX = sb + pl.oRX * 8, aRAW = sb + pl.oRAW * 8;
     const unsigned aSC0 = sb + pl.oSC * 8, aPA = sb + pl.oPA * 8;
     const unsigned aSD = aSC0 + 2 * SCB;   // scalars derived in phase DE
+    const unsigned aCF = (unsigned)__cvta_generic_to_shared(smem) + pl.oCF * 8;   // column factors, [col][2]
     const V zero{0.0, 0.0};
+
+    // the column factors (848 bytes for 53 species) live in shared memory: they are needed once
+    // per Jacobian element and do not survive in the small L1 next to the streamed tables
+    for (int i = tid; i < nsp; i += blockDim.x) {
+        const double2 c = __ldg(pl.colfac + i);
+        sts<0>(aCF + i * 16, V{c.x, c.y});
+    }
 
     // rows that never change: the empty reaction slot, the zero reaction, the zero raw row
     if (warp == 0 && sub == 0) {
@@ -564,8 +572,14 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
     if (warp == 0 && (long long)blockIdx.x < ngroups) phase_a0(blockIdx.x, 0);
     __syncthreads();
 
-    long long clk[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
+#ifdef PJ_PHASE_CLOCKS
+    long long clk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+#ifdef PJ_PHASE_CLOCKS          // development build only (tools/phase_clocks.py)
 #define PJ_TICK(i) { const long long tn_ = clock64(); clk[i] += tn_ - tprev; tprev = tn_; }
+#else
+#define PJ_TICK(i)
+#endif
     int buf = 0;
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, buf ^= 1) {
         const long long s0 = grp * GS + 2 * pr;           // first state of this lane
@@ -574,8 +588,10 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
         const unsigned aSC = aSC0 + buf * SCB;
         // fast: both states of the lane in range and 16-byte stores possible (all but tail groups)
         const bool fast = vec_ok && ok1;
+        const bool nostore = (io.dbg_skip & 128) != 0;      // timing experiments only
         auto store = [&](unsigned e, V v, bool on) {
             char* o = out0 + (unsigned long long)e * ld8;
+            if (nostore) on = false;
             if (fast) {
                 asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q st.global.v2.f64 [%0], {%1, %2};\n\t}"
                              ::"l"(o), "d"(v.x), "d"(v.y), "r"((int)on) : "memory");
@@ -758,21 +774,30 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
             auto step = [&](const uint4& A, const uint4& B) {
                 const unsigned L = A.x >> 22, e = A.x & NULL_E;
                 const unsigned x = aSP + (A.y & 0xFFFFFu);
-                const double2 cf = __ldg(pl.colfac + (A.y >> 20));
-                V p = vadd(lds<0>(aRAW + B.x), lds<0>(aRAW + B.z)), m = vadd(lds<0>(aRAW + B.y), lds<0>(aRAW + B.w));
+                const V cf = lds<0>(aCF + (A.y >> 20) * 16);
+                // signed entries: byte offset of a raw row | 1 for weight -1; two entries per unit
+                auto sgn = [](unsigned c) { return __hiloint2double((int)(0x3FF00000u | (c << 31)), 0); };
+                V p = vmul(sgn(B.x), lds<0>(aRAW + (B.x & ~1u))), m = vmul(sgn(B.y), lds<0>(aRAW + (B.y & ~1u)));
                 V v = vfma(cf.y, lds<0>(x ^ RB), vmul(cf.x, lds<0>(x)));     // W_k a_k at x, W_k b_k at x ^ RB
-                if (L > 2) {
+                if (L > 1) {
+                    p = vfma(sgn(B.z), lds<0>(aRAW + (B.z & ~1u)), p);
+                    m = vfma(sgn(B.w), lds<0>(aRAW + (B.w & ~1u)), m);
                     // units 3..L come from the overflow stream in batches of four (padded)
 #pragma unroll 1
                     for (unsigned i = 2; i < L; i += 4) {
                         const uint2 c0 = __ldg(ov), c1 = __ldg(ov + NSUB), c2 = __ldg(ov + 2 * NSUB), c3 = __ldg(ov + 3 * NSUB);
-                        prefetch_l1(ov + 8 * NSUB);
                         ov += 4 * NSUB;
-                        p = vadd(p, vadd(vadd(lds<0>(aRAW + c0.x), lds<0>(aRAW + c1.x)), vadd(lds<0>(aRAW + c2.x), lds<0>(aRAW + c3.x))));
-                        m = vadd(m, vadd(vadd(lds<0>(aRAW + c0.y), lds<0>(aRAW + c1.y)), vadd(lds<0>(aRAW + c2.y), lds<0>(aRAW + c3.y))));
+                        p = vfma(sgn(c0.x), lds<0>(aRAW + (c0.x & ~1u)), p);
+                        m = vfma(sgn(c0.y), lds<0>(aRAW + (c0.y & ~1u)), m);
+                        p = vfma(sgn(c1.x), lds<0>(aRAW + (c1.x & ~1u)), p);
+                        m = vfma(sgn(c1.y), lds<0>(aRAW + (c1.y & ~1u)), m);
+                        p = vfma(sgn(c2.x), lds<0>(aRAW + (c2.x & ~1u)), p);
+                        m = vfma(sgn(c2.y), lds<0>(aRAW + (c2.y & ~1u)), m);
+                        p = vfma(sgn(c3.x), lds<0>(aRAW + (c3.x & ~1u)), p);
+                        m = vfma(sgn(c3.y), lds<0>(aRAW + (c3.y & ~1u)), m);
                     }
                 }
-                v = vfma(__hiloint2double((int)A.w, (int)A.z), vsub(p, m), v);
+                v = vfma(__hiloint2double((int)A.w, (int)A.z), vadd(p, m), v);
                 store(e, v, e != NULL_E);
             };
             // four bundles rotate through registers; every bundle is fetched two steps ahead
@@ -789,6 +814,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 step(A3, B3);
             }
         }
+        PJ_TICK(4)
         if (!(io.dbg_skip & 16)) {
             // class D: dense-only elements by row.  A sub-group keeps W_k a_k, W_k b_k of its row
             // in registers and walks the row's dense-only columns, four in flight.
@@ -800,22 +826,30 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 const bool on = hd.x != 0xFFFFFFFFu;
                 const unsigned x = aSP + (on ? hd.x : 0u);
                 const V wa = lds<E_WA * RB>(x), wb = lds<O_WB * RB>(x ^ RB);
-                store(hd.y, lds<E_WT * RB>(x), on);                    // temperature column: W_k * T-term
-                uint2 nx[4];
+                store(hd.y, lds<E_WT * RB>(x), on && hd.y != NULL_E);  // temperature column: W_k * T-term
+                // units are fetched LA batches of four ahead (the tables come from L2: with all of
+                // shared memory in use there is no L1 to speak of)
+                constexpr int LA = 1;
+                uint2 nx[4 * LA];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) nx[j] = __ldg(dp + (1 + j) * NSUB);
+                for (int j = 0; j < 4 * LA; ++j) nx[j] = __ldg(dp + (1 + j) * NSUB);
                 for (int c = 0; c < di.y; c += 4) {
                     uint2 r[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { r[j] = nx[j]; nx[j] = __ldg(dp + (5 + c + j) * NSUB); }
-                    double2 cf[4];
+                    for (int j = 0; j < 4; ++j) r[j] = nx[j];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) cf[j] = __ldg(pl.colfac + r[j].y);
+                    for (int j = 0; j < 4 * (LA - 1); ++j) nx[j] = nx[j + 4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) nx[4 * (LA - 1) + j] = __ldg(dp + (1 + 4 * LA + c + j) * NSUB);
+                    V cf[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cf[j] = lds<0>(aCF + r[j].y * 16);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) store(r[j].x, vfma(cf[j].y, wb, vmul(cf[j].x, wa)), r[j].x != NULL_E);
                 }
             }
         }
+        PJ_TICK(5)
         if (!(io.dbg_skip & 32)) {
             // class T, the energy-equation row (cj:3095-3254): per column an enthalpy-weighted
             // gather; pl.tcoop sub-groups share a column, units come four at a time
@@ -847,7 +881,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                     for (int o = NPR; o < NPR * pl.tcoop; o <<= 1)
                         E0 = V{E0.x + __shfl_xor_sync(0xffffffffu, E0.x, o), E0.y + __shfl_xor_sync(0xffffffffu, E0.y, o)};
                     const unsigned col = hd.x & 0xFFFFu;
-                    const double2 cf = __ldg(pl.colfac + col);
+                    const V cf = lds<0>(aCF + col * 16);
                     const V cpj = lds<0>(aSP + hd.y);
                     V v = vmul(cf.x, vfma(nwt, E0, A0));
                     v = vfma(cf.y, B0, v);
@@ -856,13 +890,15 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 }
             }
         }
-        PJ_TICK(4)
+        PJ_TICK(6)
         __syncthreads();
-        PJ_TICK(5)
+        PJ_TICK(7)
     }
 #undef PJ_TICK
+#ifdef PJ_PHASE_CLOCKS
     if (io.dbg_clk && blockIdx.x == 0 && lane == 0)
-        for (int i = 0; i < 6; ++i) io.dbg_clk[warp * 8 + i] = clk[i];
+        for (int i = 0; i < 8; ++i) io.dbg_clk[warp * 8 + i] = clk[i];
+#endif
 }
 
 }  // namespace pj5

@@ -322,12 +322,12 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     UP(tb.red_rx, "red_rx", int, 1); UP(tb.red_nu, "red_nu", double, 0);
     if (!rc) {
         const pjt::Entry* pe = pjt::find(blob, "p5_cfg");
-        if (!pe || pe->dtype != 1 || pe->count < 13) rc = fail(PYJAC_EINVAL, "table blob lacks p5_cfg");
+        if (!pe || pe->dtype != 1 || pe->count < 14) rc = fail(PYJAC_EINVAL, "table blob lacks p5_cfg");
         else {
             const int* c5 = (const int*)((const char*)blob + pe->offset);
             pj5::Plan& pl = m->plan;
             int* o = &pl.gs;
-            for (int i = 0; i < 13; ++i) o[i] = c5[i];
+            for (int i = 0; i < 14; ++i) o[i] = c5[i];
             if (!jac_kernel(pl.gs) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 1024 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
                 rc = fail(PYJAC_EINVAL, "bad Jacobian plan configuration");
         }

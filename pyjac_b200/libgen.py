@@ -48,6 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC,
                                     '-o', LIB_PATH, os.path.join(CSRC, 'pyjac_b200.cu')]
+    cmd[1:1] = os.environ.get('PYJAC_B200_NVCC_EXTRA', '').split()      # development builds
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

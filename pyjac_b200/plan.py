@@ -42,10 +42,13 @@ COST_PLAIN, COST_IRREV, COST_THREE = 215.0, 150.0, 40.0
 COST_PM = {'thd': 300.0, 'lind': 450.0, 'troe': 900.0, 'sri': 1200.0}
 COST_EFF = 8.0
 COST_C_ITEM, COST_C_IT = 90.0, 28.0
-COST_S_STEP, COST_S_OVF = 40.0, 25.0
-COST_D_ITEM, COST_D_COL = 50.0, 10.0
-COST_T_ITEM, COST_T_IT = 80.0, 8.0
-COST_DOTS = 400.0            # warp 0: energy-equation scalars + the next group's phase A0
+# phase DE costs are in units of 22 cycles, fitted to per-warp clock measurements on a B200
+# (tools/phase_clocks.py): the classes are bound by shared-memory / L2 latency, not by issue
+COST_S_STEP, COST_S_OVF = 40.0, 11.0
+COST_D_ITEM, COST_D_COL = 45.0, 12.0
+COST_T_ITEM, COST_T_IT = 130.0, 11.0
+D_MAX_COLS = 24              # a row with more dense-only columns is cut into several items
+COST_DOTS = 270.0            # warp 0: energy-equation scalars + the next group's phase A0
 
 
 def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:
@@ -64,6 +67,7 @@ def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:
     take('RAW', nraw + 2)                # row nraw: zero (null contributions); nraw + 1: scratch
     take('SC', NSCAL)
     take('PA', nw * NPART)
+    take('CF', -(-2 * nsp // gs))        # per column (1/W_j, (1/W_j)(W_j/W_N)) as plain doubles
     L['total'] = off
     return L
 
@@ -239,34 +243,36 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
     zr = nraw * RB
     null_sp = sp_even(0) + SLOT_WA * RB
 
+    # signed entry = byte offset of a raw row | 1 if its weight is -1 (offsets are multiples of 16)
     elems = []
     for col in range(1, nsp):
         for k in range(last):
             plus, minus = expand(contrib.get((k, col - 1), []))
-            elems.append((max(len(plus), len(minus)), col, k, plus, minus))
+            ent = [x * RB for x in plus] + [(x * RB) | 1 for x in minus]
+            ent.sort(key=lambda v: v & ~1)
+            elems.append(((len(ent) + 1) // 2, col, k, ent))
     sparse = sorted((e for e in elems if e[0] > 0), key=lambda e: (-e[0], e[1], e[2]))
 
     s_steps = []                               # (A words, B words, overflow units, L)
     for c0 in range(0, len(sparse), nsub):
         grp = sparse[c0:c0 + nsub]
-        L = grp[0][0]
+        L = grp[0][0]                          # units of two entries
         if L > MAX_L2:
             raise ValueError('sparse Jacobian element with too many contributions')
         n_ovf = (max(L - 2, 0) + 3) // 4 * 4              # overflow units come in batches of four
         A, B, ovf = [], [], [[] for _ in range(n_ovf)]
         for sb in range(nsub):
             if sb < len(grp):
-                _, col, k, plus, minus = grp[sb]
+                _, col, k, ent = grp[sb]
                 A.append([(col * nsp + k + 1) | (L << 22), (sp_even(k) + SLOT_WA * RB) | (col << 20)]
                          + _f64_words(sp_iw[col - 1] * sp_w[k]))
             else:
-                plus, minus = [], []
+                ent = []
                 A.append([NULL_E | (L << 22), null_sp, 0, 0])
-            po = [x * RB for x in plus] + [zr] * (n_ovf + 2 - len(plus))
-            mo = [x * RB for x in minus] + [zr] * (n_ovf + 2 - len(minus))
-            B.append([po[0], mo[0], po[1], mo[1]])
-            for i in range(2, n_ovf + 2):
-                ovf[i - 2].append([po[i], mo[i]])
+            pe = ent + [zr] * (2 * (n_ovf + 2) - len(ent))
+            B.append(pe[:4])
+            for i in range(n_ovf):
+                ovf[i].append(pe[4 + 2 * i:6 + 2 * i])
         s_steps.append((A, B, ovf, L))
     null_s = ([[NULL_E, null_sp, 0, 0]] * nsub, [[zr] * 4] * nsub, [], 0)
     s_pairs = []
@@ -276,15 +282,19 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
 
     # D: rows sorted by their number of dense-only columns, NSUB rows per item
     sparse_set = {(e[1], e[2]) for e in sparse}
-    d_rows = sorted(((k, [col for col in range(1, nsp) if (col, k) not in sparse_set]) for k in range(last)),
-                    key=lambda r: (-len(r[1]), r[0]))
+    d_rows = []                                # (row, its dense-only columns, owns the temperature column)
+    for k in range(last):
+        cols = [col for col in range(1, nsp) if (col, k) not in sparse_set]
+        parts = [cols[c0:c0 + D_MAX_COLS] for c0 in range(0, len(cols), D_MAX_COLS)] or [[]]
+        d_rows += [(k, part, i == 0) for i, part in enumerate(parts)]
+    d_rows.sort(key=lambda r: (-len(r[1]), r[0]))
     d_items = []
     for c0 in range(0, len(d_rows), nsub):
         grp = d_rows[c0:c0 + nsub]
         n = (len(grp[0][1]) + 3) // 4 * 4                  # columns come in batches of four
-        units = [[[sp_even(k), k + 1] for k, _ in grp] + [[NONE32, NULL_E]] * (nsub - len(grp))]
+        units = [[[sp_even(k), k + 1 if own else NULL_E] for k, _, own in grp] + [[NONE32, NULL_E]] * (nsub - len(grp))]
         for u in range(n):
-            units.append([[cols[u] * nsp + k + 1, cols[u]] if u < len(cols) else [NULL_E, 0] for k, cols in grp]
+            units.append([[cols[u] * nsp + k + 1, cols[u]] if u < len(cols) else [NULL_E, 0] for k, cols, _ in grp]
                          + [[NULL_E, 0]] * (nsub - len(grp)))
         d_items.append((n, units))
 
@@ -373,6 +383,6 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
     # dot products) and every other warp that owns such steps (waits)
     waiters = sum(1 for w in range(1, nw) if t_nst[w])
     t_sync = 32 * (waiters + 1) if waiters else 0
-    P['p5_cfg'] = i32([gs, nt, nw, nsub, L['SP'], L['RX'], L['RAW'], L['SC'], L['PA'], L['total'], t_sync, coop, tcoop]
-                      + [0] * 3)
+    P['p5_cfg'] = i32([gs, nt, nw, nsub, L['SP'], L['RX'], L['RAW'], L['SC'], L['PA'], L['total'], t_sync, coop, tcoop, L['CF']]
+                      + [0] * 2)
     return P

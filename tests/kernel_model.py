@@ -310,8 +310,10 @@ def evaluate(Tb, P, y):
                     assert all(int(d_str[((u + 1 + i) * nsub + sub) * 2]) == NULL_E for i in range(ncol))
                     continue
                 k, sl = sp_slot(base)
-                assert sl == 0 and e0 == k + 1 and np.isnan(jac[:, e0]).all()
-                jac[:, e0] = slots8[:, k, 6]                       # temperature column: W_k * T-term
+                assert sl == 0 and e0 in (k + 1, NULL_E)
+                if e0 != NULL_E:                                   # temperature column: W_k * T-term
+                    assert np.isnan(jac[:, e0]).all()
+                    jac[:, e0] = slots8[:, k, 6]
                 for i in range(ncol):
                     eidx, col = int(d_str[((u + 1 + i) * nsub + sub) * 2]), int(d_str[((u + 1 + i) * nsub + sub) * 2 + 1])
                     if eidx == NULL_E:
@@ -331,15 +333,18 @@ def evaluate(Tb, P, y):
             for sub in range(nsub):
                 eidx, y = int(A[sub][0]) & 0x3FFFFF, int(A[sub][1])
                 pw_ = A[sub][2:4].copy().view(np.float64)[0]
-                accp = rawrow(int(B[sub][0])) + rawrow(int(B[sub][2]))
-                accm = rawrow(int(B[sub][1])) + rawrow(int(B[sub][3]))
+                acc = np.zeros(n)
+                ents = [int(v) for v in B[sub]]
                 for i in range(n_ovf):
-                    accp = accp + rawrow(int(o_str[((ou + i) * nsub + sub) * 2]))
-                    accm = accm + rawrow(int(o_str[((ou + i) * nsub + sub) * 2 + 1]))
+                    ents += [int(o_str[((ou + i) * nsub + sub) * 2]), int(o_str[((ou + i) * nsub + sub) * 2 + 1])]
+                for c in ents:
+                    acc = acc + (-1.0 if c & 1 else 1.0) * rawrow(c & ~1)
+                if L == 1:
+                    assert ents[2] == nraw * RB and ents[3] == nraw * RB
                 if eidx == NULL_E:
-                    assert not accp.any() and not accm.any()
+                    assert not acc.any()
                     continue
-                put(eidx, y, pw_ * (accp - accm))
+                put(eidx, y, pw_ * acc)
             ou += n_ovf
         assert ou == Tb['p5_o_off'][wp + 1]
         # class T: energy-equation row, tcoop sub-groups per column

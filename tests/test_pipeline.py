@@ -70,7 +70,8 @@ def test_plan_tables_are_consistent(golden_dir, tmp_path):
         for u, ncol in T['p5_d_item'].reshape(-1, 2)[:int(T['p5_d_off'][nw])]:
             for sb in range(nsub):
                 if d_str[u, sb, 0] != 0xFFFFFFFF:
-                    d_elems.append(int(d_str[u, sb, 1]))
+                    if d_str[u, sb, 1] != 0x3FFFFF:
+                        d_elems.append(int(d_str[u, sb, 1]))
                     d_elems += [int(e) for e in d_str[u + 1:u + 1 + ncol, sb, 0] if e != 0x3FFFFF]
         s = T['p5_s_str'].view(np.uint32).reshape(-1, nsub, 4)[:int(T['p5_s_off'][nw]) * 2][0::2, :, 0].ravel() & 0x3FFFFF
         elems = sorted(d_elems + [int(e) for e in s if e != 0x3FFFFF])

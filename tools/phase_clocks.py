@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Per-warp, per-phase cycle counts of block 0 of k_jacobian (development tool).
-Slots: 0 A1+barrier, 1 B work, 2 B barrier wait, 3 C+barrier, 4 DE work, 5 DE barrier wait."""
+Slots (a clock read may be scheduled before the barrier that precedes it, so a slot holds the
+warp's own work plus the wait at the previous barrier): 0 A1, 1 B, 2 -, 3 C, 4 dots/A0 + class S,
+5 class D, 6 class T, 7 -."""
 import os, sys
+os.environ['PYJAC_B200_NVCC_EXTRA'] = '-DPJ_PHASE_CLOCKS'     # instrumented build (set before the library is built)
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,15 +18,17 @@ P_h, y_h = synthetic_states(mech.NSP, n, seed=0)
 P = torch.tensor(P_h, device='cuda'); y = torch.tensor(y_h, device='cuda').t().contiguous()
 out = torch.empty((mech.NSP ** 2, n), dtype=torch.float64, device='cuda')
 clk = torch.zeros(32 * 8, dtype=torch.int64, device='cuda')
+from pyjac_b200 import libgen
+libgen.build_library(force=True)
 ev = Evaluator(mech, 0)
 ev.eval_jacob(P, y, out, y_layout='state_fastest', jac_layout='state_fastest')
 os.environ['PYJAC_DEBUG_CLK'] = str(clk.data_ptr())
 ev.eval_jacob(P, y, out, y_layout='state_fastest', jac_layout='state_fastest')
 torch.cuda.synchronize()
-c = clk.cpu().numpy().reshape(32, 8)[:16, :6]
+c = clk.cpu().numpy().reshape(32, 8)[:16, :8]
 groups = (n // 8 + 147) // 148
 print('groups per block', groups)
-print('warp   A1   Bwork  Bwait  C     DEwork DEwait   (cycles per group)')
+print('warp   A1     B      -      C      S      D      T      -    (cycles per group)')
 for w in range(16):
     print('%3d ' % w + ' '.join('%6d' % (v / groups) for v in c[w]))
 print('sum over phases (warp 0): %d cycles/group' % (c[0].sum() / groups))
