@@ -39,6 +39,8 @@ using namespace pj;
 struct Plan {
     int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync, coop, tcoop, oCF;
     const int4* rx;
+    const int* eff_off;
+    const int4* eff;
     const int *b_off, *b_npm, *b_item;
     const int* c_off;
     const int4* c_item;
@@ -194,9 +196,15 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsig
     bool rates_done = false;
     if (PM) {
         V thd = lds<Q_M * RB>(aSC);
-        const int e0 = __ldg(tb.pm_eff_off + mi), e1_ = __ldg(tb.pm_eff_off + mi + 1);
-        for (int e = e0; e < e1_; ++e)
-            thd = vfma(__ldg(tb.pm_eff_am1 + e), lds<E_C * RB>(sp_even<GS>(aSP, (unsigned)__ldg(tb.pm_eff_sp + e))), thd);
+        // collider records {alpha - 1, species row offset, raw row}, four at a time (padded)
+        const int e0 = __ldg(pl.eff_off + mi), e1_ = __ldg(pl.eff_off + mi + 1);
+        for (int e = e0; e < e1_; e += 4) {
+            const int4 r0 = __ldg(pl.eff + e), r1 = __ldg(pl.eff + e + 1), r2 = __ldg(pl.eff + e + 2), r3 = __ldg(pl.eff + e + 3);
+            thd = vfma(__hiloint2double(r0.y, r0.x), lds<E_C * RB>(aSP + r0.z), thd);
+            thd = vfma(__hiloint2double(r1.y, r1.x), lds<E_C * RB>(aSP + r1.z), thd);
+            thd = vfma(__hiloint2double(r2.y, r2.x), lds<E_C * RB>(aSP + r2.z), thd);
+            thd = vfma(__hiloint2double(r3.y, r3.x), lds<E_C * RB>(aSP + r3.z), thd);
+        }
         if (fl & F_PDEP) {
             const int csp = __ldg(tb.pm_sp + mi);
             const V ctv = csp >= 0 ? lds<E_C * RB>(sp_even<GS>(aSP, (unsigned)csp)) : thd;
@@ -371,13 +379,14 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsig
 #undef PJ_EMIT
     if (PM && valid) {
         if (fl & F_EFF_SLOTS) {
-            unsigned rb = q3.w & 0xFFFFu;
-            const int e0 = __ldg(tb.pm_eff_off + mi), e1_ = __ldg(tb.pm_eff_off + mi + 1);
-            for (int e = e0; e < e1_; ++e)
-                if (__ldg(tb.pm_eff_sp + e) != last) {
-                    sts<0>(aRAW + rb * RB, vmul(__ldg(tb.pm_eff_am1 + e), pmt));
-                    ++rb;
-                }
+            const int e0 = __ldg(pl.eff_off + mi), e1_ = __ldg(pl.eff_off + mi + 1);
+            for (int e = e0; e < e1_; e += 4) {
+                const int4 r0 = __ldg(pl.eff + e), r1 = __ldg(pl.eff + e + 1), r2 = __ldg(pl.eff + e + 2), r3 = __ldg(pl.eff + e + 3);
+                sts<0>(aRAW + r0.w * RB, vmul(__hiloint2double(r0.y, r0.x), pmt));
+                sts<0>(aRAW + r1.w * RB, vmul(__hiloint2double(r1.y, r1.x), pmt));
+                sts<0>(aRAW + r2.w * RB, vmul(__hiloint2double(r2.y, r2.x), pmt));
+                sts<0>(aRAW + r3.w * RB, vmul(__hiloint2double(r3.y, r3.x), pmt));
+            }
         }
         if (fl & F_WANT_PMT) sts<0>(aRAW + ((unsigned)q3.w >> 16) * RB, pmt);
     }

@@ -332,7 +332,7 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
                 rc = fail(PYJAC_EINVAL, "bad Jacobian plan configuration");
         }
     }
-    UP(plan.rx, "p5_rx", int4, 1);
+    UP(plan.rx, "p5_rx", int4, 1); UP(plan.eff_off, "p5_eff_off", int, 1); UP(plan.eff, "p5_eff", int4, 1);
     UP(plan.b_off, "p5_b_off", int, 1); UP(plan.b_npm, "p5_b_npm", int, 1); UP(plan.b_item, "p5_b_item", int, 1);
     UP(plan.c_off, "p5_c_off", int, 1); UP(plan.c_item, "p5_c_item", int4, 1); UP(plan.c_str, "p5_c_str", uint2, 1);
     UP(plan.d_off, "p5_d_off", int, 1); UP(plan.d_item, "p5_d_item", int2, 1); UP(plan.d_str, "p5_d_str", uint2, 1);

@@ -596,6 +596,29 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
         if any(int(sl) == last for sl in slots[p]):
             rec5[p, 8] |= F_HAS_LAST
     T['p5_rx'] = rec5.ravel()
+    # collider lists of the Jacobian kernel: per pressure-modified reaction a list padded to a
+    # multiple of four records {alpha - 1 (double), byte offset of the collider's species row,
+    # raw row that receives pres_mod_temp * (alpha - 1)}; padding: alpha - 1 = 0, empty species
+    # slot, scratch raw row.  Four records are fetched at a time.
+    spb_ = plan.SP_SLOTS * gs_ * 8
+    sp_off = lambda k: k * spb_ + (k & 1) * gs_ * 8
+    eff4, eff4_off = [], [0]
+    for p in range(first_pm, nr):
+        i = order[p]
+        m = p - first_pm
+        recs = []
+        for e in range(eff_off[m], eff_off[m + 1]):
+            sp_, am1 = eff_sp[e], eff_am1[e]
+            dst = raw_of_eff[i].get(sp_, nraw + 1) if eff_case(reacs[i]) else nraw + 1
+            lohi = np.array([am1], dtype=np.float64).view(np.int32)
+            recs.append([int(lohi[0]), int(lohi[1]), sp_off(sp_), dst])
+        while len(recs) % 4:
+            recs.append([0, 0, sp_off(nsp), nraw + 1])
+        for r_ in recs:
+            eff4 += r_
+        eff4_off.append(len(eff4) // 4)
+    T['p5_eff_off'] = i32(eff4_off if npm else [0, 0])
+    T['p5_eff'] = i32(eff4 + [0, 0, sp_off(nsp), nraw + 1] * 4)
 
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
     T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, nsub, len(con), 0,
