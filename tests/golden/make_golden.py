@@ -10,6 +10,8 @@ evaluates the emitted C on fixed states and stores inputs and outputs:
                                    functional_tester/test.py:1254-1258)
     tests/golden/torture_pasr.npz  branch-coverage mechanism, every 4th of those states
     tests/golden/gri30_syn.npz     GRI-3.0-shaped synthetic mechanism, 48 synthetic states
+    tests/golden/usc2_syn.npz      USC-Mech-II-shaped synthetic mechanism (111 sp / 784 rxn, species with
+                                   different T_mid), 8 synthetic states
 
 Arrays are in pyJac's internal (moved-last) species order, row-major per state:
 P[n], y[n,NSP] = [T, Y_0..Y_{NSP-2}], conc, fwd, rev, pres_mod, spec_rates, dydt, jac[n,NSP*NSP]
@@ -60,3 +62,9 @@ if __name__ == '__main__':
     mech = Mechanism.from_chemkin(gri)
     P, y = synthetic_states(mech.NSP, 48, seed=0)
     dump('gri30', gri, P, y, 'gri30_syn.npz')
+
+    usc = os.path.join(HERE, 'usc2_syn.inp')
+    synth.write('usc2', usc, seed=0)
+    mech = Mechanism.from_chemkin(usc)
+    P, y = synthetic_states(mech.NSP, 8, seed=7)
+    dump('usc2', usc, P, y, 'usc2_syn.npz')

@@ -12,7 +12,7 @@ from pyjac_b200.states import synthetic_states
 pytestmark = pytest.mark.gpu
 
 CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz'), ('torture.inp', 'torture_pasr.npz'),
-         ('gri30_syn.inp', 'gri30_syn.npz')]
+         ('gri30_syn.inp', 'gri30_syn.npz'), ('usc2_syn.inp', 'usc2_syn.npz')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 
