@@ -64,9 +64,10 @@ void pyjac_mech_destroy(pyjac_mech* m);
 /* dims[0..3] = NSP, FWD_RATES, REV_RATES, PRES_MOD_RATES (the mechanism.h macros,
  * mech_auxiliary.py:109-176) */
 int pyjac_mech_dims(const pyjac_mech* m, int dims[4]);
-/* Launch tuning: states per thread block (1, 2 or 4), threads per block, blocks per SM
- * (0 = keep automatic choice).  Results do not depend on these. */
-int pyjac_mech_tune(pyjac_mech* m, int states_per_block, int threads, int blocks_per_sm);
+/* Launch tuning: cap on resident thread blocks per SM (0 = automatic).  States per block and
+ * block size belong to the plan inside the table blob (pyjac_b200/plan.py).  Results do not
+ * depend on this. */
+int pyjac_mech_tune(pyjac_mech* m, int blocks_per_sm);
 /* number of kernels launched through this handle since creation */
 long long pyjac_mech_launches(const pyjac_mech* m);
 

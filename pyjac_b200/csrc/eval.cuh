@@ -30,7 +30,7 @@
 //       weighted gathers) runs after the species rows, behind a named barrier that only the
 //       warps owning such elements wait on.
 #pragma once
-#include "kernels.cuh"
+#include "common.cuh"
 
 namespace pj5 {
 
@@ -39,6 +39,7 @@ using namespace pj;
 struct Plan {
     int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync, coop, tcoop, oCF;
     const int4* rx;
+    const int4* rx_out;              // {fwd index, rev index or -1, pres_mod index or -1, 0} (M_RATES)
     const int* eff_off;
     const int4* eff;
     const int *b_off, *b_npm, *b_item;
@@ -70,7 +71,6 @@ enum : int { D_H1 = 0, D_HA, D_HB, D_HT, D_SCP, D_CPAVG, D_WDCP, NPART = 7 };
 enum : int { SP_SLOTS = 8, E_C = 0, E_DB = 2, E_WA = 4, E_WT = 6, O_B = 0, O_HW = 2, O_WB = 4, O_CP = 6, E_Y = E_C };
 enum : int { RX_NET = 0, RX_TT, RX_X1, RX_X2, RX_DH, RX_SLOTS };
 enum : unsigned { NULL_E = 0x3FFFFFu };
-enum : int { F_HAS_LAST = 1 << 13 };    // some occupied slot of the reaction holds the last species
 
 struct V {
     double x, y;
@@ -149,8 +149,20 @@ template <int GS>
 __device__ __forceinline__ V sub_sum(V v) { return V{sub_sum<GS>(v.x), sub_sum<GS>(v.y)}; }
 
 // Everything phase B does for one reaction and the two states of the lane.
-template <int GS, bool PM>
-__device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsigned aSP, unsigned aRX,
+// states of the lane that exist (tail group) and where the M_RATES outputs go
+struct Out {
+    long long s0;
+    bool ok0, ok1;
+};
+__device__ __forceinline__ void put2(double* base, const IO& io, int width, const Out& o, int v, V x)
+{
+    if (o.ok0) put(base, io, width, o.s0, v, x.x);
+    if (o.ok1) put(base, io, width, o.s0 + 1, v, x.y);
+}
+
+template <int GS, bool PM, int MODE>
+__device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const IO& io, const Out& out,
+                                         unsigned aSP, unsigned aRX,
                                          unsigned aRAW, unsigned aSC, int p, bool valid, bool three,
                                          const V T, const V logT, const V iT)
 {
@@ -311,6 +323,17 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsig
     V f = vmul(kf, vmul(c0, c1)), r = vmul(kr, vmul(c3, c4));
     if (three) { f = vmul(f, c2); r = vmul(r, c5); }
     const V net = vsub(f, r);
+    if (MODE == M_RATES && valid) {
+        const int4 ro = __ldg(pl.rx_out + p);
+        if (io.fwd) put2(io.fwd, io, tb.nr, out, ro.x, f);
+        if (io.rev && isrev) put2(io.rev, io, tb.nrev, out, ro.y, r);
+        if (PM && io.pm) put2(io.pm, io, tb.npd, out, ro.z, PM_);
+    }
+    if (MODE != M_JAC) {
+        // only the net rate is needed for the species rates
+        sts_if<RX_NET * RB>(valid, aRX + p * RXB, PM ? vmul(net, PM_) : net);
+        return;
+    }
     V pmt{0.0, 0.0};
     if (PM && (fl & F_PMT)) pmt = vmul(gg, net);
 
@@ -402,8 +425,9 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, unsig
 
 // Phase B for one reaction without pressure modification (the common case) and the two states
 // of the lane: no branches except `three` (warp-uniform) and the rare last-species fold.
-template <int GS>
-__device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl, unsigned aSP, unsigned aRX,
+template <int GS, int MODE>
+__device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl, const IO& io, const Out& out,
+                                               unsigned aSP, unsigned aRX,
                                                unsigned aRAW, unsigned aSC, int p, bool valid, bool three,
                                                const V T, const V logT, const V iT)
 {
@@ -442,6 +466,15 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     const V d0 = vmul(kf, o0), d1 = vmul(kf, o1), d3 = vmul(kr, o3), d4 = vmul(kr, o4);
     const V f = vmul(d0, c0), r = vmul(d3, c3);
     const V net = vsub(f, r);
+    if (MODE == M_RATES && valid) {
+        const int4 ro = __ldg(pl.rx_out + p);
+        if (io.fwd) put2(io.fwd, io, tb.nr, out, ro.x, f);
+        if (io.rev && isrev) put2(io.rev, io, tb.nrev, out, ro.y, r);
+    }
+    if (MODE != M_JAC) {
+        sts_if<RX_NET * RB>(valid, aRX + p * RXB, net);
+        return;
+    }
     const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
     const double omre = 1.0 - nre, ompr = 1.0 - npr;
     const V rho_inv = lds<Q_RHOINV * RB>(aSC), nmwr = lds<Q_NMWR * RB>(aSC);
@@ -483,9 +516,9 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     sts_if<RX_DH * RB>(valid, ar, dH);
 }
 
-template <int GS, int MAXT>
+template <int GS, int MAXT, int MODE>
 __global__ void __launch_bounds__(MAXT, 1)
-k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const __grid_constant__ IO io)
+k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const __grid_constant__ IO io)
 {
     extern __shared__ __align__(16) double smem[];
     constexpr int NSUB = 64 / GS;          // table items a warp works on at the same time
@@ -540,12 +573,15 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
         const long long i0 = s0 < io.n ? s0 : (long long)io.n - 1, i1 = s0 + 1 < io.n ? s0 + 1 : (long long)io.n - 1;
         const double* y0 = io.y + i0 * io.y_ss;
         const double* y1 = io.y + i1 * io.y_ss;
+        // in_conc (eval_rxn_rates / get_rxn_pres_mod entry points): the row holds T and all NSP
+        // concentrations; rho = sum C_k W_k, mw_avg = rho / sum C_k
+        const bool inc = MODE == M_RATES && io.in_conc;
         V sumY = zero, sumYW = zero;
-        for (int k = sub; k < last; k += NSUB) {
+        for (int k = sub; k < (inc ? nsp : last); k += NSUB) {
             const V Yk{y0[(long long)(k + 1) * io.y_sv], y1[(long long)(k + 1) * io.y_sv]};
             sts<E_Y * RB>(sp_even<GS>(aSP, (unsigned)k), Yk);
             sumY = vadd(sumY, Yk);
-            sumYW = vfma(__ldg(tb.sp_iw + k), Yk, sumYW);
+            sumYW = vfma(__ldg((inc ? tb.sp_w : tb.sp_iw) + k), Yk, sumYW);
         }
         sumY = sub_sum<GS>(sumY);
         sumYW = sub_sum<GS>(sumYW);
@@ -553,20 +589,24 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
             const double T[2] = {y0[0], y1[0]};
             const double P[2] = {io.pres[i0], io.pres[i1]};
             const double yN[2] = {1.0 - sumY.x, 1.0 - sumY.y};
-            const double sw[2] = {sumYW.x, sumYW.y};
+            const double sw[2] = {sumYW.x, sumYW.y}, sy[2] = {sumY.x, sumY.y};
             double o[8][2];
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
-                const double mw = 1.0 / (sw[g2] + yN[g2] * __ldg(tb.sp_iw + last));
-                const double rho = P[g2] * mw / (tb.ru * T[g2]);
+                const double mw = inc ? sw[g2] / sy[g2] : 1.0 / (sw[g2] + yN[g2] * __ldg(tb.sp_iw + last));
+                const double rho = inc ? sw[g2] : P[g2] * mw / (tb.ru * T[g2]);
                 const double rho_inv = 1.0 / rho;
+                if (MODE == M_RATES && io.scal3 && (g2 ? s0 + 1 : s0) < io.n) {
+                    double* q = io.scal3 + (g2 ? s0 + 1 : s0) * 3;
+                    q[0] = yN[g2]; q[1] = mw; q[2] = rho;
+                }
                 o[Q_T][g2] = T[g2]; o[Q_LOGT][g2] = log(T[g2]); o[Q_IT][g2] = 1.0 / T[g2];
                 o[Q_RHO][g2] = rho; o[Q_RHOINV][g2] = rho_inv;
                 o[Q_NMWR][g2] = -mw * rho_inv; o[Q_MWR][g2] = mw * rho_inv;
                 o[Q_M][g2] = P[g2] / (tb.ru * T[g2]);
             }
             const unsigned a = aSC0 + b * SCB;
-            sts<E_Y * RB>(sp_even<GS>(aSP, (unsigned)last), V{yN[0], yN[1]});
+            if (!inc) sts<E_Y * RB>(sp_even<GS>(aSP, (unsigned)last), V{yN[0], yN[1]});
             sts<Q_T * RB>(a, V{o[Q_T][0], o[Q_T][1]});
             sts<Q_LOGT * RB>(a, V{o[Q_LOGT][0], o[Q_LOGT][1]});
             sts<Q_IT * RB>(a, V{o[Q_IT][0], o[Q_IT][1]});
@@ -593,6 +633,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, buf ^= 1) {
         const long long s0 = grp * GS + 2 * pr;           // first state of this lane
         const bool ok0 = s0 < io.n, ok1 = s0 + 1 < io.n;
+        const Out out{s0, ok0, ok1};
         char* const out0 = reinterpret_cast<char*>(sf ? io.jac + s0 : io.jac + s0 * nn);
         const unsigned aSC = aSC0 + buf * SCB;
         // fast: both states of the lane in range and 16-byte stores possible (all but tail groups)
@@ -619,15 +660,16 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
             for (int k = warp * NSUB + sub; k < nsp; k += nw * NSUB) {
                 const unsigned a = sp_even<GS>(aSP, (unsigned)k), o = a ^ RB;
                 const V Yv = lds<E_Y * RB>(a);
-                const double Yk[2] = {Yv.x, Yv.y};
                 const double iw = __ldg(tb.sp_iw + k), ruw = __ldg(tb.sp_ruw + k), wk = __ldg(tb.sp_w + k);
+                const bool inc = MODE == M_RATES && io.in_conc;       // the slot holds C_k, not Y_k
+                const double Yk[2] = {inc ? Yv.x * wk / rh[0] : Yv.x, inc ? Yv.y * wk / rh[1] : Yv.y};
                 const double tmid = __ldg(tb.sp_tmid + k);
                 double ck[2], cp[2], Bk[2], dB[2], hW[2];
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     const double* c = tb.sp_nasa + (k * 2 + (Tv[g] <= tmid ? 0 : 1)) * 16;
                     const double t = Tv[g];
-                    ck[g] = rh[g] * Yk[g] * iw;
+                    ck[g] = inc ? (g ? Yv.y : Yv.x) : rh[g] * Yk[g] * iw;
                     cp[g] = ruw * (c[0] + t * (c[1] + t * (c[2] + t * (c[3] + c[4] * t))));
                     const double hh = c[6] + t * (c[7] + t * (c[8] + c[9] * t));
                     hW[g] = ruw * (c[5] + t * (c[0] + t * hh)) * wk;
@@ -638,6 +680,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                     Bk[g] = c[10] + c[11] * lT[g] + t * (c[6] + t * (c[12] + t * (c[13] + c[14] * t))) - c[5] * rT[g];
                 }
                 sts<E_C * RB>(a, V{ck[0], ck[1]});
+                if (MODE == M_RATES && io.conc) put2(io.conc, io, nsp, out, k, V{ck[0], ck[1]});
                 sts<O_B * RB>(o, V{Bk[0], Bk[1]});
                 sts<E_DB * RB>(a, V{dB[0], dB[1]});
                 sts<O_HW * RB>(o, V{hW[0], hW[1]});
@@ -663,14 +706,14 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 if (nxt >= 0) prefetch_l1(pl.rx + nxt * 4);
                 const bool valid = item >= 0;
                 if (r < rpm) {
-                    reaction<GS, true>(tb, pl, aSP, aRX, aRAW, aSC, valid ? item : tb.first_pm, valid, true, T, logT, iT);
+                    reaction<GS, true, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, valid ? item : tb.first_pm, valid, true, T, logT, iT);
                 } else {
                     const int p = valid ? item : 0;
                     const int4 c = __ldg(pl.rx + p * 4 + 2);
                     const unsigned nsp_f = sp_even<GS>(0u, (unsigned)nsp) / 16;
                     const bool has3 = ((c.z & 0xFFFFu) != nsp_f) || (((unsigned)c.w >> 16) != nsp_f);
                     const bool three = __any_sync(0xffffffffu, has3);
-                    reaction_plain<GS>(tb, pl, aSP, aRX, aRAW, aSC, p, valid, three, T, logT, iT);
+                    reaction_plain<GS, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, p, valid, three, T, logT, iT);
                 }
                 item = nxt;
             }
@@ -696,6 +739,7 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 auto unit = [&](uint2 c, double sg) {
                     const unsigned x = aRX + c.x, y = aRX + c.y;
                     aN = vfma(sg, vadd(lds<RX_NET * RB>(x), lds<RX_NET * RB>(y)), aN);
+                    if (MODE != M_JAC) return;                 // only the net rates are summed
                     aT = vfma(sg, vadd(lds<RX_TT * RB>(x), lds<RX_TT * RB>(y)), aT);
                     a1 = vfma(sg, vadd(lds<RX_X1 * RB>(x), lds<RX_X1 * RB>(y)), a1);
                     a2 = vfma(sg, vadd(lds<RX_X2 * RB>(x), lds<RX_X2 * RB>(y)), a2);
@@ -709,11 +753,27 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
                 if (i < n) unit(__ldg(cp + (i + 1) * NSUB), i < np_ ? 1.0 : -1.0);
                 for (int o = NPR; o < NPR * pl.coop; o <<= 1) {
                     aN = V{aN.x + __shfl_xor_sync(0xffffffffu, aN.x, o), aN.y + __shfl_xor_sync(0xffffffffu, aN.y, o)};
+                    if (MODE != M_JAC) continue;
                     aT = V{aT.x + __shfl_xor_sync(0xffffffffu, aT.x, o), aT.y + __shfl_xor_sync(0xffffffffu, aT.y, o)};
                     a1 = V{a1.x + __shfl_xor_sync(0xffffffffu, a1.x, o), a1.y + __shfl_xor_sync(0xffffffffu, a1.y, o)};
                     a2 = V{a2.x + __shfl_xor_sync(0xffffffffu, a2.x, o), a2.y + __shfl_xor_sync(0xffffffffu, a2.y, o)};
                 }
-                if (hd.y) {
+                if (hd.y && MODE != M_JAC) {
+                    // dydt / rates: omega_k, dY_k/dt = omega_k W_k / rho, share of sum_k h_k W_k omega_k
+                    const int k = hd.x / SPB;
+                    const double wk = __ldg(tb.sp_w + k);
+                    pH1 = vfma(lds<O_HW * RB>((aSP + hd.x) ^ RB), aN, pH1);
+                    const V ri = lds<Q_RHOINV * RB>(aSC);
+                    const V dyk = vmul(wk, vmul(aN, ri));
+                    if (MODE == M_RATES) {
+                        if (io.sr) put2(io.sr, io, nsp, out, k, aN);
+                        if (io.dy && k < last) put2(io.dy, io, nsp, out, k + 1, dyk);
+                    } else if (k < last) {
+                        if (ok0) io.dy[s0 * io.dy_ss + (long long)(k + 1) * io.dy_sv] = dyk.x;
+                        if (ok1) io.dy[(s0 + 1) * io.dy_ss + (long long)(k + 1) * io.dy_sv] = dyk.y;
+                    }
+                }
+                if (hd.y && MODE == M_JAC) {
                     const unsigned a = aSP + hd.x, o = a ^ RB;      // hd.x: even-slot base of species k
                     const double wk = __ldg(tb.sp_w + hd.x / SPB);
                     const V comp = vmul(aN, mwr);
@@ -741,6 +801,31 @@ k_jacobian(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, c
         }
         __syncthreads();
         PJ_TICK(3)
+
+        // ------------------------------------------------------------ dydt / rates: energy equation
+        if (MODE != M_JAC) {
+            if (warp == 0) {
+                V H1 = zero, cpavg = zero;
+                for (int w = sub; w < nw; w += NSUB) {
+                    H1 = vadd(H1, lds<D_H1 * RB>(aPA + w * NPART * RB));
+                    cpavg = vadd(cpavg, lds<D_CPAVG * RB>(aPA + w * NPART * RB));
+                }
+                H1 = sub_sum<GS>(H1);
+                cpavg = sub_sum<GS>(cpavg);
+                if (sub == 0 && io.dy) {
+                    const V rho = lds<Q_RHO * RB>(aSC);
+                    const V d0{-1.0 / (rho.x * cpavg.x) * H1.x, -1.0 / (rho.y * cpavg.y) * H1.y};
+                    if (MODE == M_RATES) put2(io.dy, io, nsp, out, 0, d0);
+                    else {
+                        if (ok0) io.dy[s0 * io.dy_ss] = d0.x;
+                        if (ok1) io.dy[(s0 + 1) * io.dy_ss] = d0.y;
+                    }
+                }
+                if (grp + gridDim.x < ngroups) phase_a0(grp + gridDim.x, buf ^ 1);
+            }
+            __syncthreads();
+            continue;
+        }
 
         // ------------------------------------------------------------ phase DE
         if (warp == 0 && !(io.dbg_skip & 64)) {

@@ -13,12 +13,10 @@
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
-#include "jacobian.cuh"
+#include "eval.cuh"
 #include "pjtable.h"
 
 using pj::IO;
-using pj::Layout;
 using pj::Tables;
 
 struct pyjac_mech {
@@ -28,14 +26,9 @@ struct pyjac_mech {
     int smem_per_sm = 0;
     Tables tb{};
     pj5::Plan plan{};
-    int jac_bpsm = 0;                // blocks per SM of the Jacobian kernel (0 = not configured)
     std::vector<void*> dev_allocs;
-    // launch configuration (per mode: 0 jac, 1 dydt, 2 rates)
-    int G[3] = {0, 0, 0};
-    int threads[3] = {0, 0, 0};
-    int blocks_per_sm[3] = {0, 0, 0};
-    int minb[3] = {1, 1, 1};
-    int user_G = 0, user_threads = 0, user_bpsm = 0;
+    int user_bpsm = 0;
+    int bpsm[3] = {0, 0, 0};         // blocks per SM per mode (0 = not configured yet)
     long long launches = 0;
     // staging for the host-pointer API
     cudaStream_t stream[2] = {nullptr, nullptr};
@@ -66,150 +59,49 @@ int fail(int code, const std::string& msg)
                         std::string(#call) + ": " + cudaGetErrorString(e_));             \
     } while (0)
 
-Layout make_layout(const Tables& tb, int G, bool jac)
-{
-    Layout L{};
-    L.nsp1 = tb.nsp + 1;
-    int off = 0;
-    auto take = [&](int n) { int o = off; off += ((n * G + 1) & ~1); return o; };
-    L.off_C = take(L.nsp1); L.off_B = take(L.nsp1); L.off_dB = take(L.nsp1); L.off_hW = take(L.nsp1);
-    L.off_wdot = take(L.nsp1); L.off_sT = take(L.nsp1); L.off_a = take(L.nsp1); L.off_b = take(L.nsp1);
-    L.off_cp = take(2 * L.nsp1);
-    L.off_y = take(L.nsp1);
-    L.off_scal = take(2 * pj::NSCAL);
-    L.off_net = take(tb.nr);
-    if (jac) {
-        L.off_tT = take(tb.nr); L.off_X1 = take(tb.nr); L.off_X2 = take(tb.nr); L.off_rh = take(tb.nr);
-        L.off_raw = take(tb.nraw + 2);
-        L.off_tile = take(tb.nsp * tb.nsp);
-    }
-    L.total = off;
-    return L;
-}
-
-template <int MODE, int MINB>
-const void* kernel_for(int G)
-{
-    switch (G) {
-    case 1: return (const void*)pj::k_eval<1, MODE, MINB>;
-    default: return (const void*)pj::k_eval<2, MODE, MINB>;
-    }
-}
-
-// minb = 2 selects the 80-register build (<= 384 threads) so two blocks fit on an SM
-const void* kernel_ptr(int mode_ix, int G, int minb)
-{
-    switch (mode_ix) {
-    case 0: return minb == 2 ? kernel_for<pj::M_JAC, 2>(G) : kernel_for<pj::M_JAC, 1>(G);
-    case 1: return kernel_for<pj::M_DYDT, 1>(G);
-    default: return kernel_for<pj::M_RATES, 1>(G);
-    }
-}
-
-// choose G / threads / blocks per SM for one mode and opt the kernel in to its smem size
-int configure(pyjac_mech* m, int mode_ix)
-{
-    const bool jac = mode_ix == 0;
-    const int cands[2] = {2, 1};
-    int G = 0;
-    if (m->user_G) {
-        G = m->user_G;
-        if ((size_t)make_layout(m->tb, G, jac).total * 8 > (size_t)m->smem_optin) G = 0;
-    }
-    if (!G) {
-        // default: the largest group that still lets two blocks share an SM, else the
-        // largest that fits at all
-        for (int c : cands)
-            if (((size_t)make_layout(m->tb, c, jac).total * 8 + 1024) * 2 <= (size_t)m->smem_per_sm) { G = c; break; }
-        if (!G)
-            for (int c : cands)
-                if ((size_t)make_layout(m->tb, c, jac).total * 8 <= (size_t)m->smem_optin) { G = c; break; }
-    }
-    if (!G)
-        return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
-    const size_t bytes = (size_t)make_layout(m->tb, G, jac).total * 8;
-    int threads = m->user_threads ? m->user_threads : 384;
-    threads = std::max(32 * (G + 2), std::min(512, (threads + 31) / 32 * 32));
-    int bpsm = (int)((size_t)m->smem_per_sm / (bytes + 1024));
-    bpsm = std::max(1, std::min(bpsm, 2048 / threads));
-    if (m->user_bpsm) bpsm = std::max(1, std::min(bpsm, m->user_bpsm));
-    // register file: 64 K registers per SM; the 128-register build allows 512 threads per SM
-    int minb = 1;
-    if (mode_ix == 0 && bpsm >= 2 && threads <= 384) minb = 2;
-    if (minb == 1) bpsm = std::max(1, std::min(bpsm, 512 / threads));
-    else bpsm = std::min(bpsm, 768 / threads);
-    m->G[mode_ix] = G;
-    m->threads[mode_ix] = threads;
-    m->blocks_per_sm[mode_ix] = bpsm;
-    m->minb[mode_ix] = minb;
-    const void* fn = kernel_ptr(mode_ix, G, minb);
-    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    return PYJAC_OK;
-}
-
-int launch(pyjac_mech* m, int mode_ix, const IO& io, cudaStream_t st)
-{
-    if (io.n <= 0) return PYJAC_OK;
-    CU(cudaSetDevice(m->device));
-    if (!m->G[mode_ix]) {
-        int rc = configure(m, mode_ix);
-        if (rc) return rc;
-    }
-    const int G = m->G[mode_ix];
-    Layout L = make_layout(m->tb, G, mode_ix == 0);
-    const long long groups = ((long long)io.n + G - 1) / G;
-    const int grid = (int)std::min<long long>(groups, (long long)m->sm_count * m->blocks_per_sm[mode_ix]);
-    void* args[3] = {(void*)&m->tb, (void*)&io, (void*)&L};
-    CU(cudaLaunchKernel(kernel_ptr(mode_ix, G, m->minb[mode_ix]), dim3(grid), dim3(m->threads[mode_ix]), args,
-                        (size_t)L.total * 8, st));
-    ++m->launches;
-    return PYJAC_OK;
-}
-
-template <int MAXT>
-const void* jac_kernel_t(int gs)
+template <int MODE>
+const void* kernel_t(int gs)
 {
     switch (gs) {
-    case 2: return (const void*)pj5::k_jacobian<2, MAXT>;
-    case 4: return (const void*)pj5::k_jacobian<4, MAXT>;
-    case 8: return (const void*)pj5::k_jacobian<8, MAXT>;
-    case 16: return (const void*)pj5::k_jacobian<16, MAXT>;
-    case 32: return (const void*)pj5::k_jacobian<32, MAXT>;
+    case 2: return (const void*)pj5::k_eval<2, 512, MODE>;
+    case 4: return (const void*)pj5::k_eval<4, 512, MODE>;
+    case 8: return (const void*)pj5::k_eval<8, 512, MODE>;
+    case 16: return (const void*)pj5::k_eval<16, 512, MODE>;
+    case 32: return (const void*)pj5::k_eval<32, 512, MODE>;
     default: return nullptr;
     }
 }
 
-// the build with the smallest thread bound (= most registers per thread) that admits nt
-const void* jac_kernel(int gs, int nt = 512)
+// k_eval for a plan's states per block and a mode (blocks are at most 512 threads)
+const void* kernel_for(int gs, int mode)
 {
-    if (nt <= 512) return jac_kernel_t<512>(gs);
-    if (nt <= 768) return jac_kernel_t<768>(gs);
-    return jac_kernel_t<1024>(gs);
+    if (mode == pj::M_DYDT) return kernel_t<pj::M_DYDT>(gs);
+    if (mode == pj::M_RATES) return kernel_t<pj::M_RATES>(gs);
+    return kernel_t<pj::M_JAC>(gs);
 }
 
-// eval_jacob: the plan in the table blob fixes states per block and block size
-int launch_jac(pyjac_mech* m, const IO& io, cudaStream_t st)
+// One launch of k_eval; the plan in the table blob fixes states per block and block size.
+int launch(pyjac_mech* m, int mode, const IO& io, cudaStream_t st)
 {
     if (io.n <= 0) return PYJAC_OK;
     CU(cudaSetDevice(m->device));
     const pj5::Plan& pl = m->plan;
-    const void* fn = jac_kernel(pl.gs, pl.nt);
-    if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable Jacobian plan");
+    const void* fn = kernel_for(pl.gs, mode);
+    if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable plan");
     const size_t bytes = (size_t)pl.total * 8;
-    if (!m->jac_bpsm) {
+    if (!m->bpsm[mode]) {
         if (bytes > (size_t)m->smem_optin)
             return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.nt, bytes));
-        if (occ < 1) return fail(PYJAC_ETOOBIG, "Jacobian kernel cannot be resident with this plan");
+        if (occ < 1) return fail(PYJAC_ETOOBIG, "kernel cannot be resident with this plan");
         if (m->user_bpsm) occ = std::min(occ, m->user_bpsm);
-        m->jac_bpsm = occ;
+        m->bpsm[mode] = occ;
     }
     const long long groups = ((long long)io.n + pl.gs - 1) / pl.gs;
-    const int grid = (int)std::min<long long>(groups, (long long)m->sm_count * m->jac_bpsm);
+    const int grid = (int)std::min<long long>(groups, (long long)m->sm_count * m->bpsm[mode]);
     void* args[3] = {(void*)&m->tb, (void*)&m->plan, (void*)&io};
     CU(cudaLaunchKernel(fn, dim3(grid), dim3(pl.nt), args, bytes, st));
     ++m->launches;
@@ -292,34 +184,16 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     pyjac_mech* m = new pyjac_mech();
     m->device = device;
     Tables& t = m->tb;
-    const pjt::Entry* d3e = pjt::find(blob, "dims3");
-    if (!d3e || d3e->dtype != 1 || d3e->count < 8) { delete m; return fail(PYJAC_EINVAL, "table blob lacks dims3"); }
-    const int* d3 = (const int*)((const char*)blob + d3e->offset);
     t.nsp = d[0]; t.nr = d[1]; t.nrev = d[2]; t.npd = d[3]; t.nraw = d[4];
     t.first_pm = d[8]; t.npm = d[9];
-    t.nfix = d3[0]; t.nq = d3[1]; t.nq_j = d3[2];
     t.ru = c[0];
     int rc = PYJAC_OK;
 #define UP(field, name, type, code) if (!rc) rc = upload<type>(m, blob, name, &m->field, code)
     UP(tb.sp_w, "sp_w", double, 0); UP(tb.sp_iw, "sp_iw", double, 0); UP(tb.sp_ruw, "sp_ruw", double, 0);
-    UP(tb.sp_tmid, "sp_tmid", double, 0); UP(tb.sp_mwf, "sp_mwf", double, 0); UP(tb.sp_nasa, "sp_nasa", double, 0);
-    UP(tb.rx_rec, "rx_rec", int4, 1); UP(tb.rx_dst, "rx_dst", uint4, 2);
+    UP(tb.sp_tmid, "sp_tmid", double, 0); UP(tb.sp_nasa, "sp_nasa", double, 0);
     UP(tb.pm_par, "pm_par", double, 0); UP(tb.pm_sp, "pm_sp", int, 1);
-    UP(tb.pm_eff_off, "pm_eff_off", int, 1); UP(tb.pm_eff_sp, "pm_eff_sp", int, 1); UP(tb.pm_eff_am1, "pm_eff_am1", double, 0);
-    UP(tb.red_off, "red_off", int, 1); UP(tb.red_pk, "red_pk", unsigned, 1);
-    UP(tb.d_dst, "d_dst", unsigned short, 2); UP(tb.d_con, "d_con", unsigned, 1);
-    UP(tb.q_dst, "q_dst", unsigned short, 2); UP(tb.q_off, "q_off", int, 1); UP(tb.q_con, "q_con", unsigned, 1);
-    if (!rc) {
-        const pjt::Entry* s_ = pjt::find(blob, "d_cls");
-        const pjt::Entry* c_ = pjt::find(blob, "d_ccon");
-        if (!s_ || !c_ || s_->dtype != 1 || c_->dtype != 1 || s_->count != 5 || c_->count != 4)
-            rc = fail(PYJAC_EINVAL, "table blob lacks d_cls / d_ccon");
-        else {
-            std::memcpy(t.d_cls, (const char*)blob + s_->offset, sizeof(t.d_cls));
-            std::memcpy(t.d_ccon, (const char*)blob + c_->offset, sizeof(t.d_ccon));
-        }
-    }
-    UP(tb.red_rx, "red_rx", int, 1); UP(tb.red_nu, "red_nu", double, 0);
+    UP(tb.red_off, "red_off", int, 1); UP(tb.red_rx, "red_rx", int, 1); UP(tb.red_nu, "red_nu", double, 0);
+    UP(tb.rx_out, "p5_rxout", int4, 1);
     if (!rc) {
         const pjt::Entry* pe = pjt::find(blob, "p5_cfg");
         if (!pe || pe->dtype != 1 || pe->count < 14) rc = fail(PYJAC_EINVAL, "table blob lacks p5_cfg");
@@ -328,10 +202,11 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
             pj5::Plan& pl = m->plan;
             int* o = &pl.gs;
             for (int i = 0; i < 14; ++i) o[i] = c5[i];
-            if (!jac_kernel(pl.gs) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 1024 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
-                rc = fail(PYJAC_EINVAL, "bad Jacobian plan configuration");
+            if (!kernel_for(pl.gs, pj::M_JAC) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
+                rc = fail(PYJAC_EINVAL, "bad plan configuration");
         }
     }
+    if (!rc) m->plan.rx_out = m->tb.rx_out;
     UP(plan.rx, "p5_rx", int4, 1); UP(plan.eff_off, "p5_eff_off", int, 1); UP(plan.eff, "p5_eff", int4, 1);
     UP(plan.b_off, "p5_b_off", int, 1); UP(plan.b_npm, "p5_b_npm", int, 1); UP(plan.b_item, "p5_b_item", int, 1);
     UP(plan.c_off, "p5_c_off", int, 1); UP(plan.c_item, "p5_c_item", int4, 1); UP(plan.c_str, "p5_c_str", uint2, 1);
@@ -374,14 +249,11 @@ int pyjac_mech_dims(const pyjac_mech* m, int dims[4])
     return PYJAC_OK;
 }
 
-int pyjac_mech_tune(pyjac_mech* m, int states_per_block, int threads, int blocks_per_sm)
+int pyjac_mech_tune(pyjac_mech* m, int blocks_per_sm)
 {
-    if (!m) return fail(PYJAC_EINVAL, "NULL mechanism");
-    if (states_per_block != 0 && states_per_block != 1 && states_per_block != 2)
-        return fail(PYJAC_EINVAL, "states_per_block must be 0, 1 or 2");
-    m->user_G = states_per_block; m->user_threads = threads; m->user_bpsm = blocks_per_sm;
-    m->G[0] = m->G[1] = m->G[2] = 0;    // re-derive at next launch
-    m->jac_bpsm = 0;
+    if (!m || blocks_per_sm < 0) return fail(PYJAC_EINVAL, "bad argument");
+    m->user_bpsm = blocks_per_sm;
+    m->bpsm[0] = m->bpsm[1] = m->bpsm[2] = 0;    // re-derive at next launch
     return PYJAC_OK;
 }
 
@@ -399,7 +271,7 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
     io.jac = d_jac; io.jac_layout = jac_layout; io.jac_ld = jac_ld;
     if (const char* dbg = std::getenv("PYJAC_DEBUG_SKIP")) io.dbg_skip = std::atoi(dbg);   // timing experiments only
     if (const char* dbg = std::getenv("PYJAC_DEBUG_CLK")) io.dbg_clk = (long long*)std::strtoull(dbg, nullptr, 0);
-    return launch_jac(m, io, (cudaStream_t)stream);
+    return launch(m, pj::M_JAC, io, (cudaStream_t)stream);
 }
 
 int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
@@ -410,7 +282,7 @@ int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y
     IO io{};
     io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
     io.dy = d_dy; io.dy_ss = o_ss; io.dy_sv = o_sv;
-    return launch(m, 1, io, (cudaStream_t)stream);
+    return launch(m, pj::M_DYDT, io, (cudaStream_t)stream);
 }
 
 int pyjac_rates_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
@@ -424,7 +296,7 @@ int pyjac_rates_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_
     io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
     io.conc = d_conc; io.fwd = d_fwd; io.rev = d_rev; io.pm = d_pres_mod; io.sr = d_spec_rates;
     io.dy = d_dy; io.o_sf = o_state_fastest; io.o_ld = o_ld;
-    return launch(m, 2, io, (cudaStream_t)stream);
+    return launch(m, pj::M_RATES, io, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- host-pointer batch API
@@ -623,7 +495,7 @@ static int scalar_rates(pyjac_mech* m, double T, double pres, const double* in, 
     io.in_conc = in_conc ? 1 : 0;
     io.conc = d; io.fwd = d + nsp; io.rev = d + nsp + t.nr; io.pm = d + nsp + t.nr + t.nrev;
     io.scal3 = d + n_out;
-    rc = launch(m, 2, io, st);
+    rc = launch(m, pj::M_RATES, io, st);
     if (rc) return rc;
     CU(cudaMemcpyAsync(hp, d, out_d * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -62,8 +62,10 @@ class Evaluator:
             pass
 
     # ------------------------------------------------------------------ helpers
-    def tune(self, states_per_block: int = 0, threads: int = 0, blocks_per_sm: int = 0):
-        _lib.check(self.lib.pyjac_mech_tune(self._h, states_per_block, threads, blocks_per_sm))
+    def tune(self, blocks_per_sm: int = 0):
+        """Cap on resident blocks per SM (0 = automatic); states per block / block size are the
+        ``gs`` / ``threads`` arguments of the constructor (they shape the plan tables)."""
+        _lib.check(self.lib.pyjac_mech_tune(self._h, blocks_per_sm))
 
     @property
     def launches(self) -> int:

@@ -24,7 +24,7 @@ SIGNATURES = {
     'pyjac_mech_create': (c_int, [c_void_p, c_size_t, c_int, POINTER(c_void_p)]),
     'pyjac_mech_destroy': (None, [c_void_p]),
     'pyjac_mech_dims': (c_int, [c_void_p, POINTER(c_int)]),
-    'pyjac_mech_tune': (c_int, [c_void_p, c_int, c_int, c_int]),
+    'pyjac_mech_tune': (c_int, [c_void_p, c_int]),
     'pyjac_mech_launches': (c_longlong, [c_void_p]),
     'pyjac_eval_jacob_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
                                      c_void_p, c_int, c_longlong, c_void_p]),

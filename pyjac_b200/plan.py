@@ -110,7 +110,7 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
                ) -> Dict[str, np.ndarray]:
     """kinds[p] in {'plain','thd','lind','troe','sri'} per kernel-order reaction p;
     contrib[(k, j)] = [(raw row, nu)], tcontrib[j] = [(raw row, reaction)]."""
-    assert gs in GS_CHOICES and nt % 32 == 0 and 64 <= nt <= 1024
+    assert gs in GS_CHOICES and nt % 32 == 0 and 64 <= nt <= 512
     if nsp > 2000:
         raise ValueError('too many species for the 22-bit element index')
     nw = nt // 32

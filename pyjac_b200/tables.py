@@ -596,6 +596,8 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
         if any(int(sl) == last for sl in slots[p]):
             rec5[p, 8] |= F_HAS_LAST
     T['p5_rx'] = rec5.ravel()
+    # positions of kernel-order reaction p in the reference's fwd / rev / pres_mod arrays
+    T['p5_rxout'] = i32([[order[p], rev_idx[p], pm_idx[p], 0] for p in range(nr)]).ravel()
     # collider lists of the Jacobian kernel: per pressure-modified reaction a list padded to a
     # multiple of four records {alpha - 1 (double), byte offset of the collider's species row,
     # raw row that receives pres_mod_temp * (alpha - 1)}; padding: alpha - 1 = 0, empty species

@@ -42,7 +42,7 @@ def main():
         G, th, bp = (int(v) for v in cfg.split(':'))
         try:
             ev = Evaluator(mech, 0, gs=G, threads=th)
-            ev.tune(0, 0, bp)
+            ev.tune(bp)
             ev.eval_jacob(P, y, out, y_layout=a.layout, jac_layout=a.layout)
             torch.cuda.synchronize()
         except Exception as exc:
