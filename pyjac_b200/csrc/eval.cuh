@@ -405,10 +405,11 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
             const int e0 = __ldg(pl.eff_off + mi), e1_ = __ldg(pl.eff_off + mi + 1);
             for (int e = e0; e < e1_; e += 4) {
                 const int4 r0 = __ldg(pl.eff + e), r1 = __ldg(pl.eff + e + 1), r2 = __ldg(pl.eff + e + 2), r3 = __ldg(pl.eff + e + 3);
-                sts<0>(aRAW + r0.w * RB, vmul(__hiloint2double(r0.y, r0.x), pmt));
-                sts<0>(aRAW + r1.w * RB, vmul(__hiloint2double(r1.y, r1.x), pmt));
-                sts<0>(aRAW + r2.w * RB, vmul(__hiloint2double(r2.y, r2.x), pmt));
-                sts<0>(aRAW + r3.w * RB, vmul(__hiloint2double(r3.y, r3.x), pmt));
+                const int none = tb.nraw + 1;          // padding records and colliders without a raw row
+                sts_if<0>(r0.w != none, aRAW + r0.w * RB, vmul(__hiloint2double(r0.y, r0.x), pmt));
+                sts_if<0>(r1.w != none, aRAW + r1.w * RB, vmul(__hiloint2double(r1.y, r1.x), pmt));
+                sts_if<0>(r2.w != none, aRAW + r2.w * RB, vmul(__hiloint2double(r2.y, r2.x), pmt));
+                sts_if<0>(r3.w != none, aRAW + r3.w * RB, vmul(__hiloint2double(r3.y, r3.x), pmt));
             }
         }
         if (fl & F_WANT_PMT) sts<0>(aRAW + ((unsigned)q3.w >> 16) * RB, pmt);
@@ -499,14 +500,16 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
         if (s4 == last) X2 = vsub(X2, n4);
         if (s5 == last) X2 = vsub(X2, n5);
     }
-    // raw rows (slots without one point at the scratch row)
-    sts_if<0>(valid, aRAW + (q3.x & 0xFFFFu) * RB, d0);
-    sts_if<0>(valid, aRAW + ((unsigned)q3.x >> 16) * RB, d1);
-    sts_if<0>(valid, aRAW + ((unsigned)q3.y >> 16) * RB, n3);
-    sts_if<0>(valid, aRAW + (q3.z & 0xFFFFu) * RB, n4);
+    // raw rows; slots without one carry the scratch row index and store nothing
+    const unsigned none = tb.nraw + 1;
+    auto emit = [&](unsigned dst, V d) { sts_if<0>(valid && dst != none, aRAW + dst * RB, d); };
+    emit(q3.x & 0xFFFFu, d0);
+    emit((unsigned)q3.x >> 16, d1);
+    emit((unsigned)q3.y >> 16, n3);
+    emit(q3.z & 0xFFFFu, n4);
     if (three) {
-        sts_if<0>(valid, aRAW + (q3.y & 0xFFFFu) * RB, d2);
-        sts_if<0>(valid, aRAW + ((unsigned)q3.z >> 16) * RB, n5);
+        emit(q3.y & 0xFFFFu, d2);
+        emit((unsigned)q3.z >> 16, n5);
     }
     const unsigned ar = aRX + p * RXB;
     sts_if<RX_NET * RB>(valid, ar, net);
@@ -852,6 +855,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 store(0u, V{-(-wdcp.x / cpavg.x * H1.x + SCP.x + HT.x * rho.x) / (rho.x * cpavg.x),
                             -(-wdcp.y / cpavg.y * H1.y + SCP.y + HT.y * rho.y) / (rho.y * cpavg.y)}, true);
             }
+            __syncwarp();          // the other sub-groups of warp 0 read these scalars in class T
             if (pl.t_sync > 32) {
                 __threadfence_block();
                 asm volatile("bar.arrive 1, %0;" ::"r"(pl.t_sync) : "memory");
