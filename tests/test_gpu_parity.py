@@ -213,3 +213,26 @@ def test_full_size_properties(torch, golden_dir):
                                   'full size, first replica', mech, y_h)
     assert frac > 0.999
     ev.close()
+
+
+def test_speedtest_cli(torch, golden_dir, tmp_path, capsys):
+    """The performance-test executable of the reference (tester.cu.in:51-168): data.bin rows in
+    the original species order, masked on read, one 'N,ms' line on stdout."""
+    from pyjac_b200 import speedtest
+    from pyjac_b200.create_jacobian import create_jacobian
+    out = str(tmp_path / 'out')
+    mech = create_jacobian('cuda', os.path.join(golden_dir, 'h2o2_n2.inp'), build_path=out)
+    g = dict(np.load(os.path.join(golden_dir, 'h2o2_pasr.npz')))
+    n = g['y'].shape[0]
+    # internal order -> original order (the inverse of apply_mask)
+    Y_int = np.concatenate([g['y'][:, 1:], 1.0 - g['y'][:, 1:].sum(axis=1, keepdims=True)], axis=1)
+    Y_orig = np.empty_like(Y_int)
+    Y_orig[:, mech.fwd_spec_map] = Y_int
+    data = str(tmp_path / 'data.bin')
+    speedtest.write_data_bin(data, g['y'][:, 0], g['P'], Y_orig)
+    assert speedtest.main([str(n), '4', '--build-path', out, '--data', data]) == 0
+    line = capsys.readouterr().out.strip()
+    num, ms = line.split(',')
+    assert int(num) == n and float(ms) > 0.0
+    ms2, jac = speedtest.run(n, out, data)
+    gates.check_jac(np.ascontiguousarray(jac.T), g['jac'], mech.NSP, 'speedtest', mech, g['y'])

@@ -82,3 +82,22 @@ def test_plan_tables_are_consistent(golden_dir, tmp_path):
                   for sb in range(nsub) if t_str[u, sb, 0] >> 16]
         assert sorted(t_cols) == list(range(1, nsp))
         assert int(T['p5_cfg'][9]) * 8 <= 232448
+
+
+def test_data_bin_round_trip(golden_dir, tmp_path):
+    """data.bin rows [t, T, P, Y...] in the original species order come back masked and
+    state-fastest, the way read_initial_conditions.cu:10-59 hands them to the device."""
+    from pyjac_b200 import speedtest
+    from pyjac_b200.states import pasr_states
+    out = str(tmp_path / 'out')
+    mech = create_jacobian('cuda', os.path.join(golden_dir, 'h2o2_n2.inp'), build_path=out, skip_jac=True)
+    raw = np.load(os.path.join(golden_dir, 'h2_pasr_output.npy'))
+    raw = raw.reshape(-1, raw.shape[-1])[:50]
+    data = str(tmp_path / 'data.bin')
+    speedtest.write_data_bin(data, raw[:, 1], raw[:, 2], raw[:, 3:], t=raw[:, 0])
+    assert os.path.getsize(data) == 50 * (mech.NSP + 3) * 8
+    fwd = speedtest._fwd_spec_map(out, mech.NSP)
+    assert fwd == mech.fwd_spec_map
+    y, pres = speedtest.read_initial_conditions(data, 50, fwd)
+    assert y.shape == (mech.NSP, 50) and np.array_equal(pres, raw[:, 2]) and np.array_equal(y[0], raw[:, 1])
+    assert np.array_equal(y[1:], raw[:, 3:][:, fwd][:, :-1].T)
