@@ -548,15 +548,18 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         sts<0>(aCF + i * 16, V{c.x, c.y});
     }
 
-    // rows that never change: the empty reaction slot, the zero reaction, the zero raw row
+    // rows that never change: the empty reaction slot, two all-zero reactions and raw rows (the
+    // padding of the gather lists; one on either half of a bank line)
     if (warp == 0 && sub == 0) {
         const unsigned a = sp_even<GS>(aSP, (unsigned)nsp), o = a ^ RB;
         sts<E_C * RB>(a, V{1.0, 1.0});
         sts<O_B * RB>(o, zero); sts<E_DB * RB>(a, zero); sts<O_HW * RB>(o, zero);
         sts<E_WA * RB>(a, zero); sts<O_WB * RB>(o, zero); sts<E_WT * RB>(a, zero); sts<O_CP * RB>(o, zero);
-        const unsigned ar = aRX + tb.nr * RXB;
-        sts<RX_NET * RB>(ar, zero); sts<RX_TT * RB>(ar, zero); sts<RX_X1 * RB>(ar, zero);
-        sts<RX_X2 * RB>(ar, zero); sts<RX_DH * RB>(ar, zero);
+        for (int z = 0; z < 2; ++z) {
+            const unsigned ar = aRX + (tb.nr + z) * RXB;
+            sts<RX_NET * RB>(ar, zero); sts<RX_TT * RB>(ar, zero); sts<RX_X1 * RB>(ar, zero);
+            sts<RX_X2 * RB>(ar, zero); sts<RX_DH * RB>(ar, zero);
+        }
         sts<0>(aRAW + tb.nraw * RB, zero);
         sts<0>(aRAW + (tb.nraw + 1) * RB, zero);
     }

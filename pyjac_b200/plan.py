@@ -63,8 +63,8 @@ def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:
         off += rows * gs
 
     take('SP', (nsp + 1) * SP_SLOTS)     # species nsp: the empty reaction slot (C = 1, others 0)
-    take('RX', (nr + 1) * RX_SLOTS)      # reaction nr: zeros (padding of the phase C lists)
-    take('RAW', nraw + 2)                # row nraw: zero (null contributions); nraw + 1: scratch
+    take('RX', (nr + 2) * RX_SLOTS)      # reactions nr, nr + 1: zeros (padding of the gather lists)
+    take('RAW', nraw + 2)                # rows nraw, nraw + 1: zeros (null contributions)
     take('SC', NSCAL)
     take('PA', nw * NPART)
     take('CF', -(-2 * nsp // gs))        # per column (1/W_j, (1/W_j)(W_j/W_N)) as plain doubles
@@ -88,6 +88,24 @@ def _lpt(costs: Sequence[float], nw: int, init: Sequence[float] = None) -> List[
         bins[w].append(ix)
         load[w] += costs[ix]
     return bins, load
+
+
+def balance_banks(lists: List[List[int]], half) -> None:
+    """Reorder each of the lists (one per sub-group, the order of its entries is free) so that at
+    every position about half of the lists hold an entry on either half of a 128-byte bank line
+    (``half(entry)`` in {0, 1}): the shared-memory reads of one instruction then need 4 rather than
+    up to 8 wavefronts.  Greedy: list s prefers half (s + position) & 1."""
+    pools = [[[e for e in lst if half(e) == h] for h in (0, 1)] for lst in lists]
+    out: List[List[int]] = [[] for _ in lists]
+    for pos in range(max((len(lst) for lst in lists), default=0)):
+        for s_, pool in enumerate(pools):
+            if len(out[s_]) >= len(lists[s_]):
+                continue
+            want = (s_ + pos) & 1
+            pick = want if pool[want] else 1 - want
+            out[s_].append(pool[pick].pop())
+    for lst, new in zip(lists, out):
+        lst[:] = new
 
 
 def hi16(c: float) -> int:
@@ -214,7 +232,8 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
                 for sb in range(nsub):
                     k = subs_k[sb]
                     lst = [] if k is None else c_lists[k][which][sb % coop::coop]
-                    per_sub.append([q_ * RXB for q_ in lst] + [nr * RXB] * (2 * n - len(lst)))
+                    per_sub.append([q_ * RXB for q_ in lst] + [(nr + ((sb + i) & 1)) * RXB for i in range(2 * n - len(lst))])
+                balance_banks(per_sub, lambda v: (v // RB) & 1 if (RB & 127) else 0)
                 for u in range(n):
                     for sb in range(nsub):
                         c_str += per_sub[sb][2 * u:2 * u + 2]
@@ -261,15 +280,22 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
             raise ValueError('sparse Jacobian element with too many contributions')
         n_ovf = (max(L - 2, 0) + 3) // 4 * 4              # overflow units come in batches of four
         A, B, ovf = [], [], [[] for _ in range(n_ovf)]
+        # pad with the two all-zero raw rows (nraw, nraw + 1: one on either half of a bank line),
+        # then order every list so that each position is spread over both halves
+        ents = [list(grp[sb][3]) if sb < len(grp) else [] for sb in range(nsub)]
+        for sb in range(nsub):
+            ents[sb] += [(nraw + ((sb + i) & 1)) * RB for i in range(2 * L - len(ents[sb]))]
+        balance_banks(ents, lambda v: (v // RB) & 1 if (RB & 127) else 0)
+        for sb in range(nsub):                 # positions past 2 L: skipped (L = 1) or padding of a batch
+            ents[sb] += [(nraw + ((sb + i) & 1)) * RB for i in range(2 * (n_ovf + 2) - 2 * L)]
         for sb in range(nsub):
             if sb < len(grp):
-                _, col, k, ent = grp[sb]
+                _, col, k, _ = grp[sb]
                 A.append([(col * nsp + k + 1) | (L << 22), (sp_even(k) + SLOT_WA * RB) | (col << 20)]
                          + _f64_words(sp_iw[col - 1] * sp_w[k]))
             else:
-                ent = []
                 A.append([NULL_E | (L << 22), null_sp, 0, 0])
-            pe = ent + [zr] * (2 * (n_ovf + 2) - len(ent))
+            pe = ents[sb]
             B.append(pe[:4])
             for i in range(n_ovf):
                 ovf[i].append(pe[4 + 2 * i:6 + 2 * i])
@@ -316,11 +342,15 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
             j = grp[sb // tcoop] if sb // tcoop < len(grp) else None
             if j is None:
                 hdr.append([0, null_sp])
-                per_sub.append([[zr, nr * RXB]] * n)
+                per_sub.append([[(nraw + ((sb + i) & 1)) * RB, nr * RXB] for i in range(n)])
             else:
                 lst = tcontrib.get(j, [])[sb % tcoop::tcoop]
                 hdr.append([(j + 1) | ((1 if sb % tcoop == 0 else 0) << 16), (sp_even(j) ^ RB) + (SLOT_CP - 1) * RB])
-                per_sub.append([[src * RB, rx_ * RXB] for src, rx_ in lst] + [[zr, nr * RXB]] * (n - len(lst)))
+                per_sub.append([[src * RB, rx_ * RXB] for src, rx_ in lst]
+                               + [[(nraw + ((sb + i) & 1)) * RB, nr * RXB] for i in range(n - len(lst))])
+        keyed = [[(pair[0] << 32) | pair[1] for pair in per_sub[sb]] for sb in range(nsub)]
+        balance_banks(keyed, lambda v: ((v >> 32) // RB) & 1 if (RB & 127) else 0)
+        per_sub = [[[v >> 32, v & 0xFFFFFFFF] for v in keyed[sb]] for sb in range(nsub)]
         units = [hdr] + [[per_sub[sb][u] for sb in range(nsub)] for u in range(n)]
         t_items.append((n, units))
 
