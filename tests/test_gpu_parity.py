@@ -236,3 +236,40 @@ def test_speedtest_cli(torch, golden_dir, tmp_path, capsys):
     assert int(num) == n and float(ms) > 0.0
     ms2, jac = speedtest.run(n, out, data)
     gates.check_jac(np.ascontiguousarray(jac.T), g['jac'], mech.NSP, 'speedtest', mech, g['y'])
+
+
+def test_edge_states_vs_oracle(torch, golden_dir):
+    """States at the edges of what the reference's tests feed it: the NASA range limits
+    (300 K / 3500 K and exactly T_mid), vacuum-like and 100 atm pressures, pure species and
+    mixtures with exact zeros (most concentrations 0, so whole rate products vanish)."""
+    from oracle.oracle import Oracle
+    mech, ev = _evaluator(golden_dir, 'gri30_syn.inp')
+    nsp = mech.NSP
+    rng = np.random.default_rng(5)
+    rows, pres = [], []
+    for T in (300.0, 1000.0, 1000.0000001, 999.9999999, 3500.0):
+        for P in (1.0e3, 101325.0, 1.0e7):
+            Y = np.zeros(nsp)
+            idx = rng.choice(nsp, size=4, replace=False)
+            Y[idx] = rng.dirichlet(np.ones(4))
+            Y[-1] = 1.0 - Y[:-1].sum()
+            rows.append(np.concatenate([[T], Y[:-1]]))
+            pres.append(P)
+            Y = np.zeros(nsp)                     # one pure species (the last one gets 1 - sum = 0 or 1)
+            k = int(rng.integers(nsp))
+            Y[k] = 1.0
+            rows.append(np.concatenate([[T], Y[:-1]]))
+            pres.append(P)
+    y_h, P_h = np.ascontiguousarray(rows), np.asarray(pres)
+    ora = Oracle(mech)
+    ref = dict(zip(KEYS, ora.rates(P_h, y_h)))
+    ref['dydt'] = ora.dydt(P_h, y_h)
+    ref_jac = ora.eval_jacob(P_h, y_h)
+    assert np.isfinite(ref_jac).all()
+    P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
+    new = dict(zip(KEYS + ['dydt'], [o.cpu().numpy() for o in ev.rates(P, y, want_dy=True)]))
+    jac = ev.eval_jacob(P, y).cpu().numpy()
+    assert np.isfinite(jac).all()
+    gates.check_rates(mech, P_h, y_h, new, ref, 'edge states')
+    gates.check_jac(jac, ref_jac, nsp, 'edge states', mech, y_h)
+    ev.close()
