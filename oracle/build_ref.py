@@ -94,6 +94,64 @@ def build(name: str, mech: str, last_spec=None, opt: str = '-O3', jobs: int = 8,
     return lib
 
 
+def cuda_lib_path(name: str) -> str:
+    return os.path.join(ref_dir(name + '_cuda'), 'libcu_pyjac.so')
+
+
+def build_cuda(name: str, mech: str, jobs: int = 8, force: bool = False, quiet: bool = True) -> str:
+    """The reference's *generated CUDA* for a mechanism, rebuilt for sm_100a:
+    `python -m pyjac --lang cuda` where the reference lies, then nvcc on the emitted files
+    (the reference's own flags use -arch=sm_20, libgen.py:45, and helper_cuda.h from the CUDA
+    samples, libgen.py:38-40, absent in CUDA 12.9: an empty stand-in header is used), linked
+    with oracle/ref_cuda_driver.cu into oracle/_ref/<name>_cuda/libcu_pyjac.so."""
+    out = ref_dir(name + '_cuda')
+    src = os.path.join(out, 'src')
+    lib = cuda_lib_path(name)
+    stamp = os.path.join(out, 'mech.inp')
+    mech_txt = open(mech).read()
+    if (not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == mech_txt):
+        return lib
+    if not have_reference():
+        raise RuntimeError('reference sources not present at %s' % REF_ROOT)
+    os.makedirs(src, exist_ok=True)
+    env = dict(os.environ, PYTHONPATH=REF_ROOT)
+    res = subprocess.run([sys.executable, '-W', 'ignore', '-m', 'pyjac', '--lang', 'cuda',
+                          '--input', os.path.abspath(mech), '-b', src], env=env, cwd=out,
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('reference codegen failed:\n' + res.stdout + res.stderr)
+    stub = os.path.join(out, 'stub')
+    os.makedirs(stub, exist_ok=True)
+    with open(os.path.join(stub, 'helper_cuda.h'), 'w') as fh:
+        fh.write('/* empty stand-in: CUDA 12.9 ships no samples/common/inc/helper_cuda.h */\n')
+    files = [f for f in glob.glob(os.path.join(src, '**', '*.cu'), recursive=True)
+             if os.path.basename(f) != 'sparse_multiplier.cu']      # broken upstream (SURVEY.md 8f2)
+    files.append(os.path.join(HERE, 'ref_cuda_driver.cu'))
+    flags = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-rdc=true', '-Xcompiler', '-fPIC',
+             '-I', stub, '-I', src, '-I', os.path.join(src, 'jacobs'), '-I', os.path.join(src, 'rates')]
+
+    def cc(f):
+        o = os.path.join(out, 'obj_' + os.path.basename(f)[:-3] + '.o')
+        r = subprocess.run(['nvcc'] + flags + ['-c', f, '-o', o], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed on %s:\n%s' % (f, r.stderr))
+        return o
+
+    with ThreadPoolExecutor(jobs) as ex:
+        objs = list(ex.map(cc, files))
+    r = subprocess.run(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', lib] + objs,
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n' + r.stderr)
+    for o in objs:
+        os.remove(o)
+    with open(stamp, 'w') as fh:
+        fh.write(mech_txt)
+    if not quiet:
+        print('built', lib)
+    return lib
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('name')
