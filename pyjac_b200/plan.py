@@ -1,4 +1,4 @@
-"""Static work schedule ("plan") of the sm_100a Jacobian kernel (csrc/jacobian.cuh).
+"""Static work schedule ("plan") of the sm_100a kernel (csrc/eval.cuh).
 
 The kernel evaluates GS states per thread block at a time.  A warp's 32 lanes are split into
 NSUB = 64 / GS *sub-groups* of GS / 2 lanes; every lane carries two neighbouring states (one

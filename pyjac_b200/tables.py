@@ -3,7 +3,7 @@
 This replaces the reference's *source generators* (pyjac/core/rate_subs.py and
 pyjac/core/create_jacobian.py): instead of unrolling the mechanism into C/CUDA text, the
 same information is exported once as flat arrays (packed with :mod:`pyjac_b200.blob`) that
-one fixed kernel family (pyjac_b200/csrc/pyjac_b200.cu) interprets.
+one fixed kernel family (pyjac_b200/csrc/eval.cuh) interprets.
 
 The kernel does not follow the generated code's statement order; it uses the algebraic
 structure of the emitted Jacobian (SURVEY.md section 7 / 8a'):
@@ -11,7 +11,7 @@ structure of the emitted Jacobian (SURVEY.md section 7 / 8a'):
     jac[k+1, j+1] = W_k/W_j * ( A_k + B_k * W_j/W_N + S_kj )
     A_k = sum_i nu_ki X1_i + wdot_k mw_avg/rho         B_k = sum_i nu_ki X2_i - wdot_k mw_avg/rho
     S_kj = sum over reactions i, sum over "raw" per-reaction derivative values r:
-           coef * raw[r]      (only for j among reactants/products/listed colliders of i)
+           nu * raw[r]        (only for j among reactants/products/listed colliders of i)
 
 so every Jacobian element is produced once, from a dense rank-2 part and a sparse gather.
 Where the generator prints a constant with a lossy format string and the difference can
@@ -20,28 +20,19 @@ pyjac/core/rate_subs.py, cj = pyjac/core/create_jacobian.py).
 
 Table reference (all reaction-indexed arrays are in *kernel order*, see ``rx_orig``):
 
-  dims      int32[16]  NSP NR NREV NPD NRAW NSUB NCON NCOEF FIRST_PM NPM NRED MAXRED
-                       NSUB_J NSPLIT NCHUNK ZERO_SLOT
+  dims      int32[16]  NSP NR NREV NPD NRAW - - - FIRST_PM NPM NRED MAXRED - - - -
   cst       f64[4]     RU ({:.8e}), ln(PA/RU)
   sp_*      per species (internal, moved-last order): w, iw (=1/W {:.16e}), ruw (=RU/W),
             tmid, mwf (=W_j/W_N), seen;  sp_nasa[k][branch][16] polynomial coefficients
   rx_*      orig (original reaction index), flags, rev_idx, pm_idx (positions in the
             reference's rev_rates / pres_mod arrays), raw_base, slots[6] (3 reactant + 3
-            product species, NSP = empty slot), arr[4] = lnA, b, Ta, sum(nu)*ln(PA/RU)
+            product species, NSP = empty slot), arr[4] = lnA, b, Ta, sum(nu)*ln(PA/RU),
+            dst[8] (raw row written per slot, first collider row, pres_mod_temp row);
+            the kernels read these through the packed records p5_rx / p5_rxout / p5_eff
   pm_*      per pressure-modified reaction (kernel index - FIRST_PM): collider list
             (eff_off/eff_sp/eff_am1 = alpha-1), sp (specific collider or -1), par[32]
-  rx_rec    the same per-reaction data as one 64-byte record (what the kernel loads)
-  red_*     per species CSR of (reaction, nu) for the species-side reductions;
-            chk_rx / chk_nu: the same lists cut into chunks of RCH pairs, sp_chk_off[k]
-  con       sparse sub-entries (<= SUBL contributions each, padded to 8 / 4 / 2 / 1 with
-            null contributions): classes J8 J4 J2 J1 T8 T4 T2 T1 in that order, class c holds
-            sub-entries [cls_sub[c], cls_sub[c+1]) and its contributions start at cls_con[c].
-            J: Jacobian entry (k, j), word = src | bf16(nu)<<16, result times sub_w (= W_k);
-            T: energy-equation row, word = src | reaction<<16 (coefficient = that reaction's
-            enthalpy change), result times -1/cp_avg
-  cmb_*     entries cut into several sub-entries: slot NSUB+t = sum of sub slots cmb_idx[...]
-  jmap      uint16[(NSP-1)*NSP]: (j, output row r) -> slot (ZERO_SLOT = always zero);
-            r = 0 is the energy-equation row, r >= 1 species r-1
+  red_*     per species CSR of (reaction, nu) (eval_spec_rates entry point, plan input)
+  p5_*      the records and the static work schedule of k_eval: see :mod:`pyjac_b200.plan`
 """
 from __future__ import annotations
 
@@ -54,7 +45,7 @@ from . import plan
 from .chem import PA, RU
 from .mechanism import Mechanism
 
-# flag bits shared with csrc/pyjac_b200.cu
+# flag bits shared with csrc/common.cuh
 F_REV, F_THD, F_PDEP, F_LOW, F_TROE, F_SRI = 1, 2, 4, 8, 16, 32
 F_PMT, F_PMT_INJ, F_TROE_T2, F_SRI5, F_SRI5_DT, F_NO_T = 64, 128, 256, 512, 1024, 2048
 F_EFFN1 = 4096         # third-body (non fall-off) reaction with a collider list: n' += 1
@@ -66,8 +57,6 @@ NRE_SHIFT, NPR_SHIFT = 20, 24    # occupied reactant / product slots
 MAXS = 3               # concentration slots per side of a reaction
 UNROLL = 40            # CParams.Jacob_Unroll (cj:2651): scope of the stale pres_mod_temp quirk
 NPAR = 32
-RCH = 8                # (reaction, nu) pairs per species-reduction chunk
-SUBL = 8               # contributions per sparse sub-entry
 
 
 class UnsupportedMechanism(NotImplementedError):
@@ -333,8 +322,8 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T['pm_eff_sp'] = i32(eff_sp if eff_sp else [0])
     T['pm_eff_am1'] = f64(eff_am1 if eff_am1 else [0.0])
 
-    # ---------------- species-side reductions: wdot, T column, A, B share one list per
-    # species, cut into chunks of RCH (reaction, nu) pairs (padded with nu = 0)
+    # ---------------- species-side reductions: wdot, T column, A, B share one (reaction, nu)
+    # list per species
     red = [[] for _ in range(nsp)]
     for p, i in enumerate(order):
         rx = reacs[i]
@@ -348,19 +337,6 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T['red_off'] = i32(red_off)
     T['red_rx'] = i32([p for lst in red for p, _ in lst] or [0])
     T['red_nu'] = f64([nu for lst in red for _, nu in lst] or [0.0])
-    chk_rx, chk_nu, sp_chk_off = [], [], [0]
-    for k in range(nsp):
-        lst = red[k]
-        for c0 in range(0, len(lst), RCH):
-            part = lst[c0:c0 + RCH]
-            part = part + [(0, 0.0)] * (RCH - len(part))
-            chk_rx += [p for p, _ in part]
-            chk_nu += [nu for _, nu in part]
-        sp_chk_off.append(len(chk_rx) // RCH)
-    nchunk = sp_chk_off[-1]
-    T['chk_rx'] = i32(chk_rx or [0] * RCH)
-    T['chk_nu'] = f64(chk_nu or [0.0] * RCH)
-    T['sp_chk_off'] = i32(sp_chk_off)
 
     # ---------------- sparse part: entry (k, j) <- sum coef * raw[src]
     contrib: Dict[tuple, list] = {}
@@ -406,90 +382,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
         elif i in stale_src and stale_src[i] is not None:
             tcontrib.setdefault(0, []).append((raw_of_pmt[stale_src[i]], p))
 
-    # sub-entries: at most SUBL contributions each; an entry cut into several sub-entries is
-    # summed by a short combine list afterwards.  Each sub-entry is padded to a power-of-two
-    # length (its class: 8, 4, 2 or 1 contributions) with null contributions that read the
-    # always-zero raw slot ``nraw``, so that the kernel runs fixed-length unrolled loops.
-    # kind 0: Jacobian entry, contribution = src | bf16(nu) << 16, result scaled by W_k;
-    # kind 1: energy row, contribution = src | reaction << 16 (coefficient = that reaction's
-    # enthalpy change), result scaled by -1/cp_avg.
-    def bf16_bits(c: float) -> int:
-        bits = int(np.float32(c).view(np.uint32))
-        if bits & 0xFFFF:
-            raise UnsupportedMechanism('stoichiometric coefficient %r not representable' % c)
-        return bits >> 16
-
-    def cls_len(n: int) -> int:
-        return 1 if n <= 1 else (2 if n <= 2 else (4 if n <= 4 else 8))
-
-    subs = []          # (kind, class length, owner, [packed contributions])
-    for kj, lst in contrib.items():
-        if kj[0] == last:
-            continue   # the last species has no Jacobian row; its enthalpy enters through dH
-        packed = [src | (bf16_bits(c) << 16) for src, c in lst]
-        for c0 in range(0, len(packed), SUBL):
-            piece = packed[c0:c0 + SUBL]
-            subs.append((0, cls_len(len(piece)), ('J',) + kj, piece))
-    for j, lst in tcontrib.items():
-        packed = [src | (p << 16) for src, p in lst]
-        for c0 in range(0, len(packed), SUBL):
-            piece = packed[c0:c0 + SUBL]
-            subs.append((1, cls_len(len(piece)), ('T', j), piece))
-    subs.sort(key=lambda s: (s[0], -s[1], s[2]))
-    nsub = len(subs)
-    nsub_j = sum(1 for s in subs if s[0] == 0)
-    by_owner: Dict[tuple, list] = {}
-    for ix, (_, _, owner, _) in enumerate(subs):
-        by_owner.setdefault(owner, []).append(ix)
-    split = [o for o, lst in by_owner.items() if len(lst) > 1]
-    nsplit = len(split)
-    zero_slot = nsub + nsplit
-    if zero_slot >= 0xFFFF:
-        raise UnsupportedMechanism('too many sparse Jacobian entries for 16-bit slots')
-    final_slot = {}
-    cmb_off, cmb_idx = [0], []
-    for t, o in enumerate(split):
-        final_slot[o] = nsub + t
-        cmb_idx += by_owner[o]
-        cmb_off.append(len(cmb_idx))
-    for o, lst in by_owner.items():
-        if len(lst) == 1:
-            final_slot[o] = lst[0]
-    con = []
-    cls_sub = [0] * 9      # sub index where each of the 8 (kind, length) classes starts
-    cls_con = [0] * 8      # offset of that class's first contribution in ``con``
-    sub_w = []
-    order_cls = [(0, 8), (0, 4), (0, 2), (0, 1), (1, 8), (1, 4), (1, 2), (1, 1)]
-    ix = 0
-    for c, (kind, ln) in enumerate(order_cls):
-        while len(con) % ln:
-            con.append(nraw)       # keep each class aligned to its own vector width
-        cls_sub[c] = ix
-        cls_con[c] = len(con)
-        while ix < nsub and (subs[ix][0], subs[ix][1]) == (kind, ln):
-            piece = subs[ix][3]
-            con += piece + [nraw] * (ln - len(piece))
-            sub_w.append(specs[subs[ix][2][1]].mw if kind == 0 else 0.0)
-            ix += 1
-    assert ix == nsub
-    cls_sub[8] = nsub
-    T['cls_sub'] = i32(cls_sub)
-    T['cls_con'] = i32(cls_con)
-    T['con'] = np.asarray(con + [nraw] * 8, dtype=np.uint32).view(np.int32)
-    T['sub_w'] = f64(sub_w or [0.0])
-    T['cmb_off'] = i32(cmb_off)
-    T['cmb_idx'] = i32(cmb_idx or [0])
-    # jmap[j][r]: output row r of column j+1 -> slot.  r = 0 is the energy-equation row,
-    # r >= 1 is species r-1.
-    jmap = np.full((nsp - 1, nsp), zero_slot, dtype=np.uint16)
-    for o, slot in final_slot.items():
-        if o[0] == 'J':
-            jmap[o[2], o[1] + 1] = slot
-        else:
-            jmap[o[1], 0] = slot
-    T['jmap'] = jmap.ravel()
-
-    # ---------------- v3 kernel tables -------------------------------------------------
+    # ---------------- raw rows written by each reaction
     # rx_dst[p][0..5]: raw slot written by concentration slot a (0xFFFF: none);
     # [6]: first collider-list raw slot, [7]: raw slot of pres_mod_temp (0xFFFF: none)
     NONE = 0xFFFF
@@ -503,63 +396,6 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
         if raw_of_pmt[i] >= 0:
             rx_dst[p, 7] = raw_of_pmt[i]
     T['rx_dst'] = rx_dst.ravel()
-
-    def hi16(c: float) -> int:
-        """Top 16 bits of the double c; the kernel rebuilds c as (hi16 << 48)."""
-        bits = int(np.float64(c).view(np.uint64))
-        if bits & ((1 << 48) - 1):
-            raise UnsupportedMechanism('stoichiometric coefficient %r not representable' % c)
-        return bits >> 48
-
-    # species reductions, one packed word per (reaction, nu): reaction | hi16(nu) << 16
-    T['red_pk'] = np.asarray([p | (hi16(nu) << 16) for lst in red for p, nu in lst] or [0],
-                             dtype=np.uint32).view(np.int32)
-
-    # sparse part, one entry per structurally non-zero Jacobian element.  dst = r + NSP*(j+1)
-    # with r the output row (0: energy equation, k+1: species k).  Entries with <= 8
-    # contributions go to the fixed-length classes (8, 4, 2, 1; one thread each, padded with
-    # null contributions); longer ones and every energy-row entry are summed by four lanes
-    # ("quad" entries, list padded to a multiple of 16 words, lane q takes words 4q..4q+3 of
-    # each 16).  J word: raw slot | hi16(nu) << 16; T word: raw slot | reaction << 16.
-    null_j = nraw                      # zero raw slot, coefficient +0.0
-    fixed = {8: [], 4: [], 2: [], 1: []}
-    quad_j, quad_t = [], []
-    for (k, j), lst in sorted(contrib.items()):
-        if k == last:
-            continue
-        words = [src | (hi16(c) << 16) for src, c in lst]
-        dst = (k + 1) + nsp * (j + 1)
-        if len(words) <= 8:
-            ln = cls_len(len(words))
-            fixed[ln].append((dst, words + [null_j] * (ln - len(words))))
-        else:
-            quad_j.append((dst, words))
-    for j, lst in sorted(tcontrib.items()):
-        quad_t.append((nsp * (j + 1), [src | (p << 16) for src, p in lst]))
-    d_dst, d_con, d_cls, d_ccon = [], [], [0], []
-    for ln in (8, 4, 2, 1):
-        while len(d_con) % 4:
-            d_con.append(null_j)
-        d_ccon.append(len(d_con))
-        for dst, words in fixed[ln]:
-            d_dst.append(dst)
-            d_con += words
-        d_cls.append(len(d_dst))
-    quad_j.sort(key=lambda e: -len(e[1]))
-    quad_t.sort(key=lambda e: -len(e[1]))
-    q_dst, q_off, q_con = [], [0], []
-    for dst, words in quad_j + quad_t:
-        q_dst.append(dst)
-        q_con += words + [null_j] * ((-len(words)) % 16)
-        q_off.append(len(q_con))
-    T['d_dst'] = np.asarray(d_dst or [0], dtype=np.uint16)
-    T['d_con'] = np.asarray(d_con + [null_j] * 8, dtype=np.uint32).view(np.int32)
-    T['d_cls'] = i32(d_cls)
-    T['d_ccon'] = i32(d_ccon)
-    T['q_dst'] = np.asarray(q_dst or [0], dtype=np.uint16)
-    T['q_off'] = i32(q_off)
-    T['q_con'] = np.asarray(q_con + [null_j] * 16, dtype=np.uint32).view(np.int32)
-    T['dims3'] = i32([len(d_dst), len(q_dst), len(quad_j), len(d_con), len(q_con), 0, 0, 0])
 
     # ---------------- schedule of the Jacobian kernel (plan.py)
     nt = threads or 512
@@ -623,7 +459,6 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T['p5_eff'] = i32(eff4 + [0, 0, sp_off(nsp), nraw + 1] * 4)
 
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
-    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, nsub, len(con), 0,
-                     first_pm, npm, red_off[-1], max(len(l) for l in red),
-                     nsub_j, nsplit, nchunk, zero_slot])
+    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, 0, 0, 0,
+                     first_pm, npm, red_off[-1], max(len(l) for l in red), 0, 0, 0, 0])
     return T

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-warp, per-phase cycle counts of block 0 of k_jacobian (development tool).
+"""Per-warp, per-phase cycle counts of block 0 of k_eval in Jacobian mode (development tool).
 Slots (a clock read may be scheduled before the barrier that precedes it, so a slot holds the
 warp's own work plus the wait at the previous barrier): 0 A1, 1 B, 2 -, 3 C, 4 dots/A0 + class S,
 5 class D, 6 class T, 7 -."""
