@@ -164,12 +164,11 @@ template <int GS, bool PM, int MODE>
 __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const IO& io, const Out& out,
                                          unsigned aSP, unsigned aRX,
                                          unsigned aRAW, unsigned aSC, int p, bool valid, bool three,
+                                         const int4 q0, const int4 q1, const int4 q2, const int4 q3,
                                          const V T, const V logT, const V iT)
 {
     constexpr int RB = GS * 8, SPB = SP_SLOTS * RB, RXB = RX_SLOTS * RB;
     const int nsp = tb.nsp, last = tb.nsp - 1;
-    const int4* rp = pl.rx + p * 4;
-    const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
     const double lnA = __hiloint2double(q0.y, q0.x), bexp = __hiloint2double(q0.w, q0.z);
     const double Ta = __hiloint2double(q1.y, q1.x), lnKc = __hiloint2double(q1.w, q1.z);
     const int fl = q2.x;
@@ -430,11 +429,10 @@ template <int GS, int MODE>
 __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl, const IO& io, const Out& out,
                                                unsigned aSP, unsigned aRX,
                                                unsigned aRAW, unsigned aSC, int p, bool valid, bool three,
+                                               const int4 q0, const int4 q1, const int4 q2, const int4 q3,
                                                const V T, const V logT, const V iT)
 {
     constexpr int RB = GS * 8, SPB = SP_SLOTS * RB, RXB = RX_SLOTS * RB;
-    const int4* rp = pl.rx + p * 4;
-    const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
     const double lnA = __hiloint2double(q0.y, q0.x), bexp = __hiloint2double(q0.w, q0.z);
     const double Ta = __hiloint2double(q1.y, q1.x), lnKc = __hiloint2double(q1.w, q1.z);
     const int fl = q2.x;
@@ -698,28 +696,38 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 sts<D_WDCP * RB>(aPA + warp * NPART * RB, wd);
             }
         }
+        // the first reaction record of phase B is requested before the barrier (tables come from L2)
+        const int b_r0 = __ldg(pl.b_off + warp), b_r1 = __ldg(pl.b_off + warp + 1);
+        const int b_rpm = b_r0 + __ldg(pl.b_npm + warp);
+        const int b_item0 = __ldg(pl.b_item + b_r0 * NSUB + sub);
+        int4 b_q0, b_q1, b_q2, b_q3;
+        {
+            const int4* rp = pl.rx + (b_item0 >= 0 ? b_item0 : (b_r0 < b_rpm ? tb.first_pm : 0)) * 4;
+            b_q0 = __ldg(rp); b_q1 = __ldg(rp + 1); b_q2 = __ldg(rp + 2); b_q3 = __ldg(rp + 3);
+        }
         __syncthreads();
         PJ_TICK(0)
 
         // ------------------------------------------------------------ phase B: reactions
         if (!(io.dbg_skip & 2)) {
             const V T = lds<Q_T * RB>(aSC), logT = lds<Q_LOGT * RB>(aSC), iT = lds<Q_IT * RB>(aSC);
-            const int r0 = __ldg(pl.b_off + warp), r1 = __ldg(pl.b_off + warp + 1);
-            const int rpm = r0 + __ldg(pl.b_npm + warp);
-            int item = r0 < r1 ? __ldg(pl.b_item + r0 * NSUB + sub) : -1;
-            for (int r = r0; r < r1; ++r) {
-                const int nxt = __ldg(pl.b_item + (r + 1) * NSUB + sub);    // the table ends with a null round
-                if (nxt >= 0) prefetch_l1(pl.rx + nxt * 4);
+            const unsigned nsp_f = sp_even<GS>(0u, (unsigned)nsp) / 16;
+            int item = b_item0;
+            int4 q0 = b_q0, q1 = b_q1, q2 = b_q2, q3 = b_q3;       // first record: requested before the barrier
+            for (int r = b_r0; r < b_r1; ++r) {
                 const bool valid = item >= 0;
-                if (r < rpm) {
-                    reaction<GS, true, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, valid ? item : tb.first_pm, valid, true, T, logT, iT);
+                const int p = valid ? item : (r < b_rpm ? tb.first_pm : 0);
+                if (r > b_r0) {
+                    const int4* rp = pl.rx + p * 4;
+                    q0 = __ldg(rp); q1 = __ldg(rp + 1); q2 = __ldg(rp + 2); q3 = __ldg(rp + 3);
+                }
+                const int nxt = __ldg(pl.b_item + (r + 1) * NSUB + sub);    // the table ends with a null round
+                if (r < b_rpm) {
+                    reaction<GS, true, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, p, valid, true, q0, q1, q2, q3, T, logT, iT);
                 } else {
-                    const int p = valid ? item : 0;
-                    const int4 c = __ldg(pl.rx + p * 4 + 2);
-                    const unsigned nsp_f = sp_even<GS>(0u, (unsigned)nsp) / 16;
-                    const bool has3 = ((c.z & 0xFFFFu) != nsp_f) || (((unsigned)c.w >> 16) != nsp_f);
+                    const bool has3 = ((q2.z & 0xFFFFu) != nsp_f) || (((unsigned)q2.w >> 16) != nsp_f);
                     const bool three = __any_sync(0xffffffffu, has3);
-                    reaction_plain<GS, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, p, valid, three, T, logT, iT);
+                    reaction_plain<GS, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, p, valid, three, q0, q1, q2, q3, T, logT, iT);
                 }
                 item = nxt;
             }
