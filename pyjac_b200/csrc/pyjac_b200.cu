@@ -59,25 +59,27 @@ int fail(int code, const std::string& msg)
                         std::string(#call) + ": " + cudaGetErrorString(e_));             \
     } while (0)
 
-template <int MODE>
+template <int MAXT, int MODE>
 const void* kernel_t(int gs)
 {
     switch (gs) {
-    case 2: return (const void*)pj5::k_eval<2, 512, MODE>;
-    case 4: return (const void*)pj5::k_eval<4, 512, MODE>;
-    case 8: return (const void*)pj5::k_eval<8, 512, MODE>;
-    case 16: return (const void*)pj5::k_eval<16, 512, MODE>;
-    case 32: return (const void*)pj5::k_eval<32, 512, MODE>;
+    case 2: return (const void*)pj5::k_eval<2, MAXT, MODE>;
+    case 4: return (const void*)pj5::k_eval<4, MAXT, MODE>;
+    case 8: return (const void*)pj5::k_eval<8, MAXT, MODE>;
+    case 16: return (const void*)pj5::k_eval<16, MAXT, MODE>;
+    case 32: return (const void*)pj5::k_eval<32, MAXT, MODE>;
     default: return nullptr;
     }
 }
 
-// k_eval for a plan's states per block and a mode (blocks are at most 512 threads)
-const void* kernel_for(int gs, int mode)
+// k_eval for a plan (states per block, block size <= 512) and a mode.  Blocks of up to 384
+// threads get the 168-register build, larger ones the 128-register build.
+const void* kernel_for(int gs, int mode, int nt)
 {
-    if (mode == pj::M_DYDT) return kernel_t<pj::M_DYDT>(gs);
-    if (mode == pj::M_RATES) return kernel_t<pj::M_RATES>(gs);
-    return kernel_t<pj::M_JAC>(gs);
+    const bool small = nt <= 384;
+    if (mode == pj::M_DYDT) return small ? kernel_t<384, pj::M_DYDT>(gs) : kernel_t<512, pj::M_DYDT>(gs);
+    if (mode == pj::M_RATES) return small ? kernel_t<384, pj::M_RATES>(gs) : kernel_t<512, pj::M_RATES>(gs);
+    return small ? kernel_t<384, pj::M_JAC>(gs) : kernel_t<512, pj::M_JAC>(gs);
 }
 
 // One launch of k_eval; the plan in the table blob fixes states per block and block size.
@@ -86,7 +88,7 @@ int launch(pyjac_mech* m, int mode, const IO& io, cudaStream_t st)
     if (io.n <= 0) return PYJAC_OK;
     CU(cudaSetDevice(m->device));
     const pj5::Plan& pl = m->plan;
-    const void* fn = kernel_for(pl.gs, mode);
+    const void* fn = kernel_for(pl.gs, mode, pl.nt);
     if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable plan");
     const size_t bytes = (size_t)pl.total * 8;
     if (!m->bpsm[mode]) {
@@ -202,7 +204,7 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
             pj5::Plan& pl = m->plan;
             int* o = &pl.gs;
             for (int i = 0; i < 14; ++i) o[i] = c5[i];
-            if (!kernel_for(pl.gs, pj::M_JAC) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
+            if (!kernel_for(pl.gs, pj::M_JAC, pl.nt) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
                 rc = fail(PYJAC_EINVAL, "bad plan configuration");
         }
     }

@@ -31,6 +31,7 @@ SMEM_LIMIT = 232448          # bytes of dynamic shared memory one block may opt 
 NSCAL = 24                   # per-state scalar rows: 2 x 8 from phase A0, 5 derived in DE
 NPART = 7                    # per-warp partial sums
 GS_CHOICES = (32, 16, 8, 4, 2)
+DEFAULT_THREADS = 384         # 12 warps with 168 registers each measured faster than 16 x 128
 SP_SLOTS, RX_SLOTS = 8, 5    # C B dB hW WA(Y) WB WT cp  /  net tT X1 X2 dH
 SLOT_WA, SLOT_WT, SLOT_CP = 4, 6, 7
 NULL_E = 0x3FFFFF            # element index of a padding element

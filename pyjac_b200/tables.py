@@ -398,7 +398,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T['rx_dst'] = rx_dst.ravel()
 
     # ---------------- schedule of the Jacobian kernel (plan.py)
-    nt = threads or 512
+    nt = threads or plan.DEFAULT_THREADS
     if not gs:
         gs = plan.choose_gs(nsp, nr, nraw, nt // 32)
         if not gs:
