@@ -63,11 +63,13 @@ template <int MAXT, int MODE>
 const void* kernel_t(int gs)
 {
     switch (gs) {
+#ifndef PJ_DEV_GS8_ONLY          // development builds (tools/): only the GRI-sized instantiation
     case 2: return (const void*)pj5::k_eval<2, MAXT, MODE>;
     case 4: return (const void*)pj5::k_eval<4, MAXT, MODE>;
-    case 8: return (const void*)pj5::k_eval<8, MAXT, MODE>;
     case 16: return (const void*)pj5::k_eval<16, MAXT, MODE>;
     case 32: return (const void*)pj5::k_eval<32, MAXT, MODE>;
+#endif
+    case 8: return (const void*)pj5::k_eval<8, MAXT, MODE>;
     default: return nullptr;
     }
 }

@@ -7,6 +7,7 @@ loudly if the in-tree CUDA library cannot be found or built; nothing here comput
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_size_t, c_void_p
 
 from . import libgen
@@ -59,7 +60,8 @@ def load(path: str = None) -> ctypes.CDLL:
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    lib_path = path or libgen.build_library()
+    # PYJAC_B200_LIB: a development build of the same library (tools/ A/B runs)
+    lib_path = path or os.environ.get('PYJAC_B200_LIB') or libgen.build_library()
     try:
         lib = ctypes.CDLL(lib_path)
     except OSError as exc:
