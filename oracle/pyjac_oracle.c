@@ -23,7 +23,7 @@
 
 enum { F_REV = 1, F_THD = 2, F_PDEP = 4, F_LOW = 8, F_TROE = 16, F_SRI = 32, F_EFF = 64,
        F_PDEPSP_TRUTHY = 128, F_NO_T = 256, F_TROE_T2 = 512, F_SRI5 = 1024, F_SRI5_DT = 2048,
-       F_PMT = 4096, F_PMT_IN_JTEMP = 8192, F_HAS_DBDT = 16384, F_KCJ_PREF = 32768 };
+       F_PMT = 4096, F_PMT_IN_JTEMP = 8192, F_HAS_DBDT = 16384, F_KCJ_PREF = 32768, F_PLOG = 65536 };
 
 typedef struct {
     int nsp, nr, nrev, npd;
@@ -43,6 +43,8 @@ typedef struct {
     const double *arr_main, *arr_k0, *arr_kinf, *arr_ratio;
     const double *troe_pm, *troe_j, *sri_pm, *sri_j, *rx_dt, *rx_pdt, *rx_drdy;
     const int *alpha_mode; const double *alpha_val;
+    const int *plog_off;
+    const double *plog_p4, *plog_arr, *plog_lp, *plog_dlp, *plog_dt, *plog_mid;
     const double *consts;
     void* blob;
 } OracleMech;
@@ -97,6 +99,8 @@ OracleMech* oracle_load(const void* src, size_t len)
     D(troe_pm, "troe_pm"); D(troe_j, "troe_j"); D(sri_pm, "sri_pm"); D(sri_j, "sri_j");
     D(rx_dt, "rx_dt"); D(rx_pdt, "rx_pdt"); D(rx_drdy, "rx_drdy");
     I(alpha_mode, "alpha_mode"); D(alpha_val, "alpha_val"); D(consts, "consts");
+    I(plog_off, "plog_off"); D(plog_p4, "plog_p4"); D(plog_arr, "plog_arr"); D(plog_lp, "plog_lp");
+    D(plog_dlp, "plog_dlp"); D(plog_dt, "plog_dt"); D(plog_mid, "plog_mid");
 #undef D
 #undef I
     return m;
@@ -117,6 +121,33 @@ static double arrhenius(const double* a, double T, double logT)
     case 2: return exp(a[1] - (a[3] / T));
     default: return exp(a[1] + a[2] * logT - (a[3] / T));
     }
+}
+
+/* PLOG pressure range of reaction i (rs:598-632): -1 below the first pressure, e in
+ * [o0, o1 - 1) between pressures e and e + 1, o1 - 1 above the last; -2 if no branch of the
+ * emitted if / else-if chain is taken (NaN pressure) */
+static int plog_range(const OracleMech* m, int i, double pres)
+{
+    const int o0 = m->plog_off[i], o1 = m->plog_off[i + 1];
+    if (pres <= m->plog_p4[o0]) return -1;
+    for (int e = o0; e + 1 < o1; ++e)
+        if ((pres > m->plog_p4[e]) && (pres <= m->plog_p4[e + 1])) return e;
+    if (pres > m->plog_p4[o1 - 1]) return o1 - 1;
+    return -2;
+}
+
+/* kf of a PLOG reaction as emitted (rs:598-632, cj:293-327); `kf` keeps its old value when
+ * no branch is taken */
+static double plog_kf(const OracleMech* m, int i, double T, double logT, double pres, double kf)
+{
+    const int o0 = m->plog_off[i], o1 = m->plog_off[i + 1];
+    const int e = plog_range(m, i, pres);
+    if (e == -1) return arrhenius(m->plog_arr + 4 * o0, T, logT);
+    if (e == o1 - 1) return arrhenius(m->plog_arr + 4 * (o1 - 1), T, logT);
+    if (e < 0) return kf;
+    kf = log(arrhenius(m->plog_arr + 4 * e, T, logT));
+    double kf2 = log(arrhenius(m->plog_arr + 4 * (e + 1), T, logT));
+    return exp(kf + (kf2 - kf) * (log(pres) - m->plog_lp[e]) / m->plog_dlp[e]);
 }
 
 /* C[a]*C[a]*C[b]*...: returns the left-assoc product with `tail` multiplied last.
@@ -168,10 +199,11 @@ void oracle_eval_conc(const OracleMech* m, double T, double pres, const double* 
 void oracle_eval_rxn_rates(const OracleMech* m, double T, double pres, const double* C,
                            double* fwd, double* rev)
 {
-    (void)pres;
     double logT = log(T);
+    double kf = 0.0;
     for (int i = 0; i < m->nr; ++i) {
-        double kf = arrhenius(m->arr_main + 4 * i, T, logT);
+        if (m->rx_flags[i] & F_PLOG) kf = plog_kf(m, i, T, logT, pres, kf);
+        else kf = arrhenius(m->arr_main + 4 * i, T, logT);
         fwd[i] = conc_prod_times(m->reac_sp + m->reac_off[i], m->reac_nu + m->reac_off[i],
                                  m->reac_off[i + 1] - m->reac_off[i], C, kf);
         if (m->rx_flags[i] & F_REV) {
@@ -403,7 +435,51 @@ void oracle_eval_jacob(const OracleMech* m, double t, double pres, const double*
             }
         }
 
+        /* PLOG (cj:1687-1850): below the first / above the last pressure the elementary form
+         * with that pressure's parameters; between two pressures the interpolated form */
+        int plog_e = -3;
+        double dtp[8];
+        if (fl & F_PLOG) {
+            const int o0 = m->plog_off[i], o1 = m->plog_off[i + 1];
+            plog_e = plog_range(m, i, pres);
+            if (plog_e == -1 || plog_e == o1 - 1) {
+                const double* pdt_ = m->plog_dt + 3 * (plog_e == -1 ? o0 : o1 - 1);
+                memcpy(dtp, dt, sizeof dtp);
+                dtp[0] = pdt_[0]; dtp[1] = pdt_[1]; dtp[2] = pdt_[2];
+                dt = dtp;
+                plog_e = -3;
+            }
+        }
+        if (plog_e >= 0) {
+            const double* q = m->plog_mid + 8 * plog_e;
+            double dk = 0.0;
+            int have = 0;
+            if (q[0] != 0.0) { dk = q[1]; have = 1; }
+            if (q[2] != 0.0) { dk = have ? dk + q[3] / T : q[3] / T; have = 1; }
+            {
+                double lp = (q[7] != 0.0) ? (log(pres) - m->plog_lp[plog_e]) : (log(pres));
+                double v = ((q[4] != 0.0) ? (q[5] + q[6] / T) : (q[6] / T)) * lp / m->plog_dlp[plog_e];
+                dk = have ? dk + v : v;
+            }
+            double elem = (dk) * (rev ? (f - r) : f);
+            if (dt[4] != 0.0) elem = elem + f * dt[3];
+            if (rev && ((fl & F_HAS_DBDT) || dt[6] != 0.0)) {
+                double inner;
+                if (fl & F_HAS_DBDT) {
+                    double sdb = 0.0;
+                    int o0 = m->db_off[i], o1 = m->db_off[i + 1];
+                    for (int e = o0; e < o1; ++e) {
+                        double v = (double)m->db_nu[e] * dBdT[m->db_sp[e]];
+                        sdb = (e == o0) ? v : sdb + v;
+                    }
+                    inner = (dt[6] != 0.0) ? dt[5] + -T * (sdb) : -T * (sdb);
+                } else inner = dt[5];
+                elem = elem - r * (inner);
+            }
+            j_temp = ((1.0 / T) * (elem)) * rho_inv;
+        }
         if (!(fl & F_NO_T)) {
+          if (plog_e == -3) {
             /* get_elementary_rxn_dt (cj:1426-1523) */
             double elem = 0.0;
             int dk_form = (int)dt[0];
@@ -470,6 +546,7 @@ void oracle_eval_jacob(const OracleMech* m, double t, double pres, const double*
             } else {
                 j_temp = ((1.0 / T) * (elem)) * rho_inv;
             }
+          }
 
             for (int e = m->net_off[i]; e < m->net_off[i + 1]; ++e) {
                 int k = m->net_sp[e], nu = m->net_nu[e];
@@ -528,7 +605,8 @@ void oracle_eval_jacob(const OracleMech* m, double t, double pres, const double*
             } else pres_mod_temp *= e1 / (1.0 + Pr);
         }
         /* write_rates (cj:290-338) */
-        kf = arrhenius(m->arr_main + 4 * i, T, logT);
+        if (fl & F_PLOG) kf = plog_kf(m, i, T, logT, pres, kf);
+        else kf = arrhenius(m->arr_main + 4 * i, T, logT);
         if (rev) kr = kf / Kc;
 
         const int* rs = m->reac_sp + m->reac_off[i];

@@ -6,8 +6,11 @@ the same format string, so that the C restatement -- which performs the run-time
 arithmetic in the emitted code's order -- reproduces the reference bit for bit where
 libm agrees.  Citations: rs = pyjac/core/rate_subs.py, cj = pyjac/core/create_jacobian.py.
 
-Scope: elementary, third-body and fall-off (Lindemann / Troe / SRI, LOW or HIGH)
-reactions with integer stoichiometric coefficients and positive pre-exponentials.
+Scope: elementary, third-body, fall-off (Lindemann / Troe / SRI, LOW or HIGH) and PLOG
+reactions with integer stoichiometric coefficients and positive pre-exponentials.  PLOG is
+restated for the inputs the generator emits valid C for: every two consecutive pressures
+must have different activation energies (cj:1759-1770 builds an unbalanced expression
+otherwise).
 """
 from __future__ import annotations
 
@@ -23,6 +26,7 @@ from pyjac_b200.mechanism import Mechanism
 F_REV, F_THD, F_PDEP, F_LOW, F_TROE, F_SRI, F_EFF = 1, 2, 4, 8, 16, 32, 64
 F_PDEPSP_TRUTHY, F_NO_T, F_TROE_T2, F_SRI5, F_SRI5_DT = 128, 256, 512, 1024, 2048
 F_PMT, F_PMT_IN_JTEMP, F_HAS_DBDT, F_KCJ_PREF = 4096, 8192, 16384, 32768
+F_PLOG = 65536
 
 UNROLL = 40   # CParams.Jacob_Unroll: conc_temp collapsing restarts every 40 reactions
 
@@ -132,8 +136,10 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     i32 = lambda x: np.asarray(x, dtype=np.int32)
 
     for rx in reacs:
-        if rx.plog or rx.cheb:
-            raise NotImplementedError('PLOG / Chebyshev reactions')
+        if rx.cheb:
+            raise NotImplementedError('Chebyshev reactions')
+        if rx.plog and (rx.pdep or rx.thd_body or len(rx.plog_par) < 2):
+            raise NotImplementedError('PLOG reaction with a third body / fewer than two pressures')
         if not all(is_int(v) for v in rx.reac_nu + rx.prod_nu):
             raise NotImplementedError('non-integer stoichiometric coefficients')
 
@@ -210,10 +216,37 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     alpha_mode = np.zeros((nr, max(nsp - 1, 1)), dtype=np.int32)
     alpha_val = np.zeros((nr, max(nsp - 1, 1)))
 
+    plog_off, plog_p4, plog_arr, plog_lp, plog_dlp, plog_dt, plog_mid = [0], [], [], [], [], [], []
+
     last_conc_temp = None
     do_unroll = nr > UNROLL
     for i, rx in enumerate(reacs):
         fl = 0
+        if rx.plog:
+            # rs:598-632 / cj:293-327 (rate constant), cj:1687-1850 (temperature derivative)
+            fl |= F_PLOG
+            pp = rx.plog_par
+            for e, (p1, A1, b1, E1) in enumerate(pp):
+                plog_p4.append(q('{:.4e}', p1))
+                plog_arr.append(arrhenius_form(A1, b1, E1))
+                plog_lp.append(q('{:.16e}', math.log(p1)))
+                b_on, E_on = abs(b1) > 1.0e-90, abs(E1) > 1.0e-90
+                if not rx.rev and not b_on and not E_on and sum(rx.reac_nu) == 1.0:
+                    raise NotImplementedError('PLOG end range without a temperature derivative')
+                plog_dt.append([(1 if b_on else 0) | (2 if E_on else 0), q('{:.16e}', b1), q('{:.16e}', E1)])
+                if e + 1 < len(pp):
+                    p2, A2, b2, E2 = pp[e + 1]
+                    if A2 / A1 < 0 or E2 - E1 == 0.0 or p1 == p2:
+                        raise NotImplementedError('PLOG pair the generator emits no valid C for')
+                    plog_dlp.append(q('{:.16e}', math.log(p2) - math.log(p1)))
+                    plog_mid.append([1.0 if b1 != 0.0 else 0.0, q('{:.16e}', b1),
+                                     1.0 if E1 != 0.0 else 0.0, q('{:.16e}', E1),
+                                     1.0 if b2 - b1 != 0.0 else 0.0, q('{:.16e}', b2 - b1),
+                                     q('{:.16e}', E2 - E1), 1.0 if p1 != 1.0 else 0.0])
+                else:
+                    plog_dlp.append(0.0)
+                    plog_mid.append([0.0] * 8)
+        plog_off.append(len(plog_p4))
         if rx.rev:
             fl |= F_REV
             rev_idx[i] = rev_reacs.index(i)
@@ -290,7 +323,7 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
         dt[i] = [dk_form, q('{:.16e}', rx.b), q('{:.16e}', rx.E),
                  float(str(1. - float(rnu))), 1.0 if rnu != 1.0 else 0.0,
                  float(str(1. - float(pnu))), 1.0 if pnu != 1.0 else 0.0, 0.0]
-        if not rx.rev and not dk_form and rnu == 1.0:
+        if not rx.rev and not dk_form and rnu == 1.0 and not rx.plog:
             fl |= F_NO_T
 
         if rx.pdep:
@@ -439,6 +472,13 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     T['troe_j'] = troe_j.ravel()
     T['sri_pm'] = sri_pm.ravel()
     T['sri_j'] = sri_j.ravel()
+    T['plog_off'] = i32(plog_off)
+    T['plog_p4'] = f64(plog_p4 or [0.0])
+    T['plog_arr'] = f64(plog_arr or [[0.0] * 4]).ravel()
+    T['plog_lp'] = f64(plog_lp or [0.0])
+    T['plog_dlp'] = f64(plog_dlp or [0.0])
+    T['plog_dt'] = f64(plog_dt or [[0.0] * 3]).ravel()
+    T['plog_mid'] = f64(plog_mid or [[0.0] * 8]).ravel()
     T['rx_dt'] = dt.ravel()
     T['rx_pdt'] = pdt.ravel()
     T['rx_drdy'] = drdy.ravel()

@@ -91,7 +91,13 @@ class Reaction:
     sri_par: List[float] = field(default_factory=list)
     rev_par: List[float] = field(default_factory=list)
     plog: bool = False
+    plog_par: list = field(default_factory=list)       # [[P (Pa), A, b, E (K)], ...] in file order
     cheb: bool = False
+    cheb_n_temp: int = 0
+    cheb_n_pres: int = 0
+    cheb_par: list = field(default_factory=list)       # flat while parsing, (n_temp, n_pres) array after
+    cheb_plim: List[float] = field(default_factory=list)   # [Pmin, Pmax] (Pa)
+    cheb_tlim: List[float] = field(default_factory=list)   # [Tmin, Tmax] (K)
 
     def net_nu(self, isp) -> float:
         """Net stoichiometric coefficient of species ``isp`` (utils.get_nu,

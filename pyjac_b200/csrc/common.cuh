@@ -10,6 +10,7 @@ enum : int {
     F_REV = 1, F_THD = 2, F_PDEP = 4, F_LOW = 8, F_TROE = 16, F_SRI = 32, F_PMT = 64,
     F_PMT_INJ = 128, F_TROE_T2 = 256, F_SRI5 = 512, F_SRI5_DT = 1024, F_NO_T = 2048,
     F_EFFN1 = 4096, F_HAS_LAST = 1 << 13, F_WANT_PMT = 1 << 16, F_EFF_SLOTS = 1 << 17,
+    F_PLOG = 1 << 18,
     NRE_SHIFT = 20, NPR_SHIFT = 24, NPAR = 32
 };
 
@@ -29,6 +30,11 @@ struct Tables {
     const int *red_off, *red_rx;
     const double* red_nu;
     const int4* rx_out;              // {fwd index, rev index or -1, pres_mod index or -1, 0}
+    // PLOG reactions: entries plog_off[p] .. plog_off[p + 1] of plog_par[][8] = {threshold (Pa),
+    // ln A, b, Ta, ln P, 1 / (ln P' - ln P), b' - b, Ta' - Ta}; nplog = 0: no such reaction
+    int nplog;
+    const int* plog_off;
+    const double* plog_par;
 };
 
 struct IO {

@@ -60,8 +60,8 @@ struct Plan {
 };
 
 // per-state scalars: phase A0 writes Q_* (two buffers of 8 rows), phase DE derives S_*
-enum : int { Q_T = 0, Q_LOGT, Q_IT, Q_RHO, Q_RHOINV, Q_NMWR, Q_MWR, Q_M };
-enum : int { S_NWT = 0, S_A0, S_B0, S_XT, S_CPL, NQ = 24 };
+enum : int { Q_T = 0, Q_LOGT, Q_IT, Q_RHO, Q_RHOINV, Q_LNP, Q_MWR, Q_M };     // Q_LNP: only with PLOG reactions
+enum : int { S_NWT = 0, S_A0, S_B0, S_XT, S_CPL, S_P = 5, NQ = 24 };   // S_P + buffer: pressure (PLOG)
 enum : int { D_H1 = 0, D_HA, D_HB, D_HT, D_SCP, D_CPAVG, D_WDCP, NPART = 7 };
 // A species owns SP_SLOTS rows.  Even slots (C, dB, WA, WT) are read at E + {0, 2, 4, 6} rows, odd
 // slots (B, hW, WB, cp) at O + {0, 2, 4, 6} rows, where E = region + k * SPB + (k & 1) * RB is the
@@ -338,7 +338,7 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
 
     // ---- Jacobian scalars
     const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
-    const V rho_inv = lds<Q_RHOINV * RB>(aSC), nmwr = lds<Q_NMWR * RB>(aSC);
+    const V rho_inv = lds<Q_RHOINV * RB>(aSC), mwr_ = lds<Q_MWR * RB>(aSC), nmwr{-mwr_.x, -mwr_.y};
     const double extra = (PM && (fl & F_EFFN1)) ? 1.0 : 0.0;
     const double n1 = nre + extra, n2 = npr + extra, omre = 1.0 - nre, ompr = 1.0 - npr;
     V tT, X1, X2;
@@ -428,7 +428,7 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
 template <int GS, int MODE>
 __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl, const IO& io, const Out& out,
                                                unsigned aSP, unsigned aRX,
-                                               unsigned aRAW, unsigned aSC, int p, bool valid, bool three,
+                                               unsigned aRAW, unsigned aSC, unsigned aPL, int p, bool valid, bool three,
                                                const int4 q0, const int4 q1, const int4 q2, const int4 q3,
                                                const V T, const V logT, const V iT)
 {
@@ -452,7 +452,35 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
         sdB = vadd(sdB, vsub(lds<E_DB * RB>(a5), lds<E_DB * RB>(a2)));
         dH = vadd(dH, vsub(lds<O_HW * RB>(a5 ^ RB), lds<O_HW * RB>(a2 ^ RB)));
     }
-    const V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
+    V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
+    V dk{fma(Ta, iT.x, bexp), fma(Ta, iT.y, bexp)};          // d ln kf / d ln T
+    if (fl & F_PLOG) {
+        // rate constant of a PLOG reaction (rs:598-632) and its temperature derivative
+        // (cj:1687-1850): the Arrhenius set of the first / last pressure outside the table,
+        // linear interpolation of ln kf in ln P between two pressures
+        const int o0 = __ldg(tb.plog_off + p), o1 = __ldg(tb.plog_off + p + 1);
+        const V Pv = lds<S_P * RB>(aPL), lP = lds<Q_LNP * RB>(aSC);
+        const double Ps[2] = {Pv.x, Pv.y}, lPs[2] = {lP.x, lP.y}, lTs[2] = {logT.x, logT.y}, rTs[2] = {iT.x, iT.y};
+        double lk[2], dkk[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            int e = o0;
+            while (e < o1 && Ps[g] > __ldg(tb.plog_par + 8 * e)) ++e;
+            const bool mid = e > o0 && e < o1;
+            const double* q = tb.plog_par + 8 * (e > o0 ? e - 1 : o0);
+            const double A1 = __ldg(q + 1), b1 = __ldg(q + 2), E1 = __ldg(q + 3);
+            double k = fma(b1, lTs[g], fma(-E1, rTs[g], A1)), d = fma(E1, rTs[g], b1);
+            if (mid) {
+                const double k2 = fma(__ldg(q + 10), lTs[g], fma(-__ldg(q + 11), rTs[g], __ldg(q + 9)));
+                const double w = (lPs[g] - __ldg(q + 4)) * __ldg(q + 5);
+                k = fma(k2 - k, w, k);
+                d = fma(fma(__ldg(q + 7), rTs[g], __ldg(q + 6)), w, d);
+            }
+            lk[g] = k; dkk[g] = d;
+        }
+        lnkf = V{lk[0], lk[1]};
+        dk = V{dkk[0], dkk[1]};
+    }
     const double ex[4] = {lnkf.x, lnkf.y, lnkf.x - sB.x - lnKc, lnkf.y - sB.y - lnKc};
     double ev[4];
     exp_n<4>(ex, ev);
@@ -476,8 +504,7 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     }
     const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
     const double omre = 1.0 - nre, ompr = 1.0 - npr;
-    const V rho_inv = lds<Q_RHOINV * RB>(aSC), nmwr = lds<Q_NMWR * RB>(aSC);
-    const V dk{fma(Ta, iT.x, bexp), fma(Ta, iT.y, bexp)};
+    const V rho_inv = lds<Q_RHOINV * RB>(aSC), mwr_ = lds<Q_MWR * RB>(aSC), nmwr{-mwr_.x, -mwr_.y};
     // irreversible: r = 0 makes this f * (dk + 1 - nre)          (cj:1461-1523)
     V elem = vfma(net, dk, vmul(omre, f));
     elem = V{elem.x - r.x * (ompr - T.x * sdB.x), elem.y - r.y * (ompr - T.y * sdB.y)};
@@ -606,7 +633,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 }
                 o[Q_T][g2] = T[g2]; o[Q_LOGT][g2] = log(T[g2]); o[Q_IT][g2] = 1.0 / T[g2];
                 o[Q_RHO][g2] = rho; o[Q_RHOINV][g2] = rho_inv;
-                o[Q_NMWR][g2] = -mw * rho_inv; o[Q_MWR][g2] = mw * rho_inv;
+                o[Q_LNP][g2] = tb.nplog ? log(P[g2]) : 0.0; o[Q_MWR][g2] = mw * rho_inv;
                 o[Q_M][g2] = P[g2] / (tb.ru * T[g2]);
             }
             const unsigned a = aSC0 + b * SCB;
@@ -616,9 +643,10 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             sts<Q_IT * RB>(a, V{o[Q_IT][0], o[Q_IT][1]});
             sts<Q_RHO * RB>(a, V{o[Q_RHO][0], o[Q_RHO][1]});
             sts<Q_RHOINV * RB>(a, V{o[Q_RHOINV][0], o[Q_RHOINV][1]});
-            sts<Q_NMWR * RB>(a, V{o[Q_NMWR][0], o[Q_NMWR][1]});
+            sts<Q_LNP * RB>(a, V{o[Q_LNP][0], o[Q_LNP][1]});
             sts<Q_MWR * RB>(a, V{o[Q_MWR][0], o[Q_MWR][1]});
             sts<Q_M * RB>(a, V{o[Q_M][0], o[Q_M][1]});
+            if (tb.nplog) sts<S_P * RB>(aSD + b * RB, V{P[0], P[1]});
         }
     };
 
@@ -727,7 +755,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 } else {
                     const bool has3 = ((q2.z & 0xFFFFu) != nsp_f) || (((unsigned)q2.w >> 16) != nsp_f);
                     const bool three = __any_sync(0xffffffffu, has3);
-                    reaction_plain<GS, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, p, valid, three, q0, q1, q2, q3, T, logT, iT);
+                    reaction_plain<GS, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
                 }
                 item = nxt;
             }

@@ -9,13 +9,14 @@ third-body efficiencies (``:655-661``), Troe ``T3``/``T1`` of zero bumped to 1e-
 (``:551-557``), explicit-REV reactions split into two irreversible ones
 (``:693-713``) and NASA-7 fixed-column thermo blocks (``:735-883``).
 
-PLOG / Chebyshev reactions are recognised and rejected loudly: they are outside the
-current hot-path scope (DESIGN.md "out of scope").
+PLOG and Chebyshev auxiliary lines are read as the reference reads them (``:589-654``,
+``:664-680``); which of them the kernels evaluate is decided in :mod:`pyjac_b200.tables`.
 """
 from __future__ import annotations
 
 import copy
 import logging
+import math
 import re
 from typing import List, Optional, Tuple
 
@@ -197,6 +198,20 @@ def read_mech(mech_filename: str, therm_filename: Optional[str] = None):
             else:
                 _parse_aux_line(line, reacs[-1], units_A, units_E)
 
+    # Chebyshev coefficient count, units of the first coefficient, (n_T, n_P) shape (:664-680)
+    for idx, rx in enumerate(reacs):
+        if rx.cheb:
+            n_t, n_p = rx.cheb_n_temp, rx.cheb_n_pres
+            if len(rx.cheb_par) != n_t * n_p:
+                raise MechanismError('incorrect number of CHEB coefficients in reaction %d' % idx)
+            if not rx.cheb_plim or not rx.cheb_tlim:
+                raise MechanismError('Chebyshev reaction %d without PCHEB / TCHEB limits' % idx)
+            if units_A == 'moles':
+                rx.cheb_par[0] += math.log10(0.001 ** (sum(rx.reac_nu) - 1.))
+            rx.cheb_par = [rx.cheb_par[r * n_p:(r + 1) * n_p] for r in range(n_t)]
+        if rx.plog and len(rx.plog_par) < 2:
+            raise MechanismError('PLOG reaction %d needs at least two pressures' % idx)
+
     # species named in reactions must exist (mech_interpret.py:682-691)
     known = set(sp.name for sp in specs)
     for idx, rx in enumerate(reacs):
@@ -329,10 +344,40 @@ def _parse_aux_line(line: str, rx: Reaction, units_A: str, units_E: str) -> None
         rx.sri_par = [float(t[1]), float(t[2]), float(t[3])]
         if len(t) > 4:
             rx.sri_par += [float(t[4]), float(t[5])]
-    elif key in ('che', 'pch', 'tch'):
-        raise NotImplementedError('Chebyshev reactions are outside the supported hot path')
+    elif key == 'che':
+        # CHEB / n_T n_P c.. / on the first line, further coefficients on later CHEB lines
+        # (mech_interpret.py:589-606); a Chebyshev reaction is not a fall-off reaction
+        t = line.replace('/', ' ').split()
+        if not rx.cheb:
+            rx.cheb = True
+            rx.pdep = False
+            rx.cheb_n_temp, rx.cheb_n_pres = int(t[1]), int(t[2])
+            rx.cheb_par = [float(v) for v in t[3:]]
+        else:
+            rx.cheb_par += [float(v) for v in t[1:]]
+    elif key == 'pch':
+        t = line.replace('/', ' ').split()                                    # :607-620
+        rx.cheb_plim = [float(t[1]) * PA, float(t[2]) * PA]
+        if len(t) > 3 and t[3].lower() == 'tcheb':
+            rx.cheb_tlim = [float(t[4]), float(t[5])]
+    elif key == 'tch':
+        t = line.replace('/', ' ').split()                                    # :621-631
+        rx.cheb_tlim = [float(t[1]), float(t[2])]
+        if len(t) > 3 and t[3].lower() == 'pcheb':
+            rx.cheb_plim = [float(t[4]) * PA, float(t[5]) * PA]
     elif key == 'plo':
-        raise NotImplementedError('PLOG reactions are outside the supported hot path')
+        # PLOG / P(atm) A b E /, one line per pressure (mech_interpret.py:632-654)
+        t = line.replace('/', ' ').split()
+        if not rx.plog:
+            rx.plog = True
+            rx.pdep = False
+            rx.plog_par = []
+        pars = [float(v) for v in t[1:5]]
+        pars[0] *= 101325.0
+        pars[3] *= _E_FACT[units_E]
+        if units_A == 'moles':
+            pars[1] /= 1000. ** (sum(rx.reac_nu) - 1.)
+        rx.plog_par.append(pars)
     else:
         t = line.replace('/', ' ').split()
         if len(t) % 2:

@@ -28,7 +28,7 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 SMEM_LIMIT = 232448          # bytes of dynamic shared memory one block may opt in to (sm_100)
-NSCAL = 24                   # per-state scalar rows: 2 x 8 from phase A0, 5 derived in DE
+NSCAL = 24                   # per-state scalar rows: 2 x 8 from phase A0, 5 derived in DE, 2 x P (PLOG)
 NPART = 7                    # per-warp partial sums
 GS_CHOICES = (32, 16, 8, 4, 2)
 DEFAULT_THREADS = 384         # 12 warps with 168 registers each measured faster than 16 x 128
@@ -42,6 +42,7 @@ MAX_L2 = 1023
 COST_PLAIN, COST_IRREV, COST_THREE = 215.0, 150.0, 40.0
 COST_PM = {'thd': 300.0, 'lind': 450.0, 'troe': 900.0, 'sri': 1200.0}
 COST_EFF = 8.0
+COST_PLOG = 120.0
 COST_C_ITEM, COST_C_IT = 90.0, 28.0
 # phase DE costs are in units of 22 cycles, fitted to per-warp clock measurements on a B200
 # (tools/phase_clocks.py): the classes are bound by shared-memory / L2 latency, not by issue
@@ -127,7 +128,7 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
                tcontrib: Dict[int, List[Tuple[int, int]]], sp_w: Sequence[float],
                sp_iw: Sequence[float], sp_mwf: Sequence[float], gs: int, nt: int
                ) -> Dict[str, np.ndarray]:
-    """kinds[p] in {'plain','thd','lind','troe','sri'} per kernel-order reaction p;
+    """kinds[p] in {'plain','plog','thd','lind','troe','sri'} per kernel-order reaction p;
     contrib[(k, j)] = [(raw row, nu)], tcontrib[j] = [(raw row, reaction)]."""
     assert gs in GS_CHOICES and nt % 32 == 0 and 64 <= nt <= 512
     if nsp > 2000:
@@ -141,7 +142,7 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
 
     # ---------------------------------------------------------------- phase B
     pm = list(range(first_pm, nr))
-    plain = sorted(range(first_pm), key=lambda p: (has3[p], not is_rev[p], p))
+    plain = sorted(range(first_pm), key=lambda p: (has3[p], kinds[p] == 'plog', not is_rev[p], p))
     rounds: List[Tuple[bool, List[int], float]] = []
     for c0 in range(0, len(pm), nsub):
         grp = pm[c0:c0 + nsub]
@@ -154,6 +155,8 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
         cost = COST_PLAIN if any(is_rev[p] for p in grp) else COST_IRREV
         if any(has3[p] for p in grp):
             cost += COST_THREE
+        if any(kinds[p] == 'plog' for p in grp):
+            cost += COST_PLOG
         rounds.append((False, grp, cost))
     bins, _ = _lpt([r[2] for r in rounds], nw)
     b_off, b_npm, b_item = [0], [], []

@@ -20,7 +20,7 @@ pyjac/core/rate_subs.py, cj = pyjac/core/create_jacobian.py).
 
 Table reference (all reaction-indexed arrays are in *kernel order*, see ``rx_orig``):
 
-  dims      int32[16]  NSP NR NREV NPD NRAW - - - FIRST_PM NPM NRED MAXRED - - - -
+  dims      int32[16]  NSP NR NREV NPD NRAW NPLOG - - FIRST_PM NPM NRED MAXRED - - - -
   cst       f64[4]     RU ({:.8e}), ln(PA/RU)
   sp_*      per species (internal, moved-last order): w, iw (=1/W {:.16e}), ruw (=RU/W),
             tmid, mwf (=W_j/W_N), seen;  sp_nasa[k][branch][16] polynomial coefficients
@@ -29,6 +29,8 @@ Table reference (all reaction-indexed arrays are in *kernel order*, see ``rx_ori
             product species, NSP = empty slot), arr[4] = lnA, b, Ta, sum(nu)*ln(PA/RU),
             dst[8] (raw row written per slot, first collider row, pres_mod_temp row);
             the kernels read these through the packed records p5_rx / p5_rxout / p5_eff
+  plog_*    off[NR + 1] (kernel order) into par[NPLOG][8] = threshold ({:.4e} Pa), ln A, b, Ta,
+            ln P, 1 / (ln P' - ln P), b' - b, Ta' - Ta
   pm_*      per pressure-modified reaction (kernel index - FIRST_PM): collider list
             (eff_off/eff_sp/eff_am1 = alpha-1), sp (specific collider or -1), par[32]
   red_*     per species CSR of (reaction, nu) (eval_spec_rates entry point, plan input)
@@ -52,6 +54,7 @@ F_EFFN1 = 4096         # third-body (non fall-off) reaction with a collider list
 F_HAS_LAST = 1 << 13   # (Jacobian kernel record only) an occupied slot holds the last species
 F_WANT_PMT = 1 << 16   # the kernel stores pres_mod_temp as a raw value
 F_EFF_SLOTS = 1 << 17  # ... and pres_mod_temp * (alpha_j - 1) for each listed collider j
+F_PLOG = 1 << 18       # rate constant interpolated in log P between Arrhenius sets (plog_*)
 NRE_SHIFT, NPR_SHIFT = 20, 24    # occupied reactant / product slots
 
 MAXS = 3               # concentration slots per side of a reaction
@@ -101,8 +104,16 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T: Dict[str, np.ndarray] = {}
 
     for i, rx in enumerate(reacs):
-        if rx.plog or rx.cheb:
-            raise UnsupportedMechanism('PLOG / Chebyshev reactions (reaction %d)' % i)
+        if rx.cheb:
+            raise UnsupportedMechanism('Chebyshev reactions (reaction %d)' % i)
+        if rx.plog:
+            pp = rx.plog_par
+            if rx.pdep or rx.thd_body:
+                raise UnsupportedMechanism('PLOG reaction %d with a third body' % i)
+            if len(pp) < 2 or any(not e[1] > 0 for e in pp) or \
+                    any(q('{:.4e}', pp[e + 1][0]) <= q('{:.4e}', pp[e][0]) for e in range(len(pp) - 1)):
+                # the reference does not handle these either (cj:1744-1749, 1768)
+                raise UnsupportedMechanism('PLOG reaction %d: pressures must ascend, A > 0' % i)
         if not rx.A > 0:
             raise UnsupportedMechanism('non-positive pre-exponential (reaction %d)' % i)
         if rx.pdep and not (rx.low or rx.high):
@@ -146,6 +157,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
             stale_src[i] = src[-1] if src else None
 
     flags, rev_idx, pm_idx, raw_base = [], [], [], []
+    plog_off, plog_par = [0], []
     slots = np.full((nr, 2 * MAXS), nsp, dtype=np.int32)
     arr = np.zeros((nr, 4))
     pm_par = np.zeros((max(npm, 1), NPAR))
@@ -201,8 +213,22 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
         if rx.thd_body_eff and not rx.pdep:
             fl |= F_EFFN1                                                      # cj:201-206
         b_on, E_on = abs(rx.b) > 1.0e-90, abs(rx.E) > 1.0e-90
-        if not rx.rev and not b_on and not E_on and sum(rx.reac_nu) == 1.0:
+        if not rx.rev and not b_on and not E_on and sum(rx.reac_nu) == 1.0 and not rx.plog:
             fl |= F_NO_T                                                       # cj:1507-1523
+        if rx.plog:
+            # per pressure: threshold as printed ({:.4e}: rs:601-629), ln A, b, Ta, ln P, and towards
+            # the next pressure 1 / (ln P' - ln P), b' - b, Ta' - Ta  (rs:598-632, cj:1738-1770)
+            fl |= F_PLOG
+            pp = rx.plog_par
+            for e, (p1, A1, b1, E1) in enumerate(pp):
+                row = [q('{:.4e}', p1), q('{:.16e}', math.log(A1)), b1, q('{:.16e}', E1),
+                       q('{:.16e}', math.log(p1)), 0.0, 0.0, 0.0]
+                if e + 1 < len(pp):
+                    p2, _, b2, E2 = pp[e + 1]
+                    row[5:8] = [1.0 / q('{:.16e}', math.log(p2) - math.log(p1)),
+                                q('{:.16e}', b2 - b1), q('{:.16e}', E2 - E1)]
+                plog_par.append(row)
+        plog_off.append(len(plog_par))
         rev_idx.append(rev_reacs.index(i) if rx.rev else -1)
         pm_idx.append(pdep_reacs.index(i) if (rx.thd_body or rx.pdep) else -1)
         if want_pmt[i]:
@@ -316,6 +342,8 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T['rx_raw_base'] = i32(raw_base)
     T['rx_slots'] = slots.ravel()
     T['rx_arr'] = arr.ravel()
+    T['plog_off'] = i32(plog_off)
+    T['plog_par'] = f64(plog_par or [[0.0] * 8]).ravel()
     T['pm_par'] = pm_par.ravel()
     T['pm_sp'] = pm_sp
     T['pm_eff_off'] = i32(eff_off)
@@ -407,7 +435,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     for p, i in enumerate(order):
         rx = reacs[i]
         kinds.append('sri' if rx.sri else 'troe' if rx.troe else 'lind' if rx.pdep else
-                     'thd' if rx.thd_body else 'plain')
+                     'thd' if rx.thd_body else 'plog' if rx.plog else 'plain')
         n_eff.append(sum(1 for s, a in rx.thd_body_eff if a != 1.0) if (rx.thd_body or rx.pdep) else 0)
     T.update(plan.build_plan(nsp, nr, nraw, first_pm, kinds, [bool(reacs[i].rev) for i in order],
                              [bool(slots[p, 2] != nsp or slots[p, 5] != nsp) for p in range(nr)],
@@ -459,6 +487,6 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T['p5_eff'] = i32(eff4 + [0, 0, sp_off(nsp), nraw + 1] * 4)
 
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
-    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, 0, 0, 0,
+    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, len(plog_par), 0, 0,
                      first_pm, npm, red_off[-1], max(len(l) for l in red), 0, 0, 0, 0])
     return T

@@ -13,6 +13,9 @@ evaluates the emitted C on fixed states and stores inputs and outputs:
     tests/golden/usc2_syn.npz      USC-Mech-II-shaped synthetic mechanism (111 sp / 784 rxn, species with
                                    different T_mid), 8 synthetic states
 
+    tests/golden/plog_syn.npz      PLOG coverage mechanism over the H2/O2 species, 192 synthetic states of
+                                   which 32 below and 32 above every pressure table
+
 Arrays are in pyJac's internal (moved-last) species order, row-major per state:
 P[n], y[n,NSP] = [T, Y_0..Y_{NSP-2}], conc, fwd, rev, pres_mod, spec_rates, dydt, jac[n,NSP*NSP]
 (column-major inside a state).
@@ -68,3 +71,11 @@ if __name__ == '__main__':
     mech = Mechanism.from_chemkin(usc)
     P, y = synthetic_states(mech.NSP, 8, seed=7)
     dump('usc2', usc, P, y, 'usc2_syn.npz')
+
+    plog = os.path.join(HERE, 'plog.inp')
+    mech = Mechanism.from_chemkin(plog)
+    P, y = synthetic_states(mech.NSP, 192, seed=3)
+    P = P.copy()
+    P[128:160] *= 0.01          # 0.005 - 0.25 atm: below the first pressure of most tables
+    P[160:192] *= 20.0          # 10 - 500 atm: above the last pressure
+    dump('plog', plog, P, y, 'plog_syn.npz')

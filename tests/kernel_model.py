@@ -67,6 +67,20 @@ def evaluate(Tb, P, y):
         nre = (fl >> tb.NRE_SHIFT) & 15
         npr = (fl >> tb.NPR_SHIFT) & 15
         lnkf = lnA + b * logT - Ta * iT
+        dk_ = b + Ta * iT
+        if fl & tb.F_PLOG:
+            # rs:598-632, cj:1687-1850: Arrhenius set of the end ranges, log-P interpolation between
+            pq = Tb['plog_par'].reshape(-1, 8)[Tb['plog_off'][p]:Tb['plog_off'][p + 1]]
+            idx = (P[:, None] > pq[None, :, 0]).sum(axis=1)
+            lo = np.clip(idx - 1, 0, len(pq) - 1)
+            mid = (idx > 0) & (idx < len(pq))
+            k1 = pq[lo, 1] + pq[lo, 2] * logT - pq[lo, 3] * iT
+            d1 = pq[lo, 2] + pq[lo, 3] * iT
+            hi_ = np.clip(lo + 1, 0, len(pq) - 1)
+            k2 = pq[hi_, 1] + pq[hi_, 2] * logT - pq[hi_, 3] * iT
+            wgt = np.where(mid, (np.log(P) - pq[lo, 4]) * pq[lo, 5], 0.0)
+            lnkf = k1 + (k2 - k1) * wgt
+            dk_ = d1 + (pq[lo, 6] + pq[lo, 7] * iT) * wgt
         kf = np.exp(lnkf)
         f = kf * c[0] * c[1] * c[2]
         isrev = bool(fl & tb.F_REV)
@@ -151,7 +165,7 @@ def evaluate(Tb, P, y):
         if fl & tb.F_NO_T:
             tT = np.zeros(n)
         else:
-            dk = b + Ta * iT
+            dk = dk_
             if isrev:
                 sdB = (dB[:, s[3]] + dB[:, s[4]] + dB[:, s[5]]) - (dB[:, s[0]] + dB[:, s[1]] + dB[:, s[2]])
                 elem = net * dk + f * (1.0 - nre) - r * ((1.0 - npr) - T * sdB)

@@ -12,7 +12,8 @@ from pyjac_b200.states import synthetic_states
 pytestmark = pytest.mark.gpu
 
 CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz'), ('torture.inp', 'torture_pasr.npz'),
-         ('gri30_syn.inp', 'gri30_syn.npz'), ('usc2_syn.inp', 'usc2_syn.npz')]
+         ('gri30_syn.inp', 'gri30_syn.npz'), ('usc2_syn.inp', 'usc2_syn.npz'),
+         ('plog.inp', 'plog_syn.npz')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 
@@ -110,6 +111,28 @@ def test_against_oracle_on_synthetic_states(torch, golden_dir):
     new = dict(zip(KEYS + ['dydt'], [o.cpu().numpy() for o in ev.rates(P, y, want_dy=True)]))
     gates.check_rates(mech, P_h, y_h, new, ref, 'gri30 synthetic')
     worst, frac = gates.check_jac(ev.eval_jacob(P, y).cpu().numpy(), ref_jac, mech.NSP, 'gri30 synthetic', mech, y_h)
+    assert frac > 0.999, frac
+    ev.close()
+
+
+def test_plog_against_oracle_across_pressures(torch, golden_dir):
+    """PLOG mechanism: 4096 states with pressures log-uniform over 0.001 - 1000 atm (below,
+    between and above every pressure table), plus states exactly at the table pressures."""
+    from oracle.oracle import Oracle
+    mech, ev = _evaluator(golden_dir, 'plog.inp')
+    P_h, y_h = synthetic_states(mech.NSP, 4096, seed=21)
+    rng = np.random.default_rng(5)
+    P_h = 101325.0 * 10.0 ** rng.uniform(-3.0, 3.0, size=P_h.shape)
+    exact = sorted({e[0] for rx in mech.reacs if rx.plog for e in rx.plog_par})
+    P_h[:len(exact)] = exact
+    ora = Oracle(mech)
+    ref = dict(zip(KEYS, ora.rates(P_h, y_h)))
+    ref['dydt'] = ora.dydt(P_h, y_h)
+    P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
+    new = dict(zip(KEYS + ['dydt'], [o.cpu().numpy() for o in ev.rates(P, y, want_dy=True)]))
+    gates.check_rates(mech, P_h, y_h, new, ref, 'plog pressures')
+    worst, frac = gates.check_jac(ev.eval_jacob(P, y).cpu().numpy(), ora.eval_jacob(P_h, y_h), mech.NSP,
+                                  'plog pressures', mech, y_h)
     assert frac > 0.999, frac
     ev.close()
 

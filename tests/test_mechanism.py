@@ -62,12 +62,22 @@ def test_synth_shapes(tmp_path, shape):
     assert m.specs[-1].name == 'N2'
 
 
-def test_plog_rejected(tmp_path, golden_dir):
+def test_plog_and_chebyshev_lines_are_read(tmp_path, golden_dir):
+    """PLOG / CHEB auxiliary data as the reference reads it (mech_interpret.py:589-680)."""
+    m = Mechanism.from_chemkin(os.path.join(golden_dir, 'plog.inp'))
+    rx = next(r for r in m.reacs if r.plog)
+    assert not rx.pdep and len(rx.plog_par) == 3
+    assert rx.plog_par[0][0] == pytest.approx(0.1 * 101325.0)
+    assert rx.plog_par[1][1] == pytest.approx(3.87e4 / 1000.0)          # bimolecular: cm3/mol -> m3/kmol
     src = open(os.path.join(golden_dir, 'h2o2_n2.inp')).read()
     src = src.replace('O+H2<=>H+OH                              3.870E+04    2.700    6260.00\n',
-                      'O+H2<=>H+OH                              3.870E+04    2.700    6260.00\n'
-                      ' PLOG / 1.0 3.87E+04 2.7 6260.0 /\n')
-    p = tmp_path / 'plog.inp'
+                      'O+H2(+M)<=>H+OH(+M)                      1.000E+00     .000        .00\n'
+                      ' TCHEB / 300.0 2000.0 /  PCHEB / 0.01 100.0 /\n'
+                      ' CHEB / 2 3  8.0 0.5 -0.1 /\n CHEB / -1.0 0.2 0.05 /\n')
+    p = tmp_path / 'cheb.inp'
     p.write_text(src)
-    with pytest.raises(NotImplementedError):
-        Mechanism.from_chemkin(str(p))
+    m = Mechanism.from_chemkin(str(p))
+    rx = next(r for r in m.reacs if r.cheb)
+    assert not rx.pdep and (rx.cheb_n_temp, rx.cheb_n_pres) == (2, 3)
+    assert rx.cheb_tlim == [300.0, 2000.0] and rx.cheb_plim[1] == pytest.approx(100.0 * 101325.0)
+    assert rx.cheb_par[0][0] == pytest.approx(8.0 - 3.0) and rx.cheb_par[1] == [-1.0, 0.2, 0.05]

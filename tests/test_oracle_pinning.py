@@ -16,7 +16,8 @@ from pyjac_b200.mechanism import Mechanism
 CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz', 'h2o2'),
          ('torture.inp', 'torture_pasr.npz', 'torture'),
          ('gri30_syn.inp', 'gri30_syn.npz', 'gri30'),
-         ('usc2_syn.inp', 'usc2_syn.npz', 'usc2')]
+         ('usc2_syn.inp', 'usc2_syn.npz', 'usc2'),
+         ('plog.inp', 'plog_syn.npz', 'plog')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 
