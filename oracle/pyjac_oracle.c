@@ -23,7 +23,7 @@
 
 enum { F_REV = 1, F_THD = 2, F_PDEP = 4, F_LOW = 8, F_TROE = 16, F_SRI = 32, F_EFF = 64,
        F_PDEPSP_TRUTHY = 128, F_NO_T = 256, F_TROE_T2 = 512, F_SRI5 = 1024, F_SRI5_DT = 2048,
-       F_PMT = 4096, F_PMT_IN_JTEMP = 8192, F_HAS_DBDT = 16384, F_KCJ_PREF = 32768, F_PLOG = 65536 };
+       F_PMT = 4096, F_PMT_IN_JTEMP = 8192, F_HAS_DBDT = 16384, F_KCJ_PREF = 32768, F_PLOG = 65536, F_CHEB = 131072 };
 
 typedef struct {
     int nsp, nr, nrev, npd;
@@ -43,6 +43,8 @@ typedef struct {
     const double *arr_main, *arr_k0, *arr_kinf, *arr_ratio;
     const double *troe_pm, *troe_j, *sri_pm, *sri_j, *rx_dt, *rx_pdt, *rx_drdy;
     const int *alpha_mode; const double *alpha_val;
+    const int *cheb_off, *cheb_dim;
+    const double *cheb_red, *cheb_c8, *cheb_c16;
     const int *plog_off;
     const double *plog_p4, *plog_arr, *plog_lp, *plog_dlp, *plog_dt, *plog_mid;
     const double *consts;
@@ -99,6 +101,7 @@ OracleMech* oracle_load(const void* src, size_t len)
     D(troe_pm, "troe_pm"); D(troe_j, "troe_j"); D(sri_pm, "sri_pm"); D(sri_j, "sri_j");
     D(rx_dt, "rx_dt"); D(rx_pdt, "rx_pdt"); D(rx_drdy, "rx_drdy");
     I(alpha_mode, "alpha_mode"); D(alpha_val, "alpha_val"); D(consts, "consts");
+    I(cheb_off, "cheb_off"); I(cheb_dim, "cheb_dim"); D(cheb_red, "cheb_red"); D(cheb_c8, "cheb_c8"); D(cheb_c16, "cheb_c16");
     I(plog_off, "plog_off"); D(plog_p4, "plog_p4"); D(plog_arr, "plog_arr"); D(plog_lp, "plog_lp");
     D(plog_dlp, "plog_dlp"); D(plog_dt, "plog_dt"); D(plog_mid, "plog_mid");
 #undef D
@@ -148,6 +151,79 @@ static double plog_kf(const OracleMech* m, int i, double T, double logT, double 
     kf = log(arrhenius(m->plog_arr + 4 * e, T, logT));
     double kf2 = log(arrhenius(m->plog_arr + 4 * (e + 1), T, logT));
     return exp(kf + (kf2 - kf) * (log(pres) - m->plog_lp[e]) / m->plog_dlp[e]);
+}
+
+/* get_cheb_rate (rs:149-251): kf of a Chebyshev reaction from the reduced temperature and
+ * pressure, in the emitted statement order */
+static double cheb_kf(const OracleMech* m, int i, double Tred, double Pred)
+{
+    const int nt = m->cheb_dim[2 * i], np = m->cheb_dim[2 * i + 1];
+    const double* c = m->cheb_c8 + m->cheb_off[i];
+    double dot_prod[64];
+    double cheb_temp_0 = 1, cheb_temp_1 = Pred, kf;
+    for (int r = 0; r < nt; ++r) dot_prod[r] = c[r * np] + Pred * c[r * np + 1];
+    int update_one = 1;
+    for (int j = 2; j < np; ++j) {
+        if (update_one) {
+            cheb_temp_0 = 2 * Pred * cheb_temp_1 - cheb_temp_0;
+            for (int r = 0; r < nt; ++r) dot_prod[r] += c[r * np + j] * cheb_temp_0;
+        } else {
+            cheb_temp_1 = 2 * Pred * cheb_temp_0 - cheb_temp_1;
+            for (int r = 0; r < nt; ++r) dot_prod[r] += c[r * np + j] * cheb_temp_1;
+        }
+        update_one = !update_one;
+    }
+    cheb_temp_0 = 1;
+    cheb_temp_1 = Tred;
+    kf = dot_prod[0] + Tred * dot_prod[1];
+    update_one = 1;
+    for (int r = 2; r < nt; ++r) {
+        if (update_one) {
+            cheb_temp_0 = 2 * Tred * cheb_temp_1 - cheb_temp_0;
+            kf += dot_prod[r] * cheb_temp_0;
+        } else {
+            cheb_temp_1 = 2 * Tred * cheb_temp_0 - cheb_temp_1;
+            kf += dot_prod[r] * cheb_temp_1;
+        }
+        update_one = !update_one;
+    }
+    return pow(10.0, kf);
+}
+
+/* write_cheb_ut (cj:1532-1606): the sum over second-kind polynomials of the temperature derivative */
+static double cheb_ut(const OracleMech* m, int i, double Tred, double Pred)
+{
+    const int nt = m->cheb_dim[2 * i], np = m->cheb_dim[2 * i + 1];
+    const double* c = m->cheb_c16 + m->cheb_off[i];
+    double dot_prod[64];
+    double cheb_temp_0 = 1, cheb_temp_1 = Pred, kf;
+    for (int r = 1; r < nt; ++r) dot_prod[r] = c[r * np] + Pred * c[r * np + 1];
+    int update_one = 1;
+    for (int j = 2; j < np; ++j) {
+        if (update_one) {
+            cheb_temp_0 = 2 * Pred * cheb_temp_1 - cheb_temp_0;
+            for (int r = 1; r < nt; ++r) dot_prod[r] += c[r * np + j] * cheb_temp_0;
+        } else {
+            cheb_temp_1 = 2 * Pred * cheb_temp_0 - cheb_temp_1;
+            for (int r = 1; r < nt; ++r) dot_prod[r] += c[r * np + j] * cheb_temp_1;
+        }
+        update_one = !update_one;
+    }
+    cheb_temp_0 = 1.0;
+    cheb_temp_1 = 2.0 * Tred;
+    kf = dot_prod[1] + 2.0 * Tred * dot_prod[2];
+    update_one = 1;
+    for (int r = 3; r < nt; ++r) {
+        if (update_one) {
+            cheb_temp_0 = 2.0 * Tred * cheb_temp_1 - cheb_temp_0;
+            kf += dot_prod[r] * cheb_temp_0;
+        } else {
+            cheb_temp_1 = 2.0 * Tred * cheb_temp_0 - cheb_temp_1;
+            kf += dot_prod[r] * cheb_temp_1;
+        }
+        update_one = !update_one;
+    }
+    return kf;
 }
 
 /* C[a]*C[a]*C[b]*...: returns the left-assoc product with `tail` multiplied last.
@@ -203,7 +279,12 @@ void oracle_eval_rxn_rates(const OracleMech* m, double T, double pres, const dou
     double kf = 0.0;
     for (int i = 0; i < m->nr; ++i) {
         if (m->rx_flags[i] & F_PLOG) kf = plog_kf(m, i, T, logT, pres, kf);
-        else kf = arrhenius(m->arr_main + 4 * i, T, logT);
+        else if (m->rx_flags[i] & F_CHEB) {
+            const double* cr = m->cheb_red + 12 * i;
+            double Tred = ((2.0 / T) - cr[0]) / cr[1];
+            double Pred = (2.0 * log10(pres) - cr[2]) / cr[3];
+            kf = cheb_kf(m, i, Tred, Pred);
+        } else kf = arrhenius(m->arr_main + 4 * i, T, logT);
         fwd[i] = conc_prod_times(m->reac_sp + m->reac_off[i], m->reac_nu + m->reac_off[i],
                                  m->reac_off[i + 1] - m->reac_off[i], C, kf);
         if (m->rx_flags[i] & F_REV) {
@@ -383,6 +464,7 @@ void oracle_eval_jacob(const OracleMech* m, double t, double pres, const double*
     double logT = log(T);
     double j_temp = 0.0, kf = 0.0, pres_mod_temp = 0.0, Kc = 0.0, kr = 0, Pr = 0.0;
     double Fcent = 0.0, A = 0.0, B = 0.0, lnF_AB = 0.0, X = 0.0;
+    double Tred = 0.0, Pred = 0.0;
     double rho_inv = 1.0 / rho;
     const double* K = m->consts;
 
@@ -449,6 +531,26 @@ void oracle_eval_jacob(const OracleMech* m, double t, double pres, const double*
                 dt = dtp;
                 plog_e = -3;
             }
+        }
+        if (fl & F_CHEB) {      /* write_cheb_rxn_dt (cj:1609-1684) */
+            const double* cr = m->cheb_red + 12 * i;
+            Tred = ((2.0 / T) - cr[4]) / cr[5];
+            Pred = (2.0 * log10(pres) - cr[6]) / cr[7];
+            kf = cheb_ut(m, i, Tred, Pred);
+            double elem = kf * (cr[8] / T) * (rev ? (f - r) : f);
+            if (dt[4] != 0.0) elem = elem + f * dt[3];
+            if (rev) {
+                double sdb = 0.0;
+                int o0 = m->db_off[i], o1 = m->db_off[i + 1];
+                for (int e = o0; e < o1; ++e) {
+                    double v = (double)m->db_nu[e] * dBdT[m->db_sp[e]];
+                    sdb = (e == o0) ? v : sdb + v;
+                }
+                double inner = (dt[6] != 0.0) ? dt[5] + -T * (sdb) : -T * (sdb);
+                elem = elem - r * (inner);
+            }
+            j_temp = ((1.0 / T) * (elem)) * rho_inv;
+            plog_e = -4;
         }
         if (plog_e >= 0) {
             const double* q = m->plog_mid + 8 * plog_e;
@@ -606,6 +708,7 @@ void oracle_eval_jacob(const OracleMech* m, double t, double pres, const double*
         }
         /* write_rates (cj:290-338) */
         if (fl & F_PLOG) kf = plog_kf(m, i, T, logT, pres, kf);
+        else if (fl & F_CHEB) kf = cheb_kf(m, i, Tred, Pred);      /* Tred, Pred of the T part ({:.16e}) */
         else kf = arrhenius(m->arr_main + 4 * i, T, logT);
         if (rev) kr = kf / Kc;
 

@@ -6,8 +6,8 @@ the same format string, so that the C restatement -- which performs the run-time
 arithmetic in the emitted code's order -- reproduces the reference bit for bit where
 libm agrees.  Citations: rs = pyjac/core/rate_subs.py, cj = pyjac/core/create_jacobian.py.
 
-Scope: elementary, third-body, fall-off (Lindemann / Troe / SRI, LOW or HIGH) and PLOG
-reactions with integer stoichiometric coefficients and positive pre-exponentials.  PLOG is
+Scope: elementary, third-body, fall-off (Lindemann / Troe / SRI, LOW or HIGH), PLOG and
+Chebyshev (at least 3 x 2 coefficients: cj:1583-1585 indexes dot_prod[2]) reactions with integer stoichiometric coefficients and positive pre-exponentials.  PLOG is
 restated for the inputs the generator emits valid C for: every two consecutive pressures
 must have different activation energies (cj:1759-1770 builds an unbalanced expression
 otherwise).
@@ -26,7 +26,7 @@ from pyjac_b200.mechanism import Mechanism
 F_REV, F_THD, F_PDEP, F_LOW, F_TROE, F_SRI, F_EFF = 1, 2, 4, 8, 16, 32, 64
 F_PDEPSP_TRUTHY, F_NO_T, F_TROE_T2, F_SRI5, F_SRI5_DT = 128, 256, 512, 1024, 2048
 F_PMT, F_PMT_IN_JTEMP, F_HAS_DBDT, F_KCJ_PREF = 4096, 8192, 16384, 32768
-F_PLOG = 65536
+F_PLOG, F_CHEB = 65536, 131072
 
 UNROLL = 40   # CParams.Jacob_Unroll: conc_temp collapsing restarts every 40 reactions
 
@@ -136,8 +136,8 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     i32 = lambda x: np.asarray(x, dtype=np.int32)
 
     for rx in reacs:
-        if rx.cheb:
-            raise NotImplementedError('Chebyshev reactions')
+        if rx.cheb and (rx.pdep or rx.thd_body or rx.cheb_n_temp < 3 or rx.cheb_n_pres < 2):
+            raise NotImplementedError('Chebyshev reaction with a third body / fewer than 3 x 2 coefficients')
         if rx.plog and (rx.pdep or rx.thd_body or len(rx.plog_par) < 2):
             raise NotImplementedError('PLOG reaction with a third body / fewer than two pressures')
         if not all(is_int(v) for v in rx.reac_nu + rx.prod_nu):
@@ -217,6 +217,7 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     alpha_val = np.zeros((nr, max(nsp - 1, 1)))
 
     plog_off, plog_p4, plog_arr, plog_lp, plog_dlp, plog_dt, plog_mid = [0], [], [], [], [], [], []
+    cheb_off, cheb_dim, cheb_red, cheb_c8, cheb_c16 = [0], [], [], [], []
 
     last_conc_temp = None
     do_unroll = nr > UNROLL
@@ -247,6 +248,25 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
                     plog_dlp.append(0.0)
                     plog_mid.append([0.0] * 8)
         plog_off.append(len(plog_p4))
+        if rx.cheb:
+            # rs:149-251 ({:.8e}) and cj:1532-1684 ({:.16e}, coefficients times their row index)
+            fl |= F_CHEB
+            tsum = 1.0 / rx.cheb_tlim[0] + 1.0 / rx.cheb_tlim[1]
+            tsub = 1.0 / rx.cheb_tlim[1] - 1.0 / rx.cheb_tlim[0]
+            psum = math.log10(rx.cheb_plim[0]) + math.log10(rx.cheb_plim[1])
+            psub = math.log10(rx.cheb_plim[1]) - math.log10(rx.cheb_plim[0])
+            cheb_red.append([q('{:.8e}', tsum), q('{:.8e}', tsub), q('{:.8e}', psum), q('{:.8e}', psub),
+                             q('{:.16e}', tsum), q('{:.16e}', tsub), q('{:.16e}', psum), q('{:.16e}', psub),
+                             q('{:.16e}', -2.0 * math.log(10) / tsub), 0.0, 0.0, 0.0])
+            cheb_dim.append([rx.cheb_n_temp, rx.cheb_n_pres])
+            for r_ in range(rx.cheb_n_temp):
+                for c_ in range(rx.cheb_n_pres):
+                    cheb_c8.append(q('{:.8e}', rx.cheb_par[r_][c_]))
+                    cheb_c16.append(q('{:.16e}', r_ * rx.cheb_par[r_][c_]))
+        else:
+            cheb_red.append([0.0] * 12)
+            cheb_dim.append([0, 0])
+        cheb_off.append(len(cheb_c8))
         if rx.rev:
             fl |= F_REV
             rev_idx[i] = rev_reacs.index(i)
@@ -323,7 +343,7 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
         dt[i] = [dk_form, q('{:.16e}', rx.b), q('{:.16e}', rx.E),
                  float(str(1. - float(rnu))), 1.0 if rnu != 1.0 else 0.0,
                  float(str(1. - float(pnu))), 1.0 if pnu != 1.0 else 0.0, 0.0]
-        if not rx.rev and not dk_form and rnu == 1.0 and not rx.plog:
+        if not rx.rev and not dk_form and rnu == 1.0 and not rx.plog and not rx.cheb:
             fl |= F_NO_T
 
         if rx.pdep:
@@ -472,6 +492,11 @@ def build(mech: Mechanism) -> Dict[str, np.ndarray]:
     T['troe_j'] = troe_j.ravel()
     T['sri_pm'] = sri_pm.ravel()
     T['sri_j'] = sri_j.ravel()
+    T['cheb_off'] = i32(cheb_off)
+    T['cheb_dim'] = i32(cheb_dim).ravel()
+    T['cheb_red'] = f64(cheb_red).ravel()
+    T['cheb_c8'] = f64(cheb_c8 or [0.0])
+    T['cheb_c16'] = f64(cheb_c16 or [0.0])
     T['plog_off'] = i32(plog_off)
     T['plog_p4'] = f64(plog_p4 or [0.0])
     T['plog_arr'] = f64(plog_arr or [[0.0] * 4]).ravel()

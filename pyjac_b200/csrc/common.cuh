@@ -10,7 +10,7 @@ enum : int {
     F_REV = 1, F_THD = 2, F_PDEP = 4, F_LOW = 8, F_TROE = 16, F_SRI = 32, F_PMT = 64,
     F_PMT_INJ = 128, F_TROE_T2 = 256, F_SRI5 = 512, F_SRI5_DT = 1024, F_NO_T = 2048,
     F_EFFN1 = 4096, F_HAS_LAST = 1 << 13, F_WANT_PMT = 1 << 16, F_EFF_SLOTS = 1 << 17,
-    F_PLOG = 1 << 18,
+    F_PLOG = 1 << 18, F_CHEB = 1 << 19,
     NRE_SHIFT = 20, NPR_SHIFT = 24, NPAR = 32
 };
 
@@ -35,6 +35,12 @@ struct Tables {
     int nplog;
     const int* plog_off;
     const double* plog_par;
+    // Chebyshev reactions: cheb_par + cheb_off[p] = {n_T, n_P, (tsum, tsub, psum, psub) of the rate,
+    // the same of the Jacobian, -2 ln10 / tsub, 0}, n_T x n_P rate coefficients, n_T x n_P
+    // coefficients of the temperature derivative (row i times i); ncheb = 0: no such reaction
+    int ncheb;
+    const int* cheb_off;
+    const double* cheb_par;
 };
 
 struct IO {

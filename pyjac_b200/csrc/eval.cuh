@@ -425,7 +425,7 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
 
 // Phase B for one reaction without pressure modification (the common case) and the two states
 // of the lane: no branches except `three` (warp-uniform) and the rare last-species fold.
-template <int GS, int MODE>
+template <int GS, int MODE, bool SPECIAL>
 __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl, const IO& io, const Out& out,
                                                unsigned aSP, unsigned aRX,
                                                unsigned aRAW, unsigned aSC, unsigned aPL, int p, bool valid, bool three,
@@ -453,8 +453,9 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
         dH = vadd(dH, vsub(lds<O_HW * RB>(a5 ^ RB), lds<O_HW * RB>(a2 ^ RB)));
     }
     V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
-    V dk{fma(Ta, iT.x, bexp), fma(Ta, iT.y, bexp)};          // d ln kf / d ln T
-    if (fl & F_PLOG) {
+    V dk{0.0, 0.0};                                           // d ln kf / d ln T
+    if (SPECIAL) dk = V{fma(Ta, iT.x, bexp), fma(Ta, iT.y, bexp)};
+    if (SPECIAL && (fl & F_PLOG)) {
         // rate constant of a PLOG reaction (rs:598-632) and its temperature derivative
         // (cj:1687-1850): the Arrhenius set of the first / last pressure outside the table,
         // linear interpolation of ln kf in ln P between two pressures
@@ -481,6 +482,57 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
         lnkf = V{lk[0], lk[1]};
         dk = V{dkk[0], dkk[1]};
     }
+    V rat{1.0, 1.0};
+    if (SPECIAL && (fl & F_CHEB)) {
+        // Chebyshev rate constant (rs:149-251) and its temperature derivative (cj:1532-1684).  The
+        // generated eval_jacob evaluates the rate constant of its species part with reduced
+        // variables printed to 16 digits, eval_rxn_rates with 8 digits: lnkf follows the former,
+        // `rat` = kf(rates) / kf(Jacobian) rescales the rates of progress
+        const double* cq = tb.cheb_par + __ldg(tb.cheb_off + p);
+        const int n_t = (int)__ldg(cq), n_p = (int)__ldg(cq + 1);
+        const double* c8 = cq + 12;
+        const double* c16 = c8 + n_t * n_p;
+        const V lP = lds<Q_LNP * RB>(aSC);
+        const double lPs[2] = {lP.x, lP.y}, rTs[2] = {iT.x, iT.y};
+        const double ln10 = 2.30258509299404568402, iln10 = 0.43429448190325182765;
+        double lr[2], lj[2], dkk[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const double l10p = lPs[g] * iln10;
+            const double tr8 = (2.0 * rTs[g] - __ldg(cq + 2)) / __ldg(cq + 3), pr8 = (2.0 * l10p - __ldg(cq + 4)) / __ldg(cq + 5);
+            const double tr16 = (2.0 * rTs[g] - __ldg(cq + 6)) / __ldg(cq + 7), pr16 = (2.0 * l10p - __ldg(cq + 8)) / __ldg(cq + 9);
+            double t8a = 1.0, t8b = tr8, t16a = 1.0, t16b = tr16, ua = 0.0, ub = 1.0;
+            double s8 = 0.0, s16 = 0.0, su = 0.0;
+            for (int i = 0; i < n_t; ++i) {
+                const double* r8 = c8 + i * n_p;
+                const double* r16 = c16 + i * n_p;
+                // row i: sum_j c[i][j] T_j(Pred) for both reduced pressures
+                const double c0 = __ldg(r8), c1 = __ldg(r8 + 1);
+                double pa8 = 1.0, pb8 = pr8, pa16 = 1.0, pb16 = pr16;
+                double dp8 = fma(pr8, c1, c0), dp16 = fma(pr16, c1, c0), dpu = fma(pr16, __ldg(r16 + 1), __ldg(r16));
+                for (int j = 2; j < n_p; ++j) {
+                    const double n8 = fma(2.0 * pr8, pb8, -pa8), n16 = fma(2.0 * pr16, pb16, -pa16);
+                    pa8 = pb8; pb8 = n8; pa16 = pb16; pb16 = n16;
+                    const double cc = __ldg(r8 + j);
+                    dp8 = fma(cc, n8, dp8); dp16 = fma(cc, n16, dp16); dpu = fma(__ldg(r16 + j), n16, dpu);
+                }
+                // T_i(Tred) for both reduced temperatures, U_{i-1}(Tred) for the derivative
+                double T8 = 1.0, T16 = 1.0, U = 0.0;
+                if (i == 1) { T8 = tr8; T16 = tr16; U = 1.0; }
+                else if (i > 1) {
+                    T8 = fma(2.0 * tr8, t8b, -t8a); t8a = t8b; t8b = T8;
+                    T16 = fma(2.0 * tr16, t16b, -t16a); t16a = t16b; t16b = T16;
+                    U = fma(2.0 * tr16, ub, -ua); ua = ub; ub = U;
+                }
+                s8 = fma(dp8, T8, s8); s16 = fma(dp16, T16, s16); su = fma(dpu, U, su);
+            }
+            lr[g] = ln10 * s8; lj[g] = ln10 * s16;
+            dkk[g] = su * __ldg(cq + 10) * rTs[g];
+        }
+        lnkf = V{lj[0], lj[1]};
+        dk = V{dkk[0], dkk[1]};
+        rat = V{exp_fast(lr[0] - lj[0]), exp_fast(lr[1] - lj[1])};
+    }
     const double ex[4] = {lnkf.x, lnkf.y, lnkf.x - sB.x - lnKc, lnkf.y - sB.y - lnKc};
     double ev[4];
     exp_n<4>(ex, ev);
@@ -491,7 +543,8 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     V o0 = c1, o1 = c0, o3 = c4, o4 = c3, o2 = vmul(c0, c1), o5 = vmul(c3, c4);
     if (three) { o0 = vmul(c1, c2); o1 = vmul(c0, c2); o3 = vmul(c4, c5); o4 = vmul(c3, c5); }
     const V d0 = vmul(kf, o0), d1 = vmul(kf, o1), d3 = vmul(kr, o3), d4 = vmul(kr, o4);
-    const V f = vmul(d0, c0), r = vmul(d3, c3);
+    V f = vmul(d0, c0), r = vmul(d3, c3);
+    if (SPECIAL && (fl & F_CHEB)) { f = vmul(f, rat); r = vmul(r, rat); }
     const V net = vsub(f, r);
     if (MODE == M_RATES && valid) {
         const int4 ro = __ldg(pl.rx_out + p);
@@ -505,6 +558,7 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
     const double omre = 1.0 - nre, ompr = 1.0 - npr;
     const V rho_inv = lds<Q_RHOINV * RB>(aSC), mwr_ = lds<Q_MWR * RB>(aSC), nmwr{-mwr_.x, -mwr_.y};
+    if (!SPECIAL) dk = V{fma(Ta, iT.x, bexp), fma(Ta, iT.y, bexp)};
     // irreversible: r = 0 makes this f * (dk + 1 - nre)          (cj:1461-1523)
     V elem = vfma(net, dk, vmul(omre, f));
     elem = V{elem.x - r.x * (ompr - T.x * sdB.x), elem.y - r.y * (ompr - T.y * sdB.y)};
@@ -633,7 +687,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 }
                 o[Q_T][g2] = T[g2]; o[Q_LOGT][g2] = log(T[g2]); o[Q_IT][g2] = 1.0 / T[g2];
                 o[Q_RHO][g2] = rho; o[Q_RHOINV][g2] = rho_inv;
-                o[Q_LNP][g2] = tb.nplog ? log(P[g2]) : 0.0; o[Q_MWR][g2] = mw * rho_inv;
+                o[Q_LNP][g2] = (tb.nplog | tb.ncheb) ? log(P[g2]) : 0.0; o[Q_MWR][g2] = mw * rho_inv;
                 o[Q_M][g2] = P[g2] / (tb.ru * T[g2]);
             }
             const unsigned a = aSC0 + b * SCB;
@@ -755,7 +809,15 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 } else {
                     const bool has3 = ((q2.z & 0xFFFFu) != nsp_f) || (((unsigned)q2.w >> 16) != nsp_f);
                     const bool three = __any_sync(0xffffffffu, has3);
-                    reaction_plain<GS, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
+                    // rounds holding a PLOG / Chebyshev reaction take the build of the routine that knows them
+#ifdef PJ_NO_SPECIAL
+                    if (false)
+#else
+                    if (__any_sync(0xffffffffu, (q2.x & (F_PLOG | F_CHEB)) != 0))
+#endif
+                        reaction_plain<GS, MODE, true>(tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
+                    else
+                        reaction_plain<GS, MODE, false>(tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
                 }
                 item = nxt;
             }

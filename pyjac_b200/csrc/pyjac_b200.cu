@@ -189,7 +189,7 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     m->device = device;
     Tables& t = m->tb;
     t.nsp = d[0]; t.nr = d[1]; t.nrev = d[2]; t.npd = d[3]; t.nraw = d[4];
-    t.first_pm = d[8]; t.npm = d[9]; t.nplog = d[5];
+    t.first_pm = d[8]; t.npm = d[9]; t.nplog = d[5]; t.ncheb = d[6];
     t.ru = c[0];
     int rc = PYJAC_OK;
 #define UP(field, name, type, code) if (!rc) rc = upload<type>(m, blob, name, &m->field, code)
@@ -199,6 +199,7 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     UP(tb.red_off, "red_off", int, 1); UP(tb.red_rx, "red_rx", int, 1); UP(tb.red_nu, "red_nu", double, 0);
     UP(tb.rx_out, "p5_rxout", int4, 1);
     UP(tb.plog_off, "plog_off", int, 1); UP(tb.plog_par, "plog_par", double, 0);
+    UP(tb.cheb_off, "cheb_off", int, 1); UP(tb.cheb_par, "cheb_par", double, 0);
     if (!rc) {
         const pjt::Entry* pe = pjt::find(blob, "p5_cfg");
         if (!pe || pe->dtype != 1 || pe->count < 14) rc = fail(PYJAC_EINVAL, "table blob lacks p5_cfg");

@@ -20,7 +20,7 @@ pyjac/core/rate_subs.py, cj = pyjac/core/create_jacobian.py).
 
 Table reference (all reaction-indexed arrays are in *kernel order*, see ``rx_orig``):
 
-  dims      int32[16]  NSP NR NREV NPD NRAW NPLOG - - FIRST_PM NPM NRED MAXRED - - - -
+  dims      int32[16]  NSP NR NREV NPD NRAW NPLOG NCHEB - FIRST_PM NPM NRED MAXRED - - - -
   cst       f64[4]     RU ({:.8e}), ln(PA/RU)
   sp_*      per species (internal, moved-last order): w, iw (=1/W {:.16e}), ruw (=RU/W),
             tmid, mwf (=W_j/W_N), seen;  sp_nasa[k][branch][16] polynomial coefficients
@@ -31,6 +31,8 @@ Table reference (all reaction-indexed arrays are in *kernel order*, see ``rx_ori
             the kernels read these through the packed records p5_rx / p5_rxout / p5_eff
   plog_*    off[NR + 1] (kernel order) into par[NPLOG][8] = threshold ({:.4e} Pa), ln A, b, Ta,
             ln P, 1 / (ln P' - ln P), b' - b, Ta' - Ta
+  cheb_*    off[NR + 1] (kernel order, in doubles) into par: per Chebyshev reaction a 12-double
+            header (n_T, n_P, reduced-variable constants) and two n_T x n_P coefficient blocks
   pm_*      per pressure-modified reaction (kernel index - FIRST_PM): collider list
             (eff_off/eff_sp/eff_am1 = alpha-1), sp (specific collider or -1), par[32]
   red_*     per species CSR of (reaction, nu) (eval_spec_rates entry point, plan input)
@@ -55,6 +57,8 @@ F_HAS_LAST = 1 << 13   # (Jacobian kernel record only) an occupied slot holds th
 F_WANT_PMT = 1 << 16   # the kernel stores pres_mod_temp as a raw value
 F_EFF_SLOTS = 1 << 17  # ... and pres_mod_temp * (alpha_j - 1) for each listed collider j
 F_PLOG = 1 << 18       # rate constant interpolated in log P between Arrhenius sets (plog_*)
+F_CHEB = 1 << 19       # Chebyshev rate constant in (1/T, log10 P) (cheb_*)
+NCHEB_HDR = 12         # doubles ahead of a Chebyshev reaction's coefficient blocks
 NRE_SHIFT, NPR_SHIFT = 20, 24    # occupied reactant / product slots
 
 MAXS = 3               # concentration slots per side of a reaction
@@ -104,8 +108,9 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T: Dict[str, np.ndarray] = {}
 
     for i, rx in enumerate(reacs):
-        if rx.cheb:
-            raise UnsupportedMechanism('Chebyshev reactions (reaction %d)' % i)
+        if rx.cheb and (rx.pdep or rx.thd_body or rx.plog or rx.cheb_n_temp < 2 or rx.cheb_n_pres < 2):
+            raise UnsupportedMechanism('Chebyshev reaction %d: third body / PLOG / fewer than 2 x 2 '
+                                       'coefficients' % i)
         if rx.plog:
             pp = rx.plog_par
             if rx.pdep or rx.thd_body:
@@ -158,6 +163,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
 
     flags, rev_idx, pm_idx, raw_base = [], [], [], []
     plog_off, plog_par = [0], []
+    cheb_off, cheb_par = [], []
     slots = np.full((nr, 2 * MAXS), nsp, dtype=np.int32)
     arr = np.zeros((nr, 4))
     pm_par = np.zeros((max(npm, 1), NPAR))
@@ -213,7 +219,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
         if rx.thd_body_eff and not rx.pdep:
             fl |= F_EFFN1                                                      # cj:201-206
         b_on, E_on = abs(rx.b) > 1.0e-90, abs(rx.E) > 1.0e-90
-        if not rx.rev and not b_on and not E_on and sum(rx.reac_nu) == 1.0 and not rx.plog:
+        if not rx.rev and not b_on and not E_on and sum(rx.reac_nu) == 1.0 and not rx.plog and not rx.cheb:
             fl |= F_NO_T                                                       # cj:1507-1523
         if rx.plog:
             # per pressure: threshold as printed ({:.4e}: rs:601-629), ln A, b, Ta, ln P, and towards
@@ -229,6 +235,23 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
                                 q('{:.16e}', b2 - b1), q('{:.16e}', E2 - E1)]
                 plog_par.append(row)
         plog_off.append(len(plog_par))
+        cheb_off.append(len(cheb_par))
+        if rx.cheb:
+            # header: n_T, n_P; (tsum, tsub, psum, psub) as eval_rxn_rates prints them ({:.8e},
+            # rs:175-192) and as eval_jacob does ({:.16e}, cj:1641-1660); -2 ln10 / tsub (cj:1665).
+            # Then the n_T x n_P coefficients of the rate ({:.8e}, rs:197-217) and those of the
+            # temperature derivative, row i scaled by i ({:.16e}, cj:1555-1575)
+            fl |= F_CHEB
+            tsum = 1.0 / rx.cheb_tlim[0] + 1.0 / rx.cheb_tlim[1]
+            tsub = 1.0 / rx.cheb_tlim[1] - 1.0 / rx.cheb_tlim[0]
+            psum = math.log10(rx.cheb_plim[0]) + math.log10(rx.cheb_plim[1])
+            psub = math.log10(rx.cheb_plim[1]) - math.log10(rx.cheb_plim[0])
+            cheb_par += [float(rx.cheb_n_temp), float(rx.cheb_n_pres),
+                         q('{:.8e}', tsum), q('{:.8e}', tsub), q('{:.8e}', psum), q('{:.8e}', psub),
+                         q('{:.16e}', tsum), q('{:.16e}', tsub), q('{:.16e}', psum), q('{:.16e}', psub),
+                         q('{:.16e}', -2.0 * math.log(10) / tsub), 0.0]
+            cheb_par += [q('{:.8e}', v) for row in rx.cheb_par for v in row]
+            cheb_par += [q('{:.16e}', r_ * v) for r_, row in enumerate(rx.cheb_par) for v in row]
         rev_idx.append(rev_reacs.index(i) if rx.rev else -1)
         pm_idx.append(pdep_reacs.index(i) if (rx.thd_body or rx.pdep) else -1)
         if want_pmt[i]:
@@ -342,6 +365,8 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T['rx_raw_base'] = i32(raw_base)
     T['rx_slots'] = slots.ravel()
     T['rx_arr'] = arr.ravel()
+    T['cheb_off'] = i32(cheb_off + [len(cheb_par)])
+    T['cheb_par'] = f64(cheb_par or [0.0])
     T['plog_off'] = i32(plog_off)
     T['plog_par'] = f64(plog_par or [[0.0] * 8]).ravel()
     T['pm_par'] = pm_par.ravel()
@@ -435,7 +460,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     for p, i in enumerate(order):
         rx = reacs[i]
         kinds.append('sri' if rx.sri else 'troe' if rx.troe else 'lind' if rx.pdep else
-                     'thd' if rx.thd_body else 'plog' if rx.plog else 'plain')
+                     'thd' if rx.thd_body else 'plog' if (rx.plog or rx.cheb) else 'plain')
         n_eff.append(sum(1 for s, a in rx.thd_body_eff if a != 1.0) if (rx.thd_body or rx.pdep) else 0)
     T.update(plan.build_plan(nsp, nr, nraw, first_pm, kinds, [bool(reacs[i].rev) for i in order],
                              [bool(slots[p, 2] != nsp or slots[p, 5] != nsp) for p in range(nr)],
@@ -487,6 +512,6 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T['p5_eff'] = i32(eff4 + [0, 0, sp_off(nsp), nraw + 1] * 4)
 
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
-    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, len(plog_par), 0, 0,
+    T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, len(plog_par), len(cheb_par), 0,
                      first_pm, npm, red_off[-1], max(len(l) for l in red), 0, 0, 0, 0])
     return T

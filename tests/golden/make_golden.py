@@ -15,6 +15,8 @@ evaluates the emitted C on fixed states and stores inputs and outputs:
 
     tests/golden/plog_syn.npz      PLOG coverage mechanism over the H2/O2 species, 192 synthetic states of
                                    which 32 below and 32 above every pressure table
+    tests/golden/cheb_syn.npz      Chebyshev coverage mechanism over the H2/O2 species, 160 synthetic states of
+                                   which 32 outside the fitted pressure ranges
 
 Arrays are in pyJac's internal (moved-last) species order, row-major per state:
 P[n], y[n,NSP] = [T, Y_0..Y_{NSP-2}], conc, fwd, rev, pres_mod, spec_rates, dydt, jac[n,NSP*NSP]
@@ -79,3 +81,11 @@ if __name__ == '__main__':
     P[128:160] *= 0.01          # 0.005 - 0.25 atm: below the first pressure of most tables
     P[160:192] *= 20.0          # 10 - 500 atm: above the last pressure
     dump('plog', plog, P, y, 'plog_syn.npz')
+
+    cheb = os.path.join(HERE, 'cheb.inp')
+    mech = Mechanism.from_chemkin(cheb)
+    P, y = synthetic_states(mech.NSP, 160, seed=4)
+    P = P.copy()
+    P[128:144] *= 0.01
+    P[144:160] *= 20.0
+    dump('cheb', cheb, P, y, 'cheb_syn.npz')

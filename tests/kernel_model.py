@@ -81,13 +81,43 @@ def evaluate(Tb, P, y):
             wgt = np.where(mid, (np.log(P) - pq[lo, 4]) * pq[lo, 5], 0.0)
             lnkf = k1 + (k2 - k1) * wgt
             dk_ = d1 + (pq[lo, 6] + pq[lo, 7] * iT) * wgt
+        rat = 1.0
+        if fl & tb.F_CHEB:
+            # rs:149-251 (rate, {:.8e} constants) and cj:1532-1684 (temperature derivative and the rate
+            # constant of the species part, {:.16e} reduced variables)
+            cq = Tb['cheb_par'][Tb['cheb_off'][p]:Tb['cheb_off'][p + 1]]
+            n_t, n_p = int(cq[0]), int(cq[1])
+            c8 = cq[12:12 + n_t * n_p].reshape(n_t, n_p)
+            c16 = cq[12 + n_t * n_p:].reshape(n_t, n_p)
+            l10p = np.log10(P)
+            cheb_T = np.polynomial.chebyshev.chebvander
+
+            def series(co, tr, pr, second_kind):
+                Pv = cheb_T(pr, n_p - 1)                      # (n, n_p)
+                if second_kind:                               # sum_i co[i] U_{i-1}(tr), row 0 unused
+                    U = np.zeros((len(tr), n_t))
+                    U[:, 1] = 1.0
+                    if n_t > 2:
+                        U[:, 2] = 2.0 * tr
+                    for i_ in range(3, n_t):
+                        U[:, i_] = 2.0 * tr * U[:, i_ - 1] - U[:, i_ - 2]
+                    Tv = U
+                else:
+                    Tv = cheb_T(tr, n_t - 1)
+                return np.einsum('ni,ij,nj->n', Tv, co, Pv)
+            tr8, pr8 = (2.0 * iT - cq[2]) / cq[3], (2.0 * l10p - cq[4]) / cq[5]
+            tr16, pr16 = (2.0 * iT - cq[6]) / cq[7], (2.0 * l10p - cq[8]) / cq[9]
+            lnkf_r = LN10 * series(c8, tr8, pr8, False)
+            lnkf = LN10 * series(c8, tr16, pr16, False)
+            dk_ = series(c16, tr16, pr16, True) * cq[10] * iT
+            rat = np.exp(lnkf_r - lnkf)
         kf = np.exp(lnkf)
-        f = kf * c[0] * c[1] * c[2]
+        f = kf * c[0] * c[1] * c[2] * rat
         isrev = bool(fl & tb.F_REV)
         if isrev:
             sB = (B[:, s[3]] + B[:, s[4]] + B[:, s[5]]) - (B[:, s[0]] + B[:, s[1]] + B[:, s[2]])
             kr = np.exp(lnkf - sB - lnKc)
-            r = kr * c[3] * c[4] * c[5]
+            r = kr * c[3] * c[4] * c[5] * rat
         else:
             kr = np.zeros(n)
             r = np.zeros(n)

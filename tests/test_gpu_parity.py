@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz'), ('torture.inp', 'torture_pasr.npz'),
          ('gri30_syn.inp', 'gri30_syn.npz'), ('usc2_syn.inp', 'usc2_syn.npz'),
-         ('plog.inp', 'plog_syn.npz')]
+         ('plog.inp', 'plog_syn.npz'), ('cheb.inp', 'cheb_syn.npz')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 

@@ -17,7 +17,8 @@ CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz', 'h2o2'),
          ('torture.inp', 'torture_pasr.npz', 'torture'),
          ('gri30_syn.inp', 'gri30_syn.npz', 'gri30'),
          ('usc2_syn.inp', 'usc2_syn.npz', 'usc2'),
-         ('plog.inp', 'plog_syn.npz', 'plog')]
+         ('plog.inp', 'plog_syn.npz', 'plog'),
+         ('cheb.inp', 'cheb_syn.npz', 'cheb')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 
