@@ -84,6 +84,16 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
 int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
                    long long y_ss, long long y_sv, double* d_dy, long long o_ss,
                    long long o_sv, void* stream);
+/* Finite-difference Jacobian of dydt, the independent on-device check of eval_jacob; replaces
+ * the reference's finite-difference comparison build (pyjac/performance_tester/fd_jacob.cu:23-95:
+ * same CVODE-style increments, ATOL 1e-15, RTOL 1e-8).  order 1 = the reference's default forward
+ * difference; 2, 4, 6 = central differences (the reference's FD_ORD > 1 branch sums y_temp instead
+ * of dy, fd_jacob.cu:84 -- the intended formula is used here).  r_cap = 0: the reference's
+ * increments; r_cap > 0: increments kept within [r_cap / 100, r_cap] * max(|y_j|, 1) (far from
+ * equilibrium the reference's r0 term exceeds the mass fractions, at equilibrium it vanishes).  d_y[NSP][n] and d_jac[NSP*NSP][n]
+ * state-fastest with leading dimension n; synchronous (scratch memory is allocated and freed). */
+int pyjac_fd_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y, double* d_jac,
+                       int order, double r_cap, void* stream);
 /* conc[NSP], fwd[FWD_RATES], rev[REV_RATES], pres_mod[PRES_MOD_RATES], spec_rates[NSP] and
  * dy[NSP] per state; any output pointer may be NULL.  Element v of state s of every output
  * goes to out[s*o_ss_mult*width + v] when o_state_fastest == 0 (rows), or out[v*o_ld + s]

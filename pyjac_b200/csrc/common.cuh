@@ -115,4 +115,41 @@ __global__ void k_spec_rates(const __grid_constant__ Tables tb, const double* fw
     sp_rates[k] = acc;
 }
 
+// ---- finite-difference Jacobian (the reference's comparison build, performance_tester/fd_jacob.cu:23-95)
+// All arrays state-fastest with leading dimension n.  k_fd_step: CVODE-style increment of column j,
+// r = max(sqrt(eps) |y_j|, r0 / ewt_j) with ewt = ATOL + RTOL |y|, r0 = 1000 RTOL eps NSP fac,
+// fac = rms(ewt * dy0), optionally capped; writes the increment and y_tmp = y with y_j + c * r.
+__global__ void k_fd_step(int n, int nsp, int j, double c, double r_cap, const double* y, const double* dy0, double* ytmp, double* r_out)
+{
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double atol = 1e-15, rtol = 1e-8, eps = 2.2204460492503131e-16;
+    double sum = 0.0;
+    for (int i = 0; i < nsp; ++i) {
+        const double e = (atol + rtol * fabs(y[(long long)i * n + s])) * dy0[(long long)i * n + s];
+        sum += e * e;
+    }
+    const double r0 = 1000.0 * rtol * eps * nsp * sqrt(sum / nsp);
+    const double yj = y[(long long)j * n + s];
+    double r = fmax(sqrt(eps) * fabs(yj), r0 / (atol + rtol * fabs(yj)));
+    // r0 grows with |dy/dt|: far from equilibrium the reference's increment can exceed the mass
+    // fractions themselves, and at equilibrium it vanishes (the difference quotient then amplifies
+    // the round-off of dy); r_cap > 0 keeps r within [r_cap / 100, r_cap] * max(|y_j|, 1)
+    if (r_cap > 0.0) r = fmax(fmin(r, r_cap * fmax(fabs(yj), 1.0)), 0.01 * r_cap * fmax(fabs(yj), 1.0));
+    r_out[s] = r;
+    // only row j differs from y: the caller keeps ytmp == y in every other row
+    ytmp[(long long)j * n + s] = yj + c * r;
+}
+
+// jac[:, j] (+)= w * dy / r   (first = 1: assign)
+__global__ void k_fd_accum(int n, int nsp, int j, double w, int first, const double* dy, const double* r, double* jac)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)n * nsp) return;
+    const long long i = t / n, s = t % n;
+    const double v = w * dy[i * n + s] / r[s];
+    double* o = jac + ((long long)j * nsp + i) * n + s;
+    *o = first ? v : *o + v;
+}
+
 }  // namespace pj

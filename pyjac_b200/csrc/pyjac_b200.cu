@@ -291,6 +291,49 @@ int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y
     return launch(m, pj::M_DYDT, io, (cudaStream_t)stream);
 }
 
+// Finite-difference Jacobian of dydt on the device: the independent self-check of eval_jacob
+// (the reference builds the same comparison from performance_tester/fd_jacob.cu).
+int pyjac_fd_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y, double* d_jac,
+                       int order, double r_cap, void* stream)
+{
+    if (!m || n < 0 || (n && (!d_pres || !d_y || !d_jac))) return fail(PYJAC_EINVAL, "bad argument");
+    if (order != 1 && order != 2 && order != 4 && order != 6) return fail(PYJAC_EINVAL, "order must be 1, 2, 4 or 6");
+    if (!n) return PYJAC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(m->device));
+    const int nsp = m->tb.nsp;
+    const size_t row = (size_t)n * nsp;
+    double* w = nullptr;                     // dy0 | ytmp | dy | r
+    CU(cudaMalloc(&w, (3 * row + (size_t)n) * sizeof(double)));
+    double *dy0 = w, *ytmp = w + row, *dy = w + 2 * row, *r = w + 3 * row;
+    static const double xs[4][6] = {{1}, {-1, 1}, {-2, -1, 1, 2}, {-3, -2, -1, 1, 2, 3}};
+    static const double ws[4][6] = {{1}, {-0.5, 0.5}, {1.0 / 12, -2.0 / 3, 2.0 / 3, -1.0 / 12},
+                                    {-1.0 / 60, 3.0 / 20, -3.0 / 4, 3.0 / 4, -3.0 / 20, 1.0 / 60}};
+    const int oi = order == 1 ? 0 : order == 2 ? 1 : order == 4 ? 2 : 3;
+    int rc = pyjac_dydt_dev(m, n, d_pres, d_y, 1, n, dy0, 1, n, st);
+    cudaError_t ce = cudaMemcpyAsync(ytmp, d_y, row * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    const int tb_ = 256;
+    const unsigned gs_ = (unsigned)((n + tb_ - 1) / tb_), ga_ = (unsigned)((row + tb_ - 1) / tb_);
+    for (int j = 0; j < nsp && !rc && ce == cudaSuccess; ++j) {
+        for (int k = 0; k < order && !rc; ++k) {
+            pj::k_fd_step<<<gs_, tb_, 0, st>>>(n, nsp, j, xs[oi][k], r_cap, d_y, dy0, ytmp, r);
+            rc = pyjac_dydt_dev(m, n, d_pres, ytmp, 1, n, dy, 1, n, st);
+            pj::k_fd_accum<<<ga_, tb_, 0, st>>>(n, nsp, j, ws[oi][k], k == 0, dy, r, d_jac);
+        }
+        if (order == 1 && !rc)               // forward difference: (f(y + r) - f(y)) / r
+            pj::k_fd_accum<<<ga_, tb_, 0, st>>>(n, nsp, j, -1.0, 0, dy0, r, d_jac);
+        // restore row j of ytmp
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(ytmp + (size_t)j * n, d_y + (size_t)j * n, (size_t)n * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, st);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(w);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(PYJAC_ECUDA, std::string("fd_jacob: ") + cudaGetErrorString(ce));
+    return PYJAC_OK;
+}
+
 int pyjac_rates_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
                     long long y_ss, long long y_sv, double* d_conc, double* d_fwd,
                     double* d_rev, double* d_pres_mod, double* d_spec_rates, double* d_dy,

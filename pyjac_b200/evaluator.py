@@ -125,6 +125,32 @@ class Evaluator:
                                            self._stream(stream)))
         return out
 
+    def fd_jacob(self, P, y, order: int = 6, r_cap: float = 0.0, out=None, stream=None):
+        """Finite-difference Jacobian of dydt (state-fastest ``y[NSP, n]`` -> ``jac[NSP*NSP, n]``):
+        the on-device self-check of :meth:`eval_jacob` (performance_tester/fd_jacob.cu)."""
+        torch = self._torch
+        self._check_dev(P, y, out)
+        n, _, _ = self._strides(y, 'state_fastest')
+        if out is None:
+            out = torch.empty((self.NSP * self.NSP, n), dtype=torch.float64, device=y.device)
+        assert out.shape == (self.NSP * self.NSP, n) and out.is_contiguous()
+        _lib.check(self.lib.pyjac_fd_jacob_dev(self._h, n, _ptr(P), _ptr(y), _ptr(out), int(order),
+                                               float(r_cap), self._stream(stream)))
+        return out
+
+    def self_check(self, P, y, order: int = 6, r_cap: float = 0.0):
+        """max over states and columns of |analytical - finite difference| / scale, scale = the
+        column maximum, but at least 1e-6 of the state's largest entry (finite differences cannot
+        resolve a column below their own round-off)."""
+        torch = self._torch
+        jac = self.eval_jacob(P, y, y_layout='state_fastest', jac_layout='state_fastest')
+        fd = self.fd_jacob(P, y, order, r_cap)
+        nsp, n = self.NSP, y.shape[1]
+        a, f = jac.view(nsp, nsp, n), fd.view(nsp, nsp, n)          # [column j][row i][state]
+        scale = a.abs().amax(dim=1, keepdim=True)
+        scale = torch.maximum(scale, 1e-6 * scale.amax(dim=0, keepdim=True)).clamp_min(1e-300)
+        return float(((a - f).abs() / scale).max())
+
     def rates(self, P, y, y_layout: str = 'rows', want_dy: bool = False, stream=None):
         """conc, fwd, rev, pres_mod, spec_rates[, dy] in the layout of ``y``."""
         torch = self._torch

@@ -137,6 +137,34 @@ def test_plog_against_oracle_across_pressures(torch, golden_dir):
     ev.close()
 
 
+def test_fd_self_check(torch, golden_dir):
+    """On-device finite-difference Jacobian of dydt (the reference's fd_jacob.cu comparison) against
+    the analytical Jacobian: an oracle-free check.  Sixth-order central differences with CVODE-style
+    increments; tolerance = what finite differences in fp64 can resolve."""
+    for mech_file, n in (('gri30_syn.inp', 256), ('plog.inp', 512), ('cheb.inp', 512)):
+        mech, ev = _evaluator(golden_dir, mech_file)
+        P_h, y_h = synthetic_states(mech.NSP, n, seed=31)
+        P = torch.tensor(P_h, device='cuda')
+        y = torch.tensor(y_h, device='cuda').t().contiguous()
+        # these states are far from equilibrium: the reference's r0 term would exceed the mass fractions
+        err6 = ev.self_check(P, y, order=6, r_cap=1e-5)
+        err1 = ev.self_check(P, y, order=1, r_cap=1e-5)
+        print('%s: fd order 6 %.2e, order 1 %.2e' % (mech_file, err6, err1))
+        assert err6 < 1e-3, (mech_file, err6)
+        assert err1 < 0.2, (mech_file, err1)
+        ev.close()
+    # the bundled PaSR states (many exact-zero mass fractions: the reference's r0 / ewt increment
+    # is unbounded there -- its finite-difference build is a timing comparison, not an accuracy one)
+    mech, ev = _evaluator(golden_dir, 'h2o2_n2.inp')
+    g = np.load(os.path.join(golden_dir, 'h2o2_pasr.npz'))
+    P = torch.tensor(g['P'], device='cuda')
+    y = torch.tensor(g['y'], device='cuda').t().contiguous()
+    err = ev.self_check(P, y, order=6, r_cap=1e-5)
+    print('h2o2 PaSR states: %.2e' % err)
+    assert err < 1e-3, err
+    ev.close()
+
+
 def test_empty_batch(torch, golden_dir):
     mech, ev = _evaluator(golden_dir, 'h2o2_n2.inp')
     P = torch.empty(0, dtype=torch.float64, device='cuda')
