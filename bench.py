@@ -319,7 +319,7 @@ def run_ours(args, rank, world, local_rank):
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': None if traffic is None else traffic * n,
                          'peak_source': peak_src, 'bytes_per_state': bytes_per_state,
-                         'kernel': 'pj5::k_eval<GS, 512, M_JAC>', 'kernel_ms': kernel_ms},
+                         'kernel': 'pj5::k_eval<8, 384, M_JAC>', 'kernel_ms': kernel_ms},
             'e2e': e2e, 'cpu_baseline': cpu, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)

@@ -58,6 +58,7 @@ struct IO {
     double* scal3;   // M_RATES: y_N, mw_avg, rho per state (3 doubles, rows), nullable
     int o_sf;
     long long o_ld;
+    const char* ws;  // working sets in global memory (one per block) for plans that ask for it, or NULL
     int dbg_skip;    // development only (PYJAC_DEBUG_SKIP): phases to skip when timing
     long long* dbg_clk;   // development only: per-phase cycle counts of block 0 or NULL
 };

@@ -38,6 +38,7 @@ using namespace pj;
 
 struct Plan {
     int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync, coop, tcoop, oCF;
+    int wsg;                         // 1: the working set lives in global memory (IO::ws), not in shared memory
     const int4* rx;
     const int4* rx_out;              // {fwd index, rev index or -1, pres_mod index or -1, 0} (M_RATES)
     const int* eff_off;
@@ -75,25 +76,40 @@ enum : unsigned { NULL_E = 0x3FFFFFu };
 struct V {
     double x, y;
 };
-template <int OFF = 0>
-__device__ __forceinline__ V lds(unsigned a)
-{
-    V v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF));
-    return v;
-}
-template <int OFF = 0>
-__device__ __forceinline__ void sts(unsigned a, V v)
-{
-    asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v.x), "d"(v.y) : "memory");
-}
-// store only where p holds (no branch)
-template <int OFF = 0>
-__device__ __forceinline__ void sts_if(bool p, unsigned a, V v)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t@q st.shared.v2.f64 [%0+%1], {%2, %3};\n\t}"
-                 ::"r"(a), "n"(OFF), "d"(v.x), "d"(v.y), "r"((int)p) : "memory");
-}
+// Where the working set of a block lives.  G = false: shared memory, `a` is a 32-bit shared-space
+// address.  G = true: a per-block scratch area in global memory (mechanisms whose working set
+// exceeds shared memory; L1 / L2 hold it), `a` is a byte offset from the block's base `g`.
+template <bool G>
+struct Mem {
+    const char* g;
+    template <int OFF>
+    __device__ __forceinline__ V ld(unsigned a) const
+    {
+        V v;
+        if (G) asm volatile("ld.global.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "l"(g + a), "n"(OFF) : "memory");
+        else asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF));
+        return v;
+    }
+    template <int OFF>
+    __device__ __forceinline__ void st(unsigned a, V v) const
+    {
+        if (G) asm volatile("st.global.v2.f64 [%0+%1], {%2, %3};" ::"l"(g + a), "n"(OFF), "d"(v.x), "d"(v.y) : "memory");
+        else asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v.x), "d"(v.y) : "memory");
+    }
+    // store only where p holds (no branch)
+    template <int OFF>
+    __device__ __forceinline__ void st_if(bool p, unsigned a, V v) const
+    {
+        if (G) asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t@q st.global.v2.f64 [%0+%1], {%2, %3};\n\t}"
+                            ::"l"(g + a), "n"(OFF), "d"(v.x), "d"(v.y), "r"((int)p) : "memory");
+        else asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t@q st.shared.v2.f64 [%0+%1], {%2, %3};\n\t}"
+                          ::"r"(a), "n"(OFF), "d"(v.x), "d"(v.y), "r"((int)p) : "memory");
+    }
+};
+// every routine that touches the working set has a `mem` in scope
+#define LDS(OFF, ...) mem.template ld<(OFF)>(__VA_ARGS__)
+#define STS(OFF, ...) mem.template st<(OFF)>(__VA_ARGS__)
+#define STS_IF(OFF, ...) mem.template st_if<(OFF)>(__VA_ARGS__)
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // exp of N values at once (so that the polynomial constants are materialised once): arguments
@@ -160,8 +176,8 @@ __device__ __forceinline__ void put2(double* base, const IO& io, int width, cons
     if (o.ok1) put(base, io, width, o.s0 + 1, v, x.y);
 }
 
-template <int GS, bool PM, int MODE>
-__device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const IO& io, const Out& out,
+template <int GS, bool PM, int MODE, bool WSG>
+__device__ __forceinline__ void reaction(const Mem<WSG>& mem, const Tables& tb, const Plan& pl, const IO& io, const Out& out,
                                          unsigned aSP, unsigned aRX,
                                          unsigned aRAW, unsigned aSC, int p, bool valid, bool three,
                                          const int4 q0, const int4 q1, const int4 q2, const int4 q3,
@@ -182,17 +198,17 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
     const bool isrev = fl & F_REV;
 
     // ---- species values and the arguments of kf, kr
-    const V c0 = lds<E_C * RB>(a0), c1 = lds<E_C * RB>(a1), c3 = lds<E_C * RB>(a3), c4 = lds<E_C * RB>(a4);
+    const V c0 = LDS(E_C * RB, a0), c1 = LDS(E_C * RB, a1), c3 = LDS(E_C * RB, a3), c4 = LDS(E_C * RB, a4);
     V c2{1.0, 1.0}, c5{1.0, 1.0};
-    V sB = vsub(vadd(lds<O_B * RB>(a3 ^ RB), lds<O_B * RB>(a4 ^ RB)), vadd(lds<O_B * RB>(a0 ^ RB), lds<O_B * RB>(a1 ^ RB)));
-    V sdB = vsub(vadd(lds<E_DB * RB>(a3), lds<E_DB * RB>(a4)), vadd(lds<E_DB * RB>(a0), lds<E_DB * RB>(a1)));
-    V dH = vsub(vadd(lds<O_HW * RB>(a3 ^ RB), lds<O_HW * RB>(a4 ^ RB)), vadd(lds<O_HW * RB>(a0 ^ RB), lds<O_HW * RB>(a1 ^ RB)));
+    V sB = vsub(vadd(LDS(O_B * RB, a3 ^ RB), LDS(O_B * RB, a4 ^ RB)), vadd(LDS(O_B * RB, a0 ^ RB), LDS(O_B * RB, a1 ^ RB)));
+    V sdB = vsub(vadd(LDS(E_DB * RB, a3), LDS(E_DB * RB, a4)), vadd(LDS(E_DB * RB, a0), LDS(E_DB * RB, a1)));
+    V dH = vsub(vadd(LDS(O_HW * RB, a3 ^ RB), LDS(O_HW * RB, a4 ^ RB)), vadd(LDS(O_HW * RB, a0 ^ RB), LDS(O_HW * RB, a1 ^ RB)));
     if (three) {
-        c2 = lds<E_C * RB>(a2);
-        c5 = lds<E_C * RB>(a5);
-        sB = vadd(sB, vsub(lds<O_B * RB>(a5 ^ RB), lds<O_B * RB>(a2 ^ RB)));
-        sdB = vadd(sdB, vsub(lds<E_DB * RB>(a5), lds<E_DB * RB>(a2)));
-        dH = vadd(dH, vsub(lds<O_HW * RB>(a5 ^ RB), lds<O_HW * RB>(a2 ^ RB)));
+        c2 = LDS(E_C * RB, a2);
+        c5 = LDS(E_C * RB, a5);
+        sB = vadd(sB, vsub(LDS(O_B * RB, a5 ^ RB), LDS(O_B * RB, a2 ^ RB)));
+        sdB = vadd(sdB, vsub(LDS(E_DB * RB, a5), LDS(E_DB * RB, a2)));
+        dH = vadd(dH, vsub(LDS(O_HW * RB, a5 ^ RB), LDS(O_HW * RB, a2 ^ RB)));
     }
     const V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
     const V lnkr{lnkf.x - sB.x - lnKc, lnkf.y - sB.y - lnKc};
@@ -206,19 +222,19 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
     const double* par = tb.pm_par + mi * NPAR;
     bool rates_done = false;
     if (PM) {
-        V thd = lds<Q_M * RB>(aSC);
+        V thd = LDS(Q_M * RB, aSC);
         // collider records {alpha - 1, species row offset, raw row}, four at a time (padded)
         const int e0 = __ldg(pl.eff_off + mi), e1_ = __ldg(pl.eff_off + mi + 1);
         for (int e = e0; e < e1_; e += 4) {
             const int4 r0 = __ldg(pl.eff + e), r1 = __ldg(pl.eff + e + 1), r2 = __ldg(pl.eff + e + 2), r3 = __ldg(pl.eff + e + 3);
-            thd = vfma(__hiloint2double(r0.y, r0.x), lds<E_C * RB>(aSP + r0.z), thd);
-            thd = vfma(__hiloint2double(r1.y, r1.x), lds<E_C * RB>(aSP + r1.z), thd);
-            thd = vfma(__hiloint2double(r2.y, r2.x), lds<E_C * RB>(aSP + r2.z), thd);
-            thd = vfma(__hiloint2double(r3.y, r3.x), lds<E_C * RB>(aSP + r3.z), thd);
+            thd = vfma(__hiloint2double(r0.y, r0.x), LDS(E_C * RB, aSP + r0.z), thd);
+            thd = vfma(__hiloint2double(r1.y, r1.x), LDS(E_C * RB, aSP + r1.z), thd);
+            thd = vfma(__hiloint2double(r2.y, r2.x), LDS(E_C * RB, aSP + r2.z), thd);
+            thd = vfma(__hiloint2double(r3.y, r3.x), LDS(E_C * RB, aSP + r3.z), thd);
         }
         if (fl & F_PDEP) {
             const int csp = __ldg(tb.pm_sp + mi);
-            const V ctv = csp >= 0 ? lds<E_C * RB>(sp_even<GS>(aSP, (unsigned)csp)) : thd;
+            const V ctv = csp >= 0 ? LDS(E_C * RB, sp_even<GS>(aSP, (unsigned)csp)) : thd;
             const bool low = fl & F_LOW;
             const double p0 = par[0], p1 = par[1], p2 = par[2], p3 = par[3];
             const double ct[2] = {ctv.x, ctv.y}, Tt[2] = {T.x, T.y}, lT[2] = {logT.x, logT.y}, rT[2] = {iT.x, iT.y};
@@ -330,7 +346,7 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
     }
     if (MODE != M_JAC) {
         // only the net rate is needed for the species rates
-        sts_if<RX_NET * RB>(valid, aRX + p * RXB, PM ? vmul(net, PM_) : net);
+        STS_IF(RX_NET * RB, valid, aRX + p * RXB, PM ? vmul(net, PM_) : net);
         return;
     }
     V pmt{0.0, 0.0};
@@ -338,7 +354,7 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
 
     // ---- Jacobian scalars
     const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
-    const V rho_inv = lds<Q_RHOINV * RB>(aSC), mwr_ = lds<Q_MWR * RB>(aSC), nmwr{-mwr_.x, -mwr_.y};
+    const V rho_inv = LDS(Q_RHOINV * RB, aSC), mwr_ = LDS(Q_MWR * RB, aSC), nmwr{-mwr_.x, -mwr_.y};
     const double extra = (PM && (fl & F_EFFN1)) ? 1.0 : 0.0;
     const double n1 = nre + extra, n2 = npr + extra, omre = 1.0 - nre, ompr = 1.0 - npr;
     V tT, X1, X2;
@@ -379,7 +395,7 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
     if ((SLOT) != nsp_f) {                                               \
         const V d_ = (EXPR);                                             \
         if ((SLOT) == last_f) X2 = vsub(X2, d_);                         \
-        else if (valid) sts<0>(aRAW + (DST) * RB, d_);                   \
+        else if (valid) STS(0, aRAW + (DST) * RB, d_);                   \
     }
     if (three) {
         PJ_EMIT(s0, q3.x & 0xFFFFu, vmul(pk, vmul(c1, c2)))
@@ -405,28 +421,28 @@ __device__ __forceinline__ void reaction(const Tables& tb, const Plan& pl, const
             for (int e = e0; e < e1_; e += 4) {
                 const int4 r0 = __ldg(pl.eff + e), r1 = __ldg(pl.eff + e + 1), r2 = __ldg(pl.eff + e + 2), r3 = __ldg(pl.eff + e + 3);
                 const int none = tb.nraw + 1;          // padding records and colliders without a raw row
-                sts_if<0>(r0.w != none, aRAW + r0.w * RB, vmul(__hiloint2double(r0.y, r0.x), pmt));
-                sts_if<0>(r1.w != none, aRAW + r1.w * RB, vmul(__hiloint2double(r1.y, r1.x), pmt));
-                sts_if<0>(r2.w != none, aRAW + r2.w * RB, vmul(__hiloint2double(r2.y, r2.x), pmt));
-                sts_if<0>(r3.w != none, aRAW + r3.w * RB, vmul(__hiloint2double(r3.y, r3.x), pmt));
+                STS_IF(0, r0.w != none, aRAW + r0.w * RB, vmul(__hiloint2double(r0.y, r0.x), pmt));
+                STS_IF(0, r1.w != none, aRAW + r1.w * RB, vmul(__hiloint2double(r1.y, r1.x), pmt));
+                STS_IF(0, r2.w != none, aRAW + r2.w * RB, vmul(__hiloint2double(r2.y, r2.x), pmt));
+                STS_IF(0, r3.w != none, aRAW + r3.w * RB, vmul(__hiloint2double(r3.y, r3.x), pmt));
             }
         }
-        if (fl & F_WANT_PMT) sts<0>(aRAW + ((unsigned)q3.w >> 16) * RB, pmt);
+        if (fl & F_WANT_PMT) STS(0, aRAW + ((unsigned)q3.w >> 16) * RB, pmt);
     }
     if (valid) {
         const unsigned ar = aRX + p * RXB;
-        sts<RX_NET * RB>(ar, PM ? vmul(net, PM_) : net);
-        sts<RX_TT * RB>(ar, tT);
-        sts<RX_X1 * RB>(ar, X1);
-        sts<RX_X2 * RB>(ar, X2);
-        sts<RX_DH * RB>(ar, dH);
+        STS(RX_NET * RB, ar, PM ? vmul(net, PM_) : net);
+        STS(RX_TT * RB, ar, tT);
+        STS(RX_X1 * RB, ar, X1);
+        STS(RX_X2 * RB, ar, X2);
+        STS(RX_DH * RB, ar, dH);
     }
 }
 
 // Phase B for one reaction without pressure modification (the common case) and the two states
 // of the lane: no branches except `three` (warp-uniform) and the rare last-species fold.
-template <int GS, int MODE, bool SPECIAL>
-__device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl, const IO& io, const Out& out,
+template <int GS, int MODE, bool SPECIAL, bool WSG>
+__device__ __forceinline__ void reaction_plain(const Mem<WSG>& mem, const Tables& tb, const Plan& pl, const IO& io, const Out& out,
                                                unsigned aSP, unsigned aRX,
                                                unsigned aRAW, unsigned aSC, unsigned aPL, int p, bool valid, bool three,
                                                const int4 q0, const int4 q1, const int4 q2, const int4 q3,
@@ -438,19 +454,19 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     const int fl = q2.x;
     const unsigned s0 = q2.y & 0xFFFFu, s1 = (unsigned)q2.y >> 16, s3 = (unsigned)q2.z >> 16, s4 = q2.w & 0xFFFFu;
     const unsigned a0 = aSP + s0 * 16, a1 = aSP + s1 * 16, a3 = aSP + s3 * 16, a4 = aSP + s4 * 16;
-    V c0 = lds<E_C * RB>(a0), c1 = lds<E_C * RB>(a1), c3 = lds<E_C * RB>(a3), c4 = lds<E_C * RB>(a4);
-    V sB = vsub(vadd(lds<O_B * RB>(a3 ^ RB), lds<O_B * RB>(a4 ^ RB)), vadd(lds<O_B * RB>(a0 ^ RB), lds<O_B * RB>(a1 ^ RB)));
-    V sdB = vsub(vadd(lds<E_DB * RB>(a3), lds<E_DB * RB>(a4)), vadd(lds<E_DB * RB>(a0), lds<E_DB * RB>(a1)));
-    V dH = vsub(vadd(lds<O_HW * RB>(a3 ^ RB), lds<O_HW * RB>(a4 ^ RB)), vadd(lds<O_HW * RB>(a0 ^ RB), lds<O_HW * RB>(a1 ^ RB)));
+    V c0 = LDS(E_C * RB, a0), c1 = LDS(E_C * RB, a1), c3 = LDS(E_C * RB, a3), c4 = LDS(E_C * RB, a4);
+    V sB = vsub(vadd(LDS(O_B * RB, a3 ^ RB), LDS(O_B * RB, a4 ^ RB)), vadd(LDS(O_B * RB, a0 ^ RB), LDS(O_B * RB, a1 ^ RB)));
+    V sdB = vsub(vadd(LDS(E_DB * RB, a3), LDS(E_DB * RB, a4)), vadd(LDS(E_DB * RB, a0), LDS(E_DB * RB, a1)));
+    V dH = vsub(vadd(LDS(O_HW * RB, a3 ^ RB), LDS(O_HW * RB, a4 ^ RB)), vadd(LDS(O_HW * RB, a0 ^ RB), LDS(O_HW * RB, a1 ^ RB)));
     V c2{1.0, 1.0}, c5{1.0, 1.0};
     const unsigned s2 = q2.z & 0xFFFFu, s5 = (unsigned)q2.w >> 16;
     if (three) {
         const unsigned a2 = aSP + s2 * 16, a5 = aSP + s5 * 16;
-        c2 = lds<E_C * RB>(a2);
-        c5 = lds<E_C * RB>(a5);
-        sB = vadd(sB, vsub(lds<O_B * RB>(a5 ^ RB), lds<O_B * RB>(a2 ^ RB)));
-        sdB = vadd(sdB, vsub(lds<E_DB * RB>(a5), lds<E_DB * RB>(a2)));
-        dH = vadd(dH, vsub(lds<O_HW * RB>(a5 ^ RB), lds<O_HW * RB>(a2 ^ RB)));
+        c2 = LDS(E_C * RB, a2);
+        c5 = LDS(E_C * RB, a5);
+        sB = vadd(sB, vsub(LDS(O_B * RB, a5 ^ RB), LDS(O_B * RB, a2 ^ RB)));
+        sdB = vadd(sdB, vsub(LDS(E_DB * RB, a5), LDS(E_DB * RB, a2)));
+        dH = vadd(dH, vsub(LDS(O_HW * RB, a5 ^ RB), LDS(O_HW * RB, a2 ^ RB)));
     }
     V lnkf = vfma(bexp, logT, V{fma(-Ta, iT.x, lnA), fma(-Ta, iT.y, lnA)});
     V dk{0.0, 0.0};                                           // d ln kf / d ln T
@@ -460,7 +476,7 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
         // (cj:1687-1850): the Arrhenius set of the first / last pressure outside the table,
         // linear interpolation of ln kf in ln P between two pressures
         const int o0 = __ldg(tb.plog_off + p), o1 = __ldg(tb.plog_off + p + 1);
-        const V Pv = lds<S_P * RB>(aPL), lP = lds<Q_LNP * RB>(aSC);
+        const V Pv = LDS(S_P * RB, aPL), lP = LDS(Q_LNP * RB, aSC);
         const double Ps[2] = {Pv.x, Pv.y}, lPs[2] = {lP.x, lP.y}, lTs[2] = {logT.x, logT.y}, rTs[2] = {iT.x, iT.y};
         double lk[2], dkk[2];
 #pragma unroll
@@ -492,7 +508,7 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
         const int n_t = (int)__ldg(cq), n_p = (int)__ldg(cq + 1);
         const double* c8 = cq + 12;
         const double* c16 = c8 + n_t * n_p;
-        const V lP = lds<Q_LNP * RB>(aSC);
+        const V lP = LDS(Q_LNP * RB, aSC);
         const double lPs[2] = {lP.x, lP.y}, rTs[2] = {iT.x, iT.y};
         const double ln10 = 2.30258509299404568402, iln10 = 0.43429448190325182765;
         double lr[2], lj[2], dkk[2];
@@ -552,12 +568,12 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
         if (io.rev && isrev) put2(io.rev, io, tb.nrev, out, ro.y, r);
     }
     if (MODE != M_JAC) {
-        sts_if<RX_NET * RB>(valid, aRX + p * RXB, net);
+        STS_IF(RX_NET * RB, valid, aRX + p * RXB, net);
         return;
     }
     const double nre = (double)((fl >> NRE_SHIFT) & 15), npr = (double)((fl >> NPR_SHIFT) & 15);
     const double omre = 1.0 - nre, ompr = 1.0 - npr;
-    const V rho_inv = lds<Q_RHOINV * RB>(aSC), mwr_ = lds<Q_MWR * RB>(aSC), nmwr{-mwr_.x, -mwr_.y};
+    const V rho_inv = LDS(Q_RHOINV * RB, aSC), mwr_ = LDS(Q_MWR * RB, aSC), nmwr{-mwr_.x, -mwr_.y};
     if (!SPECIAL) dk = V{fma(Ta, iT.x, bexp), fma(Ta, iT.y, bexp)};
     // irreversible: r = 0 makes this f * (dk + 1 - nre)          (cj:1461-1523)
     V elem = vfma(net, dk, vmul(omre, f));
@@ -581,7 +597,7 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
     }
     // raw rows; slots without one carry the scratch row index and store nothing
     const unsigned none = tb.nraw + 1;
-    auto emit = [&](unsigned dst, V d) { sts_if<0>(valid && dst != none, aRAW + dst * RB, d); };
+    auto emit = [&](unsigned dst, V d) { STS_IF(0, valid && dst != none, aRAW + dst * RB, d); };
     emit(q3.x & 0xFFFFu, d0);
     emit((unsigned)q3.x >> 16, d1);
     emit((unsigned)q3.y >> 16, n3);
@@ -591,14 +607,14 @@ __device__ __forceinline__ void reaction_plain(const Tables& tb, const Plan& pl,
         emit((unsigned)q3.z >> 16, n5);
     }
     const unsigned ar = aRX + p * RXB;
-    sts_if<RX_NET * RB>(valid, ar, net);
-    sts_if<RX_TT * RB>(valid, ar, tT);
-    sts_if<RX_X1 * RB>(valid, ar, X1);
-    sts_if<RX_X2 * RB>(valid, ar, X2);
-    sts_if<RX_DH * RB>(valid, ar, dH);
+    STS_IF(RX_NET * RB, valid, ar, net);
+    STS_IF(RX_TT * RB, valid, ar, tT);
+    STS_IF(RX_X1 * RB, valid, ar, X1);
+    STS_IF(RX_X2 * RB, valid, ar, X2);
+    STS_IF(RX_DH * RB, valid, ar, dH);
 }
 
-template <int GS, int MAXT, int MODE>
+template <int GS, int MAXT, int MODE, bool WSG = false>
 __global__ void __launch_bounds__(MAXT, 1)
 k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const __grid_constant__ IO io)
 {
@@ -611,36 +627,39 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
     const int nw = pl.nw;
     const int sub = lane / NPR, pr = lane % NPR;
     const int nsp = tb.nsp, last = tb.nsp - 1;
-    // 32-bit shared addresses of this lane's state pair in each region
-    const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + pr * 16;
-    if (((unsigned)__cvta_generic_to_shared(smem) + pl.oSP * 8) & (2 * RB - 1)) __trap();   // E ^ RB needs this
+    // working set: shared memory, or (WSG) this block's scratch area in global memory
+    const unsigned ws0 = WSG ? 0u : (unsigned)__cvta_generic_to_shared(smem);
+    const Mem<WSG> mem{WSG ? io.ws + (size_t)blockIdx.x * ((size_t)pl.total * 8) : nullptr};
+    // 32-bit addresses (WSG: offsets) of this lane's state pair in each region
+    const unsigned sb = ws0 + pr * 16;
+    if ((ws0 + pl.oSP * 8) & (2 * RB - 1)) __trap();   // E ^ RB needs this
     const unsigned aSP = sb + pl.oSP * 8, aRX = sb + pl.oRX * 8, aRAW = sb + pl.oRAW * 8;
     const unsigned aSC0 = sb + pl.oSC * 8, aPA = sb + pl.oPA * 8;
     const unsigned aSD = aSC0 + 2 * SCB;   // scalars derived in phase DE
-    const unsigned aCF = (unsigned)__cvta_generic_to_shared(smem) + pl.oCF * 8;   // column factors, [col][2]
+    const unsigned aCF = ws0 + pl.oCF * 8;   // column factors, [col][2]
     const V zero{0.0, 0.0};
 
     // the column factors (848 bytes for 53 species) live in shared memory: they are needed once
     // per Jacobian element and do not survive in the small L1 next to the streamed tables
     for (int i = tid; i < nsp; i += blockDim.x) {
         const double2 c = __ldg(pl.colfac + i);
-        sts<0>(aCF + i * 16, V{c.x, c.y});
+        STS(0, aCF + i * 16, V{c.x, c.y});
     }
 
     // rows that never change: the empty reaction slot, two all-zero reactions and raw rows (the
     // padding of the gather lists; one on either half of a bank line)
     if (warp == 0 && sub == 0) {
         const unsigned a = sp_even<GS>(aSP, (unsigned)nsp), o = a ^ RB;
-        sts<E_C * RB>(a, V{1.0, 1.0});
-        sts<O_B * RB>(o, zero); sts<E_DB * RB>(a, zero); sts<O_HW * RB>(o, zero);
-        sts<E_WA * RB>(a, zero); sts<O_WB * RB>(o, zero); sts<E_WT * RB>(a, zero); sts<O_CP * RB>(o, zero);
+        STS(E_C * RB, a, V{1.0, 1.0});
+        STS(O_B * RB, o, zero); STS(E_DB * RB, a, zero); STS(O_HW * RB, o, zero);
+        STS(E_WA * RB, a, zero); STS(O_WB * RB, o, zero); STS(E_WT * RB, a, zero); STS(O_CP * RB, o, zero);
         for (int z = 0; z < 2; ++z) {
             const unsigned ar = aRX + (tb.nr + z) * RXB;
-            sts<RX_NET * RB>(ar, zero); sts<RX_TT * RB>(ar, zero); sts<RX_X1 * RB>(ar, zero);
-            sts<RX_X2 * RB>(ar, zero); sts<RX_DH * RB>(ar, zero);
+            STS(RX_NET * RB, ar, zero); STS(RX_TT * RB, ar, zero); STS(RX_X1 * RB, ar, zero);
+            STS(RX_X2 * RB, ar, zero); STS(RX_DH * RB, ar, zero);
         }
-        sts<0>(aRAW + tb.nraw * RB, zero);
-        sts<0>(aRAW + (tb.nraw + 1) * RB, zero);
+        STS(0, aRAW + tb.nraw * RB, zero);
+        STS(0, aRAW + (tb.nraw + 1) * RB, zero);
     }
 
     const bool sf = io.jac_layout != 0;
@@ -664,7 +683,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         V sumY = zero, sumYW = zero;
         for (int k = sub; k < (inc ? nsp : last); k += NSUB) {
             const V Yk{y0[(long long)(k + 1) * io.y_sv], y1[(long long)(k + 1) * io.y_sv]};
-            sts<E_Y * RB>(sp_even<GS>(aSP, (unsigned)k), Yk);
+            STS(E_Y * RB, sp_even<GS>(aSP, (unsigned)k), Yk);
             sumY = vadd(sumY, Yk);
             sumYW = vfma(__ldg((inc ? tb.sp_w : tb.sp_iw) + k), Yk, sumYW);
         }
@@ -691,16 +710,16 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 o[Q_M][g2] = P[g2] / (tb.ru * T[g2]);
             }
             const unsigned a = aSC0 + b * SCB;
-            if (!inc) sts<E_Y * RB>(sp_even<GS>(aSP, (unsigned)last), V{yN[0], yN[1]});
-            sts<Q_T * RB>(a, V{o[Q_T][0], o[Q_T][1]});
-            sts<Q_LOGT * RB>(a, V{o[Q_LOGT][0], o[Q_LOGT][1]});
-            sts<Q_IT * RB>(a, V{o[Q_IT][0], o[Q_IT][1]});
-            sts<Q_RHO * RB>(a, V{o[Q_RHO][0], o[Q_RHO][1]});
-            sts<Q_RHOINV * RB>(a, V{o[Q_RHOINV][0], o[Q_RHOINV][1]});
-            sts<Q_LNP * RB>(a, V{o[Q_LNP][0], o[Q_LNP][1]});
-            sts<Q_MWR * RB>(a, V{o[Q_MWR][0], o[Q_MWR][1]});
-            sts<Q_M * RB>(a, V{o[Q_M][0], o[Q_M][1]});
-            if (tb.nplog) sts<S_P * RB>(aSD + b * RB, V{P[0], P[1]});
+            if (!inc) STS(E_Y * RB, sp_even<GS>(aSP, (unsigned)last), V{yN[0], yN[1]});
+            STS(Q_T * RB, a, V{o[Q_T][0], o[Q_T][1]});
+            STS(Q_LOGT * RB, a, V{o[Q_LOGT][0], o[Q_LOGT][1]});
+            STS(Q_IT * RB, a, V{o[Q_IT][0], o[Q_IT][1]});
+            STS(Q_RHO * RB, a, V{o[Q_RHO][0], o[Q_RHO][1]});
+            STS(Q_RHOINV * RB, a, V{o[Q_RHOINV][0], o[Q_RHOINV][1]});
+            STS(Q_LNP * RB, a, V{o[Q_LNP][0], o[Q_LNP][1]});
+            STS(Q_MWR * RB, a, V{o[Q_MWR][0], o[Q_MWR][1]});
+            STS(Q_M * RB, a, V{o[Q_M][0], o[Q_M][1]});
+            if (tb.nplog) STS(S_P * RB, aSD + b * RB, V{P[0], P[1]});
         }
     };
 
@@ -739,13 +758,13 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
 
         // ------------------------------------------------------------ phase A1: species thermo
         if (!(io.dbg_skip & 1)) {
-            const V T = lds<Q_T * RB>(aSC), logT = lds<Q_LOGT * RB>(aSC), iT = lds<Q_IT * RB>(aSC);
-            const V rho = lds<Q_RHO * RB>(aSC);
+            const V T = LDS(Q_T * RB, aSC), logT = LDS(Q_LOGT * RB, aSC), iT = LDS(Q_IT * RB, aSC);
+            const V rho = LDS(Q_RHO * RB, aSC);
             const double Tv[2] = {T.x, T.y}, lT[2] = {logT.x, logT.y}, rT[2] = {iT.x, iT.y}, rh[2] = {rho.x, rho.y};
             double cpavg[2] = {0.0, 0.0}, wdcp[2] = {0.0, 0.0};
             for (int k = warp * NSUB + sub; k < nsp; k += nw * NSUB) {
                 const unsigned a = sp_even<GS>(aSP, (unsigned)k), o = a ^ RB;
-                const V Yv = lds<E_Y * RB>(a);
+                const V Yv = LDS(E_Y * RB, a);
                 const double iw = __ldg(tb.sp_iw + k), ruw = __ldg(tb.sp_ruw + k), wk = __ldg(tb.sp_w + k);
                 const bool inc = MODE == M_RATES && io.in_conc;       // the slot holds C_k, not Y_k
                 const double Yk[2] = {inc ? Yv.x * wk / rh[0] : Yv.x, inc ? Yv.y * wk / rh[1] : Yv.y};
@@ -765,17 +784,17 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                     dB[g] = (c[11] + c[5] * rT[g]) * rT[g] + hh;
                     Bk[g] = c[10] + c[11] * lT[g] + t * (c[6] + t * (c[12] + t * (c[13] + c[14] * t))) - c[5] * rT[g];
                 }
-                sts<E_C * RB>(a, V{ck[0], ck[1]});
+                STS(E_C * RB, a, V{ck[0], ck[1]});
                 if (MODE == M_RATES && io.conc) put2(io.conc, io, nsp, out, k, V{ck[0], ck[1]});
-                sts<O_B * RB>(o, V{Bk[0], Bk[1]});
-                sts<E_DB * RB>(a, V{dB[0], dB[1]});
-                sts<O_HW * RB>(o, V{hW[0], hW[1]});
-                sts<O_CP * RB>(o, V{cp[0], cp[1]});
+                STS(O_B * RB, o, V{Bk[0], Bk[1]});
+                STS(E_DB * RB, a, V{dB[0], dB[1]});
+                STS(O_HW * RB, o, V{hW[0], hW[1]});
+                STS(O_CP * RB, o, V{cp[0], cp[1]});
             }
             const V ca = sub_sum<GS>(V{cpavg[0], cpavg[1]}), wd = sub_sum<GS>(V{wdcp[0], wdcp[1]});
             if (sub == 0) {
-                sts<D_CPAVG * RB>(aPA + warp * NPART * RB, ca);
-                sts<D_WDCP * RB>(aPA + warp * NPART * RB, wd);
+                STS(D_CPAVG * RB, aPA + warp * NPART * RB, ca);
+                STS(D_WDCP * RB, aPA + warp * NPART * RB, wd);
             }
         }
         // the first reaction record of phase B is requested before the barrier (tables come from L2)
@@ -792,7 +811,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
 
         // ------------------------------------------------------------ phase B: reactions
         if (!(io.dbg_skip & 2)) {
-            const V T = lds<Q_T * RB>(aSC), logT = lds<Q_LOGT * RB>(aSC), iT = lds<Q_IT * RB>(aSC);
+            const V T = LDS(Q_T * RB, aSC), logT = LDS(Q_LOGT * RB, aSC), iT = LDS(Q_IT * RB, aSC);
             const unsigned nsp_f = sp_even<GS>(0u, (unsigned)nsp) / 16;
             int item = b_item0;
             int4 q0 = b_q0, q1 = b_q1, q2 = b_q2, q3 = b_q3;       // first record: requested before the barrier
@@ -805,19 +824,15 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 }
                 const int nxt = __ldg(pl.b_item + (r + 1) * NSUB + sub);    // the table ends with a null round
                 if (r < b_rpm) {
-                    reaction<GS, true, MODE>(tb, pl, io, out, aSP, aRX, aRAW, aSC, p, valid, true, q0, q1, q2, q3, T, logT, iT);
+                    reaction<GS, true, MODE, WSG>(mem, tb, pl, io, out, aSP, aRX, aRAW, aSC, p, valid, true, q0, q1, q2, q3, T, logT, iT);
                 } else {
                     const bool has3 = ((q2.z & 0xFFFFu) != nsp_f) || (((unsigned)q2.w >> 16) != nsp_f);
                     const bool three = __any_sync(0xffffffffu, has3);
                     // rounds holding a PLOG / Chebyshev reaction take the build of the routine that knows them
-#ifdef PJ_NO_SPECIAL
-                    if (false)
-#else
                     if (__any_sync(0xffffffffu, (q2.x & (F_PLOG | F_CHEB)) != 0))
-#endif
-                        reaction_plain<GS, MODE, true>(tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
+                        reaction_plain<GS, MODE, true, WSG>(mem, tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
                     else
-                        reaction_plain<GS, MODE, false>(tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
+                        reaction_plain<GS, MODE, false, WSG>(mem, tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
                 }
                 item = nxt;
             }
@@ -829,7 +844,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         // ------------------------------------------------------------ phase C: species sums
         if (!(io.dbg_skip & 4)) {
             const int i0 = __ldg(pl.c_off + warp), i1 = __ldg(pl.c_off + warp + 1);
-            const V mwr = lds<Q_MWR * RB>(aSC);
+            const V mwr = LDS(Q_MWR * RB, aSC);
             V pH1 = zero, pHA = zero, pHB = zero, pHT = zero, pSCP = zero;
             // round header {first unit, #(+1) units, #(-1) units}; unit 0 = {species row offset or
             // NONE, 1 if this sub-group stores}; pl.coop sub-groups share one species
@@ -842,19 +857,23 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 V aN = zero, aT = zero, a1 = zero, a2 = zero;
                 auto unit = [&](uint2 c, double sg) {
                     const unsigned x = aRX + c.x, y = aRX + c.y;
-                    aN = vfma(sg, vadd(lds<RX_NET * RB>(x), lds<RX_NET * RB>(y)), aN);
+                    aN = vfma(sg, vadd(LDS(RX_NET * RB, x), LDS(RX_NET * RB, y)), aN);
                     if (MODE != M_JAC) return;                 // only the net rates are summed
-                    aT = vfma(sg, vadd(lds<RX_TT * RB>(x), lds<RX_TT * RB>(y)), aT);
-                    a1 = vfma(sg, vadd(lds<RX_X1 * RB>(x), lds<RX_X1 * RB>(y)), a1);
-                    a2 = vfma(sg, vadd(lds<RX_X2 * RB>(x), lds<RX_X2 * RB>(y)), a2);
+                    aT = vfma(sg, vadd(LDS(RX_TT * RB, x), LDS(RX_TT * RB, y)), aT);
+                    a1 = vfma(sg, vadd(LDS(RX_X1 * RB, x), LDS(RX_X1 * RB, y)), a1);
+                    a2 = vfma(sg, vadd(LDS(RX_X2 * RB, x), LDS(RX_X2 * RB, y)), a2);
                 };
                 int i = 0;
-                for (; i + 2 <= n; i += 2) {                   // two units in flight
-                    const uint2 c = __ldg(cp + (i + 1) * NSUB), d = __ldg(cp + (i + 2) * NSUB);
+                // two units per iteration, the next two requested before these are summed (the
+                // stream is padded: reading past the round is harmless)
+                uint2 c = __ldg(cp + NSUB), d = __ldg(cp + 2 * NSUB);
+                for (; i + 2 <= n; i += 2) {
+                    const uint2 c2 = __ldg(cp + (i + 3) * NSUB), d2 = __ldg(cp + (i + 4) * NSUB);
                     unit(c, i < np_ ? 1.0 : -1.0);
                     unit(d, i + 1 < np_ ? 1.0 : -1.0);
+                    c = c2; d = d2;
                 }
-                if (i < n) unit(__ldg(cp + (i + 1) * NSUB), i < np_ ? 1.0 : -1.0);
+                if (i < n) unit(c, i < np_ ? 1.0 : -1.0);
                 for (int o = NPR; o < NPR * pl.coop; o <<= 1) {
                     aN = V{aN.x + __shfl_xor_sync(0xffffffffu, aN.x, o), aN.y + __shfl_xor_sync(0xffffffffu, aN.y, o)};
                     if (MODE != M_JAC) continue;
@@ -866,8 +885,8 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                     // dydt / rates: omega_k, dY_k/dt = omega_k W_k / rho, share of sum_k h_k W_k omega_k
                     const int k = hd.x / SPB;
                     const double wk = __ldg(tb.sp_w + k);
-                    pH1 = vfma(lds<O_HW * RB>((aSP + hd.x) ^ RB), aN, pH1);
-                    const V ri = lds<Q_RHOINV * RB>(aSC);
+                    pH1 = vfma(LDS(O_HW * RB, (aSP + hd.x) ^ RB), aN, pH1);
+                    const V ri = LDS(Q_RHOINV * RB, aSC);
                     const V dyk = vmul(wk, vmul(aN, ri));
                     if (MODE == M_RATES) {
                         if (io.sr) put2(io.sr, io, nsp, out, k, aN);
@@ -883,15 +902,15 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                     const V comp = vmul(aN, mwr);
                     a1 = vadd(a1, comp);
                     a2 = vsub(a2, comp);
-                    const V hW = lds<O_HW * RB>(o), cp_ = lds<O_CP * RB>(o);
+                    const V hW = LDS(O_HW * RB, o), cp_ = LDS(O_CP * RB, o);
                     pH1 = vfma(hW, aN, pH1);
                     pHA = vfma(hW, a1, pHA);
                     pHB = vfma(hW, a2, pHB);
                     pHT = vfma(hW, aT, pHT);
                     pSCP = vfma(vmul(wk, cp_), aN, pSCP);
-                    sts<E_WA * RB>(a, vmul(wk, a1));
-                    sts<O_WB * RB>(o, vmul(wk, a2));
-                    sts<E_WT * RB>(a, vmul(wk, aT));
+                    STS(E_WA * RB, a, vmul(wk, a1));
+                    STS(O_WB * RB, o, vmul(wk, a2));
+                    STS(E_WT * RB, a, vmul(wk, aT));
                 }
             }
             // the warp's share of the energy-equation dot products
@@ -899,8 +918,8 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             pHT = sub_sum<GS>(pHT); pSCP = sub_sum<GS>(pSCP);
             if (sub == 0) {
                 const unsigned a = aPA + warp * NPART * RB;
-                sts<D_H1 * RB>(a, pH1); sts<D_HA * RB>(a, pHA); sts<D_HB * RB>(a, pHB);
-                sts<D_HT * RB>(a, pHT); sts<D_SCP * RB>(a, pSCP);
+                STS(D_H1 * RB, a, pH1); STS(D_HA * RB, a, pHA); STS(D_HB * RB, a, pHB);
+                STS(D_HT * RB, a, pHT); STS(D_SCP * RB, a, pSCP);
             }
         }
         __syncthreads();
@@ -911,13 +930,13 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             if (warp == 0) {
                 V H1 = zero, cpavg = zero;
                 for (int w = sub; w < nw; w += NSUB) {
-                    H1 = vadd(H1, lds<D_H1 * RB>(aPA + w * NPART * RB));
-                    cpavg = vadd(cpavg, lds<D_CPAVG * RB>(aPA + w * NPART * RB));
+                    H1 = vadd(H1, LDS(D_H1 * RB, aPA + w * NPART * RB));
+                    cpavg = vadd(cpavg, LDS(D_CPAVG * RB, aPA + w * NPART * RB));
                 }
                 H1 = sub_sum<GS>(H1);
                 cpavg = sub_sum<GS>(cpavg);
                 if (sub == 0 && io.dy) {
-                    const V rho = lds<Q_RHO * RB>(aSC);
+                    const V rho = LDS(Q_RHO * RB, aSC);
                     const V d0{-1.0 / (rho.x * cpavg.x) * H1.x, -1.0 / (rho.y * cpavg.y) * H1.y};
                     if (MODE == M_RATES) put2(io.dy, io, nsp, out, 0, d0);
                     else {
@@ -937,21 +956,21 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             // replaces warp 0's own partial
             for (int q = sub; q < NPART; q += NSUB) {
                 V a = zero;
-                for (int w = 0; w < nw; ++w) a = vadd(a, lds<0>(aPA + (w * NPART + q) * RB));
-                sts<0>(aPA + q * RB, a);
+                for (int w = 0; w < nw; ++w) a = vadd(a, LDS(0, aPA + (w * NPART + q) * RB));
+                STS(0, aPA + q * RB, a);
             }
             __syncwarp();
             if (sub == 0) {
-                const V H1 = lds<D_H1 * RB>(aPA), HA = lds<D_HA * RB>(aPA), HB = lds<D_HB * RB>(aPA);
-                const V HT = lds<D_HT * RB>(aPA), SCP = lds<D_SCP * RB>(aPA);
-                const V cpavg = lds<D_CPAVG * RB>(aPA), wdcp = lds<D_WDCP * RB>(aPA);
-                const V rho = lds<Q_RHO * RB>(aSC), cpl = lds<O_CP * RB>(sp_even<GS>(aSP, (unsigned)last) ^ RB);
+                const V H1 = LDS(D_H1 * RB, aPA), HA = LDS(D_HA * RB, aPA), HB = LDS(D_HB * RB, aPA);
+                const V HT = LDS(D_HT * RB, aPA), SCP = LDS(D_SCP * RB, aPA);
+                const V cpavg = LDS(D_CPAVG * RB, aPA), wdcp = LDS(D_WDCP * RB, aPA);
+                const V rho = LDS(Q_RHO * RB, aSC), cpl = LDS(O_CP * RB, sp_even<GS>(aSP, (unsigned)last) ^ RB);
                 const V nwt{-1.0 / cpavg.x, -1.0 / cpavg.y};
-                sts<S_NWT * RB>(aSD, nwt);
-                sts<S_A0 * RB>(aSD, vmul(nwt, HA));
-                sts<S_B0 * RB>(aSD, vmul(nwt, HB));
-                sts<S_XT * RB>(aSD, V{H1.x / (rho.x * cpavg.x * cpavg.x), H1.y / (rho.y * cpavg.y * cpavg.y)});
-                sts<S_CPL * RB>(aSD, cpl);
+                STS(S_NWT * RB, aSD, nwt);
+                STS(S_A0 * RB, aSD, vmul(nwt, HA));
+                STS(S_B0 * RB, aSD, vmul(nwt, HB));
+                STS(S_XT * RB, aSD, V{H1.x / (rho.x * cpavg.x * cpavg.x), H1.y / (rho.y * cpavg.y * cpavg.y)});
+                STS(S_CPL * RB, aSD, cpl);
                 // jac[0] (cj:1853-1905)
                 store(0u, V{-(-wdcp.x / cpavg.x * H1.x + SCP.x + HT.x * rho.x) / (rho.x * cpavg.x),
                             -(-wdcp.y / cpavg.y * H1.y + SCP.y + HT.y * rho.y) / (rho.y * cpavg.y)}, true);
@@ -969,31 +988,35 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             const int st0 = __ldg(pl.s_off + warp), st1 = __ldg(pl.s_off + warp + 1);
             const uint4* sp = pl.s_str + (long long)st0 * 2 * NSUB + sub;
             const uint2* ov = pl.o_str + (long long)__ldg(pl.o_off + warp) * NSUB + sub;
+            uint2 ob0 = __ldg(ov), ob1 = __ldg(ov + NSUB), ob2 = __ldg(ov + 2 * NSUB), ob3 = __ldg(ov + 3 * NSUB);
             // one step: the bundle (A, B) is consumed while `nA`, `nB` of a later step are fetched
             auto step = [&](const uint4& A, const uint4& B) {
                 const unsigned L = A.x >> 22, e = A.x & NULL_E;
                 const unsigned x = aSP + (A.y & 0xFFFFFu);
-                const V cf = lds<0>(aCF + (A.y >> 20) * 16);
+                const V cf = LDS(0, aCF + (A.y >> 20) * 16);
                 // signed entries: byte offset of a raw row | 1 for weight -1; two entries per unit
                 auto sgn = [](unsigned c) { return __hiloint2double((int)(0x3FF00000u | (c << 31)), 0); };
-                V p = vmul(sgn(B.x), lds<0>(aRAW + (B.x & ~1u))), m = vmul(sgn(B.y), lds<0>(aRAW + (B.y & ~1u)));
-                V v = vfma(cf.y, lds<0>(x ^ RB), vmul(cf.x, lds<0>(x)));     // W_k a_k at x, W_k b_k at x ^ RB
+                V p = vmul(sgn(B.x), LDS(0, aRAW + (B.x & ~1u))), m = vmul(sgn(B.y), LDS(0, aRAW + (B.y & ~1u)));
+                V v = vfma(cf.y, LDS(0, x ^ RB), vmul(cf.x, LDS(0, x)));     // W_k a_k at x, W_k b_k at x ^ RB
                 if (L > 1) {
-                    p = vfma(sgn(B.z), lds<0>(aRAW + (B.z & ~1u)), p);
-                    m = vfma(sgn(B.w), lds<0>(aRAW + (B.w & ~1u)), m);
+                    p = vfma(sgn(B.z), LDS(0, aRAW + (B.z & ~1u)), p);
+                    m = vfma(sgn(B.w), LDS(0, aRAW + (B.w & ~1u)), m);
                     // units 3..L come from the overflow stream in batches of four (padded)
 #pragma unroll 1
                     for (unsigned i = 2; i < L; i += 4) {
-                        const uint2 c0 = __ldg(ov), c1 = __ldg(ov + NSUB), c2 = __ldg(ov + 2 * NSUB), c3 = __ldg(ov + 3 * NSUB);
+                        // the batch was requested when the previous one was taken (the stream is
+                        // consumed in order and padded at its end)
+                        const uint2 c0 = ob0, c1 = ob1, c2 = ob2, c3 = ob3;
                         ov += 4 * NSUB;
-                        p = vfma(sgn(c0.x), lds<0>(aRAW + (c0.x & ~1u)), p);
-                        m = vfma(sgn(c0.y), lds<0>(aRAW + (c0.y & ~1u)), m);
-                        p = vfma(sgn(c1.x), lds<0>(aRAW + (c1.x & ~1u)), p);
-                        m = vfma(sgn(c1.y), lds<0>(aRAW + (c1.y & ~1u)), m);
-                        p = vfma(sgn(c2.x), lds<0>(aRAW + (c2.x & ~1u)), p);
-                        m = vfma(sgn(c2.y), lds<0>(aRAW + (c2.y & ~1u)), m);
-                        p = vfma(sgn(c3.x), lds<0>(aRAW + (c3.x & ~1u)), p);
-                        m = vfma(sgn(c3.y), lds<0>(aRAW + (c3.y & ~1u)), m);
+                        ob0 = __ldg(ov); ob1 = __ldg(ov + NSUB); ob2 = __ldg(ov + 2 * NSUB); ob3 = __ldg(ov + 3 * NSUB);
+                        p = vfma(sgn(c0.x), LDS(0, aRAW + (c0.x & ~1u)), p);
+                        m = vfma(sgn(c0.y), LDS(0, aRAW + (c0.y & ~1u)), m);
+                        p = vfma(sgn(c1.x), LDS(0, aRAW + (c1.x & ~1u)), p);
+                        m = vfma(sgn(c1.y), LDS(0, aRAW + (c1.y & ~1u)), m);
+                        p = vfma(sgn(c2.x), LDS(0, aRAW + (c2.x & ~1u)), p);
+                        m = vfma(sgn(c2.y), LDS(0, aRAW + (c2.y & ~1u)), m);
+                        p = vfma(sgn(c3.x), LDS(0, aRAW + (c3.x & ~1u)), p);
+                        m = vfma(sgn(c3.y), LDS(0, aRAW + (c3.y & ~1u)), m);
                     }
                 }
                 v = vfma(__hiloint2double((int)A.w, (int)A.z), vadd(p, m), v);
@@ -1024,8 +1047,8 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 const uint2 hd = __ldg(dp);                            // {even-slot base or NONE, element of column 0}
                 const bool on = hd.x != 0xFFFFFFFFu;
                 const unsigned x = aSP + (on ? hd.x : 0u);
-                const V wa = lds<E_WA * RB>(x), wb = lds<O_WB * RB>(x ^ RB);
-                store(hd.y, lds<E_WT * RB>(x), on && hd.y != NULL_E);  // temperature column: W_k * T-term
+                const V wa = LDS(E_WA * RB, x), wb = LDS(O_WB * RB, x ^ RB);
+                store(hd.y, LDS(E_WT * RB, x), on && hd.y != NULL_E);  // temperature column: W_k * T-term
                 // units are fetched LA batches of four ahead (the tables come from L2: with all of
                 // shared memory in use there is no L1 to speak of)
                 constexpr int LA = 1;
@@ -1042,7 +1065,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                     for (int j = 0; j < 4; ++j) nx[4 * (LA - 1) + j] = __ldg(dp + (1 + 4 * LA + c + j) * NSUB);
                     V cf[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) cf[j] = lds<0>(aCF + r[j].y * 16);
+                    for (int j = 0; j < 4; ++j) cf[j] = LDS(0, aCF + r[j].y * 16);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) store(r[j].x, vfma(cf[j].y, wb, vmul(cf[j].x, wa)), r[j].x != NULL_E);
                 }
@@ -1056,8 +1079,8 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             if (i0 < i1) {
                 int2 ti = __ldg(pl.t_item + i0);
                 if (warp != 0) asm volatile("bar.sync 1, %0;" ::"r"(pl.t_sync) : "memory");
-                const V nwt = lds<S_NWT * RB>(aSD), A0 = lds<S_A0 * RB>(aSD), B0 = lds<S_B0 * RB>(aSD);
-                const V XT = lds<S_XT * RB>(aSD), cpl = lds<S_CPL * RB>(aSD);
+                const V nwt = LDS(S_NWT * RB, aSD), A0 = LDS(S_A0 * RB, aSD), B0 = LDS(S_B0 * RB, aSD);
+                const V XT = LDS(S_XT * RB, aSD), cpl = LDS(S_CPL * RB, aSD);
                 for (int it = i0; it < i1; ++it) {
                     const uint2* up = pl.t_str + (long long)ti.x * NSUB + sub;
                     const int n = ti.y;
@@ -1071,17 +1094,17 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                         uint2 r[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) { r[j] = nx[j]; nx[j] = __ldg(up + (5 + c + j) * NSUB); }
-                        acc0 = vfma(lds<RX_DH * RB>(aRX + r[0].y), lds<0>(aRAW + r[0].x), acc0);
-                        acc1 = vfma(lds<RX_DH * RB>(aRX + r[1].y), lds<0>(aRAW + r[1].x), acc1);
-                        acc0 = vfma(lds<RX_DH * RB>(aRX + r[2].y), lds<0>(aRAW + r[2].x), acc0);
-                        acc1 = vfma(lds<RX_DH * RB>(aRX + r[3].y), lds<0>(aRAW + r[3].x), acc1);
+                        acc0 = vfma(LDS(RX_DH * RB, aRX + r[0].y), LDS(0, aRAW + r[0].x), acc0);
+                        acc1 = vfma(LDS(RX_DH * RB, aRX + r[1].y), LDS(0, aRAW + r[1].x), acc1);
+                        acc0 = vfma(LDS(RX_DH * RB, aRX + r[2].y), LDS(0, aRAW + r[2].x), acc0);
+                        acc1 = vfma(LDS(RX_DH * RB, aRX + r[3].y), LDS(0, aRAW + r[3].x), acc1);
                     }
                     V E0 = vadd(acc0, acc1);
                     for (int o = NPR; o < NPR * pl.tcoop; o <<= 1)
                         E0 = V{E0.x + __shfl_xor_sync(0xffffffffu, E0.x, o), E0.y + __shfl_xor_sync(0xffffffffu, E0.y, o)};
                     const unsigned col = hd.x & 0xFFFFu;
-                    const V cf = lds<0>(aCF + col * 16);
-                    const V cpj = lds<0>(aSP + hd.y);
+                    const V cf = LDS(0, aCF + col * 16);
+                    const V cpj = LDS(0, aSP + hd.y);
                     V v = vmul(cf.x, vfma(nwt, E0, A0));
                     v = vfma(cf.y, B0, v);
                     v = vfma(XT, vsub(cpj, cpl), v);

@@ -30,6 +30,9 @@ struct pyjac_mech {
     int user_bpsm = 0;
     int bpsm[3] = {0, 0, 0};         // blocks per SM per mode (0 = not configured yet)
     long long launches = 0;
+    char* ws = nullptr;              // per-block working sets of a plan with wsg = 1
+    size_t ws_bytes = 0;
+    cudaEvent_t ws_ev = nullptr;     // orders the launches that share `ws` across streams
     // staging for the host-pointer API
     cudaStream_t stream[2] = {nullptr, nullptr};
     double* h_pin[2] = {nullptr, nullptr};
@@ -74,10 +77,28 @@ const void* kernel_t(int gs)
     }
 }
 
-// k_eval for a plan (states per block, block size <= 512) and a mode.  Blocks of up to 384
-// threads get the 168-register build, larger ones the 128-register build.
-const void* kernel_for(int gs, int mode, int nt)
+template <int MODE>
+const void* kernel_g(int gs)
 {
+    switch (gs) {
+#ifndef PJ_DEV_GS8_ONLY
+    case 2: return (const void*)pj5::k_eval<2, 384, MODE, true>;
+#endif
+    case 8: return (const void*)pj5::k_eval<8, 384, MODE, true>;
+    default: return nullptr;
+    }
+}
+
+// k_eval for a plan (states per block, block size <= 512) and a mode.  Blocks of up to 384
+// threads get the 168-register build, larger ones the 128-register build.  Plans whose working
+// set lives in global memory (wsg) exist for 2 and 8 states per block and up to 384 threads.
+const void* kernel_for(int gs, int mode, int nt, int wsg = 0)
+{
+    if (wsg) {
+        if (nt > 384) return nullptr;
+        return mode == pj::M_DYDT ? kernel_g<pj::M_DYDT>(gs) : mode == pj::M_RATES ? kernel_g<pj::M_RATES>(gs)
+                                                                                  : kernel_g<pj::M_JAC>(gs);
+    }
     const bool small = nt <= 384;
     if (mode == pj::M_DYDT) return small ? kernel_t<384, pj::M_DYDT>(gs) : kernel_t<512, pj::M_DYDT>(gs);
     if (mode == pj::M_RATES) return small ? kernel_t<384, pj::M_RATES>(gs) : kernel_t<512, pj::M_RATES>(gs);
@@ -85,19 +106,21 @@ const void* kernel_for(int gs, int mode, int nt)
 }
 
 // One launch of k_eval; the plan in the table blob fixes states per block and block size.
-int launch(pyjac_mech* m, int mode, const IO& io, cudaStream_t st)
+int launch(pyjac_mech* m, int mode, const IO& io_in, cudaStream_t st)
 {
-    if (io.n <= 0) return PYJAC_OK;
+    if (io_in.n <= 0) return PYJAC_OK;
+    IO io = io_in;
     CU(cudaSetDevice(m->device));
     const pj5::Plan& pl = m->plan;
-    const void* fn = kernel_for(pl.gs, mode, pl.nt);
+    const void* fn = kernel_for(pl.gs, mode, pl.nt, pl.wsg);
     if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable plan");
-    const size_t bytes = (size_t)pl.total * 8;
+    const size_t bytes = pl.wsg ? 0 : (size_t)pl.total * 8;
     if (!m->bpsm[mode]) {
         if (bytes > (size_t)m->smem_optin)
             return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
-        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (!pl.wsg) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                pl.wsg ? cudaSharedmemCarveoutMaxL1 : cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.nt, bytes));
         if (occ < 1) return fail(PYJAC_ETOOBIG, "kernel cannot be resident with this plan");
@@ -106,8 +129,22 @@ int launch(pyjac_mech* m, int mode, const IO& io, cudaStream_t st)
     }
     const long long groups = ((long long)io.n + pl.gs - 1) / pl.gs;
     const int grid = (int)std::min<long long>(groups, (long long)m->sm_count * m->bpsm[mode]);
+    if (pl.wsg) {
+        // one working set per resident block, in global memory (L1 / L2 hold what is hot); the
+        // launches of one handle share it, so an event orders them across streams
+        const size_t need = (size_t)m->sm_count * m->bpsm[mode] * (size_t)pl.total * 8;
+        if (need > m->ws_bytes) {
+            if (m->ws) { CU(cudaDeviceSynchronize()); cudaFree(m->ws); m->ws = nullptr; m->ws_bytes = 0; }
+            CU(cudaMalloc(&m->ws, need));
+            m->ws_bytes = need;
+        }
+        io.ws = m->ws;
+        if (!m->ws_ev) CU(cudaEventCreateWithFlags(&m->ws_ev, cudaEventDisableTiming));
+        else CU(cudaStreamWaitEvent(st, m->ws_ev, 0));
+    }
     void* args[3] = {(void*)&m->tb, (void*)&m->plan, (void*)&io};
     CU(cudaLaunchKernel(fn, dim3(grid), dim3(pl.nt), args, bytes, st));
+    if (pl.wsg) CU(cudaEventRecord(m->ws_ev, st));
     ++m->launches;
     return PYJAC_OK;
 }
@@ -208,7 +245,8 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
             pj5::Plan& pl = m->plan;
             int* o = &pl.gs;
             for (int i = 0; i < 14; ++i) o[i] = c5[i];
-            if (!kernel_for(pl.gs, pj::M_JAC, pl.nt) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
+            pl.wsg = pe->count > 14 ? c5[14] : 0;
+            if (!kernel_for(pl.gs, pj::M_JAC, pl.nt, pl.wsg) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
                 rc = fail(PYJAC_EINVAL, "bad plan configuration");
         }
     }
@@ -245,6 +283,8 @@ void pyjac_mech_destroy(pyjac_mech* m)
     release_staging(m);
     for (int i = 0; i < 2; ++i) if (m->stream[i]) cudaStreamDestroy(m->stream[i]);
     for (void* p : m->dev_allocs) cudaFree(p);
+    if (m->ws) cudaFree(m->ws);
+    if (m->ws_ev) cudaEventDestroy(m->ws_ev);
     delete m;
 }
 

@@ -30,9 +30,11 @@ def _ptr(t) -> int:
 
 
 class Evaluator:
-    def __init__(self, mech: Mechanism, device: Optional[int] = None, gs: int = 0, threads: int = 0):
+    def __init__(self, mech: Mechanism, device: Optional[int] = None, gs: int = 0, threads: int = 0,
+                 ws_global: Optional[bool] = None):
         """gs / threads: states per thread block and block size of the Jacobian kernel's plan
-        (pyjac_b200/plan.py); 0 = automatic."""
+        (pyjac_b200/plan.py); 0 = automatic.  ws_global: working set of a block in global memory
+        instead of shared memory (None = only for mechanisms too large for shared memory)."""
         import torch
         self._torch = torch
         self.mech = mech
@@ -40,7 +42,7 @@ class Evaluator:
         if self.lib.pyjac_device_count() <= 0:
             raise _lib.PyjacError('no CUDA device: pyjac_b200 has no CPU fallback')
         self.device = torch.cuda.current_device() if device is None else int(device)
-        self.tables = _tables.build(mech, gs=gs, threads=threads)
+        self.tables = _tables.build(mech, gs=gs, threads=threads, ws_global=ws_global)
         self.plan_gs, self.plan_threads = (int(v) for v in self.tables['p5_cfg'][:2])
         data = _blob.pack(self.tables)
         h = ctypes.c_void_p()

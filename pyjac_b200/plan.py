@@ -75,10 +75,15 @@ def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:
 
 
 def choose_gs(nsp: int, nr: int, nraw: int, nw: int) -> int:
+    """Largest number of states per block whose working set fits in shared memory; 0 if not even
+    two states fit (the working set then goes to global memory, see WSG_GS)."""
     for gs in GS_CHOICES:
         if layout(nsp, nr, nraw, gs, nw)['total'] * 8 <= SMEM_LIMIT:
             return gs
     return 0
+
+
+WSG_GS = 8                   # states per block when the working set lives in global memory
 
 
 def _lpt(costs: Sequence[float], nw: int, init: Sequence[float] = None) -> List[List[int]]:
@@ -126,7 +131,7 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
                has3: List[bool], n_eff: List[int], red: List[List[Tuple[int, float]]],
                contrib: Dict[Tuple[int, int], List[Tuple[int, float]]],
                tcontrib: Dict[int, List[Tuple[int, int]]], sp_w: Sequence[float],
-               sp_iw: Sequence[float], sp_mwf: Sequence[float], gs: int, nt: int
+               sp_iw: Sequence[float], sp_mwf: Sequence[float], gs: int, nt: int, wsg: int = 0
                ) -> Dict[str, np.ndarray]:
     """kinds[p] in {'plain','plog','thd','lind','troe','sri'} per kernel-order reaction p;
     contrib[(k, j)] = [(raw row, nu)], tcontrib[j] = [(raw row, reaction)]."""
@@ -169,7 +174,7 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
         b_off.append(len(b_item) // nsub)
     P['p5_b_off'] = i32(b_off)
     P['p5_b_npm'] = i32(b_npm)
-    P['p5_b_item'] = i32(b_item + [-1] * nsub)               # ends with a null round (look-ahead)
+    P['p5_b_item'] = i32(b_item + [-1] * (2 * nsub))         # ends with two null rounds (look-ahead)
 
     # byte offsets inside the shared-memory regions (a row is GS doubles)
     RB = gs * 8
@@ -201,25 +206,32 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
 
     # ---------------------------------------------------------------- phase C
     # Per species k: sum over its reactions of nu_ki * (net, tT, X1, X2), nu split into +1 and -1
-    # entries (byte offsets of reaction rows).  D sub-groups share one species (D = the largest
-    # power of two that still lets every species be summed in one round of the block); a warp
-    # round handles NSUB / D species of similar list length.  Round r of a warp: header unit
+    # entries (byte offsets of reaction rows).  D sub-groups share one species; a warp round
+    # handles NSUB / D species of similar list length.  Round r of a warp: header unit
     # {species row offset or NONE32, 1 if this sub-group stores the result}, then nP units of
     # two +1 entries and nM units of two -1 entries per sub-group, all padded with the zero row.
+    c_lists = [expand(red[k]) for k in range(nsp)]
+
+    def c_schedule(coop):
+        """Rounds of NSUB / coop species of similar list length, dealt to the warps longest first;
+        returns (rounds per warp, largest per-warp cost)."""
+        def n_units(n_entries):
+            return (-(-n_entries // coop) + 1) // 2
+        per_round = nsub // coop
+        order_c = sorted(range(nsp), key=lambda k: (-(n_units(len(c_lists[k][0])) + n_units(len(c_lists[k][1]))), k))
+        chunks = [order_c[c0:c0 + per_round] for c0 in range(0, nsp, per_round)]
+        cost = [COST_C_ITEM + COST_C_IT * (max(n_units(len(c_lists[k][0])) for k in ch) +
+                                           max(n_units(len(c_lists[k][1])) for k in ch)) for ch in chunks]
+        bins, load = _lpt(cost, nw)
+        return [[chunks[ix] for ix in sorted(b)] for b in bins], max(load), n_units
+
+    # D sub-groups share one species: the largest power of two that still lets every species be
+    # summed in one round of the block (splitting further to even out the warps measured slower:
+    # the phase is bound by shared-memory throughput, not by its longest warp)
     coop = nsub
     while coop > 1 and nw * (nsub // coop) < nsp:
         coop //= 2
-    per_round = nsub // coop
-    c_lists = [expand(red[k]) for k in range(nsp)]
-
-    def n_units(n_entries):
-        return (-(-n_entries // coop) + 1) // 2
-
-    order_c = sorted(range(nsp), key=lambda k: (-(n_units(len(c_lists[k][0])) + n_units(len(c_lists[k][1]))), k))
-    chunks = [order_c[c0:c0 + per_round] for c0 in range(0, nsp, per_round)]
-    per_warp: List[List[List[int]]] = [[] for _ in range(nw)]
-    for ci, ch in enumerate(chunks):
-        per_warp[ci % nw].append(ch)
+    per_warp, _, n_units = c_schedule(coop)
     c_off, c_item, c_str = [0], [], []
     for w in range(nw):
         for ch in per_warp[w]:
@@ -417,6 +429,6 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
     # dot products) and every other warp that owns such steps (waits)
     waiters = sum(1 for w in range(1, nw) if t_nst[w])
     t_sync = 32 * (waiters + 1) if waiters else 0
-    P['p5_cfg'] = i32([gs, nt, nw, nsub, L['SP'], L['RX'], L['RAW'], L['SC'], L['PA'], L['total'], t_sync, coop, tcoop, L['CF']]
-                      + [0] * 2)
+    P['p5_cfg'] = i32([gs, nt, nw, nsub, L['SP'], L['RX'], L['RAW'], L['SC'], L['PA'], L['total'], t_sync, coop, tcoop, L['CF'],
+                       1 if wsg else 0, 0])
     return P

@@ -93,8 +93,10 @@ def _nasa_row(a) -> List[float]:
             a[6] - a[0], a[0] - 1.0, a[2] / 6.0, a[3] / 12.0, a[4] / 20.0, 0.0]
 
 
-def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarray]:
-    """gs / threads: states per block and block size of the Jacobian kernel's plan (0 = automatic)."""
+def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None) -> Dict[str, np.ndarray]:
+    """gs / threads: states per block and block size of the Jacobian kernel's plan (0 = automatic).
+    ws_global: True puts the per-block working set in global memory instead of shared memory;
+    None = only when not even two states fit in shared memory (n-heptane-sized mechanisms)."""
     specs, reacs = mech.specs, mech.reacs
     nsp, nr = len(specs), len(reacs)
     last = nsp - 1
@@ -452,10 +454,19 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
 
     # ---------------- schedule of the Jacobian kernel (plan.py)
     nt = threads or plan.DEFAULT_THREADS
+    if ws_global and nt > 384:
+        raise UnsupportedMechanism('plans with the working set in global memory take at most 384 threads')
     if not gs:
-        gs = plan.choose_gs(nsp, nr, nraw, nt // 32)
+        gs = plan.WSG_GS if ws_global else plan.choose_gs(nsp, nr, nraw, nt // 32)
         if not gs:
-            raise UnsupportedMechanism('working set of one state pair exceeds shared memory')
+            # not even two states fit in shared memory: the working set goes to global memory
+            if ws_global is not None or nt > 384:
+                raise UnsupportedMechanism('working set of one state pair exceeds shared memory')
+            gs, ws_global = plan.WSG_GS, True
+    if ws_global is None and plan.layout(nsp, nr, nraw, gs, nt // 32)['total'] * 8 > plan.SMEM_LIMIT:
+        ws_global = True               # a requested gs that does not fit in shared memory
+    if ws_global and gs not in (2, 8):
+        raise UnsupportedMechanism('plans with the working set in global memory hold 2 or 8 states per block')
     kinds, n_eff = [], []
     for p, i in enumerate(order):
         rx = reacs[i]
@@ -465,7 +476,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0) -> Dict[str, np.ndarra
     T.update(plan.build_plan(nsp, nr, nraw, first_pm, kinds, [bool(reacs[i].rev) for i in order],
                              [bool(slots[p, 2] != nsp or slots[p, 5] != nsp) for p in range(nr)],
                              n_eff, red, {kj: v for kj, v in contrib.items() if kj[0] != last},
-                             tcontrib, T['sp_w'], T['sp_iw'], T['sp_mwf'], gs, nt))
+                             tcontrib, T['sp_w'], T['sp_iw'], T['sp_mwf'], gs, nt, 1 if ws_global else 0))
     # the 64-byte reaction record of the Jacobian kernel: lnA, b, Ta, sum(nu) ln(PA/RU); flags;
     # six species slots and eight raw destinations packed two per int
     rec5 = np.zeros((nr, 16), dtype=np.int32)

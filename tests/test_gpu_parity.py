@@ -137,6 +137,53 @@ def test_plog_against_oracle_across_pressures(torch, golden_dir):
     ev.close()
 
 
+@pytest.mark.parametrize('mech_file,npz,gs', [('gri30_syn.inp', 'gri30_syn.npz', 8), ('torture.inp', 'torture_pasr.npz', 8),
+                                              ('cheb.inp', 'cheb_syn.npz', 2), ('usc2_syn.inp', 'usc2_syn.npz', 8)])
+def test_working_set_in_global_memory(torch, golden_dir, mech_file, npz, gs):
+    """The plan variant for mechanisms too large for shared memory (per-block working set in global
+    memory), forced on mechanisms that have golden vectors."""
+    mech, ev = _evaluator_with(golden_dir, mech_file, gs=gs, ws_global=True)
+    assert int(ev.tables['p5_cfg'][14]) == 1
+    g = dict(np.load(os.path.join(golden_dir, npz)))
+    P = torch.tensor(g['P'], device='cuda')
+    y = torch.tensor(g['y'], device='cuda').t().contiguous()
+    outs = ev.rates(P, y, y_layout='state_fastest', want_dy=True)
+    jac = ev.eval_jacob(P, y, y_layout='state_fastest', jac_layout='state_fastest')
+    dy2 = ev.dydt(P, y, y_layout='state_fastest')
+    new = dict(zip(KEYS + ['dydt'], [o.cpu().numpy().T for o in outs]))
+    gates.check_rates(mech, g['P'], g['y'], new, g, mech_file)
+    gates.check_dydt(mech, g['y'], dy2.cpu().numpy().T, g, mech_file + ' dydt kernel')
+    worst, frac = gates.check_jac(np.ascontiguousarray(jac.cpu().numpy().T), g['jac'], mech.NSP, mech_file, mech, g['y'])
+    assert frac > 0.97
+    # the host-pointer API runs its chunks on two streams: they share the working sets
+    jh = ev.eval_jacob_host(g['P'], g['y'])
+    gates.check_jac(jh, g['jac'], mech.NSP, mech_file + ' host api', mech, g['y'])
+    ev.close()
+
+
+def test_n_heptane_sized_mechanism_vs_oracle(torch, tmp_path):
+    """654 species / 2827 reactions (the shape of the LLNL n-heptane mechanism): the working set of
+    one state pair exceeds shared memory, so the plan puts it in global memory automatically."""
+    from oracle.oracle import Oracle
+    from pyjac_b200 import synth
+    from pyjac_b200.evaluator import Evaluator
+    path = str(tmp_path / 'nc7.inp')
+    synth.write('nc7', path)
+    mech = Mechanism.from_chemkin(path)
+    ev = Evaluator(mech)
+    assert int(ev.tables['p5_cfg'][14]) == 1 and ev.plan_gs == 8
+    P_h, y_h = synthetic_states(mech.NSP, 20, seed=13)          # a tail group of 4 states
+    ora = Oracle(mech)
+    ref = dict(zip(KEYS, ora.rates(P_h, y_h)))
+    ref['dydt'] = ora.dydt(P_h, y_h)
+    P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
+    new = dict(zip(KEYS + ['dydt'], [o.cpu().numpy() for o in ev.rates(P, y, want_dy=True)]))
+    gates.check_rates(mech, P_h, y_h, new, ref, 'nc7')
+    worst, frac = gates.check_jac(ev.eval_jacob(P, y).cpu().numpy(), ora.eval_jacob(P_h, y_h), mech.NSP, 'nc7', mech, y_h)
+    assert frac > 0.999, frac
+    ev.close()
+
+
 def test_fd_self_check(torch, golden_dir):
     """On-device finite-difference Jacobian of dydt (the reference's fd_jacob.cu comparison) against
     the analytical Jacobian: an oracle-free check.  Sixth-order central differences with CVODE-style
