@@ -183,7 +183,7 @@ __device__ __forceinline__ void reaction(const Mem<WSG>& mem, const Tables& tb, 
                                          const int4 q0, const int4 q1, const int4 q2, const int4 q3,
                                          const V T, const V logT, const V iT)
 {
-    constexpr int RB = GS * 8, SPB = SP_SLOTS * RB, RXB = RX_SLOTS * RB;
+    constexpr int RB = GS * 8, RXB = RX_SLOTS * RB;
     const int nsp = tb.nsp, last = tb.nsp - 1;
     const double lnA = __hiloint2double(q0.y, q0.x), bexp = __hiloint2double(q0.w, q0.z);
     const double Ta = __hiloint2double(q1.y, q1.x), lnKc = __hiloint2double(q1.w, q1.z);
@@ -448,7 +448,7 @@ __device__ __forceinline__ void reaction_plain(const Mem<WSG>& mem, const Tables
                                                const int4 q0, const int4 q1, const int4 q2, const int4 q3,
                                                const V T, const V logT, const V iT)
 {
-    constexpr int RB = GS * 8, SPB = SP_SLOTS * RB, RXB = RX_SLOTS * RB;
+    constexpr int RB = GS * 8, RXB = RX_SLOTS * RB;
     const double lnA = __hiloint2double(q0.y, q0.x), bexp = __hiloint2double(q0.w, q0.z);
     const double Ta = __hiloint2double(q1.y, q1.x), lnKc = __hiloint2double(q1.w, q1.z);
     const int fl = q2.x;

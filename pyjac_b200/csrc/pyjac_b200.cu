@@ -77,27 +77,34 @@ const void* kernel_t(int gs)
     }
 }
 
-template <int MODE>
+template <int MAXT, int MODE>
 const void* kernel_g(int gs)
 {
     switch (gs) {
 #ifndef PJ_DEV_GS8_ONLY
-    case 2: return (const void*)pj5::k_eval<2, 384, MODE, true>;
+    case 2: return (const void*)pj5::k_eval<2, MAXT, MODE, true>;
+    case 16: return (const void*)pj5::k_eval<16, MAXT, MODE, true>;
+    case 32: return (const void*)pj5::k_eval<32, MAXT, MODE, true>;
 #endif
-    case 8: return (const void*)pj5::k_eval<8, 384, MODE, true>;
+    case 8: return (const void*)pj5::k_eval<8, MAXT, MODE, true>;
     default: return nullptr;
     }
 }
 
 // k_eval for a plan (states per block, block size <= 512) and a mode.  Blocks of up to 384
 // threads get the 168-register build, larger ones the 128-register build.  Plans whose working
-// set lives in global memory (wsg) exist for 2 and 8 states per block and up to 384 threads.
+// set lives in global memory (wsg) exist for 2, 8, 16 and 32 states per block and up to 384 threads.
 const void* kernel_for(int gs, int mode, int nt, int wsg = 0)
 {
     if (wsg) {
+        // no shared memory in use: blocks of up to 256 threads take the 128-register build so that two
+        // of them are resident per SM (their phases interleave), larger ones the 168-register build
         if (nt > 384) return nullptr;
-        return mode == pj::M_DYDT ? kernel_g<pj::M_DYDT>(gs) : mode == pj::M_RATES ? kernel_g<pj::M_RATES>(gs)
-                                                                                  : kernel_g<pj::M_JAC>(gs);
+        if (nt <= 256)
+            return mode == pj::M_DYDT ? kernel_g<512, pj::M_DYDT>(gs) : mode == pj::M_RATES ? kernel_g<512, pj::M_RATES>(gs)
+                                                                                           : kernel_g<512, pj::M_JAC>(gs);
+        return mode == pj::M_DYDT ? kernel_g<384, pj::M_DYDT>(gs) : mode == pj::M_RATES ? kernel_g<384, pj::M_RATES>(gs)
+                                                                                       : kernel_g<384, pj::M_JAC>(gs);
     }
     const bool small = nt <= 384;
     if (mode == pj::M_DYDT) return small ? kernel_t<384, pj::M_DYDT>(gs) : kernel_t<512, pj::M_DYDT>(gs);

@@ -76,14 +76,24 @@ def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:
 
 def choose_gs(nsp: int, nr: int, nraw: int, nw: int) -> int:
     """Largest number of states per block whose working set fits in shared memory; 0 if not even
-    two states fit (the working set then goes to global memory, see WSG_GS)."""
+    two states fit."""
     for gs in GS_CHOICES:
         if layout(nsp, nr, nraw, gs, nw)['total'] * 8 <= SMEM_LIMIT:
             return gs
     return 0
 
 
-WSG_GS = 8                   # states per block when the working set lives in global memory
+SMEM_MIN_GS = 8              # below this many states per block in shared memory the plan moves
+                             # the working set to global memory instead (measured on a B200: USC-II-shaped
+                             # mechanism 5.3e6 states/s with 2 states in shared memory, 1.08e7 with 8 in global)
+
+
+def wsg_shape(nsp: int) -> Tuple[int, int]:
+    """(states per block, threads per block) of a plan whose working set lives in global memory.
+    Measured on a B200: n-heptane-sized mechanisms run best with 16 states (128-byte Jacobian
+    stores) and two or more 128-register blocks per SM, USC-II-sized ones with 8 states and one
+    384-thread block."""
+    return (16, 256) if nsp >= 256 else (8, DEFAULT_THREADS)
 
 
 def _lpt(costs: Sequence[float], nw: int, init: Sequence[float] = None) -> List[List[int]]:
@@ -175,20 +185,6 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
     P['p5_b_off'] = i32(b_off)
     P['p5_b_npm'] = i32(b_npm)
     P['p5_b_item'] = i32(b_item + [-1] * (2 * nsub))         # ends with two null rounds (look-ahead)
-
-    # byte offsets inside the shared-memory regions (a row is GS doubles)
-    RB = gs * 8
-    SPB, RXB = SP_SLOTS * RB, RX_SLOTS * RB
-    PF = 16                                    # null units after each stream (prefetch runs ahead)
-
-    def expand(lst):
-        """[(source, nu)] -> (sources with weight +1, sources with weight -1), nu an integer."""
-        plus, minus = [], []
-        for src, c in lst:
-            if not float(c).is_integer():
-                raise ValueError('non-integer coefficient %r' % c)
-            (plus if c > 0 else minus).extend([src] * int(abs(c)))
-        return plus, minus
 
     # byte offsets inside the shared-memory regions (a row is GS doubles)
     RB = gs * 8

@@ -95,8 +95,9 @@ def _nasa_row(a) -> List[float]:
 
 def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None) -> Dict[str, np.ndarray]:
     """gs / threads: states per block and block size of the Jacobian kernel's plan (0 = automatic).
-    ws_global: True puts the per-block working set in global memory instead of shared memory;
-    None = only when not even two states fit in shared memory (n-heptane-sized mechanisms)."""
+    ws_global: True puts the per-block working set in global memory instead of shared memory, False
+    forbids that; None = automatic (global memory when fewer than plan.SMEM_MIN_GS states fit in
+    shared memory: USC-II- and n-heptane-sized mechanisms)."""
     specs, reacs = mech.specs, mech.reacs
     nsp, nr = len(specs), len(reacs)
     last = nsp - 1
@@ -453,20 +454,26 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None) -> Dic
     T['rx_dst'] = rx_dst.ravel()
 
     # ---------------- schedule of the Jacobian kernel (plan.py)
+    # states per block, block size, and where the working set lives: shared memory when at least
+    # plan.SMEM_MIN_GS states fit there, else a per-block scratch area in global memory
     nt = threads or plan.DEFAULT_THREADS
+    if not gs:
+        gs_smem = 0 if ws_global else plan.choose_gs(nsp, nr, nraw, nt // 32)
+        if ws_global is False and not gs_smem:
+            raise UnsupportedMechanism('working set of one state pair exceeds shared memory')
+        if ws_global is False or (ws_global is None and gs_smem >= plan.SMEM_MIN_GS):
+            gs = gs_smem
+        else:
+            gs, nt_g = plan.wsg_shape(nsp)
+            ws_global = True
+            if not threads:
+                nt = nt_g
     if ws_global and nt > 384:
         raise UnsupportedMechanism('plans with the working set in global memory take at most 384 threads')
-    if not gs:
-        gs = plan.WSG_GS if ws_global else plan.choose_gs(nsp, nr, nraw, nt // 32)
-        if not gs:
-            # not even two states fit in shared memory: the working set goes to global memory
-            if ws_global is not None or nt > 384:
-                raise UnsupportedMechanism('working set of one state pair exceeds shared memory')
-            gs, ws_global = plan.WSG_GS, True
     if ws_global is None and plan.layout(nsp, nr, nraw, gs, nt // 32)['total'] * 8 > plan.SMEM_LIMIT:
         ws_global = True               # a requested gs that does not fit in shared memory
-    if ws_global and gs not in (2, 8):
-        raise UnsupportedMechanism('plans with the working set in global memory hold 2 or 8 states per block')
+    if ws_global and gs not in (2, 8, 16, 32):
+        raise UnsupportedMechanism('plans with the working set in global memory hold 2, 8, 16 or 32 states per block')
     kinds, n_eff = [], []
     for p, i in enumerate(order):
         rx = reacs[i]

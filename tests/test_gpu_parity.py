@@ -161,6 +161,20 @@ def test_working_set_in_global_memory(torch, golden_dir, mech_file, npz, gs):
     ev.close()
 
 
+def test_usc2_plan_choice_and_shared_memory_plan(torch, golden_dir):
+    """USC-II-shaped mechanism: the automatic plan keeps the working set in global memory (8 states
+    per block); the shared-memory plan (2 states per block) stays available and agrees."""
+    mech, ev = _evaluator(golden_dir, 'usc2_syn.inp')
+    assert int(ev.tables['p5_cfg'][14]) == 1 and ev.plan_gs == 8
+    mech, ev2 = _evaluator_with(golden_dir, 'usc2_syn.inp', ws_global=False)
+    assert int(ev2.tables['p5_cfg'][14]) == 0 and ev2.plan_gs == 2
+    g = dict(np.load(os.path.join(golden_dir, 'usc2_syn.npz')))
+    P, y = torch.tensor(g['P'], device='cuda'), torch.tensor(g['y'], device='cuda')
+    for e in (ev, ev2):
+        gates.check_jac(e.eval_jacob(P, y).cpu().numpy(), g['jac'], mech.NSP, 'usc2', mech, g['y'])
+        e.close()
+
+
 def test_n_heptane_sized_mechanism_vs_oracle(torch, tmp_path):
     """654 species / 2827 reactions (the shape of the LLNL n-heptane mechanism): the working set of
     one state pair exceeds shared memory, so the plan puts it in global memory automatically."""
@@ -171,7 +185,7 @@ def test_n_heptane_sized_mechanism_vs_oracle(torch, tmp_path):
     synth.write('nc7', path)
     mech = Mechanism.from_chemkin(path)
     ev = Evaluator(mech)
-    assert int(ev.tables['p5_cfg'][14]) == 1 and ev.plan_gs == 8
+    assert int(ev.tables['p5_cfg'][14]) == 1 and ev.plan_gs == 16
     P_h, y_h = synthetic_states(mech.NSP, 20, seed=13)          # a tail group of 4 states
     ora = Oracle(mech)
     ref = dict(zip(KEYS, ora.rates(P_h, y_h)))

@@ -25,7 +25,10 @@ def main():
     for case in a.cases.split(','):
         parts = case.split(':')
         shape, n = parts[0], int(parts[1])
-        kw = dict(gs=8, ws_global=True) if len(parts) > 2 else {}
+        # shape:n:gN[:tT] = working set in global memory, N states per block, T threads per block
+        kw = dict(gs=int(parts[2][1:]), ws_global=True) if len(parts) > 2 else {}
+        if len(parts) > 3:
+            kw['threads'] = int(parts[3][1:])
         path = '/tmp/%s.inp' % shape
         synth.write(shape, path)
         mech = Mechanism.from_chemkin(path)
