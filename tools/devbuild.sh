@@ -5,4 +5,4 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC -Xcompiler -O2 \
-  -DPJ_DEV_GS8_ONLY "$@" -I include -I pyjac_b200/csrc -o pyjac_b200/_build/dev_$name.so pyjac_b200/csrc/pyjac_b200.cu
+  ${DEVFULL:--DPJ_DEV_GS8_ONLY} "$@" -I include -I pyjac_b200/csrc -o pyjac_b200/_build/dev_$name.so pyjac_b200/csrc/pyjac_b200.cu
