@@ -38,6 +38,25 @@ if ROOT not in sys.path:
 MECH_FILE = os.path.join(ROOT, 'tests', 'golden', 'gri30_syn.inp')
 REF_NAME = 'gri30'
 WORKLOAD = 'GRI-3.0-shaped synthetic mechanism (53 sp / 325 rxn), eval_jacob, fp64'
+# --workload: BASELINE.json configs[1] (default, the one the metric is quoted on), [2], [3];
+# (mechanism shape of pyjac_b200/synth.py, name under oracle/_ref, description, states per GPU)
+WORKLOADS = {
+    'gri30': (None, 'gri30', WORKLOAD, 1 << 20),
+    'usc2': ('usc2', 'usc2', 'USC-Mech-II-shaped synthetic mechanism (111 sp / 784 rxn), eval_jacob, fp64', 1 << 17),
+    'nc7': ('nc7', 'nc7', 'n-heptane-shaped synthetic mechanism (654 sp / 2827 rxn), eval_jacob, fp64', 18944),
+}
+
+
+def select_workload(name: str):
+    """Point MECH_FILE / REF_NAME / WORKLOAD at one of WORKLOADS; returns its default batch."""
+    global MECH_FILE, REF_NAME, WORKLOAD
+    shape, REF_NAME, WORKLOAD, states = WORKLOADS[name]
+    if shape is not None:
+        import tempfile
+        from pyjac_b200 import synth
+        MECH_FILE = os.path.join(tempfile.gettempdir(), 'pyjac_b200_bench_%s_%d.inp' % (shape, os.getpid()))
+        synth.write(shape, MECH_FILE, seed=0)
+    return states
 METRIC = 'eval_jacob states/s'
 UNIT = 'states/s'
 
@@ -62,7 +81,7 @@ def ncu_traffic(nsp: int):
     """dram bytes per state from the committed ncu --set full capture (profiles/traffic.json)."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
-            return json.load(fh).get('gri30_dram_bytes_per_state')
+            return json.load(fh).get('%s_dram_bytes_per_state' % REF_NAME)
     except Exception:
         return None
 
@@ -223,6 +242,7 @@ def run_ours(args, rank, world, local_rank):
     n = args.states
     bytes_per_state = 8 * nsp * nsp + 8 * (nsp + 1)
     ev = Evaluator(mech, local_rank)
+    wsg = bool(int(ev.tables['p5_cfg'][14]))
     # every rank gets its own shard of the (n * world)-state batch: seed = rank
     P_h, y_h = load_states(nsp, n, seed=rank)
     P = torch.tensor(P_h, device=dev)
@@ -314,12 +334,15 @@ def run_ours(args, rank, world, local_rank):
                        'layout': 'state-fastest (struct-of-arrays) in and out: y[NSP][n], jac[NSP*NSP][n] -- the '
                                  "reference's GPU layout; e2e: one row per state in, one column-major "
                                  'NSPxNSP Jacobian per state out (the scalar API layout)',
-                       'plan': 'gs=%d states per block, %d threads' % (ev.plan_gs, ev.plan_threads),
+                       'plan': 'gs=%d states per block, %d threads, working set in %s memory'
+                               % (ev.plan_gs, ev.plan_threads, 'global' if wsg else 'shared'),
                        'parallelism': 'state batch sharded over %d GPU(s), no collective' % world},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': None if traffic is None else traffic * n,
                          'peak_source': peak_src, 'bytes_per_state': bytes_per_state,
-                         'kernel': 'pj5::k_eval<8, 384, M_JAC>', 'kernel_ms': kernel_ms},
+                         'kernel': 'pj5::k_eval<%d, %d, M_JAC%s>' % (ev.plan_gs, 384 if ev.plan_threads > 256 or not wsg else 512,
+                                                                     ', WSG' if wsg else ''),
+                         'kernel_ms': kernel_ms},
             'e2e': e2e, 'cpu_baseline': cpu, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)
@@ -334,12 +357,15 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--states', type=int, default=1 << 20, help='states per GPU per step')
+    ap.add_argument('--workload', default='gri30', choices=sorted(WORKLOADS))
+    ap.add_argument('--states', type=int, default=0, help='states per GPU per step (0 = the workload default)')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
+    default_states = select_workload(args.workload)
+    args.states = args.states or default_states
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

@@ -11,3 +11,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_final.json 2> gpurun_out/bench_final.err
 python bench.py > gpurun_out/bench_final.json 2>> gpurun_out/bench_final.err; cat gpurun_out/bench_final.json
+for w in usc2 nc7; do python bench.py --workload $w --steps 5 --no-cpu > gpurun_out/bench_$w.json 2>> gpurun_out/bench_final.err; cat gpurun_out/bench_$w.json; done
+ncu --set full --import-source on --clock-control none --kernel-name regex:k_eval --launch-skip 1 --launch-count 1 -f \
+    -o gpurun_out/prof_nc7 python tools/mech_sweep.py --cases nc7:9472 --reps 1 > gpurun_out/ncu_nc7.log 2>&1
