@@ -8,16 +8,18 @@ from pyjac_b200.evaluator import Evaluator
 from pyjac_b200.mechanism import Mechanism
 from pyjac_b200.states import synthetic_states
 
-for f, n in (('gri30_syn.inp', 37), ('h2o2_n2.inp', 70), ('usc2_syn.inp', 5)):
+# (mechanism, states, working set forced into global memory?)
+for f, n, g in (('gri30_syn.inp', 37, None), ('h2o2_n2.inp', 70, None), ('usc2_syn.inp', 5, False),
+                ('usc2_syn.inp', 21, None), ('gri30_syn.inp', 37, True), ('plog.inp', 19, None), ('cheb.inp', 19, True)):
     mech = Mechanism.from_chemkin(os.path.join(ROOT, 'tests', 'golden', f))
     P_h, y_h = synthetic_states(mech.NSP, n, seed=1)
     P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
-    ev = Evaluator(mech, 0)
+    ev = Evaluator(mech, 0, ws_global=g)
     a = ev.eval_jacob(P, y)
     b = ev.eval_jacob(P, y.t().contiguous(), y_layout='state_fastest', jac_layout='state_fastest')
     c = ev.dydt(P, y)
     d = ev.rates(P, y, want_dy=True)
     torch.cuda.synchronize()
     assert torch.equal(a, b.t()) and torch.isfinite(a).all() and torch.isfinite(c).all()
-    print(f, 'ok')
+    print(f, 'ws_global', g, 'ok')
     ev.close()
