@@ -40,17 +40,22 @@ MAX_L2 = 1023
 
 # cost estimates (warp instructions) used only for load balancing
 COST_PLAIN, COST_IRREV, COST_THREE = 215.0, 150.0, 40.0
-COST_PM = {'thd': 300.0, 'lind': 450.0, 'troe': 900.0, 'sri': 1200.0}
+COST_PM = {'thd': 300.0, 'lind': 450.0, 'troe': float(__import__('os').environ.get('PYJAC_COST_TROE', 900.0)), 'sri': 1200.0}
 COST_EFF = 8.0
 COST_PLOG = 120.0
 COST_C_ITEM, COST_C_IT = 90.0, 28.0
 # phase DE costs are in units of 22 cycles, fitted to per-warp clock measurements on a B200
-# (tools/phase_clocks.py): the classes are bound by shared-memory / L2 latency, not by issue
+# (tools/phase_clocks.py) and re-tuned by throughput for the 12-warp plan (tools/cost_sweep.sh:
+# warp 0's share and the dense rows were under-estimated, +5.6 % once corrected): the classes are
+# bound by shared-memory / L2 latency, not by issue
 COST_S_STEP, COST_S_OVF = 40.0, 11.0
-COST_D_ITEM, COST_D_COL = 45.0, 12.0
+COST_D_ITEM, COST_D_COL = 63.0, 17.0
 COST_T_ITEM, COST_T_IT = 130.0, 11.0
+if 'PYJAC_COSTS' in __import__('os').environ:        # development: tools/cost_sweep.sh
+    (COST_S_STEP, COST_S_OVF, COST_D_ITEM, COST_D_COL, COST_T_ITEM, COST_T_IT) = (
+        float(v) for v in __import__('os').environ['PYJAC_COSTS'].split(','))
 D_MAX_COLS = 24              # a row with more dense-only columns is cut into several items
-COST_DOTS = 270.0            # warp 0: energy-equation scalars + the next group's phase A0
+COST_DOTS = float(__import__('os').environ.get('PYJAC_COST_DOTS', 640.0))   # warp 0: energy-equation scalars + the next group's phase A0
 
 
 def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:

@@ -4,7 +4,9 @@ Slots (a clock read may be scheduled before the barrier that precedes it, so a s
 warp's own work plus the wait at the previous barrier): 0 A1, 1 B, 2 -, 3 C, 4 dots/A0 + class S,
 5 class D, 6 class T, 7 -."""
 import os, sys
-os.environ['PYJAC_B200_NVCC_EXTRA'] = '-DPJ_PHASE_CLOCKS'     # instrumented build (set before the library is built)
+# instrumented build: tools/devbuild.sh clk -DPJ_PHASE_CLOCKS, then PYJAC_B200_LIB=pyjac_b200/_build/dev_clk.so
+if 'PYJAC_B200_LIB' not in os.environ:
+    os.environ['PYJAC_B200_NVCC_EXTRA'] = '-DPJ_PHASE_CLOCKS'     # (set before the library is built)
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -19,7 +21,8 @@ P = torch.tensor(P_h, device='cuda'); y = torch.tensor(y_h, device='cuda').t().c
 out = torch.empty((mech.NSP ** 2, n), dtype=torch.float64, device='cuda')
 clk = torch.zeros(32 * 8, dtype=torch.int64, device='cuda')
 from pyjac_b200 import libgen
-libgen.build_library(force=True)
+if 'PYJAC_B200_LIB' not in os.environ:
+    libgen.build_library(force=True)
 ev = Evaluator(mech, 0)
 ev.eval_jacob(P, y, out, y_layout='state_fastest', jac_layout='state_fastest')
 os.environ['PYJAC_DEBUG_CLK'] = str(clk.data_ptr())
