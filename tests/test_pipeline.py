@@ -101,3 +101,25 @@ def test_data_bin_round_trip(golden_dir, tmp_path):
     y, pres = speedtest.read_initial_conditions(data, 50, fwd)
     assert y.shape == (mech.NSP, 50) and np.array_equal(pres, raw[:, 2]) and np.array_equal(y[0], raw[:, 1])
     assert np.array_equal(y[1:], raw[:, 3:][:, fwd][:, :-1].T)
+
+
+def test_plan_choice_by_mechanism_size(golden_dir, tmp_path):
+    """Where the working set of a block lives (plan.py: SMEM_MIN_GS, wsg_shape): shared memory while
+    at least 8 states fit, else global memory; both can be forced."""
+    from pyjac_b200 import synth, tables
+    from pyjac_b200.mechanism import Mechanism
+    cases = [(os.path.join(golden_dir, 'h2o2_n2.inp'), 32, 0), (os.path.join(golden_dir, 'gri30_syn.inp'), 8, 0),
+             (os.path.join(golden_dir, 'usc2_syn.inp'), 8, 1)]
+    nc7 = str(tmp_path / 'nc7.inp')
+    synth.write('nc7', nc7)
+    cases.append((nc7, 16, 1))
+    for path, gs, wsg in cases:
+        cfg = tables.build(Mechanism.from_chemkin(path))['p5_cfg']
+        assert (int(cfg[0]), int(cfg[14])) == (gs, wsg), path
+    usc = Mechanism.from_chemkin(os.path.join(golden_dir, 'usc2_syn.inp'))
+    cfg = tables.build(usc, ws_global=False)['p5_cfg']
+    assert (int(cfg[0]), int(cfg[14])) == (2, 0)
+    cfg = tables.build(Mechanism.from_chemkin(os.path.join(golden_dir, 'gri30_syn.inp')), ws_global=True)['p5_cfg']
+    assert (int(cfg[0]), int(cfg[14])) == (8, 1)
+    with pytest.raises(tables.UnsupportedMechanism):
+        tables.build(Mechanism.from_chemkin(nc7), ws_global=False)
