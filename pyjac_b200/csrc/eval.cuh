@@ -681,11 +681,30 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         // concentrations; rho = sum C_k W_k, mw_avg = rho / sum C_k
         const bool inc = MODE == M_RATES && io.in_conc;
         V sumY = zero, sumYW = zero;
-        for (int k = sub; k < (inc ? nsp : last); k += NSUB) {
-            const V Yk{y0[(long long)(k + 1) * io.y_sv], y1[(long long)(k + 1) * io.y_sv]};
-            STS(E_Y * RB, sp_even<GS>(aSP, (unsigned)k), Yk);
-            sumY = vadd(sumY, Yk);
-            sumYW = vfma(__ldg((inc ? tb.sp_w : tb.sp_iw) + k), Yk, sumYW);
+        // four species per pass, their loads (HBM latency: this is the only per-state input) issued
+        // before the first is used; same summation order as one species at a time
+        const int kend = inc ? nsp : last;
+        const double* wtab = inc ? tb.sp_w : tb.sp_iw;
+        for (int k = sub; k < kend; k += 4 * NSUB) {
+            V Yk[4];
+            double wk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = k + u * NSUB;
+                const bool in = kk < kend;
+                const long long o = (long long)((in ? kk : k) + 1) * io.y_sv;
+                Yk[u] = V{y0[o], y1[o]};
+                wk[u] = __ldg(wtab + (in ? kk : k));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = k + u * NSUB;
+                if (kk < kend) {
+                    STS(E_Y * RB, sp_even<GS>(aSP, (unsigned)kk), Yk[u]);
+                    sumY = vadd(sumY, Yk[u]);
+                    sumYW = vfma(wk[u], Yk[u], sumYW);
+                }
+            }
         }
         sumY = sub_sum<GS>(sumY);
         sumYW = sub_sum<GS>(sumYW);
