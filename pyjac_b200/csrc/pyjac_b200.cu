@@ -14,7 +14,10 @@
 #include <vector>
 
 #include "eval.cuh"
+#include "jac6.cuh"
 #include "pjtable.h"
+
+#include <map>
 
 using pj::IO;
 using pj::Tables;
@@ -26,6 +29,8 @@ struct pyjac_mech {
     int smem_per_sm = 0;
     Tables tb{};
     pj5::Plan plan{};
+    pj6::Plan6 plan6{};              // record streams of k_jac6 (eval_jacob of plans that live in shared memory)
+    bool has6 = false;
     std::vector<void*> dev_allocs;
     int user_bpsm = 0;
     int bpsm[3] = {0, 0, 0};         // blocks per SM per mode (0 = not configured yet)
@@ -112,22 +117,80 @@ const void* kernel_for(int gs, int mode, int nt, int wsg = 0)
     return small ? kernel_t<384, pj::M_JAC>(gs) : kernel_t<512, pj::M_JAC>(gs);
 }
 
+// eval_jacob of a plan with record streams (p6_*): k_jac6, 168-register build up to 384 threads
+const void* kernel6_for(int gs, int nt)
+{
+    const bool small = nt <= 384;
+    switch (gs) {
+#ifndef PJ_DEV_GS8_ONLY
+    case 4: return small ? (const void*)pj6::k_jac6<4, 384> : (const void*)pj6::k_jac6<4, 512>;
+    case 16: return small ? (const void*)pj6::k_jac6<16, 384> : (const void*)pj6::k_jac6<16, 512>;
+    case 32: return small ? (const void*)pj6::k_jac6<32, 384> : (const void*)pj6::k_jac6<32, 512>;
+#endif
+    case 8: return small ? (const void*)pj6::k_jac6<8, 384> : (const void*)pj6::k_jac6<8, 512>;
+    default: return nullptr;
+    }
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel instantiation, which handles with
+// different plans share: keep it at the largest size any handle of this process asked for
+int ensure_dyn_smem(const void* fn, int device, size_t bytes, bool prefer_l1)
+{
+    static std::map<std::pair<const void*, int>, size_t> granted;       // function attributes are per device
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = granted.find({fn, device});
+    if (it == granted.end()) {
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                prefer_l1 ? cudaSharedmemCarveoutMaxL1 : cudaSharedmemCarveoutMaxShared));
+        it = granted.emplace(std::make_pair(fn, device), (size_t)0).first;
+    }
+    if (bytes > it->second) {
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        it->second = bytes;
+    }
+    return PYJAC_OK;
+}
+
+// restores the caller's current device when an entry point returns
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // One launch of k_eval; the plan in the table blob fixes states per block and block size.
 int launch(pyjac_mech* m, int mode, const IO& io_in, cudaStream_t st)
 {
     if (io_in.n <= 0) return PYJAC_OK;
     IO io = io_in;
-    CU(cudaSetDevice(m->device));
+    DeviceGuard guard(m->device);
     const pj5::Plan& pl = m->plan;
+    if (mode == pj::M_JAC && m->has6) {
+        // the Jacobian of a plan whose working set lives in shared memory: record-stream kernel
+        const pj6::Plan6& p6 = m->plan6;
+        const void* fn6 = kernel6_for(p6.gs, p6.nt);
+        if (!fn6) return fail(PYJAC_EINVAL, "table blob holds no usable stream plan");
+        if ((size_t)p6.bytes > (size_t)m->smem_optin)
+            return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
+        int rc6 = ensure_dyn_smem(fn6, m->device, (size_t)p6.bytes, false);
+        if (rc6) return rc6;
+        const long long groups6 = ((long long)io.n + p6.gs - 1) / p6.gs;
+        const int grid6 = (int)std::min<long long>(groups6, (long long)m->sm_count);
+        void* args6[3] = {(void*)&m->tb, (void*)&m->plan6, (void*)&io};
+        CU(cudaLaunchKernel(fn6, dim3(grid6), dim3(p6.nt), args6, (size_t)p6.bytes, st));
+        ++m->launches;
+        return PYJAC_OK;
+    }
     const void* fn = kernel_for(pl.gs, mode, pl.nt, pl.wsg);
     if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable plan");
     const size_t bytes = pl.wsg ? 0 : (size_t)pl.total * 8;
+    if (bytes > (size_t)m->smem_optin)
+        return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
+    {
+        int rcs = ensure_dyn_smem(fn, m->device, bytes, pl.wsg != 0);
+        if (rcs) return rcs;
+    }
     if (!m->bpsm[mode]) {
-        if (bytes > (size_t)m->smem_optin)
-            return fail(PYJAC_ETOOBIG, "mechanism working set does not fit in shared memory");
-        if (!pl.wsg) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                pl.wsg ? cudaSharedmemCarveoutMaxL1 : cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.nt, bytes));
         if (occ < 1) return fail(PYJAC_ETOOBIG, "kernel cannot be resident with this plan");
@@ -185,7 +248,7 @@ void release_staging(pyjac_mech* m)
 
 int ensure_staging(pyjac_mech* m, size_t pin, size_t din, size_t dout)
 {
-    CU(cudaSetDevice(m->device));
+    DeviceGuard guard(m->device);
     for (int i = 0; i < 2; ++i)
         if (!m->stream[i]) CU(cudaStreamCreateWithFlags(&m->stream[i], cudaStreamNonBlocking));
     if (pin > m->pin_bytes || din > m->din_bytes || dout > m->dout_bytes) {
@@ -222,7 +285,7 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     if (!pjt::valid(blob, len)) return fail(PYJAC_EINVAL, "not a PJB200T1 table blob");
     if (pyjac_device_count() <= 0) return fail(PYJAC_ENODEVICE, "no CUDA device available (no CPU fallback exists)");
     if (device < 0) CU(cudaGetDevice(&device));
-    CU(cudaSetDevice(device));
+    DeviceGuard guard(device);
     const pjt::Entry* de = pjt::find(blob, "dims");
     const pjt::Entry* ce = pjt::find(blob, "cst");
     if (!de || de->dtype != 1 || de->count < 16 || !ce || ce->dtype != 0 || ce->count < 2)
@@ -266,6 +329,23 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     UP(plan.o_off, "p5_o_off", int, 1); UP(plan.o_str, "p5_o_str", uint2, 1);
     UP(plan.t_off, "p5_t_off", int, 1); UP(plan.t_item, "p5_t_item", int2, 1); UP(plan.t_str, "p5_t_str", uint2, 1);
     UP(plan.colfac, "p5_colfac", double2, 0);
+    if (!rc && pjt::find(blob, "p6_cfg")) {
+        const pjt::Entry* pe = pjt::find(blob, "p6_cfg");
+        if (pe->dtype != 1 || pe->count < 24) rc = fail(PYJAC_EINVAL, "bad p6_cfg");
+        else {
+            const int* c6 = (const int*)((const char*)blob + pe->offset);
+            pj6::Plan6& p6 = m->plan6;
+            int* o = &p6.gs;
+            for (int i = 0; i < 24; ++i) o[i] = c6[i];
+            if (!kernel6_for(p6.gs, p6.nt) || p6.nt != p6.nw * 32 || p6.nsub * p6.gs != 64 || p6.chb != pj6::CHB ||
+                p6.nslot != pj6::NSLOT || p6.chr != pj6::CHB / (p6.nsub * 16) || p6.coop < 1 || p6.coop > p6.nsub ||
+                p6.tcoop < 1 || p6.tcoop > p6.nsub || p6.bytes < p6.mbar + p6.nw * pj6::NSLOT * 8)
+                rc = fail(PYJAC_EINVAL, "bad stream plan configuration");
+        }
+        UP(plan6.str, "p6_str", uint4, 1); UP(plan6.hdr, "p6_hdr", int, 1);
+        UP(plan6.eff, "p6_eff", int4, 1); UP(plan6.colfac, "p6_colfac", double2, 0);
+        if (!rc) { m->plan6.eff_off = m->plan.eff_off; m->has6 = true; }
+    }
 #undef UP
     if (!rc) {
         cudaDeviceProp prop;
@@ -286,7 +366,7 @@ void pyjac_mech_destroy(pyjac_mech* m)
         std::lock_guard<std::mutex> lk(g_mu);
         if (g_current == m) g_current = nullptr;
     }
-    cudaSetDevice(m->device);
+    DeviceGuard guard(m->device);
     release_staging(m);
     for (int i = 0; i < 2; ++i) if (m->stream[i]) cudaStreamDestroy(m->stream[i]);
     for (void* p : m->dev_allocs) cudaFree(p);
@@ -347,7 +427,7 @@ int pyjac_fd_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const double*
     if (order != 1 && order != 2 && order != 4 && order != 6) return fail(PYJAC_EINVAL, "order must be 1, 2, 4 or 6");
     if (!n) return PYJAC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(m->device));
+    DeviceGuard guard(m->device);
     const int nsp = m->tb.nsp;
     const size_t row = (size_t)n * nsp;
     double* w = nullptr;                     // dy0 | ytmp | dy | r
@@ -550,7 +630,7 @@ void pyjac_cu_cleanup(void)
         std::lock_guard<std::mutex> lk(g_mu);
         m = g_current;
     }
-    if (m) { cudaSetDevice(m->device); release_staging(m); }
+    if (m) { DeviceGuard guard(m->device); release_staging(m); }
     g_cu_num = 0;
 }
 

@@ -31,10 +31,12 @@ def _ptr(t) -> int:
 
 class Evaluator:
     def __init__(self, mech: Mechanism, device: Optional[int] = None, gs: int = 0, threads: int = 0,
-                 ws_global: Optional[bool] = None):
+                 ws_global: Optional[bool] = None, streams: Optional[bool] = None):
         """gs / threads: states per thread block and block size of the Jacobian kernel's plan
         (pyjac_b200/plan.py); 0 = automatic.  ws_global: working set of a block in global memory
-        instead of shared memory (None = only for mechanisms too large for shared memory)."""
+        instead of shared memory (None = only for mechanisms too large for shared memory).
+        streams: False = eval_jacob on the schedule tables of k_eval instead of the record streams of
+        k_jac6 (pyjac_b200/plan6.py)."""
         import torch
         self._torch = torch
         self.mech = mech
@@ -42,7 +44,8 @@ class Evaluator:
         if self.lib.pyjac_device_count() <= 0:
             raise _lib.PyjacError('no CUDA device: pyjac_b200 has no CPU fallback')
         self.device = torch.cuda.current_device() if device is None else int(device)
-        self.tables = _tables.build(mech, gs=gs, threads=threads, ws_global=ws_global)
+        self.tables = _tables.build(mech, gs=gs, threads=threads, ws_global=ws_global, streams=streams)
+        self.uses_streams = 'p6_str' in self.tables
         self.plan_gs, self.plan_threads = (int(v) for v in self.tables['p5_cfg'][:2])
         data = _blob.pack(self.tables)
         h = ctypes.c_void_p()

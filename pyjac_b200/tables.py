@@ -45,7 +45,7 @@ from typing import Dict, List
 
 import numpy as np
 
-from . import plan
+from . import plan, plan6
 from .chem import PA, RU
 from .mechanism import Mechanism
 
@@ -93,11 +93,14 @@ def _nasa_row(a) -> List[float]:
             a[6] - a[0], a[0] - 1.0, a[2] / 6.0, a[3] / 12.0, a[4] / 20.0, 0.0]
 
 
-def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None) -> Dict[str, np.ndarray]:
+def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, streams=None) -> Dict[str, np.ndarray]:
     """gs / threads: states per block and block size of the Jacobian kernel's plan (0 = automatic).
     ws_global: True puts the per-block working set in global memory instead of shared memory, False
     forbids that; None = automatic (global memory when fewer than plan.SMEM_MIN_GS states fit in
-    shared memory: USC-II- and n-heptane-sized mechanisms)."""
+    shared memory: USC-II- and n-heptane-sized mechanisms).
+    streams: False leaves out the record streams of k_jac6 (plan6.py), so that eval_jacob runs on the
+    schedule tables of k_eval like dydt and the rate routines do; None / True = streams whenever the
+    working set lives in shared memory."""
     specs, reacs = mech.specs, mech.reacs
     nsp, nr = len(specs), len(reacs)
     last = nsp - 1
@@ -143,11 +146,14 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None) -> Dic
     T['sp_seen'] = i32(seen)                                                   # rs:1425-1527
 
     # ---------------- kernel order: plain, third-body, fall-off; reversible first
+    # Reactions without pressure modification that hold the last species come last among their
+    # kind: from `p_c0` on a reaction may have X1 + X2 != 0 (plan6: correction rows)
     def sort_key(i):
         rx = reacs[i]
         cls = 2 if rx.pdep else (1 if rx.thd_body else 0)
         sub = (1 if rx.troe else (2 if rx.sri else 0)) if rx.pdep else 0
-        return (cls, sub, 0 if rx.rev else 1, i)
+        has_last = 1 if (cls == 0 and last in (rx.reac + rx.prod)) else 0
+        return (cls, sub, has_last, 0 if rx.rev else 1, i)
     order = sorted(range(nr), key=sort_key)
     pos_of = {orig: p for p, orig in enumerate(order)}
     npm = len(pdep_reacs)
@@ -528,6 +534,31 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None) -> Dic
         eff4_off.append(len(eff4) // 4)
     T['p5_eff_off'] = i32(eff4_off if npm else [0, 0])
     T['p5_eff'] = i32(eff4 + [0, 0, sp_off(nsp), nraw + 1] * 4)
+
+    # ---------------- record streams of the Jacobian kernel k_jac6 (plan6.py): plans whose working
+    # set lives in shared memory
+    p_c0 = next((p for p in range(nr) if p >= first_pm or last in (reacs[order[p]].reac + reacs[order[p]].prod)), nr)
+    if streams is not False and not ws_global and gs_ in plan6.GS6 and plan6.fits(nsp, nr, nr - p_c0, nraw, gs_, nt // 32):
+        corr_rx = [False] * nr
+        for p in range(p_c0, nr):
+            par = pm_par[p - first_pm] if p >= first_pm else None
+            corr_rx[p] = bool(any(int(sl) == last for sl in slots[p]) or (par is not None and par[4] != par[5]))
+        rec6 = rec5.copy()
+        spf6 = (slots * (plan6.SP_SLOTS * gs_ * 8) + (slots & 1) * (gs_ * 8)) // 16
+        for a in range(3):
+            rec6[:, 9 + a] = spf6[:, 2 * a] | (spf6[:, 2 * a + 1] << 16)
+        rec6[p_c0:, 8] |= plan6.F_CORR
+        rec6[:, 15] = np.arange(nr, dtype=np.int32) | (dst5[:, 7] << 16)
+        T.update(plan6.build_plan6(nsp, nr, nraw, first_pm, p_c0, kinds, [bool(reacs[i].rev) for i in order],
+                                   [bool(slots[p, 2] != nsp or slots[p, 5] != nsp) for p in range(nr)],
+                                   n_eff, rec6, red, corr_rx,
+                                   {kj: v for kj, v in contrib.items() if kj[0] != last},
+                                   tcontrib, T['sp_w'], T['sp_iw'], T['sp_mwf'], gs_, nt))
+        spb6 = plan6.SP_SLOTS * gs_ * 8
+        eff6 = np.asarray(T['p5_eff']).reshape(-1, 4).copy()
+        ksp = eff6[:, 2] // spb_                       # species of each collider record
+        eff6[:, 2] = ksp * spb6 + (ksp & 1) * gs_ * 8
+        T['p6_eff'] = eff6.ravel()
 
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
     T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, len(plog_par), len(cheb_par), 0,

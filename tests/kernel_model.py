@@ -13,8 +13,9 @@ from pyjac_b200 import tables as tb
 LN10 = np.log(10.0)
 
 
-def evaluate(Tb, P, y):
-    """Returns dict(conc, fwd, rev, pres_mod, spec_rates, dydt, jac); layouts as the oracle."""
+def evaluate(Tb, P, y, plan=5):
+    """Returns dict(conc, fwd, rev, pres_mod, spec_rates, dydt, jac); layouts as the oracle.
+    plan = 5: the schedule tables of k_eval (p5_*); plan = 6: the record streams of k_jac6 (p6_*)."""
     d = Tb['dims']
     nsp, nr, nrev, npd, nraw = (int(v) for v in d[:5])
     first_pm = int(d[8])
@@ -252,6 +253,9 @@ def evaluate(Tb, P, y):
         R4[p, 0], R4[p, 1], R4[p, 2], R4[p, 3] = net * PM, tT, X1, X2
         RH[p] = (hw[:, s[3]] + hw[:, s[4]] + hw[:, s[5]]) - (hw[:, s[0]] + hw[:, s[1]] + hw[:, s[2]])
 
+    if plan == 6:
+        return _assemble6(dict(locals()))
+
     # --- phase C of the plan: per species, +1 and -1 lists of reaction-row byte offsets, two
     # entries per unit and sub-group (padding entries point at the all-zero reaction row nr)
     cfg = Tb['p5_cfg']
@@ -426,3 +430,218 @@ def evaluate(Tb, P, y):
     dydt[:, 1:] = wdot[:, :last] * w[None, :last] / rho[:, None]
     return dict(conc=conc[:, :nsp], fwd=fwd, rev=rev[:, :nrev], pres_mod=pres_mod[:, :npd],
                 spec_rates=wdot, dydt=dydt, jac=jac.reshape(n, nsp * nsp))
+
+
+def _assemble6(v):
+    """Phases C and DE of k_jac6: interprets the per-warp record streams (pyjac_b200/plan6.py) record
+    by record, exactly in the order the kernel consumes them."""
+    from pyjac_b200 import plan6
+    Tb, n, nsp, nr, nraw, last = v['Tb'], v['n'], v['nsp'], v['nr'], v['nraw'], v['last']
+    R4, RH, raw, hw, cp, w = v['R4'], v['RH'], v['raw'], v['hw'], v['cp'], v['w']
+    mw_avg, rho, rho_inv, cp_avg, wdcp = v['mw_avg'], v['rho'], v['rho_inv'], v['cp_avg'], v['wdcp']
+    cfg = [int(x) for x in Tb['p6_cfg']]
+    gs, nt, nw, nsub = cfg[:4]
+    coop, tcoop, p_c0, ncorr, chb, nslot, chr_ = cfg[16:23]
+    assert nsub * gs == 64 and nt == nw * 32 and chr_ == chb // (nsub * 16)
+    L = plan6.layout6(nsp, nr, ncorr, nraw, gs, nw)
+    assert [L[k] for k in ('SP', 'RX', 'XC', 'RAW', 'ET', 'SC', 'PA', 'CF', 'ring', 'mbar', 'bytes')] == cfg[4:15]
+    assert L['bytes'] <= plan6.SMEM_LIMIT
+    RB = gs * 8
+    SPB = plan6.SP_SLOTS * RB
+    hdr = Tb['p6_hdr'].reshape(nw, 8)
+    st = Tb['p6_str'].view(np.uint32)
+    rec6 = None
+    # reaction rows as the kernel keeps them: row index v = p * 4 + (p & 1) is the even-slot base
+    # (net, X1 at +0, +2), the odd slots (tT, dH) sit at (v ^ 1) + {0, 2}
+    RXrows = {}
+    for p in range(nr):
+        b = p * 4 + (p & 1)
+        RXrows[b] = R4[p, 0]; RXrows[b + 2] = R4[p, 2]
+        RXrows[b ^ 1] = R4[p, 1]; RXrows[(b ^ 1) + 2] = RH[p]
+    for p in (nr, nr + 1):
+        b = p * 4 + (p & 1)
+        for r_ in (b, b + 2, b ^ 1, (b ^ 1) + 2):
+            RXrows[r_] = np.zeros(n)
+    XC = np.zeros((ncorr + 2, n))
+    for p in range(p_c0, nr):
+        XC[p - p_c0] = R4[p, 2] + R4[p, 3]
+    rawz = np.concatenate([raw[:, :nraw], np.zeros((n, 2))], axis=1)
+
+    def sp_k(off):
+        assert off % RB == 0
+        k, chunk = off // SPB, (off % SPB) // RB
+        assert chunk == (k & 1)                       # even-slot base
+        return k
+
+    wdot = np.zeros((n, nsp)); tcol = np.zeros((n, nsp)); Ak = np.zeros((n, nsp)); Bk = np.zeros((n, nsp))
+    ET = np.zeros((n, max(last, 1)))
+    seen_k, seen_j = set(), set()
+    pos = [0] * nw
+    rx_seen = set()
+
+    def get(wp):
+        base = int(hdr[wp, 0]) * (chb // 4) + pos[wp]
+        pos[wp] += nsub * 4
+        assert pos[wp] <= int(hdr[wp, 1]) * (chb // 4)
+        return [[int(x) for x in st[base + 4 * sb:base + 4 * sb + 4]] for sb in range(nsub)]
+
+    def f64(lo, hi):
+        return float(np.array([lo, hi], dtype=np.uint32).view(np.float64)[0])
+
+    # ---- phase B records: every reaction once, the padding sub-groups flagged
+    rx6 = {}
+    for wp in range(nw):
+        for r in range(int(hdr[wp, 2]) + int(hdr[wp, 3])):
+            q = [get(wp) for _ in range(4)]
+            for sb in range(nsub):
+                words = q[0][sb] + q[1][sb] + q[2][sb] + q[3][sb]
+                fl, p = words[8], words[15] & 0xFFFF
+                if fl & plan6.F_NULL:
+                    continue
+                assert p not in rx6
+                rx6[p] = words
+                assert (p >= Tb['dims'][8]) == (r < int(hdr[wp, 2]))
+                assert bool(fl & plan6.F_CORR) == (p >= p_c0)
+    assert sorted(rx6) == list(range(nr))
+    v['rx6'] = rx6
+
+    # ---- phase C
+    for wp in range(nw):
+        for r in range(int(hdr[wp, 4])):
+            h = get(wp)
+            nm, nx = (h[0][1] >> 8) & 0xFF, (h[0][1] >> 16) & 0xFF
+            assert all(((x[1] >> 8) & 0xFF, (x[1] >> 16) & 0xFF) == (nm, nx) for x in h)
+            part = np.zeros((nsub, 4, n))
+            for u in range(nm):
+                e = get(wp)
+                for sb in range(nsub):
+                    for i in range(8):
+                        x = (e[sb][i // 2] >> (16 * (i & 1))) & 0xFFFF
+                        sg = -1.0 if x & 0x8000 else 1.0
+                        b = x & 0x7FFF
+                        part[sb, 0] += sg * RXrows[b]
+                        part[sb, 1] += sg * RXrows[b ^ 1]
+                        part[sb, 2] += sg * RXrows[b + 2]
+            for u in range(nx):
+                e = get(wp)
+                for sb in range(nsub):
+                    for i in range(8):
+                        x = (e[sb][i // 2] >> (16 * (i & 1))) & 0xFFFF
+                        part[sb, 3] += (-1.0 if x & 0x8000 else 1.0) * XC[x & 0x7FFF]
+            for g0 in range(0, nsub, coop):
+                spoff, lead = h[g0][0], h[g0][1] & 1
+                tot = part[g0:g0 + coop].sum(axis=0)
+                if spoff == 0xFFFFFFFF:
+                    assert not tot.any() and not lead
+                    continue
+                assert lead and all(h[g0 + d][0] == spoff and not (h[g0 + d][1] & 1) for d in range(1, coop))
+                k = sp_k(spoff)
+                assert k not in seen_k and f64(h[g0][2], h[g0][3]) == w[k]
+                seen_k.add(k)
+                wdot[:, k], tcol[:, k] = tot[0], tot[1]
+                comp = tot[0] * mw_avg * rho_inv
+                Ak[:, k] = tot[2] + comp
+                Bk[:, k] = -Ak[:, k] + tot[3]
+        for r in range(int(hdr[wp, 5])):
+            h = get(wp)
+            nrec = h[0][1]
+            assert all(x[1] == nrec for x in h)
+            part = np.zeros((nsub, n))
+            for u in range(nrec):
+                e = get(wp)
+                for sb in range(nsub):
+                    for i in range(4):
+                        ro, b = e[sb][i] & 0xFFFF, e[sb][i] >> 16
+                        part[sb] += RXrows[(b ^ 1) + 2] * rawz[:, ro]
+            for g0 in range(0, nsub, tcoop):
+                col, lead = h[g0][0] & 0xFFFF, h[g0][0] >> 16
+                E0 = part[g0:g0 + tcoop].sum(axis=0)
+                if col == 0:
+                    assert not E0.any() and not lead
+                    continue
+                assert lead == 1 and all(h[g0 + d][0] == col for d in range(1, tcoop))
+                assert col - 1 not in seen_j
+                seen_j.add(col - 1)
+                ET[:, col - 1] = E0
+    assert seen_k == set(range(nsp)) and seen_j == set(range(last))
+
+    # ---- phase DE
+    wt = 1.0 / cp_avg
+    hwk = hw[:, :nsp]
+    H1 = (hwk * wdot).sum(axis=1)
+    HA = (hwk * Ak).sum(axis=1)
+    HB = (hwk * Bk).sum(axis=1)
+    HT = (hwk * tcol).sum(axis=1)
+    SCP = (cp * w[None, :] * wdot).sum(axis=1)
+    XT = H1 / (rho * cp_avg * cp_avg)
+    WA, WB, WT = w[None, :] * Ak, w[None, :] * Bk, w[None, :] * tcol
+    colfac = Tb['p6_colfac'].reshape(nsp, 2)
+    jac = np.full((n, nsp * nsp), np.nan)
+    for wp in range(nw):
+        for sgm in range(int(hdr[wp, 6])):
+            h = get(wp)
+            Ls = h[0][1] >> 16
+            assert all(x[1] >> 16 == Ls for x in h)
+            rows_k = []
+            for sb in range(nsub):
+                if h[sb][0] == 0xFFFFFFFF:
+                    rows_k.append(None)
+                    continue
+                k = sp_k(h[sb][0])
+                assert k == (h[sb][1] >> 8) & 0xFF and f64(h[sb][2], h[sb][3]) == w[k]
+                rows_k.append(k)
+                if h[sb][1] & 1:
+                    assert np.isnan(jac[:, k + 1]).all()
+                    jac[:, k + 1] = WT[:, k]
+            acc = [np.zeros(n) for _ in range(nsub)]
+            open_e = [None] * nsub
+            for t in range(Ls):
+                r = get(wp)
+                c = (r[0][0] >> 24) & 7
+                assert c in plan6.CLASSES and all((x[0] >> 24) & 7 == c for x in r)
+                for sb in range(nsub):
+                    x0 = r[sb][0]
+                    ents = [(r[sb][1 + i // 2] >> (16 * (i & 1))) & 0xFFFF for i in range(6)]
+                    if x0 & plan6.D_FIRST:
+                        assert open_e[sb] is None
+                        acc[sb] = np.zeros(n)
+                    for i in range(6):
+                        x = ents[i]
+                        if i < c:
+                            acc[sb] = acc[sb] + (-1.0 if x & 0x8000 else 1.0) * rawz[:, x & 0x7FFF]
+                        else:
+                            assert (x & 0x7FFF) >= nraw            # entries the kernel does not read: padding
+                    if not x0 & plan6.D_VALID:
+                        assert not acc[sb].any() and x0 & plan6.D_FINAL
+                        continue
+                    k = rows_k[sb]
+                    e, col = x0 & 0xFFFF, (x0 >> 16) & 0xFF
+                    assert k is not None and e == col * nsp + k + 1 and col >= 1
+                    assert open_e[sb] in (None, e)
+                    open_e[sb] = e
+                    if x0 & plan6.D_FINAL:
+                        assert np.isnan(jac[:, e]).all()
+                        tt = w[k] * acc[sb] + WA[:, k]
+                        jac[:, e] = colfac[col, 1] * WB[:, k] + colfac[col, 0] * tt
+                        open_e[sb] = None
+            assert all(o is None for o in open_e)
+        for r_ in range(int(hdr[wp, 7])):
+            r = get(wp)
+            for sb in range(nsub):
+                col = r[sb][0]
+                if col == 0:
+                    continue
+                eidx = col * nsp
+                assert np.isnan(jac[:, eidx]).all()
+                pj, qj = colfac[col]
+                jac[:, eidx] = pj * (-wt * ET[:, col - 1] + (-wt * HA)) + qj * (-wt * HB) \
+                    + XT * (cp[:, col - 1] - cp[:, last])
+        assert pos[wp] <= int(hdr[wp, 1]) * (chb // 4) and pos[wp] > (int(hdr[wp, 1]) - 1) * (chb // 4)
+    s0 = -wdcp / cp_avg * H1 + SCP + HT * rho
+    jac[:, 0] = -s0 / (rho * cp_avg)
+    assert not np.isnan(jac).any()
+    dydt = np.empty((n, nsp))
+    dydt[:, 0] = -1.0 / (rho * cp_avg) * H1
+    dydt[:, 1:] = wdot[:, :last] * w[None, :last] / rho[:, None]
+    return dict(conc=v['conc'][:, :nsp], fwd=v['fwd'], rev=v['rev'][:, :v['nrev']], pres_mod=v['pres_mod'][:, :v['npd']],
+                spec_rates=wdot, dydt=dydt, jac=jac)

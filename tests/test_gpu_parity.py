@@ -98,6 +98,51 @@ def test_launch_shapes_give_identical_results(torch, golden_dir, gs, threads, la
     ev0.close()
 
 
+@pytest.mark.parametrize('mech_file,npz,gs,threads', [('gri30_syn.inp', 'gri30_syn.npz', 0, 0), ('gri30_syn.inp', 'gri30_syn.npz', 4, 256),
+                                                      ('gri30_syn.inp', 'gri30_syn.npz', 8, 256), ('h2o2_n2.inp', 'h2o2_pasr.npz', 0, 0),
+                                                      ('h2o2_n2.inp', 'h2o2_pasr.npz', 16, 128), ('h2o2_n2.inp', 'h2o2_pasr.npz', 8, 384),
+                                                      ('torture.inp', 'torture_pasr.npz', 4, 64), ('torture.inp', 'torture_pasr.npz', 32, 512),
+                                                      ('plog.inp', 'plog_syn.npz', 8, 256), ('cheb.inp', 'cheb_syn.npz', 16, 384)])
+def test_stream_kernel_vs_table_kernel(torch, golden_dir, mech_file, npz, gs, threads):
+    """eval_jacob through the record streams (k_jac6) against the golden vectors and against the
+    schedule-table kernel (k_eval) on the same states, ragged batch included."""
+    mech, ev = _evaluator_with(golden_dir, mech_file, gs=gs, threads=threads)
+    assert ev.uses_streams
+    mech, ev5 = _evaluator_with(golden_dir, mech_file, gs=gs, threads=threads, streams=False)
+    assert not ev5.uses_streams
+    g = dict(np.load(os.path.join(golden_dir, npz)))
+    P, y = torch.tensor(g['P'], device='cuda'), torch.tensor(g['y'], device='cuda')
+    jac = ev.eval_jacob(P, y).cpu().numpy()
+    worst, frac = gates.check_jac(jac, g['jac'], mech.NSP, mech_file + ' streams', mech, g['y'])
+    print('%s gs=%d: |d|/colmax %.2e, elementwise <= 1e-10: %.5f' % (mech_file, ev.plan_gs, worst, frac))
+    ref = ev5.eval_jacob(P, y).cpu().numpy()
+    a, b = jac.reshape(-1, mech.NSP, mech.NSP), ref.reshape(-1, mech.NSP, mech.NSP)
+    err = np.abs(a - b) / (np.abs(b).max(axis=2, keepdims=True) + 1e-300)
+    assert err.max() <= 5e-11, err.max()
+    n = len(g['P'])
+    for m_ in (1, 3, min(n, 2 * ev.plan_gs + 1)):
+        out = torch.full((mech.NSP ** 2, m_ + 1), float('nan'), dtype=torch.float64, device='cuda')
+        ev.eval_jacob(P[:m_].contiguous(), y[:m_].t().contiguous(), out, y_layout='state_fastest', jac_layout='state_fastest')
+        assert np.array_equal(out[:, :m_].t().cpu().numpy(), jac[:m_]), m_
+        assert torch.isnan(out[:, m_]).all()
+    ev.close()
+    ev5.close()
+
+
+def test_two_handles_share_one_kernel_instantiation(torch, golden_dir):
+    """The opt-in shared-memory size belongs to the kernel instantiation, not to a handle: a large plan,
+    then a small one, then the large one again (same instantiation) must all launch."""
+    mech_l, ev_l = _evaluator_with(golden_dir, 'gri30_syn.inp', gs=8, threads=384)
+    mech_s, ev_s = _evaluator_with(golden_dir, 'h2o2_n2.inp', gs=8, threads=384)
+    for mech, ev in ((mech_l, ev_l), (mech_s, ev_s), (mech_l, ev_l), (mech_s, ev_s)):
+        P_h, y_h = synthetic_states(mech.NSP, 40, seed=2)
+        P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
+        assert np.isfinite(ev.eval_jacob(P, y).cpu().numpy()).all()
+        assert np.isfinite(ev.dydt(P, y).cpu().numpy()).all()
+    ev_l.close()
+    ev_s.close()
+
+
 def test_against_oracle_on_synthetic_states(torch, golden_dir):
     """GRI-3.0-shaped mechanism, 2048 seeded synthetic states, oracle = CPU restatement."""
     from oracle.oracle import Oracle

@@ -30,6 +30,40 @@ def test_model_matches_reference_golden(golden_dir, mech_file, npz, sl):
     assert frac > 0.97
 
 
+@pytest.mark.parametrize('mech_file,npz,sl', [c for c in CASES if c[0] != 'usc2_syn.inp'])
+def test_stream_model_matches_reference_golden(golden_dir, mech_file, npz, sl):
+    """The record streams of k_jac6 (plan6.py), interpreted record by record."""
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
+    T = blob.unpack(blob.pack(tables.build(mech)))
+    assert 'p6_str' in T
+    g = {k: v[sl] for k, v in np.load(os.path.join(golden_dir, npz)).items()}
+    out = kernel_model.evaluate(T, g['P'], g['y'], plan=6)
+    worst, frac = gates.check_jac(out['jac'], g['jac'], mech.NSP, mech_file, mech, g['y'])
+    assert frac > 0.97
+    ref = kernel_model.evaluate(T, g['P'], g['y'])
+    assert np.abs(out['jac'] - ref['jac']).max() <= 1e-12 * np.abs(ref['jac']).max()
+
+
+@pytest.mark.parametrize('mech_file,npz,gs,threads', [('h2o2_n2.inp', 'h2o2_pasr.npz', 4, 128), ('h2o2_n2.inp', 'h2o2_pasr.npz', 8, 512),
+                                                      ('torture.inp', 'torture_pasr.npz', 16, 64), ('gri30_syn.inp', 'gri30_syn.npz', 4, 256),
+                                                      ('gri30_syn.inp', 'gri30_syn.npz', 8, 256)])
+def test_stream_model_other_shapes(golden_dir, mech_file, npz, gs, threads):
+    """Stream plans for other states-per-block / block sizes than the automatic choice."""
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
+    T = tables.build(mech, gs=gs, threads=threads)
+    assert 'p6_str' in T and tuple(T['p6_cfg'][:2]) == (gs, threads)
+    g = {k: v[:16] for k, v in np.load(os.path.join(golden_dir, npz)).items()}
+    out = kernel_model.evaluate(T, g['P'], g['y'], plan=6)
+    gates.check_jac(out['jac'], g['jac'], mech.NSP, mech_file, mech, g['y'])
+
+
+def test_streams_can_be_left_out(golden_dir):
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, 'h2o2_n2.inp'))
+    assert 'p6_str' not in tables.build(mech, streams=False)
+    big = Mechanism.from_chemkin(os.path.join(golden_dir, 'usc2_syn.inp'))
+    assert 'p6_str' not in tables.build(big)          # working set in global memory: schedule tables only
+
+
 def test_tables_reject_unsupported(golden_dir):
     mech = Mechanism.from_chemkin(os.path.join(golden_dir, 'h2o2_n2.inp'))
     mech.reacs[3].reac_nu = [1.5 for _ in mech.reacs[3].reac_nu]

@@ -20,7 +20,7 @@ def main():
     ap.add_argument('--shape', default=None, help='synthetic shape name instead of --mech')
     ap.add_argument('--n', type=int, default=262144)
     ap.add_argument('--configs', default='8:512:0,8:256:0,4:512:0,4:256:0,4:384:0,8:384:0,2:256:0',
-                    help='gs:threads:blocks_per_sm of the Jacobian plan')
+                    help='gs:threads:blocks_per_sm[:streams] of the Jacobian plan (streams = 0: schedule-table kernel)')
     ap.add_argument('--layout', default='state_fastest')
     ap.add_argument('--reps', type=int, default=5)
     a = ap.parse_args()
@@ -39,9 +39,9 @@ def main():
     bytes_per_state = 8 * nn + 8 * (mech.NSP + 1)
     print('mech NSP=%d NR=%d n=%d  bytes/state=%d' % (mech.NSP, mech.FWD_RATES, a.n, bytes_per_state))
     for cfg in a.configs.split(','):
-        G, th, bp = (int(v) for v in cfg.split(':'))
+        G, th, bp, *rest = (int(v) for v in cfg.split(':'))
         try:
-            ev = Evaluator(mech, 0, gs=G, threads=th)
+            ev = Evaluator(mech, 0, gs=G, threads=th, streams=bool(rest[0]) if rest else None)
             ev.tune(bp)
             ev.eval_jacob(P, y, out, y_layout=a.layout, jac_layout=a.layout)
             torch.cuda.synchronize()
@@ -56,8 +56,8 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        print('gs=%d threads=%3d bpsm=%d: %8.3f ms  %.3e states/s  %7.1f GB/s' %
-              (G, th, bp, best, a.n / best * 1e3, a.n * bytes_per_state / best / 1e6))
+        print('gs=%d threads=%3d bpsm=%d streams=%d: %8.3f ms  %.3e states/s  %7.1f GB/s' %
+              (G, th, bp, ev.uses_streams, best, a.n / best * 1e3, a.n * bytes_per_state / best / 1e6))
     # dydt for reference
     ev = Evaluator(mech, 0)
     dy = torch.empty_like(y)
