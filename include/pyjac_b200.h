@@ -125,7 +125,17 @@ int pyjac_eval_jacob_host(pyjac_mech* m, int n, const double* pres, const double
                           double* jac);
 int pyjac_dydt_host(pyjac_mech* m, int n, const double* pres, const double* y, double* dy);
 
+/* Registers the table blob of a mechanism as the one surfaces 2 and 3 use when none was selected
+ * with pyjac_set_mechanism: the per-mechanism stub library that pyjac_b200.libgen.generate_library
+ * writes (libcu_pyjac.so, the name of pyjac/libgen/libgen.py:170-186) calls this from a constructor, so a
+ * program linked against it -- the reference's tester.c.in -- needs no set-up call.  The blob is
+ * not copied; the mechanism is loaded on the current device at first use. */
+int pyjac_register_tables(const void* blob, size_t len);
+
 /* ---- 3. scalar API, reference names ------------------------------------------------ */
+/* Re-entrant and safe to call from concurrent host threads (every call stages through its own
+ * slot), like the reference's stack-only functions (tester.c.in:24-29 calls eval_jacob inside
+ * an OpenMP loop). */
 void eval_jacob(const double t, const double pres, const double* y, double* jac);
 void dydt(const double t, const double pres, const double* y, double* dy);
 void eval_conc(const double T, const double pres, const double* mass_frac, double* y_N,
@@ -135,8 +145,26 @@ void eval_rxn_rates(const double T, const double pres, const double* C, double* 
 void get_rxn_pres_mod(const double T, const double pres, const double* C, double* pres_mod);
 void eval_spec_rates(const double* fwd_rates, const double* rev_rates, const double* pres_mod,
                      double* sp_rates, double* dy_N);
+/* chem_utils.h of the emitted library (rate_subs.py:1581-1608; bodies 1806-2086): NSP mass-based
+ * enthalpies [J/kg], internal energies, and heat capacities at constant volume / pressure [J/kg/K] */
+void eval_h(const double T, double* h);
+void eval_u(const double T, double* u);
+void eval_cv(const double T, double* cv);
+void eval_cp(const double T, double* cp);
+/* mass_mole.h / mechanism.h (mech_auxiliary.py:188-206), called by read_initial_conditions.c:29:
+ * NSP mass fractions from the mechanism file's species order to pyJac's internal order (last
+ * species moved to the end) and back, in place */
+void apply_mask(double* y_specs);
+void apply_reverse_mask(double* y_specs);
 
 #ifdef __cplusplus
 }
+
+/* ---- 2'. pyjac/pywrap/pyjacob.cuh:6-10 verbatim: C++ linkage, as the reference's pyjacob.cu defines them
+ * and pyjacob_cuda_wrapper.pyx:5-10 binds them.  init = pyjac_cu_init (exits on error like the
+ * reference's cudaErrorCheck), run = pyjac_cu_run, cleanup = pyjac_cu_cleanup. */
+void run(int, int, const double*, const double*, double*, double*, double*, double*, double*, double*, double*);
+int init(int);
+void cleanup();
 #endif
 #endif

@@ -152,6 +152,53 @@ def build_cuda(name: str, mech: str, jobs: int = 8, force: bool = False, quiet: 
     return lib
 
 
+def speedtest_path(name: str) -> str:
+    return os.path.join(ref_dir(name + '_speedtest'), 'speedtest')
+
+
+def build_speedtest(name: str, mech: str, force: bool = False) -> str:
+    """The reference's own performance harness -- pyjac/performance_tester/tester.c.in (its $datafile
+    filled in with "data.bin", as performance_tester.py:430-445 does with string.Template),
+    read_initial_conditions.c and timer.h, compiled where they lie with the reference's flags
+    (performance_tester.py:480-482: -std=c99 -O3 -mtune=native -fopenmp; -D_DEFAULT_SOURCE for timersub
+    on current glibc) -- against the headers and the per-mechanism stub library that pyjac_b200 writes
+    (create_jacobian / libgen.generate_library('c', ...)) instead of the generated sources:
+    the drop-in proof of the scalar C API.  -> oracle/_ref/<name>_speedtest/speedtest, run as
+    ``speedtest <num_odes> <num_threads>`` in a directory holding data.bin."""
+    from string import Template
+    sys.path.insert(0, os.path.dirname(HERE))
+    from pyjac_b200 import create_jacobian as cj, libgen
+    out = ref_dir(name + '_speedtest')
+    exe = speedtest_path(name)
+    stamp = os.path.join(out, 'mech.inp')
+    mech_txt = open(mech).read()
+    if not force and os.path.exists(exe) and os.path.exists(stamp) and open(stamp).read() == mech_txt \
+            and os.path.getmtime(exe) >= os.path.getmtime(libgen.LIB_PATH):
+        return exe
+    if not have_reference():
+        raise RuntimeError('reference sources not present at %s' % REF_ROOT)
+    os.makedirs(out, exist_ok=True)
+    cj.create_jacobian('cuda', mech, build_path=out)
+    libgen.generate_library('c', out, out_dir=out)
+    home = os.path.join(REF_ROOT, 'pyjac', 'performance_tester')
+    with open(os.path.join(home, 'tester.c.in')) as fh:
+        main_c = Template(fh.read()).substitute(datafile='data.bin')
+    test_c = os.path.join(out, 'test.c')
+    with open(test_c, 'w') as fh:                       # generated from the template, like the reference's build dir
+        fh.write(main_c)
+    cmd = ['gcc', '-std=c99', '-O3', '-mtune=native', '-fopenmp', '-D_DEFAULT_SOURCE', '-I', out, '-I', home,
+           test_c, os.path.join(home, 'read_initial_conditions.c'), '-o', exe, '-L', out, '-lc_pyjac',
+           '-L', libgen.BUILD, '-lpyjac_b200', '-lm',
+           '-Wl,-rpath,$ORIGIN', '-Wl,-rpath,$ORIGIN/../../../pyjac_b200/_build']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.remove(test_c)
+    if r.returncode != 0:
+        raise RuntimeError('building the reference harness against pyjac_b200 failed:\n' + r.stderr)
+    with open(stamp, 'w') as fh:
+        fh.write(mech_txt)
+    return exe
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('name')

@@ -18,6 +18,113 @@ from .mechanism import Mechanism
 TABLE_FILE = 'mechanism.pjt'
 HEADER_FILE = 'mechanism.h'
 
+# The headers a program written against the emitted library includes (create_jacobian.py:2226-2248,
+# rate_subs.py:292-323,1581-1608,2130-2150, mech_auxiliary.py:109-206,440-478): same names, same
+# prototypes; the definitions live in the fixed CUDA library (include/pyjac_b200.h surface 3).
+_HEADERS = {
+    'header.h': '''#ifndef HEAD
+#define HEAD
+#include <stdlib.h>
+#include <math.h>
+
+/** Constant pressure or volume. */
+#define CONP
+//#define CONV
+
+/** Include mechanism header to get NSP and NN **/
+#include "mechanism.h"
+// OpenMP
+#ifdef _OPENMP
+ #include <omp.h>
+#else
+ #define omp_get_max_threads() 1
+ #define omp_get_num_threads() 1
+#endif
+#endif
+''',
+    'jacob.h': '''#ifndef JACOB_HEAD
+#define JACOB_HEAD
+
+#include "header.h"
+#include "chem_utils.h"
+#include "rates.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+void eval_jacob (const double, const double, const double * __restrict__, double * __restrict__);
+#ifdef __cplusplus
+}
+#endif
+
+#endif
+''',
+    'dydt.h': '''#ifndef DYDT_HEAD
+#define DYDT_HEAD
+
+#include "header.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+void dydt (const double, const double, const double * __restrict__, double * __restrict__);
+#ifdef __cplusplus
+}
+#endif
+
+#endif
+''',
+    'rates.h': '''#ifndef RATES_HEAD
+#define RATES_HEAD
+
+#include "header.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+void eval_rxn_rates (const double, const double, const double * __restrict__, double * __restrict__, double * __restrict__);
+void eval_spec_rates (const double * __restrict__, const double * __restrict__, const double * __restrict__, double * __restrict__, double * __restrict__);
+void get_rxn_pres_mod (const double, const double, const double * __restrict__, double * __restrict__);
+#ifdef __cplusplus
+}
+#endif
+
+#endif
+''',
+    'chem_utils.h': '''#ifndef CHEM_UTILS_HEAD
+#define CHEM_UTILS_HEAD
+
+#include "header.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+void eval_conc (const double, const double, const double * __restrict__, double * __restrict__, double * __restrict__, double * __restrict__, double * __restrict__);
+void eval_h (const double, double * __restrict__);
+void eval_u (const double, double * __restrict__);
+void eval_cv (const double, double * __restrict__);
+void eval_cp (const double, double * __restrict__);
+#ifdef __cplusplus
+}
+#endif
+
+#endif
+''',
+    'pyjacob.cuh': '''/* wrapper to translate to cuda arrays */
+
+#ifndef CU_PYJAC_HEAD
+#define CU_PYJAC_HEAD
+
+void run(int, int, const double*, const double*,
+			double*, double*, double*,
+			double*, double*, double*, double*);
+int init(int);
+void cleanup();
+
+#endif
+''',
+}
+
 
 def _header(mech: Mechanism) -> str:
     lines = ['#ifndef MECHANISM_H', '#define MECHANISM_H', '',
@@ -32,7 +139,11 @@ def _header(mech: Mechanism) -> str:
               '/* Number of forward reactions */', '#define FWD_RATES %d' % mech.FWD_RATES,
               '/* Number of reversible reactions */', '#define REV_RATES %d' % mech.REV_RATES,
               '/* Number of reactions with pressure modified rates */',
-              '#define PRES_MOD_RATES %d' % mech.PRES_MOD_RATES, '', '#endif', '']
+              '#define PRES_MOD_RATES %d' % mech.PRES_MOD_RATES, '',
+              '#ifdef __cplusplus', 'extern "C" {', '#endif',
+              '//apply masking of ICs for cache optimized mechanisms', 'void apply_mask(double*);',
+              'void apply_reverse_mask(double*);',
+              '#ifdef __cplusplus', '}', '#endif', '', '#endif', '']
     return '\n'.join(lines)
 
 
@@ -62,6 +173,9 @@ def create_jacobian(lang, mech_name=None, therm_name=None, gas=None, optimize_ca
     os.makedirs(build_path, exist_ok=True)
     with open(os.path.join(build_path, HEADER_FILE), 'w') as fh:
         fh.write(_header(mech))
+    for name, text in _HEADERS.items():
+        with open(os.path.join(build_path, name), 'w') as fh:
+            fh.write(text)
     if not skip_jac:
         T = tables.build(mech, gs=gs, threads=threads)
         with open(os.path.join(build_path, TABLE_FILE), 'wb') as fh:

@@ -153,4 +153,22 @@ __global__ void k_fd_accum(int n, int nsp, int j, double w, int first, const dou
     *o = first ? v : *o + v;
 }
 
+// eval_h / eval_u / eval_cv / eval_cp of the emitted chem_utils (rate_subs.py:1806-1874 h, 1876-1945 u,
+// 1947-2019 cv, 2021-2086 cp): NASA-7 polynomials per species, mass based, one thread per species.
+// sp_nasa[k][branch] = {a0..a4, a5, a1/2, a2/3, a3/4, a4/5, ., a0 - 1, ...} (tables._nasa_row).
+enum : int { TH_H = 0, TH_U = 1, TH_CV = 2, TH_CP = 3 };
+__global__ void k_thermo(const __grid_constant__ Tables tb, double T, int what, double* out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= tb.nsp) return;
+    const double* c = tb.sp_nasa + (k * 2 + (T <= tb.sp_tmid[k] ? 0 : 1)) * 16;
+    const double ruw = tb.sp_ruw[k];
+    double v;
+    if (what == TH_H) v = ruw * (c[5] + T * (c[0] + T * (c[6] + T * (c[7] + T * (c[8] + c[9] * T)))));
+    else if (what == TH_U) v = ruw * (c[5] + T * (c[11] + T * (c[6] + T * (c[7] + T * (c[8] + c[9] * T)))));
+    else if (what == TH_CV) v = ruw * (c[11] + T * (c[1] + T * (c[2] + T * (c[3] + c[4] * T))));
+    else v = ruw * (c[0] + T * (c[1] + T * (c[2] + T * (c[3] + c[4] * T))));
+    out[k] = v;
+}
+
 }  // namespace pj

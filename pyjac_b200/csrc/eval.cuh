@@ -36,6 +36,13 @@ namespace pj5 {
 
 using namespace pj;
 
+// development builds (-DPJ_DEV, tools/skip_mech.sh) can leave phases out when timing; a release build has no such switch
+#ifdef PJ_DEV
+#define PJ_SKIP(MASK) ((io.dbg_skip & (MASK)) != 0)
+#else
+#define PJ_SKIP(MASK) false
+#endif
+
 struct Plan {
     int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync, coop, tcoop, oCF;
     int wsg;                         // 1: the working set lives in global memory (IO::ws), not in shared memory
@@ -762,7 +769,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         const unsigned aSC = aSC0 + buf * SCB;
         // fast: both states of the lane in range and 16-byte stores possible (all but tail groups)
         const bool fast = vec_ok && ok1;
-        const bool nostore = (io.dbg_skip & 128) != 0;      // timing experiments only
+        const bool nostore = PJ_SKIP(128);      // development builds only
         auto store = [&](unsigned e, V v, bool on) {
             char* o = out0 + (unsigned long long)e * ld8;
             if (nostore) on = false;
@@ -783,7 +790,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         };
 
         // ------------------------------------------------------------ phase A1: species thermo
-        if (!(io.dbg_skip & 1)) {
+        if (!PJ_SKIP(1)) {
             const V T = LDS(Q_T * RB, aSC), logT = LDS(Q_LOGT * RB, aSC), iT = LDS(Q_IT * RB, aSC);
             const V rho = LDS(Q_RHO * RB, aSC);
             const double Tv[2] = {T.x, T.y}, lT[2] = {logT.x, logT.y}, rT[2] = {iT.x, iT.y}, rh[2] = {rho.x, rho.y};
@@ -836,7 +843,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         PJ_TICK(0)
 
         // ------------------------------------------------------------ phase B: reactions
-        if (!(io.dbg_skip & 2)) {
+        if (!PJ_SKIP(2)) {
             const V T = LDS(Q_T * RB, aSC), logT = LDS(Q_LOGT * RB, aSC), iT = LDS(Q_IT * RB, aSC);
             const unsigned nsp_f = sp_even<GS>(0u, (unsigned)nsp) / 16;
             int item = b_item0;
@@ -868,7 +875,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         PJ_TICK(2)
 
         // ------------------------------------------------------------ phase C: species sums
-        if (!(io.dbg_skip & 4)) {
+        if (!PJ_SKIP(4)) {
             const int i0 = __ldg(pl.c_off + warp), i1 = __ldg(pl.c_off + warp + 1);
             const V mwr = LDS(Q_MWR * RB, aSC);
             V pH1 = zero, pHA = zero, pHB = zero, pHT = zero, pSCP = zero;
@@ -977,7 +984,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         }
 
         // ------------------------------------------------------------ phase DE
-        if (warp == 0 && !(io.dbg_skip & 64)) {
+        if (warp == 0 && !PJ_SKIP(64)) {
             // energy-equation scalars from the per-warp partial sums; the result of quantity q
             // replaces warp 0's own partial
             for (int q = sub; q < NPART; q += NSUB) {
@@ -1009,7 +1016,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             // the next group's phase A0 (its inputs come from HBM: latency hidden behind DE)
             if (grp + gridDim.x < ngroups) phase_a0(grp + gridDim.x, buf ^ 1);
         }
-        if (!(io.dbg_skip & 8)) {
+        if (!PJ_SKIP(8)) {
             // class S: elements with a sparse part, two steps per iteration, next pair in flight
             const int st0 = __ldg(pl.s_off + warp), st1 = __ldg(pl.s_off + warp + 1);
             const uint4* sp = pl.s_str + (long long)st0 * 2 * NSUB + sub;
@@ -1063,7 +1070,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             }
         }
         PJ_TICK(4)
-        if (!(io.dbg_skip & 16)) {
+        if (!PJ_SKIP(16)) {
             // class D: dense-only elements by row.  A sub-group keeps W_k a_k, W_k b_k of its row
             // in registers and walks the row's dense-only columns, four in flight.
             const int i0 = __ldg(pl.d_off + warp), i1 = __ldg(pl.d_off + warp + 1);
@@ -1098,7 +1105,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             }
         }
         PJ_TICK(5)
-        if (!(io.dbg_skip & 32)) {
+        if (!PJ_SKIP(32)) {
             // class T, the energy-equation row (cj:3095-3254): per column an enthalpy-weighted
             // gather; pl.tcoop sub-groups share a column, units come four at a time
             const int i0 = __ldg(pl.t_off + warp), i1 = __ldg(pl.t_off + warp + 1);

@@ -21,6 +21,8 @@
 //     that does not hold.  The slot pairs of odd species / reactions are swapped (E ^ RB) so that
 //     equal slots of different items fall on both halves of a 128-byte bank line.
 #pragma once
+#include <type_traits>
+
 #include "eval.cuh"
 
 namespace pj6 {
@@ -56,9 +58,12 @@ enum : int { D_H1 = 0, D_HA, D_HB, D_HT, D_SCP, D_CPAVG, D_WDCP, NPART = 7 };
 enum : int { SP_SLOTS = 6, E_C = 0, E_DB = 2, E_WA = 2, E_WT = 4, O_B = 0, O_WB = 0, O_HW = 2, O_CP = 4, E_Y = E_C };
 // reaction rows: even slots (net, X1) at E + {0, 2}, odd slots (tT, dH) at (E ^ RB) + {0, 2}
 enum : int { RX_SLOTS = 4, E_NET = 0, E_X1 = 2, O_TT = 0, O_DH = 2 };
-enum : int { CHB = 512, NSLOT = 3 };
-enum : unsigned { F_NULL = 1u << 28, F_CORR = 1u << 29, D_FIRST = 1u << 28, D_FINAL = 1u << 29, D_VALID = 1u << 30,
-                  NONE32 = 0xFFFFFFFFu };
+#ifndef PJ_NSLOT
+#define PJ_NSLOT 3
+#endif
+enum : int { CHB = 512, NSLOT = PJ_NSLOT };
+enum : unsigned { F_NULL = 1u << 28, F_CORR = 1u << 29, D_CIN = 1u << 28, D_COUT = 1u << 29, D_VALID = 1u << 30, D_HDR = 1u << 31,
+                  CLS_CARRY = 7u, NONE32 = 0xFFFFFFFFu };
 
 #define LDS(OFF, ...) mem.template ld<(OFF)>(__VA_ARGS__)
 #define STS(OFF, ...) mem.template st<(OFF)>(__VA_ARGS__)
@@ -111,6 +116,9 @@ struct Stream {
     unsigned left;       // chunks not requested yet (over all groups of this block)
     unsigned nxt;        // chunk of the stream the next request fetches
     unsigned slot, par, rec;
+    unsigned pend;       // slot + 1 whose re-arming is due, 0 = none
+    unsigned guard;      // shared address of a word that always holds zero
+    unsigned chunks;     // chunks consumed so far (development checks)
     bool lane0;
 
     __device__ __forceinline__ void request(unsigned s)
@@ -122,9 +130,9 @@ struct Stream {
         nxt = nxt + 1 == nch ? 0 : nxt + 1;
         --left;
     }
-    __device__ __forceinline__ void start(unsigned ring_, unsigned word, unsigned mbar_, const char* src_, unsigned nch_, unsigned total, bool lane0_)
+    __device__ __forceinline__ void start(unsigned ring_, unsigned word, unsigned mbar_, unsigned guard_, const char* src_, unsigned nch_, unsigned total, bool lane0_)
     {
-        ring0 = ring_; ring = ring_ + word; mbar = mbar_; src = src_; nch = nch_; left = total; nxt = 0; slot = 0; par = 0; rec = 0; lane0 = lane0_;
+        guard = guard_; ring0 = ring_; ring = ring_ + word; mbar = mbar_; src = src_; nch = nch_; left = total; nxt = 0; slot = 0; par = 0; rec = 0; pend = 0; chunks = 0; lane0 = lane0_;
         if (lane0) {
             for (unsigned s = 0; s < NSLOT; ++s) mbar_init(mbar + s * 8, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -133,27 +141,74 @@ struct Stream {
         __syncwarp();
         for (unsigned s = 0; s < NSLOT && left; ++s) request(s);
     }
+    // The chunk in `slot` has been handed out.  Its slot is re-armed (the next bulk copy into it is
+    // issued) not here but by flush(), which the next wait_chunk() or align() calls: by then the
+    // records of the chunk have been *used*, so every ld.shared of the slot has returned and the copy
+    // (async proxy) cannot overtake a read (generic proxy) still in flight.  Measured on a B200:
+    // re-arming right after the last ld.shared corrupts about one record per hundred groups; a
+    // fence.proxy.async in between costs a MEMBAR per chunk.
     __device__ __forceinline__ void release()
     {
         rec = 0;
+        ++chunks;
         par ^= 1u << slot;
-        __syncwarp();                     // every lane has read the chunk before it is overwritten
-        if (left) request(slot);
+        pend = slot + 1;
         slot = slot + 1 == NSLOT ? 0 : slot + 1;
     }
+    __device__ __forceinline__ void flush()
+    {
+        if (pend) {
+            __syncwarp();
+            // Shared-memory loads of a warp complete in order: once this load of a word that is always
+            // zero has returned (the branch needs its value), every earlier ld.shared of the slot has
+            // returned too, whether or not its value has been used yet.
+            unsigned g;
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(g) : "r"(guard) : "memory");
+            if (g != 0u) __trap();
+            if (left) request(pend - 1);
+            pend = 0;
+        }
+    }
+    __device__ __forceinline__ void wait_chunk()
+    {
+        flush();
+        mbar_wait(mbar + slot * 8, (par >> slot) & 1u);
+    }
+    // address of record i of the current chunk (this sub-group's word)
+    __device__ __forceinline__ unsigned rec_addr(unsigned i) const { return ring + slot * CHB + i * RECB; }
     __device__ __forceinline__ uint4 get()
     {
-        if (rec == 0) mbar_wait(mbar + slot * 8, (par >> slot) & 1u);
-        const uint4 v = lds128(ring + slot * CHB + rec * RECB);
+        if (rec == 0) wait_chunk();
+        const uint4 v = lds128(rec_addr(rec));
         if (++rec == CHR) release();
         return v;
     }
-    // the stream of a group ends with its last chunk: skip what is left of it
-    __device__ __forceinline__ void end_group()
+    // skip to the next chunk boundary (the phases that take whole chunks start on one; the stream of
+    // a group ends with its last chunk)
+    __device__ __forceinline__ void align()
     {
         if (rec != 0) release();
+        flush();
     }
 };
+
+#ifdef PJ_DEV
+// development: a record that fails a sanity check is written to io.dbg_clk = {count, 16 words per event}
+__device__ __noinline__ void dbg_event(long long* buf, int phase, long long grp, unsigned chunks, unsigned rec, unsigned slot,
+                                       uint4 v, unsigned extra)
+{
+    if (!buf) return;
+    const unsigned long long i = atomicAdd((unsigned long long*)buf, 1ull);
+    if (i >= 64) return;
+    long long* o = buf + 1 + i * 16;
+    o[0] = blockIdx.x; o[1] = threadIdx.x; o[2] = phase; o[3] = grp; o[4] = chunks; o[5] = rec; o[6] = slot;
+    o[7] = v.x; o[8] = v.y; o[9] = v.z; o[10] = v.w; o[11] = extra;
+    __threadfence_system();
+}
+#define PJ_CHECK(COND, PHASE, V, EXTRA) if (!(COND)) dbg_event(io.dbg_clk, PHASE, grp, rd.chunks, rd.rec, rd.slot, V, EXTRA)
+#else
+#define PJ_CHECK(COND, PHASE, V, EXTRA)
+#endif
 
 __device__ __forceinline__ double dbl(unsigned lo, unsigned hi) { return __hiloint2double((int)hi, (int)lo); }
 // +1.0 / -1.0 from bit 15 of a 16-bit entry
@@ -569,7 +624,7 @@ k_jac6(const __grid_constant__ Tables tb, const __grid_constant__ Plan6 pl, cons
     const int n_c = __ldg(hd + 4), n_t = __ldg(hd + 5), n_seg = __ldg(hd + 6), n_e = __ldg(hd + 7);
     const long long my_groups = (long long)blockIdx.x < ngroups ? (ngroups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     Stream<NSUB> rd;
-    rd.start(ws0 + pl.ring + warp * (NSLOT * CHB), sub * 16, ws0 + pl.mbar + warp * (NSLOT * 8),
+    rd.start(ws0 + pl.ring + warp * (NSLOT * CHB), sub * 16, ws0 + pl.mbar + warp * (NSLOT * 8), ws0 + (pl.oRAW + tb.nraw * GS) * 8,
              reinterpret_cast<const char*>(pl.str) + (size_t)h_ch0 * CHB, (unsigned)h_nch,
              (unsigned)(my_groups * h_nch), lane == 0);
 
@@ -720,6 +775,7 @@ k_jac6(const __grid_constant__ Tables tb, const __grid_constant__ Plan6 pl, cons
                 const uint4 q0 = rd.get(), q1 = rd.get(), q2 = rd.get(), q3 = rd.get();
                 const bool valid = !(q2.x & F_NULL);
                 const int p = (int)(q3.w & 0xFFFFu);
+                PJ_CHECK(p < tb.nr && (q2.y & 0xFFFFu) <= nsp_f && (q2.w >> 16) <= nsp_f, 1, q2, q3.w);
                 if (r < n_pm) {
                     reaction<GS>(mem, tb, pl, aSP, aRX, aXC, aRAW, aSC, p, valid, q0, q1, q2, q3, T, logT, iT, rho_inv, nmwr);
                 } else {
@@ -741,6 +797,7 @@ k_jac6(const __grid_constant__ Tables tb, const __grid_constant__ Plan6 pl, cons
             for (int rnd = 0; rnd < n_c; ++rnd) {
                 const uint4 h = rd.get();
                 const int nm = (h.y >> 8) & 0xFF, nx = (h.y >> 16) & 0xFF;
+                PJ_CHECK((h.x == NONE32 || h.x <= (unsigned)nsp * SPB + RB) && nm < 40 && nx < 40 && (h.y & 0xFF) <= 1u, 2, h, 0);
                 V aN = zero, aT = zero, a1 = zero, ac = zero;
                 for (int u = 0; u < nm; ++u) {
                     const uint4 e = rd.get();
@@ -789,6 +846,7 @@ k_jac6(const __grid_constant__ Tables tb, const __grid_constant__ Plan6 pl, cons
             for (int rnd = 0; rnd < n_t; ++rnd) {
                 const uint4 h = rd.get();
                 const int n = (int)h.y;
+                PJ_CHECK((h.x & 0xFFFFu) < (unsigned)nsp && n < 100 && h.z == 0u && h.w == 0u, 3, h, 0);
                 V acc0 = zero, acc1 = zero;
                 for (int u = 0; u < n; ++u) {
                     const uint4 e = rd.get();
@@ -843,33 +901,102 @@ k_jac6(const __grid_constant__ Tables tb, const __grid_constant__ Plan6 pl, cons
             // the next group's phase A0 (its inputs come from HBM: latency hidden behind DE)
             if (grp + gridDim.x < ngroups) phase_a0(grp + gridDim.x, buf ^ 1);
         }
-        for (int sg_ = 0; sg_ < n_seg; ++sg_) {
-            // a segment: every sub-group walks a piece of one Jacobian row with W_k a_k, W_k b_k, W_k in registers
-            const uint4 h = rd.get();
-            const int L = (int)(h.y >> 16);
-            const bool on = h.x != NONE32;
-            const unsigned x = aSP + (on ? h.x : 0u);
-            const V wa = LDS(E_WA * RB, x), wb = LDS(O_WB * RB, x ^ RB);
-            const double wk = dbl(h.z, h.w);
-            if (h.y & 1u) store(((h.y >> 8) & 0xFFu) + 1u, LDS(E_WT * RB, x), on);     // temperature column: W_k * T-term
-            V p = zero, m = zero;
-            for (int t = 0; t < L; ++t) {
-                const uint4 r = rd.get();
-                const unsigned c = (r.x >> 24) & 7u;                 // entries of this step (warp-uniform)
-                if (r.x & D_FIRST) { p = zero; m = zero; }
-#define PJ_ENT(X, ACC) { const unsigned x_ = (X); ACC = vfma(sgn15(x_), LDS(0, aRAW + (x_ & 0x7FFFu) * RB), ACC); }
-                if (c >= 1) PJ_ENT(r.y & 0xFFFFu, p)
-                if (c >= 2) PJ_ENT(r.y >> 16, m)
-                if (c >= 4) { PJ_ENT(r.z & 0xFFFFu, p) PJ_ENT(r.z >> 16, m) }
-                if (c >= 6) { PJ_ENT(r.w & 0xFFFFu, p) PJ_ENT(r.w >> 16, m) }
-#undef PJ_ENT
-                if (r.x & D_FINAL) {
-                    const V cf = LDS(0, aCF + ((r.x >> 12) & 0xFF0u));
-                    const V tt = vfma(wk, vadd(p, m), wa);
-                    store(r.x & 0xFFFFu, vfma(cf.y, wb, vmul(cf.x, tt)), (r.x & D_VALID) != 0u);
+        // Elements by rows.  A segment's header hands every sub-group the species rows of one Jacobian
+        // row (W_k a_k, W_k b_k, W_k stay in registers), a second record the number of records of
+        // each kind; then the records kind by kind (plan6.py): K7 / K6 / K4 one element with up to six
+        // signed raw rows, K2 three elements with two, K1 five with one, K0 sixteen dense-only ones.
+        // The element index follows from the column: e = col * NSP + k + 1; col = 0: no element.
+        auto de_phase = [&](auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
+            V wa = zero, wb = zero, cp_ = zero, cm_ = zero;      // row constants; accumulators carried between records
+            double wk = 0.0;
+            unsigned kp1 = 0;
+            const unsigned k3ff = 0x3FF00000u;
+            // +1.0 / -1.0 from bit 15 of the low (shift = 16) or high (shift = 0) half of a record word
+            auto sgn = [&](unsigned w, int shift) {
+                unsigned hi;
+                asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(hi) : "r"(w << shift), "r"(k3ff));
+                return __hiloint2double((int)hi, 0);
+            };
+            auto lo = [&](unsigned w) { return LDS(0, aRAW + (w & 0x7FFFu) * RB); };
+            auto hi = [&](unsigned w) { return LDS(0, aRAW + ((w >> 16) & 0x7FFFu) * RB); };
+            auto put = [&](unsigned e, V v, unsigned on) {
+                char* o;
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(o) : "r"(e), "r"(ld8), "l"(out0));
+                if (FAST) {
+                    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.f64 [%0], {%1, %2};\n\t}"
+                                 ::"l"(o), "d"(v.x), "d"(v.y), "r"(on) : "memory");
+                } else if (on) {
+                    if (ok0) *reinterpret_cast<double*>(o) = v.x;
+                    if (ok1) *reinterpret_cast<double*>(o + second) = v.y;
+                }
+            };
+            // element of column col = (1 / W_j) tt + (1 / W_N) W_k b_k,  tt = W_k a_k + W_k S_kj
+            auto finish = [&](unsigned col, V tt) {
+                const V cf = LDS(0, aCF + col * 16);
+                put(col * (unsigned)nsp + kp1, vfma(cf.y, wb, vmul(cf.x, tt)), col);
+            };
+            for (int sg_ = 0; sg_ < n_seg; ++sg_) {
+                const uint4 h = rd.get(), cw = rd.get();
+                {
+                    const unsigned x = aSP + h.y;
+                    wa = LDS(E_WA * RB, x);
+                    wb = LDS(O_WB * RB, x ^ RB);
+                    wk = dbl(h.z, h.w);
+                    kp1 = ((h.x >> 8) & 0xFFu) + 1u;
+                    put(kp1, LDS(E_WT * RB, x), h.x & 1u);       // temperature column: W_k * T-term
+                }
+                const int n7 = cw.x & 0xFF, n6 = (cw.x >> 8) & 0xFF, n4 = (cw.x >> 16) & 0xFF, n2 = cw.x >> 24;
+                const int n1 = cw.y & 0xFF, n0 = (cw.y >> 8) & 0xFF;
+                for (int i = 0; i < n7; ++i) {                   // lists longer than six span records
+                    const uint4 r = rd.get();
+                    const V e0 = lo(r.y), e1 = hi(r.y), e2 = lo(r.z), e3 = hi(r.z), e4 = lo(r.w), e5 = hi(r.w);
+                    V p = zero, m = zero;
+                    if (r.x & D_CIN) { p = cp_; m = cm_; }
+                    p = vfma(sgn(r.w, 16), e4, vfma(sgn(r.z, 16), e2, vfma(sgn(r.y, 16), e0, p)));
+                    m = vfma(sgn(r.w, 0), e5, vfma(sgn(r.z, 0), e3, vfma(sgn(r.y, 0), e1, m)));
+                    if (r.x & D_COUT) { cp_ = p; cm_ = m; }
+                    else finish(r.x & 0xFFu, vfma(wk, vadd(p, m), wa));
+                }
+                for (int i = 0; i < n6; ++i) {
+                    const uint4 r = rd.get();
+                    const V e0 = lo(r.y), e1 = hi(r.y), e2 = lo(r.z), e3 = hi(r.z), e4 = lo(r.w), e5 = hi(r.w);
+                    const V p = vfma(sgn(r.w, 16), e4, vfma(sgn(r.z, 16), e2, vmul(sgn(r.y, 16), e0)));
+                    const V m = vfma(sgn(r.w, 0), e5, vfma(sgn(r.z, 0), e3, vmul(sgn(r.y, 0), e1)));
+                    finish(r.x & 0xFFu, vfma(wk, vadd(p, m), wa));
+                }
+                for (int i = 0; i < n4; ++i) {
+                    const uint4 r = rd.get();
+                    const V e0 = lo(r.y), e1 = hi(r.y), e2 = lo(r.z), e3 = hi(r.z);
+                    const V p = vfma(sgn(r.z, 16), e2, vmul(sgn(r.y, 16), e0)), m = vfma(sgn(r.z, 0), e3, vmul(sgn(r.y, 0), e1));
+                    finish(r.x & 0xFFu, vfma(wk, vadd(p, m), wa));
+                }
+                for (int i = 0; i < n2; ++i) {
+                    const uint4 r = rd.get();
+                    const V a0 = lo(r.y), a1 = hi(r.y), b0 = lo(r.z), b1 = hi(r.z), c0 = lo(r.w), c1 = hi(r.w);
+                    finish(r.x & 0xFFu, vfma(wk, vfma(sgn(r.y, 0), a1, vmul(sgn(r.y, 16), a0)), wa));
+                    finish((r.x >> 8) & 0xFFu, vfma(wk, vfma(sgn(r.z, 0), b1, vmul(sgn(r.z, 16), b0)), wa));
+                    finish((r.x >> 16) & 0xFFu, vfma(wk, vfma(sgn(r.w, 0), c1, vmul(sgn(r.w, 16), c0)), wa));
+                }
+                for (int i = 0; i < n1; ++i) {
+                    const uint4 r = rd.get();
+                    const V a0 = hi(r.y), a1 = lo(r.z), a2 = hi(r.z), a3 = lo(r.w), a4 = hi(r.w);
+                    finish(r.x & 0xFFu, vfma(wk, vmul(sgn(r.y, 0), a0), wa));
+                    finish((r.x >> 8) & 0xFFu, vfma(wk, vmul(sgn(r.z, 16), a1), wa));
+                    finish((r.x >> 16) & 0xFFu, vfma(wk, vmul(sgn(r.z, 0), a2), wa));
+                    finish(r.x >> 24, vfma(wk, vmul(sgn(r.w, 16), a3), wa));
+                    finish(r.y & 0xFFu, vfma(wk, vmul(sgn(r.w, 0), a4), wa));
+                }
+                for (int i = 0; i < n0; ++i) {
+                    const uint4 r = rd.get();
+                    const unsigned w4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) finish((w4[j >> 2] >> (8 * (j & 3))) & 0xFFu, wa);
                 }
             }
-        }
+        };
+        if (__all_sync(0xffffffffu, fast)) de_phase(std::true_type{});
+        else de_phase(std::false_type{});
         if (n_e) {
             // the energy-equation row (cj:3095-3254) from the gathers of phase C and warp 0's scalars
             if (warp != 0) asm volatile("bar.sync 1, %0;" ::"r"(pl.t_sync) : "memory");
@@ -878,6 +1005,7 @@ k_jac6(const __grid_constant__ Tables tb, const __grid_constant__ Plan6 pl, cons
             for (int i = 0; i < n_e; ++i) {
                 const uint4 r = rd.get();
                 const unsigned col = r.x;
+                PJ_CHECK(col < (unsigned)nsp && r.y == 0u, 6, r, (unsigned)i);
                 const bool on = col != 0u;
                 const unsigned j = on ? col - 1u : 0u;
                 const V cf = LDS(0, aCF + col * 16);
@@ -889,7 +1017,7 @@ k_jac6(const __grid_constant__ Tables tb, const __grid_constant__ Plan6 pl, cons
                 store(col * (unsigned)nsp, v, on);
             }
         }
-        rd.end_group();
+        rd.align();
         __syncthreads();
     }
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -34,7 +35,9 @@ struct pyjac_mech {
     std::vector<void*> dev_allocs;
     int user_bpsm = 0;
     int bpsm[3] = {0, 0, 0};         // blocks per SM per mode (0 = not configured yet)
-    long long launches = 0;
+    std::atomic<long long> launches{0};
+    std::mutex mu;                   // launch configuration and the shared scratch of a wsg plan
+    std::vector<int> fwd_map, back_map;   // species: internal position -> original index and back (apply_mask)
     char* ws = nullptr;              // per-block working sets of a plan with wsg = 1
     size_t ws_bytes = 0;
     cudaEvent_t ws_ev = nullptr;     // orders the launches that share `ws` across streams
@@ -175,7 +178,10 @@ int launch(pyjac_mech* m, int mode, const IO& io_in, cudaStream_t st)
         int rc6 = ensure_dyn_smem(fn6, m->device, (size_t)p6.bytes, false);
         if (rc6) return rc6;
         const long long groups6 = ((long long)io.n + p6.gs - 1) / p6.gs;
-        const int grid6 = (int)std::min<long long>(groups6, (long long)m->sm_count);
+        int grid6 = (int)std::min<long long>(groups6, (long long)m->sm_count);
+#ifdef PJ_DEV
+        if (m->user_bpsm < 0) grid6 = std::min(grid6, -m->user_bpsm);      // development: explicit grid
+#endif
         void* args6[3] = {(void*)&m->tb, (void*)&m->plan6, (void*)&io};
         CU(cudaLaunchKernel(fn6, dim3(grid6), dim3(p6.nt), args6, (size_t)p6.bytes, st));
         ++m->launches;
@@ -190,6 +196,7 @@ int launch(pyjac_mech* m, int mode, const IO& io_in, cudaStream_t st)
         int rcs = ensure_dyn_smem(fn, m->device, bytes, pl.wsg != 0);
         if (rcs) return rcs;
     }
+    std::unique_lock<std::mutex> lk(m->mu);          // held to the end for a wsg plan (shared scratch), else only here
     if (!m->bpsm[mode]) {
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.nt, bytes));
@@ -199,6 +206,7 @@ int launch(pyjac_mech* m, int mode, const IO& io_in, cudaStream_t st)
     }
     const long long groups = ((long long)io.n + pl.gs - 1) / pl.gs;
     const int grid = (int)std::min<long long>(groups, (long long)m->sm_count * m->bpsm[mode]);
+    if (!pl.wsg) lk.unlock();
     if (pl.wsg) {
         // one working set per resident block, in global memory (L1 / L2 hold what is hot); the
         // launches of one handle share it, so an event orders them across streams
@@ -265,6 +273,60 @@ int ensure_staging(pyjac_mech* m, size_t pin, size_t din, size_t dout)
     return PYJAC_OK;
 }
 
+// ---- staging of the scalar entry points: one slot per concurrent caller.  The reference's eval_jacob &c.
+// are re-entrant (tester.c.in:24-29 calls eval_jacob inside an OpenMP loop); here every call borrows a
+// slot (stream + pinned and device buffers) from a pool, so concurrent host threads do not share staging.
+struct Slot {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    double *h = nullptr, *d_in = nullptr, *d_out = nullptr;
+    size_t hb = 0, ib = 0, ob = 0;
+};
+std::vector<Slot*> g_slots;        // free slots
+std::mutex g_slot_mu;
+
+void slot_free(Slot* s)
+{
+    if (s->h) cudaFreeHost(s->h);
+    if (s->d_in) cudaFree(s->d_in);
+    if (s->d_out) cudaFree(s->d_out);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+}
+
+int slot_acquire(int device, size_t hb, size_t ib, size_t ob, Slot** out)
+{
+    Slot* s = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mu);
+        for (size_t i = 0; i < g_slots.size(); ++i)
+            if (g_slots[i]->device == device) { s = g_slots[i]; g_slots.erase(g_slots.begin() + i); break; }
+    }
+    if (!s) { s = new Slot(); s->device = device; }
+    *out = s;
+    if (!s->st) CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    if (hb > s->hb) { if (s->h) cudaFreeHost(s->h); s->h = nullptr; s->hb = 0; CU(cudaMallocHost((void**)&s->h, hb)); s->hb = hb; }
+    if (ib > s->ib) { if (s->d_in) cudaFree(s->d_in); s->d_in = nullptr; s->ib = 0; CU(cudaMalloc((void**)&s->d_in, ib)); s->ib = ib; }
+    if (ob > s->ob) { if (s->d_out) cudaFree(s->d_out); s->d_out = nullptr; s->ob = 0; CU(cudaMalloc((void**)&s->d_out, ob)); s->ob = ob; }
+    return PYJAC_OK;
+}
+
+void slot_release(Slot* s)
+{
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    g_slots.push_back(s);
+}
+
+struct SlotLease {                 // returns the slot to the pool when the entry point leaves
+    Slot* s = nullptr;
+    ~SlotLease() { if (s) slot_release(s); }
+};
+
+// tables registered by a per-mechanism stub library (libgen.generate_library): the mechanism the
+// reference-named entry points use when none was selected explicitly
+const void* g_reg_blob = nullptr;
+size_t g_reg_len = 0;
+
 }  // namespace
 
 extern "C" {
@@ -283,15 +345,34 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     if (!out) return fail(PYJAC_EINVAL, "out is NULL");
     *out = nullptr;
     if (!pjt::valid(blob, len)) return fail(PYJAC_EINVAL, "not a PJB200T1 table blob");
-    if (pyjac_device_count() <= 0) return fail(PYJAC_ENODEVICE, "no CUDA device available (no CPU fallback exists)");
-    if (device < 0) CU(cudaGetDevice(&device));
-    DeviceGuard guard(device);
     const pjt::Entry* de = pjt::find(blob, "dims");
     const pjt::Entry* ce = pjt::find(blob, "cst");
     if (!de || de->dtype != 1 || de->count < 16 || !ce || ce->dtype != 0 || ce->count < 2)
         return fail(PYJAC_EINVAL, "table blob lacks dims / cst");
     const int* d = (const int*)((const char*)blob + de->offset);
     const double* c = (const double*)((const char*)blob + ce->offset);
+    {
+        // a blob written by another version of tables.py / plan.py would be misread silently: refuse it
+        const pjt::Entry* me = pjt::find(blob, "meta");
+        const int* mv = me && me->dtype == 1 && me->count >= 3 ? (const int*)((const char*)blob + me->offset) : nullptr;
+        if (!mv || mv[0] != pjt::SCHEMA_VERSION || mv[1] != pjt::PLAN5_VERSION ||
+            (pjt::find(blob, "p6_cfg") && mv[2] != pjt::PLAN6_VERSION))
+            return fail(PYJAC_EINVAL, "table blob was written for another version of the library (rebuild the tables)");
+        // table lengths against the dimensions they are indexed with
+        struct { const char* name; long long count; } want[] = {
+            {"sp_w", d[0]}, {"sp_iw", d[0]}, {"sp_ruw", d[0]}, {"sp_tmid", d[0]}, {"sp_nasa", 32LL * d[0]},
+            {"p5_rx", 16LL * d[1]}, {"p5_rxout", 4LL * d[1]}, {"red_off", d[0] + 1LL}, {"plog_off", d[1] + 1LL},
+            {"cheb_off", d[1] + 1LL}, {"sp_fwd_map", d[0]}, {"p5_colfac", 2LL * d[0]}};
+        for (const auto& w_ : want) {
+            const pjt::Entry* e = pjt::find(blob, w_.name);
+            if (!e || e->count < w_.count) return fail(PYJAC_EINVAL, std::string("table blob: ") + w_.name + " is missing or too short");
+        }
+        if (d[0] < 2 || d[1] < 1 || d[4] < 0 || d[8] < 0 || d[8] > d[1] || d[9] != d[1] - d[8])
+            return fail(PYJAC_EINVAL, "table blob: inconsistent dimensions");
+    }
+    if (pyjac_device_count() <= 0) return fail(PYJAC_ENODEVICE, "no CUDA device available (no CPU fallback exists)");
+    if (device < 0) CU(cudaGetDevice(&device));
+    DeviceGuard guard(device);
     pyjac_mech* m = new pyjac_mech();
     m->device = device;
     Tables& t = m->tb;
@@ -316,11 +397,33 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
             int* o = &pl.gs;
             for (int i = 0; i < 14; ++i) o[i] = c5[i];
             pl.wsg = pe->count > 14 ? c5[14] : 0;
-            if (!kernel_for(pl.gs, pj::M_JAC, pl.nt, pl.wsg) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub)
+            // the regions of the working set (rows of gs doubles) must lie inside `total`
+            const long long gs_ = pl.gs, nraw_ = d[4];
+            const bool regions_ok = pl.oSP >= 0 && pl.oSP + (d[0] + 1LL) * pj5::SP_SLOTS * gs_ <= pl.total &&
+                                    pl.oRX >= 0 && pl.oRX + (d[1] + 2LL) * pj5::RX_SLOTS * gs_ <= pl.total &&
+                                    pl.oRAW >= 0 && pl.oRAW + (nraw_ + 2) * gs_ <= pl.total &&
+                                    pl.oSC >= 0 && pl.oSC + (long long)pj5::NQ * gs_ <= pl.total &&
+                                    pl.oPA >= 0 && pl.oPA + (long long)pl.nw * pj5::NPART * gs_ <= pl.total &&
+                                    pl.oCF >= 0 && pl.oCF + 2LL * d[0] <= pl.total;
+            if (!kernel_for(pl.gs, pj::M_JAC, pl.nt, pl.wsg) || pl.nt != pl.nw * 32 || pl.nt < 64 || pl.nt > 512 || pl.nsub * pl.gs != 64 || pl.coop < 1 || pl.coop > pl.nsub || pl.tcoop < 1 || pl.tcoop > pl.nsub || !regions_ok)
                 rc = fail(PYJAC_EINVAL, "bad plan configuration");
         }
     }
     if (!rc) m->plan.rx_out = m->tb.rx_out;
+    if (!rc) {
+        // species permutation of the mechanism (utils.get_species_mappings, utils.py:55-91) for apply_mask
+        const pjt::Entry* fe = pjt::find(blob, "sp_fwd_map");
+        if (!fe || fe->dtype != 1 || fe->count != t.nsp) rc = fail(PYJAC_EINVAL, "table blob lacks sp_fwd_map");
+        else {
+            const int* f = (const int*)((const char*)blob + fe->offset);
+            m->fwd_map.assign(f, f + t.nsp);
+            m->back_map.assign(t.nsp, -1);
+            for (int i = 0; i < t.nsp && !rc; ++i) {
+                if (f[i] < 0 || f[i] >= t.nsp || m->back_map[f[i]] >= 0) rc = fail(PYJAC_EINVAL, "sp_fwd_map is not a permutation");
+                else m->back_map[f[i]] = i;
+            }
+        }
+    }
     UP(plan.rx, "p5_rx", int4, 1); UP(plan.eff_off, "p5_eff_off", int, 1); UP(plan.eff, "p5_eff", int4, 1);
     UP(plan.b_off, "p5_b_off", int, 1); UP(plan.b_npm, "p5_b_npm", int, 1); UP(plan.b_item, "p5_b_item", int, 1);
     UP(plan.c_off, "p5_c_off", int, 1); UP(plan.c_item, "p5_c_item", int4, 1); UP(plan.c_str, "p5_c_str", uint2, 1);
@@ -384,13 +487,16 @@ int pyjac_mech_dims(const pyjac_mech* m, int dims[4])
 
 int pyjac_mech_tune(pyjac_mech* m, int blocks_per_sm)
 {
-    if (!m || blocks_per_sm < 0) return fail(PYJAC_EINVAL, "bad argument");
+#ifndef PJ_DEV
+    if (blocks_per_sm < 0) return fail(PYJAC_EINVAL, "bad argument");
+#endif
+    if (!m) return fail(PYJAC_EINVAL, "bad argument");
     m->user_bpsm = blocks_per_sm;
     m->bpsm[0] = m->bpsm[1] = m->bpsm[2] = 0;    // re-derive at next launch
     return PYJAC_OK;
 }
 
-long long pyjac_mech_launches(const pyjac_mech* m) { return m ? m->launches : 0; }
+long long pyjac_mech_launches(const pyjac_mech* m) { return m ? m->launches.load() : 0; }
 
 int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
                          long long y_ss, long long y_sv, double* d_jac, int jac_layout,
@@ -402,8 +508,10 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
     IO io{};
     io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
     io.jac = d_jac; io.jac_layout = jac_layout; io.jac_ld = jac_ld;
-    if (const char* dbg = std::getenv("PYJAC_DEBUG_SKIP")) io.dbg_skip = std::atoi(dbg);   // timing experiments only
+#ifdef PJ_DEV        // development builds only (tools/devbuild.sh NAME -DPJ_DEV): phase skipping, per-phase clocks, record checks
+    if (const char* dbg = std::getenv("PYJAC_DEBUG_SKIP")) io.dbg_skip = std::atoi(dbg);
     if (const char* dbg = std::getenv("PYJAC_DEBUG_CLK")) io.dbg_clk = (long long*)std::strtoull(dbg, nullptr, 0);
+#endif
     return launch(m, pj::M_JAC, io, (cudaStream_t)stream);
 }
 
@@ -528,12 +636,48 @@ int pyjac_set_mechanism(pyjac_mech* m)
     return PYJAC_OK;
 }
 
-static pyjac_mech* current_or_die(const char* who)
+int pyjac_register_tables(const void* blob, size_t len)
+{
+    if (!pjt::valid(blob, len)) return fail(PYJAC_EINVAL, "not a PJB200T1 table blob");
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_reg_blob = blob;
+    g_reg_len = len;
+    return PYJAC_OK;
+}
+
+static pyjac_mech* current_or_null()
 {
     pyjac_mech* m;
+    const void* blob;
+    size_t len;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         m = g_current;
+        blob = g_reg_blob;
+        len = g_reg_len;
+    }
+    if (m || !blob) return m;
+    // first use of a library that carries its mechanism (pyjac_register_tables): load it on the
+    // current device; concurrent first calls race benignly for g_current
+    static std::mutex once;
+    std::lock_guard<std::mutex> lk1(once);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_current) return g_current;
+    }
+    pyjac_mech* made = nullptr;
+    if (pyjac_mech_create(blob, len, -1, &made) != PYJAC_OK) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_current = made;
+    return made;
+}
+
+static pyjac_mech* current_or_die(const char* who)
+{
+    pyjac_mech* m = current_or_null();
+    if (!m && g_reg_blob) {
+        std::fprintf(stderr, "%s: %s\n", who, pyjac_last_error());
+        std::exit(1);
     }
     if (!m) {
         std::fprintf(stderr, "%s: no mechanism selected (pyjac_set_mechanism)\n", who);
@@ -554,11 +698,7 @@ static void die_on(int rc, const char* who)
 
 int pyjac_cu_init(int num)
 {
-    pyjac_mech* m;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        m = g_current;
-    }
+    pyjac_mech* m = current_or_null();
     if (!m) return fail(PYJAC_EINVAL, "no mechanism selected (pyjac_set_mechanism)");
     if (num <= 0) return fail(PYJAC_EINVAL, "num must be positive");
     g_cu_num = num;
@@ -632,22 +772,51 @@ void pyjac_cu_cleanup(void)
     }
     if (m) { DeviceGuard guard(m->device); release_staging(m); }
     g_cu_num = 0;
+    std::vector<Slot*> slots;
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mu);
+        slots.swap(g_slots);
+    }
+    for (Slot* s : slots) { DeviceGuard guard(s->device); slot_free(s); }
 }
 
 // ---------------------------------------------------------------- scalar API (batch of 1)
+// Every call borrows its own staging slot (stream, pinned and device buffers): re-entrant and safe to
+// call from concurrent host threads, as the reference's stack-only functions are (tester.c.in:24-29).
+
+static int scalar_state(pyjac_mech* m, double pres, const double* y, double* out, bool jac)
+{
+    const int nsp = m->tb.nsp;
+    const size_t in_b = ((size_t)nsp + 1) * 8, out_b = (jac ? (size_t)nsp * nsp : (size_t)nsp) * 8;
+    DeviceGuard guard(m->device);
+    SlotLease L;
+    int rc = slot_acquire(m->device, std::max(in_b, out_b), in_b, out_b, &L.s);
+    if (rc) return rc;
+    Slot* s = L.s;
+    std::memcpy(s->h, y, (size_t)nsp * 8);
+    s->h[nsp] = pres;
+    CU(cudaMemcpyAsync(s->d_in, s->h, in_b, cudaMemcpyHostToDevice, s->st));
+    if (jac) rc = pyjac_eval_jacob_dev(m, 1, s->d_in + nsp, s->d_in, nsp, 1, s->d_out, PYJAC_JAC_STATE_MAJOR, 0, s->st);
+    else rc = pyjac_dydt_dev(m, 1, s->d_in + nsp, s->d_in, nsp, 1, s->d_out, nsp, 1, s->st);
+    if (rc) { cudaStreamSynchronize(s->st); return rc; }
+    CU(cudaMemcpyAsync(s->h, s->d_out, out_b, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    std::memcpy(out, s->h, out_b);
+    return PYJAC_OK;
+}
 
 void eval_jacob(const double t, const double pres, const double* y, double* jac)
 {
     (void)t;
     pyjac_mech* m = current_or_die("eval_jacob");
-    die_on(pyjac_eval_jacob_host(m, 1, &pres, y, jac), "eval_jacob");
+    die_on(scalar_state(m, pres, y, jac, true), "eval_jacob");
 }
 
 void dydt(const double t, const double pres, const double* y, double* dy)
 {
     (void)t;
     pyjac_mech* m = current_or_die("dydt");
-    die_on(pyjac_dydt_host(m, 1, &pres, y, dy), "dydt");
+    die_on(scalar_state(m, pres, y, dy, false), "dydt");
 }
 
 // one state through the M_RATES kernel; in_conc selects [T, C...] input
@@ -657,24 +826,26 @@ static int scalar_rates(pyjac_mech* m, double T, double pres, const double* in, 
     const Tables& t = m->tb;
     const int nsp = t.nsp;
     const size_t in_d = (size_t)nsp + 2, n_out = (size_t)nsp + t.nr + t.nrev + t.npd, out_d = n_out + 4;
-    int rc = ensure_staging(m, std::max(in_d, out_d) * 8, in_d * 8, out_d * 8);
+    DeviceGuard guard(m->device);
+    SlotLease L;
+    int rc = slot_acquire(m->device, std::max(in_d, out_d) * 8, in_d * 8, out_d * 8, &L.s);
     if (rc) return rc;
-    cudaStream_t st = m->stream[0];
-    double* hp = m->h_pin[0];
+    Slot* s = L.s;
+    double* hp = s->h;
     hp[0] = T;
     std::memcpy(hp + 1, in, (size_t)n_in * 8);
     hp[nsp + 1] = pres;
-    CU(cudaMemcpyAsync(m->d_in[0], hp, in_d * 8, cudaMemcpyHostToDevice, st));
-    double* d = m->d_out[0];
+    CU(cudaMemcpyAsync(s->d_in, hp, in_d * 8, cudaMemcpyHostToDevice, s->st));
+    double* d = s->d_out;
     IO io{};
-    io.n = 1; io.pres = m->d_in[0] + nsp + 1; io.y = m->d_in[0]; io.y_ss = 0; io.y_sv = 1;
+    io.n = 1; io.pres = s->d_in + nsp + 1; io.y = s->d_in; io.y_ss = 0; io.y_sv = 1;
     io.in_conc = in_conc ? 1 : 0;
     io.conc = d; io.fwd = d + nsp; io.rev = d + nsp + t.nr; io.pm = d + nsp + t.nr + t.nrev;
     io.scal3 = d + n_out;
-    rc = launch(m, pj::M_RATES, io, st);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(hp, d, out_d * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    rc = launch(m, pj::M_RATES, io, s->st);
+    if (rc) { cudaStreamSynchronize(s->st); return rc; }
+    CU(cudaMemcpyAsync(hp, d, out_d * 8, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
     if (conc) std::memcpy(conc, hp, (size_t)nsp * 8);
     if (fwd) std::memcpy(fwd, hp + nsp, (size_t)t.nr * 8);
     if (rev) std::memcpy(rev, hp + nsp + t.nr, (size_t)t.nrev * 8);
@@ -718,20 +889,21 @@ void eval_spec_rates(const double* fwd_rates, const double* rev_rates, const dou
     const Tables& t = m->tb;
     const size_t in_d = (size_t)t.nr + t.nrev + t.npd + 1, out_d = (size_t)t.nsp;
     auto run = [&]() -> int {
-        int rc = ensure_staging(m, std::max(in_d, out_d) * 8, in_d * 8, out_d * 8);
+        DeviceGuard guard(m->device);
+        SlotLease L;
+        int rc = slot_acquire(m->device, std::max(in_d, out_d) * 8, in_d * 8, out_d * 8, &L.s);
         if (rc) return rc;
-        cudaStream_t st = m->stream[0];
-        double* hp = m->h_pin[0];
+        Slot* s = L.s;
+        double* hp = s->h;
         std::memcpy(hp, fwd_rates, (size_t)t.nr * 8);
         if (t.nrev) std::memcpy(hp + t.nr, rev_rates, (size_t)t.nrev * 8);
         if (t.npd) std::memcpy(hp + t.nr + t.nrev, pres_mod, (size_t)t.npd * 8);
-        CU(cudaMemcpyAsync(m->d_in[0], hp, in_d * 8, cudaMemcpyHostToDevice, st));
-        pj::k_spec_rates<<<(t.nsp + 63) / 64, 64, 0, st>>>(t, m->d_in[0], m->d_in[0] + t.nr,
-                                                          m->d_in[0] + t.nr + t.nrev, m->d_out[0]);
+        CU(cudaMemcpyAsync(s->d_in, hp, in_d * 8, cudaMemcpyHostToDevice, s->st));
+        pj::k_spec_rates<<<(t.nsp + 63) / 64, 64, 0, s->st>>>(t, s->d_in, s->d_in + t.nr, s->d_in + t.nr + t.nrev, s->d_out);
         CU(cudaGetLastError());
         ++m->launches;
-        CU(cudaMemcpyAsync(hp, m->d_out[0], out_d * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpyAsync(hp, s->d_out, out_d * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
         std::memcpy(sp_rates, hp, (size_t)(t.nsp - 1) * 8);
         *dy_N = hp[t.nsp - 1];
         return PYJAC_OK;
@@ -739,4 +911,73 @@ void eval_spec_rates(const double* fwd_rates, const double* rev_rates, const dou
     die_on(run(), "eval_spec_rates");
 }
 
+// eval_h / eval_u / eval_cv / eval_cp (chem_utils.h of the emitted library, rate_subs.py:1581-1608): NSP
+// mass-based values for one temperature
+static void scalar_thermo(const char* who, int what, double T, double* out)
+{
+    pyjac_mech* m = current_or_die(who);
+    const Tables& t = m->tb;
+    auto run = [&]() -> int {
+        DeviceGuard guard(m->device);
+        SlotLease L;
+        int rc = slot_acquire(m->device, (size_t)t.nsp * 8, 8, (size_t)t.nsp * 8, &L.s);
+        if (rc) return rc;
+        Slot* s = L.s;
+        pj::k_thermo<<<(t.nsp + 63) / 64, 64, 0, s->st>>>(t, T, what, s->d_out);
+        CU(cudaGetLastError());
+        ++m->launches;
+        CU(cudaMemcpyAsync(s->h, s->d_out, (size_t)t.nsp * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        std::memcpy(out, s->h, (size_t)t.nsp * 8);
+        return PYJAC_OK;
+    };
+    die_on(run(), who);
+}
+
+void eval_h(const double T, double* h) { scalar_thermo("eval_h", pj::TH_H, T, h); }
+void eval_u(const double T, double* u) { scalar_thermo("eval_u", pj::TH_U, T, u); }
+void eval_cv(const double T, double* cv) { scalar_thermo("eval_cv", pj::TH_CV, T, cv); }
+void eval_cp(const double T, double* cp) { scalar_thermo("eval_cp", pj::TH_CP, T, cp); }
+
+// apply_mask / apply_reverse_mask (mech_auxiliary.py:188-206): the species permutation that moves the last
+// species to the end, applied to / undone on an array of NSP mass fractions in place.  Host-side data
+// movement of NSP doubles, as in the reference (read_initial_conditions.c:29).
+void apply_mask(double* y_specs)
+{
+    pyjac_mech* m = current_or_die("apply_mask");
+    const int nsp = m->tb.nsp;
+    std::vector<double> tmp(y_specs, y_specs + nsp);
+    for (int i = 0; i < nsp; ++i) y_specs[i] = tmp[m->fwd_map[i]];
+}
+
+void apply_reverse_mask(double* y_specs)
+{
+    pyjac_mech* m = current_or_die("apply_reverse_mask");
+    const int nsp = m->tb.nsp;
+    std::vector<double> tmp(y_specs, y_specs + nsp);
+    for (int i = 0; i < nsp; ++i) y_specs[i] = tmp[m->back_map[i]];
+}
+
 }  // extern "C"
+
+// ---------------------------------------------------------------- the reference's batched GPU host API
+// pyjac/pywrap/pyjacob.cuh:6-10 declares init / run / cleanup with C++ linkage (the header is included
+// by pyjacob.cu and by the Cython C++ extension, pyjacob_cuda_wrapper.pyx:5-10): the same three symbols,
+// same signatures, so that a build of the reference's cu_pyjacob wrapper links against this library.
+int init(int num)
+{
+    const int padded = pyjac_cu_init(num);
+    if (padded < 0) {
+        std::fprintf(stderr, "init: %s\n", pyjac_last_error());
+        std::exit(1);
+    }
+    return padded;
+}
+
+void run(int num, int padded, const double* pres, const double* mass_frac, double* conc, double* fwd_rxn_rates,
+         double* rev_rxn_rates, double* pres_mod, double* spec_rates, double* dy, double* jac)
+{
+    pyjac_cu_run(num, padded, pres, mass_frac, conc, fwd_rxn_rates, rev_rxn_rates, pres_mod, spec_rates, dy, jac);
+}
+
+void cleanup() { pyjac_cu_cleanup(); }

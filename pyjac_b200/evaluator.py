@@ -35,8 +35,8 @@ class Evaluator:
         """gs / threads: states per thread block and block size of the Jacobian kernel's plan
         (pyjac_b200/plan.py); 0 = automatic.  ws_global: working set of a block in global memory
         instead of shared memory (None = only for mechanisms too large for shared memory).
-        streams: False = eval_jacob on the schedule tables of k_eval instead of the record streams of
-        k_jac6 (pyjac_b200/plan6.py)."""
+        streams: True = eval_jacob on the record streams of k_jac6 (pyjac_b200/plan6.py) instead of the
+        schedule tables of k_eval (the default, measured faster)."""
         import torch
         self._torch = torch
         self.mech = mech

@@ -47,6 +47,18 @@ SIGNATURES = {
     'eval_rxn_rates': (None, [c_double, c_double, c_void_p, c_void_p, c_void_p]),
     'get_rxn_pres_mod': (None, [c_double, c_double, c_void_p, c_void_p]),
     'eval_spec_rates': (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'eval_h': (None, [c_double, c_void_p]),
+    'eval_u': (None, [c_double, c_void_p]),
+    'eval_cv': (None, [c_double, c_void_p]),
+    'eval_cp': (None, [c_double, c_void_p]),
+    'apply_mask': (None, [c_void_p]),
+    'apply_reverse_mask': (None, [c_void_p]),
+    'pyjac_register_tables': (c_int, [c_void_p, c_size_t]),
+    # pyjac/pywrap/pyjacob.cuh:6-10, C++ linkage: int init(int); void run(int, int, const double*,
+    # const double*, double* x 7); void cleanup()
+    '_Z4initi': (c_int, [c_int]),
+    '_Z3runiiPKdS0_PdS1_S1_S1_S1_S1_S1_': (None, [c_int, c_int] + [c_void_p] * 9),
+    '_Z7cleanupv': (None, []),
 }
 
 _LIB = None
@@ -61,8 +73,7 @@ def load(path: str = None) -> ctypes.CDLL:
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    # PYJAC_B200_LIB: a development build of the same library (tools/ A/B runs)
-    lib_path = path or os.environ.get('PYJAC_B200_LIB') or libgen.build_library()
+    lib_path = path or libgen.build_library()
     try:
         lib = ctypes.CDLL(lib_path)
     except OSError as exc:
@@ -73,6 +84,16 @@ def load(path: str = None) -> ctypes.CDLL:
         fn.argtypes = args
     if path is None:
         _LIB = lib
+    return lib
+
+
+def use(path: str) -> ctypes.CDLL:
+    """Makes another build of the library (same C ABI) the one every later load() returns; the
+    development tools under tools/ compare builds this way."""
+    global _LIB
+    _LIB = None
+    lib = load(path)
+    _LIB = lib
     return lib
 
 

@@ -60,23 +60,89 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+_STUB_C = '''/* written by pyjac_b200.libgen.generate_library: the mechanism's tables, registered with the fixed
+   CUDA library when this stub is loaded (include/pyjac_b200.h: pyjac_register_tables) */
+#define _GNU_SOURCE
+#include <stddef.h>
+#include <dlfcn.h>
+extern int pyjac_register_tables(const void* blob, size_t len);
+__asm__(".section .rodata\\n.balign 16\\n.global pyjac_b200_tables_start\\npyjac_b200_tables_start:\\n"
+        ".incbin \\"%(pjt)s\\"\\n.global pyjac_b200_tables_end\\npyjac_b200_tables_end:\\n.previous\\n");
+extern const char pyjac_b200_tables_start[], pyjac_b200_tables_end[];
+__attribute__((constructor)) static void pyjac_b200_register(void)
+{
+    pyjac_register_tables(pyjac_b200_tables_start, (size_t)(pyjac_b200_tables_end - pyjac_b200_tables_start));
+}
+
+/* The entry points of the emitted library, forwarded to the CUDA library: a program that links
+   -lc_pyjac alone (performance_tester.py:466-470) resolves them here, so the linker keeps this stub
+   -- and with it the mechanism -- even under --as-needed. */
+#define FWD(ret, name, decl, call)                                         \\
+    ret name decl                                                          \\
+    {                                                                      \\
+        static ret (*fn) decl;                                             \\
+        if (!fn) fn = (ret (*) decl)dlsym(RTLD_NEXT, #name);               \\
+        return fn call;                                                    \\
+    }
+FWD(void, eval_jacob, (const double t, const double p, const double* y, double* jac), (t, p, y, jac))
+FWD(void, dydt, (const double t, const double p, const double* y, double* dy), (t, p, y, dy))
+FWD(void, eval_conc, (const double T, const double p, const double* mf, double* yN, double* mw, double* rho, double* c), (T, p, mf, yN, mw, rho, c))
+FWD(void, eval_rxn_rates, (const double T, const double p, const double* C, double* f, double* r), (T, p, C, f, r))
+FWD(void, get_rxn_pres_mod, (const double T, const double p, const double* C, double* pm), (T, p, C, pm))
+FWD(void, eval_spec_rates, (const double* f, const double* r, const double* pm, double* sp, double* dyN), (f, r, pm, sp, dyN))
+FWD(void, eval_h, (const double T, double* o), (T, o))
+FWD(void, eval_u, (const double T, double* o), (T, o))
+FWD(void, eval_cv, (const double T, double* o), (T, o))
+FWD(void, eval_cp, (const double T, double* o), (T, o))
+FWD(void, apply_mask, (double* y), (y))
+FWD(void, apply_reverse_mask, (double* y), (y))
+'''
+
+
+def lib_name(lang: str, shared: bool = True) -> str:
+    """libc_pyjac / libcu_pyjac, the names of pyjac/libgen/libgen.py:170-186."""
+    return 'lib%s_pyjac%s' % ('cu' if lang == 'cuda' else 'c', '.so' if shared else '.a')
+
+
 def generate_library(lang: str, source_dir: str, obj_dir: Optional[str] = None,
                      out_dir: Optional[str] = None, shared: Optional[bool] = None,
                      finite_difference: bool = False, auto_diff: bool = False) -> str:
     """Signature of pyjac/libgen/libgen.py:322.  ``source_dir`` is a directory written by
-    :func:`pyjac_b200.create_jacobian.create_jacobian` (mechanism.h + mechanism tables);
-    the returned path is the sm_100a library, copied into ``out_dir`` when one is given.
-    Only ``lang='cuda'`` exists -- there is no C (CPU) back end to fall back to."""
-    if lang != 'cuda':
-        raise ValueError("pyjac_b200 only builds the CUDA (sm_100a) library; lang=%r" % (lang,))
+    :func:`pyjac_b200.create_jacobian.create_jacobian` (headers + mechanism tables).
+
+    The reference compiles the generated sources into ``libc_pyjac`` / ``libcu_pyjac``; here the compute
+    library is fixed (``libpyjac_b200.so``, built for sm_100a on first use) and what is produced per
+    mechanism is a *stub* of that name: a small shared library that embeds the table blob, registers
+    it with the CUDA library when loaded and depends on it -- so ``-lc_pyjac`` (what the reference's
+    harness links, performance_tester.py:466-470) brings the entry points of ``jacob.h`` & co. with the
+    mechanism baked in, as the reference's library does.  ``lang`` only picks the name: 'c' =
+    ``libc_pyjac.so`` (the host-callable C entry points), 'cuda' = ``libcu_pyjac.so``; both run on the
+    GPU -- there is no CPU back end.  Returns the stub's path (in ``out_dir``, default ``source_dir``)."""
+    if lang not in ('c', 'cuda'):
+        raise ValueError("lang must be 'c' or 'cuda' (both name the sm_100a library); got %r" % (lang,))
     if finite_difference or auto_diff:
         raise NotImplementedError('finite-difference / autodiff comparison libraries are out of scope')
-    if not os.path.isfile(os.path.join(source_dir, 'mechanism.h')):
-        raise FileNotFoundError('%s holds no mechanism.h; run create_jacobian first' % source_dir)
+    if shared is False:
+        raise NotImplementedError('only shared libraries are built (the stub must run a constructor)')
+    pjt = os.path.abspath(os.path.join(source_dir, 'mechanism.pjt'))
+    if not os.path.isfile(os.path.join(source_dir, 'mechanism.h')) or not os.path.isfile(pjt):
+        raise FileNotFoundError('%s holds no mechanism.h / mechanism.pjt; run create_jacobian first' % source_dir)
     lib = build_library()
-    if out_dir and os.path.abspath(out_dir) != BUILD:
-        os.makedirs(out_dir, exist_ok=True)
-        dst = os.path.join(out_dir, LIB_NAME)
-        shutil.copy2(lib, dst)
-        return dst
-    return lib
+    out_dir = os.path.abspath(out_dir or source_dir)
+    obj_dir = os.path.abspath(obj_dir or out_dir)
+    os.makedirs(out_dir, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
+    stub_c = os.path.join(obj_dir, 'pyjac_b200_stub.c')
+    with open(stub_c, 'w') as fh:
+        fh.write(_STUB_C % {'pjt': pjt})
+    out = os.path.join(out_dir, lib_name(lang))
+    gcc = shutil.which('gcc') or shutil.which('cc')
+    if not gcc:
+        raise RuntimeError('gcc not found: cannot build the per-mechanism stub library')
+    # the stub finds the CUDA library next to itself or where it was built
+    cmd = [gcc, '-shared', '-fPIC', '-O1', stub_c, '-o', out, '-L', BUILD, '-lpyjac_b200',
+           '-Wl,-rpath,$ORIGIN', '-Wl,-rpath,' + BUILD]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('building %s failed:\n%s' % (out, res.stderr))
+    return out

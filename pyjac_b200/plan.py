@@ -27,6 +27,7 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
+PLAN_VERSION = 2             # of the p5_* schedule tables (checked by the library against its own)
 SMEM_LIMIT = 232448          # bytes of dynamic shared memory one block may opt in to (sm_100)
 NSCAL = 24                   # per-state scalar rows: 2 x 8 from phase A0, 5 derived in DE, 2 x P (PLOG)
 NPART = 7                    # per-warp partial sums
@@ -40,7 +41,7 @@ MAX_L2 = 1023
 
 # cost estimates (warp instructions) used only for load balancing
 COST_PLAIN, COST_IRREV, COST_THREE = 215.0, 150.0, 40.0
-COST_PM = {'thd': 300.0, 'lind': 450.0, 'troe': float(__import__('os').environ.get('PYJAC_COST_TROE', 900.0)), 'sri': 1200.0}
+COST_PM = {'thd': 300.0, 'lind': 450.0, 'troe': 900.0, 'sri': 1200.0}
 COST_EFF = 8.0
 COST_PLOG = 120.0
 COST_C_ITEM, COST_C_IT = 90.0, 28.0
@@ -51,11 +52,8 @@ COST_C_ITEM, COST_C_IT = 90.0, 28.0
 COST_S_STEP, COST_S_OVF = 40.0, 11.0
 COST_D_ITEM, COST_D_COL = 63.0, 17.0
 COST_T_ITEM, COST_T_IT = 130.0, 11.0
-if 'PYJAC_COSTS' in __import__('os').environ:        # development: tools/cost_sweep.sh
-    (COST_S_STEP, COST_S_OVF, COST_D_ITEM, COST_D_COL, COST_T_ITEM, COST_T_IT) = (
-        float(v) for v in __import__('os').environ['PYJAC_COSTS'].split(','))
 D_MAX_COLS = 24              # a row with more dense-only columns is cut into several items
-COST_DOTS = float(__import__('os').environ.get('PYJAC_COST_DOTS', 640.0))   # warp 0: energy-equation scalars + the next group's phase A0
+COST_DOTS = 640.0            # warp 0: energy-equation scalars + the next group's phase A0
 
 
 def layout(nsp: int, nr: int, nraw: int, gs: int, nw: int) -> Dict[str, int]:
@@ -128,6 +126,47 @@ def balance_banks(lists: List[List[int]], half) -> None:
             out[s_].append(pool[pick].pop())
     for lst, new in zip(lists, out):
         lst[:] = new
+
+
+def balance_pairs(lists: List[List[int]], half, wild=None) -> None:
+    """Reorder the lists (one per sub-group, all of one length, the order of their entries is free) for
+    rows of 64 bytes: a 16-byte shared-memory access is served a quarter warp at a time, i.e. sub-groups
+    2 i and 2 i + 1 together, and takes one wavefront if their two rows lie on different halves of a
+    128-byte bank line, two otherwise (measured on a B200 with ncu's per-instruction wavefront counts:
+    6.0 wavefronts per ld.shared.v2.f64 for rows of random parity, 4.0 when every pair is split).  So
+    the entries of lists 2 i and 2 i + 1 are matched position by position to opposite halves, as many
+    as there are; ``wild(v)`` -> (the entry on half 0, on half 1) for padding entries that may sit on
+    either half."""
+    for i in range(0, len(lists) - 1, 2):
+        A, B = lists[i], lists[i + 1]
+        assert len(A) == len(B)
+        pools = []
+        for lst in (A, B):
+            h = [[], []]
+            w = []
+            for v in lst:
+                if wild is not None and wild(v) is not None:
+                    w.append(wild(v))
+                else:
+                    h[half(v)].append(v)
+            pools.append((h, w))
+        (ha, wa_), (hb, wb_) = pools
+        outa, outb = [], []
+        for x, y in ((0, 1), (1, 0)):                       # real entries on opposite halves
+            while ha[x] and hb[y]:
+                outa.append(ha[x].pop()); outb.append(hb[y].pop())
+        for x in (0, 1):                                    # a real entry and a padding entry opposite to it
+            while ha[x] and wb_:
+                outa.append(ha[x].pop()); outb.append(wb_.pop()[1 - x])
+            while hb[x] and wa_:
+                outb.append(hb[x].pop()); outa.append(wa_.pop()[1 - x])
+        while wa_ and wb_:
+            outa.append(wa_.pop()[0]); outb.append(wb_.pop()[1])
+        rest_a = ha[0] + ha[1] + [w_[0] for w_ in wa_]       # what is left meets on one half
+        rest_b = hb[0] + hb[1] + [w_[1] for w_ in wb_]
+        assert len(rest_a) == len(rest_b)
+        A[:] = outa + rest_a
+        B[:] = outb + rest_b
 
 
 def hi16(c: float) -> int:
@@ -250,7 +289,11 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
                     k = subs_k[sb]
                     lst = [] if k is None else c_lists[k][which][sb % coop::coop]
                     per_sub.append([q_ * RXB for q_ in lst] + [(nr + ((sb + i) & 1)) * RXB for i in range(2 * n - len(lst))])
-                balance_banks(per_sub, lambda v: (v // RB) & 1 if (RB & 127) else 0)
+                if RB == 64:
+                    balance_pairs(per_sub, lambda v: (v // RB) & 1,
+                                  lambda v: ((nr + (nr & 1)) * RXB, (nr + 1 - (nr & 1)) * RXB) if v // RXB >= nr else None)
+                else:
+                    balance_banks(per_sub, lambda v: (v // RB) & 1 if (RB & 127) else 0)
                 for u in range(n):
                     for sb in range(nsub):
                         c_str += per_sub[sb][2 * u:2 * u + 2]
@@ -288,6 +331,24 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
             ent.sort(key=lambda v: v & ~1)
             elems.append(((len(ent) + 1) // 2, col, k, ent))
     sparse = sorted((e for e in elems if e[0] > 0), key=lambda e: (-e[0], e[1], e[2]))
+    if RB == 64:
+        # Neighbouring sub-groups (2 i, 2 i + 1) share a shared-memory phase (balance_pairs): among the
+        # elements of one list length, pair those whose raw rows lean to one half of the bank lines with
+        # those leaning to the other
+        # (the same holds for the species rows W_k a_k / W_k b_k of the element's row k, whose half is k & 1)
+        lean = lambda e: sum(1 if (v // RB) & 1 else -1 for v in e[3])
+        paired = []
+        for L in sorted({e[0] for e in sparse}, reverse=True):
+            pools = [sorted((e for e in sparse if e[0] == L and (e[2] & 1) == par), key=lambda e: (lean(e), e[1], e[2]))
+                     for par in (0, 1)]
+            while pools[0] and pools[1]:                  # rows of opposite parity, raw rows leaning opposite ways
+                paired += [pools[0].pop(0), pools[1].pop()]
+            run = pools[0] + pools[1]
+            run.sort(key=lambda e: (lean(e), e[1], e[2]))
+            while len(run) > 1:
+                paired += [run.pop(0), run.pop()]
+            paired += run
+        sparse = paired
 
     s_steps = []                               # (A words, B words, overflow units, L)
     for c0 in range(0, len(sparse), nsub):
@@ -302,7 +363,11 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
         ents = [list(grp[sb][3]) if sb < len(grp) else [] for sb in range(nsub)]
         for sb in range(nsub):
             ents[sb] += [(nraw + ((sb + i) & 1)) * RB for i in range(2 * L - len(ents[sb]))]
-        balance_banks(ents, lambda v: (v // RB) & 1 if (RB & 127) else 0)
+        if RB == 64:
+            zw = lambda v: ((nraw + (nraw & 1)) * RB | (v & 1), (nraw + 1 - (nraw & 1)) * RB | (v & 1)) if (v & ~1) // RB >= nraw else None
+            balance_pairs(ents, lambda v: (v // RB) & 1, zw)
+        else:
+            balance_banks(ents, lambda v: (v // RB) & 1 if (RB & 127) else 0)
         for sb in range(nsub):                 # positions past 2 L: skipped (L = 1) or padding of a batch
             ents[sb] += [(nraw + ((sb + i) & 1)) * RB for i in range(2 * (n_ovf + 2) - 2 * L)]
         for sb in range(nsub):

@@ -35,14 +35,14 @@ import numpy as np
 from .plan import (COST_EFF, COST_IRREV, COST_PLAIN, COST_PLOG, COST_PM, COST_THREE, NONE32, NPART,
                    NSCAL, SMEM_LIMIT, _f64_words, _lpt, balance_banks)
 
+PLAN_VERSION = 4             # of the p6_* record streams (checked by the library against its own)
 CHB = 512                    # bytes per stream chunk (one bulk copy)
-NSLOT = 3                    # ring slots per warp
+NSLOT = 3                    # ring slots per warp (two measured equally fast: profiles/README.md)
 SP_SLOTS, RX_SLOTS = 6, 4    # C B|WB dB|WA hW WT cp  /  net tT X1 dH
 F_NULL = 1 << 28             # reaction record of a padding sub-group
 F_CORR = 1 << 29             # the reaction writes X1 + X2 to its correction row
 ENT_NULL = 0x7FFF
-CLASSES = (0, 1, 2, 4, 6)    # entry counts a DE step is built for
-D_FIRST, D_FINAL, D_VALID = 1 << 28, 1 << 29, 1 << 30
+D_CIN, D_COUT, D_VALID, D_HDR = 1 << 28, 1 << 29, 1 << 30, 1 << 31      # carry in / out, element exists, header record
 MAX_NSP = 255                # 16-bit element index, 8-bit column
 GS6 = (4, 8, 16, 32)         # states per block k_jac6 is built for
 
@@ -82,13 +82,6 @@ def layout6(nsp: int, nr: int, ncorr: int, nraw: int, gs: int, nw: int) -> Dict[
 def fits(nsp: int, nr: int, ncorr: int, nraw: int, gs: int, nw: int) -> bool:
     return nsp <= MAX_NSP and nraw + 2 < ENT_NULL and (nr + 2) * RX_SLOTS + 1 < ENT_NULL and \
         layout6(nsp, nr, ncorr, nraw, gs, nw)['bytes'] <= SMEM_LIMIT
-
-
-def _cls(n: int) -> int:
-    for c in CLASSES:
-        if n <= c:
-            return c
-    return CLASSES[-1]
 
 
 def build_plan6(nsp: int, nr: int, nraw: int, first_pm: int, p_c0: int, kinds: List[str],
@@ -135,6 +128,11 @@ def build_plan6(nsp: int, nr: int, nraw: int, first_pm: int, p_c0: int, kinds: L
         assert len(rec) == nsub and all(len(r) == 4 for r in rec)
         for r in rec:
             streams[w] += [int(v) & 0xFFFFFFFF for v in r]
+
+    def align(w, fill):
+        """Pads warp w's stream to a chunk boundary with records of `fill` words per sub-group."""
+        while len(streams[w]) % (CHB // 4):
+            emit(w, [list(fill)] * nsub)
 
     # ---------------------------------------------------------------- phase B
     pm = list(range(first_pm, nr))
@@ -265,102 +263,139 @@ def build_plan6(nsp: int, nr: int, nraw: int, first_pm: int, p_c0: int, kinds: L
                     emit(w, [per_sub[sb][4 * u:4 * u + 4] for sb in range(nsub)])
 
     # ---------------------------------------------------------------- phase DE
-    # units of one Jacobian row: an element = one record (<= 6 entries) or several 6-entry records
-    def row_units(k):
-        units = []
+    # Elements by rows.  A sub-group walks a *piece* of one Jacobian row k with W_k a_k, W_k b_k, W_k in
+    # registers; the element index follows from the column (e = col * NSP + k + 1), so a record only
+    # names columns and signed raw rows.  Record kinds, by the number of entries of an element's list:
+    #   K0  16 dense-only elements: sixteen column bytes
+    #   K1  5 elements with one entry:   cols in w0 and the low byte of w1, entries in w1.hi, w2, w3
+    #   K2  3 elements with two entries: cols in w0, entry pairs in w1, w2, w3
+    #   K4 / K6  one element with up to four / six entries: col (and D_VALID) in w0, entries in w1 .. w3
+    #   K7  one element of a list longer than six: like K6, the accumulator carried in (D_CIN) / out (D_COUT)
+    # col = 0 marks an absent element.  A *segment* = eight pieces (one per sub-group): a header record
+    # {D_HDR | owns the T-column element | k << 8, species rows, W_k}, a record of the per-kind record
+    # counts (warp-uniform: the maxima over the pieces), then the records kind by kind.
+    KINDS = (7, 6, 4, 2, 1, 0)
+    PER_REC = {0: 16, 1: 5, 2: 3, 4: 1, 6: 1, 7: 1}
+    KCOST = {0: 34.0 + 11.0 * 16, 1: 34.0 + 19.0 * 5, 2: 34.0 + 29.0 * 3, 4: 34.0 + 50.0, 6: 34.0 + 66.0, 7: 34.0 + 72.0}
+
+    def kind_of(n):
+        return 0 if n == 0 else 1 if n == 1 else 2 if n == 2 else 4 if n <= 4 else 6 if n <= 6 else 7
+
+    def row_elems(k):
+        """Per kind: the elements (col, entries) of row k; a K7 element is a list of its 6-entry parts."""
+        by = {kd: [] for kd in KINDS}
         for col in range(1, nsp):
             ent = expand(contrib.get((k, col - 1), []))
-            e = col * nsp + k + 1
-            if len(ent) <= CLASSES[-1]:
-                units.append([(e, col, _cls(len(ent)), ent, True, True)])
+            kd = kind_of(len(ent))
+            if kd == 7:
+                by[7].append((col, [ent[i:i + 6] for i in range(0, len(ent), 6)]))
             else:
-                parts = [ent[i:i + 6] for i in range(0, len(ent), 6)]
-                units.append([(e, col, 6, part, i == 0, i == len(parts) - 1) for i, part in enumerate(parts)])
-        return units
+                by[kd].append((col, ent))
+        return by
 
-    def rcost(r):
-        return C6_D_REC + C6_D_ENT * r[2]
+    def n_records(by):
+        return {kd: (sum(len(parts) for _, parts in by[7]) if kd == 7 else -(-len(by[kd]) // PER_REC[kd])) for kd in KINDS}
 
-    rows = [row_units(k) for k in range(last)]
-    row_cost = [sum(rcost(r) for u in units for r in u) for units in rows]
+    def piece_cost(by):
+        nr_ = n_records(by)
+        return sum(nr_[kd] * KCOST[kd] for kd in KINDS)
+
+    rows = [row_elems(k) for k in range(last)]
+    row_cost = [piece_cost(by) for by in rows]
     total_cost = sum(row_cost)
 
     def build_de(target):
-        """Cut the rows into pieces of about `target` cost, group eight pieces of similar shape into a
-        segment, deal the segments to the warps; returns (largest warp cost, per-warp segments)."""
+        """Cut the rows into pieces of about `target` cost, group NSUB pieces of similar shape into a
+        segment, deal the segments to the warps; returns (largest warp cost, per-warp segments, loads)."""
         pieces = []
-        for k, units in enumerate(rows):
+        for k, by in enumerate(rows):
             n_k = max(1, int(round(row_cost[k] / target)))
-            bins_ = [[] for _ in range(n_k)]
-            load_ = [0.0] * n_k
-            for u in sorted(units, key=lambda u: (-u[0][2], -len(u), u[0][0])):
-                b = min(range(n_k), key=lambda i: (load_[i], i))
-                bins_[b].append(u)
-                load_[b] += sum(rcost(r) for r in u)
-            for i, b in enumerate(bins_):
-                recs = [r for u in b for r in u]           # class-descending, an element's records adjacent
-                pieces.append((k, i == 0, recs))
-        def profile(pc):
-            return tuple(-sum(1 for r in pc[2] if r[2] == c) for c in reversed(CLASSES)) + (pc[0],)
-        pieces.sort(key=profile)
+            parts = [{kd: [] for kd in KINDS} for _ in range(n_k)]
+            at = 0
+            for kd in KINDS:                       # deal each kind round-robin, continuing where the last one stopped
+                for el in by[kd]:
+                    parts[at % n_k][kd].append(el)
+                    at += 1
+            for i, pc in enumerate(parts):
+                pieces.append((k, i == 0, pc, n_records(pc)))
+        pieces.sort(key=lambda pc: tuple(-pc[3][kd] for kd in KINDS) + (pc[0],))
         segs = []
         for c0 in range(0, len(pieces), nsub):
             grp = pieces[c0:c0 + nsub]
-            L_ = max(len(pc[2]) for pc in grp)
-            step_cls = [max((pc[2][t][2] if t < len(pc[2]) else 0) for pc in grp) for t in range(L_)]
-            cost = C6_D_HDR + sum(C6_D_REC + C6_D_ENT * c for c in step_cls)
-            segs.append((grp, L_, step_cls, cost))
+            counts = {kd: max(pc[3][kd] for pc in grp) for kd in KINDS}
+            cost = C6_D_HDR + sum(counts[kd] * KCOST[kd] for kd in KINDS)
+            segs.append((grp, counts, cost))
         init = [0.0] * nw
         init[0] = C6_DOTS
-        bins_, load_ = _lpt([s_[3] for s_ in segs], nw, init)
+        bins_, load_ = _lpt([s_[2] for s_ in segs], nw, init)
         return max(load_), [[segs[ix] for ix in sorted(b)] for b in bins_], load_
 
     best = None
     per_worker = total_cost / (nw * nsub)
-    for nseg in range(1, 9):
-        for fudge in (0.85, 0.92, 1.0, 1.08, 1.16):
-            target = per_worker / nseg * fudge
-            res = build_de(target)
+    for nseg in range(1, 7):
+        for fudge in (0.8, 0.9, 1.0, 1.1, 1.2):
+            res = build_de(per_worker / nseg * fudge)
             if best is None or res[0] < best[0]:
                 best = res
     _, de_warps, de_load = best
 
-    zero_raw = lambda sb, i: nraw + ((sb + i) & 1)
+    def ent16(lst, n, sb):
+        """n signed 16-bit entries: the list, padded with the zero rows."""
+        out = [src | (sg << 15) for src, sg in lst]
+        return out + [nraw + ((sb + i) & 1) for i in range(n - len(out))]
+
+    def pack16(e):
+        return [e[2 * i] | (e[2 * i + 1] << 16) for i in range(len(e) // 2)]
+
     for w in range(nw):
         hdr[w, 6] = len(de_warps[w])
-        for grp, L_, step_cls, _ in de_warps[w]:
+        for grp, counts, _ in de_warps[w]:
             head = []
             for sb in range(nsub):
                 if sb < len(grp):
-                    k, own_t, _ = grp[sb]
-                    head.append([sp_even(k), (1 if own_t else 0) | (k << 8) | (L_ << 16)] + _f64_words(sp_w[k]))
+                    k, own_t = grp[sb][0], grp[sb][1]
+                    head.append([D_HDR | D_VALID | (1 if own_t else 0) | (k << 8), sp_even(k)] + _f64_words(sp_w[k]))
                 else:
-                    head.append([NONE32, L_ << 16, 0, 0])
+                    head.append([D_HDR, 0, 0, 0])
             emit(w, head)
-            for t in range(L_):
-                c = step_cls[t]
-                ents = []
-                for sb in range(nsub):
-                    recs = grp[sb][2] if sb < len(grp) else []
-                    lst = [src | (sg << 15) for src, sg in recs[t][3]] if t < len(recs) else []
-                    ents.append(lst + [zero_raw(sb, i) for i in range(6 - len(lst))])
-                if halves and c:
-                    # only the first c entries are read: keep real entries there, spread over both halves
-                    heads = [e_[:c] for e_ in ents]
-                    balance_banks(heads, lambda v: v & 1)
-                    ents = [h_ + e_[c:] for h_, e_ in zip(heads, ents)]
-                rec = []
-                for sb in range(nsub):
-                    recs = grp[sb][2] if sb < len(grp) else []
-                    if t < len(recs):
-                        e, col, _, lst, first, final = recs[t]
-                        assert len(lst) <= c
-                        x = e | (col << 16) | (c << 24) | (D_FIRST if first else 0) | (D_FINAL if final else 0) | D_VALID
-                    else:
-                        x = (c << 24) | D_FIRST | D_FINAL
-                    en = ents[sb]
-                    rec.append([x, en[0] | (en[1] << 16), en[2] | (en[3] << 16), en[4] | (en[5] << 16)])
-                emit(w, rec)
+            assert all(counts[kd] < 256 for kd in KINDS)
+            cw = [counts[7] | (counts[6] << 8) | (counts[4] << 16) | (counts[2] << 24), counts[1] | (counts[0] << 8), 0, 0]
+            emit(w, [cw] * nsub)
+            for kd in KINDS:
+                per = PER_REC[kd]
+                for i in range(counts[kd]):
+                    rec = []
+                    for sb in range(nsub):
+                        pc = grp[sb][2] if sb < len(grp) else {k_: [] for k_ in KINDS}
+                        if kd == 7:
+                            flat = [(col, part, j == 0, j == len(parts) - 1) for col, parts in pc[7] for j, part in enumerate(parts)]
+                            if i < len(flat):
+                                col, part, first, final = flat[i]
+                                x = col | D_VALID | (0 if first else D_CIN) | (0 if final else D_COUT)
+                                rec.append([x] + pack16(ent16(part, 6, sb)))
+                            else:
+                                rec.append([0] + pack16(ent16([], 6, sb)))
+                        elif kd in (4, 6):
+                            if i < len(pc[kd]):
+                                col, ent = pc[kd][i]
+                                rec.append([col | D_VALID] + pack16(ent16(ent, 6, sb)))
+                            else:
+                                rec.append([0] + pack16(ent16([], 6, sb)))
+                        else:
+                            els = pc[kd][i * per:(i + 1) * per]
+                            cols = [c_ for c_, _ in els] + [0] * (per - len(els))
+                            if kd == 0:
+                                rec.append([cols[4 * j] | (cols[4 * j + 1] << 8) | (cols[4 * j + 2] << 16) | (cols[4 * j + 3] << 24)
+                                            for j in range(4)])
+                            elif kd == 1:
+                                ents = [ent16(e_, 1, sb + j)[0] for j, (_, e_) in enumerate(els)] + \
+                                       [ent16([], 1, sb + j)[0] for j in range(per - len(els))]
+                                rec.append([cols[0] | (cols[1] << 8) | (cols[2] << 16) | (cols[3] << 24),
+                                            cols[4] | (ents[0] << 16), ents[1] | (ents[2] << 16), ents[3] | (ents[4] << 16)])
+                            else:
+                                pairs = [ent16(e_, 2, sb) for _, e_ in els] + [ent16([], 2, sb) for _ in range(per - len(els))]
+                                rec.append([cols[0] | (cols[1] << 8) | (cols[2] << 16)] + [pr_[0] | (pr_[1] << 16) for pr_ in pairs])
+                    emit(w, rec)
 
     # the energy-equation row: records of NSUB columns, dealt to the warps with the least phase-DE work
     e_recs = [list(range(c0, min(c0 + nsub, last))) for c0 in range(0, last, nsub)]

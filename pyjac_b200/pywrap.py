@@ -129,13 +129,52 @@ class PyJacob:
         self._lib.pyjac_cu_cleanup()
 
 
+    # ---- extras of the emitted chem_utils (no reference wrapper binds them; used by the tests)
+    def eval_thermo(self, which: str, T: float) -> np.ndarray:
+        """``which`` in {'h', 'u', 'cv', 'cp'}: NSP mass-based values (eval_h / eval_u / eval_cv / eval_cp)."""
+        self._select()
+        out = np.empty(self.NSP)
+        getattr(self._lib, 'eval_' + which)(float(T), out.ctypes.data)
+        return out
+
+
+_MODULE = '''"""``%(name)s`` for the mechanism exported to %(src)r -- written by pyjac_b200.pywrap.generate_wrapper.
+
+The reference builds a Cython extension of this name per mechanism (pyjac/pywrap/%(pyx)s);
+this module carries the same functions, bound to the fixed sm_100a library over ctypes."""
+from pyjac_b200 import create_jacobian as _cj
+from pyjac_b200.pywrap import PyJacob as _PyJacob
+
+_mod = _PyJacob(_cj.load_tables(%(src)r), %(device)r)
+NSP, FWD_RATES, REV_RATES, PRES_MOD_RATES = _mod.NSP, _mod.FWD_RATES, _mod.REV_RATES, _mod.PRES_MOD_RATES
+%(names)s
+'''
+
+_PYJACOB = ('py_dydt', 'py_eval_jacobian', 'py_eval_rxn_rates', 'py_eval_spec_rates', 'py_get_rxn_pres_mod', 'py_eval_conc')
+_CU_PYJACOB = ('py_cuinit', 'py_cujac', 'py_cuclean')
+
+
 def generate_wrapper(lang: str, source_dir: str, out_dir: Optional[str] = None, auto_diff: bool = False,
                      device: Optional[int] = None) -> PyJacob:
     """Signature of pyjac/pywrap/pywrap_gen.py:66.  ``source_dir`` was written by
-    :func:`pyjac_b200.create_jacobian.create_jacobian`; nothing is compiled here (the library is
-    fixed), the returned object carries the ``py_*`` functions for that mechanism."""
-    if lang != 'cuda':
-        raise ValueError("pyjac_b200 only targets CUDA (sm_100a); lang=%r" % (lang,))
+    :func:`pyjac_b200.create_jacobian.create_jacobian`.  The reference compiles an extension module
+    (``pyjacob`` for lang 'c', ``cu_pyjacob`` for 'cuda') into ``out_dir``, which its callers then import
+    by name (functional_tester/test.py:432,740).  Here nothing needs compiling: a module of the same
+    name is *written* into ``out_dir`` (default: the current directory, like the reference) that binds
+    the same functions to the fixed library, and the bound object is returned as well.  Both names run
+    on the GPU -- 'c' selects the one-state functions of pyjacob_wrapper.pyx, 'cuda' the batched ones of
+    pyjacob_cuda_wrapper.pyx; there is no CPU implementation behind either."""
+    if lang not in ('c', 'cuda'):
+        raise ValueError("lang must be 'c' (pyjacob) or 'cuda' (cu_pyjacob); got %r" % (lang,))
     if auto_diff:
         raise NotImplementedError('auto_diff wrappers are outside the hot path')
+    import os
+    src = os.path.abspath(source_dir)
+    name, pyx, fns = (('pyjacob', 'pyjacob_wrapper.pyx', _PYJACOB) if lang == 'c'
+                      else ('cu_pyjacob', 'pyjacob_cuda_wrapper.pyx', _CU_PYJACOB))
+    out_dir = os.path.abspath(out_dir or os.getcwd())
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, name + '.py'), 'w') as fh:
+        fh.write(_MODULE % {'name': name, 'src': src, 'pyx': pyx, 'device': device,
+                            'names': '\n'.join('%s = _mod.%s' % (f, f) for f in fns)})
     return PyJacob(_cj.load_tables(source_dir), device)

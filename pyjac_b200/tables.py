@@ -64,6 +64,7 @@ NRE_SHIFT, NPR_SHIFT = 20, 24    # occupied reactant / product slots
 MAXS = 3               # concentration slots per side of a reaction
 UNROLL = 40            # CParams.Jacob_Unroll (cj:2651): scope of the stale pres_mod_temp quirk
 NPAR = 32
+SCHEMA_VERSION = 2     # of the table set; the library refuses blobs written for another one (csrc/pjtable.h)
 
 
 class UnsupportedMechanism(NotImplementedError):
@@ -98,9 +99,10 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, stream
     ws_global: True puts the per-block working set in global memory instead of shared memory, False
     forbids that; None = automatic (global memory when fewer than plan.SMEM_MIN_GS states fit in
     shared memory: USC-II- and n-heptane-sized mechanisms).
-    streams: False leaves out the record streams of k_jac6 (plan6.py), so that eval_jacob runs on the
-    schedule tables of k_eval like dydt and the rate routines do; None / True = streams whenever the
-    working set lives in shared memory."""
+    streams: True adds the record streams of k_jac6 (plan6.py: table items staged through a shared-memory
+    ring by bulk-asynchronous copies) and makes eval_jacob run on them when the working set lives in
+    shared memory; None / False = eval_jacob on the schedule tables of k_eval like dydt and the rate
+    routines (measured faster on a B200: profiles/README.md)."""
     specs, reacs = mech.specs, mech.reacs
     nsp, nr = len(specs), len(reacs)
     last = nsp - 1
@@ -538,7 +540,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, stream
     # ---------------- record streams of the Jacobian kernel k_jac6 (plan6.py): plans whose working
     # set lives in shared memory
     p_c0 = next((p for p in range(nr) if p >= first_pm or last in (reacs[order[p]].reac + reacs[order[p]].prod)), nr)
-    if streams is not False and not ws_global and gs_ in plan6.GS6 and plan6.fits(nsp, nr, nr - p_c0, nraw, gs_, nt // 32):
+    if streams and not ws_global and gs_ in plan6.GS6 and plan6.fits(nsp, nr, nr - p_c0, nraw, gs_, nt // 32):
         corr_rx = [False] * nr
         for p in range(p_c0, nr):
             par = pm_par[p - first_pm] if p >= first_pm else None
@@ -560,6 +562,8 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, stream
         eff6[:, 2] = ksp * spb6 + (ksp & 1) * gs_ * 8
         T['p6_eff'] = eff6.ravel()
 
+    T['sp_fwd_map'] = i32(mech.fwd_spec_map)            # internal position -> index in the mechanism file (apply_mask)
+    T['meta'] = i32([SCHEMA_VERSION, plan.PLAN_VERSION, plan6.PLAN_VERSION, 0])
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
     T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, len(plog_par), len(cheb_par), 0,
                      first_pm, npm, red_off[-1], max(len(l) for l in red), 0, 0, 0, 0])

@@ -577,54 +577,97 @@ def _assemble6(v):
     WA, WB, WT = w[None, :] * Ak, w[None, :] * Bk, w[None, :] * tcol
     colfac = Tb['p6_colfac'].reshape(nsp, 2)
     jac = np.full((n, nsp * nsp), np.nan)
+    wpc = chb // 4                                   # words per chunk
+    PER_REC = {0: 16, 1: 5, 2: 3, 4: 1, 6: 1, 7: 1}
+
+    def ents_of(words):
+        return [(wd >> (16 * h)) & 0xFFFF for wd in words for h in (0, 1)]
+
+    def gather(ents):
+        acc_ = np.zeros(n)
+        for x in ents:
+            acc_ = acc_ + (-1.0 if x & 0x8000 else 1.0) * rawz[:, x & 0x7FFF]
+        return acc_
+
     for wp in range(nw):
         for sgm in range(int(hdr[wp, 6])):
             h = get(wp)
-            Ls = h[0][1] >> 16
-            assert all(x[1] >> 16 == Ls for x in h)
+            assert all(x[0] & plan6.D_HDR for x in h)
             rows_k = []
             for sb in range(nsub):
-                if h[sb][0] == 0xFFFFFFFF:
+                if not h[sb][0] & plan6.D_VALID:
                     rows_k.append(None)
                     continue
-                k = sp_k(h[sb][0])
-                assert k == (h[sb][1] >> 8) & 0xFF and f64(h[sb][2], h[sb][3]) == w[k]
+                k = sp_k(h[sb][1])
+                assert k == (h[sb][0] >> 8) & 0xFF and f64(h[sb][2], h[sb][3]) == w[k]
                 rows_k.append(k)
-                if h[sb][1] & 1:
+                if h[sb][0] & 1:
                     assert np.isnan(jac[:, k + 1]).all()
                     jac[:, k + 1] = WT[:, k]
-            acc = [np.zeros(n) for _ in range(nsub)]
-            open_e = [None] * nsub
-            for t in range(Ls):
-                r = get(wp)
-                c = (r[0][0] >> 24) & 7
-                assert c in plan6.CLASSES and all((x[0] >> 24) & 7 == c for x in r)
-                for sb in range(nsub):
-                    x0 = r[sb][0]
-                    ents = [(r[sb][1 + i // 2] >> (16 * (i & 1))) & 0xFFFF for i in range(6)]
-                    if x0 & plan6.D_FIRST:
-                        assert open_e[sb] is None
-                        acc[sb] = np.zeros(n)
-                    for i in range(6):
-                        x = ents[i]
-                        if i < c:
-                            acc[sb] = acc[sb] + (-1.0 if x & 0x8000 else 1.0) * rawz[:, x & 0x7FFF]
+            cw = get(wp)
+            assert all(x == cw[0] for x in cw)
+            counts = {7: cw[0][0] & 0xFF, 6: (cw[0][0] >> 8) & 0xFF, 4: (cw[0][0] >> 16) & 0xFF, 2: cw[0][0] >> 24,
+                      1: cw[0][1] & 0xFF, 0: (cw[0][1] >> 8) & 0xFF}
+            carry = [None] * nsub
+
+            def put_el(sb, col, acc_):
+                k = rows_k[sb]
+                assert k is not None and 1 <= col < nsp
+                e = col * nsp + k + 1
+                assert np.isnan(jac[:, e]).all()
+                tt = w[k] * acc_ + WA[:, k]
+                jac[:, e] = colfac[col, 1] * WB[:, k] + colfac[col, 0] * tt
+
+            for kd in (7, 6, 4, 2, 1, 0):
+                for i in range(counts[kd]):
+                    r = get(wp)
+                    for sb in range(nsub):
+                        x = r[sb]
+                        if kd in (7, 6, 4):
+                            ents = ents_of(x[1:4])
+                            nread = 4 if kd == 4 else 6
+                            assert all((v_ & 0x7FFF) >= nraw for v_ in ents[nread:])      # not read by the kernel: padding
+                            acc_ = gather(ents[:nread])
+                            col = x[0] & 0xFF
+                            if kd == 7 and x[0] & plan6.D_CIN:
+                                assert carry[sb] is not None and carry[sb][0] == col
+                                acc_ = acc_ + carry[sb][1]
+                            else:
+                                assert carry[sb] is None
+                            if not x[0] & plan6.D_VALID:
+                                assert not acc_.any() and col == 0 and not x[0] & (plan6.D_CIN | plan6.D_COUT)
+                                continue
+                            if kd == 7 and x[0] & plan6.D_COUT:
+                                carry[sb] = (col, acc_)
+                            else:
+                                assert not x[0] & plan6.D_COUT
+                                carry[sb] = None
+                                put_el(sb, col, acc_)
+                        elif kd == 2:
+                            cols = [x[0] & 0xFF, (x[0] >> 8) & 0xFF, (x[0] >> 16) & 0xFF]
+                            assert x[0] >> 24 == 0
+                            for j in range(3):
+                                acc_ = gather(ents_of([x[1 + j]]))
+                                if cols[j]:
+                                    put_el(sb, cols[j], acc_)
+                                else:
+                                    assert not acc_.any()
+                        elif kd == 1:
+                            cols = [x[0] & 0xFF, (x[0] >> 8) & 0xFF, (x[0] >> 16) & 0xFF, x[0] >> 24, x[1] & 0xFF]
+                            assert (x[1] >> 8) & 0xFF == 0
+                            ents = [x[1] >> 16] + ents_of(x[2:4])
+                            for j in range(5):
+                                acc_ = gather([ents[j]])
+                                if cols[j]:
+                                    put_el(sb, cols[j], acc_)
+                                else:
+                                    assert not acc_.any()
                         else:
-                            assert (x & 0x7FFF) >= nraw            # entries the kernel does not read: padding
-                    if not x0 & plan6.D_VALID:
-                        assert not acc[sb].any() and x0 & plan6.D_FINAL
-                        continue
-                    k = rows_k[sb]
-                    e, col = x0 & 0xFFFF, (x0 >> 16) & 0xFF
-                    assert k is not None and e == col * nsp + k + 1 and col >= 1
-                    assert open_e[sb] in (None, e)
-                    open_e[sb] = e
-                    if x0 & plan6.D_FINAL:
-                        assert np.isnan(jac[:, e]).all()
-                        tt = w[k] * acc[sb] + WA[:, k]
-                        jac[:, e] = colfac[col, 1] * WB[:, k] + colfac[col, 0] * tt
-                        open_e[sb] = None
-            assert all(o is None for o in open_e)
+                            for j in range(16):
+                                col = (x[j // 4] >> (8 * (j % 4))) & 0xFF
+                                if col:
+                                    put_el(sb, col, np.zeros(n))
+            assert all(c_ is None for c_ in carry)
         for r_ in range(int(hdr[wp, 7])):
             r = get(wp)
             for sb in range(nsub):

@@ -106,7 +106,7 @@ def test_launch_shapes_give_identical_results(torch, golden_dir, gs, threads, la
 def test_stream_kernel_vs_table_kernel(torch, golden_dir, mech_file, npz, gs, threads):
     """eval_jacob through the record streams (k_jac6) against the golden vectors and against the
     schedule-table kernel (k_eval) on the same states, ragged batch included."""
-    mech, ev = _evaluator_with(golden_dir, mech_file, gs=gs, threads=threads)
+    mech, ev = _evaluator_with(golden_dir, mech_file, gs=gs, threads=threads, streams=True)
     assert ev.uses_streams
     mech, ev5 = _evaluator_with(golden_dir, mech_file, gs=gs, threads=threads, streams=False)
     assert not ev5.uses_streams
@@ -132,8 +132,8 @@ def test_stream_kernel_vs_table_kernel(torch, golden_dir, mech_file, npz, gs, th
 def test_two_handles_share_one_kernel_instantiation(torch, golden_dir):
     """The opt-in shared-memory size belongs to the kernel instantiation, not to a handle: a large plan,
     then a small one, then the large one again (same instantiation) must all launch."""
-    mech_l, ev_l = _evaluator_with(golden_dir, 'gri30_syn.inp', gs=8, threads=384)
-    mech_s, ev_s = _evaluator_with(golden_dir, 'h2o2_n2.inp', gs=8, threads=384)
+    mech_l, ev_l = _evaluator_with(golden_dir, 'gri30_syn.inp', gs=8, threads=384, streams=True)
+    mech_s, ev_s = _evaluator_with(golden_dir, 'h2o2_n2.inp', gs=8, threads=384, streams=True)
     for mech, ev in ((mech_l, ev_l), (mech_s, ev_s), (mech_l, ev_l), (mech_s, ev_s)):
         P_h, y_h = synthetic_states(mech.NSP, 40, seed=2)
         P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')

@@ -31,8 +31,50 @@ def test_create_jacobian_writes_header_and_tables(golden_dir, tmp_path):
                      'last_spec': mech.last_spec_original}
     T = blob.unpack(load_tables(out))
     assert int(T['dims'][0]) == 10 and 'p5_cfg' in T
-    # the library stage hands back the one fixed sm_100a library
-    assert libgen.generate_library('cuda', out) == libgen.build_library()
+    # what a program written against the emitted library includes (tester.c.in, read_initial_conditions.c, the .pyx files)
+    for name in ('header.h', 'jacob.h', 'dydt.h', 'rates.h', 'chem_utils.h', 'pyjacob.cuh'):
+        assert os.path.isfile(os.path.join(out, name)), name
+    assert 'void apply_mask(double*);' in open(os.path.join(out, 'mechanism.h')).read()
+
+
+def test_generate_library_builds_the_mechanism_stub(golden_dir, tmp_path):
+    """generate_library: a per-mechanism library under the reference's name (libgen.py:170-186) that embeds
+    the tables, registers them with the CUDA library when loaded and forwards the emitted library's
+    entry points -- what `-lc_pyjac` links.  Loading it needs no GPU."""
+    import ctypes
+    import subprocess
+    out = str(tmp_path / 'out')
+    create_jacobian('cuda', os.path.join(golden_dir, 'h2o2_n2.inp'), build_path=out)
+    for lang, name in (('c', 'libc_pyjac.so'), ('cuda', 'libcu_pyjac.so')):
+        path = libgen.generate_library(lang, out)
+        assert os.path.basename(path) == name and os.path.dirname(path) == out
+        syms = subprocess.run(['nm', '-D', '--defined-only', path], capture_output=True, text=True).stdout
+        for fn in ('eval_jacob', 'dydt', 'eval_conc', 'eval_rxn_rates', 'get_rxn_pres_mod', 'eval_spec_rates',
+                   'eval_h', 'eval_u', 'eval_cv', 'eval_cp', 'apply_mask', 'apply_reverse_mask'):
+            assert re.search(r' T %s$' % fn, syms, flags=re.M), fn
+        needed = subprocess.run(['readelf', '-d', path], capture_output=True, text=True).stdout
+        assert 'libpyjac_b200.so' in needed
+        ctypes.CDLL(path)                     # the constructor registers the tables: host only
+    with pytest.raises(ValueError):
+        libgen.generate_library('fortran', out)
+
+
+def test_generate_wrapper_writes_importable_modules(golden_dir, tmp_path):
+    """generate_wrapper writes `pyjacob` / `cu_pyjacob` modules that the reference's callers import by name
+    (functional_tester/test.py:432,740).  Importing them needs a GPU (GPU test); here: they exist and name
+    the reference's functions."""
+    from pyjac_b200 import lib, pywrap
+    out = str(tmp_path / 'out')
+    create_jacobian('cuda', os.path.join(golden_dir, 'h2o2_n2.inp'), build_path=out)
+    mods = str(tmp_path / 'mods')
+    for lang, name, fns in (('c', 'pyjacob', pywrap._PYJACOB), ('cuda', 'cu_pyjacob', pywrap._CU_PYJACOB)):
+        try:
+            pywrap.generate_wrapper(lang, out, mods)
+        except lib.PyjacError:
+            pass                              # no device here: the module is written before the mechanism is loaded
+        text = open(os.path.join(mods, name + '.py')).read()
+        for fn in fns:
+            assert '%s = _mod.%s' % (fn, fn) in text
 
 
 def test_create_jacobian_rejects_what_it_cannot_do(golden_dir, tmp_path):
@@ -42,7 +84,7 @@ def test_create_jacobian_rejects_what_it_cannot_do(golden_dir, tmp_path):
     with pytest.raises(NotImplementedError):
         create_jacobian('cuda', mech, build_path=str(tmp_path), auto_diff=True)
     with pytest.raises(FileNotFoundError):
-        libgen.generate_library('cuda', str(tmp_path / 'nothing'))
+        libgen.generate_library('cuda', str(tmp_path))
 
 
 def test_plan_tables_are_consistent(golden_dir, tmp_path):

@@ -34,7 +34,7 @@ def test_model_matches_reference_golden(golden_dir, mech_file, npz, sl):
 def test_stream_model_matches_reference_golden(golden_dir, mech_file, npz, sl):
     """The record streams of k_jac6 (plan6.py), interpreted record by record."""
     mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
-    T = blob.unpack(blob.pack(tables.build(mech)))
+    T = blob.unpack(blob.pack(tables.build(mech, streams=True)))
     assert 'p6_str' in T
     g = {k: v[sl] for k, v in np.load(os.path.join(golden_dir, npz)).items()}
     out = kernel_model.evaluate(T, g['P'], g['y'], plan=6)
@@ -50,7 +50,7 @@ def test_stream_model_matches_reference_golden(golden_dir, mech_file, npz, sl):
 def test_stream_model_other_shapes(golden_dir, mech_file, npz, gs, threads):
     """Stream plans for other states-per-block / block sizes than the automatic choice."""
     mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
-    T = tables.build(mech, gs=gs, threads=threads)
+    T = tables.build(mech, gs=gs, threads=threads, streams=True)
     assert 'p6_str' in T and tuple(T['p6_cfg'][:2]) == (gs, threads)
     g = {k: v[:16] for k, v in np.load(os.path.join(golden_dir, npz)).items()}
     out = kernel_model.evaluate(T, g['P'], g['y'], plan=6)
@@ -59,9 +59,9 @@ def test_stream_model_other_shapes(golden_dir, mech_file, npz, gs, threads):
 
 def test_streams_can_be_left_out(golden_dir):
     mech = Mechanism.from_chemkin(os.path.join(golden_dir, 'h2o2_n2.inp'))
-    assert 'p6_str' not in tables.build(mech, streams=False)
+    assert 'p6_str' not in tables.build(mech) and 'p6_str' in tables.build(mech, streams=True)
     big = Mechanism.from_chemkin(os.path.join(golden_dir, 'usc2_syn.inp'))
-    assert 'p6_str' not in tables.build(big)          # working set in global memory: schedule tables only
+    assert 'p6_str' not in tables.build(big, streams=True)          # working set in global memory: schedule tables only
 
 
 def test_tables_reject_unsupported(golden_dir):

@@ -2,6 +2,7 @@
 """eval_jacob throughput against batch size on one GPU (BASELINE.json config 5, GRI-shaped)."""
 import os, sys
 import torch
+import _devlib  # noqa: F401,E402  (PYJAC_B200_LIB: development builds)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pyjac_b200.evaluator import Evaluator

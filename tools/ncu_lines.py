@@ -18,7 +18,7 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(so)], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-    dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    dis = subprocess.run(['nvdisasm', '-gi', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     # map offset -> line for the kernel
     line_of = {}
     cur = None

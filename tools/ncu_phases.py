@@ -15,7 +15,7 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(so)], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-    dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    dis = subprocess.run(['nvdisasm', '-gi', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     line_of, cur, in_fn = {}, None, False
     for ln in dis.splitlines():
         if ln.startswith('\t.section') or ln.startswith('//-----'):
@@ -28,9 +28,11 @@ def main():
             # for inlined library code use the outermost "inlined at" kernels.cuh line
             m2 = re.findall(r'File "([^"]+)", line (\d+)', ln)
             cur = (fn, l)
-            for f2, l2 in m2:
-                if os.path.basename(f2) == src:
-                    cur = (src, int(l2))
+            # the kernel body is the last function of its file: of all lines of FILE on the inlining
+            # chain take the largest one
+            mine = [int(l2) for f2, l2 in m2 if os.path.basename(f2) == src]
+            if mine:
+                cur = (src, max(mine))
             continue
         m = re.match(r'\s*/\*([0-9a-f]+)\*/\s+(.*?);', ln)
         if m:

@@ -8,6 +8,7 @@ import os, sys
 if 'PYJAC_B200_LIB' not in os.environ:
     os.environ['PYJAC_B200_NVCC_EXTRA'] = '-DPJ_PHASE_CLOCKS'     # (set before the library is built)
 import torch
+import _devlib  # noqa: F401,E402  (PYJAC_B200_LIB: development builds)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pyjac_b200.evaluator import Evaluator

@@ -10,6 +10,7 @@ import sys
 
 import numpy as np
 import torch
+import _devlib  # noqa: F401,E402  (PYJAC_B200_LIB: development builds)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

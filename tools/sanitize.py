@@ -2,6 +2,7 @@
 """Small eval_jacob / dydt / rates launches for compute-sanitizer (memcheck, racecheck)."""
 import os, sys
 import torch
+import _devlib  # noqa: F401,E402  (PYJAC_B200_LIB: development builds)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pyjac_b200.evaluator import Evaluator

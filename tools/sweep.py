@@ -5,6 +5,7 @@ import os
 import sys
 
 import torch
+import _devlib  # noqa: F401,E402  (PYJAC_B200_LIB: development builds)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
