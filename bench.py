@@ -18,7 +18,16 @@ roofline     HBM bound; algorithmic bytes = 8*NSP^2 + 8*(NSP+1) per state (SURVE
 cpu_baseline the reference's own generated C (oracle/_ref, OpenMP over states, all host
              threads) on a bounded sample of the same states; rank 0, N = 1 only
 
---impl reference times that generated C alone (the reference has no working sm_100 GPU path).
+workloads    sub-records for BASELINE.json's other configurations on this rank count: USC-II-shaped
+             (configs[2]), n-heptane-shaped at 32 768 states per GPU (configs[3]), the 1020 H2/O2 PaSR
+             states (configs[0]); --no-workloads leaves them out
+with_gather  (N > 1) the same batch with every Jacobian gathered to rank 0 over NCCL, chunked so that
+             the send of chunk c overlaps the kernel of chunk c + 1; rank 0 receives into a bounded ring
+             of buffers (8 x 23.6 GB would not fit one GPU).  `ingress_gbs` = bytes into rank 0 / time
+strong       (N > 1) the fixed 2^20-state batch split over the N ranks
+
+--impl reference times the reference alone (it has no working sm_100 GPU path): its generated C under its own
+harness (tester.c.in + read_initial_conditions.c + timer.h, oracle/_ref/<name>/speedtest) on all host threads.
 """
 from __future__ import annotations
 
@@ -146,30 +155,67 @@ def load_states(nsp: int, n: int, seed: int):
     return synthetic_states(nsp, n, seed=seed)
 
 
-def cpu_reference(mech):
-    """The CPU checker used as the reported baseline: the reference's generated C when
-    oracle/_ref holds it, else the oracle port."""
+class Harness:
+    """The reference's own `speedtest <num_odes> <num_threads>` (oracle/_ref/<name>/speedtest, built by
+    oracle/build_ref.py from tester.c.in where the reference lies): reads data.bin, times eval_jacob over the
+    states inside an OpenMP loop with its own timer.h, prints "num_odes,ms"."""
+
+    def __init__(self, name, mech, P, y):
+        import tempfile
+        import numpy as np
+        from pyjac_b200 import speedtest
+        self.exe = os.path.join(ROOT, 'oracle', '_ref', name, 'speedtest')
+        self.dir = tempfile.mkdtemp(prefix='pyjac_b200_bench_')
+        Y_int = np.concatenate([y[:, 1:], 1.0 - y[:, 1:].sum(axis=1, keepdims=True)], axis=1)
+        Y_orig = np.empty_like(Y_int)
+        Y_orig[:, mech.fwd_spec_map] = Y_int            # data.bin holds the mechanism file's species order
+        speedtest.write_data_bin(os.path.join(self.dir, 'data.bin'), y[:, 0], P, Y_orig)
+        self.n_max = len(P)
+
+    @staticmethod
+    def available(name):
+        return os.access(os.path.join(ROOT, 'oracle', '_ref', name, 'speedtest'), os.X_OK)
+
+    def run(self, n, threads):
+        """seconds the harness measured for n states"""
+        out = subprocess.run([self.exe, str(n), str(threads)], cwd=self.dir, capture_output=True, text=True, check=True).stdout
+        num, ms = out.strip().split(',')
+        assert int(num) == n
+        return float(ms) * 1e-3
+
+
+def cpu_reference(mech, P, y):
+    """The CPU baseline: the reference's generated C under its own harness when oracle/_ref holds it
+    (kind 'reference'), else its generated C under oracle/ref_batch.c, else the oracle port.  Returns
+    (run(n, threads) -> seconds, kind, description)."""
     from oracle.oracle import Oracle, RefLib
+    if Harness.available(REF_NAME):
+        h = Harness(REF_NAME, mech, P, y)
+        return h.run, 'reference', "reference's generated C under its own speedtest harness (tester.c.in, timer.h), gcc -std=c99 -O3 -mtune=native -fopenmp"
     if RefLib.available(REF_NAME):
-        return RefLib(REF_NAME), 'reference'
-    return Oracle(mech), 'port'
+        ref = RefLib(REF_NAME)
 
-
-def time_cpu(ref, kind, P, y, threads, target_s):
-    """states/s of the CPU implementation on a bounded sample sized for ~target_s seconds."""
-    def run(n):
-        t = time.perf_counter()
-        if kind == 'reference':
+        def run(n, threads):
+            t = time.perf_counter()
             ref.eval_jacob(P[:n], y[:n], nthreads=threads, keep=False)
-        else:
-            ref.eval_jacob(P[:n], y[:n], nthreads=threads)
+            return time.perf_counter() - t
+        return run, 'reference', "reference's generated C (gcc -std=c99 -O3 -mtune=native -fopenmp) under an OpenMP loop over states"
+
+    ora = Oracle(mech)
+
+    def run(n, threads):
+        t = time.perf_counter()
+        ora.eval_jacob(P[:n], y[:n], nthreads=threads)
         return time.perf_counter() - t
-    probe = min(len(P), 512 * threads)
-    run(probe)                                  # warm caches / OpenMP pool
-    rate = probe / run(probe)
-    n = int(max(probe, min(len(P), rate * target_s)))
-    dt = run(n)
-    return n / dt, n, dt
+    return run, 'port', 'oracle port (oracle/pyjac_oracle.c) on host cores'
+
+
+def sample_size(run, threads, n_max, target_s):
+    """number of states that keeps one pass near target_s seconds"""
+    probe = min(n_max, 256 * threads)
+    run(probe, threads)                         # warm caches / OpenMP pool
+    rate = probe / run(probe, threads)
+    return int(max(probe, min(n_max, rate * target_s)))
 
 
 def run_reference(args, rank, world):
@@ -178,22 +224,12 @@ def run_reference(args, rank, world):
     from pyjac_b200.mechanism import Mechanism
     mech = Mechanism.from_chemkin(MECH_FILE)
     threads = host_threads()
-    ref, kind = cpu_reference(mech)
     P, y = load_states(mech.NSP, 1 << 18, seed=0)
-    # bounded sample per step: ~2 s of CPU work
-    probe = min(len(P), 512 * threads)
-    ref.eval_jacob(P[:probe], y[:probe], nthreads=threads, **({'keep': False} if kind == 'reference' else {}))
-    t = time.perf_counter()
-    ref.eval_jacob(P[:probe], y[:probe], nthreads=threads, **({'keep': False} if kind == 'reference' else {}))
-    rate = probe / (time.perf_counter() - t)
-    n = int(max(probe, min(len(P), rate * 2.0)))
-    kw = {'keep': False} if kind == 'reference' else {}
+    run, kind, how = cpu_reference(mech, P, y)
+    n = sample_size(run, threads, len(P), 2.0)            # bounded sample per step: ~2 s of CPU work
     for _ in range(args.warmup):
-        ref.eval_jacob(P[:n], y[:n], nthreads=threads, **kw)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ref.eval_jacob(P[:n], y[:n], nthreads=threads, **kw)
-    dt = time.perf_counter() - t0
+        run(n, threads)
+    dt = sum(run(n, threads) for _ in range(args.steps))
     value = n * args.steps / dt
     sample = '%d states/step of the seed-0 synthetic batch, %d OpenMP threads' % (n, threads)
     line = {
@@ -201,14 +237,121 @@ def run_reference(args, rank, world):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'states_per_step': n, 'path':
-                   "reference's generated C (pyjac --lang c, gcc -std=c99 -O3 -mtune=native -fopenmp) on host cores"
-                   if kind == 'reference' else 'oracle port (oracle/pyjac_oracle.c) on host cores'},
+        'config': {'workload': WORKLOAD, 'states_per_step': n, 'path': how + ' on host cores'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def time_kernel(ev, torch, P, y, jac, steps, warmup, barrier, max_over_ranks):
+    """ms per launch of eval_jacob on state-fastest device arrays (CUDA events, max over ranks), launches"""
+    SF = dict(y_layout='state_fastest', jac_layout='state_fastest')
+    for _ in range(warmup):
+        ev.eval_jacob(P, y, jac, **SF)
+    barrier()
+    l0 = ev.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ev.eval_jacob(P, y, jac, **SF)
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)) / steps, e0.elapsed_time(e1) / steps, ev.launches - l0
+
+
+def side_workload(name, torch, dev, rank, world, barrier, max_over_ranks, peak):
+    """One of BASELINE.json's other configurations, device-resident, a few launches: sub-record of the line."""
+    import numpy as np
+    from pyjac_b200 import synth
+    from pyjac_b200.evaluator import Evaluator
+    from pyjac_b200.mechanism import Mechanism
+    import tempfile
+    if name == 'h2o2_pasr':
+        # configs[0]: the bundled PaSR states (1020, not 1024: SURVEY.md finding 2) of the 10-species H2/O2 mechanism
+        mech = Mechanism.from_chemkin(os.path.join(ROOT, 'tests', 'golden', 'h2o2_n2.inp'))
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'h2o2_pasr.npz'))
+        P_h, y_h = g['P'], g['y']
+        what = 'H2/O2 (10 sp / 28 rxn), the 1020 PaSR states of data/h2_pasr_output.npy'
+    else:
+        shape, _, what, n = SIDE[name]
+        path = os.path.join(tempfile.gettempdir(), 'pyjac_b200_bench_%s_%d.inp' % (shape, os.getpid()))
+        synth.write(shape, path, seed=0)
+        mech = Mechanism.from_chemkin(path)
+        P_h, y_h = load_states(mech.NSP, n, seed=rank)
+    nsp, n = mech.NSP, len(P_h)
+    ev = Evaluator(mech, dev.index)
+    P = torch.tensor(P_h, device=dev)
+    y = torch.tensor(y_h, device=dev).t().contiguous()
+    jac = torch.empty((nsp * nsp, n), dtype=torch.float64, device=dev)
+    ms, ms_local, launches = time_kernel(ev, torch, P, y, jac, 3, 2, barrier, max_over_ranks)
+    bps = 8 * nsp * nsp + 8 * (nsp + 1)
+    rec = {'workload': what, 'states_per_gpu': n, 'value': n * world / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+           'roofline_frac': bps * n / (ms_local * 1e-3) / 1e9 / peak, 'achieved_gbs': bps * n / (ms_local * 1e-3) / 1e9,
+           'bytes_per_state': bps, 'kernel': ev.kernel_name(0),
+           'plan': 'gs=%d, %d threads, working set in %s memory' % (ev.plan_gs, ev.plan_threads,
+                                                                    'global' if int(ev.tables['p5_cfg'][14]) else 'shared')}
+    ev.close()
+    del jac, y, P
+    torch.cuda.empty_cache()
+    return rec
+
+
+SIDE = {'usc2': WORKLOADS['usc2'], 'nc7': ('nc7', 'nc7', WORKLOADS['nc7'][2], 32768)}
+
+
+def gather_run(ev, torch, dist, dev, rank, world, P, y, jac, nsp, n, steps, barrier, max_over_ranks):
+    """eval_jacob of the rank's batch in chunks with every chunk's Jacobians gathered to rank 0 (NCCL
+    send / recv on a second stream while the next chunk's kernel runs).  Rank 0 receives into a ring of
+    two buffers per peer -- a consumer would work on a chunk and let it go: 8 x 23.6 GB do not fit one
+    GPU (SURVEY.md finding 5)."""
+    nchunk = next(c for c in (8, 4, 2, 1) if n % c == 0)
+    cs = n // nchunk
+    nn = nsp * nsp
+    comm = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    SF = dict(y_layout='state_fastest', jac_layout='state_fastest')
+    # a chunk is a column block of the state-fastest arrays, evaluated into a buffer of its own leading
+    # dimension, so that what is sent is contiguous; two buffers alternate
+    out = [torch.empty((nn, cs), dtype=torch.float64, device=dev) for _ in range(2)]
+    ring = [torch.empty((world - 1, nn, cs), dtype=torch.float64, device=dev) for _ in range(2)] if rank == 0 else None
+    Pc = [P[c * cs:(c + 1) * cs].contiguous() for c in range(nchunk)]
+    yc = [y[:, c * cs:(c + 1) * cs].contiguous() for c in range(nchunk)]
+
+    def one_pass():
+        sent = []
+        for c in range(nchunk):
+            if c >= 2:
+                main.wait_event(sent[c - 2])           # the buffer is free once chunk c - 2 has gone
+            ev.eval_jacob(Pc[c], yc[c], out[c & 1], **SF)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(done)
+                if rank:
+                    dist.send(out[c & 1], 0)
+                else:
+                    for q in [dist.irecv(ring[c & 1][r - 1], r) for r in range(1, world)]:
+                        q.wait()
+                e = torch.cuda.Event()
+                e.record(comm)
+            sent.append(e)
+        main.wait_stream(comm)
+
+    one_pass()                                     # warm-up: NCCL channels, staging
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_pass()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    return {'value': n * world / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'chunks': nchunk,
+            'ingress_gbs': (world - 1) * n * nn * 8 / (ms * 1e-3) / 1e9,
+            'how': 'NCCL send / recv of %d chunks per rank on a second stream, overlapped with the next chunk\'s '
+                   'kernel; rank 0 receives into a ring of two buffers per peer' % nchunk}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -277,6 +420,20 @@ def run_ours(args, rank, world, local_rank):
     achieved = bytes_per_state * n / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     traffic = ncu_traffic(nsp)
+    kernel_name = ev.kernel_name(0)
+
+    # ---- the multi-GPU path of the north star: Jacobians gathered to rank 0; strong scaling ----
+    with_gather = strong = None
+    if world > 1 and not args.no_gather:
+        with_gather = gather_run(ev, torch, dist, dev, rank, world, P, y, jac, nsp, n, max(1, min(args.steps, 3)),
+                                 barrier, max_over_ranks)
+    if world > 1:
+        ns = (1 << 20) // world                               # BASELINE configs[1]'s batch, split over the ranks
+        ms_s, _, _ = time_kernel(ev, torch, P[:ns].contiguous(), y[:, :ns].contiguous(),
+                                 torch.empty((nsp * nsp, ns), dtype=torch.float64, device=dev), max(1, min(args.steps, 5)), 2,
+                                 barrier, max_over_ranks)
+        strong = {'global_states': ns * world, 'states_per_gpu': ns, 'value': ns * world / (ms_s * 1e-3), 'unit': UNIT,
+                  'ms_per_step': ms_s}
 
     # ---- end to end through the host-pointer C-ABI call -------------------------------
     e2e = None
@@ -310,17 +467,32 @@ def run_ours(args, rank, world, local_rank):
         e2e = {'value': n_e * world * e_steps / dt, 'unit': UNIT,
                'h2d_bytes_per_step': n_e * (nsp + 1) * 8, 'd2h_bytes_per_step': n_e * nsp * nsp * 8,
                'states_per_step': n_e, 'steps': e_steps,
+               'd2h_gbs': n_e * world * e_steps * nsp * nsp * 8 / dt / 1e9,
                'api': 'pyjac_eval_jacob_host (pinned host rows in, pinned host Jacobians out)'}
         del yp, Pp, jp
+
+    # ---- BASELINE.json's other configurations on this rank count ------------------------
+    del jac
+    torch.cuda.empty_cache()
+    workloads = None
+    if not args.no_workloads and args.workload == 'gri30':
+        workloads = {}
+        for name in ('usc2', 'nc7', 'h2o2_pasr'):
+            try:
+                workloads[name] = side_workload(name, torch, dev, rank, world, barrier, max_over_ranks, peak)
+            except Exception as exc:                  # a side record must not cost the headline line
+                workloads[name] = {'error': str(exc).splitlines()[0][:200]}
 
     # ---- CPU baseline (rank 0, single GPU runs only) ----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = host_threads()
-        ref, kind = cpu_reference(mech)
-        v, ns, dt = time_cpu(ref, kind, P_h, y_h, threads, args.cpu_seconds)
-        cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': kind,
-               'sample': 'first %d states of the same batch, %.1f s, %d OpenMP threads' % (ns, dt, threads)}
+        ns_ = min(n, 1 << 18)
+        run, kind, how = cpu_reference(mech, P_h[:ns_], y_h[:ns_])
+        nc = sample_size(run, threads, ns_, args.cpu_seconds)
+        dt = run(nc, threads)
+        cpu = {'value': nc / dt, 'unit': UNIT, 'cores': threads, 'kind': kind,
+               'sample': 'first %d states of the same batch, %.1f s, %d OpenMP threads; %s' % (nc, dt, threads, how)}
 
     if rank == 0:
         line = {
@@ -336,14 +508,17 @@ def run_ours(args, rank, world, local_rank):
                                  'NSPxNSP Jacobian per state out (the scalar API layout)',
                        'plan': 'gs=%d states per block, %d threads, working set in %s memory'
                                % (ev.plan_gs, ev.plan_threads, 'global' if wsg else 'shared'),
-                       'parallelism': 'state batch sharded over %d GPU(s), no collective' % world},
+                       'parallelism': 'state batch sharded over %d GPU(s), no collective in the timed region of '
+                                      '`value`; `with_gather` adds the NCCL gather of the Jacobians to rank 0' % world},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': None if traffic is None else traffic * n,
+                         'traffic_source': None if traffic is None else
+                         'profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per state of an ncu --set full '
+                         'capture of this kernel (65 536 states), scaled to this batch -- not measured in this run',
                          'peak_source': peak_src, 'bytes_per_state': bytes_per_state,
-                         'kernel': 'pj5::k_eval<%d, %d, M_JAC%s>' % (ev.plan_gs, 384 if ev.plan_threads > 256 or not wsg else 512,
-                                                                     ', WSG' if wsg else ''),
-                         'kernel_ms': kernel_ms},
-            'e2e': e2e, 'cpu_baseline': cpu, 'gpu_launches': launches, 'clocks': clocks,
+                         'kernel': kernel_name, 'kernel_ms': kernel_ms},
+            'e2e': e2e, 'with_gather': with_gather, 'strong': strong, 'workloads': workloads,
+            'cpu_baseline': cpu, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)
     ev.close()
@@ -363,6 +538,8 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-workloads', action='store_true', help='leave out the sub-records of the other BASELINE configurations')
+    ap.add_argument('--no-gather', action='store_true', help='(N > 1) leave out the gather-to-rank-0 measurement')
     args = ap.parse_args()
     default_states = select_workload(args.workload)
     args.states = args.states or default_states

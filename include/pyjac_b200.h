@@ -68,6 +68,9 @@ int pyjac_mech_dims(const pyjac_mech* m, int dims[4]);
  * block size belong to the plan inside the table blob (pyjac_b200/plan.py).  Results do not
  * depend on this. */
 int pyjac_mech_tune(pyjac_mech* m, int blocks_per_sm);
+/* (mangled) symbol of the kernel that a call of mode 0 = eval_jacob, 1 = dydt, 2 = the rate routines
+ * launches for this mechanism's plan -- what a profiler lists */
+int pyjac_mech_kernel_name(const pyjac_mech* m, int mode, char* buf, size_t len);
 /* number of kernels launched through this handle since creation */
 long long pyjac_mech_launches(const pyjac_mech* m);
 

@@ -152,6 +152,52 @@ def build_cuda(name: str, mech: str, jobs: int = 8, force: bool = False, quiet: 
     return lib
 
 
+def harness_path(name: str) -> str:
+    return os.path.join(ref_dir(name), 'speedtest')
+
+
+def build_harness(name: str, jobs: int = 8, force: bool = False) -> str:
+    """The reference's own `speedtest` for mechanism `name` (built by :func:`build` before): its generated
+    C, tester.c.in (datafile "data.bin"), read_initial_conditions.c and timer.h compiled where they lie with
+    the reference's flags (libgen.py:43, performance_tester.py:480-482) -> oracle/_ref/<name>/speedtest.
+    `speedtest <num_odes> <num_threads>` in a directory holding data.bin prints "num_odes,ms": the CPU arm
+    of bench.py times the reference through it."""
+    from string import Template
+    out = ref_dir(name)
+    src = os.path.join(out, 'src')
+    exe = harness_path(name)
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) >= os.path.getmtime(lib_path(name)):
+        return exe
+    if not have_reference():
+        raise RuntimeError('reference sources not present at %s' % REF_ROOT)
+    home = os.path.join(REF_ROOT, 'pyjac', 'performance_tester')
+    with open(os.path.join(home, 'tester.c.in')) as fh:
+        main_c = Template(fh.read()).substitute(datafile='data.bin')
+    test_c = os.path.join(out, 'test.c')
+    with open(test_c, 'w') as fh:
+        fh.write(main_c)
+    cfiles = glob.glob(os.path.join(src, '**', '*.c'), recursive=True) + [test_c, os.path.join(home, 'read_initial_conditions.c')]
+    inc = ['-I', src, '-I', os.path.join(src, 'jacobs'), '-I', os.path.join(src, 'rates'), '-I', home]
+    flags = ['-std=c99', '-O3', '-mtune=native', '-fopenmp', '-D_DEFAULT_SOURCE']
+
+    def cc(f):
+        o = os.path.join(out, 'hobj_' + os.path.relpath(f, '/').replace('/', '_')[:-2] + '.o')
+        r = subprocess.run(['gcc'] + flags + inc + ['-c', f, '-o', o], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('gcc failed on %s:\n%s' % (f, r.stderr))
+        return o
+
+    with ThreadPoolExecutor(jobs) as ex:
+        objs = list(ex.map(cc, cfiles))
+    r = subprocess.run(['gcc', '-fopenmp', '-o', exe] + objs + ['-lm'], capture_output=True, text=True)
+    for o in objs:
+        os.remove(o)
+    os.remove(test_c)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n' + r.stderr)
+    return exe
+
+
 def speedtest_path(name: str) -> str:
     return os.path.join(ref_dir(name + '_speedtest'), 'speedtest')
 

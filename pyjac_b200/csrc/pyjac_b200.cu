@@ -496,6 +496,18 @@ int pyjac_mech_tune(pyjac_mech* m, int blocks_per_sm)
     return PYJAC_OK;
 }
 
+int pyjac_mech_kernel_name(const pyjac_mech* m, int mode, char* buf, size_t len)
+{
+    if (!m || !buf || !len || mode < 0 || mode > 2) return fail(PYJAC_EINVAL, "bad argument");
+    const void* fn = (mode == pj::M_JAC && m->has6) ? kernel6_for(m->plan6.gs, m->plan6.nt)
+                                                     : kernel_for(m->plan.gs, mode, m->plan.nt, m->plan.wsg);
+    if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable plan");
+    const char* name = nullptr;
+    CU(cudaFuncGetName(&name, fn));
+    std::snprintf(buf, len, "%s", name ? name : "?");
+    return PYJAC_OK;
+}
+
 long long pyjac_mech_launches(const pyjac_mech* m) { return m ? m->launches.load() : 0; }
 
 int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,

@@ -76,6 +76,18 @@ class Evaluator:
     def launches(self) -> int:
         return int(self.lib.pyjac_mech_launches(self._h))
 
+    def kernel_name(self, mode: int = 0) -> str:
+        """Demangled symbol of the kernel behind eval_jacob (mode 0), dydt (1) or the rate routines (2)."""
+        import subprocess
+        buf = ctypes.create_string_buffer(512)
+        _lib.check(self.lib.pyjac_mech_kernel_name(self._h, mode, buf, len(buf)))
+        name = buf.value.decode()
+        try:
+            out = subprocess.run(['c++filt', name], capture_output=True, text=True, timeout=10).stdout.strip()
+            return out or name
+        except Exception:
+            return name
+
     def make_current(self):
         """Select this mechanism for the reference-named entry points (pyjacob / cu_pyjacob)."""
         _lib.check(self.lib.pyjac_set_mechanism(self._h))

@@ -27,6 +27,7 @@ SIGNATURES = {
     'pyjac_mech_dims': (c_int, [c_void_p, POINTER(c_int)]),
     'pyjac_mech_tune': (c_int, [c_void_p, c_int]),
     'pyjac_mech_launches': (c_longlong, [c_void_p]),
+    'pyjac_mech_kernel_name': (c_int, [c_void_p, c_int, c_char_p, c_size_t]),
     'pyjac_eval_jacob_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
                                      c_void_p, c_int, c_longlong, c_void_p]),
     'pyjac_dydt_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
