@@ -87,6 +87,15 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
 int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
                    long long y_ss, long long y_sv, double* d_dy, long long o_ss,
                    long long o_sv, void* stream);
+/* Constant-volume dydt (the reference's `#define CONV` form, pyjac/core/rate_subs.py:2340-2485; compiled
+ * out upstream by header.h, mech_auxiliary.py:464-466, and not compilable as emitted -- DESIGN.md): d_rho holds
+ * one density per state in place of the pressure, dT/dt = -sum_k wdot_k u_k W_k / (rho cv_avg). */
+int pyjac_dydt_conv_dev(pyjac_mech* m, int n, const double* d_rho, const double* d_y,
+                        long long y_ss, long long y_sv, double* d_dy, long long o_ss,
+                        long long o_sv, void* stream);
+/* conv != 0: the reference-named dydt(t, rho, y, dy) of this handle is the constant-volume one -- what
+ * editing header.h to `#define CONV` selects in the reference; eval_jacob then fails (no such form exists). */
+int pyjac_mech_set_conv(pyjac_mech* m, int conv);
 /* Finite-difference Jacobian of dydt, the independent on-device check of eval_jacob; replaces
  * the reference's finite-difference comparison build (pyjac/performance_tester/fd_jacob.cu:23-95:
  * same CVODE-style increments, ATOL 1e-15, RTOL 1e-8).  order 1 = the reference's default forward

@@ -42,7 +42,11 @@ def have_reference() -> bool:
 
 
 def build(name: str, mech: str, last_spec=None, opt: str = '-O3', jobs: int = 8,
-          force: bool = False, quiet: bool = True) -> str:
+          force: bool = False, quiet: bool = True, conv: bool = False) -> str:
+    """conv: the constant-volume build -- the generator hard-wires `#define CONP` into the header.h it
+    emits (mech_auxiliary.py:464-466); the emitted copy under oracle/_ref/ is switched to `#define CONV`
+    before compiling, which is how a user of the reference selects it.  `name` should differ from the
+    constant-pressure build's."""
     out = ref_dir(name)
     src = os.path.join(out, 'src')
     lib = lib_path(name)
@@ -66,10 +70,32 @@ def build(name: str, mech: str, last_spec=None, opt: str = '-O3', jobs: int = 8,
     if res.returncode != 0:
         raise RuntimeError('reference codegen failed:\n' + res.stdout + res.stderr)
 
+    if conv:
+        hdr = os.path.join(src, 'header.h')
+        txt = open(hdr).read()
+        assert '#define CONP\n//#define CONV' in txt
+        with open(hdr, 'w') as fh:
+            fh.write(txt.replace('#define CONP\n//#define CONV', '//#define CONP\n#define CONV'))
+        # The constant-volume branch is dead code upstream and does not compile as emitted: the generator
+        # leaves out a comma (rate_subs.py:2361-2363 -> "eval_conc_rho (y[0]rho, ...") and a plus sign
+        # (rate_subs.py:2428-2430 -> "(cv[8] * y[9])(cv[9] * y_N)").  The two characters are put back in the
+        # emitted copy; everything else is the generator's text.
+        dy_c = os.path.join(src, 'dydt.c')
+        txt = open(dy_c).read()
+        assert 'eval_conc_rho (y[0]rho,' in txt
+        txt = txt.replace('eval_conc_rho (y[0]rho,', 'eval_conc_rho (y[0], rho,')
+        import re as _re
+        txt, nfix = _re.subn(r'\)\(cv\[(\d+)\] \* y_N\)', r') + (cv[\1] * y_N)', txt)
+        assert nfix == 1
+        with open(dy_c, 'w') as fh:
+            fh.write(txt)
     cfiles = [f for f in glob.glob(os.path.join(src, '**', '*.c'), recursive=True)]
+    if conv:
+        # eval_jacob has no constant-volume form upstream (its dydt prototype no longer matches)
+        cfiles = [f for f in cfiles if 'jacob' not in os.path.basename(f) and os.sep + 'jacobs' + os.sep not in f]
     cfiles.append(os.path.join(HERE, 'ref_batch.c'))
     inc = ['-I', src, '-I', os.path.join(src, 'jacobs'), '-I', os.path.join(src, 'rates')]
-    flags = ['-std=c99', opt, '-mtune=native', '-fPIC', '-fopenmp', '-D_DEFAULT_SOURCE']
+    flags = ['-std=c99', opt, '-mtune=native', '-fPIC', '-fopenmp', '-D_DEFAULT_SOURCE'] + (['-DREF_NO_JACOB'] if conv else [])
 
     def cc(f):
         o = os.path.join(out, 'obj_' + os.path.relpath(f, '/').replace('/', '_')[:-2] + '.o')

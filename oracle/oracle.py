@@ -56,7 +56,7 @@ class Oracle:
         L.oracle_load.restype = ctypes.c_void_p
         L.oracle_load.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         L.oracle_free.argtypes = [ctypes.c_void_p]
-        for fn in ('oracle_eval_jacob_batch', 'oracle_dydt_batch'):
+        for fn in ('oracle_eval_jacob_batch', 'oracle_dydt_batch', 'oracle_dydt_conv_batch'):
             getattr(L, fn).argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int]
         L.oracle_rates_batch.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_dp] * 7 + [ctypes.c_int]
         data = _blob.pack(ref_tables.build(mech))
@@ -88,6 +88,13 @@ class Oracle:
         P, y = self._prep(P, y)
         dy = np.zeros((y.shape[0], self.NSP))
         self.lib.oracle_dydt_batch(self._h, y.shape[0], _p(P), _p(y), _p(dy), nthreads)
+        return dy
+
+    def dydt_conv(self, rho, y, nthreads: int = 0) -> np.ndarray:
+        """constant-volume dydt(t, rho, y, dy) (rate_subs.py:2340-2485)"""
+        rho, y = self._prep(rho, y)
+        dy = np.zeros((y.shape[0], self.NSP))
+        self.lib.oracle_dydt_conv_batch(self._h, y.shape[0], _p(rho), _p(y), _p(dy), nthreads)
         return dy
 
     def rates(self, P, y, nthreads: int = 0):

@@ -115,14 +115,22 @@ int oracle_nr(const OracleMech* m) { return m->nr; }
 int oracle_nrev(const OracleMech* m) { return m->nrev; }
 int oracle_npd(const OracleMech* m) { return m->npd; }
 
-/* rs:27-146 (A > 0 forms) */
+/* rs:27-146: forms 0-3 for A > 0 (a[1] = log A), 4-7 for A < 0 (rs:108-141, a[1] = A) */
 static double arrhenius(const double* a, double T, double logT)
 {
     switch ((int)a[0]) {
     case 0: return a[1];
     case 1: return exp(a[1] + a[2] * logT);
     case 2: return exp(a[1] - (a[3] / T));
-    default: return exp(a[1] + a[2] * logT - (a[3] / T));
+    case 3: return exp(a[1] + a[2] * logT - (a[3] / T));
+    case 4: {
+        double k = a[1];
+        for (int i = 0; i < (int)a[2]; ++i) k = k * T;
+        return k;
+    }
+    case 5: return a[1] * exp(a[2] * logT);
+    case 6: return a[1] * exp(-(a[3] / T));
+    default: return a[1] * exp(a[2] * logT - (a[3] / T));
     }
 }
 
@@ -239,6 +247,31 @@ static double conc_prod_times(const int* sp, const int* nu, int n, const double*
     return first ? tail : p * tail;
 }
 
+/* rs:652-655: an irreversible reaction has its rate-constant expression printed in line after the
+ * concentrations, `C[a] * C[b] * <expr>`; for A < 0 <expr> is itself a product (rs:108-141) and C
+ * evaluates the whole line left to right */
+static double conc_prod_times_inline(const int* sp, const int* nu, int n, const double* C,
+                                     const double* a, double T, double logT)
+{
+    int form = (int)a[0];
+    int first = 1;
+    double p = 0.0;
+    if (form < 4) return conc_prod_times(sp, nu, n, C, arrhenius(a, T, logT));
+    for (int k = 0; k < n; ++k)
+        for (int r = 0; r < nu[k]; ++r) {
+            if (first) { p = C[sp[k]]; first = 0; } else p = p * C[sp[k]];
+        }
+    if (first) return arrhenius(a, T, logT);
+    p = p * a[1];
+    if (form == 4) {
+        for (int i = 0; i < (int)a[2]; ++i) p = p * T;
+        return p;
+    }
+    if (form == 5) return p * exp(a[2] * logT);
+    if (form == 6) return p * exp(-(a[3] / T));
+    return p * exp(a[2] * logT - (a[3] / T));
+}
+
 static double kc_exponent(const int* off, const double* tmid, const double* lo, const double* hi,
                           int i, double T, double logT)
 {
@@ -284,6 +317,11 @@ void oracle_eval_rxn_rates(const OracleMech* m, double T, double pres, const dou
             double Tred = ((2.0 / T) - cr[0]) / cr[1];
             double Pred = (2.0 * log10(pres) - cr[2]) / cr[3];
             kf = cheb_kf(m, i, Tred, Pred);
+        } else if (!(m->rx_flags[i] & F_REV)) {
+            fwd[i] = conc_prod_times_inline(m->reac_sp + m->reac_off[i], m->reac_nu + m->reac_off[i],
+                                            m->reac_off[i + 1] - m->reac_off[i], C,
+                                            m->arr_main + 4 * i, T, logT);
+            continue;
         } else kf = arrhenius(m->arr_main + 4 * i, T, logT);
         fwd[i] = conc_prod_times(m->reac_sp + m->reac_off[i], m->reac_nu + m->reac_off[i],
                                  m->reac_off[i + 1] - m->reac_off[i], C, kf);
@@ -432,6 +470,78 @@ void oracle_dydt(const OracleMech* m, double t, double pres, const double* y, do
         if (first) { s = v; first = 0; } else s = s + v;
     }
     dy[0] = (-1.0 / (rho * cp_avg)) * (s);
+    for (int k = 0; k < n - 1; ++k) dy[k + 1] *= (m->sp_mw[k] / rho);
+    free(w);
+}
+
+/* rs:1708-1800: concentrations from the density; the pressure follows */
+void oracle_eval_conc_rho(const OracleMech* m, double T, double rho, const double* y,
+                          double* y_N, double* mw_avg, double* pres, double* conc)
+{
+    int n = m->nsp;
+    double s = 0.0;
+    for (int k = 0; k < n - 1; ++k) s = (k == 0) ? y[0] : s + y[k];
+    *y_N = 1.0 - (s);
+    double w = 0.0;
+    for (int k = 0; k < n - 1; ++k) {
+        double t = (y[k] * m->sp_mw_inv[k]);
+        w = (k == 0) ? t : w + t;
+    }
+    if (n > 1) w = w + ((*y_N) * m->sp_mw_inv[n - 1]); else w = ((*y_N) * m->sp_mw_inv[n - 1]);
+    *mw_avg = 1.0 / w;
+    *pres = rho * m->ru8 * T / (*mw_avg);
+    for (int k = 0; k < n - 1; ++k) conc[k] = rho * y[k] * m->sp_mw_inv[k];
+    conc[n - 1] = rho * (*y_N) * m->sp_mw_inv[n - 1];
+}
+
+/* rs:1876-1945 */
+void oracle_eval_u(const OracleMech* m, double T, double* u)
+{
+    for (int k = 0; k < m->nsp; ++k) {
+        const double* c = (T <= m->sp_tmid[k]) ? m->sp_h_lo + 6 * k : m->sp_h_hi + 6 * k;
+        u[k] = m->sp_ru_mw[k] * (c[0] + T * (c[1] - 1.0 + T * (c[2] + T * (c[3] + T * (c[4] + c[5] * T)))));
+    }
+}
+
+/* rs:1947-2019 */
+void oracle_eval_cv(const OracleMech* m, double T, double* cv)
+{
+    for (int k = 0; k < m->nsp; ++k) {
+        const double* a = (T <= m->sp_tmid[k]) ? m->sp_lo + 7 * k : m->sp_hi + 7 * k;
+        cv[k] = m->sp_ru_mw[k] * (a[0] - 1.0 + T * (a[1] + T * (a[2] + T * (a[3] + a[4] * T))));
+    }
+}
+
+/* rs:2340-2485 (CONV, compiled out upstream by header.h's #define CONP, mech_auxiliary.py:464-466): the second
+ * argument is the density */
+void oracle_dydt_conv(const OracleMech* m, double t, double rho, const double* y, double* dy)
+{
+    (void)t;
+    int n = m->nsp;
+    double* w = (double*)malloc(sizeof(double) * (3 * (size_t)n + 2 * (size_t)m->nr + m->npd + 4));
+    double *conc = w, *cv = w + n, *u = w + 2 * n, *fwd = w + 3 * n, *rev = fwd + m->nr,
+           *pm = rev + m->nr;
+    double y_N, mw_avg, pres, dy_N;
+    oracle_eval_conc_rho(m, y[0], rho, &y[1], &y_N, &mw_avg, &pres, conc);
+    oracle_eval_rxn_rates(m, y[0], pres, conc, fwd, rev);
+    oracle_get_rxn_pres_mod(m, y[0], pres, conc, pm);
+    oracle_eval_spec_rates(m, fwd, rev, pm, &dy[1], &dy_N);
+    oracle_eval_cv(m, y[0], cv);
+    double cv_avg = 0.0;
+    for (int k = 0; k < n - 1; ++k) {
+        double v = (cv[k] * y[k + 1]);
+        cv_avg = (k == 0) ? v : cv_avg + v;
+    }
+    cv_avg = (n > 1) ? cv_avg + (cv[n - 1] * y_N) : (cv[n - 1] * y_N);
+    oracle_eval_u(m, y[0], u);
+    double s = 0.0;
+    int first = 1;
+    for (int k = 0; k < n; ++k) {
+        if (!m->sp_seen[k]) continue;
+        double v = ((k < n - 1 ? dy[k + 1] : dy_N) * u[k] * m->sp_mw[k]);
+        if (first) { s = v; first = 0; } else s = s + v;
+    }
+    dy[0] = (-1.0 / (rho * cv_avg)) * (s);
     for (int k = 0; k < n - 1; ++k) dy[k + 1] *= (m->sp_mw[k] / rho);
     free(w);
 }
@@ -894,6 +1004,17 @@ void oracle_dydt_batch(const OracleMech* m, int n, const double* pres, const dou
     #pragma omp parallel for
     for (int s = 0; s < n; ++s)
         oracle_dydt(m, 0.0, pres[s], y + (size_t)s * m->nsp, dy + (size_t)s * m->nsp);
+}
+
+void oracle_dydt_conv_batch(const OracleMech* m, int n, const double* rho, const double* y,
+                            double* dy, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    #pragma omp parallel for
+    for (int s = 0; s < n; ++s)
+        oracle_dydt_conv(m, 0.0, rho[s], y + (size_t)s * m->nsp, dy + (size_t)s * m->nsp);
 }
 
 /* conc[n][NSP], fwd[n][NR], rev[n][NREV], pres_mod[n][NPD], spec_rates[n][NSP] */

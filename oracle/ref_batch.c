@@ -23,6 +23,7 @@ int ref_fwd_rates(void) { return FWD_RATES; }
 int ref_rev_rates(void) { return REV_RATES; }
 int ref_pres_mod_rates(void) { return PRES_MOD_RATES; }
 
+#ifndef REF_NO_JACOB          /* the constant-volume build (build_ref.py conv=True) has no eval_jacob */
 /* jac may be NULL: results are then discarded exactly like tester.c.in does. */
 void ref_eval_jacob_batch(int n, const double* pres, const double* y, double* jac, int nthreads)
 {
@@ -42,6 +43,8 @@ void ref_eval_jacob_batch(int n, const double* pres, const double* y, double* ja
         }
     }
 }
+
+#endif
 
 void ref_dydt_batch(int n, const double* pres, const double* y, double* dy, int nthreads)
 {

@@ -41,10 +41,24 @@ def is_int(v) -> bool:
 
 
 def arrhenius_form(A: float, b: float, E: float):
-    """rs:27-146 for A > 0: returns [form, c0, b, E];  kf =
-    0: c0 | 1: exp(c0 + b*logT) | 2: exp(c0 - (E/T)) | 3: exp(c0 + b*logT - (E/T))."""
+    """rs:27-146: returns [form, c0, b, E];  A > 0 (c0 = log A):  kf =
+    0: c0 (= A) | 1: exp(c0 + b*logT) | 2: exp(c0 - (E/T)) | 3: exp(c0 + b*logT - (E/T));
+    A < 0 (rs:108-141, c0 = A):  4: c0 * T^b for an integer-valued b | 5: c0 * exp(b*logT) |
+    6: c0 * exp(-(E/T)) | 7: c0 * exp(b*logT - (E/T))."""
+    if A < 0:
+        if isinstance(b, int):
+            raise NotImplementedError('integer-typed temperature exponent')
+        if not E:
+            if not b:
+                return [0.0, float(str(A)), 0.0, 0.0]
+            if is_int(b):
+                return [4.0, float(str(A)), float(int(b)), 0.0]
+            return [5.0, q('{:.16e}', A), float(str(b)), 0.0]
+        if not b:
+            return [6.0, q('{:.16e}', A), 0.0, q('{:.16e}', E)]
+        return [7.0, q('{:.16e}', A), float(str(b)), q('{:.16e}', E)]
     if not A > 0:
-        raise NotImplementedError('non-positive pre-exponential factor')
+        raise NotImplementedError('zero pre-exponential factor')
     if isinstance(b, int):
         raise NotImplementedError('integer-typed temperature exponent')
     logA = math.log(A)

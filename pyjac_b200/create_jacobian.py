@@ -151,8 +151,9 @@ def create_jacobian(lang, mech_name=None, therm_name=None, gas=None, optimize_ca
                     initial_state='', num_blocks=8, num_threads=64, no_shared=False,
                     L1_preferred=True, multi_thread=None, force_optimize=False,
                     build_path='./out/', last_spec=None, skip_jac=False, auto_diff=False,
-                    gs: int = 0, threads: int = 0) -> Mechanism:
-    """Export the mechanism ``mech_name`` (Chemkin format, optional ``therm_name``) for the
+                    gs: int = 0, threads: int = 0, conp: bool = True) -> Mechanism:
+    """Export the mechanism ``mech_name`` (Chemkin format with optional ``therm_name``, or a Cantera ``.cti``
+    file -- read without Cantera, :mod:`pyjac_b200.cti_interpret`) for the
     B200 library into ``build_path``.
 
     Only ``lang='cuda'`` exists (there is no CPU back end).  The code-generation tuning knobs
@@ -160,6 +161,9 @@ def create_jacobian(lang, mech_name=None, therm_name=None, gas=None, optimize_ca
     ``L1_preferred``, ``multi_thread``, ``force_optimize``) have nothing to act on and are
     accepted and ignored; ``gas`` (a Cantera object), ``auto_diff`` and ``initial_state`` are
     rejected.  ``gs`` / ``threads`` choose the Jacobian kernel's plan (0 = automatic).
+    ``conp=False`` exports the constant-volume problem: header.h then says ``#define CONV`` (the reference
+    hard-wires CONP there, mech_auxiliary.py:464-466, and a user edits the file) and ``dydt(t, rho, y, dy)``
+    of a library built from this directory takes the density; ``eval_jacob`` has no such form.
     """
     if lang != 'cuda':
         raise ValueError("pyjac_b200 only targets CUDA (sm_100a); lang=%r" % (lang,))
@@ -169,15 +173,17 @@ def create_jacobian(lang, mech_name=None, therm_name=None, gas=None, optimize_ca
         raise NotImplementedError('auto_diff / initial_state are outside the hot path')
     if mech_name is None:
         raise ValueError('mech_name is required')
-    mech = Mechanism.from_chemkin(mech_name, therm_name, last_spec)
+    mech = Mechanism.from_file(mech_name, therm_name, last_spec)
     os.makedirs(build_path, exist_ok=True)
     with open(os.path.join(build_path, HEADER_FILE), 'w') as fh:
         fh.write(_header(mech))
     for name, text in _HEADERS.items():
+        if name == 'header.h' and not conp:
+            text = text.replace('#define CONP\n//#define CONV', '//#define CONP\n#define CONV')
         with open(os.path.join(build_path, name), 'w') as fh:
             fh.write(text)
     if not skip_jac:
-        T = tables.build(mech, gs=gs, threads=threads)
+        T = tables.build(mech, gs=gs, threads=threads, conv=not conp)
         with open(os.path.join(build_path, TABLE_FILE), 'wb') as fh:
             fh.write(blob.pack(T))
     return mech

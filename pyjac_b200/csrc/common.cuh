@@ -9,7 +9,7 @@ namespace pj {
 enum : int {
     F_REV = 1, F_THD = 2, F_PDEP = 4, F_LOW = 8, F_TROE = 16, F_SRI = 32, F_PMT = 64,
     F_PMT_INJ = 128, F_TROE_T2 = 256, F_SRI5 = 512, F_SRI5_DT = 1024, F_NO_T = 2048,
-    F_EFFN1 = 4096, F_HAS_LAST = 1 << 13, F_WANT_PMT = 1 << 16, F_EFF_SLOTS = 1 << 17,
+    F_EFFN1 = 4096, F_HAS_LAST = 1 << 13, F_NEGA = 1 << 14, F_WANT_PMT = 1 << 16, F_EFF_SLOTS = 1 << 17,
     F_PLOG = 1 << 18, F_CHEB = 1 << 19,
     NRE_SHIFT = 20, NPR_SHIFT = 24, NPAR = 32
 };
@@ -49,6 +49,8 @@ struct IO {
     const double* y;
     long long y_ss, y_sv;
     int in_conc;     // 1: the input row is [T, C_0 .. C_{NSP-1}] (concentrations given)
+    int conv;        // 1 (dydt / rate routines): constant volume -- `pres` holds densities, the energy
+                     // equation uses u and cv (rate_subs.py:2340-2485)
     double* jac;
     int jac_layout;
     long long jac_ld;

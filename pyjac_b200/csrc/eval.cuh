@@ -342,6 +342,7 @@ __device__ __forceinline__ void reaction(const Mem<WSG>& mem, const Tables& tb, 
         kr = V{y2[2], y2[3]};
     }
     if (!isrev) kr = V{0.0, 0.0};
+    if (fl & F_NEGA) { kf = V{-kf.x, -kf.y}; kr = V{-kr.x, -kr.y}; }   // A < 0 (rs:108-141)
     V f = vmul(kf, vmul(c0, c1)), r = vmul(kr, vmul(c3, c4));
     if (three) { f = vmul(f, c2); r = vmul(r, c5); }
     const V net = vsub(f, r);
@@ -560,8 +561,10 @@ __device__ __forceinline__ void reaction_plain(const Mem<WSG>& mem, const Tables
     double ev[4];
     exp_n<4>(ex, ev);
     const bool isrev = fl & F_REV;
-    const V kf{ev[0], ev[1]};
-    const V kr{isrev ? ev[2] : 0.0, isrev ? ev[3] : 0.0};
+    // A < 0 (rs:108-141): the table holds log|A|, the sign goes onto both rate constants
+    const double sg = (SPECIAL && (fl & F_NEGA)) ? -1.0 : 1.0;
+    const V kf{sg * ev[0], sg * ev[1]};
+    const V kr{isrev ? sg * ev[2] : 0.0, isrev ? sg * ev[3] : 0.0};
     // d(rate)/dC per occupied slot; f = d0 * c0, r = -d3 * c3
     V o0 = c1, o1 = c0, o3 = c4, o4 = c3, o2 = vmul(c0, c1), o5 = vmul(c3, c4);
     if (three) { o0 = vmul(c1, c2); o1 = vmul(c0, c2); o3 = vmul(c4, c5); o4 = vmul(c3, c5); }
@@ -717,14 +720,19 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         sumYW = sub_sum<GS>(sumYW);
         if (sub == 0) {
             const double T[2] = {y0[0], y1[0]};
-            const double P[2] = {io.pres[i0], io.pres[i1]};
+            double P[2] = {io.pres[i0], io.pres[i1]};
             const double yN[2] = {1.0 - sumY.x, 1.0 - sumY.y};
             const double sw[2] = {sumYW.x, sumYW.y}, sy[2] = {sumY.x, sumY.y};
             double o[8][2];
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
                 const double mw = inc ? sw[g2] / sy[g2] : 1.0 / (sw[g2] + yN[g2] * __ldg(tb.sp_iw + last));
-                const double rho = inc ? sw[g2] : P[g2] * mw / (tb.ru * T[g2]);
+                double rho = inc ? sw[g2] : P[g2] * mw / (tb.ru * T[g2]);
+                if (MODE != M_JAC && io.conv) {
+                    // constant volume: the caller's variable is the density, the pressure follows (rs:1708-1800)
+                    rho = P[g2];
+                    P[g2] = rho * tb.ru * T[g2] / mw;
+                }
                 const double rho_inv = 1.0 / rho;
                 if (MODE == M_RATES && io.scal3 && (g2 ? s0 + 1 : s0) < io.n) {
                     double* q = io.scal3 + (g2 ? s0 + 1 : s0) * 3;
@@ -808,9 +816,11 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                     const double* c = tb.sp_nasa + (k * 2 + (Tv[g] <= tmid ? 0 : 1)) * 16;
                     const double t = Tv[g];
                     ck[g] = inc ? (g ? Yv.y : Yv.x) : rh[g] * Yk[g] * iw;
-                    cp[g] = ruw * (c[0] + t * (c[1] + t * (c[2] + t * (c[3] + c[4] * t))));
+                    // constant volume (dydt only): cv and u in place of cp and h (rs:1876-2019), c[11] = a0 - 1
+                    const double a0 = (MODE != M_JAC && io.conv) ? c[11] : c[0];
+                    cp[g] = ruw * (a0 + t * (c[1] + t * (c[2] + t * (c[3] + c[4] * t))));
                     const double hh = c[6] + t * (c[7] + t * (c[8] + c[9] * t));
-                    hW[g] = ruw * (c[5] + t * (c[0] + t * hh)) * wk;
+                    hW[g] = ruw * (c[5] + t * (a0 + t * hh)) * wk;
                     const double dcp = ruw * (c[1] + t * (2.0 * c[2] + t * (3.0 * c[3] + 4.0 * c[4] * t)));
                     cpavg[g] += Yk[g] * cp[g];
                     wdcp[g] += Yk[g] * dcp;
@@ -861,8 +871,8 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 } else {
                     const bool has3 = ((q2.z & 0xFFFFu) != nsp_f) || (((unsigned)q2.w >> 16) != nsp_f);
                     const bool three = __any_sync(0xffffffffu, has3);
-                    // rounds holding a PLOG / Chebyshev reaction take the build of the routine that knows them
-                    if (__any_sync(0xffffffffu, (q2.x & (F_PLOG | F_CHEB)) != 0))
+                    // rounds holding a PLOG / Chebyshev / negative-A reaction take the build of the routine that knows them
+                    if (__any_sync(0xffffffffu, (q2.x & (F_PLOG | F_CHEB | F_NEGA)) != 0))
                         reaction_plain<GS, MODE, true, WSG>(mem, tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);
                     else
                         reaction_plain<GS, MODE, false, WSG>(mem, tb, pl, io, out, aSP, aRX, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT);

@@ -358,6 +358,7 @@ __device__ __forceinline__ void reaction(const Mem<false>& mem, const Tables& tb
         kr = V{y2[2], y2[3]};
     }
     if (!isrev) kr = V{0.0, 0.0};
+    if (fl & F_NEGA) { kf = V{-kf.x, -kf.y}; kr = V{-kr.x, -kr.y}; }   // A < 0 (rs:108-141)
     const V f = vmul(vmul(kf, vmul(c0, c1)), c2), r = vmul(vmul(kr, vmul(c3, c4)), c5);
     const V net = vsub(f, r);
     V pmt{0.0, 0.0};
@@ -537,8 +538,10 @@ __device__ __forceinline__ void reaction_plain(const Mem<false>& mem, const Tabl
     double ev[4];
     exp_n<4>(ex, ev);
     const bool isrev = fl & F_REV;
-    const V kf{ev[0], ev[1]};
-    const V kr{isrev ? ev[2] : 0.0, isrev ? ev[3] : 0.0};
+    // A < 0 (rs:108-141): the table holds log|A|, the sign goes onto both rate constants
+    const double sg = (SPECIAL && (fl & F_NEGA)) ? -1.0 : 1.0;
+    const V kf{sg * ev[0], sg * ev[1]};
+    const V kr{isrev ? sg * ev[2] : 0.0, isrev ? sg * ev[3] : 0.0};
     // d(rate)/dC per occupied slot; f = d0 * c0, r = -d3 * c3
     V o0 = c1, o1 = c0, o3 = c4, o4 = c3, o2 = vmul(c0, c1), o5 = vmul(c3, c4);
     if (three) { o0 = vmul(c1, c2); o1 = vmul(c0, c2); o3 = vmul(c4, c5); o4 = vmul(c3, c5); }
@@ -781,7 +784,7 @@ k_jac6(const __grid_constant__ Tables tb, const __grid_constant__ Plan6 pl, cons
                 } else {
                     const bool has3 = ((q2.z & 0xFFFFu) != nsp_f) || ((q2.w >> 16) != nsp_f);
                     const bool three = __any_sync(0xffffffffu, has3);
-                    if (__any_sync(0xffffffffu, (q2.x & (F_PLOG | F_CHEB)) != 0))
+                    if (__any_sync(0xffffffffu, (q2.x & (F_PLOG | F_CHEB | F_NEGA)) != 0))
                         reaction_plain<GS, true>(mem, tb, pl, aSP, aRX, aXC, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT, rho_inv, nmwr);
                     else
                         reaction_plain<GS, false>(mem, tb, pl, aSP, aRX, aXC, aRAW, aSC, aSD + buf * RB, p, valid, three, q0, q1, q2, q3, T, logT, iT, rho_inv, nmwr);

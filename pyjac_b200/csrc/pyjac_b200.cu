@@ -38,6 +38,7 @@ struct pyjac_mech {
     std::atomic<long long> launches{0};
     std::mutex mu;                   // launch configuration and the shared scratch of a wsg plan
     std::vector<int> fwd_map, back_map;   // species: internal position -> original index and back (apply_mask)
+    int conv = 0;                    // 1: the reference-named dydt is the constant-volume one (header.h: #define CONV)
     char* ws = nullptr;              // per-block working sets of a plan with wsg = 1
     size_t ws_bytes = 0;
     cudaEvent_t ws_ev = nullptr;     // orders the launches that share `ws` across streams
@@ -375,6 +376,10 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     DeviceGuard guard(device);
     pyjac_mech* m = new pyjac_mech();
     m->device = device;
+    {
+        const pjt::Entry* me = pjt::find(blob, "meta");
+        m->conv = me->count > 3 ? ((const int*)((const char*)blob + me->offset))[3] != 0 : 0;
+    }
     Tables& t = m->tb;
     t.nsp = d[0]; t.nr = d[1]; t.nrev = d[2]; t.npd = d[3]; t.nraw = d[4];
     t.first_pm = d[8]; t.npm = d[9]; t.nplog = d[5]; t.ncheb = d[6];
@@ -527,15 +532,36 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
     return launch(m, pj::M_JAC, io, (cudaStream_t)stream);
 }
 
+static int dydt_dev(pyjac_mech* m, int n, const double* d_var, const double* d_y, long long y_ss, long long y_sv,
+                    double* d_dy, long long o_ss, long long o_sv, int conv, void* stream)
+{
+    if (!m || n < 0 || (n && (!d_var || !d_y || !d_dy))) return fail(PYJAC_EINVAL, "bad argument");
+    IO io{};
+    io.n = n; io.pres = d_var; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
+    io.dy = d_dy; io.dy_ss = o_ss; io.dy_sv = o_sv;
+    io.conv = conv;
+    return launch(m, pj::M_DYDT, io, (cudaStream_t)stream);
+}
+
 int pyjac_dydt_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
                    long long y_ss, long long y_sv, double* d_dy, long long o_ss,
                    long long o_sv, void* stream)
 {
-    if (!m || n < 0 || (n && (!d_pres || !d_y || !d_dy))) return fail(PYJAC_EINVAL, "bad argument");
-    IO io{};
-    io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
-    io.dy = d_dy; io.dy_ss = o_ss; io.dy_sv = o_sv;
-    return launch(m, pj::M_DYDT, io, (cudaStream_t)stream);
+    return dydt_dev(m, n, d_pres, d_y, y_ss, y_sv, d_dy, o_ss, o_sv, 0, stream);
+}
+
+int pyjac_dydt_conv_dev(pyjac_mech* m, int n, const double* d_rho, const double* d_y,
+                        long long y_ss, long long y_sv, double* d_dy, long long o_ss,
+                        long long o_sv, void* stream)
+{
+    return dydt_dev(m, n, d_rho, d_y, y_ss, y_sv, d_dy, o_ss, o_sv, 1, stream);
+}
+
+int pyjac_mech_set_conv(pyjac_mech* m, int conv)
+{
+    if (!m) return fail(PYJAC_EINVAL, "bad argument");
+    m->conv = conv ? 1 : 0;
+    return PYJAC_OK;
 }
 
 // Finite-difference Jacobian of dydt on the device: the independent self-check of eval_jacob
@@ -808,8 +834,9 @@ static int scalar_state(pyjac_mech* m, double pres, const double* y, double* out
     std::memcpy(s->h, y, (size_t)nsp * 8);
     s->h[nsp] = pres;
     CU(cudaMemcpyAsync(s->d_in, s->h, in_b, cudaMemcpyHostToDevice, s->st));
+    if (jac && m->conv) return fail(PYJAC_EINVAL, "eval_jacob has no constant-volume form (the reference emits none either)");
     if (jac) rc = pyjac_eval_jacob_dev(m, 1, s->d_in + nsp, s->d_in, nsp, 1, s->d_out, PYJAC_JAC_STATE_MAJOR, 0, s->st);
-    else rc = pyjac_dydt_dev(m, 1, s->d_in + nsp, s->d_in, nsp, 1, s->d_out, nsp, 1, s->st);
+    else rc = dydt_dev(m, 1, s->d_in + nsp, s->d_in, nsp, 1, s->d_out, nsp, 1, m->conv, s->st);
     if (rc) { cudaStreamSynchronize(s->st); return rc; }
     CU(cudaMemcpyAsync(s->h, s->d_out, out_b, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));

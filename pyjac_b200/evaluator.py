@@ -131,15 +131,16 @@ class Evaluator:
                                                  lay, ld, self._stream(stream)))
         return out
 
-    def dydt(self, P, y, out=None, y_layout: str = 'rows', stream=None):
+    def dydt(self, P, y, out=None, y_layout: str = 'rows', stream=None, conv: bool = False):
+        """conv: constant volume -- ``P`` then holds one density per state (rate_subs.py:2340-2485)."""
         torch = self._torch
         self._check_dev(P, y, out)
         n, ss, sv = self._strides(y, y_layout)
         if out is None:
             out = torch.empty_like(y)
         assert out.shape == y.shape and out.is_contiguous()
-        _lib.check(self.lib.pyjac_dydt_dev(self._h, n, _ptr(P), _ptr(y), ss, sv, _ptr(out), ss, sv,
-                                           self._stream(stream)))
+        fn = self.lib.pyjac_dydt_conv_dev if conv else self.lib.pyjac_dydt_dev
+        _lib.check(fn(self._h, n, _ptr(P), _ptr(y), ss, sv, _ptr(out), ss, sv, self._stream(stream)))
         return out
 
     def fd_jacob(self, P, y, order: int = 6, r_cap: float = 0.0, out=None, stream=None):

@@ -32,6 +32,9 @@ SIGNATURES = {
                                      c_void_p, c_int, c_longlong, c_void_p]),
     'pyjac_dydt_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
                                c_void_p, c_longlong, c_longlong, c_void_p]),
+    'pyjac_dydt_conv_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
+                                    c_void_p, c_longlong, c_longlong, c_void_p]),
+    'pyjac_mech_set_conv': (c_int, [c_void_p, c_int]),
     'pyjac_fd_jacob_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p]),
     'pyjac_rates_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -59,6 +59,26 @@ class Mechanism:
         return cls.finalize(elems, specs, reacs, last_spec)
 
     @classmethod
+    def from_cti(cls, mech_name: str, last_spec: Optional[str] = None) -> 'Mechanism':
+        """A Cantera ``.cti`` file, read without Cantera (:mod:`pyjac_b200.cti_interpret`; the reference needs
+        ``cantera.Solution`` for this, mech_interpret.py:886-1137)."""
+        from . import cti_interpret
+        elems, specs, reacs = cti_interpret.read_mech_cti(mech_name)
+        if not specs or not reacs:
+            raise mech_interpret.MechanismError('no species / reactions found in %s' % mech_name)
+        return cls.finalize(elems, specs, reacs, last_spec)
+
+    @classmethod
+    def from_file(cls, mech_name: str, therm_name: Optional[str] = None, last_spec: Optional[str] = None) -> 'Mechanism':
+        """By extension, as the reference's create_jacobian does (create_jacobian.py:3476-3489): ``.cti`` ->
+        the Cantera-format reader, anything else -> Chemkin."""
+        if mech_name.lower().endswith('.cti'):
+            return cls.from_cti(mech_name, last_spec)
+        if mech_name.lower().endswith(('.xml', '.yaml', '.yml')):
+            raise mech_interpret.MechanismError('only Chemkin and .cti mechanism files are read (no Cantera here)')
+        return cls.from_chemkin(mech_name, therm_name, last_spec)
+
+    @classmethod
     def finalize(cls, elems, specs, reacs, last_spec: Optional[str] = None) -> 'Mechanism':
         last = pick_last_species(specs, last_spec)
         fwd, back = species_mappings(len(specs), last)

@@ -54,6 +54,7 @@ F_REV, F_THD, F_PDEP, F_LOW, F_TROE, F_SRI = 1, 2, 4, 8, 16, 32
 F_PMT, F_PMT_INJ, F_TROE_T2, F_SRI5, F_SRI5_DT, F_NO_T = 64, 128, 256, 512, 1024, 2048
 F_EFFN1 = 4096         # third-body (non fall-off) reaction with a collider list: n' += 1
 F_HAS_LAST = 1 << 13   # (Jacobian kernel record only) an occupied slot holds the last species
+F_NEGA = 1 << 14       # A < 0 (rs:108-141): the record holds log|A|, kf and kr take the sign
 F_WANT_PMT = 1 << 16   # the kernel stores pres_mod_temp as a raw value
 F_EFF_SLOTS = 1 << 17  # ... and pres_mod_temp * (alpha_j - 1) for each listed collider j
 F_PLOG = 1 << 18       # rate constant interpolated in log P between Arrhenius sets (plog_*)
@@ -94,7 +95,7 @@ def _nasa_row(a) -> List[float]:
             a[6] - a[0], a[0] - 1.0, a[2] / 6.0, a[3] / 12.0, a[4] / 20.0, 0.0]
 
 
-def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, streams=None) -> Dict[str, np.ndarray]:
+def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, streams=None, conv: bool = False) -> Dict[str, np.ndarray]:
     """gs / threads: states per block and block size of the Jacobian kernel's plan (0 = automatic).
     ws_global: True puts the per-block working set in global memory instead of shared memory, False
     forbids that; None = automatic (global memory when fewer than plan.SMEM_MIN_GS states fit in
@@ -102,7 +103,9 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, stream
     streams: True adds the record streams of k_jac6 (plan6.py: table items staged through a shared-memory
     ring by bulk-asynchronous copies) and makes eval_jacob run on them when the working set lives in
     shared memory; None / False = eval_jacob on the schedule tables of k_eval like dydt and the rate
-    routines (measured faster on a B200: profiles/README.md)."""
+    routines (measured faster on a B200: profiles/README.md).
+    conv: the reference-named dydt of a library loaded from these tables is the constant-volume one (what
+    `#define CONV` in header.h selects in the reference)."""
     specs, reacs = mech.specs, mech.reacs
     nsp, nr = len(specs), len(reacs)
     last = nsp - 1
@@ -127,7 +130,13 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, stream
                     any(q('{:.4e}', pp[e + 1][0]) <= q('{:.4e}', pp[e][0]) for e in range(len(pp) - 1)):
                 # the reference does not handle these either (cj:1744-1749, 1768)
                 raise UnsupportedMechanism('PLOG reaction %d: pressures must ascend, A > 0' % i)
-        if not rx.A > 0:
+        if rx.plog or rx.cheb:
+            pass        # the rate constant comes from the PLOG / Chebyshev sets; A is not used
+        elif rx.A < 0 and not rx.pdep:
+            pass        # rs:108-141 (a duplicate with a negative rate); flagged F_NEGA below
+        elif not rx.A > 0:
+            # A == 0: the reference raises as well (rs:143-144); A < 0 in a fall-off reaction
+            # makes its generated code take the logarithm of a negative reduced pressure
             raise UnsupportedMechanism('non-positive pre-exponential (reaction %d)' % i)
         if rx.pdep and not (rx.low or rx.high):
             raise UnsupportedMechanism('fall-off reaction %d without LOW or HIGH' % i)
@@ -274,7 +283,14 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, stream
 
         # Arrhenius (rs:27-146, A > 0: always the exponential form for parsed floats)
         sum_nu = sum(rx.prod_nu) - sum(rx.reac_nu)
-        arr[p] = [q('{:.16e}', math.log(rx.A)), rx.b, q('{:.16e}', rx.E),
+        if rx.plog or rx.cheb:
+            lnA = 0.0
+        elif rx.A < 0:
+            fl |= F_NEGA
+            lnA = math.log(q('{:.16e}', -rx.A))
+        else:
+            lnA = q('{:.16e}', math.log(rx.A))
+        arr[p] = [lnA, rx.b, q('{:.16e}', rx.E),
                   float(sum_nu) * ln_pa_ru if rx.rev else 0.0]
 
         raw_base.append(nraw)
@@ -563,7 +579,7 @@ def build(mech: Mechanism, gs: int = 0, threads: int = 0, ws_global=None, stream
         T['p6_eff'] = eff6.ravel()
 
     T['sp_fwd_map'] = i32(mech.fwd_spec_map)            # internal position -> index in the mechanism file (apply_mask)
-    T['meta'] = i32([SCHEMA_VERSION, plan.PLAN_VERSION, plan6.PLAN_VERSION, 0])
+    T['meta'] = i32([SCHEMA_VERSION, plan.PLAN_VERSION, plan6.PLAN_VERSION, 1 if conv else 0])
     T['cst'] = f64([q('{:.8e}', RU), ln_pa_ru, 0.0, 0.0])
     T['dims'] = i32([nsp, nr, len(rev_reacs), npm, nraw, len(plog_par), len(cheb_par), 0,
                      first_pm, npm, red_off[-1], max(len(l) for l in red), 0, 0, 0, 0])

@@ -18,6 +18,14 @@ evaluates the emitted C on fixed states and stores inputs and outputs:
     tests/golden/cheb_syn.npz      Chebyshev coverage mechanism over the H2/O2 species, 160 synthetic states of
                                    which 32 outside the fitted pressure ranges
 
+    tests/golden/nega_pasr.npz     negative pre-exponential factors (duplicate pairs, every A < 0 branch of rs:108-141),
+                                   every 4th PaSR state
+
+    tests/golden/h2o2_conv.npz     constant-volume dydt (the reference's CONV branch, its two syntax slips repaired in
+                                   the emitted copy: oracle/build_ref.py conv=True) on every 4th PaSR state:
+                                   rho (the density of the state at its pressure), y, dydt
+    tests/golden/gri30_conv.npz    the same for the GRI-3.0-shaped mechanism, 48 synthetic states
+
 Arrays are in pyJac's internal (moved-last) species order, row-major per state:
 P[n], y[n,NSP] = [T, Y_0..Y_{NSP-2}], conc, fwd, rev, pres_mod, spec_rates, dydt, jac[n,NSP*NSP]
 (column-major inside a state).
@@ -39,6 +47,23 @@ from pyjac_b200.mechanism import Mechanism                     # noqa: E402
 from pyjac_b200.states import pasr_states, synthetic_states    # noqa: E402
 
 
+def dump_conv(name, mech_file, P, y, out_name):
+    """Constant-volume dydt of the reference at the densities the states have at their pressures."""
+    import ctypes
+    build_ref.build(name, mech_file)
+    conc = RefLib(name).rates(P, y)[0]
+    w = np.array([sp.mw for sp in Mechanism.from_chemkin(mech_file).specs])
+    rho = np.ascontiguousarray((conc * w[None, :]).sum(axis=1))
+    L = ctypes.CDLL(build_ref.build(name + '_conv', mech_file, conv=True))
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.ref_dydt_batch.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_int]
+    y = np.ascontiguousarray(y)
+    dy = np.zeros_like(y)
+    L.ref_dydt_batch(len(rho), rho.ctypes.data_as(dp), y.ctypes.data_as(dp), dy.ctypes.data_as(dp), 1)
+    np.savez_compressed(os.path.join(HERE, out_name), rho=rho, y=y, dydt=dy)
+    print(name + '_conv', y.shape, 'dT/dt in [%.3g, %.3g]' % (dy[:, 0].min(), dy[:, 0].max()))
+
+
 def dump(name, mech_file, P, y, out_name):
     build_ref.build(name, mech_file)
     ref = RefLib(name)
@@ -53,6 +78,22 @@ if __name__ == '__main__':
     pasr = os.path.join(HERE, 'h2_pasr_output.npy')
     if not os.path.exists(pasr):
         shutil.copy('/root/reference/data/h2_pasr_output.npy', pasr)
+    only = set(sys.argv[1:])               # e.g. `make_golden.py conv` regenerates only the constant-volume vectors
+
+    if 'nega' in only:
+        mech = Mechanism.from_chemkin(os.path.join(HERE, 'nega.inp'))
+        P, y = pasr_states(pasr, mech)
+        dump('nega', os.path.join(HERE, 'nega.inp'), P[::4], y[::4], 'nega_pasr.npz')
+        sys.exit(0)
+
+    mech = Mechanism.from_chemkin(os.path.join(HERE, 'h2o2_n2.inp'))
+    P, y = pasr_states(pasr, mech)
+    dump_conv('h2o2', os.path.join(HERE, 'h2o2_n2.inp'), P[::4], y[::4], 'h2o2_conv.npz')
+    mech = Mechanism.from_chemkin(os.path.join(HERE, 'gri30_syn.inp'))
+    P, y = synthetic_states(mech.NSP, 48, seed=0)
+    dump_conv('gri30', os.path.join(HERE, 'gri30_syn.inp'), P, y, 'gri30_conv.npz')
+    if only == {'conv'}:
+        sys.exit(0)
 
     mech = Mechanism.from_chemkin(os.path.join(HERE, 'h2o2_n2.inp'))
     P, y = pasr_states(pasr, mech)
@@ -61,6 +102,10 @@ if __name__ == '__main__':
     mech = Mechanism.from_chemkin(os.path.join(HERE, 'torture.inp'))
     P, y = pasr_states(pasr, mech)
     dump('torture', os.path.join(HERE, 'torture.inp'), P[::4], y[::4], 'torture_pasr.npz')
+
+    mech = Mechanism.from_chemkin(os.path.join(HERE, 'nega.inp'))
+    P, y = pasr_states(pasr, mech)
+    dump('nega', os.path.join(HERE, 'nega.inp'), P[::4], y[::4], 'nega_pasr.npz')
 
     gri = os.path.join(HERE, 'gri30_syn.inp')
     synth.write('gri30', gri, seed=0)

@@ -112,12 +112,13 @@ def evaluate(Tb, P, y, plan=5):
             lnkf = LN10 * series(c8, tr16, pr16, False)
             dk_ = series(c16, tr16, pr16, True) * cq[10] * iT
             rat = np.exp(lnkf_r - lnkf)
-        kf = np.exp(lnkf)
+        sg = -1.0 if fl & tb.F_NEGA else 1.0                  # rs:108-141
+        kf = sg * np.exp(lnkf)
         f = kf * c[0] * c[1] * c[2] * rat
         isrev = bool(fl & tb.F_REV)
         if isrev:
             sB = (B[:, s[3]] + B[:, s[4]] + B[:, s[5]]) - (B[:, s[0]] + B[:, s[1]] + B[:, s[2]])
-            kr = np.exp(lnkf - sB - lnKc)
+            kr = sg * np.exp(lnkf - sB - lnKc)
             r = kr * c[3] * c[4] * c[5] * rat
         else:
             kr = np.zeros(n)

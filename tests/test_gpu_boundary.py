@@ -179,3 +179,22 @@ def test_reference_harness_links_and_runs(torch, golden_dir, tmp_path):
         num, ms = res.stdout.strip().split(',')
         assert int(num) == 1020 and float(ms) > 0.0
         print('reference harness on pyjac_b200: %s states, %d threads: %s ms' % (num, threads, ms))
+
+
+def test_constant_volume_build(torch, golden_dir, tmp_path):
+    """create_jacobian(conp=False): header.h says `#define CONV`, the reference-named dydt takes the density,
+    eval_jacob refuses (no such form upstream either)."""
+    from pyjac_b200 import lib
+    from pyjac_b200.create_jacobian import create_jacobian
+    from pyjac_b200.pywrap import generate_wrapper
+    out = str(tmp_path / 'out')
+    mech = create_jacobian('cuda', os.path.join(golden_dir, 'h2o2_n2.inp'), build_path=out, conp=False)
+    assert '\n#define CONV' in open(os.path.join(out, 'header.h')).read()
+    mod = generate_wrapper('c', out, str(tmp_path / 'mods'))
+    g = dict(np.load(os.path.join(golden_dir, 'h2o2_conv.npz')))
+    dy = np.zeros(mech.NSP)
+    for s in (0, 100, 254):
+        mod.py_dydt(0.0, float(g['rho'][s]), np.ascontiguousarray(g['y'][s]), dy)
+        ref = g['dydt'][s]
+        assert np.abs(dy - ref).max() <= 1e-9 * np.abs(ref).max()
+    mod.close()

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz'), ('torture.inp', 'torture_pasr.npz'),
          ('gri30_syn.inp', 'gri30_syn.npz'), ('usc2_syn.inp', 'usc2_syn.npz'),
-         ('plog.inp', 'plog_syn.npz'), ('cheb.inp', 'cheb_syn.npz')]
+         ('plog.inp', 'plog_syn.npz'), ('cheb.inp', 'cheb_syn.npz'), ('nega.inp', 'nega_pasr.npz')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 
@@ -141,6 +141,44 @@ def test_two_handles_share_one_kernel_instantiation(torch, golden_dir):
         assert np.isfinite(ev.dydt(P, y).cpu().numpy()).all()
     ev_l.close()
     ev_s.close()
+
+
+@pytest.mark.parametrize('mech_file,npz', [('h2o2_n2.inp', 'h2o2_conv.npz'), ('gri30_syn.inp', 'gri30_conv.npz')])
+@pytest.mark.parametrize('layout', ['rows', 'state_fastest'])
+def test_constant_volume_dydt_vs_reference_golden(torch, golden_dir, mech_file, npz, layout):
+    """pyjac_dydt_conv_dev against the reference's CONV dydt (golden vectors): dY/dt scaled by the gross
+    production like the constant-pressure gate, dT/dt by sum |u_k W_k| gross_k / (rho cv_avg)."""
+    from oracle.oracle import Oracle
+    mech, ev = _evaluator(golden_dir, mech_file)
+    g = dict(np.load(os.path.join(golden_dir, npz)))
+    rho_h, y_h = g['rho'], g['y']
+    rho, y = torch.tensor(rho_h, device='cuda'), torch.tensor(y_h, device='cuda')
+    yy = y if layout == 'rows' else y.t().contiguous()
+    dy = ev.dydt(rho, yy, y_layout=layout, conv=True).cpu().numpy()
+    if layout != 'rows':
+        dy = dy.T
+    # gross rates from the oracle at the pressure the density implies
+    Y = np.concatenate([y_h[:, 1:], 1.0 - y_h[:, 1:].sum(axis=1, keepdims=True)], axis=1)
+    w = np.array([sp.mw for sp in mech.specs])
+    from pyjac_b200.chem import RU
+    P_h = rho_h * RU * y_h[:, 0] * (Y / w[None, :]).sum(axis=1)
+    ora = Oracle(mech)
+    conc, fwd, rev, pm, sr = ora.rates(P_h, y_h)
+    gross = gates.gross_rates(mech, fwd, rev, pm)
+    cp, h = gates._thermo(mech, y_h[:, 0])
+    u = h - (RU / w)[None, :] * y_h[:, 0:1]
+    cv_avg = (Y * (cp - (RU / w)[None, :])).sum(axis=1)
+    scale = np.empty_like(dy)
+    scale[:, 1:] = gross[:, :-1] * w[None, :-1] / rho_h[:, None]
+    scale[:, 0] = (np.abs(u * w[None, :]) * gross).sum(axis=1) / (rho_h * cv_avg)
+    d = np.abs(dy - g['dydt'])
+    e = d / (scale + 1e-300)
+    e[scale == 0] = d[scale == 0]
+    assert e.max() <= gates.RTOL, e.max()
+    # and it differs from the constant-pressure dT/dt
+    cp_dy = ev.dydt(torch.tensor(P_h, device='cuda'), y).cpu().numpy()
+    assert np.abs(cp_dy[:, 0] - g['dydt'][:, 0]).max() > 1e-3 * np.abs(g['dydt'][:, 0]).max()
+    ev.close()
 
 
 def test_against_oracle_on_synthetic_states(torch, golden_dir):

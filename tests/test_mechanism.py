@@ -81,3 +81,69 @@ def test_plog_and_chebyshev_lines_are_read(tmp_path, golden_dir):
     assert not rx.pdep and (rx.cheb_n_temp, rx.cheb_n_pres) == (2, 3)
     assert rx.cheb_tlim == [300.0, 2000.0] and rx.cheb_plim[1] == pytest.approx(100.0 * 101325.0)
     assert rx.cheb_par[0][0] == pytest.approx(8.0 - 3.0) and rx.cheb_par[1] == [-1.0, 0.2, 0.05]
+
+
+def _same_mechanism(a, b, rel=0.0):
+    """Field-by-field equality of two parsed mechanisms (reaction order included).  `rel` is the relative
+    tolerance on real-valued fields: 0 where both files print the same decimal numbers."""
+    import dataclasses
+
+    def close(x, y, what):
+        if isinstance(x, (list, tuple)):
+            assert len(x) == len(y), what
+            for u, v in zip(x, y):
+                close(u, v, what)
+        elif isinstance(x, float) or isinstance(y, float):
+            assert x == y or abs(x - y) <= rel * max(abs(x), abs(y)), (what, x, y)
+        elif isinstance(x, str) and what.endswith('.elem'):
+            assert x.lower() == y.lower(), (what, x, y)         # 'Ar' (.cti) / 'AR' (Chemkin)
+        else:
+            assert x == y, (what, x, y)
+    assert [s.name for s in a.specs] == [s.name for s in b.specs]
+    assert len(a.reacs) == len(b.reacs)
+    for sa, sb in zip(a.specs, b.specs):
+        for f in dataclasses.fields(sa):
+            va, vb = getattr(sa, f.name), getattr(sb, f.name)
+            if f.name == 'elem':    # composition: the order of the file's element list
+                va, vb = sorted([e[0].lower(), e[1]] for e in va), sorted([e[0].lower(), e[1]] for e in vb)
+            close(va, vb, 'species %s.%s' % (sa.name, f.name))
+    for i, (ra, rb) in enumerate(zip(a.reacs, b.reacs)):
+        for f in dataclasses.fields(ra):
+            va, vb = getattr(ra, f.name), getattr(rb, f.name)
+            if f.name == 'thd_body_eff':
+                va, vb = sorted(va), sorted(vb)
+            if f.name == 'A' and (ra.plog or ra.cheb):
+                continue            # not used: the .cti entry has no separate Arrhenius triple
+            close(va, vb, 'reaction %d.%s' % (i, f.name))
+
+
+def test_cti_reader_matches_chemkin_twin(golden_dir):
+    """tests/golden/mini.cti and mini.inp state one mechanism (every reaction class the path knows) in the two
+    formats: the Cantera-free reader must hand the tables the same numbers."""
+    a = Mechanism.from_file(os.path.join(golden_dir, 'mini.cti'))
+    b = Mechanism.from_file(os.path.join(golden_dir, 'mini.inp'))
+    _same_mechanism(a, b)
+    from pyjac_b200 import tables
+    Ta, Tb = tables.build(a, 8, 256, False), tables.build(b, 8, 256, False)
+    assert sorted(Ta) == sorted(Tb)
+    for k in Ta:
+        assert np.array_equal(np.asarray(Ta[k]), np.asarray(Tb[k])), k
+
+
+def test_cti_reader_on_the_reference_h2o2_file(golden_dir):
+    """data/h2o2.cti of the reference is the ck2cti conversion of the mechanism tests/golden/h2o2_n2.inp was taken
+    from."""
+    cti = '/root/reference/data/h2o2.cti'
+    if not os.path.exists(cti):
+        pytest.skip('reference checkout not present')
+    a = Mechanism.from_file(cti)
+    b = Mechanism.from_chemkin(os.path.join(golden_dir, 'h2o2_n2.inp'))
+    _same_mechanism(a, b, rel=1e-15)
+
+
+def test_negative_pre_exponential(golden_dir):
+    from pyjac_b200 import tables
+    m = Mechanism.from_chemkin(os.path.join(golden_dir, 'nega.inp'))
+    assert sum(1 for rx in m.reacs if rx.A < 0) == 8          # 7 written + the split REV half
+    T = tables.build(m, 8, 256, False)
+    assert int(((np.asarray(T['rx_flags']) & tables.F_NEGA) != 0).sum()) == 8

@@ -18,7 +18,8 @@ CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz', 'h2o2'),
          ('gri30_syn.inp', 'gri30_syn.npz', 'gri30'),
          ('usc2_syn.inp', 'usc2_syn.npz', 'usc2'),
          ('plog.inp', 'plog_syn.npz', 'plog'),
-         ('cheb.inp', 'cheb_syn.npz', 'cheb')]
+         ('cheb.inp', 'cheb_syn.npz', 'cheb'),
+         ('nega.inp', 'nega_pasr.npz', 'nega')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 
@@ -62,3 +63,13 @@ def test_oracle_matches_live_reference_build(golden_dir, mech_file, npz, name):
     ora = Oracle(mech)
     assert np.array_equal(ref.eval_jacob(P, y, 1), ora.eval_jacob(P, y, 1))
     assert np.array_equal(ref.dydt(P, y, 1), ora.dydt(P, y, 1))
+
+
+@pytest.mark.parametrize('mech_file,npz', [('h2o2_n2.inp', 'h2o2_conv.npz'), ('gri30_syn.inp', 'gri30_conv.npz')])
+def test_oracle_constant_volume_dydt_matches_reference(golden_dir, mech_file, npz):
+    """Constant-volume dydt (rate_subs.py:2340-2485) against the reference's own CONV branch (the emitted copy
+    with its two syntax slips repaired, oracle/build_ref.py conv=True)."""
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
+    g = np.load(os.path.join(golden_dir, npz))
+    dy = Oracle(mech).dydt_conv(g['rho'], g['y'])
+    assert _close(dy, g['dydt'], npz) > 0.999

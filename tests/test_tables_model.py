@@ -16,7 +16,8 @@ CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz', slice(None, None, 5)),
          ('gri30_syn.inp', 'gri30_syn.npz', slice(None)),
          ('usc2_syn.inp', 'usc2_syn.npz', slice(None)),
          ('plog.inp', 'plog_syn.npz', slice(None)),
-         ('cheb.inp', 'cheb_syn.npz', slice(None))]
+         ('cheb.inp', 'cheb_syn.npz', slice(None)),
+         ('nega.inp', 'nega_pasr.npz', slice(None))]
 
 
 @pytest.mark.parametrize('mech_file,npz,sl', CASES)
