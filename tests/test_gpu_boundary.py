@@ -193,7 +193,9 @@ def test_constant_volume_build(torch, golden_dir, tmp_path):
     mod = generate_wrapper('c', out, str(tmp_path / 'mods'))
     g = dict(np.load(os.path.join(golden_dir, 'h2o2_conv.npz')))
     dy = np.zeros(mech.NSP)
-    for s in (0, 100, 254):
+    # reacting states (at near-equilibrium ones dydt is the rounding residue of cancelling rates: the gated
+    # comparison of those is tests/test_gpu_parity.py::test_constant_volume_dydt_vs_reference_golden)
+    for s in np.argsort(-np.abs(g['dydt'][:, 0]))[[0, 20, 60]]:
         mod.py_dydt(0.0, float(g['rho'][s]), np.ascontiguousarray(g['y'][s]), dy)
         ref = g['dydt'][s]
         assert np.abs(dy - ref).max() <= 1e-9 * np.abs(ref).max()
