@@ -40,6 +40,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -354,6 +356,81 @@ def gather_run(ev, torch, dist, dev, rank, world, P, y, jac, nsp, n, steps, barr
                    'kernel; rank 0 receives into a ring of two buffers per peer' % nchunk}
 
 
+def factored_runs(ev, torch, dev, mech, P_h, y_h, n_e, world, e_steps, barrier, max_over_ranks, j_chk):
+    """Side records: (1) the host call that returns the factored record instead of the dense Jacobian
+    (pyjac_eval_jacob_factored_host: 8 NF instead of 8 NSP^2 bytes per state over PCIe); (2) the consumer chain on
+    the device -- pinned host states in, factored record, x = (I - gamma J)^-1 r, only x (NSP doubles) back."""
+    nsp = mech.NSP
+    nf, nnz = ev.factored_size
+    yp = torch.empty((n_e, nsp), dtype=torch.float64, pin_memory=True)
+    Pp = torch.empty((n_e,), dtype=torch.float64, pin_memory=True)
+    fp = torch.empty((n_e, nf), dtype=torch.float64, pin_memory=True)
+    yp.numpy()[:] = y_h[:n_e]
+    Pp.numpy()[:] = P_h[:n_e]
+    y_np, P_np, f_np = yp.numpy(), Pp.numpy(), fp.numpy()
+    ev.eval_jacob_factored_host(P_np, y_np, f_np)                  # warm-up (staging buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        ev.eval_jacob_factored_host(P_np, y_np, f_np)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    k = len(j_chk)
+    dense = ev.expand_factored(f_np[:k])
+    err = np.abs(dense - j_chk) / (np.abs(j_chk).reshape(k, nsp, nsp).max(axis=2, keepdims=True).repeat(nsp, axis=2).reshape(k, -1) + 1e-300)
+    assert err.max() <= 1e-13, 'factored record does not expand to the dense Jacobian (%.2e)' % err.max()
+    fac_rec = {'value': n_e * world * e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': n_e * (nsp + 1) * 8,
+               'd2h_bytes_per_step': n_e * nf * 8, 'states_per_step': n_e, 'steps': e_steps,
+               'doubles_per_state': nf, 'dense_doubles_per_state': nsp * nsp, 'sparse_block_entries': nnz,
+               'api': 'pyjac_eval_jacob_factored_host (pinned host rows in, factored records out: energy row, T column, '
+                      'rank-2 factors, sparse block in a fixed pattern); a sample is expanded on the host and compared '
+                      'with the dense Jacobians'}
+    del fp
+    # consumer chain, chunked like the host API (2 streams would overlap copies with compute; kept simple: one stream)
+    chunk = min(n_e, 1 << 18)
+    fac = torch.empty((nf, chunk), dtype=torch.float64, device=dev)
+    yd = torch.empty((chunk, nsp), dtype=torch.float64, device=dev)
+    Pd = torch.empty((chunk,), dtype=torch.float64, device=dev)
+    xd = torch.empty((chunk, nsp), dtype=torch.float64, device=dev)
+    xp = torch.empty((n_e, nsp), dtype=torch.float64, pin_memory=True)
+    rd = torch.ones((chunk, nsp), dtype=torch.float64, device=dev) * 1e-3
+    gamma = 1.0e-6
+
+    def chain():
+        for s0 in range(0, n_e, chunk):
+            cn = min(chunk, n_e - s0)
+            yd[:cn].copy_(yp[s0:s0 + cn], non_blocking=True)
+            Pd[:cn].copy_(Pp[s0:s0 + cn], non_blocking=True)
+            # y arrives as rows; the record is written state-fastest (coalesced for the consumer kernel)
+            ev.eval_jacob_factored(Pd[:cn], yd[:cn], out=fac, fac_layout='state_fastest')
+            ev.newton_solve(fac, gamma, rd[:cn], out=xd[:cn], fac_layout='state_fastest')
+            xp[s0:s0 + cn].copy_(xd[:cn], non_blocking=True)
+        torch.cuda.synchronize()
+    chain()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        chain()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    # device-only times of the two kernels on one chunk
+    e0, e1, e2_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    ev.eval_jacob_factored(Pd, yd, out=fac, fac_layout='state_fastest')
+    e1.record()
+    ev.newton_solve(fac, gamma, rd, out=xd, fac_layout='state_fastest')
+    e2_.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(xd).all()
+    cons = {'value': n_e * world * e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': n_e * (nsp + 1) * 8,
+            'd2h_bytes_per_step': n_e * nsp * 8, 'states_per_step': n_e, 'steps': e_steps,
+            'factored_kernel_states_per_s': chunk / (e0.elapsed_time(e1) * 1e-3),
+            'newton_kernel_states_per_s': chunk / (e1.elapsed_time(e2_) * 1e-3),
+            'what': 'pinned host states in -> factored record (k_eval M_FACT) -> x = (I - gamma J)^-1 r per state (k_newton: '
+                    'matrix expanded in shared memory, LU with partial pivoting) -> x back to pinned host memory; the dense '
+                    'Jacobian is never written to HBM or sent over PCIe'}
+    return fac_rec, cons
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -464,12 +541,22 @@ def run_ours(args, rank, world, local_rank):
         if n_e == n:
             k = min(n, 64)
             assert np.array_equal(j_np[:k], jac[:, :k].t().cpu().numpy()), 'host / device API mismatch'
+        j_chk = j_np[:64].copy()
         e2e = {'value': n_e * world * e_steps / dt, 'unit': UNIT,
                'h2d_bytes_per_step': n_e * (nsp + 1) * 8, 'd2h_bytes_per_step': n_e * nsp * nsp * 8,
                'states_per_step': n_e, 'steps': e_steps,
                'd2h_gbs': n_e * world * e_steps * nsp * nsp * 8 / dt / 1e9,
                'api': 'pyjac_eval_jacob_host (pinned host rows in, pinned host Jacobians out)'}
         del yp, Pp, jp
+
+    # ---- the same call with the factored record out, and the consumer step on the device (8 f1)
+    e2e_factored = consumer = None
+    if e2e is not None and not args.no_factored:
+        try:
+            e2e_factored, consumer = factored_runs(ev, torch, dev, mech, P_h, y_h, e2e['states_per_step'], world,
+                                                   e_steps, barrier, max_over_ranks, j_chk)
+        except Exception as exc:                      # side records must not cost the headline line
+            e2e_factored = {'error': str(exc).splitlines()[0][:200]}
 
     # ---- BASELINE.json's other configurations on this rank count ------------------------
     del jac
@@ -517,7 +604,7 @@ def run_ours(args, rank, world, local_rank):
                          'capture of this kernel (65 536 states), scaled to this batch -- not measured in this run',
                          'peak_source': peak_src, 'bytes_per_state': bytes_per_state,
                          'kernel': kernel_name, 'kernel_ms': kernel_ms},
-            'e2e': e2e, 'with_gather': with_gather, 'strong': strong, 'workloads': workloads,
+            'e2e': e2e, 'e2e_factored': e2e_factored, 'consumer': consumer, 'with_gather': with_gather, 'strong': strong, 'workloads': workloads,
             'cpu_baseline': cpu, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)
@@ -537,6 +624,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-factored', action='store_true', help='skip the factored-record / consumer side records')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-workloads', action='store_true', help='leave out the sub-records of the other BASELINE configurations')
     ap.add_argument('--no-gather', action='store_true', help='(N > 1) leave out the gather-to-rank-0 measurement')

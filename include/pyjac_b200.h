@@ -68,8 +68,8 @@ int pyjac_mech_dims(const pyjac_mech* m, int dims[4]);
  * block size belong to the plan inside the table blob (pyjac_b200/plan.py).  Results do not
  * depend on this. */
 int pyjac_mech_tune(pyjac_mech* m, int blocks_per_sm);
-/* (mangled) symbol of the kernel that a call of mode 0 = eval_jacob, 1 = dydt, 2 = the rate routines
- * launches for this mechanism's plan -- what a profiler lists */
+/* (mangled) symbol of the kernel that a call of mode 0 = eval_jacob, 1 = dydt, 2 = the rate routines,
+ * 3 = the factored Jacobian launches for this mechanism's plan -- what a profiler lists */
 int pyjac_mech_kernel_name(const pyjac_mech* m, int mode, char* buf, size_t len);
 /* number of kernels launched through this handle since creation */
 long long pyjac_mech_launches(const pyjac_mech* m);
@@ -106,6 +106,40 @@ int pyjac_mech_set_conv(pyjac_mech* m, int conv);
  * state-fastest with leading dimension n; synchronous (scratch memory is allocated and freed). */
 int pyjac_fd_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y, double* d_jac,
                        int order, double r_cap, void* stream);
+/* ---- factored Jacobian and its consumers ---------------------------------
+ * The dense NSP x NSP Jacobian is the expansion of a much smaller record; the reference only gestures
+ * at a sparse form (create_jacobian.py:3301-3404, `sparse_multiplier`, broken at :3322).  Per state the
+ * record holds NF = NSP + 3 (NSP - 1) + NNZ doubles:
+ *     fac[0 .. NSP)              J[0][j]                      the energy-equation row
+ *     fac[NSP + k]               J[k+1][0]                    the temperature column, k = 0 .. NSP-2
+ *     fac[NSP + (NSP-1) + k]     WA_k
+ *     fac[NSP + 2 (NSP-1) + k]   WB_k
+ *     fac[NSP + 3 (NSP-1) + p]   S_p, entry (rows[p], cols[p]) of the sparse block, p = 0 .. NNZ-1
+ * and for i, j >= 1:   J[i][j] = ca[j] * WA_{i-1} + cb[j] * WB_{i-1} + sum_{p: (rows[p], cols[p]) = (i, j)} S_p.
+ * The pattern (rows, cols; column-major order) and the column factors ca, cb are fixed per mechanism.
+ * Layouts as for the Jacobian: PYJAC_JAC_STATE_MAJOR fac[s*NF + e], PYJAC_JAC_STATE_FASTEST fac[e*ld + s]. */
+int pyjac_factored_size(const pyjac_mech* m, int* nf, int* nnz);
+/* rows[NNZ], cols[NNZ] (indices into the NSP x NSP Jacobian), ca[NSP], cb[NSP] (entry 0 unused); any may be NULL */
+int pyjac_factored_pattern(const pyjac_mech* m, int* rows, int* cols, double* ca, double* cb);
+int pyjac_eval_jacob_factored_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
+                                  long long y_ss, long long y_sv, double* d_fac, int fac_layout,
+                                  long long fac_ld, void* stream);
+/* host rows in (as pyjac_eval_jacob_host), one record of NF doubles per state out */
+int pyjac_eval_jacob_factored_host(pyjac_mech* m, int n, const double* pres, const double* y, double* fac);
+/* out = J v per state straight from the records (J is never formed): element i of state s of v is
+ * d_v[s*v_ss + i*v_sv], of the product d_out[s*o_ss + i*o_sv] */
+int pyjac_jvp_dev(pyjac_mech* m, int n, const double* d_fac, int fac_layout, long long fac_ld,
+                  const double* d_v, long long v_ss, long long v_sv,
+                  double* d_out, long long o_ss, long long o_sv, void* stream);
+/* The consumer step of an implicit integrator (docs/faqs.rst:113-117): x = (I - gamma J)^-1 rhs per state,
+ * the matrix expanded from the record into shared memory, LU with partial pivoting -- the dense Jacobian
+ * never reaches HBM.  gamma: one value for all states, or d_gamma[n] (device) when not NULL.  d_info[n]
+ * (device, may be NULL): 0, or c + 1 when column c had no pivot (x of that state is left untouched).
+ * PYJAC_ETOOBIG when (NSP|1) * NSP + 3 NSP doubles exceed the shared memory of a block (NSP > ~165). */
+int pyjac_newton_solve_dev(pyjac_mech* m, int n, const double* d_fac, int fac_layout, long long fac_ld,
+                           double gamma, const double* d_gamma,
+                           const double* d_rhs, long long r_ss, long long r_sv,
+                           double* d_x, long long x_ss, long long x_sv, int* d_info, void* stream);
 /* conc[NSP], fwd[FWD_RATES], rev[REV_RATES], pres_mod[PRES_MOD_RATES], spec_rates[NSP] and
  * dy[NSP] per state; any output pointer may be NULL.  Element v of state s of every output
  * goes to out[s*o_ss_mult*width + v] when o_state_fastest == 0 (rows), or out[v*o_ld + s]

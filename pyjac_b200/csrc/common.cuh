@@ -17,7 +17,9 @@ enum : int {
 // what a launch of k_eval produces
 enum : int { M_JAC = 0,     // eval_jacob: the Jacobian
              M_DYDT = 1,    // dydt
-             M_RATES = 2 }; // conc / fwd / rev / pres_mod / spec_rates (/ dydt): the rate routines
+             M_RATES = 2,   // conc / fwd / rev / pres_mod / spec_rates (/ dydt): the rate routines
+             M_FACT = 3 };  // the Jacobian in factored form: energy row, T column, the rank-2 factors W_k a_k, W_k b_k
+                            // and the sparse block in a fixed pattern, through IO::jac
 
 struct Tables {
     int nsp, nr, nrev, npd, nraw, first_pm, npm;

@@ -43,6 +43,9 @@ using namespace pj;
 #define PJ_SKIP(MASK) false
 #endif
 
+// the two modes that run the whole Jacobian pipeline (phases B / C in full, then DE)
+__host__ __device__ constexpr bool jac_like(int mode) { return mode == M_JAC || mode == M_FACT; }
+
 struct Plan {
     int gs, nt, nw, nsub, oSP, oRX, oRAW, oSC, oPA, total, t_sync, coop, tcoop, oCF;
     int wsg;                         // 1: the working set lives in global memory (IO::ws), not in shared memory
@@ -65,6 +68,8 @@ struct Plan {
     const int2* t_item;
     const uint2* t_str;
     const double2* colfac;
+    const int* fac_map;              // M_FACT: dense element -> slot of the factored record (sparse block), -1: none
+    int fac_nnz;                     // entries of the sparse block
 };
 
 // per-state scalars: phase A0 writes Q_* (two buffers of 8 rows), phase DE derives S_*
@@ -352,7 +357,7 @@ __device__ __forceinline__ void reaction(const Mem<WSG>& mem, const Tables& tb, 
         if (io.rev && isrev) put2(io.rev, io, tb.nrev, out, ro.y, r);
         if (PM && io.pm) put2(io.pm, io, tb.npd, out, ro.z, PM_);
     }
-    if (MODE != M_JAC) {
+    if (!jac_like(MODE)) {
         // only the net rate is needed for the species rates
         STS_IF(RX_NET * RB, valid, aRX + p * RXB, PM ? vmul(net, PM_) : net);
         return;
@@ -577,7 +582,7 @@ __device__ __forceinline__ void reaction_plain(const Mem<WSG>& mem, const Tables
         if (io.fwd) put2(io.fwd, io, tb.nr, out, ro.x, f);
         if (io.rev && isrev) put2(io.rev, io, tb.nrev, out, ro.y, r);
     }
-    if (MODE != M_JAC) {
+    if (!jac_like(MODE)) {
         STS_IF(RX_NET * RB, valid, aRX + p * RXB, net);
         return;
     }
@@ -674,7 +679,8 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
 
     const bool sf = io.jac_layout != 0;
     const bool vec_ok = sf && ((io.jac_ld & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.jac) & 15) == 0);
-    const long long nn = (long long)nsp * nsp;
+    // values per state of the output: the dense Jacobian, or the factored record
+    const long long nn = MODE == M_FACT ? (long long)nsp + 3 * last + pl.fac_nnz : (long long)nsp * nsp;
     const long long ngroups = ((long long)io.n + GS - 1) / GS;
     // element e of state s: SoA jac[e * ld + s], AoS jac[s * nn + e]
     const unsigned ld8 = sf ? (unsigned)(io.jac_ld * 8) : 8u;
@@ -728,7 +734,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             for (int g2 = 0; g2 < 2; ++g2) {
                 const double mw = inc ? sw[g2] / sy[g2] : 1.0 / (sw[g2] + yN[g2] * __ldg(tb.sp_iw + last));
                 double rho = inc ? sw[g2] : P[g2] * mw / (tb.ru * T[g2]);
-                if (MODE != M_JAC && io.conv) {
+                if (!jac_like(MODE) && io.conv) {
                     // constant volume: the caller's variable is the density, the pressure follows (rs:1708-1800)
                     rho = P[g2];
                     P[g2] = rho * tb.ru * T[g2] / mw;
@@ -817,7 +823,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                     const double t = Tv[g];
                     ck[g] = inc ? (g ? Yv.y : Yv.x) : rh[g] * Yk[g] * iw;
                     // constant volume (dydt only): cv and u in place of cp and h (rs:1876-2019), c[11] = a0 - 1
-                    const double a0 = (MODE != M_JAC && io.conv) ? c[11] : c[0];
+                    const double a0 = (!jac_like(MODE) && io.conv) ? c[11] : c[0];
                     cp[g] = ruw * (a0 + t * (c[1] + t * (c[2] + t * (c[3] + c[4] * t))));
                     const double hh = c[6] + t * (c[7] + t * (c[8] + c[9] * t));
                     hW[g] = ruw * (c[5] + t * (a0 + t * hh)) * wk;
@@ -901,7 +907,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 auto unit = [&](uint2 c, double sg) {
                     const unsigned x = aRX + c.x, y = aRX + c.y;
                     aN = vfma(sg, vadd(LDS(RX_NET * RB, x), LDS(RX_NET * RB, y)), aN);
-                    if (MODE != M_JAC) return;                 // only the net rates are summed
+                    if (!jac_like(MODE)) return;                 // only the net rates are summed
                     aT = vfma(sg, vadd(LDS(RX_TT * RB, x), LDS(RX_TT * RB, y)), aT);
                     a1 = vfma(sg, vadd(LDS(RX_X1 * RB, x), LDS(RX_X1 * RB, y)), a1);
                     a2 = vfma(sg, vadd(LDS(RX_X2 * RB, x), LDS(RX_X2 * RB, y)), a2);
@@ -919,12 +925,12 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 if (i < n) unit(c, i < np_ ? 1.0 : -1.0);
                 for (int o = NPR; o < NPR * pl.coop; o <<= 1) {
                     aN = V{aN.x + __shfl_xor_sync(0xffffffffu, aN.x, o), aN.y + __shfl_xor_sync(0xffffffffu, aN.y, o)};
-                    if (MODE != M_JAC) continue;
+                    if (!jac_like(MODE)) continue;
                     aT = V{aT.x + __shfl_xor_sync(0xffffffffu, aT.x, o), aT.y + __shfl_xor_sync(0xffffffffu, aT.y, o)};
                     a1 = V{a1.x + __shfl_xor_sync(0xffffffffu, a1.x, o), a1.y + __shfl_xor_sync(0xffffffffu, a1.y, o)};
                     a2 = V{a2.x + __shfl_xor_sync(0xffffffffu, a2.x, o), a2.y + __shfl_xor_sync(0xffffffffu, a2.y, o)};
                 }
-                if (hd.y && MODE != M_JAC) {
+                if (hd.y && !jac_like(MODE)) {
                     // dydt / rates: omega_k, dY_k/dt = omega_k W_k / rho, share of sum_k h_k W_k omega_k
                     const int k = hd.x / SPB;
                     const double wk = __ldg(tb.sp_w + k);
@@ -939,7 +945,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                         if (ok1) io.dy[(s0 + 1) * io.dy_ss + (long long)(k + 1) * io.dy_sv] = dyk.y;
                     }
                 }
-                if (hd.y && MODE == M_JAC) {
+                if (hd.y && jac_like(MODE)) {
                     const unsigned a = aSP + hd.x, o = a ^ RB;      // hd.x: even-slot base of species k
                     const double wk = __ldg(tb.sp_w + hd.x / SPB);
                     const V comp = vmul(aN, mwr);
@@ -969,7 +975,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
         PJ_TICK(3)
 
         // ------------------------------------------------------------ dydt / rates: energy equation
-        if (MODE != M_JAC) {
+        if (!jac_like(MODE)) {
             if (warp == 0) {
                 V H1 = zero, cpavg = zero;
                 for (int w = sub; w < nw; w += NSUB) {
@@ -1034,13 +1040,17 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
             uint2 ob0 = __ldg(ov), ob1 = __ldg(ov + NSUB), ob2 = __ldg(ov + 2 * NSUB), ob3 = __ldg(ov + 3 * NSUB);
             // one step: the bundle (A, B) is consumed while `nA`, `nB` of a later step are fetched
             auto step = [&](const uint4& A, const uint4& B) {
-                const unsigned L = A.x >> 22, e = A.x & NULL_E;
+                const unsigned L = A.x >> 22;
+                unsigned e = A.x & NULL_E;
                 const unsigned x = aSP + (A.y & 0xFFFFFu);
-                const V cf = LDS(0, aCF + (A.y >> 20) * 16);
+                V cf{0.0, 0.0};
+                if (MODE == M_FACT) { if (e != NULL_E) e = (unsigned)__ldg(pl.fac_map + e); }
+                else cf = LDS(0, aCF + (A.y >> 20) * 16);
                 // signed entries: byte offset of a raw row | 1 for weight -1; two entries per unit
                 auto sgn = [](unsigned c) { return __hiloint2double((int)(0x3FF00000u | (c << 31)), 0); };
                 V p = vmul(sgn(B.x), LDS(0, aRAW + (B.x & ~1u))), m = vmul(sgn(B.y), LDS(0, aRAW + (B.y & ~1u)));
-                V v = vfma(cf.y, LDS(0, x ^ RB), vmul(cf.x, LDS(0, x)));     // W_k a_k at x, W_k b_k at x ^ RB
+                V v{0.0, 0.0};                                               // M_FACT: the sparse part alone
+                if (MODE != M_FACT) v = vfma(cf.y, LDS(0, x ^ RB), vmul(cf.x, LDS(0, x)));     // W_k a_k at x, W_k b_k at x ^ RB
                 if (L > 1) {
                     p = vfma(sgn(B.z), LDS(0, aRAW + (B.z & ~1u)), p);
                     m = vfma(sgn(B.w), LDS(0, aRAW + (B.w & ~1u)), m);
@@ -1091,6 +1101,15 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                 const bool on = hd.x != 0xFFFFFFFFu;
                 const unsigned x = aSP + (on ? hd.x : 0u);
                 const V wa = LDS(E_WA * RB, x), wb = LDS(O_WB * RB, x ^ RB);
+                if (MODE == M_FACT) {
+                    // the row's three factors, once (the item that owns the temperature column)
+                    const bool own = on && hd.y != NULL_E;
+                    const unsigned k_ = own ? hd.y - 1u : 0u;                  // hd.y: element (k + 1, 0)
+                    store((unsigned)nsp + k_, LDS(E_WT * RB, x), own);
+                    store((unsigned)(nsp + last) + k_, wa, own);
+                    store((unsigned)(nsp + 2 * last) + k_, wb, own);
+                    continue;
+                }
                 store(hd.y, LDS(E_WT * RB, x), on && hd.y != NULL_E);  // temperature column: W_k * T-term
                 // units are fetched LA batches of four ahead (the tables come from L2: with all of
                 // shared memory in use there is no L1 to speak of)
@@ -1151,7 +1170,7 @@ k_eval(const __grid_constant__ Tables tb, const __grid_constant__ Plan pl, const
                     V v = vmul(cf.x, vfma(nwt, E0, A0));
                     v = vfma(cf.y, B0, v);
                     v = vfma(XT, vsub(cpj, cpl), v);
-                    store(col * (unsigned)nsp, v, (hd.x >> 16) != 0u);
+                    store(MODE == M_FACT ? col : col * (unsigned)nsp, v, (hd.x >> 16) != 0u);
                 }
             }
         }

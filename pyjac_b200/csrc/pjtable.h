@@ -11,7 +11,7 @@ namespace pjt {
 
 // versions this library was written for: table set, p5_* schedule tables, p6_* record streams
 // (pyjac_b200/tables.py SCHEMA_VERSION, plan.py / plan6.py PLAN_VERSION)
-enum : int32_t { SCHEMA_VERSION = 2, PLAN5_VERSION = 2, PLAN6_VERSION = 4 };
+enum : int32_t { SCHEMA_VERSION = 2, PLAN5_VERSION = 3, PLAN6_VERSION = 4 };
 
 struct Entry {
     char name[24];

@@ -16,6 +16,7 @@
 
 #include "eval.cuh"
 #include "jac6.cuh"
+#include "consumer.cuh"
 #include "pjtable.h"
 
 #include <map>
@@ -34,7 +35,11 @@ struct pyjac_mech {
     bool has6 = false;
     std::vector<void*> dev_allocs;
     int user_bpsm = 0;
-    int bpsm[3] = {0, 0, 0};         // blocks per SM per mode (0 = not configured yet)
+    int bpsm[4] = {0, 0, 0, 0};      // blocks per SM per mode (0 = not configured yet)
+    // factored output (M_FACT): pattern of the sparse block in record order (host copies) and by row (device)
+    std::vector<int> fac_rows, fac_cols;
+    std::vector<double> colfac_h;
+    pjc::Fac fac{};
     std::atomic<long long> launches{0};
     std::mutex mu;                   // launch configuration and the shared scratch of a wsg plan
     std::vector<int> fwd_map, back_map;   // species: internal position -> original index and back (apply_mask)
@@ -111,13 +116,14 @@ const void* kernel_for(int gs, int mode, int nt, int wsg = 0)
         if (nt > 384) return nullptr;
         if (nt <= 256)
             return mode == pj::M_DYDT ? kernel_g<512, pj::M_DYDT>(gs) : mode == pj::M_RATES ? kernel_g<512, pj::M_RATES>(gs)
-                                                                                           : kernel_g<512, pj::M_JAC>(gs);
+                 : mode == pj::M_FACT ? kernel_g<512, pj::M_FACT>(gs) : kernel_g<512, pj::M_JAC>(gs);
         return mode == pj::M_DYDT ? kernel_g<384, pj::M_DYDT>(gs) : mode == pj::M_RATES ? kernel_g<384, pj::M_RATES>(gs)
-                                                                                       : kernel_g<384, pj::M_JAC>(gs);
+             : mode == pj::M_FACT ? kernel_g<384, pj::M_FACT>(gs) : kernel_g<384, pj::M_JAC>(gs);
     }
     const bool small = nt <= 384;
     if (mode == pj::M_DYDT) return small ? kernel_t<384, pj::M_DYDT>(gs) : kernel_t<512, pj::M_DYDT>(gs);
     if (mode == pj::M_RATES) return small ? kernel_t<384, pj::M_RATES>(gs) : kernel_t<512, pj::M_RATES>(gs);
+    if (mode == pj::M_FACT) return small ? kernel_t<384, pj::M_FACT>(gs) : kernel_t<512, pj::M_FACT>(gs);
     return small ? kernel_t<384, pj::M_JAC>(gs) : kernel_t<512, pj::M_JAC>(gs);
 }
 
@@ -226,6 +232,60 @@ int launch(pyjac_mech* m, int mode, const IO& io_in, cudaStream_t st)
     if (pl.wsg) CU(cudaEventRecord(m->ws_ev, st));
     ++m->launches;
     return PYJAC_OK;
+}
+
+
+// Pattern of the factored record's sparse block (plan.py: fac_rows / fac_cols, column-major record order):
+// checked, kept on the host for pyjac_factored_pattern and uploaded by row for the consumers.
+int setup_factored(pyjac_mech* m, const void* blob)
+{
+    const int nsp = m->tb.nsp;
+    const pjt::Entry* pe = pjt::find(blob, "p5_cfg");
+    const pjt::Entry* re = pjt::find(blob, "fac_rows");
+    const pjt::Entry* ce = pjt::find(blob, "fac_cols");
+    const pjt::Entry* fe = pjt::find(blob, "p5_colfac");
+    if (!pe || pe->count < 16 || !re || !ce || re->dtype != 1 || ce->dtype != 1 || !fe)
+        return fail(PYJAC_EINVAL, "table blob lacks the factored-output pattern");
+    const int nnz = ((const int*)((const char*)blob + pe->offset))[15];
+    if (nnz < 0 || re->count < nnz || ce->count < nnz || (long long)nnz > (long long)nsp * nsp)
+        return fail(PYJAC_EINVAL, "bad factored-output pattern");
+    const int* rows = (const int*)((const char*)blob + re->offset);
+    const int* cols = (const int*)((const char*)blob + ce->offset);
+    m->fac_rows.assign(rows, rows + nnz);
+    m->fac_cols.assign(cols, cols + nnz);
+    const double* cf = (const double*)((const char*)blob + fe->offset);
+    m->colfac_h.assign(cf, cf + 2 * (size_t)nsp);
+    std::vector<int> ptr(nsp, 0), slot(std::max(nnz, 1), 0), col(std::max(nnz, 1), 0);
+    for (int p = 0; p < nnz; ++p) {
+        if (rows[p] < 1 || rows[p] >= nsp || cols[p] < 1 || cols[p] >= nsp) return fail(PYJAC_EINVAL, "bad factored-output pattern");
+        ++ptr[rows[p]];                      // ptr[k + 1] counts row k + 1 (k = 0 .. nsp-2)
+    }
+    for (int k = 1; k < nsp; ++k) ptr[k] += ptr[k - 1];
+    std::vector<int> fill(ptr.begin(), ptr.end());      // row k + 1 starts at ptr[k]
+    for (int p = 0; p < nnz; ++p) {
+        const int at = fill[rows[p] - 1]++;
+        slot[at] = nsp + 3 * (nsp - 1) + p;
+        col[at] = cols[p];
+    }
+    auto up = [&](const std::vector<int>& v, const int** out) -> int {
+        void* dptr = nullptr;
+        CU(cudaMalloc(&dptr, std::max<size_t>(v.size() * 4, 64)));
+        m->dev_allocs.push_back(dptr);
+        CU(cudaMemcpy(dptr, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+        *out = (const int*)dptr;
+        return PYJAC_OK;
+    };
+    pjc::Fac& f = m->fac;
+    f.nsp = nsp; f.nnz = nnz; f.colfac = m->plan.colfac;
+    std::vector<int> r_(m->fac_rows), c_(m->fac_cols);
+    if (r_.empty()) { r_.push_back(0); c_.push_back(0); }
+    int rc = up(ptr, &f.ptr);
+    if (!rc) rc = up(slot, &f.slot);
+    if (!rc) rc = up(col, &f.col);
+    if (!rc) rc = up(r_, &f.rows);
+    if (!rc) rc = up(c_, &f.cols);
+    m->plan.fac_nnz = nnz;
+    return rc;
 }
 
 template <typename T>
@@ -363,7 +423,8 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
         struct { const char* name; long long count; } want[] = {
             {"sp_w", d[0]}, {"sp_iw", d[0]}, {"sp_ruw", d[0]}, {"sp_tmid", d[0]}, {"sp_nasa", 32LL * d[0]},
             {"p5_rx", 16LL * d[1]}, {"p5_rxout", 4LL * d[1]}, {"red_off", d[0] + 1LL}, {"plog_off", d[1] + 1LL},
-            {"cheb_off", d[1] + 1LL}, {"sp_fwd_map", d[0]}, {"p5_colfac", 2LL * d[0]}};
+            {"cheb_off", d[1] + 1LL}, {"sp_fwd_map", d[0]}, {"p5_colfac", 2LL * d[0]},
+            {"p5_fac_map", (long long)d[0] * d[0]}};
         for (const auto& w_ : want) {
             const pjt::Entry* e = pjt::find(blob, w_.name);
             if (!e || e->count < w_.count) return fail(PYJAC_EINVAL, std::string("table blob: ") + w_.name + " is missing or too short");
@@ -437,6 +498,8 @@ int pyjac_mech_create(const void* blob, size_t len, int device, pyjac_mech** out
     UP(plan.o_off, "p5_o_off", int, 1); UP(plan.o_str, "p5_o_str", uint2, 1);
     UP(plan.t_off, "p5_t_off", int, 1); UP(plan.t_item, "p5_t_item", int2, 1); UP(plan.t_str, "p5_t_str", uint2, 1);
     UP(plan.colfac, "p5_colfac", double2, 0);
+    UP(plan.fac_map, "p5_fac_map", int, 1);
+    if (!rc) rc = setup_factored(m, blob);
     if (!rc && pjt::find(blob, "p6_cfg")) {
         const pjt::Entry* pe = pjt::find(blob, "p6_cfg");
         if (pe->dtype != 1 || pe->count < 24) rc = fail(PYJAC_EINVAL, "bad p6_cfg");
@@ -497,13 +560,13 @@ int pyjac_mech_tune(pyjac_mech* m, int blocks_per_sm)
 #endif
     if (!m) return fail(PYJAC_EINVAL, "bad argument");
     m->user_bpsm = blocks_per_sm;
-    m->bpsm[0] = m->bpsm[1] = m->bpsm[2] = 0;    // re-derive at next launch
+    m->bpsm[0] = m->bpsm[1] = m->bpsm[2] = m->bpsm[3] = 0;    // re-derive at next launch
     return PYJAC_OK;
 }
 
 int pyjac_mech_kernel_name(const pyjac_mech* m, int mode, char* buf, size_t len)
 {
-    if (!m || !buf || !len || mode < 0 || mode > 2) return fail(PYJAC_EINVAL, "bad argument");
+    if (!m || !buf || !len || mode < 0 || mode > 3) return fail(PYJAC_EINVAL, "bad argument");
     const void* fn = (mode == pj::M_JAC && m->has6) ? kernel6_for(m->plan6.gs, m->plan6.nt)
                                                      : kernel_for(m->plan.gs, mode, m->plan.nt, m->plan.wsg);
     if (!fn) return fail(PYJAC_EINVAL, "table blob holds no usable plan");
@@ -530,6 +593,95 @@ int pyjac_eval_jacob_dev(pyjac_mech* m, int n, const double* d_pres, const doubl
     if (const char* dbg = std::getenv("PYJAC_DEBUG_CLK")) io.dbg_clk = (long long*)std::strtoull(dbg, nullptr, 0);
 #endif
     return launch(m, pj::M_JAC, io, (cudaStream_t)stream);
+}
+
+
+/* ---- factored Jacobian and its consumers (csrc/consumer.cuh) ---- */
+
+int pyjac_factored_size(const pyjac_mech* m, int* nf, int* nnz)
+{
+    if (!m) return fail(PYJAC_EINVAL, "bad argument");
+    if (nf) *nf = m->tb.nsp + 3 * (m->tb.nsp - 1) + m->fac.nnz;
+    if (nnz) *nnz = m->fac.nnz;
+    return PYJAC_OK;
+}
+
+int pyjac_factored_pattern(const pyjac_mech* m, int* rows, int* cols, double* ca, double* cb)
+{
+    if (!m) return fail(PYJAC_EINVAL, "bad argument");
+    for (int p = 0; p < m->fac.nnz; ++p) {
+        if (rows) rows[p] = m->fac_rows[p];
+        if (cols) cols[p] = m->fac_cols[p];
+    }
+    for (int j = 0; j < m->tb.nsp; ++j) {
+        if (ca) ca[j] = j ? m->colfac_h[2 * j] : 0.0;
+        if (cb) cb[j] = j ? m->colfac_h[2 * j + 1] : 0.0;
+    }
+    return PYJAC_OK;
+}
+
+static int fac_layout_ok(const pyjac_mech* m, int n, int layout, long long ld)
+{
+    if (layout == PYJAC_JAC_STATE_FASTEST && (ld < n || ld >= (1LL << 28))) return fail(PYJAC_EINVAL, "ld must be in [n, 2^28)");
+    if (layout != PYJAC_JAC_STATE_FASTEST && layout != PYJAC_JAC_STATE_MAJOR) return fail(PYJAC_EINVAL, "bad layout");
+    (void)m;
+    return PYJAC_OK;
+}
+
+int pyjac_eval_jacob_factored_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_y,
+                                  long long y_ss, long long y_sv, double* d_fac, int fac_layout,
+                                  long long fac_ld, void* stream)
+{
+    if (!m || n < 0 || (n && (!d_pres || !d_y || !d_fac))) return fail(PYJAC_EINVAL, "bad argument");
+    if (int rc = fac_layout_ok(m, n, fac_layout, fac_ld)) return rc;
+    IO io{};
+    io.n = n; io.pres = d_pres; io.y = d_y; io.y_ss = y_ss; io.y_sv = y_sv;
+    io.jac = d_fac; io.jac_layout = fac_layout; io.jac_ld = fac_ld;
+    return launch(m, pj::M_FACT, io, (cudaStream_t)stream);
+}
+
+int pyjac_jvp_dev(pyjac_mech* m, int n, const double* d_fac, int fac_layout, long long fac_ld,
+                  const double* d_v, long long v_ss, long long v_sv,
+                  double* d_out, long long o_ss, long long o_sv, void* stream)
+{
+    if (!m || n < 0 || (n && (!d_fac || !d_v || !d_out))) return fail(PYJAC_EINVAL, "bad argument");
+    if (int rc = fac_layout_ok(m, n, fac_layout, fac_ld)) return rc;
+    if (!n) return PYJAC_OK;
+    DeviceGuard guard(m->device);
+    pjc::Fac f = m->fac;
+    f.fac = d_fac; f.sf = fac_layout == PYJAC_JAC_STATE_FASTEST; f.ld = fac_ld;
+    pjc::k_jvp<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(f, n, d_v, v_ss, v_sv, d_out, o_ss, o_sv);
+    CU(cudaGetLastError());
+    ++m->launches;
+    return PYJAC_OK;
+}
+
+int pyjac_newton_solve_dev(pyjac_mech* m, int n, const double* d_fac, int fac_layout, long long fac_ld,
+                           double gamma, const double* d_gamma,
+                           const double* d_rhs, long long r_ss, long long r_sv,
+                           double* d_x, long long x_ss, long long x_sv, int* d_info, void* stream)
+{
+    if (!m || n < 0 || (n && (!d_fac || !d_rhs || !d_x))) return fail(PYJAC_EINVAL, "bad argument");
+    if (int rc = fac_layout_ok(m, n, fac_layout, fac_ld)) return rc;
+    if (!n) return PYJAC_OK;
+    DeviceGuard guard(m->device);
+    const int nsp = m->tb.nsp;
+    const int ldm = nsp | 1;                                   // odd: row accesses spread over the banks
+    const size_t per_warp = ((size_t)ldm * nsp + 3 * (size_t)nsp) * 8;
+    if (per_warp > (size_t)m->smem_optin)
+        return fail(PYJAC_ETOOBIG, "the Newton matrix of this mechanism does not fit in shared memory");
+    const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)m->smem_optin / per_warp));
+    const size_t bytes = per_warp * wpb;
+    int rc = ensure_dyn_smem((const void*)pjc::k_newton, m->device, bytes, false);
+    if (rc) return rc;
+    const long long want = ((long long)n + wpb - 1) / wpb;
+    const int grid = (int)std::min<long long>(want, (long long)m->sm_count);
+    pjc::Fac f = m->fac;
+    f.fac = d_fac; f.sf = fac_layout == PYJAC_JAC_STATE_FASTEST; f.ld = fac_ld;
+    pjc::k_newton<<<grid, wpb * 32, bytes, (cudaStream_t)stream>>>(f, n, gamma, d_gamma, d_rhs, r_ss, r_sv, d_x, x_ss, x_sv, d_info, ldm);
+    CU(cudaGetLastError());
+    ++m->launches;
+    return PYJAC_OK;
 }
 
 static int dydt_dev(pyjac_mech* m, int n, const double* d_var, const double* d_y, long long y_ss, long long y_sv,
@@ -625,13 +777,13 @@ int pyjac_rates_dev(pyjac_mech* m, int n, const double* d_pres, const double* d_
 
 // Streams row-major host states through two pinned/device staging slots:
 // H2D(y, P) -> kernel -> D2H(result), chunk c+1 overlapping the D2H of chunk c.
-static int host_stream(pyjac_mech* m, int n, const double* pres, const double* y, double* out, bool jac)
+static int host_stream(pyjac_mech* m, int n, const double* pres, const double* y, double* out, int kind)   // kind: 0 dydt, 1 Jacobian, 2 factored record
 {
     if (!m || n < 0 || (n && (!pres || !y || !out))) return fail(PYJAC_EINVAL, "bad argument");
     if (!n) return PYJAC_OK;
     const int nsp = m->tb.nsp;
     const size_t in_w = (size_t)nsp + 1;                       // y row + pressure
-    const size_t out_w = jac ? (size_t)nsp * nsp : (size_t)nsp;
+    const size_t out_w = kind == 1 ? (size_t)nsp * nsp : kind == 2 ? (size_t)nsp + 3 * ((size_t)nsp - 1) + m->fac.nnz : (size_t)nsp;
     const size_t budget = (size_t)256 << 20;                   // bytes of output per chunk
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, budget / (out_w * 8)));
     int rc = ensure_staging(m, (size_t)chunk * in_w * 8, (size_t)chunk * in_w * 8, (size_t)chunk * out_w * 8);
@@ -647,7 +799,8 @@ static int host_stream(pyjac_mech* m, int n, const double* pres, const double* y
         CU(cudaMemcpyAsync(m->d_in[slot], hp, (size_t)cn * in_w * 8, cudaMemcpyHostToDevice, st));
         const double* dy_ = m->d_in[slot];
         const double* dp_ = dy_ + (size_t)cn * nsp;
-        if (jac) rc = pyjac_eval_jacob_dev(m, cn, dp_, dy_, nsp, 1, m->d_out[slot], PYJAC_JAC_STATE_MAJOR, 0, st);
+        if (kind == 1) rc = pyjac_eval_jacob_dev(m, cn, dp_, dy_, nsp, 1, m->d_out[slot], PYJAC_JAC_STATE_MAJOR, 0, st);
+        else if (kind == 2) rc = pyjac_eval_jacob_factored_dev(m, cn, dp_, dy_, nsp, 1, m->d_out[slot], PYJAC_JAC_STATE_MAJOR, 0, st);
         else rc = pyjac_dydt_dev(m, cn, dp_, dy_, nsp, 1, m->d_out[slot], nsp, 1, st);
         if (rc) return rc;
         CU(cudaMemcpyAsync(out + (size_t)s0 * out_w, m->d_out[slot], (size_t)cn * out_w * 8,
@@ -659,12 +812,17 @@ static int host_stream(pyjac_mech* m, int n, const double* pres, const double* y
 
 int pyjac_eval_jacob_host(pyjac_mech* m, int n, const double* pres, const double* y, double* jac)
 {
-    return host_stream(m, n, pres, y, jac, true);
+    return host_stream(m, n, pres, y, jac, 1);
+}
+
+int pyjac_eval_jacob_factored_host(pyjac_mech* m, int n, const double* pres, const double* y, double* fac)
+{
+    return host_stream(m, n, pres, y, fac, 2);
 }
 
 int pyjac_dydt_host(pyjac_mech* m, int n, const double* pres, const double* y, double* dy)
 {
-    return host_stream(m, n, pres, y, dy, false);
+    return host_stream(m, n, pres, y, dy, 0);
 }
 
 int pyjac_set_mechanism(pyjac_mech* m)

@@ -77,7 +77,8 @@ class Evaluator:
         return int(self.lib.pyjac_mech_launches(self._h))
 
     def kernel_name(self, mode: int = 0) -> str:
-        """Demangled symbol of the kernel behind eval_jacob (mode 0), dydt (1) or the rate routines (2)."""
+        """Demangled symbol of the kernel behind eval_jacob (mode 0), dydt (1), the rate routines (2) or the
+        factored Jacobian (3)."""
         import subprocess
         buf = ctypes.create_string_buffer(512)
         _lib.check(self.lib.pyjac_mech_kernel_name(self._h, mode, buf, len(buf)))
@@ -182,6 +183,99 @@ class Evaluator:
         _lib.check(self.lib.pyjac_rates_dev(self._h, n, _ptr(P), _ptr(y), ss, sv, *ptrs,
                                             1 if sf else 0, n, self._stream(stream)))
         return tuple(outs)
+
+    # ------------------------------------------------------------------ factored Jacobian and its consumers
+    @property
+    def factored_size(self):
+        """(NF, NNZ): doubles per state of the factored record, entries of its sparse block."""
+        import ctypes
+        nf, nnz = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.lib.pyjac_factored_size(self._h, ctypes.byref(nf), ctypes.byref(nnz)))
+        return nf.value, nnz.value
+
+    def factored_pattern(self):
+        """rows[NNZ], cols[NNZ] of the sparse block (indices into the NSP x NSP Jacobian) and the column
+        factors ca[NSP], cb[NSP] of the rank-2 part (include/pyjac_b200.h)."""
+        nf, nnz = self.factored_size
+        rows, cols = np.zeros(max(nnz, 1), dtype=np.int32), np.zeros(max(nnz, 1), dtype=np.int32)
+        ca, cb = np.zeros(self.NSP), np.zeros(self.NSP)
+        _lib.check(self.lib.pyjac_factored_pattern(self._h, rows.ctypes.data, cols.ctypes.data,
+                                                   ca.ctypes.data, cb.ctypes.data))
+        return rows[:nnz], cols[:nnz], ca, cb
+
+    def _fac_layout(self, fac, n, layout):
+        nf = self.factored_size[0]
+        if layout == 'rows':
+            assert fac.shape == (n, nf) and fac.is_contiguous()
+            return _lib.JAC_STATE_MAJOR, 0
+        assert fac.shape[0] == nf and fac.shape[1] >= n and fac.is_contiguous()
+        return _lib.JAC_STATE_FASTEST, fac.shape[1]
+
+    def eval_jacob_factored(self, P, y, out=None, y_layout: str = 'rows', fac_layout: str = 'rows', stream=None):
+        """The Jacobian as the record it is expanded from: NF doubles per state instead of NSP^2."""
+        torch = self._torch
+        self._check_dev(P, y, out)
+        n, ss, sv = self._strides(y, y_layout)
+        nf = self.factored_size[0]
+        if out is None:
+            out = torch.empty((n, nf) if fac_layout == 'rows' else (nf, n), dtype=torch.float64, device=y.device)
+        lay, ld = self._fac_layout(out, n, fac_layout)
+        _lib.check(self.lib.pyjac_eval_jacob_factored_dev(self._h, n, _ptr(P), _ptr(y), ss, sv, _ptr(out),
+                                                          lay, ld, self._stream(stream)))
+        return out
+
+    def expand_factored(self, fac: np.ndarray) -> np.ndarray:
+        """Host-side expansion of records (n, NF) to column-major dense Jacobians (n, NSP*NSP): what a caller of
+        the reference API would be handed; the parity tests compare this with the oracle."""
+        from . import factored
+        return factored.expand(fac, self.NSP, *self.factored_pattern())
+
+    def jvp(self, fac, v, out=None, fac_layout: str = 'rows', v_layout: str = 'rows', stream=None):
+        """J v per state from the records of :meth:`eval_jacob_factored` (J is never formed)."""
+        torch = self._torch
+        self._check_dev(fac, v, out)
+        n, ss, sv = self._strides(v, v_layout)
+        lay, ld = self._fac_layout(fac, n, fac_layout)
+        if out is None:
+            out = torch.empty_like(v)
+        assert out.shape == v.shape and out.is_contiguous()
+        _lib.check(self.lib.pyjac_jvp_dev(self._h, n, _ptr(fac), lay, ld, _ptr(v), ss, sv, _ptr(out), ss, sv,
+                                          self._stream(stream)))
+        return out
+
+    def newton_solve(self, fac, gamma, rhs, out=None, fac_layout: str = 'rows', v_layout: str = 'rows', stream=None):
+        """x = (I - gamma J)^-1 rhs per state (the linear solve of an implicit integrator step, SURVEY 8 f1);
+        ``gamma``: a float or a device tensor with one value per state.  Returns (x, info)."""
+        torch = self._torch
+        self._check_dev(fac, rhs, out)
+        n, ss, sv = self._strides(rhs, v_layout)
+        lay, ld = self._fac_layout(fac, n, fac_layout)
+        if out is None:
+            out = torch.empty_like(rhs)
+        assert out.shape == rhs.shape and out.is_contiguous()
+        info = torch.zeros(n, dtype=torch.int32, device=rhs.device)
+        if isinstance(gamma, (int, float)):
+            g, gp = float(gamma), None
+        else:
+            self._check_dev(gamma)
+            assert gamma.shape == (n,) and gamma.dtype == torch.float64 and gamma.is_contiguous()
+            g, gp = 0.0, _ptr(gamma)
+        _lib.check(self.lib.pyjac_newton_solve_dev(self._h, n, _ptr(fac), lay, ld, g, gp, _ptr(rhs), ss, sv,
+                                                   _ptr(out), ss, sv, _ptr(info), self._stream(stream)))
+        return out, info
+
+    def eval_jacob_factored_host(self, P, y, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """numpy rows in, records (n, NF) out: the host API with 8 NF instead of 8 NSP^2 bytes per state back."""
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        P = np.ascontiguousarray(np.broadcast_to(np.asarray(P, dtype=np.float64), (y.shape[0],)))
+        assert y.ndim == 2 and y.shape[1] == self.NSP
+        nf = self.factored_size[0]
+        if out is None:
+            out = np.empty((y.shape[0], nf))
+        assert out.flags.c_contiguous and out.shape == (y.shape[0], nf)
+        _lib.check(self.lib.pyjac_eval_jacob_factored_host(self._h, y.shape[0], P.ctypes.data, y.ctypes.data,
+                                                           out.ctypes.data))
+        return out
 
     # ------------------------------------------------------------------ host batch API
     def eval_jacob_host(self, P, y, out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -44,6 +44,16 @@ SIGNATURES = {
     'pyjac_cu_run': (None, [c_int, c_int] + [c_void_p] * 9),
     'pyjac_cu_cleanup': (None, []),
     'pyjac_eval_jacob_host': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'pyjac_factored_size': (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    'pyjac_factored_pattern': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'pyjac_eval_jacob_factored_dev': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_longlong,
+                                              c_void_p, c_int, c_longlong, c_void_p]),
+    'pyjac_eval_jacob_factored_host': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'pyjac_jvp_dev': (c_int, [c_void_p, c_int, c_void_p, c_int, c_longlong, c_void_p, c_longlong, c_longlong,
+                              c_void_p, c_longlong, c_longlong, c_void_p]),
+    'pyjac_newton_solve_dev': (c_int, [c_void_p, c_int, c_void_p, c_int, c_longlong, c_double, c_void_p,
+                                       c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_longlong,
+                                       c_void_p, c_void_p]),
     'pyjac_dydt_host': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'eval_jacob': (None, [c_double, c_double, c_void_p, c_void_p]),
     'dydt': (None, [c_double, c_double, c_void_p, c_void_p]),

@@ -27,7 +27,7 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
-PLAN_VERSION = 2             # of the p5_* schedule tables (checked by the library against its own)
+PLAN_VERSION = 3             # of the p5_* schedule tables (checked by the library against its own)
 SMEM_LIMIT = 232448          # bytes of dynamic shared memory one block may opt in to (sm_100)
 NSCAL = 24                   # per-state scalar rows: 2 x 8 from phase A0, 5 derived in DE, 2 x P (PLOG)
 NPART = 7                    # per-warp partial sums
@@ -390,6 +390,17 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
 
     # D: rows sorted by their number of dense-only columns, NSUB rows per item
     sparse_set = {(e[1], e[2]) for e in sparse}
+    # Factored output: [energy row: nsp][T column: nsp - 1][W_k a_k: nsp - 1][W_k b_k: nsp - 1]
+    # [sparse block (W_k / W_j) S_kj in column-major pattern order].  fac_map: dense element -> slot of the
+    # sparse block (-1: the element has no sparse part)
+    fac_pat = sorted(sparse_set)
+    fac_map = [-1] * (nsp * nsp)
+    for s_, (col, k) in enumerate(fac_pat):
+        fac_map[col * nsp + k + 1] = nsp + 3 * last + s_
+    P['p5_fac_map'] = i32(fac_map)
+    P['fac_rows'] = i32([k + 1 for col, k in fac_pat] or [0])
+    P['fac_cols'] = i32([col for col, k in fac_pat] or [0])
+    fac_nnz = len(fac_pat)
     d_rows = []                                # (row, its dense-only columns, owns the temperature column)
     for k in range(last):
         cols = [col for col in range(1, nsp) if (col, k) not in sparse_set]
@@ -496,5 +507,5 @@ def build_plan(nsp: int, nr: int, nraw: int, first_pm: int, kinds: List[str], is
     waiters = sum(1 for w in range(1, nw) if t_nst[w])
     t_sync = 32 * (waiters + 1) if waiters else 0
     P['p5_cfg'] = i32([gs, nt, nw, nsub, L['SP'], L['RX'], L['RAW'], L['SC'], L['PA'], L['total'], t_sync, coop, tcoop, L['CF'],
-                       1 if wsg else 0, 0])
+                       1 if wsg else 0, fac_nnz])
     return P

@@ -323,6 +323,9 @@ def evaluate(Tb, P, y, plan=5):
     colfac = Tb['p5_colfac'].reshape(nsp, 2)
     jac = np.full((n, nsp * nsp), np.nan)          # [state, col * nsp + row]; every element once
     NULL_E = 0x3FFFFF
+    # the factored record k_eval<.., M_FACT> writes instead (include/pyjac_b200.h)
+    fac_map, fac_nnz = Tb['p5_fac_map'], int(cfg[15])
+    fac = np.full((n, nsp + 3 * last + fac_nnz), np.nan)
 
     def rawrow(off):
         assert off % RB == 0 and off // RB <= nraw + 1      # rows nraw, nraw + 1: zeros
@@ -343,6 +346,8 @@ def evaluate(Tb, P, y, plan=5):
         assert k2 == k and sl == 4 and sl2 == 5 and col >= 1
         assert np.isnan(jac[:, eidx]).all() and eidx == col * nsp + k + 1
         jac[:, eidx] = colfac[col, 0] * slots8[:, k, sl] + colfac[col, 1] * slots8[:, k, sl2] + extra
+        assert fac_map[eidx] >= nsp + 3 * last and np.isnan(fac[:, fac_map[eidx]]).all()
+        fac[:, fac_map[eidx]] = extra
 
     d_str, d_item = Tb['p5_d_str'].view(np.uint32), Tb['p5_d_item'].reshape(-1, 2)
     s_str, o_str = Tb['p5_s_str'].view(np.uint32), Tb['p5_o_str'].view(np.uint32)
@@ -363,11 +368,12 @@ def evaluate(Tb, P, y, plan=5):
                 if e0 != NULL_E:                                   # temperature column: W_k * T-term
                     assert np.isnan(jac[:, e0]).all()
                     jac[:, e0] = slots8[:, k, 6]
+                    fac[:, nsp + k], fac[:, nsp + last + k], fac[:, nsp + 2 * last + k] = slots8[:, k, 6], slots8[:, k, 4], slots8[:, k, 5]
                 for i in range(ncol):
                     eidx, col = int(d_str[((u + 1 + i) * nsub + sub) * 2]), int(d_str[((u + 1 + i) * nsub + sub) * 2 + 1])
                     if eidx == NULL_E:
                         continue
-                    assert eidx == col * nsp + k + 1 and col >= 1 and np.isnan(jac[:, eidx]).all()
+                    assert eidx == col * nsp + k + 1 and col >= 1 and np.isnan(jac[:, eidx]).all() and fac_map[eidx] == -1
                     jac[:, eidx] = colfac[col, 0] * slots8[:, k, 4] + colfac[col, 1] * slots8[:, k, 5]
         # class S: two uint4 per element and step, overflow units beyond the first two
         lo, hi = int(Tb['p5_s_off'][wp]), int(Tb['p5_s_off'][wp + 1])
@@ -421,16 +427,18 @@ def evaluate(Tb, P, y, plan=5):
                 pj, qj = colfac[col]
                 jac[:, eidx] = pj * (-wt * HA) + qj * (-wt * HB) + pj * (-wt) * E0 \
                     + XT * (cp[:, col - 1] - cp[:, last])
+                fac[:, col] = jac[:, eidx]
     s0 = -wdcp / cp_avg * H1 + SCP + HT * rho
     jac[:, 0] = -s0 / (rho * cp_avg)
-    assert not np.isnan(jac).any()
+    fac[:, 0] = jac[:, 0]
+    assert not np.isnan(jac).any() and not np.isnan(fac).any()
     jac = jac.reshape(n, nsp, nsp)
 
     dydt = np.empty((n, nsp))
     dydt[:, 0] = -1.0 / (rho * cp_avg) * H1
     dydt[:, 1:] = wdot[:, :last] * w[None, :last] / rho[:, None]
     return dict(conc=conc[:, :nsp], fwd=fwd, rev=rev[:, :nrev], pres_mod=pres_mod[:, :npd],
-                spec_rates=wdot, dydt=dydt, jac=jac.reshape(n, nsp * nsp))
+                spec_rates=wdot, dydt=dydt, jac=jac.reshape(n, nsp * nsp), fac=fac)
 
 
 def _assemble6(v):

@@ -87,3 +87,32 @@ def test_table_structure(golden_dir):
     rows = sorted(int(v) for v in dst[:, :6].ravel() if v != 0xFFFF)
     assert len(set(rows)) == len(rows) and (not rows or rows[-1] < nraw)
     assert T['red_off'][-1] == len(T['red_rx']) == len(T['red_nu'])
+
+
+@pytest.mark.parametrize('mech_file,npz,sl', CASES)
+def test_factored_record_expands_to_the_jacobian(golden_dir, mech_file, npz, sl):
+    """the record k_eval<.., M_FACT> writes (energy row, T column, rank-2 factors, sparse block in a
+    fixed pattern) expands to the dense Jacobian, and J v computed from the record equals (dense J) v."""
+    from pyjac_b200 import factored
+    mech = Mechanism.from_chemkin(os.path.join(golden_dir, mech_file))
+    T = blob.unpack(blob.pack(tables.build(mech)))
+    g = {k: v[sl][:32] for k, v in np.load(os.path.join(golden_dir, npz)).items()}
+    out = kernel_model.evaluate(T, g['P'], g['y'])
+    nsp = mech.NSP
+    rows, cols, ca, cb = factored.pattern_from_tables(T)
+    assert len(rows) == int(T['p5_cfg'][15]) and out['fac'].shape[1] == nsp + 3 * (nsp - 1) + len(rows)
+    assert len(set(zip(rows.tolist(), cols.tolist()))) == len(rows) and rows.min() >= 1 and cols.min() >= 1
+    dense = factored.expand(out['fac'], nsp, rows, cols, ca, cb)
+    scale = np.abs(out['jac']).max(axis=1, keepdims=True)
+    assert (np.abs(dense - out['jac']) <= 4e-16 * scale).all()
+    gates.check_jac(dense, g['jac'], nsp, mech_file, mech, g['y'])
+    rng = np.random.default_rng(11)
+    v = rng.standard_normal((dense.shape[0], nsp))
+    ref = np.einsum('ncr,nc->nr', g['jac'].reshape(-1, nsp, nsp), v)          # golden J (column-major) times v
+    got = factored.jvp(out['fac'], v, nsp, rows, cols, ca, cb)
+    # J v sums NSP products whose magnitudes differ by many decades: compare against the sum of magnitudes
+    mag = np.einsum('ncr,nc->nr', np.abs(g['jac'].reshape(-1, nsp, nsp)), np.abs(v))
+    assert (np.abs(got - ref) <= 1e-9 * mag + 1e-300).all()
+    # the record is what makes the host round trip cheaper (the synthetic mechanisms draw their species at random, so
+    # their sparse blocks are denser than those of real mechanisms of the same size)
+    assert out['fac'].shape[1] < 0.75 * nsp * nsp or nsp <= 10
