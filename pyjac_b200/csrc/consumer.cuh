@@ -149,7 +149,22 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
                 b[i] = fma(-l, bc, b[i]);                                    // forward substitution on the fly
             }
             __syncwarp();
-            for (int j = c + 1; j < nsp; ++j) {
+            // trailing update, four columns at a time: independent chains hide the shared-memory latency
+            // (two warps per scheduler are all that fit next to their matrices)
+            int j = c + 1;
+            for (; j + 4 <= nsp; j += 4) {
+                double* q0 = M + (size_t)j * ldm;
+                double* q1 = q0 + ldm;
+                double* q2 = q1 + ldm;
+                double* q3 = q2 + ldm;
+                const double u0 = q0[c], u1 = q1[c], u2 = q2[c], u3 = q3[c];
+                for (int i = c + 1 + lane; i < nsp; i += 32) {
+                    const double l = colc[i];
+                    const double a0 = q0[i], a1 = q1[i], a2 = q2[i], a3 = q3[i];
+                    q0[i] = fma(-l, u0, a0); q1[i] = fma(-l, u1, a1); q2[i] = fma(-l, u2, a2); q3[i] = fma(-l, u3, a3);
+                }
+            }
+            for (; j < nsp; ++j) {
                 double* q = M + (size_t)j * ldm;
                 const double u = q[c];
                 for (int i = c + 1 + lane; i < nsp; i += 32) q[i] = fma(-colc[i], u, q[i]);

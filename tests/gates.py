@@ -68,6 +68,24 @@ def check_jac(new, ref, nsp, what='jac', mech=None, y=None):
     return worst, float((rel[b != 0] <= RTOL).mean())
 
 
+# Per fixture: (cap on the worst |d| / scale, floor on the fraction of non-zero elements that also agree ELEMENTWISE to
+# RTOL).  Measured on the B200 kernels and on the CPU model of the tables (tools/measure_gates.py; profiles/README.md
+# lists the measured values), then given a margin: worst x 10, fraction - 0.005.  The elementwise fraction is below 1
+# where the states sit near equilibrium: an element that is the difference of cancelling rates carries the rounding
+# of its terms, which the per-column scale of check_jac accounts for and an elementwise comparison cannot.
+CASE_LIMITS = {
+    'h2o2_n2.inp': (5.0e-11, 0.986), 'torture.inp': (2.0e-13, 0.971), 'gri30_syn.inp': (3.0e-13, 0.9995),
+    'usc2_syn.inp': (6.0e-13, 0.9995), 'plog.inp': (3.0e-13, 0.9995), 'cheb.inp': (3.0e-13, 0.9995),
+    'nega.inp': (2.0e-11, 0.985),
+}
+
+
+def check_case(mech_file, worst, frac):
+    cap, floor = CASE_LIMITS[mech_file]
+    assert worst <= cap, '%s: |d|/scale %.3e above the measured level (cap %.1e)' % (mech_file, worst, cap)
+    assert frac >= floor, '%s: elementwise agreement %.5f below the measured level (floor %.4f)' % (mech_file, frac, floor)
+
+
 def check_rates(mech, P, y, new, ref, what=''):
     """new / ref: dicts with conc, fwd, rev, pres_mod, spec_rates and optionally dydt."""
     w = np.array([sp.mw for sp in mech.specs])

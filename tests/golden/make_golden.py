@@ -11,12 +11,16 @@ evaluates the emitted C on fixed states and stores inputs and outputs:
     tests/golden/torture_pasr.npz  branch-coverage mechanism, every 4th of those states
     tests/golden/gri30_syn.npz     GRI-3.0-shaped synthetic mechanism, 48 synthetic states
     tests/golden/usc2_syn.npz      USC-Mech-II-shaped synthetic mechanism (111 sp / 784 rxn, species with
-                                   different T_mid), 8 synthetic states
+                                   different T_mid), 64 synthetic states
 
     tests/golden/plog_syn.npz      PLOG coverage mechanism over the H2/O2 species, 192 synthetic states of
                                    which 32 below and 32 above every pressure table
     tests/golden/cheb_syn.npz      Chebyshev coverage mechanism over the H2/O2 species, 160 synthetic states of
                                    which 32 outside the fitted pressure ranges
+
+    tests/golden/nc7_syn.npz       n-heptane-sized synthetic mechanism (654 sp / 2827 rxn; the file is synth.write('nc7', seed=0)),
+                                   4 synthetic states; rates and dydt in full, of the Jacobian all rows of 96 columns and
+                                   all columns of 32 rows (+ the per-column maxima the gate scales with)
 
     tests/golden/nega_pasr.npz     negative pre-exponential factors (duplicate pairs, every A < 0 branch of rs:108-141),
                                    every 4th PaSR state
@@ -80,6 +84,35 @@ if __name__ == '__main__':
         shutil.copy('/root/reference/data/h2_pasr_output.npy', pasr)
     only = set(sys.argv[1:])               # e.g. `make_golden.py conv` regenerates only the constant-volume vectors
 
+    if 'nc7' in only:
+        # 654 species / 2827 reactions: the generator emits 7.5 M lines of C (609 MB); built outside the repo with -O0
+        # (no value-changing optimisation is enabled at -O3 -mtune=native either: the other fixtures are bit-identical
+        # at both levels), and only a sample of the Jacobian is kept: all rows of 96 columns, all columns of 32 rows
+        build_ref.OUT_ROOT = '/tmp/pyjac_ref_big'
+        nc7 = '/tmp/pyjac_ref_big/nc7_syn.inp'
+        os.makedirs(build_ref.OUT_ROOT, exist_ok=True)
+        synth.write('nc7', nc7, seed=0)
+        mech = Mechanism.from_chemkin(nc7)
+        P, y = synthetic_states(mech.NSP, 4, seed=21)
+        lib = build_ref.build('nc7', nc7, opt='-O0', jobs=8)
+        ref = RefLib(lib)
+        conc, fwd, rev, pm, sr = ref.rates(P, y)
+        jac = ref.eval_jacob(P, y, 1).reshape(4, mech.NSP, mech.NSP)            # [state, col, row]
+        rng = np.random.default_rng(0)
+        cols = np.unique(np.concatenate([[0, 1, mech.NSP - 1], rng.choice(mech.NSP, 93, replace=False)]))
+        rows = np.unique(np.concatenate([[0, 1, mech.NSP - 1], rng.choice(mech.NSP, 29, replace=False)]))
+        np.savez_compressed(os.path.join(HERE, 'nc7_syn.npz'), P=P, y=y, conc=conc, fwd=fwd, rev=rev, pres_mod=pm,
+                            spec_rates=sr, dydt=ref.dydt(P, y, 1), cols=cols, rows=rows,
+                            jac_cols=jac[:, cols, :], jac_rows=jac[:, :, rows],
+                            jac_colmax=np.abs(jac).max(axis=2))
+        print('nc7', y.shape, 'sampled jac', jac[:, cols, :].shape, jac[:, :, rows].shape)
+        sys.exit(0)
+    if 'usc2' in only:
+        usc = os.path.join(HERE, 'usc2_syn.inp')
+        mech = Mechanism.from_chemkin(usc)
+        P, y = synthetic_states(mech.NSP, 64, seed=7)
+        dump('usc2', usc, P, y, 'usc2_syn.npz')
+        sys.exit(0)
     if 'nega' in only:
         mech = Mechanism.from_chemkin(os.path.join(HERE, 'nega.inp'))
         P, y = pasr_states(pasr, mech)
@@ -116,7 +149,7 @@ if __name__ == '__main__':
     usc = os.path.join(HERE, 'usc2_syn.inp')
     synth.write('usc2', usc, seed=0)
     mech = Mechanism.from_chemkin(usc)
-    P, y = synthetic_states(mech.NSP, 8, seed=7)
+    P, y = synthetic_states(mech.NSP, 64, seed=7)
     dump('usc2', usc, P, y, 'usc2_syn.npz')
 
     plog = os.path.join(HERE, 'plog.inp')

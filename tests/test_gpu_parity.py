@@ -54,7 +54,7 @@ def test_device_api_vs_reference_golden(torch, golden_dir, mech_file, npz, layou
     gates.check_rates(mech, g['P'], g['y'], new, g, mech_file)
     gates.check_dydt(mech, g['y'], dy2, g, mech_file + ' dydt kernel')
     worst, frac = gates.check_jac(np.ascontiguousarray(jac), g['jac'], mech.NSP, mech_file, mech, g['y'])
-    assert frac > 0.97
+    gates.check_case(mech_file, worst, frac)
     ev.close()
 
 
@@ -237,7 +237,7 @@ def test_working_set_in_global_memory(torch, golden_dir, mech_file, npz, gs):
     gates.check_rates(mech, g['P'], g['y'], new, g, mech_file)
     gates.check_dydt(mech, g['y'], dy2.cpu().numpy().T, g, mech_file + ' dydt kernel')
     worst, frac = gates.check_jac(np.ascontiguousarray(jac.cpu().numpy().T), g['jac'], mech.NSP, mech_file, mech, g['y'])
-    assert frac > 0.97
+    gates.check_case(mech_file, worst, frac)
     # the host-pointer API runs its chunks on two streams: they share the working sets
     jh = ev.eval_jacob_host(g['P'], g['y'])
     gates.check_jac(jh, g['jac'], mech.NSP, mech_file + ' host api', mech, g['y'])
@@ -379,7 +379,7 @@ def test_pyjacob_wrappers_vs_reference_golden(torch, golden_dir, tmp_path):
     back = {k: v.reshape(-1, num).T for k, v in outs.items()}
     gates.check_rates(mech, g['P'], g['y'], back, g, 'cu_pyjacob')
     worst, frac = gates.check_jac(np.ascontiguousarray(back['jac']), g['jac'], nsp, 'cu_pyjacob', mech, g['y'])
-    assert frac > 0.97
+    gates.check_case('h2o2_n2.inp', worst, frac)
     mod.close()
 
 
