@@ -79,6 +79,35 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+def bind_near_gpu(torch, dev):
+    """Pinned staging buffers should live on the NUMA node the GPU hangs off: restrict this process to that node's
+    CPUs before they are allocated (first touch places the pages).  Returns what was found and done, and the previous
+    affinity for restore().  On hosts that expose a single node (the VMs of this pool) there is nothing to do."""
+    info = {'nodes_visible': None, 'gpu_node': None, 'bound': False}
+    prev = None
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir('/sys/devices/system/node') if d.startswith('node') and d[4:].isdigit())
+        info['nodes_visible'] = len(nodes)
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bdf).read())
+        info['gpu_node'] = node
+        if len(nodes) > 1 and node >= 0:
+            cpus = set()
+            for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            prev = os.sched_getaffinity(0)
+            use = cpus & prev
+            if use:
+                os.sched_setaffinity(0, use)
+                info['bound'] = True
+                info['cpus'] = len(use)
+    except Exception as exc:                              # sysfs layout / permissions: report, do not fail the bench
+        info['note'] = str(exc).splitlines()[0][:120]
+    return info, prev
+
+
 def measured_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -516,6 +545,7 @@ def run_ours(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         import psutil
+        numa, prev_aff = bind_near_gpu(torch, dev)
         n_e = n
         need = n_e * nsp * nsp * 8
         avail = psutil.virtual_memory().available // max(1, min(world, torch.cuda.device_count()))
@@ -546,6 +576,7 @@ def run_ours(args, rank, world, local_rank):
                'h2d_bytes_per_step': n_e * (nsp + 1) * 8, 'd2h_bytes_per_step': n_e * nsp * nsp * 8,
                'states_per_step': n_e, 'steps': e_steps,
                'd2h_gbs': n_e * world * e_steps * nsp * nsp * 8 / dt / 1e9,
+               'numa': numa,
                'api': 'pyjac_eval_jacob_host (pinned host rows in, pinned host Jacobians out)'}
         del yp, Pp, jp
 
@@ -557,6 +588,9 @@ def run_ours(args, rank, world, local_rank):
                                                    e_steps, barrier, max_over_ranks, j_chk)
         except Exception as exc:                      # side records must not cost the headline line
             e2e_factored = {'error': str(exc).splitlines()[0][:200]}
+
+    if not args.no_e2e and prev_aff is not None:
+        os.sched_setaffinity(0, prev_aff)                 # the CPU baseline below uses every host thread again
 
     # ---- BASELINE.json's other configurations on this rank count ------------------------
     del jac

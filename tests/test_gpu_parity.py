@@ -281,6 +281,43 @@ def test_n_heptane_sized_mechanism_vs_oracle(torch, tmp_path):
     ev.close()
 
 
+def test_n_heptane_sized_mechanism_vs_reference_golden(torch, golden_dir, tmp_path):
+    """The same mechanism against the REFERENCE's generated C (tests/golden/nc7_syn.npz: rates and dydt in full, the
+    Jacobian on all rows of 95 columns and all columns of 32 rows, with the per-column maxima the gate scales by)."""
+    from pyjac_b200 import synth
+    from pyjac_b200.evaluator import Evaluator
+    path = str(tmp_path / 'nc7.inp')
+    synth.write('nc7', path, seed=0)
+    mech = Mechanism.from_chemkin(path)
+    g = dict(np.load(os.path.join(golden_dir, 'nc7_syn.npz')))
+    nsp = mech.NSP
+    ev = Evaluator(mech)
+    P, y = torch.tensor(g['P'], device='cuda'), torch.tensor(g['y'], device='cuda')
+    new = dict(zip(KEYS + ['dydt'], [o.cpu().numpy() for o in ev.rates(P, y, want_dy=True)]))
+    gates.check_rates(mech, g['P'], g['y'], new, g, 'nc7 golden')
+    jac = ev.eval_jacob(P, y).cpu().numpy().reshape(-1, nsp, nsp)           # [state, col, row]
+    # the gate of gates.check_jac on the stored sample: per-column maximum, the energy row's own scale
+    cp, h = gates._thermo(mech, g['y'][:, 0])
+    Y = np.concatenate([g['y'][:, 1:], 1.0 - g['y'][:, 1:].sum(axis=1, keepdims=True)], axis=1)
+    cp_avg = (Y * cp).sum(axis=1)
+    colmax = g['jac_colmax']                                                 # [state, col]
+    for got, ref, cm in ((jac[:, g['cols'], :], g['jac_cols'], colmax[:, g['cols']][:, :, None]),
+                         (jac[:, :, g['rows']], g['jac_rows'], colmax[:, :, None])):
+        scale = np.broadcast_to(cm, ref.shape).copy()
+        err = np.abs(got - ref) / (scale + 1e-300)
+        rows0 = np.broadcast_to((np.arange(ref.shape[2]) if ref.shape[2] == nsp else g['rows'])[None, None, :] == 0, ref.shape)
+        assert err[~rows0].max() <= gates.RTOL, err[~rows0].max()
+    # energy-equation row of the sampled columns: scale max(colmax, sum_k |h_k J[k, j]| / cp_avg)
+    ref_c = g['jac_cols']
+    row0 = (np.abs(h[:, None, :nsp - 1]) * np.abs(ref_c[:, :, 1:])).sum(axis=2) / cp_avg[:, None]
+    sc0 = np.maximum(colmax[:, g['cols']], row0)
+    assert (np.abs(jac[:, g['cols'], 0] - ref_c[:, :, 0]) / (sc0 + 1e-300)).max() <= gates.RTOL
+    rel = np.abs(jac[:, g['cols'], :] - ref_c) / (np.abs(ref_c) + 1e-300)
+    frac = float((rel[ref_c != 0] <= gates.RTOL).mean())
+    assert frac > 0.999, frac
+    ev.close()
+
+
 def test_fd_self_check(torch, golden_dir):
     """On-device finite-difference Jacobian of dydt (the reference's fd_jacob.cu comparison) against
     the analytical Jacobian: an oracle-free check.  Sixth-order central differences with CVODE-style

@@ -73,3 +73,23 @@ def test_oracle_constant_volume_dydt_matches_reference(golden_dir, mech_file, np
     g = np.load(os.path.join(golden_dir, npz))
     dy = Oracle(mech).dydt_conv(g['rho'], g['y'])
     assert _close(dy, g['dydt'], npz) > 0.999
+
+
+def test_oracle_matches_reference_on_the_n_heptane_sized_mechanism(golden_dir, tmp_path):
+    """654 species / 2827 reactions through the reference's own generator (tests/golden/make_golden.py nc7): rates and
+    dydt in full, the Jacobian on the stored sample (all rows of 95 columns, all columns of 32 rows), bitwise."""
+    from pyjac_b200 import synth
+    path = str(tmp_path / 'nc7.inp')
+    synth.write('nc7', path, seed=0)
+    mech = Mechanism.from_chemkin(path)
+    g = np.load(os.path.join(golden_dir, 'nc7_syn.npz'))
+    ora = Oracle(mech)
+    nsp = mech.NSP
+    assert (ora.NSP, ora.NR) == (654, 2827) and g['y'].shape == (4, nsp)
+    for key, arr in zip(KEYS, ora.rates(g['P'], g['y'])):
+        assert np.array_equal(arr, g[key]), key
+    assert np.array_equal(ora.dydt(g['P'], g['y']), g['dydt'])
+    jac = ora.eval_jacob(g['P'], g['y']).reshape(4, nsp, nsp)               # [state, col, row]
+    assert np.array_equal(jac[:, g['cols'], :], g['jac_cols'])
+    assert np.array_equal(jac[:, :, g['rows']], g['jac_rows'])
+    assert np.array_equal(np.abs(jac).max(axis=2), g['jac_colmax'])
