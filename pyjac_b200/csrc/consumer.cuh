@@ -21,6 +21,8 @@
 
 namespace pjc {
 
+enum : int { NEWTON_MAX_R = 6 };      // rows per lane k_newton is instantiated for: NSP <= 192 (shared memory ends it near 165)
+
 struct Fac {
     int nsp, nnz;
     const double* fac;       // the records
@@ -72,10 +74,24 @@ __global__ void __launch_bounds__(128) k_jvp(Fac f, int n, const double* __restr
     }
 }
 
+__device__ __forceinline__ double lds64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
 // x = (I - gamma J)^-1 r, one warp per state.  Shared memory per warp: the matrix column-major with
-// leading dimension ldm (odd), the right-hand side, WA / WB of the state.  gamma: one value for all
-// states (gamma_s == nullptr) or one per state.
-//   info[s] = 0, or c + 1 when column c had no usable pivot (the state's x is then not written).
+// leading dimension ldm (odd), the right-hand side, WA / WB of the state.  A lane owns the rows
+// lane, lane + 32, ... (R = ceil(nsp / 32) of them): their multipliers stay in registers through the
+// trailing update, which walks the columns with one broadcast load of the pivot row's element and one
+// load / fma / store per owned row.  gamma: one value for all states (gamma_s == nullptr) or one per
+// state.  info[s] = 0, or c + 1 when column c had no usable pivot (the state's x is then not written).
+template <int R>
 __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, const double* __restrict__ gamma_s,
                                                 const double* __restrict__ r, long long r_ss, long long r_sv,
                                                 double* __restrict__ x, long long x_ss, long long x_sv,
@@ -89,6 +105,8 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
     double* b = M + (size_t)ldm * nsp;
     double* wa = b + nsp;
     double* wb = wa + nsp;
+    const unsigned aM = (unsigned)__cvta_generic_to_shared(M), aB = (unsigned)__cvta_generic_to_shared(b);
+    const unsigned cstep = (unsigned)ldm * 8u;                  // bytes between columns
     for (long long s = (long long)blockIdx.x * wpb + warp; s < n; s += (long long)gridDim.x * wpb) {
         const double g = gamma_s ? gamma_s[s] : gamma;
         // ---- expand -gamma J (+ I) into shared memory
@@ -102,10 +120,21 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
             b[j] = r[s * r_ss + (long long)j * r_sv];
         }
         __syncwarp();
-        for (int j = 1; j < nsp; ++j) {
-            const double2 c = __ldg(f.colfac + j);
-            double* col = M + (size_t)j * ldm;
-            for (int k = lane; k < last; k += 32) col[k + 1] = -g * fma(c.x, wa[k], c.y * wb[k]);
+        {
+            double was[R], wbs[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int k = lane + 32 * q;
+                was[q] = k < last ? -g * wa[k] : 0.0;
+                wbs[q] = k < last ? -g * wb[k] : 0.0;
+            }
+            unsigned ac = aM + cstep + 8u * (unsigned)(lane + 1);
+            for (int j = 1; j < nsp; ++j, ac += cstep) {
+                const double2 c = __ldg(f.colfac + j);
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (lane + 32 * q < last) sts64(ac + 256u * q, fma(c.x, was[q], c.y * wbs[q]));
+            }
         }
         __syncwarp();
         for (int p = lane; p < f.nnz; p += 32) {
@@ -119,13 +148,18 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
         // ---- LU with partial pivoting (right-looking), the right-hand side carried along
         int bad = 0;
         for (int c = 0; c < nsp; ++c) {
-            double* colc = M + (size_t)c * ldm;
+            const unsigned acol = aM + (unsigned)c * cstep;
             double best = -1.0;
             int arg = c;
-            for (int i = c + lane; i < nsp; i += 32) {
-                const double a = fabs(colc[i]);
-                if (a > best) { best = a; arg = i; }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int i = lane + 32 * q;
+                if (i >= c && i < nsp) {
+                    const double a = fabs(lds64(acol + 8u * i));
+                    if (a > best) { best = a; arg = i; }
+                }
             }
+#pragma unroll
             for (int o = 16; o; o >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, o);
                 const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
@@ -134,51 +168,69 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
             if (!(best > 0.0) || !isfinite(best)) { bad = c + 1; break; }
             if (arg != c) {
                 for (int j = lane; j < nsp; j += 32) {
-                    double* q = M + (size_t)j * ldm;
-                    const double t = q[c]; q[c] = q[arg]; q[arg] = t;
+                    const unsigned q = aM + (unsigned)j * cstep;
+                    const double t0 = lds64(q + 8u * c), t1 = lds64(q + 8u * arg);
+                    sts64(q + 8u * c, t1); sts64(q + 8u * arg, t0);
                 }
-                if (lane == 0) { const double t = b[c]; b[c] = b[arg]; b[arg] = t; }
+                if (lane == 0) { const double t0 = lds64(aB + 8u * c), t1 = lds64(aB + 8u * arg); sts64(aB + 8u * c, t1); sts64(aB + 8u * arg, t0); }
             }
             __syncwarp();
-            const double ip = 1.0 / colc[c];
-            const double bc = b[c];
+            const double ip = 1.0 / lds64(acol + 8u * c);
+            const double bc = lds64(aB + 8u * c);
             __syncwarp();
-            for (int i = c + 1 + lane; i < nsp; i += 32) {
-                const double l = colc[i] * ip;
-                colc[i] = l;
-                b[i] = fma(-l, bc, b[i]);                                    // forward substitution on the fly
+            // multipliers of the owned rows below the pivot (0 for the others: their updates are no-ops
+            // that are skipped by predicate), forward substitution on the fly
+            double l[R];
+            bool on[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int i = lane + 32 * q;
+                on[q] = i > c && i < nsp;
+                l[q] = 0.0;
+                if (on[q]) {
+                    l[q] = lds64(acol + 8u * i) * ip;
+                    sts64(acol + 8u * i, l[q]);
+                    sts64(aB + 8u * i, fma(-l[q], bc, lds64(aB + 8u * i)));
+                }
             }
-            __syncwarp();
-            // trailing update, four columns at a time: independent chains hide the shared-memory latency
-            // (two warps per scheduler are all that fit next to their matrices)
+            // trailing update: column j -= l * M[c][j]
+            unsigned aj = acol + cstep;
             int j = c + 1;
-            for (; j + 4 <= nsp; j += 4) {
-                double* q0 = M + (size_t)j * ldm;
-                double* q1 = q0 + ldm;
-                double* q2 = q1 + ldm;
-                double* q3 = q2 + ldm;
-                const double u0 = q0[c], u1 = q1[c], u2 = q2[c], u3 = q3[c];
-                for (int i = c + 1 + lane; i < nsp; i += 32) {
-                    const double l = colc[i];
-                    const double a0 = q0[i], a1 = q1[i], a2 = q2[i], a3 = q3[i];
-                    q0[i] = fma(-l, u0, a0); q1[i] = fma(-l, u1, a1); q2[i] = fma(-l, u2, a2); q3[i] = fma(-l, u3, a3);
+            for (; j + 4 <= nsp; j += 4, aj += 4 * cstep) {
+                const double u0 = lds64(aj + 8u * c), u1 = lds64(aj + cstep + 8u * c);
+                const double u2 = lds64(aj + 2 * cstep + 8u * c), u3 = lds64(aj + 3 * cstep + 8u * c);
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    if (!on[q]) continue;
+                    const unsigned ai = aj + 8u * (unsigned)(lane + 32 * q);
+                    const double a0 = lds64(ai), a1 = lds64(ai + cstep), a2 = lds64(ai + 2 * cstep), a3 = lds64(ai + 3 * cstep);
+                    sts64(ai, fma(-l[q], u0, a0)); sts64(ai + cstep, fma(-l[q], u1, a1));
+                    sts64(ai + 2 * cstep, fma(-l[q], u2, a2)); sts64(ai + 3 * cstep, fma(-l[q], u3, a3));
                 }
             }
-            for (; j < nsp; ++j) {
-                double* q = M + (size_t)j * ldm;
-                const double u = q[c];
-                for (int i = c + 1 + lane; i < nsp; i += 32) q[i] = fma(-colc[i], u, q[i]);
+            for (; j < nsp; ++j, aj += cstep) {
+                const double u = lds64(aj + 8u * c);
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    if (!on[q]) continue;
+                    const unsigned ai = aj + 8u * (unsigned)(lane + 32 * q);
+                    sts64(ai, fma(-l[q], u, lds64(ai)));
+                }
             }
             __syncwarp();
         }
         if (!bad) {
             // ---- back substitution, column oriented
             for (int c = nsp - 1; c >= 0; --c) {
-                const double* colc = M + (size_t)c * ldm;
-                const double xc = b[c] / colc[c];
+                const unsigned acol = aM + (unsigned)c * cstep;
+                const double xc = lds64(aB + 8u * c) / lds64(acol + 8u * c);
                 __syncwarp();
-                if (lane == 0) b[c] = xc;
-                for (int i = lane; i < c; i += 32) b[i] = fma(-colc[i], xc, b[i]);
+                if (lane == 0) sts64(aB + 8u * c, xc);
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const int i = lane + 32 * q;
+                    if (i < c) sts64(aB + 8u * i, fma(-lds64(acol + 8u * i), xc, lds64(aB + 8u * i)));
+                }
                 __syncwarp();
             }
             for (int j = lane; j < nsp; j += 32) x[s * x_ss + (long long)j * x_sv] = b[j];

@@ -672,13 +672,21 @@ int pyjac_newton_solve_dev(pyjac_mech* m, int n, const double* d_fac, int fac_la
         return fail(PYJAC_ETOOBIG, "the Newton matrix of this mechanism does not fit in shared memory");
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)m->smem_optin / per_warp));
     const size_t bytes = per_warp * wpb;
-    int rc = ensure_dyn_smem((const void*)pjc::k_newton, m->device, bytes, false);
+    const int rpl = (nsp + 31) / 32;                           // rows per lane
+    const void* fn = rpl == 1 ? (const void*)pjc::k_newton<1> : rpl == 2 ? (const void*)pjc::k_newton<2>
+                   : rpl == 3 ? (const void*)pjc::k_newton<3> : rpl == 4 ? (const void*)pjc::k_newton<4>
+                   : rpl == 5 ? (const void*)pjc::k_newton<5> : rpl == 6 ? (const void*)pjc::k_newton<6> : nullptr;
+    if (!fn) return fail(PYJAC_ETOOBIG, "the Newton matrix of this mechanism does not fit in shared memory");
+    int rc = ensure_dyn_smem(fn, m->device, bytes, false);
     if (rc) return rc;
     const long long want = ((long long)n + wpb - 1) / wpb;
-    const int grid = (int)std::min<long long>(want, (long long)m->sm_count);
+    int grid = (int)std::min<long long>(want, (long long)m->sm_count);
     pjc::Fac f = m->fac;
     f.fac = d_fac; f.sf = fac_layout == PYJAC_JAC_STATE_FASTEST; f.ld = fac_ld;
-    pjc::k_newton<<<grid, wpb * 32, bytes, (cudaStream_t)stream>>>(f, n, gamma, d_gamma, d_rhs, r_ss, r_sv, d_x, x_ss, x_sv, d_info, ldm);
+    int ldm_ = ldm;
+    void* args[] = {(void*)&f, (void*)&n, (void*)&gamma, (void*)&d_gamma, (void*)&d_rhs, (void*)&r_ss, (void*)&r_sv,
+                    (void*)&d_x, (void*)&x_ss, (void*)&x_sv, (void*)&d_info, (void*)&ldm_};
+    CU(cudaLaunchKernel(fn, dim3(grid), dim3(wpb * 32), args, bytes, (cudaStream_t)stream));
     CU(cudaGetLastError());
     ++m->launches;
     return PYJAC_OK;

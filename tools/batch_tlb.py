@@ -19,7 +19,7 @@ P_h, y_h = synthetic_states(nsp, 1 << 16, seed=0)
 P = torch.tensor(P_h, device='cuda').repeat(nmax >> 16)
 y_sf = torch.tensor(y_h, device='cuda').t().contiguous().repeat(1, nmax >> 16)
 y_rows = y_sf.t().contiguous()
-out = torch.empty(nn * nmax, dtype=torch.float64, device='cuda')
+out = torch.empty(nn * (nmax + 64), dtype=torch.float64, device='cuda')
 
 
 def timed(fn):
@@ -35,11 +35,12 @@ def timed(fn):
 
 
 print('| states | layout | ld | stride between elements of a state | ms | states/s |\n|---|---|---|---|---|---|')
-for n, ld in ((1 << 20, 1 << 20), (1 << 21, 1 << 21), (1 << 21, 1 << 22), (1 << 22, 1 << 22), (1 << 20, 1 << 22), (3 << 20, 3 << 20)):
+for n, ld in ((1 << 20, 1 << 20), (1 << 21, 1 << 21), (1 << 21, 1 << 22), (1 << 22, 1 << 22), (1 << 20, 1 << 22), (3 << 20, 3 << 20),
+              (1 << 22, (1 << 22) + 64), (1 << 20, (1 << 22) + 64)):
     o = out[:nn * ld].view(nn, ld)
     yy = y_sf[:, :n].contiguous()
     ms = timed(lambda: ev.eval_jacob(P[:n], yy, o, y_layout='state_fastest', jac_layout='state_fastest'))
-    print('| %d | state-fastest | %d | %d MB | %.2f | %.3e |' % (n, ld, ld * 8 >> 20, ms, n / ms * 1e3))
+    print('| %d | state-fastest | %d | %.4f MB | %.2f | %.3e |' % (n, ld, ld * 8 / 2 ** 20, ms, n / ms * 1e3))
     del yy
 for n in (1 << 20, 1 << 22):
     o = out[:nn * n].view(n, nn)
