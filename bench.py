@@ -582,7 +582,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the same call with the factored record out, and the consumer step on the device (8 f1)
     e2e_factored = consumer = None
-    if e2e is not None and not args.no_factored:
+    if e2e is not None and not args.no_factored and world == 1:        # single-GPU side records (no collective inside: a
+        # failure on one rank must not leave the others waiting)
         try:
             e2e_factored, consumer = factored_runs(ev, torch, dev, mech, P_h, y_h, e2e['states_per_step'], world,
                                                    e_steps, barrier, max_over_ranks, j_chk)
