@@ -37,26 +37,44 @@ def _nvcc() -> str:
     return exe
 
 
+def _fresh() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return False
+    built = os.path.getmtime(LIB_PATH)
+    return all(os.path.getmtime(s) <= built for s in _sources())
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/pyjac_b200.cu for sm_100a if the in-tree library is missing or stale."""
-    if not force and os.path.exists(LIB_PATH):
-        built = os.path.getmtime(LIB_PATH)
-        if all(os.path.getmtime(s) <= built for s in _sources()):
-            return LIB_PATH
-        if not (shutil.which('nvcc') or os.path.exists('/usr/local/cuda/bin/nvcc')):
-            return LIB_PATH        # a box without nvcc uses the library it was shipped
+    """Compile csrc/pyjac_b200.cu for sm_100a if the in-tree library is missing or stale.  Safe when several
+    processes (one per GPU under torchrun) get here together: the build runs under an exclusive file lock, into a
+    temporary file that replaces the library atomically, and whoever waited for the lock finds it fresh."""
+    import fcntl
+    if not force and _fresh():
+        return LIB_PATH
+    if not force and os.path.exists(LIB_PATH) and not (shutil.which('nvcc') or os.path.exists('/usr/local/cuda/bin/nvcc')):
+        return LIB_PATH            # a box without nvcc uses the library it was shipped
     os.makedirs(BUILD, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC,
-                                    '-o', LIB_PATH, os.path.join(CSRC, 'pyjac_b200.cu')]
-    cmd[1:1] = os.environ.get('PYJAC_B200_NVCC_EXTRA', '').split()      # development builds
-    if verbose:
-        cmd.insert(1, '-Xptxas')
-        cmd.insert(2, '-v')
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(os.path.join(BUILD, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _fresh():
+                return LIB_PATH
+            tmp = LIB_PATH + '.tmp%d' % os.getpid()
+            cmd = [_nvcc()] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC,
+                                            '-o', tmp, os.path.join(CSRC, 'pyjac_b200.cu')]
+            if verbose:
+                cmd.insert(1, '-Xptxas')
+                cmd.insert(2, '-v')
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
