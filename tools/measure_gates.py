@@ -10,6 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+import _devlib                                                 # noqa: E402,F401  (PYJAC_B200_LIB: development builds)
 import gates                                                   # noqa: E402
 import torch                                                   # noqa: E402
 from pyjac_b200.evaluator import Evaluator                     # noqa: E402
