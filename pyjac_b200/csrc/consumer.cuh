@@ -85,12 +85,20 @@ __device__ __forceinline__ void sts64(unsigned a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
-// x = (I - gamma J)^-1 r, one warp per state.  Shared memory per warp: the matrix column-major with
-// leading dimension ldm (odd), the right-hand side, WA / WB of the state.  A lane owns the rows
-// lane, lane + 32, ... (R = ceil(nsp / 32) of them): their multipliers stay in registers through the
-// trailing update, which walks the columns with one broadcast load of the pivot row's element and one
-// load / fma / store per owned row.  gamma: one value for all states (gamma_s == nullptr) or one per
-// state.  info[s] = 0, or c + 1 when column c had no usable pivot (the state's x is then not written).
+// x = (I - gamma J)^-1 r, one warp per state.  Shared memory per warp: the matrix column-major with leading
+// dimension ldm (odd), three vectors of NSP doubles (WA, then the pivot rows as ints; WB, then the pivot
+// reciprocals; the solution).  A lane owns the rows lane, lane + 32, ... (R = ceil(nsp / 32) of them).
+//
+// Left-looking LU with implicit partial pivoting: column j is loaded into registers, updated with every earlier
+// column c < j (one broadcast of its element in pivot row c by shuffle, one shared-memory load and one fma per
+// owned row that was not a pivot row yet), then its pivot is chosen among the rows not used so far, the rows below
+// are scaled and the column is stored once.  Compared with a right-looking update this reads each L element once
+// per later column but stores each element once instead of once per pivot, and no rows are ever swapped (a row's
+// pivot step is kept in a register).  The right-hand side goes through the same update as one more column;
+// the back substitution walks the columns from the last with the solution component broadcast by shuffle.
+// The arithmetic (order of the fmas of an element, pivot choice) is that of the textbook right-looking form.
+// gamma: one value for all states (gamma_s == nullptr) or one per state.  info[s] = 0, or c + 1 when column c had
+// no usable pivot (the state's x is then not written).
 template <int R>
 __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, const double* __restrict__ gamma_s,
                                                 const double* __restrict__ r, long long r_ss, long long r_sv,
@@ -102,11 +110,21 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
     const int nsp = f.nsp, last = nsp - 1;
     const long long nf = (long long)nsp + 3 * last + f.nnz;
     double* M = sm + (size_t)warp * ((size_t)ldm * nsp + 3 * (size_t)nsp);
-    double* b = M + (size_t)ldm * nsp;
-    double* wa = b + nsp;
+    double* wa = M + (size_t)ldm * nsp;
     double* wb = wa + nsp;
-    const unsigned aM = (unsigned)__cvta_generic_to_shared(M), aB = (unsigned)__cvta_generic_to_shared(b);
-    const unsigned cstep = (unsigned)ldm * 8u;                  // bytes between columns
+    double* xs = wb + nsp;
+    const unsigned aM = (unsigned)__cvta_generic_to_shared(M);
+    const unsigned aPV = (unsigned)__cvta_generic_to_shared(wa);      // pivot row of step c (int), reuses WA after the expansion
+    const unsigned aIP = (unsigned)__cvta_generic_to_shared(wb);      // 1 / pivot of step c, reuses WB
+    const unsigned aX = (unsigned)__cvta_generic_to_shared(xs);
+    const unsigned cstep = (unsigned)ldm * 8u;                        // bytes between columns
+    const unsigned arow = 8u * (unsigned)lane;                        // byte offset of the lane's first row in a column
+    auto pick = [&](const double (&v)[R], int q) {                    // v[q], q warp-uniform
+        double o = v[0];
+#pragma unroll
+        for (int t = 1; t < R; ++t) o = q == t ? v[t] : o;
+        return o;
+    };
     for (long long s = (long long)blockIdx.x * wpb + warp; s < n; s += (long long)gridDim.x * wpb) {
         const double g = gamma_s ? gamma_s[s] : gamma;
         // ---- expand -gamma J (+ I) into shared memory
@@ -115,10 +133,7 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
             wb[k] = fac_at(f, nf, s, nsp + 2 * last + k);
             M[k + 1] = -g * fac_at(f, nf, s, nsp + k);                       // column 0: temperature column
         }
-        for (int j = lane; j < nsp; j += 32) {
-            M[(size_t)j * ldm] = -g * fac_at(f, nf, s, j);                   // row 0: energy-equation row
-            b[j] = r[s * r_ss + (long long)j * r_sv];
-        }
+        for (int j = lane; j < nsp; j += 32) M[(size_t)j * ldm] = -g * fac_at(f, nf, s, j);   // row 0: energy-equation row
         __syncwarp();
         {
             double was[R], wbs[R];
@@ -128,7 +143,7 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
                 was[q] = k < last ? -g * wa[k] : 0.0;
                 wbs[q] = k < last ? -g * wb[k] : 0.0;
             }
-            unsigned ac = aM + cstep + 8u * (unsigned)(lane + 1);
+            unsigned ac = aM + cstep + arow + 8u;
             for (int j = 1; j < nsp; ++j, ac += cstep) {
                 const double2 c = __ldg(f.colfac + j);
 #pragma unroll
@@ -145,95 +160,112 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
         __syncwarp();
         for (int j = lane; j < nsp; j += 32) M[(size_t)j * ldm + j] += 1.0;
         __syncwarp();
-        // ---- LU with partial pivoting (right-looking), the right-hand side carried along
+        // ---- factorisation, column by column; ps[q]: the step at which the lane's q-th row became a pivot row
+        // (nsp: not yet; -1: the row does not exist)
+        int ps[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) ps[q] = lane + 32 * q < nsp ? nsp : -1;
         int bad = 0;
-        for (int c = 0; c < nsp; ++c) {
-            const unsigned acol = aM + (unsigned)c * cstep;
-            double best = -1.0;
-            int arg = c;
+        // Panels of NB columns: the updates with the columns of earlier panels (phase 1) run on NB independent
+        // shuffle / fma chains that share the loads of the L columns; inside a panel (phase 2) the multipliers are
+        // still in registers.  Column index nsp is the right-hand side, taken through the same updates.
+        constexpr int NB = R <= 2 ? 8 : 4;
+        const int* pvr = reinterpret_cast<const int*>(wa);
+        for (int j0 = 0; j0 <= nsp && !bad; j0 += NB) {
+            double a[NB][R];
+            int pr[NB];                                                      // pivot rows chosen inside this panel
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int i = lane + 32 * q;
-                if (i >= c && i < nsp) {
-                    const double a = fabs(lds64(acol + 8u * i));
-                    if (a > best) { best = a; arg = i; }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-            }
-            if (!(best > 0.0) || !isfinite(best)) { bad = c + 1; break; }
-            if (arg != c) {
-                for (int j = lane; j < nsp; j += 32) {
-                    const unsigned q = aM + (unsigned)j * cstep;
-                    const double t0 = lds64(q + 8u * c), t1 = lds64(q + 8u * arg);
-                    sts64(q + 8u * c, t1); sts64(q + 8u * arg, t0);
-                }
-                if (lane == 0) { const double t0 = lds64(aB + 8u * c), t1 = lds64(aB + 8u * arg); sts64(aB + 8u * c, t1); sts64(aB + 8u * arg, t0); }
-            }
-            __syncwarp();
-            const double ip = 1.0 / lds64(acol + 8u * c);
-            const double bc = lds64(aB + 8u * c);
-            __syncwarp();
-            // multipliers of the owned rows below the pivot (0 for the others: their updates are no-ops
-            // that are skipped by predicate), forward substitution on the fly
-            double l[R];
-            bool on[R];
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int i = lane + 32 * q;
-                on[q] = i > c && i < nsp;
-                l[q] = 0.0;
-                if (on[q]) {
-                    l[q] = lds64(acol + 8u * i) * ip;
-                    sts64(acol + 8u * i, l[q]);
-                    sts64(aB + 8u * i, fma(-l[q], bc, lds64(aB + 8u * i)));
-                }
-            }
-            // trailing update: column j -= l * M[c][j]
-            unsigned aj = acol + cstep;
-            int j = c + 1;
-            for (; j + 4 <= nsp; j += 4, aj += 4 * cstep) {
-                const double u0 = lds64(aj + 8u * c), u1 = lds64(aj + cstep + 8u * c);
-                const double u2 = lds64(aj + 2 * cstep + 8u * c), u3 = lds64(aj + 3 * cstep + 8u * c);
+            for (int t = 0; t < NB; ++t) {
+                const int col = j0 + t;
+                pr[t] = 0;
 #pragma unroll
                 for (int q = 0; q < R; ++q) {
-                    if (!on[q]) continue;
-                    const unsigned ai = aj + 8u * (unsigned)(lane + 32 * q);
-                    const double a0 = lds64(ai), a1 = lds64(ai + cstep), a2 = lds64(ai + 2 * cstep), a3 = lds64(ai + 3 * cstep);
-                    sts64(ai, fma(-l[q], u0, a0)); sts64(ai + cstep, fma(-l[q], u1, a1));
-                    sts64(ai + 2 * cstep, fma(-l[q], u2, a2)); sts64(ai + 3 * cstep, fma(-l[q], u3, a3));
+                    a[t][q] = 0.0;
+                    if (ps[q] >= 0 && col < nsp) a[t][q] = lds64(aM + (unsigned)col * cstep + arow + 256u * q);
+                    if (ps[q] >= 0 && col == nsp) a[t][q] = r[s * r_ss + (long long)(lane + 32 * q) * r_sv];
                 }
             }
-            for (; j < nsp; ++j, aj += cstep) {
-                const double u = lds64(aj + 8u * c);
+            // phase 1: plain loads (nothing is stored inside this loop, so the compiler may unroll it and hoist the
+            // loads of the pivot rows and of the L columns ahead of the chains)
+            const double* lcol = M + lane;
+            const int cend = j0 < nsp ? j0 : nsp;
+#pragma unroll 2
+            for (int c = 0; c < cend; ++c, lcol += ldm) {
+                const int pc = pvr[c];
+                double u[NB];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) u[t] = __shfl_sync(0xffffffffu, pick(a[t], pc >> 5), pc & 31);
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (ps[q] > c) {
+                        const double l = lcol[32 * q];
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) a[t][q] = fma(-l, u[t], a[t][q]);
+                    }
+            }
+            // phase 2: column by column inside the panel
+#pragma unroll
+            for (int t = 0; t < NB; ++t) {
+                const int col = j0 + t;
+                if (col <= nsp && !bad) {                                    // (no break: the loop must unroll so that a[][] stays in registers)
+#pragma unroll
+                for (int t2 = 0; t2 < t; ++t2) {
+                    const int c = j0 + t2;
+                    const double u = __shfl_sync(0xffffffffu, pick(a[t], pr[t2] >> 5), pr[t2] & 31);
+#pragma unroll
+                    for (int q = 0; q < R; ++q)
+                        if (ps[q] > c) a[t][q] = fma(-a[t2][q], u, a[t][q]);
+                }
+                if (col == nsp) {
+                    // back substitution: y sits in a[t][] by row; component c of the solution is y[pivot row c] / pivot c
+                    for (int c = nsp - 1; c >= 0; --c) {
+                        const int pc = pvr[c];
+                        const double xc = __shfl_sync(0xffffffffu, pick(a[t], pc >> 5), pc & 31) * lds64(aIP + 8u * c);
+                        if (lane == 0) sts64(aX + 8u * c, xc);
+                        const unsigned ac = aM + (unsigned)c * cstep + arow;
+#pragma unroll
+                        for (int q = 0; q < R; ++q)
+                            if (ps[q] >= 0 && ps[q] < c) a[t][q] = fma(-lds64(ac + 256u * q), xc, a[t][q]);     // U[ps][c] x_c
+                    }
+                } else {
+                // pivot of this column among the rows not used so far
+                double best = -1.0;
+                int arg = 0x7fffffff;
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (ps[q] == nsp) {
+                        const double v = fabs(a[t][q]);
+                        if (v > best) { best = v; arg = lane + 32 * q; }
+                    }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+                }
+                if (!(best > 0.0) || !isfinite(best)) bad = col + 1;
+                else {
+                const double ip = 1.0 / __shfl_sync(0xffffffffu, pick(a[t], arg >> 5), arg & 31);
+                pr[t] = arg;
 #pragma unroll
                 for (int q = 0; q < R; ++q) {
-                    if (!on[q]) continue;
-                    const unsigned ai = aj + 8u * (unsigned)(lane + 32 * q);
-                    sts64(ai, fma(-l[q], u, lds64(ai)));
+                    if (lane + 32 * q == arg) ps[q] = col;
+                    else if (ps[q] == nsp) a[t][q] *= ip;                     // multipliers of the rows still to be eliminated
+                    if (ps[q] >= 0) sts64(aM + (unsigned)col * cstep + arow + 256u * q, a[t][q]);
+                }
+                if (lane == 0) {
+                    asm volatile("st.shared.s32 [%0], %1;" ::"r"(aPV + 4u * col), "r"(arg) : "memory");
+                    sts64(aIP + 8u * col, ip);
+                }
+                }
+                }
                 }
             }
             __syncwarp();
         }
         if (!bad) {
-            // ---- back substitution, column oriented
-            for (int c = nsp - 1; c >= 0; --c) {
-                const unsigned acol = aM + (unsigned)c * cstep;
-                const double xc = lds64(aB + 8u * c) / lds64(acol + 8u * c);
-                __syncwarp();
-                if (lane == 0) sts64(aB + 8u * c, xc);
-#pragma unroll
-                for (int q = 0; q < R; ++q) {
-                    const int i = lane + 32 * q;
-                    if (i < c) sts64(aB + 8u * i, fma(-lds64(acol + 8u * i), xc, lds64(aB + 8u * i)));
-                }
-                __syncwarp();
-            }
-            for (int j = lane; j < nsp; j += 32) x[s * x_ss + (long long)j * x_sv] = b[j];
+            __syncwarp();
+            for (int j = lane; j < nsp; j += 32) x[s * x_ss + (long long)j * x_sv] = xs[j];
         }
         if (info && lane == 0) info[s] = bad;
         __syncwarp();
