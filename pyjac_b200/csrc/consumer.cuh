@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(256) k_newton(Fac f, int n, double gamma, cons
                         if (ps[q] > c) a[t][q] = fma(-a[t2][q], u, a[t][q]);
                 }
                 if (col == nsp) {
-                    // back substitution: y sits in a[t][] by row; component c of the solution is y[pivot row c] / pivot c
+                    // back substitution: y sits in a[t][] by row; component c of the solution is y[pivot row c] / pivot c.
+                    // The last columns, their pivot rows and reciprocals may have been stored in this very panel.
+                    __syncwarp();
                     for (int c = nsp - 1; c >= 0; --c) {
                         const int pc = pvr[c];
                         const double xc = __shfl_sync(0xffffffffu, pick(a[t], pc >> 5), pc & 31) * lds64(aIP + 8u * c);
