@@ -11,7 +11,8 @@ Per state ``NF = NSP + 3 (NSP - 1) + NNZ`` doubles::
     J[i, j] = ca[j] WA_{i-1} + cb[j] WB_{i-1} + S(i, j)       i, j >= 1
 
 The reference only has the dense form (its ``sparse_multiplier`` emitter, create_jacobian.py:3301-3404, is
-broken at :3322); these helpers expand records for callers that want it and for the parity tests.
+broken at :3322); these helpers describe the record and convert it to the dense layout for callers that want the reference's format
+(a format conversion of results the GPU computed -- there is no CPU evaluation of anything in this package).
 """
 import numpy as np
 
@@ -39,16 +40,3 @@ def expand(fac, nsp, rows, cols, ca, cb):
     J[:, 1:, 1:] = ca[None, 1:, None] * wa[:, None, :] + cb[None, 1:, None] * wb[:, None, :]
     J[:, cols, rows] += fac[:, nsp + 3 * last:]
     return J.reshape(n, nsp * nsp)
-
-
-def jvp(fac, v, nsp, rows, cols, ca, cb):
-    """J v per state from the records without forming J (numpy statement of csrc/consumer.cuh k_jvp)."""
-    fac, v = np.asarray(fac), np.asarray(v)
-    last = nsp - 1
-    out = np.empty_like(v)
-    out[:, 0] = (fac[:, :nsp] * v).sum(axis=1)
-    sa, sb = (ca[None, 1:] * v[:, 1:]).sum(axis=1), (cb[None, 1:] * v[:, 1:]).sum(axis=1)
-    out[:, 1:] = fac[:, nsp:nsp + last] * v[:, :1] + fac[:, nsp + last:nsp + 2 * last] * sa[:, None] \
-        + fac[:, nsp + 2 * last:nsp + 3 * last] * sb[:, None]
-    np.add.at(out, (slice(None), rows), fac[:, nsp + 3 * last:] * v[:, cols])
-    return out

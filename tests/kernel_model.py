@@ -697,3 +697,17 @@ def _assemble6(v):
     dydt[:, 1:] = wdot[:, :last] * w[None, :last] / rho[:, None]
     return dict(conc=v['conc'][:, :nsp], fwd=v['fwd'], rev=v['rev'][:, :v['nrev']], pres_mod=v['pres_mod'][:, :v['npd']],
                 spec_rates=wdot, dydt=dydt, jac=jac)
+
+
+def factored_jvp(fac, v, nsp, rows, cols, ca, cb):
+    """J v per state from the factored records without forming J (numpy statement of csrc/consumer.cuh k_jvp; test
+    reference only)."""
+    fac, v = np.asarray(fac), np.asarray(v)
+    last = nsp - 1
+    out = np.empty_like(v)
+    out[:, 0] = (fac[:, :nsp] * v).sum(axis=1)
+    sa, sb = (ca[None, 1:] * v[:, 1:]).sum(axis=1), (cb[None, 1:] * v[:, 1:]).sum(axis=1)
+    out[:, 1:] = fac[:, nsp:nsp + last] * v[:, :1] + fac[:, nsp + last:nsp + 2 * last] * sa[:, None] \
+        + fac[:, nsp + 2 * last:nsp + 3 * last] * sb[:, None]
+    np.add.at(out, (slice(None), rows), fac[:, nsp + 3 * last:] * v[:, cols])
+    return out

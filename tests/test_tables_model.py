@@ -109,7 +109,7 @@ def test_factored_record_expands_to_the_jacobian(golden_dir, mech_file, npz, sl)
     rng = np.random.default_rng(11)
     v = rng.standard_normal((dense.shape[0], nsp))
     ref = np.einsum('ncr,nc->nr', g['jac'].reshape(-1, nsp, nsp), v)          # golden J (column-major) times v
-    got = factored.jvp(out['fac'], v, nsp, rows, cols, ca, cb)
+    got = kernel_model.factored_jvp(out['fac'], v, nsp, rows, cols, ca, cb)
     # J v sums NSP products whose magnitudes differ by many decades: compare against the sum of magnitudes
     mag = np.einsum('ncr,nc->nr', np.abs(g['jac'].reshape(-1, nsp, nsp)), np.abs(v))
     assert (np.abs(got - ref) <= 1e-9 * mag + 1e-300).all()
