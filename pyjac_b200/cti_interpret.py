@@ -85,7 +85,9 @@ def _pressure(val) -> float:
     return float(val)
 
 
-def _efficiencies(text: str) -> Dict[str, float]:
+def _efficiencies(text) -> Dict[str, float]:
+    if isinstance(text, dict):
+        return {str(k): float(v) for k, v in text.items()}
     out = {}
     for tok in text.split():
         name, _, val = tok.rpartition(':')
@@ -163,8 +165,14 @@ def read_mech_cti(filename: str) -> Tuple[List[str], List[Species], List[Reactio
         raise
     except Exception as exc:
         raise MechanismError('cannot read %s: %s' % (filename, exc))
+    return _convert(filename, phases, species_decl, reactions_decl)
+
+
+def _convert(filename, phases, species_decl, reactions_decl):
+    """The collected declarations (of a .cti script or of a YAML document, :mod:`pyjac_b200.yaml_interpret`) ->
+    (elements, species, reactions) in pyJac's records and units."""
     if not phases:
-        raise MechanismError('no ideal_gas(...) phase in %s' % filename)
+        raise MechanismError('no ideal-gas phase in %s' % filename)
     ph = phases[0]
     names = ph['species'].replace(',', ' ').split() if isinstance(ph['species'], str) else list(ph['species'])
     if names == ['all']:
@@ -177,7 +185,9 @@ def read_mech_cti(filename: str) -> Tuple[List[str], List[Species], List[Reactio
             raise MechanismError('species %s is not declared' % nm)
         d = species_decl[nm]
         sp = Species(nm)
-        for tok in d['atoms'].replace(',', ' ').split():
+        atoms = d['atoms']
+        toks = ['%s:%s' % kv for kv in atoms.items()] if isinstance(atoms, dict) else atoms.replace(',', ' ').split()
+        for tok in toks:
             el, _, cnt = tok.partition(':')
             sp.elem.append((el, int(float(cnt))))
             if el.lower() not in ELEM_WT:

@@ -69,13 +69,24 @@ class Mechanism:
         return cls.finalize(elems, specs, reacs, last_spec)
 
     @classmethod
+    def from_yaml(cls, mech_name: str, last_spec: Optional[str] = None) -> 'Mechanism':
+        """A Cantera YAML file, read without Cantera (:mod:`pyjac_b200.yaml_interpret`)."""
+        from . import yaml_interpret
+        elems, specs, reacs = yaml_interpret.read_mech_yaml(mech_name)
+        if not specs or not reacs:
+            raise mech_interpret.MechanismError('no species / reactions found in %s' % mech_name)
+        return cls.finalize(elems, specs, reacs, last_spec)
+
+    @classmethod
     def from_file(cls, mech_name: str, therm_name: Optional[str] = None, last_spec: Optional[str] = None) -> 'Mechanism':
-        """By extension, as the reference's create_jacobian does (create_jacobian.py:3476-3489): ``.cti`` ->
-        the Cantera-format reader, anything else -> Chemkin."""
+        """By extension, as the reference's create_jacobian does (create_jacobian.py:3476-3489): ``.cti`` / ``.yaml`` ->
+        the Cantera-format readers, anything else -> Chemkin."""
         if mech_name.lower().endswith('.cti'):
             return cls.from_cti(mech_name, last_spec)
-        if mech_name.lower().endswith(('.xml', '.yaml', '.yml')):
-            raise mech_interpret.MechanismError('only Chemkin and .cti mechanism files are read (no Cantera here)')
+        if mech_name.lower().endswith(('.yaml', '.yml')):
+            return cls.from_yaml(mech_name, last_spec)
+        if mech_name.lower().endswith('.xml'):
+            raise mech_interpret.MechanismError('Cantera .xml (ctml) files are not read: convert to .cti or .yaml')
         return cls.from_chemkin(mech_name, therm_name, last_spec)
 
     @classmethod

@@ -147,3 +147,40 @@ def test_negative_pre_exponential(golden_dir):
     assert sum(1 for rx in m.reacs if rx.A < 0) == 8          # 7 written + the split REV half
     T = tables.build(m, 8, 256, False)
     assert int(((np.asarray(T['rx_flags']) & tables.F_NEGA) != 0).sum()) == 8
+
+
+def test_yaml_reader_matches_chemkin_twin(golden_dir):
+    """tests/golden/mini.yaml states the mini mechanism in Cantera's YAML layout (mol-cm-s, activation temperatures):
+    the Cantera-free reader must hand the tables the same numbers as the Chemkin text and the .cti file."""
+    a = Mechanism.from_file(os.path.join(golden_dir, 'mini.yaml'))
+    b = Mechanism.from_file(os.path.join(golden_dir, 'mini.inp'))
+    c = Mechanism.from_file(os.path.join(golden_dir, 'mini.cti'))
+    _same_mechanism(a, b)
+    _same_mechanism(a, c)
+    from pyjac_b200 import tables
+    Ta, Tb = tables.build(a, 8, 256, False), tables.build(b, 8, 256, False)
+    assert sorted(Ta) == sorted(Tb)
+    for k in Ta:
+        assert np.array_equal(np.asarray(Ta[k]), np.asarray(Tb[k])), k
+
+
+def test_yaml_reader_units_and_refusals(tmp_path, golden_dir):
+    from pyjac_b200.mech_interpret import MechanismError
+    txt = open(os.path.join(golden_dir, 'mini.yaml')).read()
+    # the same file in kcal/mol with one energy written with its own unit, and a three-body type left to inference
+    alt = txt.replace('activation-energy: K', 'activation-energy: kcal/mol')
+    alt = alt.replace('Ea: 3150.14}', 'Ea: 3150.14 K}').replace('  type: three-body\n', '')
+    p = tmp_path / 'alt.yaml'
+    p.write_text(alt)
+    a = Mechanism.from_file(str(p))
+    b = Mechanism.from_file(os.path.join(golden_dir, 'mini.inp'))
+    assert a.reacs[0].E == b.reacs[0].E and a.reacs[1].thd_body and a.reacs[1].A == b.reacs[1].A
+    assert abs(a.reacs[10].E - b.reacs[10].E * 4184.0 / 8.3144621) <= 1e-9 * abs(a.reacs[10].E)
+    for bad, what in ((txt.replace('model: NASA7', 'model: Shomate', 1), 'NASA7'),
+                      (txt.replace('  duplicate: true\n', '  duplicate: true\n  orders: {HO2: 1.5}\n', 1), 'orders'),
+                      (txt.replace('thermo: ideal-gas', 'thermo: Redlich-Kwong'), 'ideal-gas'),
+                      (txt.replace('time: s', 'time: ms'), 'time')):
+        q = tmp_path / 'bad.yaml'
+        q.write_text(bad)
+        with pytest.raises(MechanismError, match=what):
+            Mechanism.from_file(str(q))
