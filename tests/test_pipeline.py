@@ -165,3 +165,42 @@ def test_plan_choice_by_mechanism_size(golden_dir, tmp_path):
     assert (int(cfg[0]), int(cfg[14])) == (8, 1)
     with pytest.raises(tables.UnsupportedMechanism):
         tables.build(Mechanism.from_chemkin(nc7), ws_global=False)
+
+
+def _build_in_child(build_dir, counter, q):
+    """Child of test_library_build_is_safe_under_concurrent_ranks: libgen redirected to a scratch directory and a
+    fake compiler that takes a while and counts its runs."""
+    import stat
+    from pyjac_b200 import libgen
+    fake = os.path.join(build_dir, 'fake_nvcc.sh')
+    if not os.path.exists(fake):
+        with open(fake + '.tmp%d' % os.getpid(), 'w') as fh:
+            fh.write('#!/bin/bash\nout=""\nwhile [ $# -gt 0 ]; do if [ "$1" = "-o" ]; then out="$2"; fi; shift; done\n'
+                     'echo run >> %s\nsleep 0.5\nprintf "x%%.0s" $(seq 1 200000) > "$out"\n' % counter)
+        os.chmod(fake + '.tmp%d' % os.getpid(), stat.S_IRWXU)
+        os.replace(fake + '.tmp%d' % os.getpid(), fake)
+    libgen.BUILD = build_dir
+    libgen.LIB_PATH = os.path.join(build_dir, libgen.LIB_NAME)
+    libgen._nvcc = lambda: fake
+    path = libgen.build_library()
+    q.put(os.path.getsize(path))
+
+
+def test_library_build_is_safe_under_concurrent_ranks(tmp_path):
+    """One process per GPU may find the in-tree library stale at the same moment (torchrun): the build must run once,
+    under a lock, and nobody may see a half-written file (this corrupted an 8-rank bench run once)."""
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    build_dir, counter = str(tmp_path / 'b'), str(tmp_path / 'runs')
+    os.makedirs(build_dir)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_build_in_child, args=(build_dir, counter, q)) for _ in range(4)]
+    for p in procs:
+        p.start()
+    sizes = [q.get(timeout=60) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert sizes == [200000] * 4                                   # everybody loaded the complete file
+    assert open(counter).read().count('run') == 1                 # ... which was built once
+    assert not [f for f in os.listdir(build_dir) if '.tmp' in f]
