@@ -76,7 +76,7 @@ def check_jac(new, ref, nsp, what='jac', mech=None, y=None):
 CASE_LIMITS = {
     'h2o2_n2.inp': (5.0e-11, 0.986), 'torture.inp': (2.0e-13, 0.971), 'gri30_syn.inp': (3.0e-13, 0.9995),
     'usc2_syn.inp': (6.0e-13, 0.9995), 'plog.inp': (3.0e-13, 0.9995), 'cheb.inp': (3.0e-13, 0.9995),
-    'nega.inp': (2.0e-11, 0.985),
+    'nega.inp': (2.0e-11, 0.985), 'mini.inp': (3.0e-13, 0.9995),
 }
 
 

@@ -18,6 +18,9 @@ evaluates the emitted C on fixed states and stores inputs and outputs:
     tests/golden/cheb_syn.npz      Chebyshev coverage mechanism over the H2/O2 species, 160 synthetic states of
                                    which 32 outside the fitted pressure ranges
 
+    tests/golden/mini_syn.npz      the mechanism that also exists as mini.cti / mini.yaml (third body, Troe, SRI, Lindemann with a
+                                   specific collider, chemically activated, PLOG, Chebyshev, duplicates), 96 synthetic states
+
     tests/golden/nc7_syn.npz       n-heptane-sized synthetic mechanism (654 sp / 2827 rxn; the file is synth.write('nc7', seed=0)),
                                    4 synthetic states; rates and dydt in full, of the Jacobian all rows of 96 columns and
                                    all columns of 32 rows (+ the per-column maxima the gate scales with)
@@ -84,6 +87,14 @@ if __name__ == '__main__':
         shutil.copy('/root/reference/data/h2_pasr_output.npy', pasr)
     only = set(sys.argv[1:])               # e.g. `make_golden.py conv` regenerates only the constant-volume vectors
 
+    if 'mini' in only:
+        mech = Mechanism.from_chemkin(os.path.join(HERE, 'mini.inp'))
+        P, y = synthetic_states(mech.NSP, 96, seed=8)
+        P = P.copy()
+        P[64:80] *= 0.01          # below / above the PLOG table and the Chebyshev pressure range
+        P[80:96] *= 20.0
+        dump('mini', os.path.join(HERE, 'mini.inp'), P, y, 'mini_syn.npz')
+        sys.exit(0)
     if 'nc7' in only:
         # 654 species / 2827 reactions: the generator emits 7.5 M lines of C (609 MB); built outside the repo with -O0
         # (no value-changing optimisation is enabled at -O3 -mtune=native either: the other fixtures are bit-identical

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz'), ('torture.inp', 'torture_pasr.npz'),
          ('gri30_syn.inp', 'gri30_syn.npz'), ('usc2_syn.inp', 'usc2_syn.npz'),
-         ('plog.inp', 'plog_syn.npz'), ('cheb.inp', 'cheb_syn.npz'), ('nega.inp', 'nega_pasr.npz')]
+         ('plog.inp', 'plog_syn.npz'), ('cheb.inp', 'cheb_syn.npz'), ('nega.inp', 'nega_pasr.npz'),
+         ('mini.inp', 'mini_syn.npz')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 
@@ -507,22 +508,19 @@ def test_edge_states_vs_oracle(torch, golden_dir):
     ev.close()
 
 
-def test_cti_mechanism_on_the_gpu_vs_oracle_of_its_chemkin_twin(torch, golden_dir):
-    """A mechanism read from a Cantera .cti file (no Cantera) runs through the kernel and matches the oracle built from
-    the Chemkin statement of the same mechanism (every reaction class: third body, Troe, SRI, chemically activated,
-    PLOG, Chebyshev, duplicates)."""
-    from oracle.oracle import Oracle
+@pytest.mark.parametrize('mech_file', ['mini.cti', 'mini.yaml'])
+def test_cantera_format_mechanism_on_the_gpu_vs_reference_golden(torch, golden_dir, mech_file):
+    """A mechanism read from a Cantera .cti / YAML file (no Cantera) runs through the kernel and matches what the
+    REFERENCE's generated C gives for the Chemkin statement of the same mechanism (tests/golden/mini_syn.npz: third
+    body, Troe, SRI, Lindemann with a specific collider, chemically activated, PLOG, Chebyshev, duplicates)."""
     from pyjac_b200.evaluator import Evaluator
-    mech = Mechanism.from_file(os.path.join(golden_dir, 'mini.cti'))
+    mech = Mechanism.from_file(os.path.join(golden_dir, mech_file))
     twin = Mechanism.from_file(os.path.join(golden_dir, 'mini.inp'))
+    g = dict(np.load(os.path.join(golden_dir, 'mini_syn.npz')))
     ev = Evaluator(mech)
-    P_h, y_h = synthetic_states(mech.NSP, 300, seed=31)
-    P, y = torch.tensor(P_h, device='cuda'), torch.tensor(y_h, device='cuda')
-    ora = Oracle(twin)
-    ref = dict(zip(KEYS, ora.rates(P_h, y_h)))
-    ref['dydt'] = ora.dydt(P_h, y_h)
+    P, y = torch.tensor(g['P'], device='cuda'), torch.tensor(g['y'], device='cuda')
     new = dict(zip(KEYS + ['dydt'], [o.cpu().numpy() for o in ev.rates(P, y, want_dy=True)]))
-    gates.check_rates(twin, P_h, y_h, new, ref, 'mini.cti')
-    worst, frac = gates.check_jac(ev.eval_jacob(P, y).cpu().numpy(), ora.eval_jacob(P_h, y_h), mech.NSP, 'mini.cti', twin, y_h)
-    assert frac > 0.999, frac
+    gates.check_rates(twin, g['P'], g['y'], new, g, mech_file)
+    worst, frac = gates.check_jac(ev.eval_jacob(P, y).cpu().numpy(), g['jac'], mech.NSP, mech_file, twin, g['y'])
+    gates.check_case('mini.inp', worst, frac)
     ev.close()

@@ -19,7 +19,8 @@ CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz', 'h2o2'),
          ('usc2_syn.inp', 'usc2_syn.npz', 'usc2'),
          ('plog.inp', 'plog_syn.npz', 'plog'),
          ('cheb.inp', 'cheb_syn.npz', 'cheb'),
-         ('nega.inp', 'nega_pasr.npz', 'nega')]
+         ('nega.inp', 'nega_pasr.npz', 'nega'),
+         ('mini.inp', 'mini_syn.npz', 'mini')]
 KEYS = ['conc', 'fwd', 'rev', 'pres_mod', 'spec_rates']
 
 

@@ -17,7 +17,8 @@ CASES = [('h2o2_n2.inp', 'h2o2_pasr.npz', slice(None, None, 5)),
          ('usc2_syn.inp', 'usc2_syn.npz', slice(None)),
          ('plog.inp', 'plog_syn.npz', slice(None)),
          ('cheb.inp', 'cheb_syn.npz', slice(None)),
-         ('nega.inp', 'nega_pasr.npz', slice(None))]
+         ('nega.inp', 'nega_pasr.npz', slice(None)),
+         ('mini.inp', 'mini_syn.npz', slice(None))]
 
 
 @pytest.mark.parametrize('mech_file,npz,sl', CASES)
