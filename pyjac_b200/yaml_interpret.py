@@ -121,9 +121,15 @@ def read_mech_yaml(filename: str) -> Tuple[List[str], List[Species], List[Reacti
             d.update(kind='plog', rates=rows)
         elif kind == 'Chebyshev':
             tr, pr = rx['temperature-range'], rx['pressure-range']
-            d.update(kind='cheb', Tmin=float(_quantity(tr[0]) if not isinstance(_quantity(tr[0]), tuple) else _quantity(tr[0])[0]),
-                     Tmax=float(_quantity(tr[1]) if not isinstance(_quantity(tr[1]), tuple) else _quantity(tr[1])[0]),
-                     Pmin=_quantity(pr[0]), Pmax=_quantity(pr[1]), coeffs=rx['data'])
+            def kelvin(v):
+                q = _quantity(v)
+                if isinstance(q, tuple):
+                    if q[1] != 'K':
+                        raise MechanismError('reaction %d (%s): temperature range in %s' % (i, eq, q[1]))
+                    return float(q[0])
+                return float(q)
+            d.update(kind='cheb', Tmin=kelvin(tr[0]), Tmax=kelvin(tr[1]), Pmin=_quantity(pr[0]), Pmax=_quantity(pr[1]),
+                     coeffs=rx['data'])
         else:
             raise MechanismError('reaction %d (%s): unsupported type %s' % (i, eq, kind))
         reactions_decl.append(d)
