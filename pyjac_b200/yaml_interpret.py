@@ -12,9 +12,9 @@ Read: the top-level ``units`` mapping (length, quantity, activation-energy; time
 refused), ``species`` with ``composition`` and two-range ``NASA7`` thermo, and ``reactions`` of type elementary
 (default), ``three-body`` (also inferred from ``+ M`` in the equation, as Cantera 3 does), ``falloff`` and
 ``chemically-activated`` (``Troe`` / ``SRI`` / Lindemann), ``pressure-dependent-Arrhenius`` and ``Chebyshev``, with
-``efficiencies``, ``duplicate`` and quantities written with a unit (``1 atm``, ``10 kcal/mol``).  Refused, loudly:
-``default-efficiency`` other than 1, explicit reaction ``orders``, ``negative-A`` needs no flag here (A < 0 is
-accepted), other thermo models and reaction types.
+``efficiencies``, ``duplicate`` and quantities written with a unit (``1 atm``, ``10 kcal/mol``); ``negative-A`` is
+not needed (A < 0 is accepted as it stands).  Refused, loudly: ``default-efficiency`` other than 1, explicit reaction
+``orders``, other thermo models and reaction types.
 """
 from __future__ import annotations
 
